@@ -1,0 +1,318 @@
+#!/usr/bin/env python3
+"""Generate the golden fixtures under tests/golden/ from the UNMODIFIED reference.
+
+TEST INFRASTRUCTURE ONLY.  Runs in the build container (needs /root/reference and the
+oracle binaries built by `make -C oracle/ref_build`); the fixtures it writes are committed,
+so nothing on the GPU box ever reads /root/reference.
+
+Every number in the fixtures is produced by the reference's own code path
+(oracle/_ref/ref_harness calls sys->CalculateWavefunction / CalculateExpectationValues /
+CalculateWFQuotient / DoMetropolisStep / VectorDisplacementNIC of mathiasgartner/TDVMC);
+this script only chooses the inputs and re-packs the text dumps as .npz.
+
+    python oracle/gen_golden.py            # regenerate everything
+"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get("TDVMC_REFERENCE", "/root/reference")
+HARNESS = os.path.join(HERE, "_ref", "ref_harness")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def smooth_params(P, rmax, a_r=-0.5, w_r=0.8, a_i=0.05, c_i=1.5, w_i=0.5):
+    """Fixed smooth parameter profile: a short-range repulsive real part
+    and a small imaginary bump so that kinetic and imaginary estimators are non-trivial."""
+    h = rmax / (P - 1)
+    k = np.arange(P)
+    uR = a_r * np.exp(-((k * h / w_r) ** 2))
+    uI = a_i * np.exp(-(((k * h - c_i) / w_i) ** 2))
+    return uR, uI
+
+
+def write_case(path, system, scal, arrays, moves=()):
+    with open(path, "w") as f:
+        f.write(f"system {system}\n")
+        f.write(f"configdir {REF}/config/\n")
+        for k, v in scal.items():
+            f.write(f"{k} {v!r}\n")
+        for k, v in arrays.items():
+            f.write(k + " " + " ".join(repr(float(x)) for x in np.asarray(v).ravel()) + "\n")
+        for m in moves:
+            f.write("move " + " ".join(repr(float(x)) for x in m) + "\n")
+
+
+def parse_dump(path):
+    out = {}
+    with open(path) as f:
+        lines = f.read().split("\n")
+    i = 0
+    while i + 1 < len(lines):
+        head = lines[i].split()
+        if not head:
+            i += 1
+            continue
+        name, nd = head[0], int(head[1])
+        shape = tuple(int(x) for x in head[2:2 + nd])
+        vals = np.array(lines[i + 1].split(), dtype=np.float64)
+        out[name] = vals.reshape(shape) if nd else vals.reshape(())
+        i += 2
+    return out
+
+
+def run(mode, case_path, out_path=None):
+    cmd = [HARNESS, mode, case_path] + ([out_path] if out_path else [])
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=tempfile.gettempdir())
+    if r.returncode != 0:
+        raise RuntimeError(f"{cmd} failed: {r.stderr}\n{r.stdout}")
+    return r.stdout
+
+
+def read_csv_positions(name):
+    with open(os.path.join(REF, "config", name)) as f:
+        last = [l for l in f.read().split("\n") if l.strip()][-1]
+    return np.array([float(x) for x in last.split(",") if x.strip()])
+
+
+def jittered_lattice(N, L, seed):
+    """Cubic lattice + uniform jitter, the shape of the reference's start-up lattice
+    (src/TDVMC.cpp:727-739); exact values do not matter, they are inputs."""
+    m = int(round(N ** (1.0 / 3.0)))
+    assert m ** 3 == N
+    l = L / m
+    rng = np.random.default_rng(seed)
+    g = (np.arange(m) + 0.5) * l - L / 2
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    R = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+    return R + rng.uniform(-0.05, 0.05, R.shape) * l
+
+
+def contract_drift(d, uR, uI, system):
+    """Drift F_n = grad_n ln(psi) from the REFERENCE's sD table (generator-side, long double)."""
+    sD = d["sD"].astype(np.longdouble)   # [K][N][D]
+    K = sD.shape[0]
+    P = len(uR)
+    ut_r = np.zeros(K, np.longdouble)
+    ut_i = np.zeros(K, np.longdouble)
+    rows = bc_rows(d, system, P, K)
+    for p, row in enumerate(rows):
+        for k, fac in row:
+            ut_r[k] += np.longdouble(uR[p]) * np.longdouble(fac)
+            ut_i[k] += np.longdouble(uI[p]) * np.longdouble(fac)
+    FR = np.einsum("k,kna->na", ut_r, sD).astype(np.float64)
+    FI = np.einsum("k,kna->na", ut_i, sD).astype(np.float64)
+    return FR, FI
+
+
+def bc_rows(d, system, P, K):
+    """Sparse rows of the boundary-condition map O_p = sum_k M[p][k] ss[k] as the reference applies it
+    (BosonsBulk.cpp:158-177 with the dumped bcFactors; NUBosonsBulkPB.cpp:219-232)."""
+    rows = []
+    if system == "BosonsBulk":
+        bs, be = d["bc_start"], d["bc_end"]
+        np1 = bs.shape[0]
+        np2 = P - be.shape[0]
+        for i in range(np1):
+            rows.append([(j, bs[i][j]) for j in range(3)])
+        for i in range(np1, np2):
+            rows.append([(3 + (i - np1), 1.0)])
+        for i in range(be.shape[0]):
+            rows.append([(K - 3 + j, be[i][j]) for j in range(3)])
+    elif system == "NUBosonsBulkPB":
+        for i in range(P):
+            rows.append([(i + 1, 1.0)])
+        rows[1].append((0, 1.0))
+        rows[P - 1].append((K - 2, 1.0))
+        rows[P - 1].append((K - 1, 1.0))
+    else:
+        raise ValueError(system)
+    return rows
+
+
+def pack_eval(name, system, scal, arrays, moves, keep_tables="full", subset=(0, 1, 2, 3)):
+    with tempfile.TemporaryDirectory() as td:
+        cp, op = os.path.join(td, "case.txt"), os.path.join(td, "out.txt")
+        write_case(cp, system, scal, arrays, moves)
+        run("eval", cp, op)
+        d = parse_dump(op)
+    out = {
+        "system": np.array(system),
+        "N": np.array(scal["N"]), "DIM": np.array(3), "LBOX": np.array(scal["LBOX"]),
+        "N_PARAM": np.array(scal["N_PARAM"]),
+        "SYSTEM_PARAMS": np.asarray(arrays["SYSTEM_PARAMS"], np.float64),
+        "time": np.array(scal.get("time", 0.0)),
+        "R": np.asarray(arrays["R"], np.float64).reshape(-1, 3),
+        "uR": np.asarray(arrays["uR"], np.float64), "uI": np.asarray(arrays["uI"], np.float64),
+        "phiR": np.array(scal.get("phiR", 0.0)), "phiI": np.array(scal.get("phiI", 0.0)),
+        "moves": np.asarray(moves, np.float64).reshape(-1, 4),
+    }
+    if "NURBS_GRID" in arrays:
+        out["NURBS_GRID"] = np.asarray(arrays["NURBS_GRID"], np.float64)
+    for k in ("exponent", "exponent_wf", "wf", "local_energy_r", "local_energy_i", "local_operators",
+              "local_operator_energy_r", "local_operator_energy_i", "other_expectation_values",
+              "local_operators_matrix_diag", "local_operators_matrix_row3", "knots", "spline_weights",
+              "spline_sums", "outer_sum", "max_distance", "other_local_operators", "move_quotient",
+              "move_exponent_new", "bc_start", "bc_end"):
+        if k in d:
+            out[k] = d[k]
+    FR, FI = contract_drift(d, out["uR"], out["uI"], system)
+    out["drift_r"], out["drift_i"] = FR, FI
+    sD, sD2 = d["sD"], d["sD2"]
+    # particle-weighted checksums of the full tables (plain sums cancel pairwise by antisymmetry)
+    wn = 1.0 + 0.5 * np.sin(np.arange(sD.shape[1]))
+    out["table_checksum_weights"] = wn
+    out["sD_checksum"] = np.einsum("n,kna->ka", wn, sD)   # [K][D]
+    out["sD2_checksum"] = np.einsum("n,kn->k", wn, sD2)   # [K]
+    if keep_tables == "full":
+        out["sD"], out["sD2"] = sD, sD2
+    else:
+        idx = np.array(subset)
+        out["table_particles"] = idx
+        out["sD_subset"] = sD[:, idx, :]
+        out["sD2_subset"] = sD2[:, idx]
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(f"{name}: E_R={float(d['local_energy_r']):.12g} E_I={float(d['local_energy_i']):.12g} "
+          f"exponent={float(d['exponent']):.12g} q={d['move_quotient']}")
+    return d
+
+
+def run_mc(system, scal, arrays):
+    with tempfile.TemporaryDirectory() as td:
+        cp, op = os.path.join(td, "case.txt"), os.path.join(td, "out.txt")
+        write_case(cp, system, scal, arrays)
+        run("mc", cp, op)
+        return parse_dump(op)
+
+
+def default_moves(R, L, rng, n=6, sigma=0.5):
+    moves = []
+    for _ in range(n):
+        p = int(rng.integers(0, R.shape[0]))
+        moves.append([p] + list(R[p] + rng.normal(0, sigma, 3)))
+    return moves
+
+
+def gen_bosonsbulk():
+    rng = np.random.default_rng(20261017)
+    # (1) reference fixture particleconfiguration_64.csv: L=4, rho=1, small P
+    N, L, P = 64, 4.0, 33
+    R = read_csv_positions("particleconfiguration_64.csv").reshape(N, 3)
+    uR, uI = smooth_params(P, L / 2, w_r=0.6, c_i=1.0, w_i=0.4)
+    scal = dict(N=N, LBOX=L, N_PARAM=P, time=0.0, phiR=0.25, phiI=-0.1)
+    arr = dict(R=R, uR=uR, uI=uI, SYSTEM_PARAMS=[1.0, 1.0])
+    pack_eval("bosonsbulk_n64_fixture", "BosonsBulk", scal, arr, default_moves(R, L, rng))
+
+    # (2) same system after the reference's own sampler has equilibrated it (non-lattice distances),
+    #     time-switched potential parameters (BosonsBulk.cpp:237-243)
+    mc = run_mc("BosonsBulk", dict(scal, MC_STEP=0.4, MC_NSTEPS=1, MC_NTHERMSTEPS=64 * 200, seed=7), arr)
+    R2 = mc["R_final"].reshape(N, 3)
+    arr2 = dict(arr, R=R2, SYSTEM_PARAMS=[1.0, 1.0, 0.5, 0.8, 2.5])
+    pack_eval("bosonsbulk_n64_equil", "BosonsBulk", dict(scal, time=1.0), arr2, default_moves(R2, L, rng))
+
+    # (3) headline shape: N=343, P=201, natural-box lattice fixture particleconfiguration_343_.csv
+    N, P = 343, 201
+    R = read_csv_positions("particleconfiguration_343_.csv").reshape(N, 3)
+    L = 7.0 * 10.0 ** (1.0 / 3.0)
+    uR, uI = smooth_params(P, L / 2, w_r=2.0, c_i=3.5, w_i=1.0)
+    scal = dict(N=N, LBOX=L, N_PARAM=P, time=0.0, phiR=0.0, phiI=0.0)
+    arr = dict(R=R, uR=uR, uI=uI, SYSTEM_PARAMS=[2.5, 1.0])
+    pack_eval("bosonsbulk_n343_lattice", "BosonsBulk", scal, arr, default_moves(R, L, rng),
+              keep_tables="subset", subset=(0, 1, 171, 342))
+
+    # (4) headline workload: N=343, L=7 (rho=1), P=201, equilibrated by the reference sampler
+    L = 7.0
+    R0 = jittered_lattice(N, L, seed=1)
+    uR, uI = smooth_params(P, L / 2)
+    scal = dict(N=N, LBOX=L, N_PARAM=P, time=0.0, phiR=0.0, phiI=0.0)
+    arr = dict(R=R0, uR=uR, uI=uI, SYSTEM_PARAMS=[1.0, 1.0])
+    mc = run_mc("BosonsBulk", dict(scal, MC_STEP=0.5, MC_NSTEPS=1, MC_NTHERMSTEPS=343 * 30, seed=3), arr)
+    R1 = mc["R_final"].reshape(N, 3)
+    pack_eval("bosonsbulk_n343_equil", "BosonsBulk", scal, dict(arr, R=R1), default_moves(R1, L, rng),
+              keep_tables="subset", subset=(0, 1, 171, 342))
+
+
+def gen_bosonsbulk_mc():
+    """Statistical golden: the reference sampler at fixed parameters, with its per-sample series."""
+    N, L, P = 64, 4.0, 33
+    R = read_csv_positions("particleconfiguration_64.csv").reshape(N, 3)
+    uR, uI = smooth_params(P, L / 2, w_r=0.6, c_i=1.0, w_i=0.4)
+    scal = dict(N=N, LBOX=L, N_PARAM=P, time=0.0, phiR=0.0, phiI=0.0, MC_STEP=0.4,
+                MC_NINITIALIZATIONSTEPS=64 * 100, MC_NSTEPS=6000, MC_NTHERMSTEPS=64, seed=11)
+    arr = dict(R=R, uR=uR, uI=uI, SYSTEM_PARAMS=[1.0, 1.0])
+    d = run_mc("BosonsBulk", scal, arr)
+    er = d["energy_r_series"]
+    out = dict(N=np.array(N), LBOX=np.array(L), N_PARAM=np.array(P), MC_STEP=np.array(0.4),
+               SYSTEM_PARAMS=np.array([1.0, 1.0]), uR=uR, uI=uI, R0=R,
+               n_samples=np.array(len(er)), n_therm=np.array(64),
+               energy_r_series=er, energy_i_series=d["energy_i_series"],
+               local_energy_r=d["local_energy_r"], local_energy_i=d["local_energy_i"],
+               local_operators=d["local_operators"], local_operator_energy_r=d["local_operator_energy_r"],
+               local_operator_energy_i=d["local_operator_energy_i"],
+               local_operators_matrix=d["local_operators_matrix"],
+               other_expectation_values=d["other_expectation_values"],
+               acceptance=np.array(float(d["n_acceptances"]) / float(d["n_trials"])))
+    np.savez_compressed(os.path.join(GOLDEN, "bosonsbulk_n64_mc.npz"), **out)
+    print(f"bosonsbulk_n64_mc: <E_R>={float(d['local_energy_r']):.8g} acc={out['acceptance']:.4f}")
+
+
+def gen_nubosonsbulkpb():
+    rng = np.random.default_rng(4)
+    # reduced copy of config/NUBosonsBulkPB3D.config: rho=1, L=6, non-uniform knot grid on [0, 3]
+    N, L, P = 216, 6.0, 40
+    x = np.linspace(0.0, 1.0, P + 1)
+    grid = 3.0 * (0.35 * x + 0.65 * x ** 2)          # finer near the origin
+    grid[-1] = 3.0
+    R0 = jittered_lattice(N, L, seed=5)
+    uR, uI = smooth_params(P, L / 2, w_r=0.8, c_i=1.2, w_i=0.5)
+    scal = dict(N=N, LBOX=L, N_PARAM=P, USE_NURBS=1, time=0.0, phiR=0.1, phiI=0.0, GR_BIN_COUNT=50)
+    arr = dict(R=R0, uR=uR, uI=uI, SYSTEM_PARAMS=[0.0, 0.0, 0.0, 0.9, 50.0], NURBS_GRID=grid)
+    mc = run_mc("NUBosonsBulkPB", dict(scal, MC_STEP=0.5, MC_NSTEPS=1, MC_NTHERMSTEPS=216 * 30, seed=9), arr)
+    R1 = mc["R_final"].reshape(N, 3)
+    pack_eval("nubosonsbulkpb_n216_equil", "NUBosonsBulkPB", scal, dict(arr, R=R1),
+              default_moves(R1, L, rng), keep_tables="subset", subset=(0, 7, 100, 215))
+
+
+def gen_min_image():
+    """Reference minimum-image displacement on edge cases + random inputs (Utils.cpp:266-281, 352-382)."""
+    rng = np.random.default_rng(99)
+    rows = []
+    for L in (4.0, 5.0, 7.0, 15.081):
+        for _ in range(64):
+            a = rng.uniform(-2.5 * L, 2.5 * L, 3)
+            b = rng.uniform(-2.5 * L, 2.5 * L, 3)
+            rows.append((L, a, b))
+        # exact half-box ties and multiples of the box
+        for s in (0.5, -0.5, 1.0, -1.0, 1.5, -1.5, 2.5, 0.0):
+            rows.append((L, np.array([s * L, 0.0, -s * L]), np.zeros(3)))
+            rows.append((L, np.array([0.1, s * L / 2, 0.3]), np.array([0.1, -s * L / 2, 0.3])))
+    with tempfile.TemporaryDirectory() as td:
+        ip, op = os.path.join(td, "in.txt"), os.path.join(td, "out.txt")
+        with open(ip, "w") as f:
+            for L, a, b in rows:
+                f.write(f"{float(L)!r} 3 " + " ".join(repr(float(x)) for x in [*a, *b]) + "\n")
+        run("nic", ip, op)
+        res = np.loadtxt(op)
+    np.savez_compressed(os.path.join(GOLDEN, "min_image_reference.npz"),
+                        L=np.array([r[0] for r in rows]), a=np.array([r[1] for r in rows]),
+                        b=np.array([r[2] for r in rows]), norm=res[:, 0], disp=res[:, 1:4])
+    print(f"min_image_reference: {len(rows)} cases")
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    if not os.path.exists(HARNESS):
+        sys.exit("build the oracle first: make -C oracle/ref_build")
+    which = sys.argv[1:] or ["min_image", "bosonsbulk", "bosonsbulk_mc", "nubosonsbulkpb"]
+    for w in which:
+        globals()["gen_" + w]()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,419 @@
+/*
+ * ref_harness — drives the UNMODIFIED reference (mathiasgartner/TDVMC) as a CPU oracle.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This translation unit textually includes the
+ * reference's src/TDVMC.cpp (where it lies under /root/reference; nothing is
+ * copied into this repository) with its main() renamed, and then calls the
+ * reference's own functions:
+ *
+ *   InitializePhysicalSystem()  src/TDVMC.cpp:2786
+ *   Init()                      src/TDVMC.cpp:514
+ *   PostSystemInit()            src/TDVMC.cpp:616
+ *   sys->CalculateWavefunction / CalculateExpectationValues / CalculateWFQuotient
+ *                               src/PhysicalSystems/IPhysicalSystem.h:98-122
+ *   DoMetropolisStep()          src/TDVMC.cpp:858
+ *   VectorDisplacementNIC()     src/Utils.cpp:376
+ *
+ * Modes (argv[1]):
+ *   eval  <case> <out>   fixed-configuration evaluation -> named arrays, %.17g
+ *   mc    <case> <out>   fixed-parameter sampling run   -> estimators + series
+ *   bench <case>         timed sampling run, prints one line "trials seconds samples"
+ *   nic   <in> <out>     minimum-image displacement for a list of vector pairs
+ *
+ * `private`/`protected` are re-declared public for this TU only, so that the
+ * harness can read the reference's internal tables (knots, spline weights,
+ * basis sums).  The reference objects it links against are compiled unchanged.
+ */
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <map>
+#include <random>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#define private public
+#define protected public
+#define main tdvmc_reference_main
+#include "src/TDVMC.cpp"
+#undef main
+#undef private
+#undef protected
+
+namespace
+{
+
+struct Case
+{
+    std::map<std::string, std::vector<double> > num;
+    std::map<std::string, std::string> str;
+    std::vector<std::vector<double> > moves; // particle, new x, y, z
+
+    bool has(const std::string& k) const { return num.count(k) > 0; }
+    double d(const std::string& k, double def = 0.0) const
+    {
+        auto it = num.find(k);
+        return (it == num.end() || it->second.empty()) ? def : it->second[0];
+    }
+    int i(const std::string& k, int def = 0) const { return (int)std::llround(d(k, def)); }
+    std::vector<double> v(const std::string& k) const
+    {
+        auto it = num.find(k);
+        return it == num.end() ? std::vector<double>() : it->second;
+    }
+};
+
+// case file: one record per line, "<key> <values...>"; "system <name>", "configdir <path>"
+// and "move <p> <x> <y> <z>" are special.
+Case ReadCase(const std::string& path)
+{
+    Case c;
+    std::ifstream f(path);
+    if (!f)
+    {
+        std::cerr << "cannot open case file " << path << std::endl;
+        std::exit(2);
+    }
+    std::string line;
+    while (std::getline(f, line))
+    {
+        std::istringstream ss(line);
+        std::string key;
+        if (!(ss >> key) || key[0] == '#') continue;
+        if (key == "system" || key == "configdir")
+        {
+            std::string s;
+            ss >> s;
+            c.str[key] = s;
+            continue;
+        }
+        std::vector<double> vals;
+        std::string tok;
+        while (ss >> tok) vals.push_back(std::strtod(tok.c_str(), nullptr));
+        if (key == "move") c.moves.push_back(vals);
+        else c.num[key] = vals;
+    }
+    return c;
+}
+
+struct Dump
+{
+    std::ofstream f;
+    explicit Dump(const std::string& path) : f(path)
+    {
+        f << std::setprecision(17);
+    }
+    void scalar(const std::string& name, double x)
+    {
+        f << name << " 0\n" << x << "\n";
+    }
+    void vec(const std::string& name, const std::vector<double>& x)
+    {
+        f << name << " 1 " << x.size() << "\n";
+        for (double y : x) f << y << " ";
+        f << "\n";
+    }
+    void vecll(const std::string& name, const std::vector<long long>& x)
+    {
+        f << name << " 1 " << x.size() << "\n";
+        for (long long y : x) f << y << " ";
+        f << "\n";
+    }
+    void mat(const std::string& name, const std::vector<std::vector<double> >& x)
+    {
+        size_t c = x.empty() ? 0 : x[0].size();
+        f << name << " 2 " << x.size() << " " << c << "\n";
+        for (auto& r : x)
+            for (double y : r) f << y << " ";
+        f << "\n";
+    }
+    void ten(const std::string& name, const std::vector<std::vector<std::vector<double> > >& x)
+    {
+        size_t b = x.empty() ? 0 : x[0].size();
+        size_t c = (x.empty() || x[0].empty()) ? 0 : x[0][0].size();
+        f << name << " 3 " << x.size() << " " << b << " " << c << "\n";
+        for (auto& m : x)
+            for (auto& r : m)
+                for (double y : r) f << y << " ";
+        f << "\n";
+    }
+};
+
+std::vector<std::vector<double> > R;
+std::vector<double> uR, uI;
+double phiR = 0, phiI = 0;
+
+// Sets the reference's file-scope configuration globals (src/TDVMC.cpp:76-131) from the
+// case, builds the system through the reference's own factory and initialises it.
+void SetupReference(const Case& c)
+{
+    SYSTEM_TYPE = c.str.at("system");
+    configDirectory = c.str.count("configdir") ? c.str.at("configdir") : std::string("./");
+    N = c.i("N");
+    DIM = c.i("DIM", 3);
+    LBOX = c.d("LBOX");
+    N_PARAM = c.i("N_PARAM");
+    RHO = c.d("RHO", 0.0);
+    RC = c.d("RC", 0.0);
+    MC_STEP = c.d("MC_STEP", 0.5);
+    MC_NSTEPS = c.i("MC_NSTEPS", 1);
+    MC_NTHERMSTEPS = c.i("MC_NTHERMSTEPS", 1);
+    MC_NINITIALIZATIONSTEPS = c.i("MC_NINITIALIZATIONSTEPS", 0);
+    IMAGINARY_TIME = c.i("IMAGINARY_TIME", 1);
+    GR_BIN_COUNT = c.i("GR_BIN_COUNT", 100);
+    RHO_BIN_COUNT = c.i("RHO_BIN_COUNT", 100);
+    USE_NURBS = c.i("USE_NURBS", 0);
+    NURBS_GRID = c.v("NURBS_GRID");
+    SYSTEM_PARAMS = c.v("SYSTEM_PARAMS");
+    PARTICLE_TYPES.clear();
+    for (double t : c.v("PARTICLE_TYPES")) PARTICLE_TYPES.push_back((int)t);
+    WRITE_EVERY_NTH_STEP_TO_FILE = 1;
+    MC_NSTEP_MULTIPLICATION_FACTOR_FOR_WRITE_DATA = 1;
+    UPDATE_SAMPLES_EVERY_NTH_STEP = 0;
+    processRank = c.i("rank", 0);
+    numOfProcesses = 1;
+    isRootRank = false; // keeps the reference's progress output quiet
+
+    if (!InitializePhysicalSystem())
+    {
+        std::cerr << "unknown system type " << SYSTEM_TYPE << std::endl;
+        std::exit(2);
+    }
+    // Init() prints a few lines to stdout; silence them.
+    std::streambuf* old = std::cout.rdbuf();
+    std::ostringstream sink;
+    std::cout.rdbuf(sink.rdbuf());
+    Init();
+    std::cout.rdbuf(old);
+
+    std::vector<double> flat = c.v("R");
+    R.assign(N, std::vector<double>(DIM, 0.0));
+    for (int n = 0; n < N; n++)
+        for (int a = 0; a < DIM; a++) R[n][a] = flat[(size_t)n * DIM + a];
+    uR = c.v("uR");
+    uI = c.v("uI");
+    uR.resize(N_PARAM, 0.0);
+    uI.resize(N_PARAM, 0.0);
+    phiR = c.d("phiR", 0.0);
+    phiI = c.d("phiI", 0.0);
+
+    std::cout.rdbuf(sink.rdbuf());
+    sys->InitSystem();
+    PostSystemInit();
+    std::cout.rdbuf(old);
+    sys->SetTime(c.d("time", 0.0));
+}
+
+template <class S>
+void DumpSplineInternals(Dump& d, S* s)
+{
+    d.vec("knots", s->nodes);
+    d.ten("spline_weights", s->splineWeights);
+    d.vec("spline_sums", s->splineSums);
+    d.scalar("outer_sum", s->outerSum);
+    d.scalar("max_distance", s->maxDistance);
+    d.ten("sD", s->splineSumsD);
+    d.mat("sD2", s->splineSumsD2);
+    d.vec("other_local_operators", s->otherLocalOperators);
+}
+
+void DumpSystemInternals(Dump& d)
+{
+    if (auto s = dynamic_cast<PhysicalSystems::BosonsBulk*>(sys))
+    {
+        DumpSplineInternals(d, s);
+        d.mat("bc_start", s->bcFactorsStart);
+        d.mat("bc_end", s->bcFactorsEnd);
+    }
+    else if (auto s = dynamic_cast<PhysicalSystems::NUBosonsBulkPB*>(sys))
+    {
+        DumpSplineInternals(d, s);
+    }
+}
+
+int ModeEval(const Case& c, const std::string& out)
+{
+    SetupReference(c);
+    Dump d(out);
+
+    sys->CalculateWavefunction(R, uR, uI, phiR, phiI);
+    d.scalar("exponent_wf", sys->GetExponent());
+    sys->CalculateExpectationValues(R, uR, uI, phiR, phiI);
+
+    d.scalar("exponent", sys->GetExponent());
+    d.scalar("wf", sys->GetWf());
+    d.scalar("local_energy_r", sys->GetLocalEnergyR());
+    d.scalar("local_energy_i", sys->GetLocalEnergyI());
+    d.vec("local_operators", sys->GetLocalOperators());
+    d.vec("local_operator_energy_r", sys->GetLocalOperatorlocalEnergyR());
+    d.vec("local_operator_energy_i", sys->GetLocalOperatorlocalEnergyI());
+    d.vec("other_expectation_values", sys->GetOtherExpectationValues());
+    // one row and the diagonal of O (x) O are enough to pin the layout of the P x P matrix
+    std::vector<std::vector<double> > M = sys->GetLocalOperatorsMatrix();
+    std::vector<double> diag(M.size()), row3;
+    for (size_t k = 0; k < M.size(); k++) diag[k] = M[k][k];
+    if (M.size() > 3) row3 = M[3];
+    d.vec("local_operators_matrix_diag", diag);
+    d.vec("local_operators_matrix_row3", row3);
+    DumpSystemInternals(d);
+
+    // scripted single-particle moves: quotient for the proposal, state left untouched
+    std::vector<double> q, en;
+    for (auto& m : c.moves)
+    {
+        int p = (int)m[0];
+        std::vector<double> oldPosition(R[p]);
+        for (int a = 0; a < DIM; a++) R[p][a] = m[1 + a];
+        q.push_back(sys->CalculateWFQuotient(R, uR, uI, phiR, phiI, p, oldPosition));
+        en.push_back(sys->GetExponentNew());
+        R[p] = oldPosition;
+    }
+    d.vec("move_quotient", q);
+    d.vec("move_exponent_new", en);
+    return 0;
+}
+
+// Fixed-parameter sampling, mirroring UpdateExpectationValues (src/TDVMC.cpp:1038-1150)
+// but keeping the per-sample series so that error bars can be attached.
+int ModeMC(const Case& c, const std::string& out, bool benchOnly)
+{
+    SetupReference(c);
+    int nSamples = c.i("MC_NSTEPS", 1);
+    int nTherm = c.i("MC_NTHERMSTEPS", 1);
+    int nInit = c.i("MC_NINITIALIZATIONSTEPS", 0);
+    int seed = c.i("seed", 1);
+    generator = std::mt19937_64((unsigned long long)seed);
+
+    std::vector<double> O(N_PARAM, 0.0), OER(N_PARAM, 0.0), OEI(N_PARAM, 0.0), erSeries, eiSeries;
+    std::vector<std::vector<double> > S(N_PARAM, std::vector<double>(N_PARAM, 0.0));
+    std::vector<double> other;
+    double er = 0, ei = 0;
+
+    sys->CalculateWavefunction(R, uR, uI, phiR, phiI);
+    for (int i = 0; i < nInit; i++) DoMetropolisStep(R, uR, uI, phiR, phiI);
+    nTrials = 0;
+    nAcceptances = 0;
+
+    auto t0 = std::chrono::steady_clock::now();
+    for (int s = 0; s < nSamples; s++)
+    {
+        for (int t = 0; t < nTherm; t++) DoMetropolisStep(R, uR, uI, phiR, phiI);
+        sys->CalculateExpectationValues(R, uR, uI, phiR, phiI);
+        if (benchOnly)
+        {
+            // the reference's estimator accumulation (src/TDVMC.cpp:1103-1109) is part of the path
+            localOperators += sys->GetLocalOperators() / (double)nSamples;
+            localEnergyR += sys->GetLocalEnergyR() / (double)nSamples;
+            localEnergyI += sys->GetLocalEnergyI() / (double)nSamples;
+            localOperatorsMatrix += sys->GetLocalOperatorsMatrix() / (double)nSamples;
+            localOperatorlocalEnergyR += sys->GetLocalOperatorlocalEnergyR() / (double)nSamples;
+            localOperatorlocalEnergyI += sys->GetLocalOperatorlocalEnergyI() / (double)nSamples;
+            otherExpectationValues += sys->GetOtherExpectationValues() / (double)nSamples;
+            continue;
+        }
+        std::vector<double> o = sys->GetLocalOperators();
+        double e1 = sys->GetLocalEnergyR(), e2 = sys->GetLocalEnergyI();
+        erSeries.push_back(e1);
+        eiSeries.push_back(e2);
+        er += e1;
+        ei += e2;
+        for (int k = 0; k < N_PARAM; k++)
+        {
+            O[k] += o[k];
+            OER[k] += o[k] * e1;
+            OEI[k] += o[k] * e2;
+            for (int j = 0; j < N_PARAM; j++) S[k][j] += o[k] * o[j];
+        }
+        std::vector<double> oth = sys->GetOtherExpectationValues();
+        if (other.empty()) other.assign(oth.size(), 0.0);
+        for (size_t k = 0; k < oth.size(); k++) other[k] += oth[k];
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    double seconds = std::chrono::duration<double>(t1 - t0).count();
+
+    if (benchOnly)
+    {
+        std::printf("%lld %.6f %d %.10g\n", nTrials, seconds, nSamples, localEnergyR);
+        return 0;
+    }
+
+    double inv = 1.0 / nSamples;
+    for (int k = 0; k < N_PARAM; k++)
+    {
+        O[k] *= inv;
+        OER[k] *= inv;
+        OEI[k] *= inv;
+        for (int j = 0; j < N_PARAM; j++) S[k][j] *= inv;
+    }
+    for (auto& x : other) x *= inv;
+    Dump d(out);
+    d.scalar("local_energy_r", er * inv);
+    d.scalar("local_energy_i", ei * inv);
+    d.vec("local_operators", O);
+    d.vec("local_operator_energy_r", OER);
+    d.vec("local_operator_energy_i", OEI);
+    d.mat("local_operators_matrix", S);
+    d.vec("other_expectation_values", other);
+    d.vec("energy_r_series", erSeries);
+    d.vec("energy_i_series", eiSeries);
+    d.scalar("n_trials", (double)nTrials);
+    d.scalar("n_acceptances", (double)nAcceptances);
+    d.scalar("seconds", seconds);
+    std::vector<double> flat;
+    for (auto& r : R)
+        for (double x : r) flat.push_back(x);
+    d.vec("R_final", flat);
+    return 0;
+}
+
+// input: "L dim" then lines "i1 i2 i3 j1 j2 j3"; output per line: norm, d1, d2, d3
+int ModeNic(const std::string& in, const std::string& out)
+{
+    std::ifstream f(in);
+    std::ofstream o(out);
+    o << std::setprecision(17);
+    std::string line;
+    while (std::getline(f, line))
+    {
+        std::istringstream ss(line);
+        double L;
+        int dim;
+        if (!(ss >> L >> dim)) continue;
+        LBOX = L;
+        LBOX_R = 1.0 / LBOX;
+        LBOX_2 = LBOX / 2.0;
+        DIM = dim;
+        std::vector<double> a(dim), b(dim), r(dim);
+        for (int k = 0; k < dim; k++) ss >> a[k];
+        for (int k = 0; k < dim; k++) ss >> b[k];
+        double n = VectorDisplacementNIC(a, b, r);
+        o << n;
+        for (int k = 0; k < dim; k++) o << " " << r[k];
+        o << "\n";
+    }
+    return 0;
+}
+
+} // namespace
+
+int main(int argc, char** argv)
+{
+    if (argc < 3)
+    {
+        std::cerr << "usage: ref_harness eval|mc <case> <out> | bench <case> | nic <in> <out>" << std::endl;
+        return 2;
+    }
+    std::string mode = argv[1];
+    if (mode == "eval" && argc >= 4) return ModeEval(ReadCase(argv[2]), argv[3]);
+    if (mode == "mc" && argc >= 4) return ModeMC(ReadCase(argv[2]), argv[3], false);
+    if (mode == "bench") return ModeMC(ReadCase(argv[2]), "", true);
+    if (mode == "nic" && argc >= 4) return ModeNic(argv[2], argv[3]);
+    std::cerr << "bad arguments" << std::endl;
+    return 2;
+}
