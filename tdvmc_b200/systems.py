@@ -1,0 +1,161 @@
+"""Host-side description of a physical system for the walker hot path.
+
+Mirrors what the reference's ``IPhysicalSystem`` plugins set up in ``InitSystem()`` -- knots,
+spline table, boundary-condition map, cut-off rule, pair potential -- as plain data that is
+handed to the CUDA library through ``tdvmc_system_desc`` (include/tdvmc_gpu.h).  Systems are data,
+not kernels: the device code is driven by the flags in this description.
+
+Covered so far:
+  * ``BosonsBulk``      src/PhysicalSystems/BosonsBulk.cpp:49-156   (config 3, headline)
+  * ``NUBosonsBulkPB``  src/PhysicalSystems/NUBosonsBulkPB.cpp:53-216 (config 4)
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import splines
+
+PAIR_RULE_CUT = 0      # r <= r_max -> spline, else tail count        (BosonsBulk.cpp:195-210)
+PAIR_RULE_REFLECT = 1  # r -> 2 r_max - r beyond r_max, then r < r_max (NUBosonsBulkPB.cpp:249-269)
+
+HBAR2_2M = 1.0  # src/Constants.h:12
+
+
+@dataclass
+class SystemSpec:
+    name: str
+    n_particles: int
+    n_params: int
+    lbox: float
+    knots: np.ndarray              # [K+4]
+    weights: np.ndarray            # [K][4][4], SplineFactory::GetWeights3 layout
+    map_ptr: np.ndarray            # [P+1] CSR rows: O_p = sum_j map_val[j] * ss[map_col[j]]
+    map_col: np.ndarray
+    map_val: np.ndarray
+    pair_rule: int
+    system_params: np.ndarray      # SYSTEM_PARAMS as in the config
+    n_other: int = 9               # length of otherExpectationValues
+    dim: int = 3
+    hbar2_2m: float = HBAR2_2M
+    tail_param: int = -1
+    extra: dict = field(default_factory=dict)
+
+    @property
+    def n_splines(self):
+        return len(self.knots) - 4
+
+    @property
+    def r_max(self):
+        return float(self.knots[len(self.knots) - 4])
+
+    def potential(self, time):
+        """Square-well (a, b) with the time switch of BosonsBulk.cpp:237-243 / NUBosonsBulkPB.cpp:300-307."""
+        p = self.system_params
+        a, b = float(p[0]), float(p[1])
+        if len(p) > 2 and time >= p[2]:
+            a, b = float(p[3]), float(p[4])
+        return a, b
+
+    def map_rows(self):
+        return [[(int(self.map_col[j]), float(self.map_val[j])) for j in range(self.map_ptr[p], self.map_ptr[p + 1])]
+                for p in range(self.n_params)]
+
+    def spline_space(self, u):
+        """u~_k = sum_p u_p M[p][k]: parameters pushed through the transposed boundary map."""
+        ut = np.zeros(self.n_splines, dtype=np.float64)
+        for p, row in enumerate(self.map_rows()):
+            for k, f in row:
+                ut[k] += u[p] * f
+        return ut
+
+
+def _csr(rows):
+    ptr = np.zeros(len(rows) + 1, dtype=np.int32)
+    col, val = [], []
+    for p, row in enumerate(rows):
+        for k, f in row:
+            col.append(k)
+            val.append(f)
+        ptr[p + 1] = len(col)
+    return ptr, np.array(col, dtype=np.int32), np.array(val, dtype=np.float64)
+
+
+def bosons_bulk(n_particles, lbox, n_params, system_params=(1.0, 1.0), nurbs_grid=None, weights=None):
+    """``BosonsBulk`` (BosonsBulk.cpp:49-156).
+
+    Knots: uniform ``(i L/2)/(P-1)``, i=-3..P+2 (:61-67) or a mirrored NURBS grid (:35-44).
+    Boundary map: ``SetBoundaryConditions3_1D_OR_2`` at the origin and ``..._CO_2`` at the cut
+    (SplineFactory.cpp:423-456, 563-596; both are called with ``uniform=true``, BosonsBulk.cpp:75-76),
+    applied as in ``RefreshLocalOperators`` (:158-177).  ``P`` must equal ``K - 2`` (:85-91).
+    """
+    knots = splines.uniform_knots(n_params, lbox / 2.0) if nurbs_grid is None else splines.extend_knots_mirrored(nurbs_grid)
+    K = len(knots) - 4
+    if n_params != K - 2:
+        raise ValueError(f"BosonsBulk needs N_PARAM = K - 2 = {K - 2}, got {n_params}")
+    if weights is None:
+        weights = splines.bspline_monomial_weights(knots)
+    rows = [[(1, 1.0)], [(0, 1.0), (2, 1.0)]]
+    rows += [[(3 + i, 1.0)] for i in range(n_params - 4)]
+    rows += [[(K - 3, 1.0), (K - 1, 1.0)], [(K - 2, 1.0)]]
+    ptr, col, val = _csr(rows)
+    return SystemSpec("BosonsBulk", n_particles, n_params, float(lbox), knots, np.ascontiguousarray(weights), ptr, col, val,
+                      PAIR_RULE_CUT, np.asarray(system_params, dtype=np.float64), n_other=9, tail_param=n_params - 1)
+
+
+def nu_bosons_bulk_pb(n_particles, lbox, n_params, nurbs_grid, system_params=(0.0, 0.0, 0.0, 0.1, 50.0),
+                      gr_bin_count=400, weights=None):
+    """``NUBosonsBulkPB`` (NUBosonsBulkPB.cpp:53-216): non-uniform knots, periodic-box reflection.
+
+    ``K = P + 3`` (:71); map ``O_i = ss[i+1]``, ``O_1 += ss[0]``, ``O_{P-1} += ss[K-2] + ss[K-1]`` (:219-232);
+    ``otherExpectationValues`` has ``9 + GR_BIN_COUNT`` entries of which only the first nine are filled (:61, :578-581).
+    """
+    knots = splines.extend_knots_mirrored(nurbs_grid)
+    K = len(knots) - 4
+    if K != n_params + 3:
+        raise ValueError(f"NUBosonsBulkPB needs K = N_PARAM + 3, got K={K}, N_PARAM={n_params}")
+    if weights is None:
+        weights = splines.bspline_monomial_weights(knots)
+    rows = [[(i + 1, 1.0)] for i in range(n_params)]
+    rows[1].append((0, 1.0))
+    rows[n_params - 1] += [(K - 2, 1.0), (K - 1, 1.0)]
+    ptr, col, val = _csr(rows)
+    return SystemSpec("NUBosonsBulkPB", n_particles, n_params, float(lbox), knots, np.ascontiguousarray(weights), ptr, col, val,
+                      PAIR_RULE_REFLECT, np.asarray(system_params, dtype=np.float64), n_other=9 + int(gr_bin_count),
+                      tail_param=n_params - 1)
+
+
+def from_golden(g):
+    """Build the spec of a tests/golden fixture, taking knots and spline table from the reference dump."""
+    name = str(g["system"])
+    N, L, P = int(g["N"]), float(g["LBOX"]), int(g["N_PARAM"])
+    if name == "BosonsBulk":
+        spec = bosons_bulk(N, L, P, g["SYSTEM_PARAMS"], weights=g["spline_weights"])
+    elif name == "NUBosonsBulkPB":
+        spec = nu_bosons_bulk_pb(N, L, P, g["NURBS_GRID"], g["SYSTEM_PARAMS"], weights=g["spline_weights"],
+                                 gr_bin_count=len(g["other_expectation_values"]) - 9)
+    else:
+        raise ValueError(name)
+    if not np.array_equal(spec.knots, g["knots"]):
+        raise AssertionError("knot construction differs from the reference dump")
+    return spec
+
+
+def smooth_params(n_params, r_max, a_r=-0.5, w_r=0.8, a_i=0.05, c_i=1.5, w_i=0.5):
+    """The fixed smooth parameter profile used for synthetic workloads."""
+    h = r_max / (n_params - 1)
+    k = np.arange(n_params)
+    uR = a_r * np.exp(-((k * h / w_r) ** 2))
+    uI = a_i * np.exp(-(((k * h - c_i) / w_i) ** 2))
+    return uR, uI
+
+
+def jittered_lattice(n_particles, lbox, rng):
+    """Start-up lattice + U(-0.05, 0.05) l jitter, the shape of src/TDVMC.cpp:727-739."""
+    m = int(round(n_particles ** (1.0 / 3.0)))
+    if m ** 3 != n_particles:
+        raise ValueError("cubic lattice needs N = m^3")
+    l = lbox / m
+    g = (np.arange(m) + 0.5) * l - lbox / 2
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    R = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+    return R + rng.uniform(-0.05, 0.05, R.shape) * l

@@ -1,0 +1,109 @@
+"""Pins oracle/tdvmc_oracle.c against fixtures produced by the UNMODIFIED reference
+(oracle/_ref/ref_harness via oracle/gen_golden.py).  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle_lib import Oracle
+from tdvmc_b200 import systems
+
+EVAL_CASES = ["bosonsbulk_n64_fixture", "bosonsbulk_n64_equil", "bosonsbulk_n343_lattice", "bosonsbulk_n343_equil",
+              "nubosonsbulkpb_n216_equil"]
+RTOL = 1e-10  # north_star: fixed-configuration E_L, drift, O_k within 1e-10 relative
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+def test_min_image_known_answers():
+    """The reference's 3-D known-answer cases (src/test/Tests.h:76-129), tolerance 1e-9 as there (:11)."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    cases = json.load(open(os.path.join(here, "golden", "min_image_known_answers.json")))["cases"]
+    spec = systems.bosons_bulk(8, 4.0, 9)
+    o = Oracle(spec)
+    assert len(cases) == 48
+    for c in cases:
+        a = np.array(c["a"] + [0.0] * (3 - len(c["a"])))
+        b = np.array(c["b"] + [0.0] * (3 - len(c["b"])))
+        n, d = o.min_image(c["L"], a, b)
+        assert abs(n - c["norm"]) < 1e-9, c
+        for k, want in enumerate(c["disp"]):
+            assert abs(d[k] - want) < 1e-9, c
+
+
+def test_min_image_bit_exact_vs_reference(golden):
+    g = golden("min_image_reference")
+    o = Oracle(systems.bosons_bulk(8, 4.0, 9))
+    for L, a, b, n, d in zip(g["L"], g["a"], g["b"], g["norm"], g["disp"]):
+        n2, d2 = o.min_image(float(L), a, b)
+        assert n2 == n and np.array_equal(d2, d)
+
+
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_fixed_configuration_matches_reference(golden, name):
+    g = golden(name)
+    spec = systems.from_golden(g)
+    o = Oracle(spec, time=float(g["time"]))
+    r = o.evaluate(g["R"], g["uR"], g["uI"], float(g["phiR"]))
+    # same arithmetic in the same order: the restatement reproduces the reference to the last bits
+    assert rel(r["ss"], g["spline_sums"]) < 1e-14
+    assert r["outer"] == float(g["outer_sum"])
+    assert rel(r["O"], g["local_operators"]) < 1e-14
+    assert abs(r["exponent"] - float(g["exponent"])) < 1e-12 * abs(float(g["exponent"]))
+    assert rel(r["e_r"], g["local_energy_r"]) < 1e-12
+    assert rel(r["e_i"], g["local_energy_i"]) < 1e-12
+    assert rel(r["other"], g["other_expectation_values"][:9]) < 1e-12
+    assert rel(r["drift_r"], g["drift_r"]) < RTOL
+    assert rel(r["drift_i"], g["drift_i"]) < RTOL
+    wn = g["table_checksum_weights"]
+    assert rel(np.einsum("n,kna->ka", wn, r["sD"]), g["sD_checksum"]) < 1e-12
+    assert rel(np.einsum("n,kn->k", wn, r["sD2"]), g["sD2_checksum"]) < 1e-12
+    if "sD" in g:
+        assert np.array_equal(r["sD"], g["sD"]) and np.array_equal(r["sD2"], g["sD2"])
+    else:
+        idx = g["table_particles"]
+        assert np.array_equal(r["sD"][:, idx, :], g["sD_subset"])
+        assert np.array_equal(r["sD2"][:, idx], g["sD2_subset"])
+
+
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_scripted_move_quotient_matches_reference(golden, name):
+    g = golden(name)
+    spec = systems.from_golden(g)
+    o = Oracle(spec, time=float(g["time"]))
+    for m, q_ref, en_ref in zip(g["moves"], g["move_quotient"], g["move_exponent_new"]):
+        q, en, _ = o.quotient(g["R"], int(m[0]), m[1:4], g["uR"])
+        assert abs(en - en_ref) < 1e-12 * abs(en_ref)
+        assert abs(q - q_ref) < 1e-10 * q_ref
+
+
+def test_sampler_statistics_match_reference(golden):
+    """The oracle sampler (Philox proposals) against the reference sampler (mt19937_64): same
+    distribution, different streams -> agreement within combined error bars (4 sigma)."""
+    g = golden("bosonsbulk_n64_mc")
+    spec = systems.bosons_bulk(int(g["N"]), float(g["LBOX"]), int(g["N_PARAM"]), g["SYSTEM_PARAMS"])
+    o = Oracle(spec)
+    n_therm, mc_step = int(g["n_therm"]), float(g["MC_STEP"])
+    n_samples = 1500
+    r = o.sample_walker(g["R0"], g["uR"], g["uI"], 0.0, seed=5, walker=0, step0=0, n_init=64 * 100,
+                        n_samples=n_samples, n_therm=n_therm, mc_step=mc_step)
+    er = r["rows"][:, spec.n_params]
+
+    def blocked(x, nb=20):
+        b = x[:len(x) // nb * nb].reshape(nb, -1).mean(axis=1)
+        return b.mean(), b.std(ddof=1) / np.sqrt(nb)
+
+    m1, s1 = blocked(er)
+    m2, s2 = blocked(g["energy_r_series"])
+    assert abs(m1 - m2) < 4.0 * np.hypot(s1, s2), (m1, s1, m2, s2)
+    acc = r["accepted"] / r["steps"]
+    assert abs(acc - float(g["acceptance"])) < 0.01
+    # <O_k> profile
+    est = o.unpack_est(r["est"], n_samples)
+    O_ref = g["local_operators"]
+    scale = np.abs(O_ref).max()
+    assert np.max(np.abs(est["O"] - O_ref)) / scale < 0.02
