@@ -1,0 +1,186 @@
+/*
+ * tdvmc_gpu.h — C ABI of the B200 walker-ensemble library (libtdvmc_b200.so).
+ *
+ * Drop-in boundary for the walker-parallel sampling + evaluation path of mathiasgartner/TDVMC.
+ * The reference calls its IPhysicalSystem plugin once per Metropolis proposal
+ * (src/TDVMC.cpp:876), which is far too fine-grained for a device; the seam therefore sits one
+ * level up, at the three per-rank loops whose contract is "fill the seven estimator arrays and
+ * the acceptance counters for parameters (uR, uI, phiR, phiI)":
+ *
+ *   UpdateExpectationValues                    src/TDVMC.cpp:1038-1150
+ *   UpdateExpectationValuesForGivenSamples     src/TDVMC.cpp:1222-1303
+ *   MPIMethods::ReduceToAverage x7             src/TDVMC.cpp:1182-1188, src/MPIMethods.h:132-206,329-362
+ *
+ * Conventions: plain pointers and sizes, caller-owned host buffers, row-major doubles.  Every
+ * function returns 0 on success and a non-zero status otherwise; tdvmc_gpu_last_error() gives the
+ * message.  One handle per process/GPU; not thread-safe.  All device memory lives behind the
+ * opaque handle.  There is NO CPU fallback: without a CUDA device every entry point fails.
+ *
+ * Positions on the host are array-of-structs R[walker][particle][dim], exactly the
+ * vector<vector<double>> of the reference flattened; on the device they are SoA per walker.
+ */
+#ifndef TDVMC_GPU_H
+#define TDVMC_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDVMC_GPU_ABI_VERSION 1
+
+typedef struct tdvmc_gpu_handle tdvmc_gpu_handle;
+
+enum tdvmc_pair_rule
+{
+    TDVMC_PAIR_RULE_CUT = 0,    /* BosonsBulk.cpp:195-210: r <= r_max spline, else tail count */
+    TDVMC_PAIR_RULE_REFLECT = 1 /* NUBosonsBulkPB.cpp:249-269: r -> 2 r_max - r beyond r_max */
+};
+
+/* What IPhysicalSystem::InitSystem() sets up, as data (BosonsBulk.cpp:49-156, NUBosonsBulkPB.cpp:53-216). */
+typedef struct tdvmc_system_desc
+{
+    uint32_t struct_size;      /* sizeof(tdvmc_system_desc), for ABI evolution */
+    int32_t n_particles;       /* N */
+    int32_t dim;               /* DIM, must be 3 */
+    int32_t n_params;          /* N_PARAM */
+    int32_t n_splines;         /* K = #knots - 4 (BosonsBulk.cpp:71) */
+    int32_t pair_rule;         /* enum tdvmc_pair_rule */
+    int32_t tail_param;        /* parameter that multiplies the tail count in the exponent (BosonsBulk.cpp:532-534) */
+    int32_t n_other;           /* length of otherExpectationValues (>= 9) */
+    double lbox;               /* LBOX */
+    double hbar2_2m;           /* HBAR2_2M (src/Constants.h:12) */
+    const double* knots;       /* [K+4], nodes (BosonsBulk.cpp:61-67 or SetNodes :35-44) */
+    const double* spline_weights; /* [K][4][4] as returned by SplineFactory::GetWeights3 (SplineFactory.cpp:54-101) */
+    const int32_t* map_ptr;    /* [N_PARAM+1] CSR rows of the boundary-condition map (BosonsBulk.cpp:158-177) */
+    const int32_t* map_col;    /*   O_p = sum_j map_val[j] * splineSums[map_col[j]] */
+    const double* map_val;
+    const double* system_params; /* SYSTEM_PARAMS: a, b [, t_switch, a2, b2] (BosonsBulk.cpp:237-243) */
+    int32_t n_system_params;
+    int32_t reserved;
+} tdvmc_system_desc;
+
+/* The walker ensemble owned by this rank.  The reference runs one walker per MPI rank, seeded
+ * rank+1 (src/TDVMC.cpp:524); here a rank owns n_walkers chains with global ids
+ * first_walker .. first_walker + n_walkers - 1, each with its own Philox4x32-10 stream
+ * keyed by (seed, global id), so results do not depend on how walkers are split over GPUs. */
+typedef struct tdvmc_ensemble_desc
+{
+    uint32_t struct_size;
+    int32_t device;            /* CUDA device ordinal */
+    int32_t n_walkers;         /* walkers resident on this GPU */
+    int32_t first_walker;      /* global id of the first local walker */
+    int32_t max_samples_per_walker; /* capacity of the sample store (MC_NSTEPS) */
+    int32_t keep_sample_positions;  /* != 0: keep R of every sample for tdvmc_gpu_reevaluate_stored */
+    uint64_t seed;
+    double mc_step;            /* MC_STEP */
+} tdvmc_ensemble_desc;
+
+/* Averages as the reference's root rank holds them after ReduceToAverage (src/TDVMC.cpp:147-153). */
+typedef struct tdvmc_estimators
+{
+    double* local_operators;            /* [P]    <O_k>      */
+    double* local_energy_r;             /* [1]    <E^R>      */
+    double* local_energy_i;             /* [1]    <E^I>      */
+    double* local_operators_matrix;     /* [P*P]  <O_k O_j>  row-major */
+    double* local_operator_energy_r;    /* [P]    <O_k E^R>  */
+    double* local_operator_energy_i;    /* [P]    <O_k E^I>  */
+    double* other_expectation_values;   /* [n_other]         */
+    int64_t n_acceptances;              /* summed over all ranks (src/TDVMC.cpp:3727) */
+    int64_t n_trials;
+    int64_t n_samples;                  /* samples in the averages, all ranks */
+} tdvmc_estimators;
+
+int tdvmc_gpu_abi_version(void);
+int tdvmc_gpu_device_count(void);
+
+int tdvmc_gpu_create(const tdvmc_system_desc* system, const tdvmc_ensemble_desc* ensemble, tdvmc_gpu_handle** out);
+void tdvmc_gpu_destroy(tdvmc_gpu_handle* h);
+const char* tdvmc_gpu_last_error(const tdvmc_gpu_handle* h); /* h may be NULL: error of the last failed create */
+
+/* ---- state ---- */
+/* R[n_walkers][N][3] host <-> device SoA (the reference's R, src/TDVMC.cpp:3095). */
+int tdvmc_gpu_set_positions(tdvmc_gpu_handle* h, const double* R, int32_t first_local_walker, int32_t n_walkers);
+int tdvmc_gpu_get_positions(tdvmc_gpu_handle* h, double* R, int32_t first_local_walker, int32_t n_walkers);
+/* BroadcastNewParameters + sys->SetTime (src/TDVMC.cpp:506-512, 3437). */
+int tdvmc_gpu_set_params(tdvmc_gpu_handle* h, const double* uR, const double* uI, double phiR, double phiI, double time);
+/* MoveCoordinatesToFirstCell (src/TDVMC.cpp:787-796). */
+int tdvmc_gpu_wrap_positions(tdvmc_gpu_handle* h);
+
+/* ---- sampling ---- */
+/* DoMetropolisSteps for every local walker (src/TDVMC.cpp:858-924). */
+int tdvmc_gpu_sweep(tdvmc_gpu_handle* h, int64_t n_steps);
+/* UpdateExpectationValues (src/TDVMC.cpp:1038-1150): n_init steps, then n_samples x (n_therm steps +
+ * evaluation of O_k, E_L, other) per walker, then S / F accumulation over all local samples.
+ * Results stay on the device until tdvmc_gpu_allreduce_and_fetch. */
+int tdvmc_gpu_sample_and_accumulate(tdvmc_gpu_handle* h, int32_t n_samples, int32_t n_therm, int32_t n_init);
+/* UpdateExpectationValuesForGivenSamples (src/TDVMC.cpp:1222-1303): re-evaluate the stored samples at the
+ * current parameters (recomputed from the stored R) and accumulate.  Needs keep_sample_positions. */
+int tdvmc_gpu_reevaluate_stored(tdvmc_gpu_handle* h);
+/* ReduceToAverage x7 + nAcceptances (src/TDVMC.cpp:1182-1188, 3727): one packed all-reduce over the
+ * communicator (if any), division by the global sample count; every rank receives the averages. */
+int tdvmc_gpu_allreduce_and_fetch(tdvmc_gpu_handle* h, tdvmc_estimators* out);
+/* sys->GetExponent() of the first local walker's last sample, for NormalizeWavefunction (src/TDVMC.cpp:3763). */
+int tdvmc_gpu_last_exponent(tdvmc_gpu_handle* h, double* exponent);
+
+/* ---- communicator (replaces MPI_COMM_WORLD for the reduce; src/MPIMethods.h) ---- */
+#define TDVMC_GPU_UNIQUE_ID_BYTES 128
+int tdvmc_gpu_comm_unique_id(uint8_t id[TDVMC_GPU_UNIQUE_ID_BYTES]);          /* rank 0, then broadcast by the host */
+int tdvmc_gpu_comm_init(tdvmc_gpu_handle* h, const uint8_t id[TDVMC_GPU_UNIQUE_ID_BYTES], int32_t rank, int32_t n_ranks);
+
+/* ---- fixed-configuration entry points (parity tests; no random numbers) ---- */
+/* CalculateWavefunction + CalculateExpectationValues on n_cfg given configurations R[n_cfg][N][3]
+ * (BosonsBulk.cpp:460-466, 541-545).  Any output pointer may be NULL.
+ * e_r/e_i/exponent: [n_cfg]; O: [n_cfg][P]; other: [n_cfg][n_other]; drift_r/drift_i: [n_cfg][N][3]
+ * (vecKineticSumR1/I1 per particle, BosonsBulk.cpp:354-420); spline_sums: [n_cfg][K]; outer: [n_cfg]. */
+int tdvmc_gpu_evaluate_fixed(tdvmc_gpu_handle* h, const double* R, int32_t n_cfg, double* e_r, double* e_i,
+                             double* O, double* other, double* exponent, double* drift_r, double* drift_i,
+                             double* spline_sums, double* outer);
+/* CalculateWFQuotient (BosonsBulk.cpp:649-657) for n_moves scripted single-particle moves of ONE configuration
+ * R[N][3]: moves[n_moves][4] = {particle, x, y, z}.  quotient/delta: [n_moves]; delta = exponentNew - exponent. */
+int tdvmc_gpu_quotient_fixed(tdvmc_gpu_handle* h, const double* R, const double* moves, int32_t n_moves,
+                             double* quotient, double* delta);
+/* CalculateOtherLocalOperators tables (BosonsBulk.cpp:220-336) in the reference's layout:
+ * sD[K][N][3], sD2[K][N] for ONE configuration. */
+int tdvmc_gpu_tables_fixed(tdvmc_gpu_handle* h, const double* R, double* sD, double* sD2);
+/* Minimum-image displacement a - b and norm for n vector pairs (Utils.cpp:266-281, 368-374). */
+int tdvmc_gpu_min_image(tdvmc_gpu_handle* h, double lbox, const double* a, const double* b, int32_t n, double* norm,
+                        double* disp);
+/* S/F accumulation alone (src/TDVMC.cpp:1103-1109) on caller-provided samples: O[M][P], e_r[M], e_i[M] ->
+ * sums (not averages) S[P*P], f_r[P], f_i[P], o[P]. */
+int tdvmc_gpu_accumulate_fixed(tdvmc_gpu_handle* h, const double* O, const double* e_r, const double* e_i, int64_t M,
+                               double* S, double* f_r, double* f_i, double* o);
+/* The proposal stream: particle, displacement[3], log(u) for (walker, step) -- lets tests replay a chain. */
+int tdvmc_gpu_proposals(tdvmc_gpu_handle* h, int32_t global_walker, int64_t first_step, int32_t n, int32_t* particle,
+                        double* disp, double* log_u);
+
+/* ---- measurement hooks ---- */
+enum tdvmc_kernel_id
+{
+    TDVMC_KERNEL_SWEEP = 0,
+    TDVMC_KERNEL_EVALUATE = 1,
+    TDVMC_KERNEL_ACCUMULATE = 2,
+    TDVMC_KERNEL_TABLES = 3,
+    TDVMC_KERNEL_CONTRACT = 4,
+    TDVMC_KERNEL_OTHER = 5,
+    TDVMC_KERNEL_COUNT = 6
+};
+/* Per-kernel CUDA-event timing on the library's stream. enable=1 starts, stats are cumulative since the last reset. */
+int tdvmc_gpu_profile(tdvmc_gpu_handle* h, int32_t enable, int32_t reset);
+int tdvmc_gpu_kernel_stats(tdvmc_gpu_handle* h, int32_t kernel_id, int64_t* launches, double* total_ms);
+int tdvmc_gpu_synchronize(tdvmc_gpu_handle* h);
+/* K3/K4 exhibits on the resident walkers (reference table semantics, BosonsBulk.cpp:220-336 and :349-458):
+ * materialise the sD/sD2 tables of every local walker and contract them again.  Used by bench.py. */
+int tdvmc_gpu_tables_resident(tdvmc_gpu_handle* h, int32_t n_walkers);
+int tdvmc_gpu_contract_resident(tdvmc_gpu_handle* h, int32_t n_walkers, double* e_r, double* e_i);
+/* Walkers the sweep kernel keeps resident per SM (one warp each) and the SM count: an ensemble that is a
+ * multiple of per_sm * sm_count fills the machine without a partial last wave. */
+int tdvmc_gpu_resident_walkers(tdvmc_gpu_handle* h, int32_t* per_sm, int32_t* sm_count);
+/* Device microbenchmarks for the roofline denominators the driver does not provide (FP64). */
+int tdvmc_gpu_measure_fp64_peak(tdvmc_gpu_handle* h, double* dfma_tflops, double* dmma_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,1103 @@
+// C ABI of libtdvmc_b200.so (include/tdvmc_gpu.h): handle, host-side table preparation, launch
+// sequencing, NCCL all-reduce.  No CPU fallback: every entry point needs a CUDA device.
+#include "../../include/tdvmc_gpu.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
+
+using namespace tdvmc;
+
+namespace
+{
+
+std::string g_create_error;
+
+// ---- NCCL, bound at run time so that single-GPU use needs no NCCL at all ----
+struct UniqueId
+{
+    char internal[TDVMC_GPU_UNIQUE_ID_BYTES];
+};
+struct NcclApi
+{
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, /* ncclUniqueId by value */ UniqueId, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+constexpr int kNcclDouble = 8; // ncclFloat64
+constexpr int kNcclSum = 0;    // ncclSum
+
+bool load_nccl(std::string& err)
+{
+    if (g_nccl.AllReduce) return true;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib)
+    {
+        err = std::string("cannot load libnccl.so.2: ") + dlerror();
+        return false;
+    }
+    g_nccl.lib = lib;
+    g_nccl.GetUniqueId = (int (*)(void*))dlsym(lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, UniqueId, int))dlsym(lib, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+    {
+        err = "libnccl.so.2 lacks a required symbol";
+        g_nccl = NcclApi();
+        return false;
+    }
+    return true;
+}
+
+template <class T>
+struct DevBuf
+{
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count)
+    {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e != cudaSuccess) p = nullptr;
+        return e;
+    }
+    cudaError_t ensure(size_t count)
+    {
+        if (count <= n && p) return cudaSuccess;
+        return alloc(count);
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+};
+
+struct TimedLaunch
+{
+    int kernel;
+    cudaEvent_t e0, e1;
+};
+
+} // namespace
+
+struct tdvmc_gpu_handle
+{
+    std::string error;
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+
+    // system (host copies)
+    int N = 0, Np = 0, P = 0, K = 0, pair_rule = 0, tail_param = 0, n_other = 9;
+    double L = 0, hbar = 1.0;
+    std::vector<double> knots, weights, map_val, sys_params, uR, uI;
+    std::vector<int> map_ptr, map_col;
+    double phiR = 0, phiI = 0, time = 0;
+    bool params_set = false;
+    int first_bin = 3, nbins = 0, ncell = 0, uniform = 0;
+    double h = 0;
+
+    // ensemble
+    int W = 0, first_walker = 0, max_samples = 1, keep_positions = 0;
+    uint64_t seed = 1;
+    double mc_step = 0.5;
+    uint64_t step_counter = 0; // Metropolis steps done per walker (identical for all walkers)
+    uint64_t trials_local = 0; // proposals on this rank since creation
+    int wpb = 8, npp = 0, resident_per_sm = 0;
+
+    // device tables
+    DevBuf<double> d_knots, d_rec, d_cub, d_map_val, d_uR, d_uI, d_utR, d_utI;
+    DevBuf<unsigned short> d_lut;
+    DevBuf<int> d_map_ptr, d_map_col;
+    // walkers and samples
+    DevBuf<double> d_pos, d_aos, d_A, d_other, d_exponent, d_samp_pos, d_est, d_scratch;
+    DevBuf<unsigned long long> d_accepted;
+    DevBuf<double> d_T, d_vint, d_tab_e; // K3/K4 exhibit buffers, allocated on demand
+    int lda = 0, ldc = 0;
+    long long rows_cap = 0;    // padded row capacity of d_A
+    long long rows_used = 0;   // samples of the last accumulation
+    int stored_samples = 0;    // samples per walker kept in d_samp_pos
+    double* h_est = nullptr;   // pinned
+    size_t est_len = 0;
+    bool est_valid = false;
+
+    // communicator
+    void* comm = nullptr;
+    int rank = 0, n_ranks = 1;
+
+    // profiling
+    bool profiling = false;
+    std::vector<TimedLaunch> pending;
+    std::vector<cudaEvent_t> event_pool;
+    long long launches[TDVMC_KERNEL_COUNT] = { 0 };
+    double total_ms[TDVMC_KERNEL_COUNT] = { 0 };
+
+    SysDev sysdev() const;
+};
+
+namespace
+{
+
+#define CK(call)                                                                                        \
+    do                                                                                                  \
+    {                                                                                                   \
+        cudaError_t _e = (call);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+        {                                                                                               \
+            h->error = std::string(#call) + ": " + cudaGetErrorString(_e);                              \
+            return (int)_e ? (int)_e : -1;                                                              \
+        }                                                                                               \
+    } while (0)
+
+int fail(tdvmc_gpu_handle* h, const std::string& msg, int code = -1)
+{
+    h->error = msg;
+    return code;
+}
+
+cudaEvent_t get_event(tdvmc_gpu_handle* h)
+{
+    if (!h->event_pool.empty())
+    {
+        cudaEvent_t e = h->event_pool.back();
+        h->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct Timed
+{
+    tdvmc_gpu_handle* h;
+    int kernel;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    Timed(tdvmc_gpu_handle* h_, int k) : h(h_), kernel(k)
+    {
+        h->launches[k]++;
+        if (h->profiling)
+        {
+            e0 = get_event(h);
+            e1 = get_event(h);
+            cudaEventRecord(e0, h->stream);
+        }
+    }
+    ~Timed()
+    {
+        if (e0)
+        {
+            cudaEventRecord(e1, h->stream);
+            h->pending.push_back({ kernel, e0, e1 });
+        }
+    }
+};
+
+void collect_timings(tdvmc_gpu_handle* h)
+{
+    if (h->pending.empty()) return;
+    cudaStreamSynchronize(h->stream);
+    for (auto& t : h->pending)
+    {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess) h->total_ms[t.kernel] += ms;
+        h->event_pool.push_back(t.e0);
+        h->event_pool.push_back(t.e1);
+    }
+    h->pending.clear();
+}
+
+template <class T>
+cudaError_t upload(DevBuf<T>& b, const std::vector<T>& v, cudaStream_t st)
+{
+    cudaError_t e = b.ensure(v.size());
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+}
+
+// time-switched square well (BosonsBulk.cpp:237-243, NUBosonsBulkPB.cpp:300-307)
+void potential_ab(const tdvmc_gpu_handle* h, double& a, double& b)
+{
+    a = h->sys_params.size() > 0 ? h->sys_params[0] : 0.0;
+    b = h->sys_params.size() > 1 ? h->sys_params[1] : 0.0;
+    if (h->sys_params.size() > 2 && h->time >= h->sys_params[2])
+    {
+        a = h->sys_params[3];
+        b = h->sys_params[4];
+    }
+}
+
+// Static tables: per-interval records of the spline pieces, interval lookup grid.
+int build_static_tables(tdvmc_gpu_handle* h)
+{
+    const int K = h->K;
+    const std::vector<double>& t = h->knots;
+    // first interval a distance can fall in: knots[first_bin] <= 0 < knots[first_bin + 1]
+    int fb = 0;
+    while (fb + 1 < K && t[fb + 1] <= 0.0) fb++;
+    h->first_bin = fb;
+    h->nbins = K - fb;
+    if (h->nbins <= 0 || fb < 3) return fail(h, "knot vector must have three knots below the first non-negative one");
+    const double rmax = t[K];
+    // uniform?
+    const double h0 = (t[K] - t[fb]) / h->nbins;
+    bool uni = (t[fb] == 0.0);
+    double min_sp = rmax;
+    for (int j = fb; j < K; j++)
+    {
+        const double sp = t[j + 1] - t[j];
+        if (!(sp > 0.0)) return fail(h, "knots must be strictly increasing on [0, r_max]");
+        min_sp = std::min(min_sp, sp);
+        if (std::fabs(sp - h0) > 1e-9 * h0) uni = false;
+    }
+    h->uniform = uni ? 1 : 0;
+    h->h = h0;
+    h->ncell = uni ? h->nbins : (int)std::min(8192.0, std::ceil(2.0 * rmax / min_sp));
+    if (h->ncell < 1) h->ncell = 1;
+    std::vector<unsigned short> lut(h->ncell);
+    const double cw = rmax / h->ncell;
+    int j = fb;
+    for (int c = 0; c < h->ncell; c++)
+    {
+        const double x = c * cw;
+        while (j + 1 < K && t[j + 1] <= x) j++;
+        lut[c] = (unsigned short)j;
+    }
+    std::vector<double> rec((size_t)h->nbins * kRecStride, 0.0);
+    for (int b = fb; b < K; b++)
+        for (int p = 0; p < 4; p++)
+            for (int c = 0; c < 4; c++)
+                rec[(size_t)(b - fb) * kRecStride + p * 4 + c] = h->weights[((size_t)(b - p) * 4 + p) * 4 + c];
+    CK(upload(h->d_knots, h->knots, h->stream));
+    CK(upload(h->d_rec, rec, h->stream));
+    CK(upload(h->d_lut, lut, h->stream));
+    CK(upload(h->d_map_ptr, h->map_ptr, h->stream));
+    CK(upload(h->d_map_col, h->map_col, h->stream));
+    CK(upload(h->d_map_val, h->map_val, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// Parameter-dependent tables: u~ = M^T u and the per-interval cubic of the sweep.
+int build_param_tables(tdvmc_gpu_handle* h)
+{
+    const int K = h->K, P = h->P, fb = h->first_bin;
+    std::vector<double> utR(K, 0.0), utI(K, 0.0);
+    for (int p = 0; p < P; p++)
+        for (int j = h->map_ptr[p]; j < h->map_ptr[p + 1]; j++)
+        {
+            utR[h->map_col[j]] += h->uR[p] * h->map_val[j];
+            utI[h->map_col[j]] += h->uI[p] * h->map_val[j];
+        }
+    // u(r) on interval b in the local coordinate s = r - t_b, expanded exactly (long double) from the
+    // caller's monomial table: u(r) = sum_p u~[b-p] * piece_p(b-p)(r)
+    std::vector<double> cub((size_t)h->nbins * kCubStride, 0.0);
+    for (int b = fb; b < K; b++)
+    {
+        long double C[4] = { 0, 0, 0, 0 };
+        for (int p = 0; p < 4; p++)
+            for (int c = 0; c < 4; c++)
+                C[c] += (long double)utR[b - p] * (long double)h->weights[((size_t)(b - p) * 4 + p) * 4 + c];
+        const long double t0 = h->knots[b];
+        double* q = &cub[(size_t)(b - fb) * kCubStride];
+        q[0] = (double)(C[0] + t0 * (C[1] + t0 * (C[2] + t0 * C[3])));
+        q[1] = (double)(C[1] + t0 * (2 * C[2] + 3 * t0 * C[3]));
+        q[2] = (double)(C[2] + 3 * t0 * C[3]);
+        q[3] = (double)C[3];
+        q[4] = h->knots[b];
+        q[5] = h->knots[b + 1];
+    }
+    CK(upload(h->d_uR, h->uR, h->stream));
+    CK(upload(h->d_uI, h->uI, h->stream));
+    CK(upload(h->d_utR, utR, h->stream));
+    CK(upload(h->d_utI, utI, h->stream));
+    CK(upload(h->d_cub, cub, h->stream));
+    CK(cudaStreamSynchronize(h->stream)); // host vectors go out of scope
+    return 0;
+}
+
+int need_params(tdvmc_gpu_handle* h)
+{
+    if (!h->params_set) return fail(h, "tdvmc_gpu_set_params must be called first");
+    return 0;
+}
+
+} // namespace
+
+SysDev tdvmc_gpu_handle::sysdev() const
+{
+    SysDev s;
+    memset(&s, 0, sizeof(s));
+    s.N = N; s.Np = Np; s.P = P; s.K = K;
+    s.pair_rule = pair_rule; s.tail_param = tail_param; s.n_other = n_other;
+    s.first_bin = first_bin; s.nbins = nbins; s.ncell = ncell; s.uniform = uniform;
+    s.L = L; s.Linv = 1.0 / L; s.Lhalf = L / 2.0; // src/TDVMC.cpp:535-536
+    s.rmax = knots[K];
+    s.hbar = hbar;
+    potential_ab(this, s.pot_a, s.pot_b);
+    s.phiR = phiR;
+    s.inv_cell = ncell / s.rmax;
+    s.h = h; s.inv_h = 1.0 / h;
+    s.u_tail = (params_set && tail_param >= 0) ? uR[tail_param] : 0.0;
+    s.knots = d_knots.p; s.rec = d_rec.p; s.cub = d_cub.p; s.lut = d_lut.p;
+    s.map_ptr = d_map_ptr.p; s.map_col = d_map_col.p; s.map_val = d_map_val.p;
+    s.uR = d_uR.p; s.uI = d_uI.p; s.utR = d_utR.p; s.utI = d_utI.p;
+    return s;
+}
+
+extern "C" {
+
+int tdvmc_gpu_abi_version(void) { return TDVMC_GPU_ABI_VERSION; }
+
+int tdvmc_gpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char* tdvmc_gpu_last_error(const tdvmc_gpu_handle* h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed, tdvmc_gpu_handle** out)
+{
+    if (!sd || !ed || !out)
+    {
+        g_create_error = "null argument";
+        return -1;
+    }
+    *out = nullptr;
+    if (sd->struct_size != sizeof(tdvmc_system_desc) || ed->struct_size != sizeof(tdvmc_ensemble_desc))
+    {
+        g_create_error = "struct_size mismatch (ABI version)";
+        return -1;
+    }
+    if (sd->dim != 3 || sd->n_particles < 2 || sd->n_params < 1 || sd->n_splines < 4 || ed->n_walkers < 1 || sd->n_other < 9 ||
+        sd->tail_param < 0 || sd->tail_param >= sd->n_params || !(sd->lbox > 0.0))
+    {
+        g_create_error = "invalid system/ensemble description";
+        return -1;
+    }
+    if (sd->n_params + 3 > 8 * kAccMaxTiles)
+    {
+        g_create_error = "N_PARAM + 3 exceeds the 208 columns of the accumulation kernel";
+        return -1;
+    }
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev <= 0)
+    {
+        g_create_error = std::string("no CUDA device: ") + (ce != cudaSuccess ? cudaGetErrorString(ce) : "device count 0") +
+                         " (this library has no CPU fallback)";
+        return -2;
+    }
+    tdvmc_gpu_handle* h = new tdvmc_gpu_handle();
+    auto bail = [&](int code) {
+        g_create_error = h->error;
+        tdvmc_gpu_destroy(h);
+        return code;
+    };
+    h->device = ed->device;
+    if (cudaSetDevice(h->device) != cudaSuccess)
+    {
+        h->error = "cudaSetDevice failed";
+        return bail(-2);
+    }
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
+    {
+        h->error = "cudaStreamCreate failed";
+        return bail(-2);
+    }
+    h->N = sd->n_particles;
+    h->Np = (h->N + 3) & ~3;
+    h->P = sd->n_params;
+    h->K = sd->n_splines;
+    h->pair_rule = sd->pair_rule;
+    h->tail_param = sd->tail_param;
+    h->n_other = sd->n_other;
+    h->L = sd->lbox;
+    h->hbar = sd->hbar2_2m;
+    h->knots.assign(sd->knots, sd->knots + h->K + 4);
+    h->weights.assign(sd->spline_weights, sd->spline_weights + (size_t)h->K * 16);
+    h->map_ptr.assign(sd->map_ptr, sd->map_ptr + h->P + 1);
+    const int nnz = h->map_ptr[h->P];
+    h->map_col.assign(sd->map_col, sd->map_col + nnz);
+    h->map_val.assign(sd->map_val, sd->map_val + nnz);
+    for (int c : h->map_col)
+        if (c < 0 || c >= h->K)
+        {
+            h->error = "boundary map column out of range";
+            return bail(-1);
+        }
+    h->sys_params.assign(sd->system_params, sd->system_params + sd->n_system_params);
+    if (h->sys_params.size() > 2 && h->sys_params.size() < 5)
+    {
+        h->error = "SYSTEM_PARAMS needs 2 or 5 entries";
+        return bail(-1);
+    }
+    h->uR.assign(h->P, 0.0);
+    h->uI.assign(h->P, 0.0);
+
+    h->W = ed->n_walkers;
+    h->first_walker = ed->first_walker;
+    h->max_samples = std::max(1, ed->max_samples_per_walker);
+    h->keep_positions = ed->keep_sample_positions;
+    h->seed = ed->seed;
+    h->mc_step = ed->mc_step;
+
+    int rc = build_static_tables(h);
+    if (rc) return bail(rc);
+
+    // sample store: augmented rows [O | E^R | E^I | 1], see accumulate.cu
+    const int ncols = h->P + 3;
+    h->ldc = 16 * ((ncols + 15) / 16);
+    h->lda = h->ldc + 4;
+    const long long rows = (long long)h->W * h->max_samples;
+    h->rows_cap = ((rows + kAccChunkRows - 1) / kAccChunkRows) * kAccChunkRows;
+    h->est_len = (size_t)h->P * h->P + 3 * (size_t)h->P + 2 + h->n_other + 3;
+    const size_t scratch = (size_t)h->sm_count * h->ldc * h->ldc + (size_t)h->ldc * h->ldc + (size_t)148 * h->n_other;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](cudaError_t x) {
+        if (e == cudaSuccess) e = x;
+    };
+    A(h->d_pos.alloc((size_t)h->W * 3 * h->Np));
+    A(h->d_aos.alloc((size_t)h->W * 3 * h->N));
+    A(h->d_accepted.alloc(h->W));
+    A(h->d_A.alloc((size_t)h->rows_cap * h->lda));
+    A(h->d_other.alloc((size_t)h->rows_cap * h->n_other));
+    A(h->d_exponent.alloc((size_t)h->rows_cap));
+    A(h->d_est.alloc(h->est_len));
+    A(h->d_scratch.alloc(scratch));
+    if (h->keep_positions) A(h->d_samp_pos.alloc((size_t)rows * 3 * h->Np));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_est, h->est_len * sizeof(double));
+    if (e != cudaSuccess)
+    {
+        h->error = std::string("device allocation failed: ") + cudaGetErrorString(e);
+        return bail(-3);
+    }
+    cudaMemsetAsync(h->d_pos.p, 0, h->d_pos.n * sizeof(double), h->stream);
+    cudaMemsetAsync(h->d_accepted.p, 0, h->d_accepted.n * sizeof(unsigned long long), h->stream);
+    cudaMemsetAsync(h->d_A.p, 0, h->d_A.n * sizeof(double), h->stream);
+    cudaMemsetAsync(h->d_other.p, 0, h->d_other.n * sizeof(double), h->stream);
+    cudaMemsetAsync(h->d_est.p, 0, h->d_est.n * sizeof(double), h->stream);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess)
+    {
+        h->error = "initialisation failed";
+        return bail(-3);
+    }
+
+    // sweep geometry: as many walkers (warps) per block as keep >= 2 blocks per SM resident
+    h->npp = (h->N + 1) & ~1;
+    SysDev s = h->sysdev();
+    int best_wpb = 1, best_res = 0;
+    for (int wpb = 1; wpb <= kSweepMaxThreads / 32; wpb++)
+    {
+        const int res = sweep_blocks_per_sm(s, wpb, h->npp) * wpb; // walkers resident per SM
+        if (res > best_res || (res == best_res && std::abs(wpb - 8) < std::abs(best_wpb - 8)))
+        {
+            best_res = res;
+            best_wpb = wpb;
+        }
+    }
+    h->resident_per_sm = best_res;
+    if (best_res == 0)
+    {
+        h->error = "system does not fit the sweep kernel's shared memory";
+        return bail(-3);
+    }
+    h->wpb = best_wpb;
+    *out = h;
+    return 0;
+}
+
+void tdvmc_gpu_destroy(tdvmc_gpu_handle* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    for (auto& t : h->pending)
+    {
+        cudaEventDestroy(t.e0);
+        cudaEventDestroy(t.e1);
+    }
+    for (auto e : h->event_pool) cudaEventDestroy(e);
+    if (h->h_est) cudaFreeHost(h->h_est);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int tdvmc_gpu_set_positions(tdvmc_gpu_handle* h, const double* R, int32_t first, int32_t n)
+{
+    if (!h || !R || first < 0 || n < 0 || first + n > h->W) return h ? fail(h, "set_positions: bad range") : -1;
+    CK(cudaSetDevice(h->device));
+    const size_t cnt = (size_t)n * h->N * 3;
+    CK(cudaMemcpyAsync(h->d_aos.p, R, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(launch_transpose_in(h->d_aos.p, h->d_pos.p + (size_t)first * 3 * h->Np, n, h->N, h->Np, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int tdvmc_gpu_get_positions(tdvmc_gpu_handle* h, double* R, int32_t first, int32_t n)
+{
+    if (!h || !R || first < 0 || n < 0 || first + n > h->W) return h ? fail(h, "get_positions: bad range") : -1;
+    CK(cudaSetDevice(h->device));
+    const size_t cnt = (size_t)n * h->N * 3;
+    CK(launch_transpose_out(h->d_pos.p + (size_t)first * 3 * h->Np, h->d_aos.p, n, h->N, h->Np, h->stream));
+    CK(cudaMemcpyAsync(R, h->d_aos.p, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int tdvmc_gpu_set_params(tdvmc_gpu_handle* h, const double* uR, const double* uI, double phiR, double phiI, double time)
+{
+    if (!h || !uR || !uI) return h ? fail(h, "set_params: null argument") : -1;
+    CK(cudaSetDevice(h->device));
+    h->uR.assign(uR, uR + h->P);
+    h->uI.assign(uI, uI + h->P);
+    h->phiR = phiR;
+    h->phiI = phiI;
+    h->time = time;
+    h->params_set = true;
+    return build_param_tables(h);
+}
+
+int tdvmc_gpu_wrap_positions(tdvmc_gpu_handle* h)
+{
+    if (!h) return -1;
+    CK(cudaSetDevice(h->device));
+    Timed t(h, TDVMC_KERNEL_OTHER);
+    CK(launch_wrap(h->sysdev(), h->d_pos.p, h->W, h->stream));
+    return 0;
+}
+
+static int do_sweep(tdvmc_gpu_handle* h, long long n_steps)
+{
+    if (n_steps <= 0) return 0;
+    SweepArgs a;
+    a.s = h->sysdev();
+    a.pos = h->d_pos.p;
+    a.accepted = h->d_accepted.p;
+    a.W = h->W;
+    a.first_walker = h->first_walker;
+    a.wpb = h->wpb;
+    a.npp = h->npp;
+    a.pos_offset = 0;
+    a.seed = h->seed;
+    a.first_step = h->step_counter;
+    a.n_steps = n_steps;
+    a.mc_step = h->mc_step;
+    {
+        Timed t(h, TDVMC_KERNEL_SWEEP);
+        CK(launch_sweep(a, h->stream));
+    }
+    h->step_counter += (uint64_t)n_steps;
+    h->trials_local += (uint64_t)n_steps * (uint64_t)h->W;
+    return 0;
+}
+
+int tdvmc_gpu_sweep(tdvmc_gpu_handle* h, int64_t n_steps)
+{
+    if (!h) return -1;
+    if (int rc = need_params(h)) return rc;
+    CK(cudaSetDevice(h->device));
+    return do_sweep(h, n_steps);
+}
+
+static int do_evaluate_walkers(tdvmc_gpu_handle* h, const double* pos, int n_cfg, long long row0)
+{
+    EvalArgs a;
+    memset(&a, 0, sizeof(a));
+    a.s = h->sysdev();
+    a.pos = pos;
+    a.n_cfg = n_cfg;
+    a.A = h->d_A.p;
+    a.lda = h->lda;
+    a.row0 = row0;
+    a.row_stride = 1;
+    a.other = h->d_other.p;
+    a.exponent = h->d_exponent.p;
+    Timed t(h, TDVMC_KERNEL_EVALUATE);
+    CK(launch_evaluate(a, h->stream));
+    return 0;
+}
+
+static int do_accumulate(tdvmc_gpu_handle* h, const double* A, const double* other, long long M)
+{
+    const long long rows_pad = ((M + kAccChunkRows - 1) / kAccChunkRows) * kAccChunkRows;
+    AccArgs a;
+    a.A = A;
+    a.lda = h->lda;
+    a.ncols = h->P + 3;
+    a.n_chunks = rows_pad / kAccChunkRows;
+    a.n_cta = (int)std::max(1ll, std::min((long long)h->sm_count, a.n_chunks / 4));
+    a.partial = h->d_scratch.p;
+    a.ldc = h->ldc;
+    AccFinishArgs f;
+    f.partial = h->d_scratch.p;
+    f.n_cta = a.n_cta;
+    f.ldc = h->ldc;
+    f.P = h->P;
+    f.other = other;
+    f.M = M;
+    f.n_other = h->n_other;
+    f.accepted = h->d_accepted.p;
+    f.W = h->W;
+    f.n_trials = (double)h->trials_local;
+    f.est = h->d_est.p;
+    {
+        Timed t(h, TDVMC_KERNEL_ACCUMULATE);
+        CK(launch_accumulate(a, h->stream));
+    }
+    {
+        Timed t(h, TDVMC_KERNEL_OTHER);
+        CK(launch_acc_finish(f, h->stream));
+    }
+    h->rows_used = M;
+    h->est_valid = true;
+    return 0;
+}
+
+int tdvmc_gpu_sample_and_accumulate(tdvmc_gpu_handle* h, int32_t n_samples, int32_t n_therm, int32_t n_init)
+{
+    if (!h) return -1;
+    if (int rc = need_params(h)) return rc;
+    if (n_samples < 1 || n_samples > h->max_samples || n_therm < 0 || n_init < 0)
+        return fail(h, "sample_and_accumulate: n_samples exceeds max_samples_per_walker or negative step count");
+    CK(cudaSetDevice(h->device));
+    const long long M = (long long)n_samples * h->W;
+    const long long rows_pad = ((M + kAccChunkRows - 1) / kAccChunkRows) * kAccChunkRows;
+    if (rows_pad > M) // rows beyond M must be zero for the padded SYRK chunks
+        CK(cudaMemsetAsync(h->d_A.p + (size_t)M * h->lda, 0, (size_t)(rows_pad - M) * h->lda * sizeof(double), h->stream));
+    if (int rc = do_sweep(h, n_init)) return rc; // MC_NINITIALIZATIONSTEPS, src/TDVMC.cpp:1068-1071
+    for (int m = 0; m < n_samples; m++)
+    {
+        if (int rc = do_sweep(h, n_therm)) return rc; // src/TDVMC.cpp:1075-1078
+        if (int rc = do_evaluate_walkers(h, h->d_pos.p, h->W, (long long)m * h->W)) return rc; // :1080
+        if (h->keep_positions)                                                                 // :1082-1091
+            CK(cudaMemcpyAsync(h->d_samp_pos.p + (size_t)m * h->W * 3 * h->Np, h->d_pos.p, (size_t)h->W * 3 * h->Np * sizeof(double),
+                               cudaMemcpyDeviceToDevice, h->stream));
+    }
+    if (h->keep_positions) h->stored_samples = n_samples;
+    return do_accumulate(h, h->d_A.p, h->d_other.p, M); // :1103-1109
+}
+
+int tdvmc_gpu_reevaluate_stored(tdvmc_gpu_handle* h)
+{
+    if (!h) return -1;
+    if (int rc = need_params(h)) return rc;
+    if (!h->keep_positions || h->stored_samples < 1) return fail(h, "reevaluate_stored: no stored samples (keep_sample_positions)");
+    CK(cudaSetDevice(h->device));
+    const long long M = (long long)h->stored_samples * h->W;
+    if (int rc = do_evaluate_walkers(h, h->d_samp_pos.p, (int)M, 0)) return rc; // src/TDVMC.cpp:1244-1262
+    return do_accumulate(h, h->d_A.p, h->d_other.p, M);
+}
+
+int tdvmc_gpu_allreduce_and_fetch(tdvmc_gpu_handle* h, tdvmc_estimators* out)
+{
+    if (!h || !out) return h ? fail(h, "allreduce_and_fetch: null argument") : -1;
+    if (!h->est_valid) return fail(h, "allreduce_and_fetch: nothing accumulated yet");
+    CK(cudaSetDevice(h->device));
+    if (h->comm)
+    {
+        int rc = g_nccl.AllReduce(h->d_est.p, h->d_est.p, h->est_len, kNcclDouble, kNcclSum, h->comm, h->stream);
+        if (rc != 0) return fail(h, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"), rc);
+    }
+    CK(cudaMemcpyAsync(h->h_est, h->d_est.p, h->est_len * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->est_valid = !h->comm; // an in-place all-reduce must not be applied twice
+    const int P = h->P;
+    const double* S = h->h_est;
+    const double* FR = S + (size_t)P * P;
+    const double* FI = FR + P;
+    const double* O = FI + P;
+    const double* E = O + P;
+    const double* oth = E + 2;
+    const double* cnt = oth + h->n_other;
+    const double n = cnt[2];
+    if (!(n > 0.0)) return fail(h, "allreduce_and_fetch: zero samples");
+    const double inv = 1.0 / n; // ReduceToAverage: sum over ranks / numOfProcesses (src/MPIMethods.h:199-203)
+    if (out->local_operators_matrix)
+        for (size_t i = 0; i < (size_t)P * P; i++) out->local_operators_matrix[i] = S[i] * inv;
+    for (int k = 0; k < P; k++)
+    {
+        if (out->local_operator_energy_r) out->local_operator_energy_r[k] = FR[k] * inv;
+        if (out->local_operator_energy_i) out->local_operator_energy_i[k] = FI[k] * inv;
+        if (out->local_operators) out->local_operators[k] = O[k] * inv;
+    }
+    if (out->local_energy_r) *out->local_energy_r = E[0] * inv;
+    if (out->local_energy_i) *out->local_energy_i = E[1] * inv;
+    if (out->other_expectation_values)
+        for (int k = 0; k < h->n_other; k++) out->other_expectation_values[k] = oth[k] * inv;
+    out->n_acceptances = (int64_t)llround(cnt[0]);
+    out->n_trials = (int64_t)llround(cnt[1]);
+    out->n_samples = (int64_t)llround(n);
+    return 0;
+}
+
+int tdvmc_gpu_last_exponent(tdvmc_gpu_handle* h, double* exponent)
+{
+    if (!h || !exponent) return -1;
+    if (h->rows_used < 1) return fail(h, "last_exponent: no sample evaluated yet");
+    CK(cudaSetDevice(h->device));
+    const long long row = h->rows_used - h->W; // first local walker, last sample
+    CK(cudaMemcpyAsync(exponent, h->d_exponent.p + row, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int tdvmc_gpu_comm_unique_id(uint8_t id[TDVMC_GPU_UNIQUE_ID_BYTES])
+{
+    std::string err;
+    if (!load_nccl(err))
+    {
+        g_create_error = err;
+        return -1;
+    }
+    UniqueId u;
+    memset(&u, 0, sizeof(u));
+    int rc = g_nccl.GetUniqueId(&u);
+    if (rc != 0)
+    {
+        g_create_error = "ncclGetUniqueId failed";
+        return rc;
+    }
+    memcpy(id, u.internal, TDVMC_GPU_UNIQUE_ID_BYTES);
+    return 0;
+}
+
+int tdvmc_gpu_comm_init(tdvmc_gpu_handle* h, const uint8_t id[TDVMC_GPU_UNIQUE_ID_BYTES], int32_t rank, int32_t n_ranks)
+{
+    if (!h || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return h ? fail(h, "comm_init: bad arguments") : -1;
+    CK(cudaSetDevice(h->device));
+    h->rank = rank;
+    h->n_ranks = n_ranks;
+    if (n_ranks == 1) return 0;
+    std::string err;
+    if (!load_nccl(err)) return fail(h, err);
+    UniqueId u;
+    memcpy(u.internal, id, TDVMC_GPU_UNIQUE_ID_BYTES);
+    int rc = g_nccl.CommInitRank(&h->comm, n_ranks, u, rank);
+    if (rc != 0)
+    {
+        h->comm = nullptr;
+        return fail(h, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"), rc);
+    }
+    return 0;
+}
+
+// ---- fixed-configuration entry points ----
+
+int tdvmc_gpu_evaluate_fixed(tdvmc_gpu_handle* h, const double* R, int32_t n_cfg, double* e_r, double* e_i, double* O,
+                             double* other, double* exponent, double* drift_r, double* drift_i, double* spline_sums,
+                             double* outer)
+{
+    if (!h || !R || n_cfg < 1) return h ? fail(h, "evaluate_fixed: bad arguments") : -1;
+    if (int rc = need_params(h)) return rc;
+    CK(cudaSetDevice(h->device));
+    const int N = h->N, P = h->P, K = h->K;
+    DevBuf<double> aos, pos, A, oth, ex, dr, di, ss, out;
+    CK(aos.alloc((size_t)n_cfg * N * 3));
+    CK(pos.alloc((size_t)n_cfg * 3 * h->Np));
+    CK(A.alloc((size_t)n_cfg * h->lda));
+    CK(oth.alloc((size_t)n_cfg * h->n_other));
+    CK(ex.alloc(n_cfg));
+    CK(dr.alloc((size_t)n_cfg * N * 3));
+    CK(di.alloc((size_t)n_cfg * N * 3));
+    CK(ss.alloc((size_t)n_cfg * K));
+    CK(out.alloc(n_cfg));
+    CK(cudaMemsetAsync(pos.p, 0, pos.n * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(oth.p, 0, oth.n * sizeof(double), h->stream));
+    CK(cudaMemcpyAsync(aos.p, R, aos.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(launch_transpose_in(aos.p, pos.p, n_cfg, N, h->Np, h->stream));
+    EvalArgs a;
+    memset(&a, 0, sizeof(a));
+    a.s = h->sysdev();
+    a.pos = pos.p;
+    a.n_cfg = n_cfg;
+    a.A = A.p;
+    a.lda = h->lda;
+    a.row0 = 0;
+    a.row_stride = 1;
+    a.other = oth.p;
+    a.exponent = ex.p;
+    a.drift_r = dr.p;
+    a.drift_i = di.p;
+    a.ss_out = ss.p;
+    a.outer_out = out.p;
+    {
+        Timed t(h, TDVMC_KERNEL_EVALUATE);
+        CK(launch_evaluate(a, h->stream));
+    }
+    std::vector<double> hA((size_t)n_cfg * h->lda);
+    CK(cudaMemcpyAsync(hA.data(), A.p, hA.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (other) CK(cudaMemcpyAsync(other, oth.p, oth.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (exponent) CK(cudaMemcpyAsync(exponent, ex.p, ex.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (drift_r) CK(cudaMemcpyAsync(drift_r, dr.p, dr.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (drift_i) CK(cudaMemcpyAsync(drift_i, di.p, di.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (spline_sums) CK(cudaMemcpyAsync(spline_sums, ss.p, ss.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (outer) CK(cudaMemcpyAsync(outer, out.p, out.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int c = 0; c < n_cfg; c++)
+    {
+        const double* row = &hA[(size_t)c * h->lda];
+        if (O) memcpy(O + (size_t)c * P, row, sizeof(double) * P);
+        if (e_r) e_r[c] = row[P];
+        if (e_i) e_i[c] = row[P + 1];
+    }
+    return 0;
+}
+
+int tdvmc_gpu_quotient_fixed(tdvmc_gpu_handle* h, const double* R, const double* moves, int32_t n_moves, double* quotient,
+                             double* delta)
+{
+    if (!h || !R || !moves || n_moves < 1) return h ? fail(h, "quotient_fixed: bad arguments") : -1;
+    if (int rc = need_params(h)) return rc;
+    CK(cudaSetDevice(h->device));
+    for (int m = 0; m < n_moves; m++)
+        if (moves[4 * m] < 0 || moves[4 * m] >= h->N) return fail(h, "quotient_fixed: particle index out of range");
+    DevBuf<double> aos, pos, mv, dl;
+    CK(aos.alloc((size_t)h->N * 3));
+    CK(pos.alloc((size_t)3 * h->Np));
+    CK(mv.alloc((size_t)n_moves * 4));
+    CK(dl.alloc(n_moves));
+    CK(cudaMemsetAsync(pos.p, 0, pos.n * sizeof(double), h->stream));
+    CK(cudaMemcpyAsync(aos.p, R, aos.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(mv.p, moves, mv.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(launch_transpose_in(aos.p, pos.p, 1, h->N, h->Np, h->stream));
+    QuotientArgs a;
+    a.s = h->sysdev();
+    a.pos = pos.p;
+    a.moves = mv.p;
+    a.n_moves = n_moves;
+    a.delta = dl.p;
+    CK(launch_quotient(a, h->stream));
+    std::vector<double> d(n_moves);
+    CK(cudaMemcpyAsync(d.data(), dl.p, sizeof(double) * n_moves, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int m = 0; m < n_moves; m++)
+    {
+        if (delta) delta[m] = d[m];
+        if (quotient) quotient[m] = exp(2.0 * d[m]); // BosonsBulk.cpp:652
+    }
+    return 0;
+}
+
+static int run_tables(tdvmc_gpu_handle* h, const double* pos, int n_cfg)
+{
+    CK(h->d_T.ensure((size_t)n_cfg * h->N * h->K * 4));
+    CK(h->d_vint.ensure(n_cfg));
+    CK(h->d_tab_e.ensure((size_t)n_cfg * 7));
+    TableArgs a;
+    a.s = h->sysdev();
+    a.pos = pos;
+    a.n_cfg = n_cfg;
+    a.T = h->d_T.p;
+    a.v_int = h->d_vint.p;
+    Timed t(h, TDVMC_KERNEL_TABLES);
+    CK(launch_tables(a, h->stream));
+    return 0;
+}
+
+static int run_contract(tdvmc_gpu_handle* h, int n_cfg)
+{
+    ContractArgs a;
+    a.s = h->sysdev();
+    a.T = h->d_T.p;
+    a.v_int = h->d_vint.p;
+    a.n_cfg = n_cfg;
+    a.e_r = h->d_tab_e.p;
+    a.e_i = h->d_tab_e.p + n_cfg;
+    a.sums = h->d_tab_e.p + 2 * (size_t)n_cfg;
+    Timed t(h, TDVMC_KERNEL_CONTRACT);
+    CK(launch_contract(a, h->stream));
+    return 0;
+}
+
+int tdvmc_gpu_tables_fixed(tdvmc_gpu_handle* h, const double* R, double* sD, double* sD2)
+{
+    if (!h || !R) return h ? fail(h, "tables_fixed: bad arguments") : -1;
+    if (int rc = need_params(h)) return rc;
+    CK(cudaSetDevice(h->device));
+    const int N = h->N, K = h->K;
+    DevBuf<double> aos, pos;
+    CK(aos.alloc((size_t)N * 3));
+    CK(pos.alloc((size_t)3 * h->Np));
+    CK(cudaMemsetAsync(pos.p, 0, pos.n * sizeof(double), h->stream));
+    CK(cudaMemcpyAsync(aos.p, R, aos.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(launch_transpose_in(aos.p, pos.p, 1, N, h->Np, h->stream));
+    if (int rc = run_tables(h, pos.p, 1)) return rc;
+    std::vector<double> T((size_t)N * K * 4);
+    CK(cudaMemcpyAsync(T.data(), h->d_T.p, T.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int n = 0; n < N; n++)
+        for (int k = 0; k < K; k++)
+        {
+            const double* t = &T[((size_t)n * K + k) * 4];
+            if (sD)
+                for (int a = 0; a < 3; a++) sD[((size_t)k * N + n) * 3 + a] = t[a]; // reference layout [k][n][a]
+            if (sD2) sD2[(size_t)k * N + n] = t[3];
+        }
+    return 0;
+}
+
+int tdvmc_gpu_tables_resident(tdvmc_gpu_handle* h, int32_t n_walkers)
+{
+    if (!h || n_walkers < 1 || n_walkers > h->W) return h ? fail(h, "tables_resident: bad walker count") : -1;
+    if (int rc = need_params(h)) return rc;
+    CK(cudaSetDevice(h->device));
+    return run_tables(h, h->d_pos.p, n_walkers);
+}
+
+int tdvmc_gpu_contract_resident(tdvmc_gpu_handle* h, int32_t n_walkers, double* e_r, double* e_i)
+{
+    if (!h || n_walkers < 1 || n_walkers > h->W) return h ? fail(h, "contract_resident: bad walker count") : -1;
+    if (int rc = need_params(h)) return rc;
+    if (!h->d_T.p || h->d_T.n < (size_t)n_walkers * h->N * h->K * 4) return fail(h, "contract_resident: tables not built");
+    CK(cudaSetDevice(h->device));
+    if (int rc = run_contract(h, n_walkers)) return rc;
+    if (e_r) CK(cudaMemcpyAsync(e_r, h->d_tab_e.p, sizeof(double) * n_walkers, cudaMemcpyDeviceToHost, h->stream));
+    if (e_i) CK(cudaMemcpyAsync(e_i, h->d_tab_e.p + n_walkers, sizeof(double) * n_walkers, cudaMemcpyDeviceToHost, h->stream));
+    if (e_r || e_i) CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int tdvmc_gpu_min_image(tdvmc_gpu_handle* h, double lbox, const double* a, const double* b, int32_t n, double* norm,
+                        double* disp)
+{
+    if (!h || !a || !b || !norm || !disp || n < 1) return h ? fail(h, "min_image: bad arguments") : -1;
+    CK(cudaSetDevice(h->device));
+    DevBuf<double> da, db, dn, dd;
+    CK(da.alloc((size_t)n * 3));
+    CK(db.alloc((size_t)n * 3));
+    CK(dn.alloc(n));
+    CK(dd.alloc((size_t)n * 3));
+    CK(cudaMemcpyAsync(da.p, a, da.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(db.p, b, db.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(launch_min_image(h->sysdev(), lbox, da.p, db.p, n, dn.p, dd.p, h->stream));
+    CK(cudaMemcpyAsync(norm, dn.p, dn.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(disp, dd.p, dd.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int tdvmc_gpu_accumulate_fixed(tdvmc_gpu_handle* h, const double* O, const double* e_r, const double* e_i, int64_t M,
+                               double* S, double* f_r, double* f_i, double* o)
+{
+    if (!h || !O || !e_r || !e_i || M < 1) return h ? fail(h, "accumulate_fixed: bad arguments") : -1;
+    CK(cudaSetDevice(h->device));
+    const int P = h->P;
+    const long long rows_pad = ((M + kAccChunkRows - 1) / kAccChunkRows) * kAccChunkRows;
+    DevBuf<double> dO, dER, dEI, A, oth;
+    CK(dO.alloc((size_t)M * P));
+    CK(dER.alloc(M));
+    CK(dEI.alloc(M));
+    CK(A.alloc((size_t)rows_pad * h->lda));
+    CK(oth.alloc((size_t)M * h->n_other));
+    CK(cudaMemsetAsync(A.p, 0, A.n * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(oth.p, 0, oth.n * sizeof(double), h->stream));
+    CK(cudaMemcpyAsync(dO.p, O, dO.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dER.p, e_r, dER.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dEI.p, e_i, dEI.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(launch_fill_rows(A.p, h->lda, P, dO.p, dER.p, dEI.p, M, h->stream));
+    const long long saved_rows = h->rows_used;
+    if (int rc = do_accumulate(h, A.p, oth.p, M)) return rc;
+    h->rows_used = saved_rows;
+    h->est_valid = false;
+    std::vector<double> est(h->est_len);
+    CK(cudaMemcpyAsync(est.data(), h->d_est.p, est.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (S) memcpy(S, est.data(), sizeof(double) * (size_t)P * P);
+    if (f_r) memcpy(f_r, est.data() + (size_t)P * P, sizeof(double) * P);
+    if (f_i) memcpy(f_i, est.data() + (size_t)P * P + P, sizeof(double) * P);
+    if (o) memcpy(o, est.data() + (size_t)P * P + 2 * P, sizeof(double) * P);
+    return 0;
+}
+
+int tdvmc_gpu_proposals(tdvmc_gpu_handle* h, int32_t global_walker, int64_t first_step, int32_t n, int32_t* particle,
+                        double* disp, double* log_u)
+{
+    if (!h || n < 1 || !particle || !disp || !log_u) return h ? fail(h, "proposals: bad arguments") : -1;
+    CK(cudaSetDevice(h->device));
+    DevBuf<int> dp;
+    DevBuf<double> dd, dl;
+    CK(dp.alloc(n));
+    CK(dd.alloc((size_t)n * 3));
+    CK(dl.alloc(n));
+    CK(launch_proposals(h->seed, (uint32_t)global_walker, (uint64_t)first_step, n, h->N, h->mc_step, dp.p, dd.p, dl.p, h->stream));
+    CK(cudaMemcpyAsync(particle, dp.p, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(disp, dd.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(log_u, dl.p, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---- measurement hooks ----
+
+int tdvmc_gpu_profile(tdvmc_gpu_handle* h, int32_t enable, int32_t reset)
+{
+    if (!h) return -1;
+    CK(cudaSetDevice(h->device));
+    collect_timings(h);
+    if (reset)
+        for (int k = 0; k < TDVMC_KERNEL_COUNT; k++)
+        {
+            h->launches[k] = 0;
+            h->total_ms[k] = 0.0;
+        }
+    h->profiling = enable != 0;
+    return 0;
+}
+
+int tdvmc_gpu_kernel_stats(tdvmc_gpu_handle* h, int32_t kernel_id, int64_t* launches, double* total_ms)
+{
+    if (!h || kernel_id < 0 || kernel_id >= TDVMC_KERNEL_COUNT) return h ? fail(h, "kernel_stats: bad id") : -1;
+    CK(cudaSetDevice(h->device));
+    collect_timings(h);
+    if (launches) *launches = h->launches[kernel_id];
+    if (total_ms) *total_ms = h->total_ms[kernel_id];
+    return 0;
+}
+
+int tdvmc_gpu_synchronize(tdvmc_gpu_handle* h)
+{
+    if (!h) return -1;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int tdvmc_gpu_resident_walkers(tdvmc_gpu_handle* h, int32_t* per_sm, int32_t* sm_count)
+{
+    if (!h) return -1;
+    if (per_sm) *per_sm = h->resident_per_sm;
+    if (sm_count) *sm_count = h->sm_count;
+    return 0;
+}
+
+int tdvmc_gpu_measure_fp64_peak(tdvmc_gpu_handle* h, double* dfma_tflops, double* dmma_tflops)
+{
+    if (!h || !dfma_tflops || !dmma_tflops) return -1;
+    CK(cudaSetDevice(h->device));
+    CK(measure_fp64(dfma_tflops, dmma_tflops, h->stream));
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,166 @@
+// Shared device-side definitions of the walker-ensemble library (sm_100a).
+//
+// The whole library is compiled with -fmad=false: every a*b+c written with operators is a
+// separate IEEE multiply and add, in the association order of the expression, exactly like the
+// reference compiled for baseline x86-64.  Fused operations appear only where fma() is spelled out.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace tdvmc
+{
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
+constexpr int kRecStride = 18;   // doubles per knot-interval record of the evaluation table (bank spreading)
+constexpr int kCubStride = 6;    // doubles per interval record of the sweep table: c0..c3, t_lo, t_hi
+
+// Read-only description of the system as the kernels see it.  Pointers are device memory.
+struct SysDev
+{
+    int N;            // particles
+    int Np;           // padded particle count (SoA row length in HBM)
+    int P;            // parameters
+    int K;            // basis splines
+    int pair_rule;    // TDVMC_PAIR_RULE_*
+    int tail_param;
+    int n_other;
+    int first_bin;    // first knot interval a distance can fall in (knots[first_bin] == 0)
+    int nbins;        // K - first_bin
+    int ncell;        // cells of the uniform bin lookup grid
+    int uniform;      // != 0: knots are a uniform grid, interval index = floor(r / h)
+    double L, Linv, Lhalf;   // LBOX, 1/LBOX, LBOX/2 (src/TDVMC.cpp:535-536)
+    double rmax;             // maxDistance = knots[K]
+    double hbar;             // HBAR2_2M
+    double pot_a, pot_b;     // square well, time switch applied
+    double phiR;
+    double inv_cell;         // ncell / rmax
+    double h, inv_h;         // uniform knot spacing
+    double u_tail;           // uR[tail_param]
+    const double* knots;     // [K+4]
+    const double* rec;       // [nbins][kRecStride]: piece p of spline (bin-p) at [p*4 + c]
+    const double* cub;       // [nbins][kCubStride]: u(r) on the interval in the local coordinate r - t_lo
+    const unsigned short* lut; // [ncell] -> interval index guess
+    const int* map_ptr;
+    const int* map_col;
+    const double* map_val;
+    const double* uR;        // [P]
+    const double* uI;        // [P]
+    const double* utR;       // [K]  parameters in spline space, u~_k = sum_p u_p M[p][k]
+    const double* utI;       // [K]
+};
+
+// ---- minimum image -------------------------------------------------------------------------
+// GetCoordinateNIC (src/Utils.cpp:266-281): round half away from zero through an int cast, and a
+// 1e-10 nudge when the result lands exactly on +-L/2.  Same expressions, same order, no FMA.
+__device__ __forceinline__ double nic_exact(double r, double L, double Linv, double Lhalf)
+{
+    int k = (int)(r * Linv + ((r >= 0.0) ? 0.5 : -0.5));
+    double result = r - k * L;
+    if (result == Lhalf) result -= 1e-10;
+    else if (result == -Lhalf) result += 1e-10;
+    return result;
+}
+
+// VectorDisplacementNIC_3D (src/Utils.cpp:329-338, 368-374): a - b per coordinate, then the norm
+// sqrt(x*x + y*y + z*z) in that association (src/Utils.cpp:174-179, 207-212).
+__device__ __forceinline__ double disp_exact(const SysDev& s, double ax, double ay, double az, double bx, double by,
+                                             double bz, double& vx, double& vy, double& vz)
+{
+    vx = nic_exact(ax - bx, s.L, s.Linv, s.Lhalf);
+    vy = nic_exact(ay - by, s.L, s.Linv, s.Lhalf);
+    vz = nic_exact(az - bz, s.L, s.Linv, s.Lhalf);
+    return sqrt(vx * vx + vy * vy + vz * vz);
+}
+
+// std::lower_bound(nodes, r) - 1  <=>  knots[bin] < r <= knots[bin+1]  (BosonsBulk.cpp:197-198).
+// A uniform lookup grid gives the starting guess, two short loops make it exact.
+__device__ __forceinline__ int find_bin_exact(const SysDev& s, const double* knots, const unsigned short* lut, double r)
+{
+    int c = (int)(r * s.inv_cell);
+    c = max(0, min(c, s.ncell - 1));
+    int b = lut[c];
+    while (b < s.K - 1 && r > knots[b + 1]) b++;
+    while (b > s.first_bin && !(knots[b] < r)) b--;
+    return b;
+}
+
+// ---- warp / block reductions ------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+    return v;
+}
+
+__device__ __forceinline__ int warp_sum_int(int v)
+{
+    return __reduce_add_sync(FULL_MASK, v);
+}
+
+// ---- Philox4x32-10 proposal stream (same definition as oracle_proposal in oracle/tdvmc_oracle.c) ----
+struct Philox4
+{
+    uint32_t x, y, z, w;
+};
+
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                          uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int round = 0; round < 10; round++)
+    {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    Philox4 r = { c0, c1, c2, c3 };
+    return r;
+}
+
+__host__ __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) // (0, 1]
+{
+    uint64_t x = (((uint64_t)hi << 32) | lo) >> 11;
+    return ((double)x + 1.0) * (1.0 / 9007199254740992.0);
+}
+
+struct Proposal
+{
+    int particle;
+    double dx, dy, dz;
+    double log_u;
+};
+
+// Replaces randomParticleIndex() + DIM x randomNormal(MC_STEP) + random01() of DoMetropolisStep
+// (src/TDVMC.cpp:870-875, 900) by a counter-based stream: a pure function of (seed, walker, step).
+__device__ __forceinline__ Proposal make_proposal(uint64_t seed, uint32_t walker, uint64_t step, int n_particles,
+                                                  double mc_step)
+{
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    uint32_t s0 = (uint32_t)step, s1 = (uint32_t)(step >> 32);
+    Philox4 a = philox4x32_10(s0, s1, walker, 0u, k0, k1);
+    Philox4 b = philox4x32_10(s0, s1, walker, 1u, k0, k1);
+    Philox4 c = philox4x32_10(s0, s1, walker, 2u, k0, k1);
+    Proposal p;
+    p.particle = (int)(((uint64_t)a.x * (uint64_t)n_particles) >> 32);
+    p.log_u = log(u53(a.y, a.z));
+    const double two_pi = 6.283185307179586476925286766559;
+    double rad0 = sqrt(-2.0 * log(u53(a.w, b.x)));
+    double ang0 = two_pi * (u53(b.y, b.z) - 1.0 / 9007199254740992.0);
+    double rad1 = sqrt(-2.0 * log(u53(b.w, c.x)));
+    double ang1 = two_pi * (u53(c.y, c.z) - 1.0 / 9007199254740992.0);
+    double s, co;
+    sincos(ang0, &s, &co);
+    p.dx = rad0 * co * mc_step;
+    p.dy = rad0 * s * mc_step;
+    p.dz = rad1 * cos(ang1) * mc_step;
+    return p;
+}
+
+} // namespace tdvmc

@@ -1,0 +1,318 @@
+// K2 + K3 + K4 fused — evaluate one configuration per thread block, nothing materialised.
+//
+// Replaces, per sample, CalculateLocalOperators / RefreshLocalOperators (BosonsBulk.cpp:158-218),
+// CalculateOtherLocalOperators (:220-336) and CalculateExpectationValues (:349-458) (and their
+// NUBosonsBulkPB twins, NUBosonsBulkPB.cpp:219-277, 279-414, 427-560).
+//
+// The reference first fills sD[k][n][a] and sD2[k][n] (2.2 MB per sample at N=343, K=203) and then
+// contracts them with u.  Both steps are linear, so the contraction is done on the fly:
+//     F_n   = sum_i  e_ni  * sum_p u~[bin-p] B'_{bin-p}(r_ni)
+//     lap_n = sum_i          sum_p u~[bin-p] (B''_{bin-p}(r_ni) + (D-1)/r_ni B'_{bin-p}(r_ni))
+// with u~ = M^T u (boundary-condition map applied to the parameters).  Per-term arithmetic keeps the
+// reference's expressions and association (the monomial table in absolute r is ill-conditioned, so
+// a different evaluation order would differ from the reference at the 1e-10 level); only the order
+// of the sums over particles differs.
+//
+// Thread n owns particle n and walks over all partners i (positions broadcast from shared memory).
+// The basis sums ss[k] (needed for O_k) are a histogram over knot intervals; each warp keeps a
+// private copy and adds to it without atomics: lanes whose pair falls into the same interval are
+// ranked with match.any and take turns, so every round touches distinct addresses.
+#include "kernels.cuh"
+
+namespace tdvmc
+{
+
+// Conflict-free warp-cooperative  hist[bin - p] += v[p], p = 0..3  for the lanes with active == true.
+// Must be called by all 32 lanes.  Lanes sharing a bin are serialised by their rank within the group;
+// the four pieces are separated by __syncwarp() because bin-p of one lane aliases bin'-p' of another.
+__device__ __forceinline__ void warp_hist_add4(double* hist, int bin, bool active, const double (&v)[4], int lane)
+{
+    const unsigned amask = __ballot_sync(FULL_MASK, active);
+    if (amask == 0u) return;
+    const int key = active ? bin : (-1 - lane);
+    const unsigned peers = __match_any_sync(FULL_MASK, key);
+    const int rank = __popc(peers & ((1u << lane) - 1u));
+    for (int round = 0;; round++)
+    {
+        const bool mine = active && (rank == round);
+        if (__ballot_sync(FULL_MASK, mine) == 0u) break;
+#pragma unroll
+        for (int p = 0; p < 4; p++)
+        {
+            if (mine) hist[bin - p] += v[p];
+            __syncwarp();
+        }
+    }
+}
+
+struct EvalSmem
+{
+    double* knots;
+    double* rec;
+    double* utR;
+    double* utI;
+    double* px;
+    double* py;
+    double* pz;
+    double* hist;
+    double* sstot;
+    double* red;
+    unsigned short* lut;
+};
+
+struct SmemCarver
+{
+    unsigned char* base;
+    size_t off;
+    __host__ __device__ double* take(size_t n_doubles)
+    {
+        double* p = reinterpret_cast<double*>(base + off);
+        off += ((n_doubles + 1) & ~(size_t)1) * sizeof(double);
+        return p;
+    }
+};
+
+__host__ __device__ inline size_t eval_smem_layout(const SysDev& s, int nwarps, EvalSmem* out, unsigned char* base)
+{
+    SmemCarver c = { base, 0 };
+    const int Npad = (s.N + 1) & ~1;
+    EvalSmem m;
+    m.knots = c.take(s.K + 4);
+    m.rec = c.take((size_t)s.nbins * kRecStride);
+    m.utR = c.take(s.K);
+    m.utI = c.take(s.K);
+    m.px = c.take(Npad);
+    m.py = c.take(Npad);
+    m.pz = c.take(Npad);
+    m.hist = c.take((size_t)nwarps * s.K);
+    m.sstot = c.take(s.K);
+    m.red = c.take((size_t)nwarps * 8);
+    m.lut = reinterpret_cast<unsigned short*>(base + c.off);
+    c.off += ((size_t)s.ncell * sizeof(unsigned short) + 15) & ~(size_t)15;
+    if (out) *out = m;
+    return c.off;
+}
+
+template <bool REFLECT>
+__global__ void __launch_bounds__(384) evaluate_kernel(EvalArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SysDev& s = a.s;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const int cfg = blockIdx.x;
+    const int N = s.N, K = s.K, P = s.P;
+
+    EvalSmem m;
+    eval_smem_layout(s, nwarps, &m, smem_raw);
+
+    for (int i = tid; i < K + 4; i += blockDim.x) m.knots[i] = s.knots[i];
+    for (int i = tid; i < s.nbins * kRecStride; i += blockDim.x) m.rec[i] = s.rec[i];
+    for (int i = tid; i < K; i += blockDim.x)
+    {
+        m.utR[i] = s.utR[i];
+        m.utI[i] = s.utI[i];
+    }
+    for (int i = tid; i < s.ncell; i += blockDim.x) m.lut[i] = s.lut[i];
+    const double* gpos = a.pos + (size_t)cfg * 3 * s.Np;
+    for (int i = tid; i < N; i += blockDim.x)
+    {
+        m.px[i] = gpos[i];
+        m.py[i] = gpos[s.Np + i];
+        m.pz[i] = gpos[2 * s.Np + i];
+    }
+    for (int i = tid; i < nwarps * K; i += blockDim.x) m.hist[i] = 0.0;
+    __syncthreads();
+
+    double* hist = m.hist + (size_t)warp * K;
+    const double rmax = s.rmax;
+    const double pot_a = s.pot_a;
+
+    double R1 = 0.0, I1 = 0.0, RI = 0.0, lapR = 0.0, lapI = 0.0;
+    int vcount = 0, outer = 0;
+
+    for (int n0 = warp * 32; n0 < N; n0 += blockDim.x)
+    {
+        const int n = n0 + lane;
+        const bool valid = n < N;
+        const double xn = valid ? m.px[n] : 0.0, yn = valid ? m.py[n] : 0.0, zn = valid ? m.pz[n] : 0.0;
+        double fRx = 0.0, fRy = 0.0, fRz = 0.0, fIx = 0.0, fIy = 0.0, fIz = 0.0;
+
+        for (int i = 0; i < N; i++)
+        {
+            double vx, vy, vz;
+            double r = disp_exact(s, xn, yn, zn, m.px[i], m.py[i], m.pz[i], vx, vy, vz); // R[n] - R[i]
+            const bool pair = valid && (i != n);
+            bool inside;
+            if (REFLECT)
+            {
+                if (!(r < rmax)) r = 2 * rmax - r; // NUBosonsBulkPB.cpp:250-253, 331-335
+                inside = r < rmax;
+            }
+            else
+            {
+                inside = r <= rmax; // BosonsBulk.cpp:195, 257
+            }
+            const bool act = pair && inside;
+            const bool lower = act && (i < n);
+            if (pair && !inside && (i < n)) outer++; // BosonsBulk.cpp:207-210
+            if (lower && (r < pot_a)) vcount++;      // BosonsBulk.cpp:268-271
+
+            int bin = 0;
+            double val[4] = { 0.0, 0.0, 0.0, 0.0 };
+            if (act)
+            {
+                bin = find_bin_exact(s, m.knots, m.lut, r);
+                const double* w = m.rec + (size_t)(bin - s.first_bin) * kRecStride;
+                const double r2 = r * r;
+                const double rinv = 1.0 / r;
+                const double f2 = 2.0 * rinv; // (DIM - 1) / r, BosonsBulk.cpp:319-322
+                double gR = 0.0, gI = 0.0;
+#pragma unroll
+                for (int p = 0; p < 4; p++)
+                {
+                    const double2 w01 = *reinterpret_cast<const double2*>(w + p * 4);
+                    const double2 w23 = *reinterpret_cast<const double2*>(w + p * 4 + 2);
+                    const double d1 = w01.y + 2.0 * w23.x * r + 3.0 * w23.y * r2; // BosonsBulk.cpp:299
+                    const double d2 = 2.0 * w23.x + 6.0 * w23.y * r;              // BosonsBulk.cpp:301
+                    const double uRk = m.utR[bin - p], uIk = m.utI[bin - p];
+                    const double t2 = d2 + f2 * d1;
+                    gR = fma(uRk, d1, gR);
+                    gI = fma(uIk, d1, gI);
+                    lapR = fma(uRk, t2, lapR);
+                    lapI = fma(uIk, t2, lapI);
+                    if (lower) val[p] = w01.x + w01.y * r + w23.x * r2 + w23.y * (r2 * r); // BosonsBulk.cpp:204
+                }
+                const double ex = vx * rinv, ey = vy * rinv, ez = vz * rinv; // unreflected vec / (reflected) r
+                fRx = fma(gR, ex, fRx);
+                fRy = fma(gR, ey, fRy);
+                fRz = fma(gR, ez, fRz);
+                fIx = fma(gI, ex, fIx);
+                fIy = fma(gI, ey, fIy);
+                fIz = fma(gI, ez, fIz);
+            }
+            warp_hist_add4(hist, bin, lower, val, lane);
+        }
+
+        if (valid)
+        {
+            R1 += fRx * fRx + fRy * fRy + fRz * fRz;          // VectorNorm2, BosonsBulk.cpp:418-419
+            I1 += fIx * fIx + fIy * fIy + fIz * fIz;
+            RI += fRx * fIx + fRy * fIy + fRz * fIz;          // kineticSumR1I1 / 2, BosonsBulk.cpp:417
+            if (a.drift_r)
+            {
+                double* d = a.drift_r + ((size_t)cfg * N + n) * 3;
+                d[0] = fRx; d[1] = fRy; d[2] = fRz;
+            }
+            if (a.drift_i)
+            {
+                double* d = a.drift_i + ((size_t)cfg * N + n) * 3;
+                d[0] = fIx; d[1] = fIy; d[2] = fIz;
+            }
+        }
+    }
+
+    // block reduction (fixed order -> deterministic)
+    R1 = warp_sum(R1);
+    I1 = warp_sum(I1);
+    RI = warp_sum(RI);
+    lapR = warp_sum(lapR);
+    lapI = warp_sum(lapI);
+    vcount = warp_sum_int(vcount);
+    outer = warp_sum_int(outer);
+    if (lane == 0)
+    {
+        double* r = m.red + warp * 8;
+        r[0] = R1; r[1] = I1; r[2] = RI; r[3] = lapR; r[4] = lapI; r[5] = (double)vcount; r[6] = (double)outer;
+    }
+    __syncthreads();
+
+    for (int k = tid; k < K; k += blockDim.x)
+    {
+        double t = 0.0;
+        for (int w = 0; w < nwarps; w++) t += m.hist[(size_t)w * K + k];
+        m.sstot[k] = t;
+        if (a.ss_out) a.ss_out[(size_t)cfg * K + k] = t;
+    }
+    __syncthreads();
+
+    const long long row = a.row0 + (long long)cfg * a.row_stride;
+    double* Arow = a.A + (size_t)row * a.lda;
+    double epart = 0.0;
+    for (int p = tid; p < P; p += blockDim.x)
+    {
+        double o = 0.0;
+        for (int j = s.map_ptr[p]; j < s.map_ptr[p + 1]; j++) o += s.map_val[j] * m.sstot[s.map_col[j]]; // BosonsBulk.cpp:158-177
+        Arow[p] = o;
+        epart = fma(s.uR[p], o, epart); // BosonsBulk.cpp:526-529
+    }
+    epart = warp_sum(epart);
+    if (lane == 0) m.red[warp * 8 + 7] = epart;
+    __syncthreads();
+
+    if (tid == 0)
+    {
+        double t[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+        for (int w = 0; w < nwarps; w++)
+            for (int q = 0; q < 8; q++) t[q] += m.red[w * 8 + q];
+        const double outer_sum = t[6];
+        const double v_int = s.pot_b * t[5];
+        const double exponent = t[7] + s.uR[s.tail_param] * outer_sum; // BosonsBulk.cpp:532-536
+        const double kR1 = t[0], kI1 = t[1], kRI = 2.0 * t[2], kR2 = t[3], kI2 = t[4];
+        const double kin_r = -(kR1 - kI1 + kR2) * s.hbar; // BosonsBulk.cpp:422
+        const double kin_i = -(kRI + kI2) * s.hbar;       // BosonsBulk.cpp:423
+        const double e_r = kin_r + v_int;                 // :425, external potential is zero (:344-347)
+        const double e_i = kin_i;
+        Arow[P] = e_r;
+        Arow[P + 1] = e_i;
+        Arow[P + 2] = 1.0;
+        double* o = a.other + (size_t)row * s.n_other;   // BosonsBulk.cpp:449-457
+        o[0] = kin_r;
+        o[1] = v_int;
+        o[2] = exp(exponent + s.phiR);
+        o[3] = exponent;
+        o[4] = kR1;
+        o[5] = kI1;
+        o[6] = kR2;
+        o[7] = kI2;
+        o[8] = kRI;
+        if (a.exponent) a.exponent[row] = exponent;
+        if (a.outer_out) a.outer_out[cfg] = outer_sum;
+    }
+}
+
+int evaluate_threads(const SysDev& s)
+{
+    int t = ((s.N + 31) / 32) * 32;
+    return t > 384 ? 384 : t;
+}
+
+size_t evaluate_smem_bytes(const SysDev& s)
+{
+    return eval_smem_layout(s, evaluate_threads(s) / 32, nullptr, nullptr);
+}
+
+cudaError_t launch_evaluate(const EvalArgs& a, cudaStream_t st)
+{
+    if (a.n_cfg <= 0) return cudaSuccess;
+    const int threads = evaluate_threads(a.s);
+    const size_t smem = evaluate_smem_bytes(a.s);
+    cudaError_t e;
+    if (a.s.pair_rule == 1)
+    {
+        e = cudaFuncSetAttribute(evaluate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        evaluate_kernel<true><<<a.n_cfg, threads, smem, st>>>(a);
+    }
+    else
+    {
+        e = cudaFuncSetAttribute(evaluate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        evaluate_kernel<false><<<a.n_cfg, threads, smem, st>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+} // namespace tdvmc

@@ -1,0 +1,124 @@
+// Kernel argument blocks and host-side launchers of the walker-ensemble library.
+#pragma once
+
+#include "common.cuh"
+
+namespace tdvmc
+{
+
+constexpr int kSweepMaxThreads = 512;
+
+// ---- K1: Metropolis sweep (sweep.cu) ----
+struct SweepArgs
+{
+    SysDev s;
+    double* pos;                  // [W][3][Np]
+    unsigned long long* accepted; // [W]
+    int W;                        // local walkers
+    int first_walker;             // global id of local walker 0
+    int wpb;                      // walkers (= warps) per block
+    int npp;                      // padded row length of the shared-memory position arrays
+    int pos_offset;               // byte offset of the position arrays in dynamic shared memory
+    uint64_t seed;
+    uint64_t first_step;          // per-walker step counter at launch (same for every walker)
+    long long n_steps;
+    double mc_step;
+};
+cudaError_t launch_sweep(SweepArgs a, cudaStream_t st);
+int sweep_blocks_per_sm(const SysDev& s, int wpb, int npp);
+
+// ---- K2+K3+K4: fused evaluation of one configuration per block (evaluate.cu) ----
+struct EvalArgs
+{
+    SysDev s;
+    const double* pos;      // [n_cfg][3][Np]
+    int n_cfg;
+    // sample row of configuration c: row0 + c * row_stride
+    double* A;              // [rows][lda]: O_0..O_{P-1}, E^R, E^I, 1, 0...
+    int lda;
+    long long row0, row_stride;
+    double* other;          // [rows][n_other]
+    double* exponent;       // [rows] or null
+    double* drift_r;        // [n_cfg][N][3] or null
+    double* drift_i;
+    double* ss_out;         // [n_cfg][K] or null
+    double* outer_out;      // [n_cfg] or null
+};
+cudaError_t launch_evaluate(const EvalArgs& a, cudaStream_t st);
+
+// single-particle move ratios for scripted moves of one configuration (quotient_fixed)
+struct QuotientArgs
+{
+    SysDev s;
+    const double* pos;   // [3][Np]
+    const double* moves; // [n][4]
+    int n_moves;
+    double* delta;       // [n] exponentNew - exponent
+};
+cudaError_t launch_quotient(const QuotientArgs& a, cudaStream_t st);
+
+// ---- K3 (table form) and K4 (contraction from tables): reference semantics (tables.cu) ----
+struct TableArgs
+{
+    SysDev s;
+    const double* pos;   // [n_cfg][3][Np]
+    int n_cfg;
+    double* T;           // [n_cfg][N][K][4] = {sD_x, sD_y, sD_z, sD2}
+    double* v_int;       // [n_cfg]
+};
+cudaError_t launch_tables(const TableArgs& a, cudaStream_t st);
+
+struct ContractArgs
+{
+    SysDev s;
+    const double* T;     // [n_cfg][N][K][4]
+    const double* v_int; // [n_cfg]
+    int n_cfg;
+    double* e_r;         // [n_cfg]
+    double* e_i;
+    double* sums;        // [n_cfg][5] = R1, I1, R2, I2, R1I1 (or null)
+};
+cudaError_t launch_contract(const ContractArgs& a, cudaStream_t st);
+
+// ---- K5: S / F accumulation, FP64 tensor-core SYRK on the augmented sample matrix (accumulate.cu) ----
+constexpr int kAccChunkRows = 32;  // samples per TMA stage
+constexpr int kAccMaxTiles = 26;   // 8x8 output tiles per dimension -> P + 3 <= 208
+struct AccArgs
+{
+    const double* A;      // [rows_padded][lda], rows beyond M are zero
+    int lda;              // row stride in doubles, lda % 16 == 4
+    int ncols;            // P + 3 used columns
+    long long n_chunks;   // rows_padded / kAccChunkRows
+    int n_cta;
+    double* partial;      // [n_cta][ldc][ldc], ldc = 8 * ceil(ncols / 8)
+    int ldc;
+};
+cudaError_t launch_accumulate(const AccArgs& a, cudaStream_t st);
+
+struct AccFinishArgs
+{
+    const double* partial;
+    int n_cta, ldc, P;
+    const double* other;  // [M][n_other]
+    long long M;
+    int n_other;
+    const unsigned long long* accepted; // [W]
+    int W;
+    double n_trials;      // proposals since the counters were cleared, this rank
+    double* est;          // packed: S[P*P] | F_R[P] | F_I[P] | O[P] | E_R | E_I | other[n_other] | acc | trials | samples
+};
+cudaError_t launch_acc_finish(const AccFinishArgs& a, cudaStream_t st);
+
+// ---- small utilities (util.cu) ----
+cudaError_t launch_wrap(const SysDev& s, double* pos, int W, cudaStream_t st);
+cudaError_t launch_min_image(const SysDev& s, double L, const double* a, const double* b, int n, double* norm, double* disp,
+                             cudaStream_t st);
+cudaError_t launch_proposals(uint64_t seed, uint32_t walker, uint64_t first_step, int n, int n_particles, double mc_step,
+                             int* particle, double* disp, double* log_u, cudaStream_t st);
+cudaError_t launch_transpose_in(const double* aos, double* soa, int n_cfg, int N, int Np, cudaStream_t st);  // [c][N][3] -> [c][3][Np]
+cudaError_t launch_transpose_out(const double* soa, double* aos, int n_cfg, int N, int Np, cudaStream_t st);
+cudaError_t launch_fill_rows(double* A, int lda, int P, const double* O, const double* e_r, const double* e_i, long long M,
+                             cudaStream_t st);
+cudaError_t measure_fp64(double* dfma_tflops, double* dmma_tflops, cudaStream_t st);
+
+} // namespace tdvmc

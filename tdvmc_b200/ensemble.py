@@ -1,0 +1,77 @@
+"""Host-side mirror of the reference's per-rank estimator loops on top of the CUDA library.
+
+Same names, argument meaning and results as the reference's L3 entry points (src/TDVMC.cpp):
+
+    ParallelUpdateExpectationValues(R, uR, uI, phiR, phiI)                  :1152-1220
+    ParallelUpdateExpectationValuesForGivenSamples(samples, uR, uI, ...)    :1305-1330
+    DoMetropolisSteps(R, uR, uI, phiR, phiI, n)                             :918-924
+    MoveCoordinatesToFirstCell(R)                                           :787-796
+
+with one difference in kind: the reference owns ONE walker per rank and loops MC_NSTEPS samples
+over it, this class owns ``n_walkers`` device-resident walkers per GPU and draws MC_NSTEPS samples
+from each.  The seven estimator arrays come back under the reference's global names
+(src/TDVMC.cpp:147-153).  Everything here calls libtdvmc_b200.so; there is no CPU path.
+"""
+import numpy as np
+
+from . import capi
+from .estimators import shard_walkers
+
+
+class GpuEnsembleSystem:
+    def __init__(self, spec, n_walkers_total, mc_step, seed=1, rank=0, world=1, device=None, mc_nsteps=1,
+                 update_samples_every_nth_step=0, unique_id=None):
+        self.spec = spec
+        self.rank, self.world = rank, world
+        self.first_walker, self.n_local = shard_walkers(n_walkers_total, rank, world)
+        self.n_walkers_total = n_walkers_total
+        self.handle = capi.Handle(spec, self.n_local, seed=seed, mc_step=mc_step, first_walker=self.first_walker,
+                                  max_samples=mc_nsteps, keep_sample_positions=update_samples_every_nth_step > 0,
+                                  device=rank if device is None else device)
+        if world > 1:
+            if unique_id is None:
+                raise ValueError("world > 1 needs the NCCL unique id of rank 0 (capi.comm_unique_id(), broadcast by the host)")
+            self.handle.comm_init(unique_id, rank, world)
+
+    # -- state ------------------------------------------------------------------------------
+    def SetPositions(self, R):
+        """R: [n_local][N][3] (this rank's walkers)."""
+        self.handle.set_positions(R)
+
+    def GetPositions(self):
+        return self.handle.get_positions()
+
+    def BroadcastNewParameters(self, uR, uI, phiR, phiI, time=0.0):
+        """Every rank passes the same values (the reference broadcasts from root, :506-512)."""
+        self.handle.set_params(uR, uI, phiR, phiI, time)
+
+    def MoveCoordinatesToFirstCell(self):
+        self.handle.wrap_positions()
+
+    def DoMetropolisSteps(self, n):
+        self.handle.sweep(n)
+
+    # -- estimator loops ----------------------------------------------------------------------
+    def ParallelUpdateExpectationValues(self, uR, uI, phiR, phiI, MC_NSTEPS, MC_NTHERMSTEPS, MC_NINITIALIZATIONSTEPS=0,
+                                        time=0.0):
+        self.handle.set_params(uR, uI, phiR, phiI, time)
+        self.handle.sample_and_accumulate(MC_NSTEPS, MC_NTHERMSTEPS, MC_NINITIALIZATIONSTEPS)
+        return self._fetch()
+
+    def ParallelUpdateExpectationValuesForGivenSamples(self, uR, uI, phiR, phiI, time=0.0):
+        self.handle.set_params(uR, uI, phiR, phiI, time)
+        self.handle.reevaluate_stored()
+        return self._fetch()
+
+    def GetExponent(self):
+        return self.handle.last_exponent()
+
+    def _fetch(self):
+        o = self.handle.allreduce_and_fetch()
+        return dict(localOperators=o["O"], localEnergyR=float(o["e_r"][0]), localEnergyI=float(o["e_i"][0]),
+                    localOperatorsMatrix=o["S"], localOperatorlocalEnergyR=o["OER"], localOperatorlocalEnergyI=o["OEI"],
+                    otherExpectationValues=o["other"], nAcceptances=o["n_acceptances"], nTrials=o["n_trials"],
+                    nSamples=o["n_samples"])
+
+    def close(self):
+        self.handle.close()

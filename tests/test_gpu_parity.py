@@ -1,0 +1,293 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against reference fixtures and the pinned oracle.
+
+Tolerances: fixed-configuration E_L, drift and O_k within 1e-10 relative (north_star); the
+single-move quotient within 1e-7 -- the sweep evaluates the SAME polynomial the reference's table
+defines, but in a well-conditioned local form, while the reference's own monomial evaluation
+carries ~1e-10 absolute error per pair term (coefficients up to 4e6), which accumulates over the
+2(N-1) terms of a move.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle_lib import Oracle
+from tdvmc_b200 import systems
+
+pytestmark = pytest.mark.gpu
+
+EVAL_CASES = ["bosonsbulk_n64_fixture", "bosonsbulk_n64_equil", "bosonsbulk_n343_lattice", "bosonsbulk_n343_equil",
+              "nubosonsbulkpb_n216_equil"]
+RTOL = 1e-10
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from tdvmc_b200 import capi as c
+
+    c.load()
+    assert c.load().tdvmc_gpu_device_count() > 0, "no CUDA device: the GPU tests have no fallback"
+    return c
+
+
+def make_handle(capi, g, n_walkers=4, **kw):
+    spec = systems.from_golden(g)
+    h = capi.Handle(spec, n_walkers, **kw)
+    h.set_params(g["uR"], g["uI"], float(g["phiR"]), float(g["phiI"]), float(g["time"]))
+    return spec, h
+
+
+def test_min_image_known_answers_and_reference_bits(capi, golden):
+    g0 = golden("bosonsbulk_n64_fixture")
+    _, h = make_handle(capi, g0)
+    here = os.path.dirname(os.path.abspath(__file__))
+    cases = [c for c in json.load(open(os.path.join(here, "golden", "min_image_known_answers.json")))["cases"]]
+    for L in (4.0, 5.0):
+        sub = [c for c in cases if c["L"] == L]
+        a = np.array([c["a"] + [0.0] * (3 - len(c["a"])) for c in sub])
+        b = np.array([c["b"] + [0.0] * (3 - len(c["b"])) for c in sub])
+        norm, disp = h.min_image(L, a, b)
+        for c, n, d in zip(sub, norm, disp):
+            assert abs(n - c["norm"]) < 1e-9, c           # src/test/Tests.h:11
+            for k, want in enumerate(c["disp"]):
+                assert abs(d[k] - want) < 1e-9, c
+    g = golden("min_image_reference")
+    for L in np.unique(g["L"]):
+        m = g["L"] == L
+        norm, disp = h.min_image(float(L), g["a"][m], g["b"][m])
+        assert np.array_equal(norm, g["norm"][m])         # same IEEE operations in the same order
+        assert np.array_equal(disp, g["disp"][m])
+    h.close()
+
+
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_fixed_configuration_energy_drift_operators(capi, golden, name):
+    g = golden(name)
+    spec, h = make_handle(capi, g)
+    r = h.evaluate_fixed(g["R"])
+    assert rel(r["ss"][0], g["spline_sums"]) < 1e-13
+    assert r["outer"][0] == float(g["outer_sum"])
+    assert rel(r["O"][0], g["local_operators"]) < RTOL
+    assert abs(r["exponent"][0] - float(g["exponent"])) < RTOL * abs(float(g["exponent"]))
+    assert abs(r["e_r"][0] - float(g["local_energy_r"])) < RTOL * abs(float(g["local_energy_r"]))
+    assert abs(r["e_i"][0] - float(g["local_energy_i"])) < RTOL * abs(float(g["local_energy_i"]))
+    assert rel(r["drift_r"][0], g["drift_r"]) < RTOL
+    assert rel(r["drift_i"][0], g["drift_i"]) < RTOL
+    want = g["other_expectation_values"]
+    got = r["other"][0]
+    assert got.shape == want.shape
+    for k in range(9):
+        assert abs(got[k] - want[k]) <= RTOL * max(abs(want[k]), 1e-300), (k, got[k], want[k])
+    assert np.all(got[9:] == 0.0) and np.all(want[9:] == 0.0)
+    h.close()
+
+
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_tables_match_reference(capi, golden, name):
+    g = golden(name)
+    spec, h = make_handle(capi, g)
+    sD, sD2 = h.tables_fixed(g["R"])
+    wn = g["table_checksum_weights"]
+    assert rel(np.einsum("n,kna->ka", wn, sD), g["sD_checksum"]) < 1e-12
+    assert rel(np.einsum("n,kn->k", wn, sD2), g["sD2_checksum"]) < 1e-12
+    if "sD" in g:
+        assert rel(sD, g["sD"]) < 1e-13 and rel(sD2, g["sD2"]) < 1e-13
+    else:
+        idx = g["table_particles"]
+        assert rel(sD[:, idx, :], g["sD_subset"]) < 1e-13
+        assert rel(sD2[:, idx], g["sD2_subset"]) < 1e-13
+    h.close()
+
+
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_scripted_move_quotient(capi, golden, name):
+    g = golden(name)
+    spec, h = make_handle(capi, g)
+    q, d = h.quotient_fixed(g["R"], g["moves"])
+    d_ref = g["move_exponent_new"] - float(g["exponent"])
+    assert np.max(np.abs(d - d_ref)) < 5e-8
+    assert np.max(np.abs(q / g["move_quotient"] - 1.0)) < 1e-7
+    h.close()
+
+
+def test_contract_from_tables_matches_fused(capi, golden):
+    g = golden("bosonsbulk_n343_equil")
+    spec, h = make_handle(capi, g, n_walkers=3)
+    R = np.stack([g["R"], g["R"] + 0.01, np.roll(g["R"], 1, axis=0)])
+    h.set_positions(R)
+    r = h.evaluate_fixed(R)
+    h.tables_resident(3)
+    e_r, e_i = h.contract_resident(3)
+    assert rel(e_r, r["e_r"]) < 1e-11 and rel(e_i, r["e_i"]) < 1e-11
+    h.close()
+
+
+def test_proposal_stream_matches_oracle(capi, golden):
+    g = golden("bosonsbulk_n64_fixture")
+    spec, h = make_handle(capi, g, seed=1234567890123, mc_step=0.4)
+    o = Oracle(spec)
+    p, d, lu = h.proposals(global_walker=5, first_step=(1 << 32) - 3, n=64)
+    for i in range(64):
+        p2, d2, lu2 = o.proposal(1234567890123, 5, (1 << 32) - 3 + i, 0.4)
+        assert p[i] == p2
+        assert np.allclose(d[i], d2, rtol=1e-13, atol=1e-15)
+        assert abs(lu[i] - lu2) <= 1e-13 * max(1.0, abs(lu2))
+    h.close()
+
+
+@pytest.mark.parametrize("name,n_steps", [("bosonsbulk_n64_equil", 640), ("nubosonsbulkpb_n216_equil", 432)])
+def test_sweep_replays_oracle_chain(capi, golden, name, n_steps):
+    """Same proposal stream, same accept rule: the device chain follows the oracle chain move for move."""
+    g = golden(name)
+    W, seed, mc_step, first = 3, 77, 0.35, 10
+    spec, h = make_handle(capi, g, n_walkers=W, seed=seed, mc_step=mc_step, first_walker=first)
+    o = Oracle(spec, time=float(g["time"]))
+    R0 = np.stack([g["R"] + 0.003 * w for w in range(W)])
+    h.set_positions(R0)
+    h.sweep(n_steps // 2)
+    h.sweep(n_steps - n_steps // 2)          # the stream is a function of the step counter, not of the launch
+    R_gpu = h.get_positions()
+    acc_gpu = None
+    for w in range(W):
+        R_ref, acc = o.sweep(R0[w], g["uR"], seed, first + w, 0, n_steps, mc_step)
+        assert np.max(np.abs(R_gpu[w] - R_ref)) < 1e-9, w
+    h.close()
+
+
+def test_sample_and_accumulate_matches_oracle(capi, golden):
+    g = golden("bosonsbulk_n64_equil")
+    W, seed, mc_step = 5, 9, 0.4
+    n_samples, n_therm, n_init = 3, 64, 32
+    spec, h = make_handle(capi, g, n_walkers=W, seed=seed, mc_step=mc_step, max_samples=n_samples)
+    o = Oracle(spec, time=float(g["time"]))
+    R0 = np.stack([g["R"] + 0.002 * w for w in range(W)])
+    h.set_positions(R0)
+    h.sample_and_accumulate(n_samples, n_therm, n_init)
+    got = h.allreduce_and_fetch()
+    est = np.zeros(o.est_size())
+    acc = 0
+    for w in range(W):
+        r = o.sample_walker(R0[w], g["uR"], g["uI"], float(g["phiR"]), seed, w, 0, n_init, n_samples, n_therm, mc_step, est)
+        acc += r["accepted"]
+    want = o.unpack_est(est, W * n_samples)
+    assert got["n_samples"] == W * n_samples
+    assert got["n_trials"] == W * (n_init + n_samples * n_therm)
+    assert got["n_acceptances"] == acc
+    assert rel(got["O"], want["O"]) < 1e-9
+    assert abs(got["e_r"][0] - want["e_r"]) < 1e-9 * abs(want["e_r"])
+    assert abs(got["e_i"][0] - want["e_i"]) < 1e-9 * abs(want["e_i"])
+    assert rel(got["S"], want["S"]) < 1e-9
+    assert rel(got["OER"], want["OER"]) < 1e-9
+    assert rel(got["OEI"], want["OEI"]) < 1e-9
+    assert rel(got["other"][[0, 1, 3, 4, 5, 6, 7, 8]], want["other"][[0, 1, 3, 4, 5, 6, 7, 8]]) < 1e-9
+    assert abs(h.last_exponent() - o.evaluate(h.get_positions()[0], g["uR"], g["uI"])["exponent"]) < 1e-9
+    h.close()
+
+
+@pytest.mark.parametrize("M,P_case", [(1, "bosonsbulk_n64_fixture"), (33, "bosonsbulk_n64_fixture"),
+                                       (4096 + 17, "bosonsbulk_n343_equil"), (20000, "nubosonsbulkpb_n216_equil")])
+def test_accumulate_fixed_matches_numpy(capi, golden, M, P_case):
+    g = golden(P_case)
+    spec, h = make_handle(capi, g)
+    P = spec.n_params
+    rng = np.random.default_rng(2)
+    O = rng.normal(50.0 + np.arange(P), 5.0, size=(M, P))
+    e_r = rng.normal(-3.0, 1.0, M)
+    e_i = rng.normal(0.5, 0.2, M)
+    S, fr, fi, o = h.accumulate_fixed(O, e_r, e_i)
+    Ol = O.astype(np.longdouble)
+    assert rel(S, (Ol.T @ Ol).astype(float)) < 1e-13
+    assert rel(fr, (Ol.T @ e_r.astype(np.longdouble)).astype(float)) < 1e-13
+    assert rel(fi, (Ol.T @ e_i.astype(np.longdouble)).astype(float)) < 1e-13
+    assert rel(o, Ol.sum(axis=0).astype(float)) < 1e-13
+    assert np.array_equal(S, S.T)
+    h.close()
+
+
+def test_ensemble_statistics_match_reference_sampler(capi, golden):
+    """Energies agree with the reference's own sampler within stated error bars (north_star level 2)."""
+    g = golden("bosonsbulk_n64_mc")
+    spec = systems.bosons_bulk(int(g["N"]), float(g["LBOX"]), int(g["N_PARAM"]), g["SYSTEM_PARAMS"])
+    W = 512
+    h = capi.Handle(spec, W, seed=2024, mc_step=float(g["MC_STEP"]), max_samples=8)
+    h.set_params(g["uR"], g["uI"], 0.0, 0.0, 0.0)
+    h.set_positions(np.broadcast_to(g["R0"], (W, spec.n_particles, 3)).copy())
+    h.sample_and_accumulate(8, int(g["n_therm"]), 64 * 100)
+    got = h.allreduce_and_fetch()
+    er = g["energy_r_series"]
+    nb = 20
+    b = er[:len(er) // nb * nb].reshape(nb, -1).mean(axis=1)
+    m_ref, s_ref = b.mean(), b.std(ddof=1) / np.sqrt(nb)
+    var = np.var(er)                                              # per-sample variance from the reference series
+    s_gpu = np.sqrt(var / (W * 8)) * 2.0                          # x2: 8 consecutive samples are correlated
+    assert abs(got["e_r"][0] - m_ref) < 4.0 * np.hypot(s_ref, s_gpu), (got["e_r"][0], m_ref, s_ref, s_gpu)
+    acc = got["n_acceptances"] / got["n_trials"]
+    assert abs(acc - float(g["acceptance"])) < 0.01
+    scale = np.abs(g["local_operators"]).max()
+    assert np.max(np.abs(got["O"] - g["local_operators"])) / scale < 0.01
+    h.close()
+
+
+def test_full_size_properties(capi, golden):
+    """BASELINE size (N=343, P=201): size-independent properties of the resident path."""
+    g = golden("bosonsbulk_n343_equil")
+    W = 64
+    spec, h = make_handle(capi, g, n_walkers=W, seed=3, mc_step=0.5, max_samples=2, keep_sample_positions=True)
+    R0 = np.broadcast_to(g["R"], (W, 343, 3)).copy()
+    h.set_positions(R0)
+    assert np.array_equal(h.get_positions(), R0)                  # layout round trip
+    h.sample_and_accumulate(2, 343, 100)
+    a = h.allreduce_and_fetch()
+    assert a["n_samples"] == 2 * W and a["n_trials"] == W * (100 + 2 * 343)
+    assert 0.2 < a["n_acceptances"] / a["n_trials"] < 0.95
+    assert np.array_equal(a["S"], a["S"].T)
+    # Cauchy-Schwarz / positivity of the second-moment matrix
+    ev = np.linalg.eigvalsh(a["S"] - np.outer(a["O"], a["O"]))
+    assert ev.min() > -1e-8 * ev.max()
+    # sum_k O_k = number of pairs inside the cut (partition of unity of the B-spline basis) -> bounded by N(N-1)/2
+    assert a["O"].sum() <= 343 * 342 / 2 * (1 + 1e-4)
+    # re-evaluating the stored samples at unchanged parameters reproduces the estimators
+    h.reevaluate_stored()
+    b = h.allreduce_and_fetch()
+    for k in ("O", "S", "OER", "OEI", "e_r", "e_i"):
+        assert rel(b[k], a[k]) < 1e-13, k
+    # fixed evaluation of the final positions equals the last stored sample rows on average
+    Rf = h.get_positions()
+    ev2 = h.evaluate_fixed(Rf[:4])
+    o = Oracle(spec)
+    ref = o.evaluate(Rf[0], g["uR"], g["uI"], float(g["phiR"]))
+    assert abs(ev2["e_r"][0] - ref["e_r"]) < RTOL * abs(ref["e_r"])
+    assert rel(ev2["O"][0], ref["O"]) < RTOL
+    # periodic images: shifting every particle by a lattice vector leaves E_L unchanged
+    shift = np.array([7.0, -14.0, 7.0])
+    ev3 = h.evaluate_fixed(Rf[:1] + shift)
+    assert abs(ev3["e_r"][0] - ev2["e_r"][0]) < 1e-9 * abs(ev2["e_r"][0])
+    # wrap keeps distances: energies after MoveCoordinatesToFirstCell are unchanged
+    h.wrap_positions()
+    Rw = h.get_positions()
+    assert np.all(np.abs(Rw) <= 3.5 + 1e-9)
+    ev4 = h.evaluate_fixed(Rw[:1])
+    assert abs(ev4["e_r"][0] - ev2["e_r"][0]) < 1e-9 * abs(ev2["e_r"][0])
+    h.close()
+
+
+def test_errors_are_loud(capi, golden):
+    g = golden("bosonsbulk_n64_fixture")
+    spec = systems.from_golden(g)
+    h = capi.Handle(spec, 2)
+    with pytest.raises(capi.TdvmcError):
+        h.sweep(10)                                   # parameters not set
+    h.set_params(g["uR"], g["uI"])
+    with pytest.raises(capi.TdvmcError):
+        h.sample_and_accumulate(5, 1, 0)              # exceeds max_samples_per_walker
+    with pytest.raises(capi.TdvmcError):
+        h.allreduce_and_fetch()                       # nothing accumulated
+    with pytest.raises(capi.TdvmcError):
+        h.reevaluate_stored()                         # no stored samples
+    h.close()

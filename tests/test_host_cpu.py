@@ -1,0 +1,170 @@
+"""CPU-only tests: host logic, C-ABI surface, multi-rank reduction semantics (gloo)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle_lib import Oracle
+from tdvmc_b200 import estimators, splines, systems
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lib_path():
+    path = os.path.join(ROOT, "tdvmc_b200", "libtdvmc_b200.so")
+    if not os.path.exists(path):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "tdvmc_b200", "csrc"), "-j8"])
+    return path
+
+
+def test_library_exports_every_declared_symbol():
+    """Every function include/tdvmc_gpu.h declares is exported by the built library and bound in capi.py."""
+    from tdvmc_b200 import capi
+
+    header = open(os.path.join(ROOT, "include", "tdvmc_gpu.h")).read()
+    declared = set(re.findall(r"\b(tdvmc_gpu_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 25
+    lib = C.CDLL(_lib_path())
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == {n for n, _, _ in capi.SYMBOLS}
+    assert capi.load().tdvmc_gpu_abi_version() == 1
+
+
+def test_struct_layouts_match_header_sizes():
+    from tdvmc_b200 import capi
+
+    # 8 int32 + 2 double + 6 pointers + 2 int32 ; uint32 + 5 int32 + uint64 + double ; 7 pointers + 3 int64
+    assert C.sizeof(capi.SystemDesc) == 8 * 4 + 2 * 8 + 6 * 8 + 2 * 4
+    assert C.sizeof(capi.EnsembleDesc) == 6 * 4 + 8 + 8
+    assert C.sizeof(capi.Estimators) == 7 * 8 + 3 * 8
+
+
+def test_no_cpu_fallback_without_a_device(golden):
+    from tdvmc_b200 import capi
+
+    lib = capi.load()
+    if lib.tdvmc_gpu_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    spec = systems.from_golden(golden("bosonsbulk_n64_fixture"))
+    with pytest.raises(capi.TdvmcError, match="no CUDA device"):
+        capi.Handle(spec, 4)
+
+
+def test_product_package_never_touches_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "tdvmc_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "liboracle" not in text and "oracle_lib" not in text and "tdvmc_oracle.h" not in text, f
+
+
+@pytest.mark.parametrize("name", ["bosonsbulk_n343_equil", "nubosonsbulkpb_n216_equil", "bosonsbulk_n64_fixture"])
+def test_spline_builder_against_reference_table(golden, name):
+    g = golden(name)
+    w_ref = g["spline_weights"]
+    w = splines.bspline_monomial_weights(g["knots"])
+    assert w.shape == w_ref.shape
+    # coefficient-level agreement; the reference's closed forms lose ~3e-12 relative to cancellation
+    scale = np.abs(w_ref).max(axis=2, keepdims=True)
+    assert np.max(np.abs(w - w_ref) / scale) < 1e-10
+    # partition of unity of our table on (0, r_max)
+    knots = g["knots"]
+    K = len(knots) - 4
+    for r in np.linspace(knots[3] + 1e-6, knots[K] - 1e-6, 97):
+        b = int(np.searchsorted(knots, r, side="left")) - 1
+        tot = sum(np.polyval(w[b - p, p, ::-1], r) for p in range(4))
+        assert abs(tot - 1.0) < 1e-7
+
+
+def test_system_builders_reproduce_reference_setup(golden):
+    for name in ("bosonsbulk_n343_equil", "nubosonsbulkpb_n216_equil"):
+        g = golden(name)
+        spec = systems.from_golden(g)                    # asserts bit-equal knots
+        assert spec.r_max == float(g["max_distance"])
+        o = Oracle(spec)
+        assert np.allclose(o.local_operators(g["spline_sums"]), g["local_operators"], rtol=1e-15, atol=0)
+    with pytest.raises(ValueError):
+        systems.bosons_bulk(8, 4.0, 10, nurbs_grid=np.linspace(0, 2, 5))
+
+
+def test_shard_walkers_is_a_partition():
+    for total in (1, 7, 8, 4096, 4736):
+        for world in (1, 2, 3, 8):
+            got = [estimators.shard_walkers(total, r, world) for r in range(world)]
+            ids = [i for f, n in got for i in range(f, f + n)]
+            assert ids == list(range(total))
+            assert max(n for _, n in got) - min(n for _, n in got) <= 1
+
+
+def test_estimator_layout_roundtrip():
+    lay = estimators.EstimatorLayout(5, 9)
+    rng = np.random.default_rng(0)
+    S = rng.normal(size=(5, 5))
+    buf = lay.pack(S, rng.normal(size=5), rng.normal(size=5), np.arange(5.0), 3.0, -1.0, np.arange(9.0), 10, 40, 4)
+    assert buf.size == lay.size == 25 + 15 + 2 + 9 + 3
+    av = lay.averages(buf)
+    assert np.allclose(av["localOperatorsMatrix"], S / 4)
+    assert av["localEnergyR"] == 0.75 and av["nTrials"] == 40 and av["nSamples"] == 4
+    assert np.allclose(av["localOperators"], np.arange(5.0) / 4)
+
+
+_WORKER = r"""
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+from oracle_lib import Oracle
+from tdvmc_b200 import estimators, systems
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+g = np.load(os.path.join(sys.argv[1], "tests", "golden", "bosonsbulk_n64_equil.npz"))
+spec = systems.from_golden(g)
+o = Oracle(spec, time=float(g["time"]))
+W, n_samples, n_therm = 6, 2, 32
+first, n_local = estimators.shard_walkers(W, rank, world)
+lay = estimators.EstimatorLayout(spec.n_params, 9)
+est = np.zeros(o.est_size()); acc = 0
+for w in range(first, first + n_local):
+    r = o.sample_walker(g["R"] + 0.002 * w, g["uR"], g["uI"], float(g["phiR"]), 9, w, 0, 16, n_samples, n_therm, 0.4, est)
+    acc += r["accepted"]
+u = o.unpack_est(est, 1.0)
+buf = lay.pack(u["S"], u["OER"], u["OEI"], u["O"], u["e_r"], u["e_i"], u["other"], acc, n_local * (16 + n_samples * n_therm),
+               n_local * n_samples)
+buf = estimators.allreduce_sum(buf)
+if rank == 0:
+    np.save(sys.argv[2], buf)
+dist.destroy_process_group()
+"""
+
+
+def _run_world(tmp_path, world, tag):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    out = tmp_path / f"est_{tag}.npy"
+    port = 29500 + (os.getpid() % 2000) + world
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT, str(out)], env=env))
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    return np.load(out)
+
+
+def test_two_rank_reduction_equals_single_rank(tmp_path):
+    """Walkers sharded over 2 gloo ranks + one packed all-reduce == the same ensemble on one rank
+    (Philox streams are keyed by GLOBAL walker id, averages divide by the GLOBAL sample count)."""
+    one = _run_world(tmp_path, 1, "w1")
+    two = _run_world(tmp_path, 2, "w2")
+    lay = estimators.EstimatorLayout(33, 9)
+    a, b = lay.averages(one), lay.averages(two)
+    assert a["nSamples"] == b["nSamples"] == 12 and a["nTrials"] == b["nTrials"] and a["nAcceptances"] == b["nAcceptances"]
+    for k in ("localOperators", "localOperatorsMatrix", "localOperatorlocalEnergyR", "localOperatorlocalEnergyI",
+              "otherExpectationValues"):
+        assert np.allclose(a[k], b[k], rtol=1e-13, atol=1e-13), k
+    assert abs(a["localEnergyR"] - b["localEnergyR"]) < 1e-12 * abs(a["localEnergyR"])
