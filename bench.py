@@ -1,0 +1,417 @@
+#!/usr/bin/env python3
+"""Headline benchmark: walker-steps/s of the walker-parallel sampling + evaluation path.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path on the host cores
+
+Workload (BASELINE.json configs[2]): config/BosonsBulk3D.config scaled to N=343, LBOX=7, N_PARAM=201.
+One "step" is one ParallelUpdateExpectationValues pass (src/TDVMC.cpp:1152-1188) with the config's own
+sample counts: MC_NINITIALIZATIONSTEPS=1000 + MC_NSTEPS=2 x MC_NTHERMSTEPS=5000 Metropolis proposals
+per walker, 2 evaluations per walker, the S/F accumulation, the packed all-reduce and the fetch of
+the seven estimator arrays.  value = proposals of all walkers on all GPUs / time (walker-steps/s).
+
+Prints ONE JSON line (rank 0).  Under torchrun (N > 1) every rank drives one GPU; walkers are
+sharded (fixed count per GPU -> "weak"), the only collective is the packed NCCL all-reduce.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from tdvmc_b200 import systems  # noqa: E402
+
+# config/BosonsBulk3D.config, scaled as BASELINE.json configs[2] says
+N, LBOX, N_PARAM = 343, 7.0, 201
+MC_STEP, MC_NSTEPS, MC_NTHERMSTEPS, MC_NINIT = 0.5, 2, 5000, 1000
+SYSTEM_PARAMS = [1.0, 1.0]
+STEPS_PER_WALKER = MC_NINIT + MC_NSTEPS * MC_NTHERMSTEPS
+# algorithmic work per unit
+FLOP_PER_WALKER_STEP = 2 * (N - 1) * (22 + 1 + 6)          # 19 836
+FLOP_PER_EVALUATION = 5.0e6
+BYTES_PER_TABLE = 8 * 203 * N * 4 + 24 * N                  # 2 236 360 (K3 table kernel)
+METRIC = "walker-steps/s"
+
+
+def golden_spec():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "bosonsbulk_n343_equil.npz"))
+    spec = systems.bosons_bulk(N, LBOX, N_PARAM, SYSTEM_PARAMS, weights=g["spline_weights"])
+    assert np.array_equal(spec.knots, g["knots"])
+    uR, uI = systems.smooth_params(N_PARAM, LBOX / 2)
+    return spec, uR, uI, g["R"]
+
+
+def workload_config(extra=None):
+    c = {"workload": "BosonsBulk3D.config scaled to N=343 (LBOX=7, N_PARAM=201): ParallelUpdateExpectationValues pass",
+         "N": N, "LBOX": LBOX, "N_PARAM": N_PARAM, "MC_STEP": MC_STEP, "MC_NSTEPS": MC_NSTEPS,
+         "MC_NTHERMSTEPS": MC_NTHERMSTEPS, "MC_NINITIALIZATIONSTEPS": MC_NINIT,
+         "proposals_per_walker_per_step": STEPS_PER_WALKER,
+         "spline_table": "reference SplineFactory::GetWeights3 output (tests/golden/bosonsbulk_n343_equil.npz)"}
+    c.update(extra or {})
+    return c
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the unmodified reference (oracle/_ref/ref_harness) on the host cores
+# ------------------------------------------------------------------------------------------------
+def physical_cores():
+    allowed = sorted(os.sched_getaffinity(0))
+    seen, cpus = set(), []
+    for c in allowed:
+        try:
+            sib = open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list").read().strip()
+        except OSError:
+            sib = str(c)
+        if sib not in seen:
+            seen.add(sib)
+            cpus.append(c)
+    return cpus
+
+
+def write_reference_case(path, spec, uR, uI, R, seed):
+    with open(path, "w") as f:
+        f.write("system BosonsBulk\n")
+        f.write(f"configdir {ROOT}/oracle/_ref/config/\n")
+        for k, v in dict(N=N, DIM=3, LBOX=LBOX, N_PARAM=N_PARAM, MC_STEP=MC_STEP, MC_NSTEPS=MC_NSTEPS,
+                         MC_NTHERMSTEPS=MC_NTHERMSTEPS, MC_NINITIALIZATIONSTEPS=MC_NINIT, seed=seed).items():
+            f.write(f"{k} {v!r}\n")
+        for k, v in dict(R=R, uR=uR, uI=uI, SYSTEM_PARAMS=SYSTEM_PARAMS).items():
+            f.write(k + " " + " ".join(repr(float(x)) for x in np.asarray(v).ravel()) + "\n")
+
+
+def reference_step(cases, cpus):
+    """Every host core runs ONE walker's pass (1000 + 2 x 5000 proposals, 2 evaluations + the reference's
+    estimator accumulation) through the reference's own code; returns (proposals, seconds of the slowest)."""
+    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    procs = []
+    for case, cpu in zip(cases, cpus):
+        cmd = ["taskset", "-c", str(cpu), harness, "bench", case]
+        procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True))
+    trials, secs = 0, 0.0
+    for p in procs:
+        out = p.communicate()[0].split()
+        if p.returncode != 0 or len(out) < 3:
+            raise RuntimeError("ref_harness failed")
+        trials += int(out[0])
+        secs = max(secs, float(out[1]))
+    return trials, secs
+
+
+def run_reference(steps, warmup, tmpdir, spec, uR, uI, R):
+    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    if not os.path.exists(harness):
+        raise RuntimeError("oracle/_ref/ref_harness missing: build it with `make -C oracle ref` where /root/reference exists")
+    cpus = physical_cores()
+    cases = []
+    for i, _ in enumerate(cpus):
+        path = os.path.join(tmpdir, f"case_{i}.txt")
+        write_reference_case(path, spec, uR, uI, R, seed=i + 1)   # rank-seeded like src/TDVMC.cpp:524
+        cases.append(path)
+    for _ in range(warmup):
+        reference_step(cases, cpus)
+    trials, secs = 0, 0.0
+    for _ in range(steps):
+        t, s = reference_step(cases, cpus)
+        trials += t
+        secs += s
+    return trials, secs, len(cpus)
+
+
+def reference_main(args, rank):
+    if rank != 0:
+        return
+    spec, uR, uI, R = golden_spec()
+    with tempfile.TemporaryDirectory() as td:
+        trials, secs, cores = run_reference(args.steps, args.warmup, td, spec, uR, uI, R)
+    value = trials / secs
+    sample = (f"{cores} single-rank processes of the unmodified reference (one per physical core, taskset-pinned, "
+              f"serial MPI shim), each one walker's pass per step: {STEPS_PER_WALKER} proposals + {MC_NSTEPS} evaluations")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "walker-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config({"walkers": cores}),
+            "time_steps_per_s": args.steps / secs,
+            "cpu_baseline": {"value": value, "unit": "walker-steps/s", "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": value, "unit": "walker-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+                if self.stop_flag.is_set():
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag.set()
+        try:
+            self.proc.terminate()
+        except Exception:
+            pass
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active") and "not" not in v.lower():
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--walkers-per-gpu", type=int, default=0, help="0: one full wave of the sweep kernel")
+    ap.add_argument("--no-exhibits", action="store_true", help="skip the K3/K4/K5 roofline exhibits and the CPU baseline")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_main(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from tdvmc_b200 import capi
+
+    if not torch.cuda.is_available() or capi.load().tdvmc_gpu_device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    spec, uR, uI, R_seed = golden_spec()
+
+    # ensemble size: one full wave of the sweep kernel per GPU (weak scaling: fixed walkers per GPU)
+    probe = capi.Handle(spec, 1, device=local_rank)
+    per_sm, sms = probe.resident_walkers()
+    probe.close()
+    W = args.walkers_per_gpu or per_sm * sms
+    first = rank * W
+    h = capi.Handle(spec, W, seed=1, mc_step=MC_STEP, first_walker=first, max_samples=MC_NSTEPS, device=local_rank)
+    if world > 1:
+        uid = torch.zeros(capi.UNIQUE_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        h.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+
+    # synthetic ensemble: jittered 7^3 lattices (src/TDVMC.cpp:727-739), equilibrated by 100 sweeps
+    rng = np.random.default_rng(1000 + rank)
+    R_host = torch.empty((W, N, 3), dtype=torch.float64).pin_memory()
+    R_np = R_host.numpy()
+    base = systems.jittered_lattice(N, LBOX, rng)
+    R_np[:] = base[None] + rng.uniform(-0.02, 0.02, (W, N, 3))
+    h.set_params(uR, uI, 0.0, 0.0, 0.0)
+    h.set_positions_raw(R_host.data_ptr(), 0, W)
+    h.sweep(100 * N)
+    h.wrap_positions()
+    h.synchronize()
+
+    out = None
+
+    def step(e2e):
+        nonlocal out
+        if e2e:
+            h.set_positions_raw(R_host.data_ptr(), 0, W)                      # H2D from pinned memory
+        h.set_params(uR, uI, 0.0, 0.0, 0.0)                                   # BroadcastNewParameters
+        h.sample_and_accumulate(MC_NSTEPS, MC_NTHERMSTEPS, MC_NINIT)          # UpdateExpectationValues
+        out = h.allreduce_and_fetch(out)                                      # ReduceToAverage x7 (D2H)
+        if e2e:
+            h.get_positions(0, W, out=R_np)                                   # D2H into pinned memory
+        h.flush_l2()                                                          # next step starts with a cold L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+        h.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(k, e2e):
+        barrier()
+        h.timer_start()
+        for _ in range(k):
+            step(e2e)
+        ms = h.timer_stop()
+        barrier()
+        return max_over_ranks(ms)
+
+    for _ in range(args.warmup):
+        step(False)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    h.profile(True, True)
+    launches0 = h.launch_count()
+    ms_total = timed(args.steps, False)
+    launches = h.launch_count() - launches0
+    stats = h.kernel_stats()
+    h.profile(False, False)
+    clocks = sampler.finish()
+    step(True)
+    ms_e2e = timed(args.steps, True)
+
+    proposals = float(W) * world * STEPS_PER_WALKER * args.steps
+    value = proposals / (ms_total * 1e-3)
+    e2e_value = proposals / (ms_e2e * 1e-3)
+    est_bytes = 8 * (N_PARAM * N_PARAM + 3 * N_PARAM + 2 + spec.n_other)
+    h2d = W * N * 3 * 8 + 2 * N_PARAM * 8 + 16
+    d2h = W * N * 3 * 8 + est_bytes
+
+    # ---- roofline of the dominant kernel (K1 sweep): FP64 pipe, denominators measured live ----
+    dfma_peak, dmma_peak = h.measure_fp64_peak()
+    n_sweep, ms_sweep = stats["sweep"]
+    sweep_flops = FLOP_PER_WALKER_STEP * float(W) * STEPS_PER_WALKER * args.steps
+    sweep_tf = sweep_flops / (ms_sweep * 1e-3) / 1e12
+    roofline = {"kernel": "sweep_kernel (K1)", "bound": "fp64", "achieved": sweep_tf, "peak": dfma_peak, "unit": "TFLOP/s",
+                "frac": sweep_tf / dfma_peak, "traffic": None,
+                "note": "FP64 DFMA-pipe bound (SURVEY 8d): 19 836 algorithmic flop per walker-step; peak = DFMA microbenchmark "
+                        "measured in this run (MEASURED_PEAKS.json has no FP64 entry); HBM traffic is 16.5 KB per walker per launch",
+                "launches": n_sweep, "avg_launch_ms": ms_sweep / max(n_sweep, 1), "share_of_step": ms_sweep / ms_total}
+    n_ev, ms_ev = stats["evaluate"]
+    ev_tf = FLOP_PER_EVALUATION * float(W) * MC_NSTEPS * args.steps / (ms_ev * 1e-3) / 1e12
+    kernels = [roofline,
+               {"kernel": "evaluate_kernel (K2+K3+K4 fused)", "bound": "fp64", "achieved": ev_tf, "peak": dfma_peak,
+                "unit": "TFLOP/s", "frac": ev_tf / dfma_peak, "launches": n_ev, "avg_launch_ms": ms_ev / max(n_ev, 1),
+                "share_of_step": ms_ev / ms_total, "samples_per_s": float(W) * MC_NSTEPS * args.steps / (ms_ev * 1e-3)},
+               {"kernel": "syrk_kernel (K5) inside the step", "launches": stats["accumulate"][0],
+                "avg_launch_ms": stats["accumulate"][1] / max(stats["accumulate"][0], 1),
+                "share_of_step": stats["accumulate"][1] / ms_total}]
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+
+    cpu_baseline = None
+    if not args.no_exhibits and rank == 0:
+        # K3 / K4 exhibits: reference table semantics on resident walkers (HBM bound)
+        nt = min(W, 1024)
+        h.tables_resident(nt)
+        h.contract_resident(nt, fetch=False)
+        h.flush_l2()
+        h.profile(True, True)
+        for _ in range(3):
+            h.tables_resident(nt)
+            h.flush_l2()
+            h.contract_resident(nt, fetch=False)
+            h.flush_l2()
+        st = h.kernel_stats()
+        h.profile(False, False)
+        t_tab = st["tables"][1] / st["tables"][0] * 1e-3
+        t_con = st["contract"][1] / st["contract"][0] * 1e-3
+        kernels.append({"kernel": "tables_kernel (K3, reference table form)", "bound": "hbm",
+                        "achieved": nt * BYTES_PER_TABLE / t_tab / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": nt * BYTES_PER_TABLE / t_tab / 1e9 / hbm_peak, "peak_source": hbm_src,
+                        "samples_per_s": nt / t_tab, "configs_per_launch": nt})
+        con_bytes = 8 * 203 * N * 4
+        kernels.append({"kernel": "contract_kernel (K4 from tables)", "bound": "hbm", "achieved": nt * con_bytes / t_con / 1e9,
+                        "peak": hbm_peak, "unit": "GB/s", "frac": nt * con_bytes / t_con / 1e9 / hbm_peak,
+                        "peak_source": hbm_src, "samples_per_s": nt / t_con, "configs_per_launch": nt})
+        # K5 exhibit: S/F accumulation on M = 2^17 synthetic samples, against cuBLAS DGEMM and the DMMA probe
+        M = 1 << 17
+        rngk = np.random.default_rng(2)
+        O = rngk.normal(50.0 + np.arange(N_PARAM), 5.0, size=(M, N_PARAM))
+        er, ei = rngk.normal(size=M), rngk.normal(size=M)
+        h.accumulate_fixed(O[:4096], er[:4096], ei[:4096])
+        h.profile(True, True)
+        h.accumulate_fixed(O, er, ei)
+        st = h.kernel_stats()
+        h.profile(False, False)
+        t_acc = st["accumulate"][1] / st["accumulate"][0] * 1e-3
+        a = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+        torch.matmul(a, a)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            torch.matmul(a, a)
+        e1.record()
+        torch.cuda.synchronize()
+        dgemm_tf = 3 * 2 * 4096 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+        syrk_flops = float(M) * (N_PARAM + 3) * (N_PARAM + 4)
+        kernels.append({"kernel": "syrk_kernel (K5, M=2^17 synthetic samples)", "bound": "tensor",
+                        "achieved": syrk_flops / t_acc / 1e12, "peak": dgemm_tf, "unit": "TFLOP/s",
+                        "frac": syrk_flops / t_acc / 1e12 / dgemm_tf, "peak_source": "cuBLAS DGEMM 4096^3 measured in this run",
+                        "dmma_probe_tflops": dmma_peak, "flop_convention": "symmetric: M (P+3)(P+4)", "ms": t_acc * 1e3})
+        # CPU baseline: the unmodified reference on this box's host cores, one pass per core
+        if world == 1:
+            try:
+                with tempfile.TemporaryDirectory() as td:
+                    trials, secs, cores = run_reference(1, 0, td, spec, uR, uI, R_seed)
+                cpu_baseline = {"value": trials / secs, "unit": "walker-steps/s", "cores": cores, "kind": "reference",
+                                "sample": f"{cores} pinned single-rank processes of the unmodified reference, one walker's pass each "
+                                          f"({STEPS_PER_WALKER} proposals + {MC_NSTEPS} evaluations), {secs:.2f} s"}
+            except Exception as ex:  # the baseline is a report, never the product
+                cpu_baseline = {"value": None, "unit": "walker-steps/s", "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "walker-steps/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config({"walkers_per_gpu": W, "walkers": W * world, "parallelism": f"walkers x{world}",
+                                           "l2": "flushed between steps (256 MiB memset); walker state is 29 MB per GPU"}),
+                "time_steps_per_s": args.steps / (ms_total * 1e-3),
+                "e2e": {"value": e2e_value, "unit": "walker-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,
+                "fp64_peaks": {"dfma_tflops": dfma_peak, "dmma_tflops": dmma_peak},
+                "cpu_baseline": cpu_baseline,
+                "estimators": {"local_energy_r": float(out["e_r"][0]), "acceptance": out["n_acceptances"] / max(out["n_trials"], 1)}}
+        print(json.dumps(line))
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -170,6 +170,13 @@ enum tdvmc_kernel_id
 int tdvmc_gpu_profile(tdvmc_gpu_handle* h, int32_t enable, int32_t reset);
 int tdvmc_gpu_kernel_stats(tdvmc_gpu_handle* h, int32_t kernel_id, int64_t* launches, double* total_ms);
 int tdvmc_gpu_synchronize(tdvmc_gpu_handle* h);
+/* CUDA-event stopwatch on the library's stream (the stream every kernel and copy of this handle is issued on). */
+int tdvmc_gpu_timer_start(tdvmc_gpu_handle* h);
+int tdvmc_gpu_timer_stop(tdvmc_gpu_handle* h, double* elapsed_ms); /* records, synchronises, returns the elapsed time */
+/* Number of kernels of this library launched on the handle since creation. */
+int tdvmc_gpu_launch_count(tdvmc_gpu_handle* h, int64_t* n);
+/* Evict the L2 cache: overwrite a scratch buffer of n_bytes (>= L2 size) on the library's stream. */
+int tdvmc_gpu_flush_l2(tdvmc_gpu_handle* h, int64_t n_bytes);
 /* K3/K4 exhibits on the resident walkers (reference table semantics, BosonsBulk.cpp:220-336 and :349-458):
  * materialise the sD/sD2 tables of every local walker and contract them again.  Used by bench.py. */
 int tdvmc_gpu_tables_resident(tdvmc_gpu_handle* h, int32_t n_walkers);

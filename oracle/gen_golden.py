@@ -40,7 +40,7 @@ def smooth_params(P, rmax, a_r=-0.5, w_r=0.8, a_i=0.05, c_i=1.5, w_i=0.5):
 def write_case(path, system, scal, arrays, moves=()):
     with open(path, "w") as f:
         f.write(f"system {system}\n")
-        f.write(f"configdir {REF}/config/\n")
+        f.write(f"configdir {HERE}/_ref/config/\n")
         for k, v in scal.items():
             f.write(f"{k} {v!r}\n")
         for k, v in arrays.items():

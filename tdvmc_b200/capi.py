@@ -66,6 +66,10 @@ SYMBOLS = [
     ("tdvmc_gpu_profile", C.c_int, [_VP, C.c_int32, C.c_int32]),
     ("tdvmc_gpu_kernel_stats", C.c_int, [_VP, C.c_int32, C.POINTER(C.c_int64), dp]),
     ("tdvmc_gpu_synchronize", C.c_int, [_VP]),
+    ("tdvmc_gpu_timer_start", C.c_int, [_VP]),
+    ("tdvmc_gpu_timer_stop", C.c_int, [_VP, dp]),
+    ("tdvmc_gpu_launch_count", C.c_int, [_VP, C.POINTER(C.c_int64)]),
+    ("tdvmc_gpu_flush_l2", C.c_int, [_VP, C.c_int64]),
     ("tdvmc_gpu_tables_resident", C.c_int, [_VP, C.c_int32]),
     ("tdvmc_gpu_contract_resident", C.c_int, [_VP, C.c_int32, dp, dp]),
     ("tdvmc_gpu_resident_walkers", C.c_int, [_VP, ip, ip]),
@@ -263,6 +267,22 @@ class Handle:
 
     def synchronize(self):
         self._ck(self.lib.tdvmc_gpu_synchronize(self.h), "synchronize")
+
+    def timer_start(self):
+        self._ck(self.lib.tdvmc_gpu_timer_start(self.h), "timer_start")
+
+    def timer_stop(self):
+        ms = C.c_double(0)
+        self._ck(self.lib.tdvmc_gpu_timer_stop(self.h, C.byref(ms)), "timer_stop")
+        return ms.value
+
+    def launch_count(self):
+        n = C.c_int64(0)
+        self._ck(self.lib.tdvmc_gpu_launch_count(self.h, C.byref(n)), "launch_count")
+        return n.value
+
+    def flush_l2(self, n_bytes=256 << 20):
+        self._ck(self.lib.tdvmc_gpu_flush_l2(self.h, n_bytes), "flush_l2")
 
     def tables_resident(self, n_walkers):
         self._ck(self.lib.tdvmc_gpu_tables_resident(self.h, n_walkers), "tables_resident")

@@ -146,6 +146,9 @@ struct tdvmc_gpu_handle
     bool profiling = false;
     std::vector<TimedLaunch> pending;
     std::vector<cudaEvent_t> event_pool;
+    cudaEvent_t timer0 = nullptr, timer1 = nullptr;
+    DevBuf<unsigned char> d_flush;
+    long long n_launched = 0; // kernels of this library launched on the handle
     long long launches[TDVMC_KERNEL_COUNT] = { 0 };
     double total_ms[TDVMC_KERNEL_COUNT] = { 0 };
 
@@ -190,9 +193,10 @@ struct Timed
     tdvmc_gpu_handle* h;
     int kernel;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    Timed(tdvmc_gpu_handle* h_, int k) : h(h_), kernel(k)
+    Timed(tdvmc_gpu_handle* h_, int k, int n_kernels = 1) : h(h_), kernel(k)
     {
         h->launches[k]++;
+        h->n_launched += n_kernels;
         if (h->profiling)
         {
             e0 = get_event(h);
@@ -539,6 +543,8 @@ void tdvmc_gpu_destroy(tdvmc_gpu_handle* h)
         cudaEventDestroy(t.e1);
     }
     for (auto e : h->event_pool) cudaEventDestroy(e);
+    if (h->timer0) cudaEventDestroy(h->timer0);
+    if (h->timer1) cudaEventDestroy(h->timer1);
     if (h->h_est) cudaFreeHost(h->h_est);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -551,6 +557,7 @@ int tdvmc_gpu_set_positions(tdvmc_gpu_handle* h, const double* R, int32_t first,
     const size_t cnt = (size_t)n * h->N * 3;
     CK(cudaMemcpyAsync(h->d_aos.p, R, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(launch_transpose_in(h->d_aos.p, h->d_pos.p + (size_t)first * 3 * h->Np, n, h->N, h->Np, h->stream));
+    h->n_launched++;
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -561,6 +568,7 @@ int tdvmc_gpu_get_positions(tdvmc_gpu_handle* h, double* R, int32_t first, int32
     CK(cudaSetDevice(h->device));
     const size_t cnt = (size_t)n * h->N * 3;
     CK(launch_transpose_out(h->d_pos.p + (size_t)first * 3 * h->Np, h->d_aos.p, n, h->N, h->Np, h->stream));
+    h->n_launched++;
     CK(cudaMemcpyAsync(R, h->d_aos.p, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
@@ -667,7 +675,7 @@ static int do_accumulate(tdvmc_gpu_handle* h, const double* A, const double* oth
         CK(launch_accumulate(a, h->stream));
     }
     {
-        Timed t(h, TDVMC_KERNEL_OTHER);
+        Timed t(h, TDVMC_KERNEL_OTHER, 3);
         CK(launch_acc_finish(f, h->stream));
     }
     h->rows_used = M;
@@ -1081,6 +1089,47 @@ int tdvmc_gpu_synchronize(tdvmc_gpu_handle* h)
     if (!h) return -1;
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int tdvmc_gpu_timer_start(tdvmc_gpu_handle* h)
+{
+    if (!h) return -1;
+    CK(cudaSetDevice(h->device));
+    if (!h->timer0)
+    {
+        CK(cudaEventCreate(&h->timer0));
+        CK(cudaEventCreate(&h->timer1));
+    }
+    CK(cudaEventRecord(h->timer0, h->stream));
+    return 0;
+}
+
+int tdvmc_gpu_timer_stop(tdvmc_gpu_handle* h, double* elapsed_ms)
+{
+    if (!h || !elapsed_ms || !h->timer0) return h ? fail(h, "timer_stop: timer not started") : -1;
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->timer1, h->stream));
+    CK(cudaEventSynchronize(h->timer1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->timer0, h->timer1));
+    *elapsed_ms = ms;
+    return 0;
+}
+
+int tdvmc_gpu_launch_count(tdvmc_gpu_handle* h, int64_t* n)
+{
+    if (!h || !n) return -1;
+    *n = h->n_launched;
+    return 0;
+}
+
+int tdvmc_gpu_flush_l2(tdvmc_gpu_handle* h, int64_t n_bytes)
+{
+    if (!h || n_bytes < 1) return h ? fail(h, "flush_l2: bad size") : -1;
+    CK(cudaSetDevice(h->device));
+    CK(h->d_flush.ensure((size_t)n_bytes));
+    CK(cudaMemsetAsync(h->d_flush.p, 0, (size_t)n_bytes, h->stream));
     return 0;
 }
 

@@ -107,7 +107,9 @@ struct Philox4
 __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                           uint32_t k0, uint32_t k1)
 {
+#ifdef __CUDA_ARCH__
 #pragma unroll
+#endif
     for (int round = 0; round < 10; round++)
     {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0;
