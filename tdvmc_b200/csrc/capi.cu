@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 #include <string>
@@ -312,22 +313,28 @@ int build_param_tables(tdvmc_gpu_handle* h)
         }
     // u(r) on interval b in the local coordinate s = r - t_b, expanded exactly (long double) from the
     // caller's monomial table: u(r) = sum_p u~[b-p] * piece_p(b-p)(r)
-    std::vector<double> cub((size_t)h->nbins * kCubStride, 0.0);
-    for (int b = fb; b < K; b++)
+    // planes: [c0,c1] | [c2,c3] | [t_lo,t_hi], nbins + 1 records each; record nbins is the constant tail
+    // uR[tail_param] every pair beyond r_max contributes (BosonsBulk.cpp:532-534)
+    const int nrec = h->nbins + 1;
+    std::vector<double> cub((size_t)nrec * 6, 0.0);
+    for (int rec = 0; rec < h->nbins; rec++)
     {
+        const int b = fb + rec;
         long double C[4] = { 0, 0, 0, 0 };
         for (int p = 0; p < 4; p++)
             for (int c = 0; c < 4; c++)
                 C[c] += (long double)utR[b - p] * (long double)h->weights[((size_t)(b - p) * 4 + p) * 4 + c];
         const long double t0 = h->knots[b];
-        double* q = &cub[(size_t)(b - fb) * kCubStride];
-        q[0] = (double)(C[0] + t0 * (C[1] + t0 * (C[2] + t0 * C[3])));
-        q[1] = (double)(C[1] + t0 * (2 * C[2] + 3 * t0 * C[3]));
-        q[2] = (double)(C[2] + 3 * t0 * C[3]);
-        q[3] = (double)C[3];
-        q[4] = h->knots[b];
-        q[5] = h->knots[b + 1];
+        cub[(size_t)rec * 2 + 0] = (double)(C[0] + t0 * (C[1] + t0 * (C[2] + t0 * C[3])));
+        cub[(size_t)rec * 2 + 1] = (double)(C[1] + t0 * (2 * C[2] + 3 * t0 * C[3]));
+        cub[(size_t)(nrec + rec) * 2 + 0] = (double)(C[2] + 3 * t0 * C[3]);
+        cub[(size_t)(nrec + rec) * 2 + 1] = (double)C[3];
+        cub[(size_t)(2 * nrec + rec) * 2 + 0] = h->knots[b];
+        cub[(size_t)(2 * nrec + rec) * 2 + 1] = h->knots[b + 1];
     }
+    cub[(size_t)h->nbins * 2 + 0] = h->tail_param >= 0 ? h->uR[h->tail_param] : 0.0;
+    cub[(size_t)(2 * nrec + h->nbins) * 2 + 0] = h->knots[K];
+    cub[(size_t)(2 * nrec + h->nbins) * 2 + 1] = 1e300;
     CK(upload(h->d_uR, h->uR, h->stream));
     CK(upload(h->d_uI, h->uI, h->stream));
     CK(upload(h->d_utR, utR, h->stream));
@@ -510,14 +517,27 @@ int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed,
     // sweep geometry: as many walkers (warps) per block as keep >= 2 blocks per SM resident
     h->npp = (h->N + 1) & ~1;
     SysDev s = h->sysdev();
-    int best_wpb = 1, best_res = 0;
+    // Walkers (warps) per block: as many as fit, but a multiple of 4 per SM -- the four SM sub-partitions
+    // each run resident/4 warps and the slowest one sets the pace (measured: 20 walkers/SM beat 21 by 13 %).
+    int best_wpb = 1, best_res = 0, best_score = -1;
     for (int wpb = 1; wpb <= kSweepMaxThreads / 32; wpb++)
     {
         const int res = sweep_blocks_per_sm(s, wpb, h->npp) * wpb; // walkers resident per SM
-        if (res > best_res || (res == best_res && std::abs(wpb - 8) < std::abs(best_wpb - 8)))
+        const int score = res >= 4 ? (res / 4) * 4 * 2 + (res % 4 == 0 ? 1 : 0) : res;
+        if (score >= best_score && res > 0) // ties: the larger block shares one copy of the coefficient planes
         {
+            best_score = score;
             best_res = res;
             best_wpb = wpb;
+        }
+    }
+    if (const char* e = getenv("TDVMC_SWEEP_WPB")) // tuning knob
+    {
+        const int wpb = atoi(e);
+        if (wpb >= 1 && wpb <= kSweepMaxThreads / 32 && sweep_blocks_per_sm(s, wpb, h->npp) > 0)
+        {
+            best_wpb = wpb;
+            best_res = sweep_blocks_per_sm(s, wpb, h->npp) * wpb;
         }
     }
     h->resident_per_sm = best_res;

@@ -13,7 +13,6 @@ namespace tdvmc
 
 constexpr unsigned FULL_MASK = 0xffffffffu;
 constexpr int kRecStride = 18;   // doubles per knot-interval record of the evaluation table (bank spreading)
-constexpr int kCubStride = 6;    // doubles per interval record of the sweep table: c0..c3, t_lo, t_hi
 
 // Read-only description of the system as the kernels see it.  Pointers are device memory.
 struct SysDev
@@ -39,7 +38,8 @@ struct SysDev
     double u_tail;           // uR[tail_param]
     const double* knots;     // [K+4]
     const double* rec;       // [nbins][kRecStride]: piece p of spline (bin-p) at [p*4 + c]
-    const double* cub;       // [nbins][kCubStride]: u(r) on the interval in the local coordinate r - t_lo
+    const double* cub;       // sweep table, 3 planes of (nbins+1) double2: [c0,c1] | [c2,c3] | [t_lo,t_hi];
+                             // u(r) = c0 + c1 s + c2 s^2 + c3 s^3 on the interval, s = r - t_lo
     const unsigned short* lut; // [ncell] -> interval index guess
     const int* map_ptr;
     const int* map_col;

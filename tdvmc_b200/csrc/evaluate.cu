@@ -94,7 +94,7 @@ __host__ __device__ inline size_t eval_smem_layout(const SysDev& s, int nwarps, 
 }
 
 template <bool REFLECT>
-__global__ void __launch_bounds__(384) evaluate_kernel(EvalArgs a)
+__global__ void __launch_bounds__(384, 2) evaluate_kernel(EvalArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SysDev& s = a.s;
@@ -304,12 +304,14 @@ cudaError_t launch_evaluate(const EvalArgs& a, cudaStream_t st)
     {
         e = cudaFuncSetAttribute(evaluate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        cudaFuncSetAttribute(evaluate_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         evaluate_kernel<true><<<a.n_cfg, threads, smem, st>>>(a);
     }
     else
     {
         e = cudaFuncSetAttribute(evaluate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        cudaFuncSetAttribute(evaluate_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         evaluate_kernel<false><<<a.n_cfg, threads, smem, st>>>(a);
     }
     return cudaGetLastError();

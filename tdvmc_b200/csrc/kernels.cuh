@@ -6,7 +6,8 @@
 namespace tdvmc
 {
 
-constexpr int kSweepMaxThreads = 512;
+constexpr int kSweepMaxThreads = 704; // up to 22 walkers (warps) per block -> at most 93 registers per thread
+constexpr int kSweepMinBlocks = 1;
 
 // ---- K1: Metropolis sweep (sweep.cu) ----
 struct SweepArgs

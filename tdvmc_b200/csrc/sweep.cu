@@ -10,86 +10,130 @@
 // precision on the host from the caller's spline table), and a proposal costs 2(N-1) distance +
 // cubic evaluations and one warp reduction:
 //     delta = sum_{i != p} u(|r_new - r_i|) - u(|r_old - r_i|),   accept iff log(U) <= 2 delta.
+//
 // Positions stay in shared memory for the whole launch (structure of arrays, one row per
-// coordinate), HBM is touched once on entry and once on exit.
+// coordinate); HBM is touched once on entry and once on exit.  ncu (profiles/r01a_sweep_ncu.txt)
+// showed the first version bound by shared-memory wavefronts (83 %) ahead of the FP64 pipe (55 %),
+// so the table is split into 16-byte planes (a random record index then spreads over all eight
+// 16-byte slots of a bank row), uniform knots need no t_lo load, positions are kept wrapped into
+// the first cell so the minimum image is min(|d|, L - |d|) (3 FP64 ops per coordinate instead of 4),
+// and the square root drops the final correctly-rounding step (2 ulp are irrelevant for sampling).
+// A second capture (profiles/r01c_sweep_ncu.txt) still had 80 % shared-memory wavefronts: a random
+// LDS.128 is served quarter-warp by quarter-warp, and two of eight lanes hitting the same 16-byte
+// slot of a bank row with different records serialise.  The coefficient planes are therefore
+// replicated eight times, copy c in slot c of every 128-byte row, and lane l reads copy l % 8: each
+// quarter-warp covers the eight slots exactly once, whatever the record indices are.
 #include "kernels.cuh"
+
+#include <cstdlib>
 
 namespace tdvmc
 {
 
 constexpr double kMagic = 6755399441055744.0; // 2^52 + 2^51: (x + kMagic) - kMagic rounds x to nearest
+constexpr int kCubCopies = 8;                 // shared-memory replicas of the coefficient planes (one per 16-byte slot)
 
-// minimum image of one coordinate difference; ties at exactly +-L/2 are irrelevant for sampling
-__device__ __forceinline__ double mi_fast(double d, double L, double Linv)
+// x - L * rint(x / L): into [-L/2, L/2]
+__device__ __forceinline__ double wrap_fast(double d, double L, double Linv)
 {
     double k = fma(d, Linv, kMagic) - kMagic;
     return fma(-k, L, d);
 }
 
-// pair term of the exponent at distance r, with the system's cut rule
-template <bool UNIFORM, bool REFLECT>
-__device__ __forceinline__ double pair_u(const SysDev& s, const double* __restrict__ cub,
-                                         const unsigned short* __restrict__ lut, double r)
+// squared minimum-image distance of two points that both lie in the first cell (|d| <= L per coordinate):
+// min(|d|, L - |d|) = L/2 - ||d| - L/2|, two FP64 adds with free |.| modifiers and no select
+__device__ __forceinline__ double mi2_wrapped(double dx, double dy, double dz, double Lhalf)
 {
-    bool inside;
-    if (REFLECT)
-    {
-        if (!(r < s.rmax)) r = 2.0 * s.rmax - r; // NUBosonsBulkPB.cpp:689-692
-        inside = r < s.rmax;
-    }
-    else
-    {
-        inside = r <= s.rmax; // BosonsBulk.cpp:571 (the strict '<' of :593 differs on a null set)
-    }
+    const double mx = Lhalf - fabs(fabs(dx) - Lhalf);
+    const double my = Lhalf - fabs(fabs(dy) - Lhalf);
+    const double mz = Lhalf - fabs(fabs(dz) - Lhalf);
+    return fma(mz, mz, fma(my, my, mx * mx));
+}
+
+// sqrt(x) to ~2 ulp: MUFU.RSQ64H seed (22 bits) + one third-order step; x == 0 gives NaN, which the
+// callers discard (it only happens for the moved particle against itself)
+__device__ __forceinline__ double sqrt_fast(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double t = x * y;
+    const double e = fma(-t, y, 1.0);
+    const double p = fma(e, 0.375, 0.5);
+    const double ye = y * e;
+    const double y1 = fma(ye, p, y);
+    return x * y1;
+}
+
+// pair term of the exponent at distance r, with the system's cut rule
+template <bool UNIFORM, bool REFLECT, int STRIDE>
+__device__ __forceinline__ double pair_u(const SysDev& s, const double2* __restrict__ c01p, const double2* __restrict__ c23p,
+                                         const double2* __restrict__ ttp, const unsigned short* __restrict__ lut, double r)
+{
+    // Beyond r_max every pair contributes the constant u_tail (BosonsBulk.cpp:207-210, 532-534): record
+    // nbins of the table holds exactly that constant, so the cut needs no compare/select.  (At r == r_max
+    // the reference's '<=' (:571) / '<' (:593) pick the spline or the tail; a null set for sampling.)
+    if (REFLECT) r = (r < s.rmax) ? r : 2.0 * s.rmax - r; // NUBosonsBulkPB.cpp:689-692
     // floor(r * inv) via the rounding constant; the integer sits in the low word
-    double y = fma(r, UNIFORM ? s.inv_h : s.inv_cell, -0.5) + kMagic;
-    int c = __double2loint(y);
+    const double y = fma(r, UNIFORM ? s.inv_h : s.inv_cell, -0.5) + kMagic;
+    const int c = __double2loint(y);
+    double t;
     int j;
     if (UNIFORM)
     {
-        j = max(0, min(c, s.nbins - 1));
+        j = max(0, min(c, s.nbins));          // record nbins: constant tail
+        t = fma(-(y - kMagic), s.h, r);       // r - floor(r/h) h (multiplies zero coefficients when j was clamped)
     }
     else
     {
-        c = max(0, min(c, s.ncell - 1));
-        j = (int)lut[c] - s.first_bin;
-    }
-    const double* q = cub + j * kCubStride;
-    double2 c01 = *reinterpret_cast<const double2*>(q);
-    double2 c23 = *reinterpret_cast<const double2*>(q + 2);
-    double2 tt = *reinterpret_cast<const double2*>(q + 4);
-    if (!UNIFORM)
-    {
-        while (r > tt.y && j < s.nbins - 1)
+        j = (int)lut[max(0, min(c, s.ncell - 1))] - s.first_bin;
+        double2 tt = ttp[j];
+        while (r > tt.y)
         {
             j++;
-            q += kCubStride;
-            c01 = *reinterpret_cast<const double2*>(q);
-            c23 = *reinterpret_cast<const double2*>(q + 2);
-            tt = *reinterpret_cast<const double2*>(q + 4);
+            tt = ttp[j];
         }
+        t = r - tt.x;
     }
-    double t = r - tt.x;
-    double v = fma(fma(fma(c23.y, t, c23.x), t, c01.y), t, c01.x);
-    return inside ? v : s.u_tail;
+    const double2 c01 = c01p[j * STRIDE]; // STRIDE = 8: replicated planes, the caller's pointers select this lane's copy
+    const double2 c23 = c23p[j * STRIDE];
+    const double v = fma(fma(fma(c23.y, t, c23.x), t, c01.y), t, c01.x);
+    return v;
 }
 
-template <bool UNIFORM, bool REFLECT>
-__global__ void __launch_bounds__(kSweepMaxThreads) sweep_kernel(SweepArgs a)
+template <bool UNIFORM, bool REFLECT, int UNROLL>
+__global__ void __launch_bounds__(kSweepMaxThreads, kSweepMinBlocks) sweep_kernel(SweepArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SysDev& s = a.s;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int Npp = a.npp;
+    const int nrec = s.nbins + 1;
 
-    double* cub = reinterpret_cast<double*>(smem_raw);
-    unsigned short* lut = reinterpret_cast<unsigned short*>(cub + s.nbins * kCubStride);
+    // shared memory: c01 plane [nrec][8 copies] | c23 plane [nrec][8 copies] | (non-uniform: t plane [nrec] | lut) | positions
+    double2* c01s = reinterpret_cast<double2*>(smem_raw);
+    double2* c23s = c01s + (size_t)nrec * kCubCopies;
+    double2* tts = c23s + (size_t)nrec * kCubCopies;
+    unsigned short* lut = reinterpret_cast<unsigned short*>(tts + (UNIFORM ? 0 : nrec));
     double* pos_base = reinterpret_cast<double*>(smem_raw + a.pos_offset);
-
-    for (int i = threadIdx.x; i < s.nbins * kCubStride; i += blockDim.x) cub[i] = s.cub[i];
-    if (!UNIFORM)
-        for (int i = threadIdx.x; i < s.ncell; i += blockDim.x) lut[i] = s.lut[i];
+    {
+        const double2* g01 = reinterpret_cast<const double2*>(s.cub);
+        const double2* g23 = g01 + nrec;
+        const double2* gtt = g23 + nrec;
+        for (int i = threadIdx.x; i < nrec * kCubCopies; i += blockDim.x)
+        {
+            c01s[i] = g01[i / kCubCopies];
+            c23s[i] = g23[i / kCubCopies];
+        }
+        if (!UNIFORM)
+        {
+            for (int i = threadIdx.x; i < nrec; i += blockDim.x) tts[i] = gtt[i];
+            for (int i = threadIdx.x; i < s.ncell; i += blockDim.x) lut[i] = s.lut[i];
+        }
+    }
+    const double2* c01p = c01s + (lane & (kCubCopies - 1));
+    const double2* c23p = c23s + (lane & (kCubCopies - 1));
+    const double2* ttp = tts;
 
     const int w = blockIdx.x * a.wpb + warp; // local walker
     double* px = pos_base + (size_t)warp * 3 * Npp;
@@ -97,13 +141,14 @@ __global__ void __launch_bounds__(kSweepMaxThreads) sweep_kernel(SweepArgs a)
     double* pz = py + Npp;
     const bool have = w < a.W;
     double* gpos = a.pos + (size_t)(have ? w : 0) * 3 * s.Np;
+    const double L = s.L, Linv = s.Linv, Lhalf = s.Lhalf;
     if (have)
     {
-        for (int i = lane; i < s.N; i += 32)
+        for (int i = lane; i < s.N; i += 32) // positions live wrapped into the first cell during the sweep
         {
-            px[i] = gpos[i];
-            py[i] = gpos[s.Np + i];
-            pz[i] = gpos[2 * s.Np + i];
+            px[i] = wrap_fast(gpos[i], L, Linv);
+            py[i] = wrap_fast(gpos[s.Np + i], L, Linv);
+            pz[i] = wrap_fast(gpos[2 * s.Np + i], L, Linv);
         }
     }
     __syncthreads();
@@ -111,7 +156,6 @@ __global__ void __launch_bounds__(kSweepMaxThreads) sweep_kernel(SweepArgs a)
 
     const uint32_t gw = (uint32_t)(a.first_walker + w);
     const int N = s.N;
-    const double L = s.L, Linv = s.Linv;
     unsigned long long n_acc = 0;
 
     for (long long t0 = 0; t0 < a.n_steps; t0 += 32)
@@ -133,25 +177,21 @@ __global__ void __launch_bounds__(kSweepMaxThreads) sweep_kernel(SweepArgs a)
             const double log_u = __shfl_sync(FULL_MASK, mine.log_u, sidx);
 
             const double ox = px[p], oy = py[p], oz = pz[p];
-            const double nx = ox + ddx, ny = oy + ddy, nz = oz + ddz; // src/TDVMC.cpp:872-875
+            const double nx = wrap_fast(ox + ddx, L, Linv); // src/TDVMC.cpp:872-875, kept in the first cell
+            const double ny = wrap_fast(oy + ddy, L, Linv);
+            const double nz = wrap_fast(oz + ddz, L, Linv);
 
             double delta = 0.0;
-#pragma unroll 2
+#pragma unroll UNROLL
             for (int i = lane; i < N; i += 32)
             {
                 const double xi = px[i], yi = py[i], zi = pz[i];
-                double ax = mi_fast(xi - ox, L, Linv);
-                double ay = mi_fast(yi - oy, L, Linv);
-                double az = mi_fast(zi - oz, L, Linv);
-                double bx = mi_fast(xi - nx, L, Linv);
-                double by = mi_fast(yi - ny, L, Linv);
-                double bz = mi_fast(zi - nz, L, Linv);
-                double r_old = sqrt(fma(az, az, fma(ay, ay, ax * ax)));
-                double r_new = sqrt(fma(bz, bz, fma(by, by, bx * bx)));
-                double u_old = pair_u<UNIFORM, REFLECT>(s, cub, lut, r_old);
-                double u_new = pair_u<UNIFORM, REFLECT>(s, cub, lut, r_new);
-                double d = u_new - u_old;
-                delta += (i == p) ? 0.0 : d;
+                const double r_old = sqrt_fast(mi2_wrapped(xi - ox, yi - oy, zi - oz, Lhalf));
+                const double r_new = sqrt_fast(mi2_wrapped(xi - nx, yi - ny, zi - nz, Lhalf));
+                const double u_old = pair_u<UNIFORM, REFLECT, kCubCopies>(s, c01p, c23p, ttp, lut, r_old);
+                const double u_new = pair_u<UNIFORM, REFLECT, kCubCopies>(s, c01p, c23p, ttp, lut, r_new);
+                const double d = u_new - u_old;
+                if (i != p) delta += d;
             }
             delta = warp_sum(delta);
 
@@ -189,22 +229,27 @@ __global__ void quotient_kernel(QuotientArgs a)
     const SysDev& s = a.s;
     const int lane = threadIdx.x & 31;
     const int mv = blockIdx.x;
+    const int nrec = s.nbins + 1;
+    const double2* c01p = reinterpret_cast<const double2*>(s.cub);
+    const double2* c23p = c01p + nrec;
+    const double2* ttp = c23p + nrec;
     const double* px = a.pos;
     const double* py = a.pos + s.Np;
     const double* pz = a.pos + 2 * s.Np;
+    const double L = s.L, Linv = s.Linv, Lhalf = s.Lhalf;
     const int p = (int)a.moves[mv * 4];
-    const double nx = a.moves[mv * 4 + 1], ny = a.moves[mv * 4 + 2], nz = a.moves[mv * 4 + 3];
-    const double ox = px[p], oy = py[p], oz = pz[p];
+    const double nx = wrap_fast(a.moves[mv * 4 + 1], L, Linv), ny = wrap_fast(a.moves[mv * 4 + 2], L, Linv),
+                 nz = wrap_fast(a.moves[mv * 4 + 3], L, Linv);
+    const double ox = wrap_fast(px[p], L, Linv), oy = wrap_fast(py[p], L, Linv), oz = wrap_fast(pz[p], L, Linv);
     double delta = 0.0;
     for (int i = lane; i < s.N; i += 32)
     {
-        const double xi = px[i], yi = py[i], zi = pz[i];
-        double ax = mi_fast(xi - ox, s.L, s.Linv), ay = mi_fast(yi - oy, s.L, s.Linv), az = mi_fast(zi - oz, s.L, s.Linv);
-        double bx = mi_fast(xi - nx, s.L, s.Linv), by = mi_fast(yi - ny, s.L, s.Linv), bz = mi_fast(zi - nz, s.L, s.Linv);
-        double r_old = sqrt(fma(az, az, fma(ay, ay, ax * ax)));
-        double r_new = sqrt(fma(bz, bz, fma(by, by, bx * bx)));
-        double d = pair_u<UNIFORM, REFLECT>(s, s.cub, s.lut, r_new) - pair_u<UNIFORM, REFLECT>(s, s.cub, s.lut, r_old);
-        delta += (i == p) ? 0.0 : d;
+        const double xi = wrap_fast(px[i], L, Linv), yi = wrap_fast(py[i], L, Linv), zi = wrap_fast(pz[i], L, Linv);
+        const double r_old = sqrt_fast(mi2_wrapped(xi - ox, yi - oy, zi - oz, Lhalf));
+        const double r_new = sqrt_fast(mi2_wrapped(xi - nx, yi - ny, zi - nz, Lhalf));
+        const double d = pair_u<UNIFORM, REFLECT, 1>(s, c01p, c23p, ttp, s.lut, r_new) -
+                         pair_u<UNIFORM, REFLECT, 1>(s, c01p, c23p, ttp, s.lut, r_old);
+        if (i != p) delta += d;
     }
     delta = warp_sum(delta);
     if (lane == 0) a.delta[mv] = delta;
@@ -229,20 +274,51 @@ cudaError_t launch_quotient(const QuotientArgs& a, cudaStream_t st)
 
 size_t sweep_smem_bytes(const SysDev& s, int wpb, int npp, size_t* pos_offset)
 {
-    size_t off = (size_t)s.nbins * kCubStride * sizeof(double);
-    if (!s.uniform) off += (size_t)s.ncell * sizeof(unsigned short);
+    const size_t nrec = (size_t)s.nbins + 1;
+    size_t off = nrec * kCubCopies * 2 * sizeof(double2);
+    if (!s.uniform) off += nrec * sizeof(double2) + (size_t)s.ncell * sizeof(unsigned short);
     off = (off + 15) & ~(size_t)15;
     *pos_offset = off;
     return off + (size_t)wpb * 3 * npp * sizeof(double);
 }
 
-template <bool U, bool R>
+template <bool U, bool R, int UNROLL>
 static cudaError_t launch_one(const SweepArgs& a, int grid, int threads, size_t smem, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<U, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<U, R, UNROLL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    sweep_kernel<U, R><<<grid, threads, smem, st>>>(a);
+    cudaFuncSetAttribute(sweep_kernel<U, R, UNROLL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    sweep_kernel<U, R, UNROLL><<<grid, threads, smem, st>>>(a);
     return cudaGetLastError();
+}
+
+static int sweep_unroll()
+{
+    static int u = -1;
+    if (u < 0)
+    {
+        const char* e = getenv("TDVMC_SWEEP_UNROLL"); // tuning knob, default 2
+        u = e ? atoi(e) : 2;
+        if (u != 1 && u != 2 && u != 4) u = 2;
+    }
+    return u;
+}
+
+template <int UNROLL>
+static const void* sweep_fn(const SysDev& s)
+{
+    const bool refl = s.pair_rule == 1;
+    return s.uniform ? (refl ? (const void*)sweep_kernel<true, true, UNROLL> : (const void*)sweep_kernel<true, false, UNROLL>)
+                     : (refl ? (const void*)sweep_kernel<false, true, UNROLL> : (const void*)sweep_kernel<false, false, UNROLL>);
+}
+
+template <int UNROLL>
+static cudaError_t launch_unroll(const SweepArgs& a, int grid, int threads, size_t smem, cudaStream_t st)
+{
+    const bool refl = a.s.pair_rule == 1;
+    if (a.s.uniform)
+        return refl ? launch_one<true, true, UNROLL>(a, grid, threads, smem, st) : launch_one<true, false, UNROLL>(a, grid, threads, smem, st);
+    return refl ? launch_one<false, true, UNROLL>(a, grid, threads, smem, st) : launch_one<false, false, UNROLL>(a, grid, threads, smem, st);
 }
 
 cudaError_t launch_sweep(SweepArgs a, cudaStream_t st)
@@ -252,9 +328,12 @@ cudaError_t launch_sweep(SweepArgs a, cudaStream_t st)
     a.pos_offset = (int)pos_off;
     int grid = (a.W + a.wpb - 1) / a.wpb;
     int threads = a.wpb * 32;
-    bool refl = a.s.pair_rule == 1;
-    if (a.s.uniform) return refl ? launch_one<true, true>(a, grid, threads, smem, st) : launch_one<true, false>(a, grid, threads, smem, st);
-    return refl ? launch_one<false, true>(a, grid, threads, smem, st) : launch_one<false, false>(a, grid, threads, smem, st);
+    switch (sweep_unroll())
+    {
+    case 1: return launch_unroll<1>(a, grid, threads, smem, st);
+    case 4: return launch_unroll<4>(a, grid, threads, smem, st);
+    default: return launch_unroll<2>(a, grid, threads, smem, st);
+    }
 }
 
 int sweep_blocks_per_sm(const SysDev& s, int wpb, int npp)
@@ -262,10 +341,10 @@ int sweep_blocks_per_sm(const SysDev& s, int wpb, int npp)
     size_t pos_off;
     size_t smem = sweep_smem_bytes(s, wpb, npp, &pos_off);
     int nb = 0;
-    bool refl = s.pair_rule == 1;
-    const void* fn = s.uniform ? (refl ? (const void*)sweep_kernel<true, true> : (const void*)sweep_kernel<true, false>)
-                               : (refl ? (const void*)sweep_kernel<false, true> : (const void*)sweep_kernel<false, false>);
+    const int u = sweep_unroll();
+    const void* fn = u == 1 ? sweep_fn<1>(s) : (u == 4 ? sweep_fn<4>(s) : sweep_fn<2>(s));
     cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, wpb * 32, smem) != cudaSuccess) return 0;
     return nb;
 }
