@@ -1,0 +1,113 @@
+// GpuEnsembleSystem — C++ host adapter between the reference's driver and libtdvmc_b200.so.
+//
+// The reference driver (src/TDVMC.cpp) keeps its seven estimator globals (:147-153) and calls
+//     ParallelUpdateExpectationValues(R, uR, uI, phiR, phiI)                  :1152-1220
+//     ParallelUpdateExpectationValuesForGivenSamples(samples, uR, uI, ...)    :1305-1330
+//     MoveCoordinatesToFirstCell(R)                                           :787-796
+//     sys->GetExponent()  (NormalizeWavefunction)                             :3763
+// once per estimator evaluation.  This class offers the same calls on std::vector arguments (the
+// reference's own types) and forwards them to the C ABI of include/tdvmc_gpu.h; INTEGRATION.md shows
+// the few lines that re-point the driver.  It owns no physics: knots, spline table and boundary map
+// come from the reference's own InitSystem() results (or from SystemTables.h for the two covered
+// systems when the caller has only the config values).
+//
+// One instance per process / GPU.  Errors throw std::runtime_error carrying tdvmc_gpu_last_error().
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/tdvmc_gpu.h"
+
+namespace tdvmc_host
+{
+
+// Plain-data copy of what IPhysicalSystem::InitSystem() computed (BosonsBulk.cpp:49-156).
+struct SystemTables
+{
+    int n_particles = 0;
+    int n_params = 0;
+    int pair_rule = TDVMC_PAIR_RULE_CUT;
+    int tail_param = 0;
+    int n_other = 9;
+    double lbox = 0.0;
+    double hbar2_2m = 1.0;                 // HBAR2_2M, src/Constants.h:12
+    std::vector<double> knots;             // nodes
+    std::vector<double> spline_weights;    // splineWeights flattened [K][4][4]
+    std::vector<int32_t> map_ptr, map_col; // boundary-condition map, CSR over parameters
+    std::vector<double> map_val;
+    std::vector<double> system_params;     // SYSTEM_PARAMS
+};
+
+// Flattens the reference's vector<vector<vector<double>>> splineWeights (SplineFactory::GetWeights3).
+std::vector<double> FlattenWeights(const std::vector<std::vector<std::vector<double> > >& w);
+
+// BosonsBulk (BosonsBulk.cpp:61-106, 158-177): knots/weights as computed by the reference.
+SystemTables MakeBosonsBulkTables(int N, double LBOX, int N_PARAM, const std::vector<double>& nodes,
+                                  const std::vector<std::vector<std::vector<double> > >& splineWeights,
+                                  const std::vector<double>& SYSTEM_PARAMS);
+// NUBosonsBulkPB (NUBosonsBulkPB.cpp:53-135, 219-232).
+SystemTables MakeNUBosonsBulkPBTables(int N, double LBOX, int N_PARAM, const std::vector<double>& nodes,
+                                      const std::vector<std::vector<std::vector<double> > >& splineWeights,
+                                      const std::vector<double>& SYSTEM_PARAMS, int grBinCount);
+
+// The seven estimator arrays under the reference's global names (src/TDVMC.cpp:147-153).
+struct Estimators
+{
+    std::vector<double> localOperators;
+    double localEnergyR = 0.0;
+    double localEnergyI = 0.0;
+    std::vector<std::vector<double> > localOperatorsMatrix;
+    std::vector<double> localOperatorlocalEnergyR;
+    std::vector<double> localOperatorlocalEnergyI;
+    std::vector<double> otherExpectationValues;
+    long long nAcceptances = 0;
+    long long nTrials = 0;
+    long long nSamples = 0;
+};
+
+class GpuEnsembleSystem
+{
+public:
+    // walkersTotal walkers are split evenly over numOfProcesses ranks (processRank owns a contiguous block);
+    // MC_NSTEPS is the per-walker sample capacity, UPDATE_SAMPLES_EVERY_NTH_STEP > 0 keeps the sample positions.
+    GpuEnsembleSystem(const SystemTables& tables, int walkersTotal, double MC_STEP, int MC_NSTEPS,
+                      int UPDATE_SAMPLES_EVERY_NTH_STEP, unsigned long long seed, int processRank, int numOfProcesses,
+                      int device);
+    ~GpuEnsembleSystem();
+    GpuEnsembleSystem(const GpuEnsembleSystem&) = delete;
+    GpuEnsembleSystem& operator=(const GpuEnsembleSystem&) = delete;
+
+    int LocalWalkers() const { return nLocal; }
+    int FirstWalker() const { return firstWalker; }
+
+    // rank 0 creates the id, the driver broadcasts it (MPI_Bcast of 128 bytes), every rank joins
+    static std::vector<unsigned char> CreateCommunicatorId();
+    void JoinCommunicator(const std::vector<unsigned char>& id);
+
+    // R[w][n][a] for the local walkers
+    void SetPositions(const std::vector<std::vector<std::vector<double> > >& R);
+    void GetPositions(std::vector<std::vector<std::vector<double> > >& R);
+    void MoveCoordinatesToFirstCell();
+    void DoMetropolisSteps(long long n, const std::vector<double>& uR, const std::vector<double>& uI, double phiR,
+                           double phiI);
+
+    Estimators ParallelUpdateExpectationValues(const std::vector<double>& uR, const std::vector<double>& uI, double phiR,
+                                               double phiI, int MC_NSTEPS, int MC_NTHERMSTEPS,
+                                               int MC_NINITIALIZATIONSTEPS, double time);
+    Estimators ParallelUpdateExpectationValuesForGivenSamples(const std::vector<double>& uR, const std::vector<double>& uI,
+                                                              double phiR, double phiI, double time);
+    double GetExponent();
+
+private:
+    void Check(int rc, const char* what);
+    Estimators Fetch();
+
+    tdvmc_gpu_handle* handle = nullptr;
+    int N = 0, P = 0, nOther = 9;
+    int nLocal = 0, firstWalker = 0, rank = 0, world = 1;
+    std::vector<double> flat;
+};
+
+} // namespace tdvmc_host

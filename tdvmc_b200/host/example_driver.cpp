@@ -1,0 +1,68 @@
+// Minimal C++ driver over GpuEnsembleSystem: what the reference's time loop does around one
+// estimator evaluation (src/TDVMC.cpp:3437-3763), for a BosonsBulk system whose knots and spline
+// table are read from a text file (the reference driver would pass its own SplineFactory output).
+//
+//   example_driver <tables.txt>      tables.txt: N LBOX N_PARAM n_knots, knots..., K*16 weights...
+//
+// Exit code 0 and one line "E_R=... acceptance=..." on success; without a CUDA device the library
+// refuses to run (no CPU fallback) and the driver prints the error and exits with code 3.
+#include "GpuEnsembleSystem.h"
+
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <stdexcept>
+
+using namespace tdvmc_host;
+
+int main(int argc, char** argv)
+{
+    if (argc < 2)
+    {
+        std::fprintf(stderr, "usage: example_driver <tables.txt>\n");
+        return 2;
+    }
+    std::ifstream f(argv[1]);
+    int N, P, nk;
+    double L;
+    if (!(f >> N >> L >> P >> nk)) return 2;
+    std::vector<double> nodes(nk);
+    for (double& x : nodes) f >> x;
+    const int K = nk - 4;
+    std::vector<std::vector<std::vector<double> > > w(K, std::vector<std::vector<double> >(4, std::vector<double>(4)));
+    for (auto& s : w)
+        for (auto& p : s)
+            for (double& c : p) f >> c;
+    if (!f) return 2;
+
+    try
+    {
+        SystemTables t = MakeBosonsBulkTables(N, L, P, nodes, w, { 1.0, 1.0 });
+        const int walkers = 64, MC_NSTEPS = 2, MC_NTHERMSTEPS = N, MC_NINIT = 10 * N;
+        GpuEnsembleSystem gpu(t, walkers, 0.5, MC_NSTEPS, 0, 1ull, 0, 1, 0);
+        // start-up lattice (src/TDVMC.cpp:727-739 shape)
+        const int m = (int)std::lround(std::cbrt((double)N));
+        std::vector<std::vector<std::vector<double> > > R(walkers, std::vector<std::vector<double> >(N, std::vector<double>(3)));
+        for (int wk = 0; wk < walkers; wk++)
+            for (int n = 0; n < N; n++)
+            {
+                R[wk][n][0] = ((n % m) + 0.5 + 0.01 * wk / walkers) * L / m - L / 2;
+                R[wk][n][1] = (((n / m) % m) + 0.5) * L / m - L / 2;
+                R[wk][n][2] = ((n / (m * m)) + 0.5) * L / m - L / 2;
+            }
+        gpu.SetPositions(R);
+        std::vector<double> uR(P), uI(P, 0.0);
+        for (int k = 0; k < P; k++) uR[k] = -0.5 * std::exp(-std::pow(k * (L / 2) / (P - 1) / 0.8, 2));
+        gpu.MoveCoordinatesToFirstCell();
+        Estimators e = gpu.ParallelUpdateExpectationValues(uR, uI, 0.0, 0.0, MC_NSTEPS, MC_NTHERMSTEPS, MC_NINIT, 0.0);
+        std::printf("E_R=%.12g acceptance=%.4f samples=%lld exponent=%.10g\n", e.localEnergyR,
+                    (double)e.nAcceptances / (double)e.nTrials, e.nSamples, gpu.GetExponent());
+    }
+    catch (const std::exception& ex)
+    {
+        std::fprintf(stderr, "example_driver: %s\n", ex.what());
+        return 3;
+    }
+    return 0;
+}

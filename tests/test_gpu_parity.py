@@ -324,3 +324,41 @@ def test_errors_are_loud(capi, golden):
     with pytest.raises(capi.TdvmcError):
         h.reevaluate_stored()                         # no stored samples
     h.close()
+
+
+def test_cpp_host_adapter_matches_python_path(capi, golden, tmp_path):
+    """tdvmc_b200/host/example_driver (C++ over the C ABI) reproduces the ctypes path on the same inputs."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host = os.path.join(root, "tdvmc_b200", "host")
+    subprocess.check_call(["make", "-C", host, "example_driver"])
+    g = golden("bosonsbulk_n64_fixture")
+    tables = tmp_path / "tables.txt"
+    with open(tables, "w") as f:
+        f.write(f"{int(g['N'])} {float(g['LBOX'])!r} {int(g['N_PARAM'])} {len(g['knots'])}\n")
+        f.write(" ".join(repr(float(x)) for x in g["knots"]) + "\n")
+        f.write(" ".join(repr(float(x)) for x in g["spline_weights"].ravel()) + "\n")
+    r = subprocess.run([os.path.join(host, "example_driver"), str(tables)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    e_cpp = float(r.stdout.split("E_R=")[1].split()[0])
+    # same ensemble through the Python binding
+    N, L, P = int(g["N"]), float(g["LBOX"]), int(g["N_PARAM"])
+    spec = systems.bosons_bulk(N, L, P, [1.0, 1.0], weights=g["spline_weights"])
+    W, m = 64, round(N ** (1 / 3))
+    R = np.zeros((W, N, 3))
+    n = np.arange(N)
+    for w in range(W):
+        R[w, :, 0] = ((n % m) + 0.5 + 0.01 * w / W) * L / m - L / 2
+        R[w, :, 1] = (((n // m) % m) + 0.5) * L / m - L / 2
+        R[w, :, 2] = ((n // (m * m)) + 0.5) * L / m - L / 2
+    k = np.arange(P)
+    uR = -0.5 * np.exp(-((k * (L / 2) / (P - 1) / 0.8) ** 2))
+    h = capi.Handle(spec, W, seed=1, mc_step=0.5, max_samples=2)
+    h.set_positions(R)
+    h.wrap_positions()
+    h.set_params(uR, np.zeros(P))
+    h.sample_and_accumulate(2, N, 10 * N)
+    e_py = h.allreduce_and_fetch()["e_r"][0]
+    assert abs(e_cpp - e_py) < 1e-9 * abs(e_py)
+    h.close()

@@ -168,3 +168,27 @@ def test_two_rank_reduction_equals_single_rank(tmp_path):
               "otherExpectationValues"):
         assert np.allclose(a[k], b[k], rtol=1e-13, atol=1e-13), k
     assert abs(a["localEnergyR"] - b["localEnergyR"]) < 1e-12 * abs(a["localEnergyR"])
+
+
+def _write_tables(path, g):
+    with open(path, "w") as f:
+        f.write(f"{int(g['N'])} {float(g['LBOX'])!r} {int(g['N_PARAM'])} {len(g['knots'])}\n")
+        f.write(" ".join(repr(float(x)) for x in g["knots"]) + "\n")
+        f.write(" ".join(repr(float(x)) for x in g["spline_weights"].ravel()) + "\n")
+
+
+def test_cpp_host_adapter_builds_and_refuses_without_gpu(tmp_path, golden):
+    """The C++ adapter (tdvmc_b200/host) compiles with plain g++ against the C ABI; without a CUDA device
+    the driver stops with the library's error instead of computing anything on the CPU."""
+    from tdvmc_b200 import capi
+
+    _lib_path()
+    host = os.path.join(ROOT, "tdvmc_b200", "host")
+    subprocess.check_call(["make", "-C", host, "example_driver"])
+    tables = tmp_path / "tables.txt"
+    _write_tables(tables, golden("bosonsbulk_n64_fixture"))
+    r = subprocess.run([os.path.join(host, "example_driver"), str(tables)], capture_output=True, text=True)
+    if capi.load().tdvmc_gpu_device_count() > 0:
+        assert r.returncode == 0 and "E_R=" in r.stdout
+    else:
+        assert r.returncode == 3 and "no CUDA device" in r.stderr and "no CPU fallback" in r.stderr
