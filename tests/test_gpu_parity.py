@@ -362,3 +362,60 @@ def test_cpp_host_adapter_matches_python_path(capi, golden, tmp_path):
     e_py = h.allreduce_and_fetch()["e_r"][0]
     assert abs(e_cpp - e_py) < 1e-9 * abs(e_py)
     h.close()
+
+
+_MG_WORKER = r"""
+import os, sys, time
+import numpy as np
+root, tmp, rank, world = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4])
+sys.path.insert(0, root)
+from tdvmc_b200 import capi, systems
+from tdvmc_b200.ensemble import GpuEnsembleSystem
+g = np.load(os.path.join(root, "tests", "golden", "bosonsbulk_n64_equil.npz"))
+spec = systems.from_golden(g)
+idf = os.path.join(tmp, "nccl_id.bin")
+if rank == 0:
+    uid = capi.comm_unique_id()
+    open(idf + ".tmp", "wb").write(uid)
+    os.rename(idf + ".tmp", idf)
+else:
+    while not os.path.exists(idf):
+        time.sleep(0.05)
+    uid = open(idf, "rb").read()
+W = 10
+ens = GpuEnsembleSystem(spec, W, mc_step=0.4, seed=21, rank=rank, world=world, device=rank, mc_nsteps=2, unique_id=uid)
+R = np.stack([g["R"] + 0.002 * w for w in range(W)])
+ens.SetPositions(R[ens.first_walker:ens.first_walker + ens.n_local])
+e = ens.ParallelUpdateExpectationValues(g["uR"], g["uI"], float(g["phiR"]), float(g["phiI"]), 2, 64, 32, float(g["time"]))
+np.savez(os.path.join(tmp, f"rank{rank}.npz"), **{k: np.asarray(v) for k, v in e.items()})
+ens.close()
+"""
+
+
+def test_two_gpu_allreduce_matches_single_gpu(capi, golden, tmp_path):
+    """Walkers sharded over 2 GPUs + the packed NCCL all-reduce == the same ensemble on one GPU, on every rank."""
+    import subprocess
+    import sys
+
+    if capi.load().tdvmc_gpu_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "worker.py"
+    script.write_text(_MG_WORKER)
+    procs = [subprocess.Popen([sys.executable, str(script), root, str(tmp_path), str(r), "2"]) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=600) == 0
+    g = golden("bosonsbulk_n64_equil")
+    spec, h = make_handle(capi, g, n_walkers=10, seed=21, mc_step=0.4, max_samples=2)
+    h.set_positions(np.stack([g["R"] + 0.002 * w for w in range(10)]))
+    h.sample_and_accumulate(2, 64, 32)
+    one = h.allreduce_and_fetch()
+    h.close()
+    for r in range(2):
+        two = np.load(tmp_path / f"rank{r}.npz")
+        assert int(two["nSamples"]) == 20 and int(two["nTrials"]) == one["n_trials"]
+        assert int(two["nAcceptances"]) == one["n_acceptances"]
+        assert rel(two["localOperators"], one["O"]) < 1e-13
+        assert rel(two["localOperatorsMatrix"], one["S"]) < 1e-13
+        assert rel(two["localOperatorlocalEnergyR"], one["OER"]) < 1e-13
+        assert abs(float(two["localEnergyR"]) - one["e_r"][0]) < 1e-13 * abs(one["e_r"][0])
