@@ -32,6 +32,14 @@ extern "C" {
 
 typedef struct tdvmc_gpu_handle tdvmc_gpu_handle;
 
+enum tdvmc_system_kind
+{
+    TDVMC_SYSTEM_SPLINE_TABLE = 0, /* BosonsBulk, NUBosonsBulkPB: monomial spline table + boundary-condition map */
+    TDVMC_SYSTEM_HE_BULK = 1       /* HeBulk (HeBulk.cpp): McMillan r^-5 core below rijSplit = 1.95, uniform cubic B-splines
+                                      in the local coordinate above it, Aziz HFD-B(He) inline, g(r) in other[3..102];
+                                      knots / spline_weights are not used (may be NULL) */
+};
+
 enum tdvmc_pair_rule
 {
     TDVMC_PAIR_RULE_CUT = 0,    /* BosonsBulk.cpp:195-210: r <= r_max spline, else tail count */
@@ -47,7 +55,7 @@ typedef struct tdvmc_system_desc
     int32_t n_params;          /* N_PARAM */
     int32_t n_splines;         /* K = #knots - 4 (BosonsBulk.cpp:71) */
     int32_t pair_rule;         /* enum tdvmc_pair_rule */
-    int32_t tail_param;        /* parameter that multiplies the tail count in the exponent (BosonsBulk.cpp:532-534) */
+    int32_t tail_param;        /* parameter that multiplies the tail count in the exponent (BosonsBulk.cpp:532-534), -1: none */
     int32_t n_other;           /* length of otherExpectationValues (>= 9) */
     double lbox;               /* LBOX */
     double hbar2_2m;           /* HBAR2_2M (src/Constants.h:12) */
@@ -58,7 +66,14 @@ typedef struct tdvmc_system_desc
     const double* map_val;
     const double* system_params; /* SYSTEM_PARAMS: a, b [, t_switch, a2, b2] (BosonsBulk.cpp:237-243) */
     int32_t n_system_params;
+    int32_t system_kind;       /* enum tdvmc_system_kind */
+    /* Columns of the map beyond the K spline sums (analytic basis sums).  HeBulk: n_ext = K + 1, column K is the
+     * McMillan sum (HeBulk.cpp:376-383).  Spline-table systems: n_ext = K. */
+    int32_t n_ext;
     int32_t reserved;
+    const double* map_const;   /* [N_PARAM] constant part of O_p (HeBulk.cpp:383: 1.0 + ...), NULL = zeros */
+    const double* grad_const;  /* [N_PARAM] constant added to every gradient component of parameter p
+                                  (the literal 1 of HeBulk.cpp:351), NULL = zeros */
 } tdvmc_system_desc;
 
 /* The walker ensemble owned by this rank.  The reference runs one walker per MPI rank, seeded
@@ -133,7 +148,7 @@ int tdvmc_gpu_comm_init(tdvmc_gpu_handle* h, const uint8_t id[TDVMC_GPU_UNIQUE_I
 /* CalculateWavefunction + CalculateExpectationValues on n_cfg given configurations R[n_cfg][N][3]
  * (BosonsBulk.cpp:460-466, 541-545).  Any output pointer may be NULL.
  * e_r/e_i/exponent: [n_cfg]; O: [n_cfg][P]; other: [n_cfg][n_other]; drift_r/drift_i: [n_cfg][N][3]
- * (vecKineticSumR1/I1 per particle, BosonsBulk.cpp:354-420); spline_sums: [n_cfg][K]; outer: [n_cfg]. */
+ * (vecKineticSumR1/I1 per particle, BosonsBulk.cpp:354-420); spline_sums: [n_cfg][n_ext]; outer: [n_cfg]. */
 int tdvmc_gpu_evaluate_fixed(tdvmc_gpu_handle* h, const double* R, int32_t n_cfg, double* e_r, double* e_i,
                              double* O, double* other, double* exponent, double* drift_r, double* drift_i,
                              double* spline_sums, double* outer);

@@ -279,6 +279,76 @@ def gen_nubosonsbulkpb():
               default_moves(R1, L, rng), keep_tables="subset", subset=(0, 7, 100, 215))
 
 
+def hebulk_drift(d, uR, uI):
+    """Drift from the REFERENCE's HeBulk tables with its parameter map (HeBulk.cpp:319-356), long double."""
+    sD = d["sD"].astype(np.longdouble)
+    mc = d["mcmillan_sum_d"].astype(np.longdouble)
+    f11, f12, f21, f22, fSL, fL, fSLP, fLP = [np.longdouble(x) for x in d["bc_factors"]]
+    K, P = sD.shape[0], len(uR)
+    out = []
+    for u in (uR, uI):
+        u = u.astype(np.longdouble)
+        F = u[0] * (mc + f11 * sD[0] + f21 * sD[1]) + u[1] * (sD[2] + f12 * sD[0] + f22 * sD[1])
+        for k in range(2, P - 2):
+            F = F + u[k] * sD[k + 1]
+        F = F + u[P - 2] * (sD[K - 6] + fSL * sD[K - 5] + fL * sD[K - 4])
+        F = F + u[P - 1] * (1 + fSLP * sD[K - 5] + fLP * sD[K - 4])
+        out.append(F.astype(np.float64))
+    return out
+
+
+def pack_eval_hebulk(name, scal, arrays, moves):
+    with tempfile.TemporaryDirectory() as td:
+        cp, op = os.path.join(td, "case.txt"), os.path.join(td, "out.txt")
+        write_case(cp, "HeBulk", scal, arrays, moves)
+        run("eval", cp, op)
+        d = parse_dump(op)
+    out = {"system": np.array("HeBulk"), "N": np.array(scal["N"]), "DIM": np.array(3), "LBOX": np.array(scal["LBOX"]),
+           "N_PARAM": np.array(scal["N_PARAM"]), "SYSTEM_PARAMS": np.zeros(0), "time": np.array(0.0),
+           "R": np.asarray(arrays["R"], np.float64).reshape(-1, 3), "uR": np.asarray(arrays["uR"], np.float64),
+           "uI": np.asarray(arrays["uI"], np.float64), "phiR": np.array(scal.get("phiR", 0.0)),
+           "phiI": np.array(scal.get("phiI", 0.0)), "moves": np.asarray(moves, np.float64).reshape(-1, 4)}
+    for k in ("exponent", "exponent_wf", "wf", "local_energy_r", "local_energy_i", "local_operators",
+              "local_operator_energy_r", "local_operator_energy_i", "other_expectation_values",
+              "local_operators_matrix_diag", "local_operators_matrix_row3", "spline_sums", "mcmillan_sum", "sD", "sD2",
+              "mcmillan_sum_d", "mcmillan_sum_d2", "rij_split", "node_point_spacing", "max_distance", "bc_factors",
+              "move_quotient", "move_exponent_new"):
+        out[k] = d[k]
+    out["drift_r"], out["drift_i"] = hebulk_drift(d, out["uR"], out["uI"])
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(f"{name}: E_R={float(d['local_energy_r']):.12g} E_I={float(d['local_energy_i']):.12g} "
+          f"exponent={float(d['exponent']):.12g} q={d['move_quotient']}")
+    return d
+
+
+def gen_hebulk():
+    """config/bulk_64.config: 64 He-4 atoms at rho = 0.0219 (L = 14.30), N_PARAM = 49, the config's own PARAMS_REAL."""
+    rng = np.random.default_rng(64)
+    cfg = json.load(open(os.path.join(REF, "config", "bulk_64.config")))
+    N, P = int(cfg["N"]), int(cfg["N_PARAM"])
+    L = (N / float(cfg["RHO"])) ** (1.0 / 3.0)
+    uR = np.array(cfg["PARAMS_REAL"], dtype=np.float64)
+    uI = 0.02 * np.sin(0.3 * np.arange(P))           # the config is imaginary-time (uI = 0); exercise the imaginary part
+    # (1) the reference's 64-particle fixture (L=4 lattice-like), scaled to the He box (SURVEY 8c)
+    R = read_csv_positions("particleconfiguration_64.csv").reshape(N, 3) * (L / 4.0)
+    scal = dict(N=N, LBOX=L, N_PARAM=P, phiR=float(cfg["PARAM_PHIR"]), phiI=0.0)
+    arr = dict(R=R, uR=uR, uI=uI)
+    pack_eval_hebulk("hebulk_n64_fixture", scal, arr, default_moves(R, L, rng, sigma=0.3))
+    # (2) equilibrated by the reference's own sampler
+    mc = run_mc("HeBulk", dict(scal, MC_STEP=float(cfg["MC_STEP"]), MC_NSTEPS=1, MC_NTHERMSTEPS=64 * 300, seed=5), arr)
+    R2 = mc["R_final"].reshape(N, 3)
+    pack_eval_hebulk("hebulk_n64_equil", scal, dict(arr, R=R2), default_moves(R2, L, rng, sigma=0.3))
+    # (3) sampler statistics at the config's parameters
+    d = run_mc("HeBulk", dict(scal, MC_STEP=float(cfg["MC_STEP"]), MC_NINITIALIZATIONSTEPS=64 * 300, MC_NSTEPS=4000,
+                              MC_NTHERMSTEPS=64, seed=13), dict(arr, uI=np.zeros(P)))
+    np.savez_compressed(os.path.join(GOLDEN, "hebulk_n64_mc.npz"), N=np.array(N), LBOX=np.array(L), N_PARAM=np.array(P),
+                        MC_STEP=np.array(float(cfg["MC_STEP"])), uR=uR, uI=np.zeros(P), R0=R, n_therm=np.array(64),
+                        energy_r_series=d["energy_r_series"], local_energy_r=d["local_energy_r"],
+                        local_operators=d["local_operators"], other_expectation_values=d["other_expectation_values"],
+                        acceptance=np.array(float(d["n_acceptances"]) / float(d["n_trials"])))
+    print(f"hebulk_n64_mc: <E_R>={float(d['local_energy_r']):.8g} acc={float(d['n_acceptances']) / float(d['n_trials']):.4f}")
+
+
 def gen_min_image():
     """Reference minimum-image displacement on edge cases + random inputs (Utils.cpp:266-281, 352-382)."""
     rng = np.random.default_rng(99)
@@ -309,7 +379,7 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     if not os.path.exists(HARNESS):
         sys.exit("build the oracle first: make -C oracle/ref_build")
-    which = sys.argv[1:] or ["min_image", "bosonsbulk", "bosonsbulk_mc", "nubosonsbulkpb"]
+    which = sys.argv[1:] or ["min_image", "bosonsbulk", "bosonsbulk_mc", "nubosonsbulkpb", "hebulk"]
     for w in which:
         globals()["gen_" + w]()
 

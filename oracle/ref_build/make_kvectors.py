@@ -12,7 +12,7 @@ import sys
 out = sys.argv[1]
 os.makedirs(out, exist_ok=True)
 shells = {}
-m = 8
+m = 21
 for x in range(m + 1):
     for y in range(m + 1):
         for z in range(m + 1):
@@ -21,6 +21,8 @@ for x in range(m + 1):
                 shells.setdefault(n2, []).append([x, y, z])
 keys = sorted(shells)[:400]
 with open(os.path.join(out, "kVectors3D.json"), "w") as f:
+    json.dump({"data": [sorted(shells[k]) for k in keys]}, f)
+with open(os.path.join(out, "kVectors.json"), "w") as f:   # the name HeBulk / HeDrop read (HeBulk.cpp:139)
     json.dump({"data": [sorted(shells[k]) for k in keys]}, f)
 with open(os.path.join(out, "kNorm3D.csv"), "w") as f:
     f.write("\n".join(repr(math.sqrt(k)) for k in keys) + "\n")

@@ -235,6 +235,20 @@ void DumpSystemInternals(Dump& d)
     {
         DumpSplineInternals(d, s);
     }
+    else if (auto s = dynamic_cast<PhysicalSystems::HeBulk*>(sys))
+    {
+        d.vec("spline_sums", s->splineSums);
+        d.scalar("mcmillan_sum", s->mcMillanSum);
+        d.ten("sD", s->splineSumsD);
+        d.mat("sD2", s->splineSumsD2);
+        d.mat("mcmillan_sum_d", s->mcMillanSumD);
+        d.vec("mcmillan_sum_d2", s->mcMillanSumD2);
+        d.scalar("rij_split", s->rijSplit);
+        d.scalar("node_point_spacing", s->nodePointSpacing);
+        d.scalar("max_distance", s->maxDistance);
+        d.vec("bc_factors", { s->factorFirstSpline1, s->factorFirstSpline2, s->factorSecondSpline1, s->factorSecondSpline2,
+                              s->factorSecondLastSpline, s->factorLastSpline, s->factorSecondLastSplinePhi, s->factorLastSplinePhi });
+    }
 }
 
 int ModeEval(const Case& c, const std::string& out)

@@ -97,3 +97,49 @@ int64_t oracle_sample_walker(const oracle_system* s, double* R, const double* uR
 }
 #endif
 #endif
+
+/* ------------------------------------------------------------------------------------------------
+ * HeBulk (src/PhysicalSystems/HeBulk.cpp): periodic He-4, McMillan r^-5 core + uniform cubic
+ * B-splines in the local coordinate, Aziz HFD-B(He) potential inline, g(r) in other[3..102].
+ * ------------------------------------------------------------------------------------------------ */
+#ifndef TDVMC_ORACLE_HE_H
+#define TDVMC_ORACLE_HE_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct oracle_hebulk
+{
+    int32_t n_particles, n_params, n_splines, gr_bins;
+    double lbox, rij_split, h, max_distance, hbar2_2m;
+    double f[8]; /* factorFirstSpline1, FirstSpline2, SecondSpline1, SecondSpline2, SecondLastSpline, LastSpline,
+                    SecondLastSplinePhi, LastSplinePhi (HeBulk.cpp:57-67) */
+} oracle_hebulk;
+
+/* HeBulk::InitSystem (HeBulk.cpp:40-70) */
+void oracle_hebulk_init(oracle_hebulk* s, int n_particles, double lbox, int n_params);
+/* value sums of CalculateWavefunction (HeBulk.cpp:462-489) */
+void oracle_hebulk_values(const oracle_hebulk* s, const double* R, double* ss, double* mcm);
+/* localOperators (HeBulk.cpp:376-383) and the exponent (:491-498) */
+void oracle_hebulk_operators(const oracle_hebulk* s, const double* ss, double mcm, double* O);
+double oracle_hebulk_exponent(const oracle_hebulk* s, const double* ss, double mcm, const double* uR);
+/* CalculateExpectationValues (HeBulk.cpp:166-405). other: [3 + gr_bins]; drift_*: [N][3] or NULL;
+ * sD [K][N][3], sD2 [K][N], mcD [N][3], mcD2 [N]: caller-provided scratch (also outputs). */
+void oracle_hebulk_expectation(const oracle_hebulk* s, const double* R, double wf, const double* uR, const double* uI,
+                               double* e_r, double* e_i, double* other, double* drift_r, double* drift_i, double* sD,
+                               double* sD2, double* mcD, double* mcD2);
+/* CalculateWFChange / Quotient (HeBulk.cpp:512-604) */
+double oracle_hebulk_quotient(const oracle_hebulk* s, const double* R, int particle, const double* old_pos, const double* ss,
+                              double mcm, double exponent, const double* uR, double* ss_new, double* mcm_new,
+                              double* exponent_new);
+int64_t oracle_hebulk_sweep(const oracle_hebulk* s, double* R, double* ss, double* mcm, double* exponent, const double* uR,
+                            uint64_t seed, uint32_t walker, uint64_t first_step, int64_t n_steps, double mc_step);
+/* est: [O(P) | E_R | E_I | S(P*P) | OE_R(P) | OE_I(P) | other(3 + gr_bins)] sums; rows: per sample [O(P), E_R, E_I] */
+int64_t oracle_hebulk_sample_walker(const oracle_hebulk* s, double* R, const double* uR, const double* uI, uint64_t seed,
+                                    uint32_t walker, uint64_t* step_counter, int n_init, int n_samples, int n_therm,
+                                    double mc_step, double* est, double* sample_rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -23,7 +23,8 @@ class SystemDesc(C.Structure):
                 ("n_splines", C.c_int32), ("pair_rule", C.c_int32), ("tail_param", C.c_int32), ("n_other", C.c_int32),
                 ("lbox", C.c_double), ("hbar2_2m", C.c_double), ("knots", dp), ("spline_weights", dp), ("map_ptr", ip),
                 ("map_col", ip), ("map_val", dp), ("system_params", dp), ("n_system_params", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("system_kind", C.c_int32), ("n_ext", C.c_int32), ("reserved", C.c_int32), ("map_const", dp),
+                ("grad_const", dp)]
 
 
 class EnsembleDesc(C.Structure):
@@ -111,16 +112,19 @@ class Handle:
         self.lib = lib
         self.spec = spec
         self.N, self.P, self.K, self.n_other = spec.n_particles, spec.n_params, spec.n_splines, spec.n_other
+        self.n_ext = spec.n_ext
         self.W = int(n_walkers)
         self._keep = dict(knots=np.ascontiguousarray(spec.knots, np.float64),
                           w=np.ascontiguousarray(spec.weights, np.float64).reshape(-1),
                           mp=np.ascontiguousarray(spec.map_ptr, np.int32), mc=np.ascontiguousarray(spec.map_col, np.int32),
                           mv=np.ascontiguousarray(spec.map_val, np.float64),
-                          sp=np.ascontiguousarray(spec.system_params, np.float64))
+                          sp=np.ascontiguousarray(spec.system_params, np.float64),
+                          mk=np.ascontiguousarray(spec.map_const, np.float64), gk=np.ascontiguousarray(spec.grad_const, np.float64))
         k = self._keep
         sd = SystemDesc(C.sizeof(SystemDesc), spec.n_particles, spec.dim, spec.n_params, spec.n_splines, spec.pair_rule,
                         spec.tail_param, spec.n_other, spec.lbox, spec.hbar2_2m, _d(k["knots"]), _d(k["w"]),
-                        k["mp"].ctypes.data_as(ip), k["mc"].ctypes.data_as(ip), _d(k["mv"]), _d(k["sp"]), len(k["sp"]), 0)
+                        k["mp"].ctypes.data_as(ip), k["mc"].ctypes.data_as(ip), _d(k["mv"]), _d(k["sp"]), len(k["sp"]),
+                        spec.kind, spec.n_ext, 0, _d(k["mk"]), _d(k["gk"]))
         ed = EnsembleDesc(C.sizeof(EnsembleDesc), device, self.W, first_walker, max_samples, int(keep_sample_positions),
                           seed, mc_step)
         h = _VP()
@@ -204,7 +208,7 @@ class Handle:
         n = R.shape[0]
         o = dict(e_r=np.empty(n), e_i=np.empty(n), O=np.empty((n, self.P)), other=np.empty((n, self.n_other)),
                  exponent=np.empty(n), drift_r=np.empty((n, self.N, 3)), drift_i=np.empty((n, self.N, 3)),
-                 ss=np.empty((n, self.K)), outer=np.empty(n))
+                 ss=np.empty((n, self.n_ext)), outer=np.empty(n))
         self._ck(self.lib.tdvmc_gpu_evaluate_fixed(self.h, _d(R), n, _d(o["e_r"]), _d(o["e_i"]), _d(o["O"]), _d(o["other"]),
                                                    _d(o["exponent"]), _d(o["drift_r"]), _d(o["drift_i"]), _d(o["ss"]),
                                                    _d(o["outer"])), "evaluate_fixed")

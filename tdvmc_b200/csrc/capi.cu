@@ -106,7 +106,9 @@ struct tdvmc_gpu_handle
     cudaStream_t stream = nullptr;
 
     // system (host copies)
-    int N = 0, Np = 0, P = 0, K = 0, pair_rule = 0, tail_param = 0, n_other = 9;
+    int N = 0, Np = 0, P = 0, K = 0, pair_rule = 0, tail_param = 0, n_other = 9, kind = 0, n_ext = 0, gr_bins = 0;
+    double he_rs = 0, core_m = 0;
+    std::vector<double> map_const, grad_const;
     double L = 0, hbar = 1.0;
     std::vector<double> knots, weights, map_val, sys_params, uR, uI;
     std::vector<int> map_ptr, map_col;
@@ -124,7 +126,7 @@ struct tdvmc_gpu_handle
     int wpb = 8, npp = 0, resident_per_sm = 0;
 
     // device tables
-    DevBuf<double> d_knots, d_rec, d_cub, d_map_val, d_uR, d_uI, d_utR, d_utI;
+    DevBuf<double> d_knots, d_rec, d_cub, d_map_val, d_uR, d_uI, d_utR, d_utI, d_map_const;
     DevBuf<unsigned short> d_lut;
     DevBuf<int> d_map_ptr, d_map_col;
     // walkers and samples
@@ -253,6 +255,25 @@ void potential_ab(const tdvmc_gpu_handle* h, double& a, double& b)
 int build_static_tables(tdvmc_gpu_handle* h)
 {
     const int K = h->K;
+    if (h->kind == TDVMC_SYSTEM_HE_BULK)
+    {
+        // HeBulk::InitSystem (HeBulk.cpp:40-70): uniform grid of K - 3 intervals from rijSplit to L/2
+        h->he_rs = 1.95;
+        h->core_m = -5.0;
+        h->gr_bins = 100;
+        h->first_bin = 0;
+        h->nbins = K - 3;
+        h->uniform = 1;
+        h->ncell = 1;
+        h->h = (h->L / 2.0 - h->he_rs) / (double)(K - 3.0);
+        CK(upload(h->d_map_ptr, h->map_ptr, h->stream));
+        CK(upload(h->d_map_col, h->map_col, h->stream));
+        CK(upload(h->d_map_val, h->map_val, h->stream));
+        CK(upload(h->d_map_const, h->map_const, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    CK(upload(h->d_map_const, h->map_const, h->stream));
     const std::vector<double>& t = h->knots;
     // first interval a distance can fall in: knots[first_bin] <= 0 < knots[first_bin + 1]
     int fb = 0;
@@ -304,7 +325,7 @@ int build_static_tables(tdvmc_gpu_handle* h)
 int build_param_tables(tdvmc_gpu_handle* h)
 {
     const int K = h->K, P = h->P, fb = h->first_bin;
-    std::vector<double> utR(K, 0.0), utI(K, 0.0);
+    std::vector<double> utR(h->n_ext, 0.0), utI(h->n_ext, 0.0);
     for (int p = 0; p < P; p++)
         for (int j = h->map_ptr[p]; j < h->map_ptr[p + 1]; j++)
         {
@@ -317,7 +338,29 @@ int build_param_tables(tdvmc_gpu_handle* h)
     // uR[tail_param] every pair beyond r_max contributes (BosonsBulk.cpp:532-534)
     const int nrec = h->nbins + 1;
     std::vector<double> cub((size_t)nrec * 6, 0.0);
-    for (int rec = 0; rec < h->nbins; rec++)
+    if (h->kind == TDVMC_SYSTEM_HE_BULK)
+    {
+        // u(r) on interval j of the uniform grid: sum_b u~[j+b] beta_b(res), res = (r - rs)/h - j, with the cubic
+        // B-spline pieces of HeBulk.cpp:483-486 as polynomials in res; stored in powers of s = res h
+        static const long double beta[4][4] = { { 1.0L / 6, -3.0L / 6, 3.0L / 6, -1.0L / 6 },
+                                                { 4.0L / 6, 0.0L, -6.0L / 6, 3.0L / 6 },
+                                                { 1.0L / 6, 3.0L / 6, 3.0L / 6, -3.0L / 6 },
+                                                { 0.0L, 0.0L, 0.0L, 1.0L / 6 } };
+        const long double hh = h->h;
+        for (int rec = 0; rec < h->nbins; rec++)
+        {
+            long double C[4] = { 0, 0, 0, 0 };
+            for (int b = 0; b < 4; b++)
+                for (int c = 0; c < 4; c++) C[c] += (long double)utR[rec + b] * beta[b][c];
+            cub[(size_t)rec * 2 + 0] = (double)C[0];
+            cub[(size_t)rec * 2 + 1] = (double)(C[1] / hh);
+            cub[(size_t)(nrec + rec) * 2 + 0] = (double)(C[2] / (hh * hh));
+            cub[(size_t)(nrec + rec) * 2 + 1] = (double)(C[3] / (hh * hh * hh));
+            cub[(size_t)(2 * nrec + rec) * 2 + 0] = h->he_rs + rec * h->h;
+            cub[(size_t)(2 * nrec + rec) * 2 + 1] = h->he_rs + (rec + 1) * h->h;
+        }
+    }
+    for (int rec = 0; h->kind != TDVMC_SYSTEM_HE_BULK && rec < h->nbins; rec++)
     {
         const int b = fb + rec;
         long double C[4] = { 0, 0, 0, 0 };
@@ -333,7 +376,7 @@ int build_param_tables(tdvmc_gpu_handle* h)
         cub[(size_t)(2 * nrec + rec) * 2 + 1] = h->knots[b + 1];
     }
     cub[(size_t)h->nbins * 2 + 0] = h->tail_param >= 0 ? h->uR[h->tail_param] : 0.0;
-    cub[(size_t)(2 * nrec + h->nbins) * 2 + 0] = h->knots[K];
+    cub[(size_t)(2 * nrec + h->nbins) * 2 + 0] = h->kind == TDVMC_SYSTEM_HE_BULK ? h->L / 2.0 : h->knots[K];
     cub[(size_t)(2 * nrec + h->nbins) * 2 + 1] = 1e300;
     CK(upload(h->d_uR, h->uR, h->stream));
     CK(upload(h->d_uI, h->uI, h->stream));
@@ -360,16 +403,32 @@ SysDev tdvmc_gpu_handle::sysdev() const
     s.pair_rule = pair_rule; s.tail_param = tail_param; s.n_other = n_other;
     s.first_bin = first_bin; s.nbins = nbins; s.ncell = ncell; s.uniform = uniform;
     s.L = L; s.Linv = 1.0 / L; s.Lhalf = L / 2.0; // src/TDVMC.cpp:535-536
-    s.rmax = knots[K];
+    s.kind = kind; s.n_ext = n_ext; s.gr_bins = gr_bins;
+    s.rmax = kind == TDVMC_SYSTEM_HE_BULK ? L / 2.0 : knots[K]; // HeBulk.cpp:54
     s.hbar = hbar;
-    potential_ab(this, s.pot_a, s.pot_b);
+    s.r0 = he_rs; s.core_m = core_m;
+    s.u_core = 0.0; s.g0R = 0.0; s.g0I = 0.0;
+    if (params_set)
+    {
+        for (int p = 0; p < P; p++)
+        {
+            s.g0R += uR[p] * grad_const[p];
+            s.g0I += uI[p] * grad_const[p];
+        }
+        if (kind == TDVMC_SYSTEM_HE_BULK) // u~ of the McMillan column K
+            for (int p = 0; p < P; p++)
+                for (int j = map_ptr[p]; j < map_ptr[p + 1]; j++)
+                    if (map_col[j] == K) s.u_core += uR[p] * map_val[j];
+    }
+    if (kind == TDVMC_SYSTEM_SPLINE_TABLE) potential_ab(this, s.pot_a, s.pot_b);
     s.phiR = phiR;
     s.inv_cell = ncell / s.rmax;
     s.h = h; s.inv_h = 1.0 / h;
     s.u_tail = (params_set && tail_param >= 0) ? uR[tail_param] : 0.0;
+    if (tail_param < 0) s.tail_param = 0; // kernels index uR[tail_param]; the tail count is zero for these systems
     s.knots = d_knots.p; s.rec = d_rec.p; s.cub = d_cub.p; s.lut = d_lut.p;
     s.map_ptr = d_map_ptr.p; s.map_col = d_map_col.p; s.map_val = d_map_val.p;
-    s.uR = d_uR.p; s.uI = d_uI.p; s.utR = d_utR.p; s.utI = d_utI.p;
+    s.uR = d_uR.p; s.uI = d_uI.p; s.utR = d_utR.p; s.utI = d_utI.p; s.map_const = d_map_const.p;
     return s;
 }
 
@@ -399,8 +458,11 @@ int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed,
         g_create_error = "struct_size mismatch (ABI version)";
         return -1;
     }
-    if (sd->dim != 3 || sd->n_particles < 2 || sd->n_params < 1 || sd->n_splines < 4 || ed->n_walkers < 1 || sd->n_other < 9 ||
-        sd->tail_param < 0 || sd->tail_param >= sd->n_params || !(sd->lbox > 0.0))
+    if (sd->dim != 3 || sd->n_particles < 2 || sd->n_params < 1 || sd->n_splines < 4 || ed->n_walkers < 1 || sd->n_other < 3 ||
+        sd->tail_param < -1 || sd->tail_param >= sd->n_params || !(sd->lbox > 0.0) || sd->n_ext < sd->n_splines ||
+        (sd->system_kind != TDVMC_SYSTEM_SPLINE_TABLE && sd->system_kind != TDVMC_SYSTEM_HE_BULK) ||
+        (sd->system_kind == TDVMC_SYSTEM_SPLINE_TABLE && (!sd->knots || !sd->spline_weights || sd->n_other < 9)) ||
+        (sd->system_kind == TDVMC_SYSTEM_HE_BULK && (sd->n_ext != sd->n_splines + 1 || sd->n_other != 103)))
     {
         g_create_error = "invalid system/ensemble description";
         return -1;
@@ -445,14 +507,20 @@ int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed,
     h->n_other = sd->n_other;
     h->L = sd->lbox;
     h->hbar = sd->hbar2_2m;
-    h->knots.assign(sd->knots, sd->knots + h->K + 4);
-    h->weights.assign(sd->spline_weights, sd->spline_weights + (size_t)h->K * 16);
+    h->kind = sd->system_kind;
+    h->n_ext = sd->n_ext;
+    if (sd->knots) h->knots.assign(sd->knots, sd->knots + h->K + 4);
+    if (sd->spline_weights) h->weights.assign(sd->spline_weights, sd->spline_weights + (size_t)h->K * 16);
+    h->map_const.assign(h->P, 0.0);
+    h->grad_const.assign(h->P, 0.0);
+    if (sd->map_const) h->map_const.assign(sd->map_const, sd->map_const + h->P);
+    if (sd->grad_const) h->grad_const.assign(sd->grad_const, sd->grad_const + h->P);
     h->map_ptr.assign(sd->map_ptr, sd->map_ptr + h->P + 1);
     const int nnz = h->map_ptr[h->P];
     h->map_col.assign(sd->map_col, sd->map_col + nnz);
     h->map_val.assign(sd->map_val, sd->map_val + nnz);
     for (int c : h->map_col)
-        if (c < 0 || c >= h->K)
+        if (c < 0 || c >= h->n_ext)
         {
             h->error = "boundary map column out of range";
             return bail(-1);
@@ -663,7 +731,7 @@ static int do_evaluate_walkers(tdvmc_gpu_handle* h, const double* pos, int n_cfg
     a.other = h->d_other.p;
     a.exponent = h->d_exponent.p;
     Timed t(h, TDVMC_KERNEL_EVALUATE);
-    CK(launch_evaluate(a, h->stream));
+    CK(h->kind == TDVMC_SYSTEM_HE_BULK ? launch_evaluate_he(a, h->stream) : launch_evaluate(a, h->stream));
     return 0;
 }
 
@@ -840,7 +908,7 @@ int tdvmc_gpu_evaluate_fixed(tdvmc_gpu_handle* h, const double* R, int32_t n_cfg
     if (!h || !R || n_cfg < 1) return h ? fail(h, "evaluate_fixed: bad arguments") : -1;
     if (int rc = need_params(h)) return rc;
     CK(cudaSetDevice(h->device));
-    const int N = h->N, P = h->P, K = h->K;
+    const int N = h->N, P = h->P, K = h->n_ext;
     DevBuf<double> aos, pos, A, oth, ex, dr, di, ss, out;
     CK(aos.alloc((size_t)n_cfg * N * 3));
     CK(pos.alloc((size_t)n_cfg * 3 * h->Np));
@@ -872,7 +940,7 @@ int tdvmc_gpu_evaluate_fixed(tdvmc_gpu_handle* h, const double* R, int32_t n_cfg
     a.outer_out = out.p;
     {
         Timed t(h, TDVMC_KERNEL_EVALUATE);
-        CK(launch_evaluate(a, h->stream));
+        CK(h->kind == TDVMC_SYSTEM_HE_BULK ? launch_evaluate_he(a, h->stream) : launch_evaluate(a, h->stream));
     }
     std::vector<double> hA((size_t)n_cfg * h->lda);
     CK(cudaMemcpyAsync(hA.data(), A.p, hA.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -930,6 +998,7 @@ int tdvmc_gpu_quotient_fixed(tdvmc_gpu_handle* h, const double* R, const double*
 
 static int run_tables(tdvmc_gpu_handle* h, const double* pos, int n_cfg)
 {
+    if (h->kind != TDVMC_SYSTEM_SPLINE_TABLE) return fail(h, "the table kernels cover the spline-table systems only");
     CK(h->d_T.ensure((size_t)n_cfg * h->N * h->K * 4));
     CK(h->d_vint.ensure(n_cfg));
     CK(h->d_tab_e.ensure((size_t)n_cfg * 7));

@@ -28,6 +28,9 @@ struct SysDev
     int nbins;        // K - first_bin
     int ncell;        // cells of the uniform bin lookup grid
     int uniform;      // != 0: knots are a uniform grid, interval index = floor(r / h)
+    int kind;         // TDVMC_SYSTEM_*: 0 spline table (BosonsBulk, NUBosonsBulkPB), 1 HeBulk
+    int n_ext;        // columns of the parameter map: K spline sums + analytic extras
+    int gr_bins;      // g(r) bins carried in other[] (HeBulk: 100)
     double L, Linv, Lhalf;   // LBOX, 1/LBOX, LBOX/2 (src/TDVMC.cpp:535-536)
     double rmax;             // maxDistance = knots[K]
     double hbar;             // HBAR2_2M
@@ -36,6 +39,10 @@ struct SysDev
     double inv_cell;         // ncell / rmax
     double h, inv_h;         // uniform knot spacing
     double u_tail;           // uR[tail_param]
+    double r0;               // start of the uniform spline grid (HeBulk: rijSplit; 0 otherwise)
+    double core_m;           // McMillan exponent (HeBulk: -5)
+    double u_core;           // u~ of the McMillan column
+    double g0R, g0I;         // sum_p u_p grad_const[p]: the literal gradient constant (HeBulk.cpp:351)
     const double* knots;     // [K+4]
     const double* rec;       // [nbins][kRecStride]: piece p of spline (bin-p) at [p*4 + c]
     const double* cub;       // sweep table, 3 planes of (nbins+1) double2: [c0,c1] | [c2,c3] | [t_lo,t_hi];
@@ -46,8 +53,9 @@ struct SysDev
     const double* map_val;
     const double* uR;        // [P]
     const double* uI;        // [P]
-    const double* utR;       // [K]  parameters in spline space, u~_k = sum_p u_p M[p][k]
-    const double* utI;       // [K]
+    const double* utR;       // [n_ext]  parameters in spline space, u~_k = sum_p u_p M[p][k]
+    const double* utI;       // [n_ext]
+    const double* map_const; // [P] constant part of O_p
 };
 
 // ---- minimum image -------------------------------------------------------------------------

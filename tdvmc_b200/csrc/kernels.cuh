@@ -46,6 +46,7 @@ struct EvalArgs
     double* outer_out;      // [n_cfg] or null
 };
 cudaError_t launch_evaluate(const EvalArgs& a, cudaStream_t st);
+cudaError_t launch_evaluate_he(const EvalArgs& a, cudaStream_t st); // HeBulk (evaluate_he.cu)
 
 // single-particle move ratios for scripted moves of one configuration (quotient_fixed)
 struct QuotientArgs

@@ -65,7 +65,7 @@ __device__ __forceinline__ double sqrt_fast(double x)
 }
 
 // pair term of the exponent at distance r, with the system's cut rule
-template <bool UNIFORM, bool REFLECT, int STRIDE>
+template <bool UNIFORM, bool REFLECT, int STRIDE, bool HE = false>
 __device__ __forceinline__ double pair_u(const SysDev& s, const double2* __restrict__ c01p, const double2* __restrict__ c23p,
                                          const double2* __restrict__ ttp, const unsigned short* __restrict__ lut, double r)
 {
@@ -73,6 +73,12 @@ __device__ __forceinline__ double pair_u(const SysDev& s, const double2* __restr
     // nbins of the table holds exactly that constant, so the cut needs no compare/select.  (At r == r_max
     // the reference's '<=' (:571) / '<' (:593) pick the spline or the tail; a null set for sampling.)
     if (REFLECT) r = (r < s.rmax) ? r : 2.0 * s.rmax - r; // NUBosonsBulkPB.cpp:689-692
+    if (HE)
+    {
+        // HeBulk: McMillan core u~_mc r^m below rijSplit (HeBulk.cpp:471-474); the uniform grid starts at rijSplit
+        if (r < s.r0) return s.u_core * pow(r, s.core_m);
+        r -= s.r0;
+    }
     // floor(r * inv) via the rounding constant; the integer sits in the low word
     const double y = fma(r, UNIFORM ? s.inv_h : s.inv_cell, -0.5) + kMagic;
     const int c = __double2loint(y);
@@ -100,7 +106,7 @@ __device__ __forceinline__ double pair_u(const SysDev& s, const double2* __restr
     return v;
 }
 
-template <bool UNIFORM, bool REFLECT, int UNROLL>
+template <bool UNIFORM, bool REFLECT, int UNROLL, bool HE = false>
 __global__ void __launch_bounds__(kSweepMaxThreads, kSweepMinBlocks) sweep_kernel(SweepArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -188,8 +194,8 @@ __global__ void __launch_bounds__(kSweepMaxThreads, kSweepMinBlocks) sweep_kerne
                 const double xi = px[i], yi = py[i], zi = pz[i];
                 const double r_old = sqrt_fast(mi2_wrapped(xi - ox, yi - oy, zi - oz, Lhalf));
                 const double r_new = sqrt_fast(mi2_wrapped(xi - nx, yi - ny, zi - nz, Lhalf));
-                const double u_old = pair_u<UNIFORM, REFLECT, kCubCopies>(s, c01p, c23p, ttp, lut, r_old);
-                const double u_new = pair_u<UNIFORM, REFLECT, kCubCopies>(s, c01p, c23p, ttp, lut, r_new);
+                const double u_old = pair_u<UNIFORM, REFLECT, kCubCopies, HE>(s, c01p, c23p, ttp, lut, r_old);
+                const double u_new = pair_u<UNIFORM, REFLECT, kCubCopies, HE>(s, c01p, c23p, ttp, lut, r_new);
                 const double d = u_new - u_old;
                 if (i != p) delta += d;
             }
@@ -223,7 +229,7 @@ __global__ void __launch_bounds__(kSweepMaxThreads, kSweepMinBlocks) sweep_kerne
 
 // exponentNew - exponent for scripted moves of one configuration: the ratio evaluator of the sweep,
 // one warp per move, tables read straight from global memory (parity entry point, not a hot path)
-template <bool UNIFORM, bool REFLECT>
+template <bool UNIFORM, bool REFLECT, bool HE = false>
 __global__ void quotient_kernel(QuotientArgs a)
 {
     const SysDev& s = a.s;
@@ -247,8 +253,8 @@ __global__ void quotient_kernel(QuotientArgs a)
         const double xi = wrap_fast(px[i], L, Linv), yi = wrap_fast(py[i], L, Linv), zi = wrap_fast(pz[i], L, Linv);
         const double r_old = sqrt_fast(mi2_wrapped(xi - ox, yi - oy, zi - oz, Lhalf));
         const double r_new = sqrt_fast(mi2_wrapped(xi - nx, yi - ny, zi - nz, Lhalf));
-        const double d = pair_u<UNIFORM, REFLECT, 1>(s, c01p, c23p, ttp, s.lut, r_new) -
-                         pair_u<UNIFORM, REFLECT, 1>(s, c01p, c23p, ttp, s.lut, r_old);
+        const double d = pair_u<UNIFORM, REFLECT, 1, HE>(s, c01p, c23p, ttp, s.lut, r_new) -
+                         pair_u<UNIFORM, REFLECT, 1, HE>(s, c01p, c23p, ttp, s.lut, r_old);
         if (i != p) delta += d;
     }
     delta = warp_sum(delta);
@@ -259,7 +265,11 @@ cudaError_t launch_quotient(const QuotientArgs& a, cudaStream_t st)
 {
     if (a.n_moves <= 0) return cudaSuccess;
     const bool refl = a.s.pair_rule == 1;
-    if (a.s.uniform)
+    if (a.s.kind == 1)
+    {
+        quotient_kernel<true, false, true><<<a.n_moves, 32, 0, st>>>(a);
+    }
+    else if (a.s.uniform)
     {
         if (refl) quotient_kernel<true, true><<<a.n_moves, 32, 0, st>>>(a);
         else quotient_kernel<true, false><<<a.n_moves, 32, 0, st>>>(a);
@@ -282,13 +292,13 @@ size_t sweep_smem_bytes(const SysDev& s, int wpb, int npp, size_t* pos_offset)
     return off + (size_t)wpb * 3 * npp * sizeof(double);
 }
 
-template <bool U, bool R, int UNROLL>
+template <bool U, bool R, int UNROLL, bool HE = false>
 static cudaError_t launch_one(const SweepArgs& a, int grid, int threads, size_t smem, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<U, R, UNROLL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<U, R, UNROLL, HE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    cudaFuncSetAttribute(sweep_kernel<U, R, UNROLL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    sweep_kernel<U, R, UNROLL><<<grid, threads, smem, st>>>(a);
+    cudaFuncSetAttribute(sweep_kernel<U, R, UNROLL, HE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    sweep_kernel<U, R, UNROLL, HE><<<grid, threads, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -308,6 +318,7 @@ template <int UNROLL>
 static const void* sweep_fn(const SysDev& s)
 {
     const bool refl = s.pair_rule == 1;
+    if (s.kind == 1) return (const void*)sweep_kernel<true, false, UNROLL, true>;
     return s.uniform ? (refl ? (const void*)sweep_kernel<true, true, UNROLL> : (const void*)sweep_kernel<true, false, UNROLL>)
                      : (refl ? (const void*)sweep_kernel<false, true, UNROLL> : (const void*)sweep_kernel<false, false, UNROLL>);
 }
@@ -316,6 +327,7 @@ template <int UNROLL>
 static cudaError_t launch_unroll(const SweepArgs& a, int grid, int threads, size_t smem, cudaStream_t st)
 {
     const bool refl = a.s.pair_rule == 1;
+    if (a.s.kind == 1) return launch_one<true, false, UNROLL, true>(a, grid, threads, smem, st);
     if (a.s.uniform)
         return refl ? launch_one<true, true, UNROLL>(a, grid, threads, smem, st) : launch_one<true, false, UNROLL>(a, grid, threads, smem, st);
     return refl ? launch_one<false, true, UNROLL>(a, grid, threads, smem, st) : launch_one<false, false, UNROLL>(a, grid, threads, smem, st);

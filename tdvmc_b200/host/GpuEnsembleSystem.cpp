@@ -113,7 +113,11 @@ GpuEnsembleSystem::GpuEnsembleSystem(const SystemTables& tb, int walkersTotal, d
     sd.map_val = tb.map_val.data();
     sd.system_params = tb.system_params.data();
     sd.n_system_params = (int32_t)tb.system_params.size();
+    sd.system_kind = tb.system_kind;
+    sd.n_ext = tb.n_ext > 0 ? tb.n_ext : sd.n_splines;
     sd.reserved = 0;
+    sd.map_const = tb.map_const.empty() ? nullptr : tb.map_const.data();
+    sd.grad_const = tb.grad_const.empty() ? nullptr : tb.grad_const.data();
     tdvmc_ensemble_desc ed;
     ed.struct_size = sizeof(ed);
     ed.device = device;

@@ -38,6 +38,9 @@ struct SystemTables
     std::vector<int32_t> map_ptr, map_col; // boundary-condition map, CSR over parameters
     std::vector<double> map_val;
     std::vector<double> system_params;     // SYSTEM_PARAMS
+    int system_kind = TDVMC_SYSTEM_SPLINE_TABLE;
+    int n_ext = 0;                         // 0: number of splines
+    std::vector<double> map_const, grad_const; // empty: zeros
 };
 
 // Flattens the reference's vector<vector<vector<double>>> splineWeights (SplineFactory::GetWeights3).

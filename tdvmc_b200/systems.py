@@ -18,6 +18,9 @@ from . import splines
 PAIR_RULE_CUT = 0      # r <= r_max -> spline, else tail count        (BosonsBulk.cpp:195-210)
 PAIR_RULE_REFLECT = 1  # r -> 2 r_max - r beyond r_max, then r < r_max (NUBosonsBulkPB.cpp:249-269)
 
+KIND_SPLINE_TABLE = 0   # BosonsBulk, NUBosonsBulkPB: monomial spline table + boundary map
+KIND_HE_BULK = 1        # HeBulk: McMillan core + uniform B-splines in the local coordinate + Aziz potential
+
 HBAR2_2M = 1.0  # src/Constants.h:12
 
 
@@ -38,15 +41,27 @@ class SystemSpec:
     dim: int = 3
     hbar2_2m: float = HBAR2_2M
     tail_param: int = -1
+    kind: int = KIND_SPLINE_TABLE
+    n_ext: int = 0                  # columns of the map: K spline sums (+ analytic extras, e.g. the McMillan sum)
+    map_const: np.ndarray = None    # [P] constant added to O_p (HeBulk.cpp:383: the literal 1.0 of the last operator)
+    grad_const: np.ndarray = None   # [P] constant added to every gradient component of parameter p (HeBulk.cpp:351)
     extra: dict = field(default_factory=dict)
+
+    def __post_init__(self):
+        if not self.n_ext:
+            self.n_ext = len(self.knots) - 4
+        if self.map_const is None:
+            self.map_const = np.zeros(self.n_params)
+        if self.grad_const is None:
+            self.grad_const = np.zeros(self.n_params)
 
     @property
     def n_splines(self):
-        return len(self.knots) - 4
+        return int(self.extra["n_splines"]) if "n_splines" in self.extra else len(self.knots) - 4
 
     @property
     def r_max(self):
-        return float(self.knots[len(self.knots) - 4])
+        return float(self.extra["r_max"]) if "r_max" in self.extra else float(self.knots[len(self.knots) - 4])
 
     def potential(self, time):
         """Square-well (a, b) with the time switch of BosonsBulk.cpp:237-243 / NUBosonsBulkPB.cpp:300-307."""
@@ -62,7 +77,7 @@ class SystemSpec:
 
     def spline_space(self, u):
         """u~_k = sum_p u_p M[p][k]: parameters pushed through the transposed boundary map."""
-        ut = np.zeros(self.n_splines, dtype=np.float64)
+        ut = np.zeros(self.n_ext, dtype=np.float64)
         for p, row in enumerate(self.map_rows()):
             for k, f in row:
                 ut[k] += u[p] * f
@@ -124,10 +139,41 @@ def nu_bosons_bulk_pb(n_particles, lbox, n_params, nurbs_grid, system_params=(0.
                       tail_param=n_params - 1)
 
 
+def he_bulk(n_particles, lbox, n_params):
+    """``HeBulk`` (HeBulk.cpp:40-70): ``K = P + 5`` uniform splines of spacing ``h = (L/2 - rs)/(K - 3)`` starting at the
+    McMillan split ``rs = 1.95``; extended sums are ``[ss_0 .. ss_{K-1}, mcMillanSum]``; parameter map of :376-383 with
+    the constant 1 of the last operator and the literal 1 added to its gradient (:351)."""
+    P = n_params
+    K = P - 1 + 3 + 3
+    rs = 1.95
+    half = lbox / 2.0
+    h = (half - rs) / float(K - 3.0)
+    f11 = 10.0 * h / rs ** 6.0
+    f21 = (-5.0 * h + 3.0 * rs) / (2.0 * rs ** 6.0)
+    MC = K  # column of the McMillan sum
+    rows = [[(MC, 1.0), (0, f11), (1, f21)], [(2, 1.0), (0, 1.0), (1, -0.5)]]
+    rows += [[(i + 1, 1.0)] for i in range(2, P - 2)]
+    rows += [[(K - 6, 1.0), (K - 5, -0.5), (K - 4, 1.0)], [(K - 5, -1.5), (K - 4, 0.0)]]
+    ptr, col, val = _csr(rows)
+    mconst = np.zeros(P)
+    mconst[P - 1] = 1.0
+    gconst = np.zeros(P)
+    gconst[P - 1] = 1.0
+    knots = rs + h * np.arange(-3, K + 1, dtype=np.float64)   # informational only: the kernels use (rs, h)
+    return SystemSpec("HeBulk", n_particles, P, float(lbox), knots, np.zeros((K, 4, 4)), ptr, col, val, PAIR_RULE_CUT,
+                      np.zeros(0), n_other=3 + 100, tail_param=-1, kind=KIND_HE_BULK, n_ext=K + 1, map_const=mconst,
+                      grad_const=gconst, extra=dict(n_splines=K, r_max=half, rij_split=rs, h=h, factors=(f11, 1.0, f21, -0.5, -0.5, 1.0, -1.5, 0.0)))
+
+
 def from_golden(g):
     """Build the spec of a tests/golden fixture, taking knots and spline table from the reference dump."""
     name = str(g["system"])
     N, L, P = int(g["N"]), float(g["LBOX"]), int(g["N_PARAM"])
+    if name == "HeBulk":
+        spec = he_bulk(N, L, P)
+        if spec.extra["h"] != float(g["node_point_spacing"]) or not np.array_equal(spec.extra["factors"], g["bc_factors"]):
+            raise AssertionError("HeBulk set-up differs from the reference dump")
+        return spec
     if name == "BosonsBulk":
         spec = bosons_bulk(N, L, P, g["SYSTEM_PARAMS"], weights=g["spline_weights"])
     elif name == "NUBosonsBulkPB":

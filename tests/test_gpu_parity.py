@@ -419,3 +419,86 @@ def test_two_gpu_allreduce_matches_single_gpu(capi, golden, tmp_path):
         assert rel(two["localOperatorsMatrix"], one["S"]) < 1e-13
         assert rel(two["localOperatorlocalEnergyR"], one["OER"]) < 1e-13
         assert abs(float(two["localEnergyR"]) - one["e_r"][0]) < 1e-13 * abs(one["e_r"][0])
+
+
+# ---------------------------------------------------------------------------------------------------
+# HeBulk (BASELINE configs[1], config/bulk_64.config): McMillan core + uniform splines + Aziz potential
+# ---------------------------------------------------------------------------------------------------
+HE_CASES = ["hebulk_n64_fixture", "hebulk_n64_equil"]
+
+
+@pytest.mark.parametrize("name", HE_CASES)
+def test_hebulk_fixed_configuration(capi, golden, name):
+    g = golden(name)
+    spec, h = make_handle(capi, g)
+    r = h.evaluate_fixed(g["R"])
+    K = spec.n_splines
+    assert rel(r["ss"][0][:K], g["spline_sums"]) < 1e-13
+    assert abs(r["ss"][0][K] - float(g["mcmillan_sum"])) <= 1e-13 * abs(float(g["mcmillan_sum"]))
+    assert rel(r["O"][0], g["local_operators"]) < RTOL
+    assert abs(r["exponent"][0] - float(g["exponent"])) < RTOL * abs(float(g["exponent"]))
+    assert abs(r["e_r"][0] - float(g["local_energy_r"])) < RTOL * abs(float(g["local_energy_r"]))
+    assert abs(r["e_i"][0] - float(g["local_energy_i"])) < RTOL * abs(float(g["local_energy_i"]))
+    assert rel(r["drift_r"][0], g["drift_r"]) < RTOL
+    assert rel(r["drift_i"][0], g["drift_i"]) < RTOL
+    want, got = g["other_expectation_values"], r["other"][0]
+    assert got.shape == want.shape == (103,)
+    assert abs(got[0] - want[0]) < RTOL * abs(want[0]) and abs(got[1] - want[1]) < RTOL * abs(want[1])
+    assert abs(got[2] - want[2]) <= 1e-9 * abs(want[2])                      # wf = exp(exponent)
+    assert rel(got[3:], want[3:]) < 1e-12                                     # g(r)
+    q, d = h.quotient_fixed(g["R"], g["moves"])
+    d_ref = g["move_exponent_new"] - float(g["exponent"])
+    assert np.max(np.abs(d - d_ref) / np.maximum(1.0, np.abs(d_ref))) < 1e-9
+    h.close()
+
+
+def test_hebulk_sweep_and_estimators_match_oracle(capi, golden):
+    from oracle_lib import OracleHeBulk
+
+    g = golden("hebulk_n64_equil")
+    W, seed, mc_step = 4, 31, 0.3
+    n_samples, n_therm, n_init = 2, 64, 64
+    spec, h = make_handle(capi, g, n_walkers=W, seed=seed, mc_step=mc_step, max_samples=n_samples)
+    o = OracleHeBulk(spec)
+    R0 = np.stack([g["R"] + 0.002 * w for w in range(W)])
+    h.set_positions(R0)
+    h.sample_and_accumulate(n_samples, n_therm, n_init)
+    got = h.allreduce_and_fetch()
+    est = np.zeros(o.est_size())
+    acc = 0
+    for w in range(W):
+        r = o.sample_walker(R0[w], g["uR"], g["uI"], 0.0, seed, w, 0, n_init, n_samples, n_therm, mc_step, est)
+        acc += r["accepted"]
+    want = o.unpack_est(est, W * n_samples)
+    assert got["n_acceptances"] == acc and got["n_trials"] == W * (n_init + n_samples * n_therm)
+    assert rel(got["O"], want["O"]) < 1e-9
+    assert abs(got["e_r"][0] - want["e_r"]) < 1e-9 * abs(want["e_r"])
+    assert rel(got["S"], want["S"]) < 1e-9 and rel(got["OER"], want["OER"]) < 1e-9
+    assert rel(got["other"][[0, 1]], want["other"][[0, 1]]) < 1e-9
+    assert rel(got["other"][3:], want["other"][3:]) < 1e-9
+    Rg = h.get_positions()
+    for w in range(W):
+        d = Rg[w] - r["R"] if w == W - 1 else None
+    d = Rg[W - 1] - r["R"]
+    d -= spec.lbox * np.round(d / spec.lbox)
+    assert np.max(np.abs(d)) < 1e-9
+    h.close()
+
+
+def test_hebulk_statistics_match_reference_sampler(capi, golden):
+    g = golden("hebulk_n64_mc")
+    spec = systems.he_bulk(int(g["N"]), float(g["LBOX"]), int(g["N_PARAM"]))
+    W = 512
+    h = capi.Handle(spec, W, seed=77, mc_step=float(g["MC_STEP"]), max_samples=8)
+    h.set_params(g["uR"], g["uI"])
+    h.set_positions(np.broadcast_to(g["R0"], (W, spec.n_particles, 3)).copy())
+    h.sample_and_accumulate(8, int(g["n_therm"]), 64 * 300)
+    got = h.allreduce_and_fetch()
+    er = g["energy_r_series"]
+    nb = 20
+    b = er[:len(er) // nb * nb].reshape(nb, -1).mean(axis=1)
+    m_ref, s_ref = b.mean(), b.std(ddof=1) / np.sqrt(nb)
+    s_gpu = np.sqrt(np.var(er) / (W * 8)) * 2.0
+    assert abs(got["e_r"][0] - m_ref) < 4.0 * np.hypot(s_ref, s_gpu), (got["e_r"][0], m_ref, s_ref, s_gpu)
+    assert abs(got["n_acceptances"] / got["n_trials"] - float(g["acceptance"])) < 0.015
+    h.close()
