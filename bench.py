@@ -39,6 +39,9 @@ FLOP_PER_WALKER_STEP = 2 * (N - 1) * (22 + 1 + 6)          # 19 836
 FLOP_PER_EVALUATION = 5.0e6
 BYTES_PER_TABLE = 8 * 203 * N * 4 + 24 * N                  # 2 236 360 (K3 table kernel)
 METRIC = "walker-steps/s"
+# dram__bytes_read.sum + dram__bytes_write.sum of one sweep_kernel launch (2960 walkers) from the ncu --set full capture
+# profiles/r01d_sweep_ncu.txt; algorithmic traffic is 2 x 8.2 KB per walker per launch = 48.7 MB (the write-back stays in L2)
+SWEEP_DRAM_BYTES_PER_LAUNCH_NCU = 24.5e6
 
 
 def golden_spec():
@@ -310,7 +313,7 @@ def main():
     sweep_flops = FLOP_PER_WALKER_STEP * float(W) * STEPS_PER_WALKER * args.steps
     sweep_tf = sweep_flops / (ms_sweep * 1e-3) / 1e12
     roofline = {"kernel": "sweep_kernel (K1)", "bound": "fp64", "achieved": sweep_tf, "peak": dfma_peak, "unit": "TFLOP/s",
-                "frac": sweep_tf / dfma_peak, "traffic": None,
+                "frac": sweep_tf / dfma_peak, "traffic": SWEEP_DRAM_BYTES_PER_LAUNCH_NCU,
                 "note": "FP64 DFMA-pipe bound (SURVEY 8d): 19 836 algorithmic flop per walker-step; peak = DFMA microbenchmark "
                         "measured in this run (MEASURED_PEAKS.json has no FP64 entry); HBM traffic is 16.5 KB per walker per launch",
                 "launches": n_sweep, "avg_launch_ms": ms_sweep / max(n_sweep, 1), "share_of_step": ms_sweep / ms_total}

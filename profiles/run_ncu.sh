@@ -11,6 +11,8 @@ ncu --set full --clock-control none --import-source on -k regex:sweep_kernel -s 
     python bench.py --steps 1 --warmup 3 --no-exhibits > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:evaluate_kernel -s 2 -c 1 -f -o gpurun_out/evaluate_${TAG} \
     python bench.py --steps 1 --warmup 3 --no-exhibits > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"tables_kernel|contract_kernel|syrk_kernel" -c 6 -f -o gpurun_out/exhibits_${TAG} \
+ncu --set full --clock-control none --import-source on -k regex:"tables_kernel|contract_kernel" -c 2 -f -o gpurun_out/tables_${TAG} \
+    python bench.py --steps 1 --warmup 3 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:syrk_kernel -s 5 -c 1 -f -o gpurun_out/syrk_${TAG} \
     python bench.py --steps 1 --warmup 3 > /dev/null 2>&1
 ls -la gpurun_out
