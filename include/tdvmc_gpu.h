@@ -38,6 +38,11 @@ enum tdvmc_system_kind
     TDVMC_SYSTEM_HE_BULK = 1       /* HeBulk (HeBulk.cpp): McMillan r^-5 core below rijSplit = 1.95, uniform cubic B-splines
                                       in the local coordinate above it, Aziz HFD-B(He) inline, g(r) in other[3..102];
                                       knots / spline_weights are not used (may be NULL) */
+    ,
+    TDVMC_SYSTEM_HE_DROP = 2       /* HeDrop (HeDrop.cpp): open boundary, McMillan r^-4.7 core below 3.0, 70 splines of spacing 0.1
+                                      then spacing 0.5 up to rijTail, constant + linear tails beyond, Lennard-Jones inline,
+                                      g(r) and the density profile in other[3..402]; lbox unused; wrap_positions moves the
+                                      centre of mass to zero (src/TDVMC.cpp:798-809) */
 };
 
 enum tdvmc_pair_rule
@@ -67,8 +72,8 @@ typedef struct tdvmc_system_desc
     const double* system_params; /* SYSTEM_PARAMS: a, b [, t_switch, a2, b2] (BosonsBulk.cpp:237-243) */
     int32_t n_system_params;
     int32_t system_kind;       /* enum tdvmc_system_kind */
-    /* Columns of the map beyond the K spline sums (analytic basis sums).  HeBulk: n_ext = K + 1, column K is the
-     * McMillan sum (HeBulk.cpp:376-383).  Spline-table systems: n_ext = K. */
+    /* Columns of the map: the K spline sums plus analytic basis sums.  He family: n_ext = K + 3, columns K, K+1, K+2 are
+     * the McMillan, constant and linear sums (HeBulk.cpp:376-383, HeDrop.cpp:609-626).  Spline-table systems: n_ext = K. */
     int32_t n_ext;
     int32_t reserved;
     const double* map_const;   /* [N_PARAM] constant part of O_p (HeBulk.cpp:383: 1.0 + ...), NULL = zeros */

@@ -20,6 +20,9 @@ import tempfile
 
 import numpy as np
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tdvmc_b200 import systems as tsys  # noqa: E402  (host-side set-up only: maps, knots)
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 REF = os.environ.get("TDVMC_REFERENCE", "/root/reference")
@@ -349,6 +352,71 @@ def gen_hebulk():
     print(f"hebulk_n64_mc: <E_R>={float(d['local_energy_r']):.8g} acc={float(d['n_acceptances']) / float(d['n_trials']):.4f}")
 
 
+def he_drift_from_tables(spec, d, uR, uI):
+    """Drift from the REFERENCE's derivative tables through the parameter map, long double."""
+    sD = d["sD"].astype(np.longdouble)
+    N = sD.shape[1]
+    zero = np.zeros((1, N, 3), np.longdouble)
+    lin = d["linear_sum_d"].astype(np.longdouble)[None] if "linear_sum_d" in d else zero
+    tab = np.concatenate([sD, d["mcmillan_sum_d"].astype(np.longdouble)[None], zero, lin])
+    out = []
+    for u in (uR, uI):
+        F = np.zeros((N, 3), np.longdouble)
+        for p, row in enumerate(spec.map_rows()):
+            t = np.full((N, 3), np.longdouble(spec.grad_const[p]))
+            for k, f in row:
+                t = t + np.longdouble(f) * tab[k]
+            F = F + np.longdouble(u[p]) * t
+        out.append(F.astype(np.float64))
+    return out
+
+
+def pack_eval_hedrop(name, scal, arrays, moves):
+    with tempfile.TemporaryDirectory() as td:
+        cp, op = os.path.join(td, "case.txt"), os.path.join(td, "out.txt")
+        write_case(cp, "HeDrop", scal, arrays, moves)
+        run("eval", cp, op)
+        d = parse_dump(op)
+    out = {"system": np.array("HeDrop"), "N": np.array(scal["N"]), "DIM": np.array(3), "LBOX": np.array(scal["LBOX"]),
+           "N_PARAM": np.array(scal["N_PARAM"]), "SYSTEM_PARAMS": np.zeros(0), "time": np.array(0.0),
+           "R": np.asarray(arrays["R"], np.float64).reshape(-1, 3), "uR": np.asarray(arrays["uR"], np.float64),
+           "uI": np.asarray(arrays["uI"], np.float64), "phiR": np.array(scal.get("phiR", 0.0)),
+           "phiI": np.array(scal.get("phiI", 0.0)), "moves": np.asarray(moves, np.float64).reshape(-1, 4)}
+    for k in ("exponent", "exponent_wf", "wf", "local_energy_r", "local_energy_i", "local_operators",
+              "local_operator_energy_r", "local_operator_energy_i", "other_expectation_values",
+              "local_operators_matrix_diag", "local_operators_matrix_row3", "spline_sums", "mcmillan_sum", "const_sum",
+              "linear_sum", "sD", "sD2", "mcmillan_sum_d", "mcmillan_sum_d2", "linear_sum_d", "linear_sum_d2", "rij_split",
+              "rij_spline_split", "rij_tail", "bc_factors", "move_quotient", "move_exponent_new"):
+        out[k] = d[k]
+    spec = tsys.he_drop(int(scal["N"]), int(scal["N_PARAM"]))
+    out["drift_r"], out["drift_i"] = he_drift_from_tables(spec, d, out["uR"], out["uI"])
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(f"{name}: E_R={float(d['local_energy_r']):.12g} E_I={float(d['local_energy_i']):.12g} "
+          f"exponent={float(d['exponent']):.12g} q={d['move_quotient']}")
+    return d
+
+
+def gen_hedrop():
+    """config/drop_6.config: 6 He-4 atoms, open boundary, N_PARAM = 93, the config's own PARAMS_REAL."""
+    rng = np.random.default_rng(6)
+    cfg = json.load(open(os.path.join(REF, "config", "drop_6.config")))
+    N, P = int(cfg["N"]), int(cfg["N_PARAM"])
+    uR = np.array(cfg["PARAMS_REAL"], dtype=np.float64)
+    uI = 0.01 * np.cos(0.2 * np.arange(P))
+    R = read_csv_positions("particleconfiguration_6.csv").reshape(N, 3)      # the reference's 6-particle fixture
+    scal = dict(N=N, LBOX=40.0, N_PARAM=P, phiR=float(cfg["PARAM_PHIR"]), phiI=0.0, GR_BIN_COUNT=200, RHO_BIN_COUNT=200)
+    arr = dict(R=R, uR=uR, uI=uI)
+    pack_eval_hedrop("hedrop_n6_fixture", scal, arr, default_moves(R, 0.0, rng, sigma=0.5))
+    # a spread-out configuration that reaches the 0.5-spacing grid and the const/linear tails (r >= r_tail = 21.2)
+    R2 = R * 3.4
+    pack_eval_hedrop("hedrop_n6_spread", scal, dict(arr, R=R2), default_moves(R2, 0.0, rng, sigma=1.5))
+    mc = run_mc("HeDrop", dict(scal, MC_STEP=float(cfg["MC_STEP"]), MC_NSTEPS=1, MC_NTHERMSTEPS=6 * 2000, seed=4), arr)
+    R3 = mc["R_final"].reshape(N, 3)
+    pack_eval_hedrop("hedrop_n6_equil", scal, dict(arr, R=R3), default_moves(R3, 0.0, rng, sigma=0.5))
+    # no sampler-statistics fixture for HeDrop: with HBAR2_2M = 1 (src/Constants.h:12) the 6-atom droplet is unbound and
+    # the chain is not stationary; sampling is pinned by replaying the oracle chain move for move instead
+
+
 def gen_min_image():
     """Reference minimum-image displacement on edge cases + random inputs (Utils.cpp:266-281, 352-382)."""
     rng = np.random.default_rng(99)
@@ -379,7 +447,7 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     if not os.path.exists(HARNESS):
         sys.exit("build the oracle first: make -C oracle/ref_build")
-    which = sys.argv[1:] or ["min_image", "bosonsbulk", "bosonsbulk_mc", "nubosonsbulkpb", "hebulk"]
+    which = sys.argv[1:] or ["min_image", "bosonsbulk", "bosonsbulk_mc", "nubosonsbulkpb", "hebulk", "hedrop"]
     for w in which:
         globals()["gen_" + w]()
 

@@ -235,6 +235,27 @@ void DumpSystemInternals(Dump& d)
     {
         DumpSplineInternals(d, s);
     }
+    else if (auto s = dynamic_cast<PhysicalSystems::HeDrop*>(sys))
+    {
+        d.vec("spline_sums", s->splineSums);
+        d.scalar("mcmillan_sum", s->mcMillanSum);
+        d.scalar("const_sum", s->constSum);
+        d.scalar("linear_sum", s->linearSum);
+        d.ten("sD", s->splineSumsD);
+        d.mat("sD2", s->splineSumsD2);
+        d.mat("mcmillan_sum_d", s->mcMillanSumD);
+        d.vec("mcmillan_sum_d2", s->mcMillanSumD2);
+        d.mat("linear_sum_d", s->linearSumD);
+        d.vec("linear_sum_d2", s->linearSumD2);
+        d.scalar("rij_split", s->rijSplit);
+        d.scalar("rij_spline_split", s->rijSplineSplit);
+        d.scalar("rij_tail", s->rijTail);
+        d.vec("bc_factors", { s->factorFirstSpline1, s->factorFirstSpline2, s->factorSecondSpline1, s->factorSecondSpline2,
+                              s->factorSecondLastSpline, s->factorSecondLastSplineConst, s->factorSecondLastSplineLinear,
+                              s->factorLastSpline, s->factorLastSplineConst, s->factorLastSplineLinear,
+                              s->factorSecondLastShort, s->factorSecondLastLarge, s->factorLastShort, s->factorLastLarge,
+                              s->factorFirstShort, s->factorFirstLarge, s->factorSecondShort, s->factorSecondLarge });
+    }
     else if (auto s = dynamic_cast<PhysicalSystems::HeBulk*>(sys))
     {
         d.vec("spline_sums", s->splineSums);

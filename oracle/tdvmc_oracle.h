@@ -99,8 +99,13 @@ int64_t oracle_sample_walker(const oracle_system* s, double* R, const double* uR
 #endif
 
 /* ------------------------------------------------------------------------------------------------
- * HeBulk (src/PhysicalSystems/HeBulk.cpp): periodic He-4, McMillan r^-5 core + uniform cubic
- * B-splines in the local coordinate, Aziz HFD-B(He) potential inline, g(r) in other[3..102].
+ * He family: HeBulk (src/PhysicalSystems/HeBulk.cpp) and HeDrop (src/PhysicalSystems/HeDrop.cpp).
+ * McMillan core r^m below rs, uniform cubic B-splines written in the local coordinate on one (HeBulk)
+ * or two (HeDrop: spacing 0.1 then 0.5) grids, const + linear tails beyond r_tail (HeDrop), Aziz HFD-B
+ * (HeBulk.cpp:187-195) or Lennard-Jones (HeDrop.cpp:389-394) potential, g(r) (and, for HeDrop, the
+ * density profile around the centre of mass) carried in otherExpectationValues.
+ * Extended basis sums: ext = [ss_0 .. ss_{K-1} | mcMillanSum | constSum | linearSum]; the parameter map
+ * (HeBulk.cpp:376-383, HeDrop.cpp:609-626) is passed as CSR rows over ext plus per-parameter constants.
  * ------------------------------------------------------------------------------------------------ */
 #ifndef TDVMC_ORACLE_HE_H
 #define TDVMC_ORACLE_HE_H
@@ -108,36 +113,38 @@ int64_t oracle_sample_walker(const oracle_system* s, double* R, const double* uR
 extern "C" {
 #endif
 
-typedef struct oracle_hebulk
+typedef struct oracle_he
 {
-    int32_t n_particles, n_params, n_splines, gr_bins;
-    double lbox, rij_split, h, max_distance, hbar2_2m;
-    double f[8]; /* factorFirstSpline1, FirstSpline2, SecondSpline1, SecondSpline2, SecondLastSpline, LastSpline,
-                    SecondLastSplinePhi, LastSplinePhi (HeBulk.cpp:57-67) */
-} oracle_hebulk;
+    int32_t n_particles, n_params, n_splines, n_short; /* n_short: numberOfShortSplines (HeBulk: = n_splines) */
+    int32_t periodic;      /* 1: minimum image in a box of lbox (HeBulk), 0: open (HeDrop) */
+    int32_t potential;     /* 0: Aziz HFD-B(He) inline (HeBulk), 1: LJ sigma=4 eps=3.56 (HeDrop) */
+    int32_t gr_bins, rho_bins, use_phi;
+    int32_t pad;
+    double lbox, rs, r_split2, r_tail, h_short, h_large, max_distance, mcm, gr_max, hbar2_2m;
+    const int32_t* map_ptr; /* [P+1] rows over ext columns (K + 3) */
+    const int32_t* map_col;
+    const double* map_val;
+    const double* map_const;  /* [P] */
+    const double* grad_const; /* [P] the literal gradient constant of HeBulk.cpp:351 */
+} oracle_he;
 
-/* HeBulk::InitSystem (HeBulk.cpp:40-70) */
-void oracle_hebulk_init(oracle_hebulk* s, int n_particles, double lbox, int n_params);
-/* value sums of CalculateWavefunction (HeBulk.cpp:462-489) */
-void oracle_hebulk_values(const oracle_hebulk* s, const double* R, double* ss, double* mcm);
-/* localOperators (HeBulk.cpp:376-383) and the exponent (:491-498) */
-void oracle_hebulk_operators(const oracle_hebulk* s, const double* ss, double mcm, double* O);
-double oracle_hebulk_exponent(const oracle_hebulk* s, const double* ss, double mcm, const double* uR);
-/* CalculateExpectationValues (HeBulk.cpp:166-405). other: [3 + gr_bins]; drift_*: [N][3] or NULL;
- * sD [K][N][3], sD2 [K][N], mcD [N][3], mcD2 [N]: caller-provided scratch (also outputs). */
-void oracle_hebulk_expectation(const oracle_hebulk* s, const double* R, double wf, const double* uR, const double* uI,
-                               double* e_r, double* e_i, double* other, double* drift_r, double* drift_i, double* sD,
-                               double* sD2, double* mcD, double* mcD2);
-/* CalculateWFChange / Quotient (HeBulk.cpp:512-604) */
-double oracle_hebulk_quotient(const oracle_hebulk* s, const double* R, int particle, const double* old_pos, const double* ss,
-                              double mcm, double exponent, const double* uR, double* ss_new, double* mcm_new,
-                              double* exponent_new);
-int64_t oracle_hebulk_sweep(const oracle_hebulk* s, double* R, double* ss, double* mcm, double* exponent, const double* uR,
-                            uint64_t seed, uint32_t walker, uint64_t first_step, int64_t n_steps, double mc_step);
-/* est: [O(P) | E_R | E_I | S(P*P) | OE_R(P) | OE_I(P) | other(3 + gr_bins)] sums; rows: per sample [O(P), E_R, E_I] */
-int64_t oracle_hebulk_sample_walker(const oracle_hebulk* s, double* R, const double* uR, const double* uI, uint64_t seed,
-                                    uint32_t walker, uint64_t* step_counter, int n_init, int n_samples, int n_therm,
-                                    double mc_step, double* est, double* sample_rows);
+/* value sums of CalculateWavefunction (HeBulk.cpp:462-489, HeDrop.cpp:718-763): ext[K+3] */
+void oracle_he_values(const oracle_he* s, const double* R, double* ext);
+void oracle_he_operators(const oracle_he* s, const double* ext, double* O);
+double oracle_he_exponent(const oracle_he* s, const double* ext, const double* uR);
+/* CalculateExpectationValues (HeBulk.cpp:166-405, HeDrop.cpp:277-648).  other: [3 + gr_bins + rho_bins];
+ * tabD [K+3][N][3], tabD2 [K+3][N]: derivative tables of every ext column (outputs / scratch). */
+void oracle_he_expectation(const oracle_he* s, const double* R, double wf, const double* uR, const double* uI, double* e_r,
+                           double* e_i, double* other, double* drift_r, double* drift_i, double* tabD, double* tabD2);
+/* CalculateWFChange / Quotient (HeBulk.cpp:512-604, HeDrop.cpp:796-938) incl. the max(0, .) clamps */
+double oracle_he_quotient(const oracle_he* s, const double* R, int particle, const double* old_pos, const double* ext,
+                          double exponent, const double* uR, double* ext_new, double* exponent_new);
+int64_t oracle_he_sweep(const oracle_he* s, double* R, double* ext, double* exponent, const double* uR, uint64_t seed,
+                        uint32_t walker, uint64_t first_step, int64_t n_steps, double mc_step);
+/* est: [O(P) | E_R | E_I | S(P*P) | OE_R(P) | OE_I(P) | other(n_other)] sums; rows: per sample [O(P), E_R, E_I] */
+int64_t oracle_he_sample_walker(const oracle_he* s, double* R, const double* uR, const double* uI, double phiR, uint64_t seed,
+                                uint32_t walker, uint64_t* step_counter, int n_init, int n_samples, int n_therm,
+                                double mc_step, double* est, double* sample_rows);
 
 #ifdef __cplusplus
 }

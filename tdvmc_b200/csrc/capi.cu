@@ -107,7 +107,8 @@ struct tdvmc_gpu_handle
 
     // system (host copies)
     int N = 0, Np = 0, P = 0, K = 0, pair_rule = 0, tail_param = 0, n_other = 9, kind = 0, n_ext = 0, gr_bins = 0;
-    double he_rs = 0, core_m = 0;
+    double he_rs = 0, core_m = 0, he_hl = 0, r_split2 = 1e300, r_tail = 1e300, gr_max = 0, u_core = 0, u_const = 0, u_lin = 0;
+    int n_short = 0, potential = 0, rho_bins = 0, use_phi = 0, periodic = 1;
     std::vector<double> map_const, grad_const;
     double L = 0, hbar = 1.0;
     std::vector<double> knots, weights, map_val, sys_params, uR, uI;
@@ -255,17 +256,61 @@ void potential_ab(const tdvmc_gpu_handle* h, double& a, double& b)
 int build_static_tables(tdvmc_gpu_handle* h)
 {
     const int K = h->K;
-    if (h->kind == TDVMC_SYSTEM_HE_BULK)
+    if (h->kind == TDVMC_SYSTEM_HE_BULK || h->kind == TDVMC_SYSTEM_HE_DROP)
     {
-        // HeBulk::InitSystem (HeBulk.cpp:40-70): uniform grid of K - 3 intervals from rijSplit to L/2
-        h->he_rs = 1.95;
-        h->core_m = -5.0;
-        h->gr_bins = 100;
+        std::vector<unsigned short> lut(1, 0);
+        if (h->kind == TDVMC_SYSTEM_HE_BULK)
+        {
+            // HeBulk::InitSystem (HeBulk.cpp:40-70): uniform grid of K - 3 intervals from rijSplit to L/2
+            h->he_rs = 1.95;
+            h->core_m = -5.0;
+            h->gr_bins = 100;
+            h->n_short = K;
+            h->nbins = K - 3;
+            h->uniform = 1;
+            h->ncell = 1;
+            h->h = (h->L / 2.0 - h->he_rs) / (double)(K - 3.0);
+            h->he_hl = h->h;
+            h->gr_max = h->L / 2.0;
+            h->potential = 0;
+            h->periodic = 1;
+        }
+        else
+        {
+            // HeDrop::InitSystem (HeDrop.cpp:71-97): 70 splines of spacing 0.1 from rijSplit = 3, then spacing 0.5
+            h->he_rs = 3.0;
+            h->core_m = -4.7;
+            h->gr_bins = 200;
+            h->rho_bins = 200;
+            h->n_short = 70;
+            h->h = 0.1;
+            h->he_hl = 0.5;
+            const int n_large = K - h->n_short;
+            if (n_large < 4) return fail(h, "HeDrop needs N_PARAM >= 71");
+            h->r_split2 = h->h * (h->n_short - 3.0) + h->he_rs;
+            h->r_tail = h->he_hl * (n_large - 3.0) + h->r_split2;
+            h->gr_max = h->r_tail * 2.0; // HeDrop.cpp:222
+            h->nbins = (h->n_short - 3) + (n_large - 3);
+            h->uniform = 0;
+            h->potential = 1;
+            h->use_phi = 1;
+            h->periodic = 0;
+            // interval lookup over [0, r_tail - rs] in cells of half the short spacing
+            const double span = h->r_tail - h->he_rs;
+            h->ncell = (int)std::ceil(2.0 * span / h->h);
+            lut.assign(h->ncell, 0);
+            const double cw = span / h->ncell;
+            for (int c = 0; c < h->ncell; c++)
+            {
+                const double x = c * cw;
+                int jj = x < (h->r_split2 - h->he_rs) ? (int)std::floor(x / h->h)
+                                                       : (h->n_short - 3) + (int)std::floor((x - (h->r_split2 - h->he_rs)) / h->he_hl);
+                if (jj > 0) jj--; // start one interval low: the device loop only walks upwards
+                lut[c] = (unsigned short)std::min(jj, h->nbins - 1);
+            }
+        }
         h->first_bin = 0;
-        h->nbins = K - 3;
-        h->uniform = 1;
-        h->ncell = 1;
-        h->h = (h->L / 2.0 - h->he_rs) / (double)(K - 3.0);
+        CK(upload(h->d_lut, lut, h->stream));
         CK(upload(h->d_map_ptr, h->map_ptr, h->stream));
         CK(upload(h->d_map_col, h->map_col, h->stream));
         CK(upload(h->d_map_val, h->map_val, h->stream));
@@ -338,29 +383,37 @@ int build_param_tables(tdvmc_gpu_handle* h)
     // uR[tail_param] every pair beyond r_max contributes (BosonsBulk.cpp:532-534)
     const int nrec = h->nbins + 1;
     std::vector<double> cub((size_t)nrec * 6, 0.0);
-    if (h->kind == TDVMC_SYSTEM_HE_BULK)
+    const bool he = h->kind != TDVMC_SYSTEM_SPLINE_TABLE;
+    if (he)
     {
-        // u(r) on interval j of the uniform grid: sum_b u~[j+b] beta_b(res), res = (r - rs)/h - j, with the cubic
-        // B-spline pieces of HeBulk.cpp:483-486 as polynomials in res; stored in powers of s = res h
+        // u(r) on interval j of a uniform grid: sum_b u~[b0+b] beta_b(res), res = (r - t_lo)/h, with the cubic B-spline
+        // pieces of HeBulk.cpp:483-486 as polynomials in res; stored in powers of s = res h; knots relative to rijSplit
         static const long double beta[4][4] = { { 1.0L / 6, -3.0L / 6, 3.0L / 6, -1.0L / 6 },
                                                 { 4.0L / 6, 0.0L, -6.0L / 6, 3.0L / 6 },
                                                 { 1.0L / 6, 3.0L / 6, 3.0L / 6, -3.0L / 6 },
                                                 { 0.0L, 0.0L, 0.0L, 1.0L / 6 } };
-        const long double hh = h->h;
+        const int n_short_iv = h->n_short - 3;
         for (int rec = 0; rec < h->nbins; rec++)
         {
+            const bool lng = h->kind == TDVMC_SYSTEM_HE_DROP && rec >= n_short_iv;
+            const long double hh = lng ? h->he_hl : h->h;
+            const int b0 = lng ? h->n_short + (rec - n_short_iv) : rec;
+            const double t_lo = lng ? (h->r_split2 - h->he_rs) + (rec - n_short_iv) * h->he_hl : rec * h->h;
             long double C[4] = { 0, 0, 0, 0 };
             for (int b = 0; b < 4; b++)
-                for (int c = 0; c < 4; c++) C[c] += (long double)utR[rec + b] * beta[b][c];
+                for (int c = 0; c < 4; c++) C[c] += (long double)utR[b0 + b] * beta[b][c];
             cub[(size_t)rec * 2 + 0] = (double)C[0];
             cub[(size_t)rec * 2 + 1] = (double)(C[1] / hh);
             cub[(size_t)(nrec + rec) * 2 + 0] = (double)(C[2] / (hh * hh));
             cub[(size_t)(nrec + rec) * 2 + 1] = (double)(C[3] / (hh * hh * hh));
-            cub[(size_t)(2 * nrec + rec) * 2 + 0] = h->he_rs + rec * h->h;
-            cub[(size_t)(2 * nrec + rec) * 2 + 1] = h->he_rs + (rec + 1) * h->h;
+            cub[(size_t)(2 * nrec + rec) * 2 + 0] = t_lo;
+            cub[(size_t)(2 * nrec + rec) * 2 + 1] = t_lo + (double)hh;
         }
+        h->u_core = utR[K];
+        h->u_const = utR[K + 1];
+        h->u_lin = utR[K + 2];
     }
-    for (int rec = 0; h->kind != TDVMC_SYSTEM_HE_BULK && rec < h->nbins; rec++)
+    for (int rec = 0; !he && rec < h->nbins; rec++)
     {
         const int b = fb + rec;
         long double C[4] = { 0, 0, 0, 0 };
@@ -376,7 +429,7 @@ int build_param_tables(tdvmc_gpu_handle* h)
         cub[(size_t)(2 * nrec + rec) * 2 + 1] = h->knots[b + 1];
     }
     cub[(size_t)h->nbins * 2 + 0] = h->tail_param >= 0 ? h->uR[h->tail_param] : 0.0;
-    cub[(size_t)(2 * nrec + h->nbins) * 2 + 0] = h->kind == TDVMC_SYSTEM_HE_BULK ? h->L / 2.0 : h->knots[K];
+    cub[(size_t)(2 * nrec + h->nbins) * 2 + 0] = he ? (h->kind == TDVMC_SYSTEM_HE_BULK ? h->L / 2.0 : h->r_tail) - h->he_rs : h->knots[K];
     cub[(size_t)(2 * nrec + h->nbins) * 2 + 1] = 1e300;
     CK(upload(h->d_uR, h->uR, h->stream));
     CK(upload(h->d_uI, h->uI, h->stream));
@@ -402,27 +455,23 @@ SysDev tdvmc_gpu_handle::sysdev() const
     s.N = N; s.Np = Np; s.P = P; s.K = K;
     s.pair_rule = pair_rule; s.tail_param = tail_param; s.n_other = n_other;
     s.first_bin = first_bin; s.nbins = nbins; s.ncell = ncell; s.uniform = uniform;
-    s.L = L; s.Linv = 1.0 / L; s.Lhalf = L / 2.0; // src/TDVMC.cpp:535-536
+    s.L = L; s.Linv = L > 0.0 ? 1.0 / L : 0.0; s.Lhalf = L / 2.0; // src/TDVMC.cpp:535-536
     s.kind = kind; s.n_ext = n_ext; s.gr_bins = gr_bins;
-    s.rmax = kind == TDVMC_SYSTEM_HE_BULK ? L / 2.0 : knots[K]; // HeBulk.cpp:54
+    s.periodic = periodic; s.n_short = n_short; s.potential = potential; s.rho_bins = rho_bins; s.use_phi = use_phi;
+    s.rmax = kind == TDVMC_SYSTEM_HE_BULK ? L / 2.0 : (kind == TDVMC_SYSTEM_HE_DROP ? 1e300 : knots[K]); // HeBulk.cpp:54
     s.hbar = hbar;
-    s.r0 = he_rs; s.core_m = core_m;
-    s.u_core = 0.0; s.g0R = 0.0; s.g0I = 0.0;
+    s.r0 = he_rs; s.core_m = core_m; s.r_split2 = r_split2; s.r_tail = r_tail; s.h_large = he_hl; s.gr_max = gr_max;
+    s.u_core = u_core; s.u_const = u_const; s.u_lin = u_lin;
+    s.g0R = 0.0; s.g0I = 0.0;
     if (params_set)
-    {
         for (int p = 0; p < P; p++)
         {
             s.g0R += uR[p] * grad_const[p];
             s.g0I += uI[p] * grad_const[p];
         }
-        if (kind == TDVMC_SYSTEM_HE_BULK) // u~ of the McMillan column K
-            for (int p = 0; p < P; p++)
-                for (int j = map_ptr[p]; j < map_ptr[p + 1]; j++)
-                    if (map_col[j] == K) s.u_core += uR[p] * map_val[j];
-    }
     if (kind == TDVMC_SYSTEM_SPLINE_TABLE) potential_ab(this, s.pot_a, s.pot_b);
     s.phiR = phiR;
-    s.inv_cell = ncell / s.rmax;
+    s.inv_cell = kind == TDVMC_SYSTEM_HE_DROP ? ncell / (r_tail - he_rs) : ncell / s.rmax;
     s.h = h; s.inv_h = 1.0 / h;
     s.u_tail = (params_set && tail_param >= 0) ? uR[tail_param] : 0.0;
     if (tail_param < 0) s.tail_param = 0; // kernels index uR[tail_param]; the tail count is zero for these systems
@@ -459,10 +508,12 @@ int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed,
         return -1;
     }
     if (sd->dim != 3 || sd->n_particles < 2 || sd->n_params < 1 || sd->n_splines < 4 || ed->n_walkers < 1 || sd->n_other < 3 ||
-        sd->tail_param < -1 || sd->tail_param >= sd->n_params || !(sd->lbox > 0.0) || sd->n_ext < sd->n_splines ||
-        (sd->system_kind != TDVMC_SYSTEM_SPLINE_TABLE && sd->system_kind != TDVMC_SYSTEM_HE_BULK) ||
+        sd->tail_param < -1 || sd->tail_param >= sd->n_params || (!(sd->lbox > 0.0) && sd->system_kind != TDVMC_SYSTEM_HE_DROP) || sd->n_ext < sd->n_splines ||
+        (sd->system_kind != TDVMC_SYSTEM_SPLINE_TABLE && sd->system_kind != TDVMC_SYSTEM_HE_BULK &&
+         sd->system_kind != TDVMC_SYSTEM_HE_DROP) ||
         (sd->system_kind == TDVMC_SYSTEM_SPLINE_TABLE && (!sd->knots || !sd->spline_weights || sd->n_other < 9)) ||
-        (sd->system_kind == TDVMC_SYSTEM_HE_BULK && (sd->n_ext != sd->n_splines + 1 || sd->n_other != 103)))
+        (sd->system_kind == TDVMC_SYSTEM_HE_BULK && (sd->n_ext != sd->n_splines + 3 || sd->n_other != 103)) ||
+        (sd->system_kind == TDVMC_SYSTEM_HE_DROP && (sd->n_ext != sd->n_splines + 3 || sd->n_other != 403)))
     {
         g_create_error = "invalid system/ensemble description";
         return -1;
@@ -731,7 +782,7 @@ static int do_evaluate_walkers(tdvmc_gpu_handle* h, const double* pos, int n_cfg
     a.other = h->d_other.p;
     a.exponent = h->d_exponent.p;
     Timed t(h, TDVMC_KERNEL_EVALUATE);
-    CK(h->kind == TDVMC_SYSTEM_HE_BULK ? launch_evaluate_he(a, h->stream) : launch_evaluate(a, h->stream));
+    CK(h->kind != TDVMC_SYSTEM_SPLINE_TABLE ? launch_evaluate_he(a, h->stream) : launch_evaluate(a, h->stream));
     return 0;
 }
 
@@ -940,7 +991,7 @@ int tdvmc_gpu_evaluate_fixed(tdvmc_gpu_handle* h, const double* R, int32_t n_cfg
     a.outer_out = out.p;
     {
         Timed t(h, TDVMC_KERNEL_EVALUATE);
-        CK(h->kind == TDVMC_SYSTEM_HE_BULK ? launch_evaluate_he(a, h->stream) : launch_evaluate(a, h->stream));
+        CK(h->kind != TDVMC_SYSTEM_SPLINE_TABLE ? launch_evaluate_he(a, h->stream) : launch_evaluate(a, h->stream));
     }
     std::vector<double> hA((size_t)n_cfg * h->lda);
     CK(cudaMemcpyAsync(hA.data(), A.p, hA.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

@@ -28,7 +28,12 @@ struct SysDev
     int nbins;        // K - first_bin
     int ncell;        // cells of the uniform bin lookup grid
     int uniform;      // != 0: knots are a uniform grid, interval index = floor(r / h)
-    int kind;         // TDVMC_SYSTEM_*: 0 spline table (BosonsBulk, NUBosonsBulkPB), 1 HeBulk
+    int kind;         // TDVMC_SYSTEM_*: 0 spline table (BosonsBulk, NUBosonsBulkPB), 1 HeBulk, 2 HeDrop
+    int periodic;     // 1: minimum image in the box, 0: open boundary (HeDrop)
+    int n_short;      // He family: splines on the short grid (HeDrop: 70; HeBulk: all)
+    int potential;    // He family: 0 Aziz HFD-B(He) (HeBulk.cpp:187-195), 1 Lennard-Jones sigma=4 eps=3.56 (HeDrop.cpp:389-394)
+    int rho_bins;     // density-profile bins carried in other[] after g(r) (HeDrop: 200)
+    int use_phi;      // wf = exp(exponent + phiR) (HeDrop.cpp:783) or exp(exponent) (HeBulk.cpp:500)
     int n_ext;        // columns of the parameter map: K spline sums + analytic extras
     int gr_bins;      // g(r) bins carried in other[] (HeBulk: 100)
     double L, Linv, Lhalf;   // LBOX, 1/LBOX, LBOX/2 (src/TDVMC.cpp:535-536)
@@ -43,6 +48,11 @@ struct SysDev
     double core_m;           // McMillan exponent (HeBulk: -5)
     double u_core;           // u~ of the McMillan column
     double g0R, g0I;         // sum_p u_p grad_const[p]: the literal gradient constant (HeBulk.cpp:351)
+    double r_split2;         // He family: start of the long grid (HeDrop: rijSplineSplit), else huge
+    double r_tail;           // He family: const + linear tails from here on (HeDrop: rijTail), else huge
+    double h_large;          // spacing of the long grid
+    double gr_max;           // g(r) / density-profile range
+    double u_const, u_lin;   // u~ of the const and linear tail columns
     const double* knots;     // [K+4]
     const double* rec;       // [nbins][kRecStride]: piece p of spline (bin-p) at [p*4 + c]
     const double* cub;       // sweep table, 3 planes of (nbins+1) double2: [c0,c1] | [c2,c3] | [t_lo,t_hi];

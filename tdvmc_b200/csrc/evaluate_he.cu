@@ -1,11 +1,14 @@
-// Fused evaluation for HeBulk (src/PhysicalSystems/HeBulk.cpp): periodic He-4 with a McMillan r^-5 core
-// below rijSplit, uniform cubic B-splines written in the local coordinate res = (r - rs)/h - bin above it,
-// the Aziz HFD-B(He) potential inline and g(r) carried in otherExpectationValues[3..102].
+// Fused evaluation for the He family: HeBulk (src/PhysicalSystems/HeBulk.cpp) and HeDrop
+// (src/PhysicalSystems/HeDrop.cpp).  McMillan core r^m below rijSplit, uniform cubic B-splines written in
+// the local coordinate res = (r - r0)/h - bin on one (HeBulk) or two (HeDrop: h = 0.1 then 0.5) grids,
+// constant + linear tails beyond rijTail (HeDrop), Aziz HFD-B(He) or Lennard-Jones potential inline,
+// g(r) -- and for HeDrop the density profile around the centre of mass -- carried in otherExpectationValues.
 //
 // Same structure as evaluate.cu (one block per configuration, thread n owns particle n, contraction with
-// u~ = M^T u on the fly, per-warp conflict-free histogram for the value sums); the per-pair expressions are
-// the reference's (HeBulk.cpp:268-302, 471-486), so each term agrees with the reference to the last bits
-// (libm pow/exp differ from glibc by <= 1-2 ulp).
+// u~ = M^T u on the fly, per-warp conflict-free histogram for the value sums).  The per-pair expressions are
+// the reference's (HeBulk.cpp:268-302, 471-486; HeDrop.cpp:399-468, 728-761), so each term agrees with the
+// reference to the last bits (libm pow/exp differ from glibc by <= 1-2 ulp).
+// Extended basis sums: ext = [ss_0 .. ss_{K-1} | mcMillanSum | constSum | linearSum].
 #include "kernels.cuh"
 
 namespace tdvmc
@@ -32,13 +35,41 @@ __device__ __forceinline__ void warp_hist_add4_he(double* hist, int bin, bool ac
     }
 }
 
+__device__ __forceinline__ double he_pair_potential(const SysDev& s, double r)
+{
+    if (s.potential == 0)
+    {
+        // Aziz HFD-B(He), HeBulk.cpp:187-195, 251-261
+        const double e = 10.948, rm = 2.963, aa = 184431.01, alpha = 10.43329537, beta = -2.27965105, dd = 1.4826,
+                     c6 = 1.36745214, c8 = 0.42123807, c10 = 0.17473318;
+        const double x = r / rm;
+        const double x2 = x * x;
+        const double xm2 = 1.0 / x2;
+        const double xm6 = xm2 * xm2 * xm2;
+        double F = 1;
+        if (x < dd)
+        {
+            const double q = dd / x - 1;
+            F = exp(-(q * q));
+        }
+        return e * (aa * exp(-alpha * x + beta * x2) - F * xm6 * (c6 + xm2 * (c8 + xm2 * c10)));
+    }
+    // Lennard-Jones, HeDrop.cpp:389-394
+    const double sigma = 4.0, eps = 3.56;
+    const double q = sigma / r;
+    const double q2 = q * q;
+    const double s6 = q2 * q2 * q2;
+    return 4.0 * eps * s6 * (s6 - 1.0);
+}
+
 __global__ void __launch_bounds__(256) evaluate_he_kernel(EvalArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SysDev& s = a.s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int cfg = blockIdx.x;
-    const int N = s.N, K = s.K, P = s.P, G = s.gr_bins, NE = s.n_ext;
+    const int N = s.N, K = s.K, P = s.P, G = s.gr_bins, NR = s.rho_bins, NE = s.n_ext;
+    const int MC = K, CO = K + 1, LI = K + 2;
 
     double* utR = reinterpret_cast<double*>(smem_raw);
     double* utI = utR + NE;
@@ -46,9 +77,10 @@ __global__ void __launch_bounds__(256) evaluate_he_kernel(EvalArgs a)
     double* py = px + N;
     double* pz = py + N;
     double* hist = pz + N;                    // [nwarps][K]
-    double* ext = hist + (size_t)nwarps * K;  // [NE] extended sums: ss[0..K) then the McMillan sum
-    double* red = ext + NE;                   // [nwarps][8]
-    int* gr = reinterpret_cast<int*>(red + (size_t)nwarps * 8); // [G]
+    double* ext = hist + (size_t)nwarps * K;  // [NE]
+    double* red = ext + NE;                   // [nwarps][12]
+    double* com = red + (size_t)nwarps * 12;  // [4]
+    int* gr = reinterpret_cast<int*>(com + 4); // [G + NR]
 
     for (int i = tid; i < NE; i += blockDim.x)
     {
@@ -63,19 +95,29 @@ __global__ void __launch_bounds__(256) evaluate_he_kernel(EvalArgs a)
         pz[i] = gpos[2 * s.Np + i];
     }
     for (int i = tid; i < nwarps * K; i += blockDim.x) hist[i] = 0.0;
-    for (int i = tid; i < G; i += blockDim.x) gr[i] = 0;
+    for (int i = tid; i < G + NR; i += blockDim.x) gr[i] = 0;
+    __syncthreads();
+    if (tid == 0 && NR > 0) // GetCenterOfMass, HeDrop.cpp:255-270
+    {
+        double cx = 0, cy = 0, cz = 0;
+        for (int i = 0; i < N; i++)
+        {
+            cx += px[i];
+            cy += py[i];
+            cz += pz[i];
+        }
+        com[0] = cx / (double)N;
+        com[1] = cy / (double)N;
+        com[2] = cz / (double)N;
+    }
     __syncthreads();
 
     double* myhist = hist + (size_t)warp * K;
-    const double rs = s.r0, h = s.h, rmax = s.rmax;
-    const double h2 = h * h; // pow(nodePointSpacing, 2), HeBulk.cpp:56
-    const double gr_spacing = rmax / (double)G; // HeBulk.cpp:130-131
-    // Aziz HFD-B(He), HeBulk.cpp:187-195
-    const double e = 10.948, rm = 2.963, aa = 184431.01, alpha = 10.43329537, beta = -2.27965105, dd = 1.4826,
-                 c6 = 1.36745214, c8 = 0.42123807, c10 = 0.17473318;
-    const double ucR = utR[K], ucI = utI[K]; // McMillan column
+    const double rs = s.r0, rmax = s.rmax, r2s = s.r_split2, rt = s.r_tail, m = s.core_m;
+    const double gr_spacing = s.gr_max / (double)G;
+    const double ucR = utR[MC], ucI = utI[MC], ulR = utR[LI], ulI = utI[LI];
 
-    double R1 = 0.0, I1 = 0.0, RI = 0.0, lapR = 0.0, lapI = 0.0, pot = 0.0, mcm = 0.0;
+    double R1 = 0.0, I1 = 0.0, RI = 0.0, lapR = 0.0, lapI = 0.0, pot = 0.0, mcm = 0.0, csum = 0.0, lsum = 0.0;
 
     for (int n0 = warp * 32; n0 < N; n0 += blockDim.x)
     {
@@ -85,58 +127,81 @@ __global__ void __launch_bounds__(256) evaluate_he_kernel(EvalArgs a)
         double fRx = 0.0, fRy = 0.0, fRz = 0.0, fIx = 0.0, fIy = 0.0, fIz = 0.0;
         for (int i = 0; i < N; i++)
         {
-            double vx, vy, vz;
-            const double r = disp_exact(s, xn, yn, zn, px[i], py[i], pz[i], vx, vy, vz);
-            const bool act = valid && (i != n) && (r < rmax); // HeBulk.cpp:232
+            double vx, vy, vz, r;
+            if (s.periodic)
+            {
+                r = disp_exact(s, xn, yn, zn, px[i], py[i], pz[i], vx, vy, vz);
+            }
+            else
+            {
+                vx = xn - px[i]; // VectorDisplacement, Utils.cpp:253-263
+                vy = yn - py[i];
+                vz = zn - pz[i];
+                r = sqrt(vx * vx + vy * vy + vz * vz);
+            }
+            const bool act = valid && (i != n) && (r < rmax); // HeBulk.cpp:232 (HeDrop: no cut)
             const bool lower = act && (i < n);
             int bin = 0;
             double val[4] = { 0.0, 0.0, 0.0, 0.0 };
             bool spline_val = false;
-            if (lower)
-            {
-                // Aziz potential, HeBulk.cpp:251-261
-                const double x = r / rm;
-                const double x2 = x * x;
-                const double xm2 = 1.0 / x2;
-                const double xm6 = xm2 * xm2 * xm2;
-                double F = 1;
-                if (x < dd)
-                {
-                    const double q = dd / x - 1;
-                    F = exp(-(q * q));
-                }
-                pot += e * (aa * exp(-alpha * x + beta * x2) - F * xm6 * (c6 + xm2 * (c8 + xm2 * c10)));
-                atomicAdd(&gr[min((int)floor(r / gr_spacing), G - 1)], 1); // g(r) counts, HeBulk.cpp:305-311
-            }
+            if (lower) pot += he_pair_potential(s, r);
+            if (valid && (i < n) && (r < s.gr_max)) atomicAdd(&gr[min((int)floor(r / gr_spacing), G - 1)], 1); // g(r) counts
             if (act)
             {
                 if (r < rs)
                 {
-                    // McMillan core, HeBulk.cpp:268-276, 471-474
-                    const double rm7 = pow(r, -7.0);
-                    const double g = -5.0 * rm7;
+                    // McMillan core, HeBulk.cpp:268-276 (m = -5), HeDrop.cpp:402-410
+                    const double rp = pow(r, m - 2.0);
+                    const double g = m * rp;
+                    const double l2 = m * (m + 1.0) * rp;
                     fRx = fma(ucR * g, vx, fRx); fRy = fma(ucR * g, vy, fRy); fRz = fma(ucR * g, vz, fRz);
                     fIx = fma(ucI * g, vx, fIx); fIy = fma(ucI * g, vy, fIy); fIz = fma(ucI * g, vz, fIz);
-                    lapR = fma(ucR, 20.0 * rm7, lapR);
-                    lapI = fma(ucI, 20.0 * rm7, lapI);
-                    if (lower) mcm += pow(r, -5.0);
+                    lapR = fma(ucR, l2, lapR);
+                    lapI = fma(ucI, l2, lapI);
+                    if (lower) mcm += pow(r, m);
+                }
+                else if (r >= rt)
+                {
+                    // constant + linear tails, HeDrop.cpp:411-426, 732-737
+                    const double ex = vx / r, ey = vy / r, ez = vz / r;
+                    fRx = fma(ulR, ex, fRx); fRy = fma(ulR, ey, fRy); fRz = fma(ulR, ez, fRz);
+                    fIx = fma(ulI, ex, fIx); fIy = fma(ulI, ey, fIy); fIz = fma(ulI, ez, fIz);
+                    lapR = fma(ulR, 2.0 / r, lapR);
+                    lapI = fma(ulI, 2.0 / r, lapI);
+                    if (lower)
+                    {
+                        csum += 1.0;
+                        lsum += r;
+                    }
                 }
                 else
                 {
-                    const double interval = (r - rs) / h; // HeBulk.cpp:279-282
-                    bin = (int)floor(interval);
-                    const double res = interval - bin;
+                    double interval, nps; // HeBulk.cpp:279-282, HeDrop.cpp:431-446
+                    if (r < r2s)
+                    {
+                        nps = s.h;
+                        interval = (r - rs) / nps;
+                        bin = (int)floor(interval);
+                    }
+                    else
+                    {
+                        nps = s.h_large;
+                        interval = (r - r2s) / nps;
+                        bin = (int)floor(interval) + s.n_short;
+                    }
+                    const double res = interval - floor(interval);
                     const double res2 = res * res;
+                    const double nps2 = nps * nps;
                     double tmp[4], l2[4];
                     tmp[0] = -1.0 / 2.0 * (1.0 - 2.0 * res + res2); // HeBulk.cpp:284-287
                     tmp[1] = 1.0 / 6.0 * (-12.0 * res + 9.0 * res2);
                     tmp[2] = 1.0 / 6.0 * (3.0 + 6.0 * res - 9.0 * res2);
                     tmp[3] = 1.0 / 2.0 * res2;
-                    const double f2 = 2.0 / (h * r);
-                    l2[0] = 1.0 / h2 * (1.0 - res) + f2 * tmp[0]; // HeBulk.cpp:299-302
-                    l2[1] = 1.0 / h2 * (1.0 / 6.0 * (-12.0 + 18.0 * res)) + f2 * tmp[1];
-                    l2[2] = 1.0 / h2 * (1.0 / 6.0 * (6.0 - 18.0 * res)) + f2 * tmp[2];
-                    l2[3] = 1.0 / h2 * (res) + f2 * tmp[3];
+                    const double f2 = 2.0 / (nps * r);
+                    l2[0] = 1.0 / nps2 * (1.0 - res) + f2 * tmp[0]; // HeBulk.cpp:299-302
+                    l2[1] = 1.0 / nps2 * (1.0 / 6.0 * (-12.0 + 18.0 * res)) + f2 * tmp[1];
+                    l2[2] = 1.0 / nps2 * (1.0 / 6.0 * (6.0 - 18.0 * res)) + f2 * tmp[2];
+                    l2[3] = 1.0 / nps2 * (res) + f2 * tmp[3];
                     const double ex = vx / r, ey = vy / r, ez = vz / r;
                     double gR = 0.0, gI = 0.0;
 #pragma unroll
@@ -148,8 +213,8 @@ __global__ void __launch_bounds__(256) evaluate_he_kernel(EvalArgs a)
                         lapR = fma(uRk, l2[b], lapR);
                         lapI = fma(uIk, l2[b], lapI);
                     }
-                    gR = gR / h;
-                    gI = gI / h;
+                    gR = gR / nps;
+                    gI = gI / nps;
                     fRx = fma(gR, ex, fRx); fRy = fma(gR, ey, fRy); fRz = fma(gR, ez, fRz);
                     fIx = fma(gI, ex, fIx); fIy = fma(gI, ey, fIy); fIz = fma(gI, ez, fIz);
                     if (lower)
@@ -168,6 +233,12 @@ __global__ void __launch_bounds__(256) evaluate_he_kernel(EvalArgs a)
         }
         if (valid)
         {
+            if (NR > 0) // density profile around the centre of mass, HeDrop.cpp:482-491
+            {
+                const double d0 = xn - com[0], d1 = yn - com[1], d2 = zn - com[2];
+                const double rr = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+                if (rr < s.gr_max) atomicAdd(&gr[G + min((int)floor(rr / gr_spacing), NR - 1)], 1);
+            }
             fRx += s.g0R; fRy += s.g0R; fRz += s.g0R; // the literal 1 of the last parameter, HeBulk.cpp:351
             fIx += s.g0I; fIy += s.g0I; fIz += s.g0I;
             R1 += fRx * fRx + fRy * fRy + fRz * fRz;
@@ -187,11 +258,12 @@ __global__ void __launch_bounds__(256) evaluate_he_kernel(EvalArgs a)
     }
 
     R1 = warp_sum(R1); I1 = warp_sum(I1); RI = warp_sum(RI);
-    lapR = warp_sum(lapR); lapI = warp_sum(lapI); pot = warp_sum(pot); mcm = warp_sum(mcm);
+    lapR = warp_sum(lapR); lapI = warp_sum(lapI); pot = warp_sum(pot);
+    mcm = warp_sum(mcm); csum = warp_sum(csum); lsum = warp_sum(lsum);
     if (lane == 0)
     {
-        double* r = red + warp * 8;
-        r[0] = R1; r[1] = I1; r[2] = RI; r[3] = lapR; r[4] = lapI; r[5] = pot; r[6] = mcm; r[7] = 0.0;
+        double* r = red + warp * 12;
+        r[0] = R1; r[1] = I1; r[2] = RI; r[3] = lapR; r[4] = lapI; r[5] = pot; r[6] = mcm; r[7] = csum; r[8] = lsum;
     }
     __syncthreads();
     for (int k = tid; k < K; k += blockDim.x)
@@ -199,45 +271,53 @@ __global__ void __launch_bounds__(256) evaluate_he_kernel(EvalArgs a)
         double t = 0.0;
         for (int w = 0; w < nwarps; w++) t += hist[(size_t)w * K + k];
         ext[k] = t;
-        if (a.ss_out) a.ss_out[(size_t)cfg * NE + k] = t;
     }
     if (tid == 0)
     {
-        double t = 0.0;
-        for (int w = 0; w < nwarps; w++) t += red[w * 8 + 6];
-        ext[K] = t;
-        if (a.ss_out) a.ss_out[(size_t)cfg * NE + K] = t;
+        double t6 = 0.0, t7 = 0.0, t8 = 0.0;
+        for (int w = 0; w < nwarps; w++)
+        {
+            t6 += red[w * 12 + 6];
+            t7 += red[w * 12 + 7];
+            t8 += red[w * 12 + 8];
+        }
+        ext[MC] = t6;
+        ext[CO] = t7;
+        ext[LI] = t8;
     }
     __syncthreads();
+    if (a.ss_out)
+        for (int k = tid; k < NE; k += blockDim.x) a.ss_out[(size_t)cfg * NE + k] = ext[k];
 
     const long long row = a.row0 + (long long)cfg * a.row_stride;
     double* Arow = a.A + (size_t)row * a.lda;
     double epart = 0.0;
     for (int p = tid; p < P; p += blockDim.x)
     {
-        double o = s.map_const[p]; // HeBulk.cpp:376-383
+        double o = s.map_const[p]; // HeBulk.cpp:376-383, HeDrop.cpp:609-626
         for (int j = s.map_ptr[p]; j < s.map_ptr[p + 1]; j++) o += s.map_val[j] * ext[s.map_col[j]];
         Arow[p] = o;
         epart = fma(s.uR[p], o, epart); // HeBulk.cpp:491-498
     }
     epart = warp_sum(epart);
-    if (lane == 0) red[warp * 8 + 7] = epart;
+    if (lane == 0) red[warp * 12 + 9] = epart;
     __syncthreads();
     double* orow = a.other + (size_t)row * s.n_other;
-    for (int b = tid; b < G; b += blockDim.x)
+    for (int b = tid; b < G + NR; b += blockDim.x)
     {
-        // 1 / grBinVolumes[b], HeBulk.cpp:133-143
-        const double r1 = gr_spacing * (b + 1), r0 = gr_spacing * b;
+        // 1 / grBinVolumes[b], HeBulk.cpp:133-143 (the density profile uses the same shell volumes, HeDrop.cpp:490)
+        const int bb = b < G ? b : b - G;
+        const double r1 = gr_spacing * (bb + 1), r0 = gr_spacing * bb;
         double vol = 4.0 * M_PI * (r1 * r1 * r1) / 3.0;
-        if (b > 0) vol = vol - 4.0 * M_PI * (r0 * r0 * r0) / 3.0;
+        if (bb > 0) vol = vol - 4.0 * M_PI * (r0 * r0 * r0) / 3.0;
         orow[3 + b] = (double)gr[b] * (1.0 / vol);
     }
     if (tid == 0)
     {
-        double t[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+        double t[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
         for (int w = 0; w < nwarps; w++)
-            for (int q = 0; q < 8; q++) t[q] += red[w * 8 + q];
-        const double exponent = t[7];
+            for (int q = 0; q < 10; q++) t[q] += red[w * 12 + q];
+        const double exponent = t[9];
         const double kRI = 2.0 * t[2];
         const double kin_r = -s.hbar * (t[0] - t[1] + t[3]); // HeBulk.cpp:363-364
         const double kin_i = -s.hbar * (kRI + t[4]);
@@ -247,7 +327,7 @@ __global__ void __launch_bounds__(256) evaluate_he_kernel(EvalArgs a)
         Arow[P + 2] = 1.0;
         orow[0] = kin_r; // HeBulk.cpp:395-397
         orow[1] = t[5];
-        orow[2] = exp(exponent);
+        orow[2] = s.use_phi ? exp(exponent + s.phiR) : exp(exponent);
         if (a.exponent) a.exponent[row] = exponent;
         if (a.outer_out) a.outer_out[cfg] = 0.0;
     }
@@ -260,8 +340,8 @@ cudaError_t launch_evaluate_he(const EvalArgs& a, cudaStream_t st)
     int threads = ((s.N + 31) / 32) * 32;
     if (threads > 256) threads = 256;
     const int nwarps = threads / 32;
-    size_t smem = sizeof(double) * ((size_t)2 * s.n_ext + 3 * (size_t)s.N + (size_t)nwarps * s.K + s.n_ext + (size_t)nwarps * 8) +
-                  sizeof(int) * (size_t)s.gr_bins + 16;
+    size_t smem = sizeof(double) * ((size_t)2 * s.n_ext + 3 * (size_t)s.N + (size_t)nwarps * s.K + s.n_ext + (size_t)nwarps * 12 + 4) +
+                  sizeof(int) * (size_t)(s.gr_bins + s.rho_bins) + 16;
     cudaError_t e = cudaFuncSetAttribute(evaluate_he_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     evaluate_he_kernel<<<a.n_cfg, threads, smem, st>>>(a);

@@ -50,6 +50,14 @@ __device__ __forceinline__ double mi2_wrapped(double dx, double dy, double dz, d
     return fma(mz, mz, fma(my, my, mx * mx));
 }
 
+// squared pair distance: minimum image of wrapped points, or the plain difference for open boundaries
+template <bool OPEN>
+__device__ __forceinline__ double dist2(double dx, double dy, double dz, double Lhalf)
+{
+    if (OPEN) return fma(dz, dz, fma(dy, dy, dx * dx));
+    return mi2_wrapped(dx, dy, dz, Lhalf);
+}
+
 // sqrt(x) to ~2 ulp: MUFU.RSQ64H seed (22 bits) + one third-order step; x == 0 gives NaN, which the
 // callers discard (it only happens for the moved particle against itself)
 __device__ __forceinline__ double sqrt_fast(double x)
@@ -77,6 +85,7 @@ __device__ __forceinline__ double pair_u(const SysDev& s, const double2* __restr
     {
         // HeBulk: McMillan core u~_mc r^m below rijSplit (HeBulk.cpp:471-474); the uniform grid starts at rijSplit
         if (r < s.r0) return s.u_core * pow(r, s.core_m);
+        if (r >= s.r_tail) return fma(s.u_lin, r, s.u_const); // const + linear tails, HeDrop.cpp:732-737
         r -= s.r0;
     }
     // floor(r * inv) via the rounding constant; the integer sits in the low word
@@ -106,7 +115,7 @@ __device__ __forceinline__ double pair_u(const SysDev& s, const double2* __restr
     return v;
 }
 
-template <bool UNIFORM, bool REFLECT, int UNROLL, bool HE = false>
+template <bool UNIFORM, bool REFLECT, int UNROLL, bool HE = false, bool OPEN = false>
 __global__ void __launch_bounds__(kSweepMaxThreads, kSweepMinBlocks) sweep_kernel(SweepArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -152,9 +161,9 @@ __global__ void __launch_bounds__(kSweepMaxThreads, kSweepMinBlocks) sweep_kerne
     {
         for (int i = lane; i < s.N; i += 32) // positions live wrapped into the first cell during the sweep
         {
-            px[i] = wrap_fast(gpos[i], L, Linv);
-            py[i] = wrap_fast(gpos[s.Np + i], L, Linv);
-            pz[i] = wrap_fast(gpos[2 * s.Np + i], L, Linv);
+            px[i] = OPEN ? gpos[i] : wrap_fast(gpos[i], L, Linv);
+            py[i] = OPEN ? gpos[s.Np + i] : wrap_fast(gpos[s.Np + i], L, Linv);
+            pz[i] = OPEN ? gpos[2 * s.Np + i] : wrap_fast(gpos[2 * s.Np + i], L, Linv);
         }
     }
     __syncthreads();
@@ -183,17 +192,17 @@ __global__ void __launch_bounds__(kSweepMaxThreads, kSweepMinBlocks) sweep_kerne
             const double log_u = __shfl_sync(FULL_MASK, mine.log_u, sidx);
 
             const double ox = px[p], oy = py[p], oz = pz[p];
-            const double nx = wrap_fast(ox + ddx, L, Linv); // src/TDVMC.cpp:872-875, kept in the first cell
-            const double ny = wrap_fast(oy + ddy, L, Linv);
-            const double nz = wrap_fast(oz + ddz, L, Linv);
+            const double nx = OPEN ? ox + ddx : wrap_fast(ox + ddx, L, Linv); // src/TDVMC.cpp:872-875, kept in the first cell
+            const double ny = OPEN ? oy + ddy : wrap_fast(oy + ddy, L, Linv);
+            const double nz = OPEN ? oz + ddz : wrap_fast(oz + ddz, L, Linv);
 
             double delta = 0.0;
 #pragma unroll UNROLL
             for (int i = lane; i < N; i += 32)
             {
                 const double xi = px[i], yi = py[i], zi = pz[i];
-                const double r_old = sqrt_fast(mi2_wrapped(xi - ox, yi - oy, zi - oz, Lhalf));
-                const double r_new = sqrt_fast(mi2_wrapped(xi - nx, yi - ny, zi - nz, Lhalf));
+                const double r_old = sqrt_fast(dist2<OPEN>(xi - ox, yi - oy, zi - oz, Lhalf));
+                const double r_new = sqrt_fast(dist2<OPEN>(xi - nx, yi - ny, zi - nz, Lhalf));
                 const double u_old = pair_u<UNIFORM, REFLECT, kCubCopies, HE>(s, c01p, c23p, ttp, lut, r_old);
                 const double u_new = pair_u<UNIFORM, REFLECT, kCubCopies, HE>(s, c01p, c23p, ttp, lut, r_new);
                 const double d = u_new - u_old;
@@ -229,7 +238,7 @@ __global__ void __launch_bounds__(kSweepMaxThreads, kSweepMinBlocks) sweep_kerne
 
 // exponentNew - exponent for scripted moves of one configuration: the ratio evaluator of the sweep,
 // one warp per move, tables read straight from global memory (parity entry point, not a hot path)
-template <bool UNIFORM, bool REFLECT, bool HE = false>
+template <bool UNIFORM, bool REFLECT, bool HE = false, bool OPEN = false>
 __global__ void quotient_kernel(QuotientArgs a)
 {
     const SysDev& s = a.s;
@@ -244,15 +253,15 @@ __global__ void quotient_kernel(QuotientArgs a)
     const double* pz = a.pos + 2 * s.Np;
     const double L = s.L, Linv = s.Linv, Lhalf = s.Lhalf;
     const int p = (int)a.moves[mv * 4];
-    const double nx = wrap_fast(a.moves[mv * 4 + 1], L, Linv), ny = wrap_fast(a.moves[mv * 4 + 2], L, Linv),
-                 nz = wrap_fast(a.moves[mv * 4 + 3], L, Linv);
-    const double ox = wrap_fast(px[p], L, Linv), oy = wrap_fast(py[p], L, Linv), oz = wrap_fast(pz[p], L, Linv);
+    auto W = [&](double x) { return OPEN ? x : wrap_fast(x, L, Linv); };
+    const double nx = W(a.moves[mv * 4 + 1]), ny = W(a.moves[mv * 4 + 2]), nz = W(a.moves[mv * 4 + 3]);
+    const double ox = W(px[p]), oy = W(py[p]), oz = W(pz[p]);
     double delta = 0.0;
     for (int i = lane; i < s.N; i += 32)
     {
-        const double xi = wrap_fast(px[i], L, Linv), yi = wrap_fast(py[i], L, Linv), zi = wrap_fast(pz[i], L, Linv);
-        const double r_old = sqrt_fast(mi2_wrapped(xi - ox, yi - oy, zi - oz, Lhalf));
-        const double r_new = sqrt_fast(mi2_wrapped(xi - nx, yi - ny, zi - nz, Lhalf));
+        const double xi = W(px[i]), yi = W(py[i]), zi = W(pz[i]);
+        const double r_old = sqrt_fast(dist2<OPEN>(xi - ox, yi - oy, zi - oz, Lhalf));
+        const double r_new = sqrt_fast(dist2<OPEN>(xi - nx, yi - ny, zi - nz, Lhalf));
         const double d = pair_u<UNIFORM, REFLECT, 1, HE>(s, c01p, c23p, ttp, s.lut, r_new) -
                          pair_u<UNIFORM, REFLECT, 1, HE>(s, c01p, c23p, ttp, s.lut, r_old);
         if (i != p) delta += d;
@@ -268,6 +277,10 @@ cudaError_t launch_quotient(const QuotientArgs& a, cudaStream_t st)
     if (a.s.kind == 1)
     {
         quotient_kernel<true, false, true><<<a.n_moves, 32, 0, st>>>(a);
+    }
+    else if (a.s.kind == 2)
+    {
+        quotient_kernel<false, false, true, true><<<a.n_moves, 32, 0, st>>>(a);
     }
     else if (a.s.uniform)
     {
@@ -292,13 +305,13 @@ size_t sweep_smem_bytes(const SysDev& s, int wpb, int npp, size_t* pos_offset)
     return off + (size_t)wpb * 3 * npp * sizeof(double);
 }
 
-template <bool U, bool R, int UNROLL, bool HE = false>
+template <bool U, bool R, int UNROLL, bool HE = false, bool OPEN = false>
 static cudaError_t launch_one(const SweepArgs& a, int grid, int threads, size_t smem, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<U, R, UNROLL, HE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<U, R, UNROLL, HE, OPEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    cudaFuncSetAttribute(sweep_kernel<U, R, UNROLL, HE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    sweep_kernel<U, R, UNROLL, HE><<<grid, threads, smem, st>>>(a);
+    cudaFuncSetAttribute(sweep_kernel<U, R, UNROLL, HE, OPEN>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    sweep_kernel<U, R, UNROLL, HE, OPEN><<<grid, threads, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -319,6 +332,7 @@ static const void* sweep_fn(const SysDev& s)
 {
     const bool refl = s.pair_rule == 1;
     if (s.kind == 1) return (const void*)sweep_kernel<true, false, UNROLL, true>;
+    if (s.kind == 2) return (const void*)sweep_kernel<false, false, UNROLL, true, true>;
     return s.uniform ? (refl ? (const void*)sweep_kernel<true, true, UNROLL> : (const void*)sweep_kernel<true, false, UNROLL>)
                      : (refl ? (const void*)sweep_kernel<false, true, UNROLL> : (const void*)sweep_kernel<false, false, UNROLL>);
 }
@@ -328,6 +342,7 @@ static cudaError_t launch_unroll(const SweepArgs& a, int grid, int threads, size
 {
     const bool refl = a.s.pair_rule == 1;
     if (a.s.kind == 1) return launch_one<true, false, UNROLL, true>(a, grid, threads, smem, st);
+    if (a.s.kind == 2) return launch_one<false, false, UNROLL, true, true>(a, grid, threads, smem, st);
     if (a.s.uniform)
         return refl ? launch_one<true, true, UNROLL>(a, grid, threads, smem, st) : launch_one<true, false, UNROLL>(a, grid, threads, smem, st);
     return refl ? launch_one<false, true, UNROLL>(a, grid, threads, smem, st) : launch_one<false, false, UNROLL>(a, grid, threads, smem, st);

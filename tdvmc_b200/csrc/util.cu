@@ -4,7 +4,9 @@
 namespace tdvmc
 {
 
-// MoveCoordinatesToFirstCell (src/TDVMC.cpp:787-796): R[i][j] = GetCoordinateNIC(R[i][j])
+// AlignCoordinates (src/TDVMC.cpp:2569-2582): MoveCoordinatesToFirstCell for USE_NIC systems (:787-796,
+// R[i][j] = GetCoordinateNIC(R[i][j])), MoveCenterOfMassToZero for USE_MOVE_COM_TO_ZERO systems (:798-809,
+// HeDrop::GetCenterOfMass, HeDrop.cpp:255-270: plain mean)
 __global__ void wrap_kernel(SysDev s, double* pos, int W)
 {
     const size_t total = (size_t)W * 3 * s.Np;
@@ -14,9 +16,22 @@ __global__ void wrap_kernel(SysDev s, double* pos, int W)
         if (i < s.N) pos[idx] = nic_exact(pos[idx], s.L, s.Linv, s.Lhalf);
     }
 }
+__global__ void com_kernel(SysDev s, double* pos, int W)
+{
+    // one warp per (walker, coordinate) row
+    const int lane = threadIdx.x & 31;
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= W * 3) return;
+    double* p = pos + (size_t)row * s.Np;
+    double t = 0.0;
+    for (int i = lane; i < s.N; i += 32) t += p[i];
+    t = warp_sum(t) / (double)s.N;
+    for (int i = lane; i < s.N; i += 32) p[i] -= t;
+}
 cudaError_t launch_wrap(const SysDev& s, double* pos, int W, cudaStream_t st)
 {
-    wrap_kernel<<<296, 256, 0, st>>>(s, pos, W);
+    if (s.periodic) wrap_kernel<<<296, 256, 0, st>>>(s, pos, W);
+    else com_kernel<<<(W * 3 * 32 + 255) / 256, 256, 0, st>>>(s, pos, W);
     return cudaGetLastError();
 }
 

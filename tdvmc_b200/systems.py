@@ -20,6 +20,7 @@ PAIR_RULE_REFLECT = 1  # r -> 2 r_max - r beyond r_max, then r < r_max (NUBosons
 
 KIND_SPLINE_TABLE = 0   # BosonsBulk, NUBosonsBulkPB: monomial spline table + boundary map
 KIND_HE_BULK = 1        # HeBulk: McMillan core + uniform B-splines in the local coordinate + Aziz potential
+KIND_HE_DROP = 2        # HeDrop: open boundary, McMillan core, two uniform grids, const + linear tails, LJ potential
 
 HBAR2_2M = 1.0  # src/Constants.h:12
 
@@ -141,8 +142,8 @@ def nu_bosons_bulk_pb(n_particles, lbox, n_params, nurbs_grid, system_params=(0.
 
 def he_bulk(n_particles, lbox, n_params):
     """``HeBulk`` (HeBulk.cpp:40-70): ``K = P + 5`` uniform splines of spacing ``h = (L/2 - rs)/(K - 3)`` starting at the
-    McMillan split ``rs = 1.95``; extended sums are ``[ss_0 .. ss_{K-1}, mcMillanSum]``; parameter map of :376-383 with
-    the constant 1 of the last operator and the literal 1 added to its gradient (:351)."""
+    McMillan split ``rs = 1.95``; extended sums are ``[ss_0 .. ss_{K-1}, mcMillanSum, constSum, linearSum]`` (the last two
+    unused); parameter map of :376-383 with the constant 1 of the last operator and the literal 1 added to its gradient (:351)."""
     P = n_params
     K = P - 1 + 3 + 3
     rs = 1.95
@@ -160,9 +161,47 @@ def he_bulk(n_particles, lbox, n_params):
     gconst = np.zeros(P)
     gconst[P - 1] = 1.0
     knots = rs + h * np.arange(-3, K + 1, dtype=np.float64)   # informational only: the kernels use (rs, h)
+    inf = float("inf")
     return SystemSpec("HeBulk", n_particles, P, float(lbox), knots, np.zeros((K, 4, 4)), ptr, col, val, PAIR_RULE_CUT,
-                      np.zeros(0), n_other=3 + 100, tail_param=-1, kind=KIND_HE_BULK, n_ext=K + 1, map_const=mconst,
-                      grad_const=gconst, extra=dict(n_splines=K, r_max=half, rij_split=rs, h=h, factors=(f11, 1.0, f21, -0.5, -0.5, 1.0, -1.5, 0.0)))
+                      np.zeros(0), n_other=3 + 100, tail_param=-1, kind=KIND_HE_BULK, n_ext=K + 3, map_const=mconst,
+                      grad_const=gconst,
+                      extra=dict(n_splines=K, n_short=K, r_max=half, rij_split=rs, h=h, h_large=h, r_split2=inf, r_tail=inf,
+                                 mcm=-5.0, gr_bins=100, rho_bins=0, gr_max=half, periodic=1, potential=0, use_phi=0,
+                                 factors=(f11, 1.0, f21, -0.5, -0.5, 1.0, -1.5, 0.0)))
+
+
+def he_drop(n_particles, n_params):
+    """``HeDrop`` (HeDrop.cpp:71-135): open boundary, McMillan ``r^-4.7`` below ``rs = 3``, 70 splines of spacing 0.1, then
+    spacing 0.5 up to ``r_tail``, constant + linear tails beyond; ``K = P + 3``; parameter map of :609-626."""
+    P = n_params
+    m, rs, hS, hL, nS = -4.7, 3.0, 0.1, 0.5, 70
+    K = P + 1 + 2
+    nL = K - nS
+    r2 = hS * (nS - 3.0) + rs
+    rt = hL * (nL - 3.0) + r2
+    fFS1 = -2.0 * m * hS * rs ** (m - 1.0)
+    fSS1 = (m * hS + 3.0 * rs) * rs ** (m - 1.0) / 2.0
+    d = 1.0 / (hS + hL)
+    fSLS, fSLL = (-hS + hL) * d, (2.0 * hL) * d
+    fLS, fLL = (-4.0 * hS) * d, (4.0 * hL) * d
+    fFS, fFL = (4.0 * hS) * d, (-4.0 * hL) * d
+    fSS, fSL = (2.0 * hS) * d, (hS - hL) * d
+    MC, CO, LI = K, K + 1, K + 2
+    rows = [[(MC, 1.0), (0, fFS1), (1, fSS1)], [(2, 1.0), (0, 1.0), (1, -0.5)]]
+    rows += [[(i + 1, 1.0)] for i in range(2, nS - 4)]
+    rows += [[(nS - 3, 1.0), (nS - 1, fSLS), (nS, fSLL)], [(nS - 2, 1.0), (nS - 1, fLS), (nS, fLL)],
+             [(nS + 1, 1.0), (nS - 1, fFS), (nS, fFL)], [(nS + 2, 1.0), (nS - 1, fSS), (nS, fSL)]]
+    rows += [[(i + 3, 1.0)] for i in range(nS, P - 3)]
+    rows += [[(K - 3, 1.0), (K - 2, -0.5), (K - 1, 1.0)], [(CO, 1.0), (K - 2, 1.5), (K - 1, 0.0)],
+             [(LI, 1.0), (K - 2, 1.5 * rt - hL / 2.0), (K - 1, 2.0 * hL)]]
+    assert len(rows) == P
+    ptr, col, val = _csr(rows)
+    knots = np.concatenate([rs + hS * np.arange(0, nS - 3), r2 + hL * np.arange(0, nL - 2)])
+    inf = float("inf")
+    return SystemSpec("HeDrop", n_particles, P, 0.0, knots, np.zeros((K, 4, 4)), ptr, col, val, PAIR_RULE_CUT, np.zeros(0),
+                      n_other=3 + 200 + 200, tail_param=-1, kind=KIND_HE_DROP, n_ext=K + 3,
+                      extra=dict(n_splines=K, n_short=nS, r_max=inf, rij_split=rs, h=hS, h_large=hL, r_split2=r2, r_tail=rt,
+                                 mcm=m, gr_bins=200, rho_bins=200, gr_max=2.0 * rt, periodic=0, potential=1, use_phi=1))
 
 
 def from_golden(g):
@@ -173,6 +212,18 @@ def from_golden(g):
         spec = he_bulk(N, L, P)
         if spec.extra["h"] != float(g["node_point_spacing"]) or not np.array_equal(spec.extra["factors"], g["bc_factors"]):
             raise AssertionError("HeBulk set-up differs from the reference dump")
+        return spec
+    if name == "HeDrop":
+        spec = he_drop(N, P)
+        ref = g["bc_factors"]   # every factor* member of the reference object, in declaration order (HeDrop.h:70-89)
+        rows = spec.map_rows()
+        nS, K = 70, spec.n_splines
+        mine = [rows[0][1][1], rows[1][1][1], rows[0][2][1], rows[1][2][1], rows[P - 3][1][1], rows[P - 2][1][1],
+                rows[P - 1][1][1], rows[P - 3][2][1], rows[P - 2][2][1], rows[P - 1][2][1], rows[nS - 4][1][1],
+                rows[nS - 4][2][1], rows[nS - 3][1][1], rows[nS - 3][2][1], rows[nS - 2][1][1], rows[nS - 2][2][1],
+                rows[nS - 1][1][1], rows[nS - 1][2][1]]
+        if not np.array_equal(np.array(mine), ref) or spec.extra["r_tail"] != float(g["rij_tail"]):
+            raise AssertionError("HeDrop set-up differs from the reference dump")
         return spec
     if name == "BosonsBulk":
         spec = bosons_bulk(N, L, P, g["SYSTEM_PARAMS"], weights=g["spline_weights"])

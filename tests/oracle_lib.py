@@ -19,10 +19,13 @@ class OracleSystem(C.Structure):
                 ("map_ptr", ip), ("map_col", ip), ("map_val", dp)]
 
 
-class OracleHeBulkStruct(C.Structure):
-    _fields_ = [("n_particles", C.c_int32), ("n_params", C.c_int32), ("n_splines", C.c_int32), ("gr_bins", C.c_int32),
-                ("lbox", C.c_double), ("rij_split", C.c_double), ("h", C.c_double), ("max_distance", C.c_double),
-                ("hbar2_2m", C.c_double), ("f", C.c_double * 8)]
+class OracleHeStruct(C.Structure):
+    _fields_ = [("n_particles", C.c_int32), ("n_params", C.c_int32), ("n_splines", C.c_int32), ("n_short", C.c_int32),
+                ("periodic", C.c_int32), ("potential", C.c_int32), ("gr_bins", C.c_int32), ("rho_bins", C.c_int32),
+                ("use_phi", C.c_int32), ("pad", C.c_int32), ("lbox", C.c_double), ("rs", C.c_double), ("r_split2", C.c_double),
+                ("r_tail", C.c_double), ("h_short", C.c_double), ("h_large", C.c_double), ("max_distance", C.c_double),
+                ("mcm", C.c_double), ("gr_max", C.c_double), ("hbar2_2m", C.c_double), ("map_ptr", ip), ("map_col", ip),
+                ("map_val", dp), ("map_const", dp), ("grad_const", dp)]
 
 
 def lib():
@@ -37,10 +40,10 @@ def lib():
         L.oracle_wf_quotient.restype = C.c_double
         L.oracle_sweep.restype = C.c_int64
         L.oracle_sample_walker.restype = C.c_int64
-        L.oracle_hebulk_exponent.restype = C.c_double
-        L.oracle_hebulk_quotient.restype = C.c_double
-        L.oracle_hebulk_sweep.restype = C.c_int64
-        L.oracle_hebulk_sample_walker.restype = C.c_int64
+        L.oracle_he_exponent.restype = C.c_double
+        L.oracle_he_quotient.restype = C.c_double
+        L.oracle_he_sweep.restype = C.c_int64
+        L.oracle_he_sample_walker.restype = C.c_int64
         _LIB = L
     return _LIB
 
@@ -168,68 +171,76 @@ class Oracle:
                     other=est[P + 2 + P * P + 2 * P:] / n)
 
 
-class OracleHeBulk:
-    """HeBulk restatement (oracle/tdvmc_oracle_he.c) with numpy in/out."""
+class OracleHe:
+    """He family restatement (oracle/tdvmc_oracle_he.c: HeBulk, HeDrop) with numpy in/out."""
 
     def __init__(self, spec, time=0.0):
         self.spec = spec
-        self.sys = OracleHeBulkStruct()
-        lib().oracle_hebulk_init(C.byref(self.sys), spec.n_particles, C.c_double(spec.lbox), spec.n_params)
-        self.N, self.P, self.K, self.NO = spec.n_particles, spec.n_params, self.sys.n_splines, 3 + self.sys.gr_bins
+        e = spec.extra
+        self._keep = [np.ascontiguousarray(spec.map_ptr, np.int32), np.ascontiguousarray(spec.map_col, np.int32),
+                      np.ascontiguousarray(spec.map_val, np.float64), np.ascontiguousarray(spec.map_const, np.float64),
+                      np.ascontiguousarray(spec.grad_const, np.float64)]
+        k = self._keep
+        big = 1e300
+        f = lambda x: float(min(x, big))
+        self.sys = OracleHeStruct(spec.n_particles, spec.n_params, e["n_splines"], e["n_short"], e["periodic"], e["potential"],
+                                  e["gr_bins"], e["rho_bins"], e["use_phi"], 0, spec.lbox, e["rij_split"], f(e["r_split2"]),
+                                  f(e["r_tail"]), e["h"], e["h_large"], f(e["r_max"]), e["mcm"], e["gr_max"], spec.hbar2_2m,
+                                  k[0].ctypes.data_as(ip), k[1].ctypes.data_as(ip), _d(k[2]), _d(k[3]), _d(k[4]))
+        self.N, self.P, self.K, self.NE = spec.n_particles, spec.n_params, e["n_splines"], e["n_splines"] + 3
+        self.NO = 3 + e["gr_bins"] + e["rho_bins"]
+        self.use_phi = e["use_phi"]
 
     def values(self, R):
         R = np.ascontiguousarray(R, np.float64)
-        ss = np.zeros(self.K)
-        mcm = C.c_double(0)
-        lib().oracle_hebulk_values(C.byref(self.sys), _d(R), _d(ss), C.byref(mcm))
-        return ss, mcm.value
+        ext = np.zeros(self.NE)
+        lib().oracle_he_values(C.byref(self.sys), _d(R), _d(ext))
+        return ext
 
-    def operators(self, ss, mcm):
+    def operators(self, ext):
         O = np.zeros(self.P)
-        lib().oracle_hebulk_operators(C.byref(self.sys), _d(np.ascontiguousarray(ss)), C.c_double(mcm), _d(O))
+        lib().oracle_he_operators(C.byref(self.sys), _d(np.ascontiguousarray(ext)), _d(O))
         return O
 
-    def exponent(self, ss, mcm, uR):
-        return lib().oracle_hebulk_exponent(C.byref(self.sys), _d(np.ascontiguousarray(ss)), C.c_double(mcm),
-                                            _d(np.ascontiguousarray(uR, np.float64)))
+    def exponent(self, ext, uR):
+        return lib().oracle_he_exponent(C.byref(self.sys), _d(np.ascontiguousarray(ext)), _d(np.ascontiguousarray(uR, np.float64)))
 
     def evaluate(self, R, uR, uI, phiR=0.0):
         R = np.ascontiguousarray(R, np.float64)
         uR = np.ascontiguousarray(uR, np.float64)
         uI = np.ascontiguousarray(uI, np.float64)
-        ss, mcm = self.values(R)
-        ex = self.exponent(ss, mcm, uR)
+        ext = self.values(R)
+        ex = self.exponent(ext, uR)
+        wf = np.exp(ex + phiR) if self.use_phi else np.exp(ex)
         er, ei = C.c_double(0), C.c_double(0)
         other = np.zeros(self.NO)
         dr, di = np.zeros((self.N, 3)), np.zeros((self.N, 3))
-        sD, sD2 = np.zeros((self.K, self.N, 3)), np.zeros((self.K, self.N))
-        mcD, mcD2 = np.zeros((self.N, 3)), np.zeros(self.N)
-        lib().oracle_hebulk_expectation(C.byref(self.sys), _d(R), C.c_double(np.exp(ex)), _d(uR), _d(uI), C.byref(er), C.byref(ei),
-                                        _d(other), _d(dr), _d(di), _d(sD), _d(sD2), _d(mcD), _d(mcD2))
-        return dict(ss=ss, mcm=mcm, O=self.operators(ss, mcm), exponent=ex, e_r=er.value, e_i=ei.value, other=other,
-                    drift_r=dr, drift_i=di, sD=sD, sD2=sD2, mcD=mcD, mcD2=mcD2)
+        tD, tD2 = np.zeros((self.NE, self.N, 3)), np.zeros((self.NE, self.N))
+        lib().oracle_he_expectation(C.byref(self.sys), _d(R), C.c_double(wf), _d(uR), _d(uI), C.byref(er), C.byref(ei), _d(other),
+                                    _d(dr), _d(di), _d(tD), _d(tD2))
+        return dict(ext=ext, ss=ext[:self.K], mcm=ext[self.K], O=self.operators(ext), exponent=ex, e_r=er.value, e_i=ei.value,
+                    other=other, drift_r=dr, drift_i=di, tabD=tD, tabD2=tD2)
 
     def quotient(self, R, particle, new_pos, uR):
         R = np.array(R, np.float64)
         uR = np.ascontiguousarray(uR, np.float64)
-        ss, mcm = self.values(R)
-        ex = self.exponent(ss, mcm, uR)
+        ext = self.values(R)
+        ex = self.exponent(ext, uR)
         old = R[particle].copy()
         R[particle] = new_pos
-        ss_new = np.zeros(self.K)
-        mn, en = C.c_double(0), C.c_double(0)
-        q = lib().oracle_hebulk_quotient(C.byref(self.sys), _d(R), int(particle), _d(old), _d(ss), C.c_double(mcm),
-                                         C.c_double(ex), _d(uR), _d(ss_new), C.byref(mn), C.byref(en))
+        ext_new = np.zeros(self.NE)
+        en = C.c_double(0)
+        q = lib().oracle_he_quotient(C.byref(self.sys), _d(R), int(particle), _d(old), _d(ext), C.c_double(ex), _d(uR),
+                                     _d(ext_new), C.byref(en))
         return q, en.value, ex
 
     def sweep(self, R, uR, seed, walker, first_step, n_steps, mc_step):
         R = np.array(R, np.float64)
         uR = np.ascontiguousarray(uR, np.float64)
-        ss, mcm = self.values(R)
-        ex = C.c_double(self.exponent(ss, mcm, uR))
-        m = C.c_double(mcm)
-        acc = lib().oracle_hebulk_sweep(C.byref(self.sys), _d(R), _d(ss), C.byref(m), C.byref(ex), _d(uR), C.c_uint64(seed),
-                                        C.c_uint32(walker), C.c_uint64(first_step), C.c_int64(n_steps), C.c_double(mc_step))
+        ext = self.values(R)
+        ex = C.c_double(self.exponent(ext, uR))
+        acc = lib().oracle_he_sweep(C.byref(self.sys), _d(R), _d(ext), C.byref(ex), _d(uR), C.c_uint64(seed), C.c_uint32(walker),
+                                    C.c_uint64(first_step), C.c_int64(n_steps), C.c_double(mc_step))
         return R, int(acc)
 
     def est_size(self):
@@ -241,16 +252,20 @@ class OracleHeBulk:
             est = np.zeros(self.est_size())
         rows = np.zeros((n_samples, self.P + 2))
         sc = C.c_uint64(step0)
-        acc = lib().oracle_hebulk_sample_walker(C.byref(self.sys), _d(R), _d(np.ascontiguousarray(uR, np.float64)),
-                                                _d(np.ascontiguousarray(uI, np.float64)), C.c_uint64(seed), C.c_uint32(walker),
-                                                C.byref(sc), n_init, n_samples, n_therm, C.c_double(mc_step), _d(est), _d(rows))
+        acc = lib().oracle_he_sample_walker(C.byref(self.sys), _d(R), _d(np.ascontiguousarray(uR, np.float64)),
+                                            _d(np.ascontiguousarray(uI, np.float64)), C.c_double(phiR), C.c_uint64(seed),
+                                            C.c_uint32(walker), C.byref(sc), n_init, n_samples, n_therm, C.c_double(mc_step),
+                                            _d(est), _d(rows))
         return dict(R=R, est=est, rows=rows, accepted=int(acc), steps=sc.value)
 
     def unpack_est(self, est, n):
         return Oracle.unpack_est(self, est, n)
 
 
+OracleHeBulk = OracleHe
+
+
 def make_oracle(spec, time=0.0):
     from tdvmc_b200 import systems
 
-    return OracleHeBulk(spec, time) if spec.kind == systems.KIND_HE_BULK else Oracle(spec, time)
+    return Oracle(spec, time) if spec.kind == systems.KIND_SPLINE_TABLE else OracleHe(spec, time)

@@ -502,3 +502,66 @@ def test_hebulk_statistics_match_reference_sampler(capi, golden):
     assert abs(got["e_r"][0] - m_ref) < 4.0 * np.hypot(s_ref, s_gpu), (got["e_r"][0], m_ref, s_ref, s_gpu)
     assert abs(got["n_acceptances"] / got["n_trials"] - float(g["acceptance"])) < 0.015
     h.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# HeDrop (BASELINE configs[0], config/drop_6.config): open boundary, two spline grids, const/linear tails, LJ
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["hedrop_n6_fixture", "hedrop_n6_spread", "hedrop_n6_equil"])
+def test_hedrop_fixed_configuration(capi, golden, name):
+    g = golden(name)
+    spec, h = make_handle(capi, g)
+    r = h.evaluate_fixed(g["R"])
+    K = spec.n_splines
+    assert rel(r["ss"][0][:K], g["spline_sums"]) < 1e-13
+    assert abs(r["ss"][0][K] - float(g["mcmillan_sum"])) <= 1e-13 * max(abs(float(g["mcmillan_sum"])), 1e-300)
+    assert r["ss"][0][K + 1] == float(g["const_sum"])
+    assert abs(r["ss"][0][K + 2] - float(g["linear_sum"])) <= 1e-13 * max(abs(float(g["linear_sum"])), 1e-300)
+    assert rel(r["O"][0], g["local_operators"]) < RTOL
+    assert abs(r["exponent"][0] - float(g["exponent"])) < RTOL * abs(float(g["exponent"]))
+    assert abs(r["e_r"][0] - float(g["local_energy_r"])) < RTOL * abs(float(g["local_energy_r"]))
+    assert abs(r["e_i"][0] - float(g["local_energy_i"])) < RTOL * abs(float(g["local_energy_i"]))
+    assert rel(r["drift_r"][0], g["drift_r"]) < RTOL and rel(r["drift_i"][0], g["drift_i"]) < RTOL
+    want, got = g["other_expectation_values"], r["other"][0]
+    assert got.shape == want.shape == (403,)
+    assert abs(got[0] - want[0]) < RTOL * abs(want[0]) and abs(got[1] - want[1]) < RTOL * abs(want[1])
+    assert abs(got[2] - want[2]) <= 1e-9 * abs(want[2])                      # wf = exp(exponent + phiR)
+    assert rel(got[3:], want[3:]) < 1e-12                                     # g(r) and the density profile
+    q, d = h.quotient_fixed(g["R"], g["moves"])
+    d_ref = g["move_exponent_new"] - float(g["exponent"])
+    assert np.max(np.abs(d - d_ref) / np.maximum(1.0, np.abs(d_ref))) < 1e-9
+    h.close()
+
+
+def test_hedrop_chain_estimators_and_com(capi, golden):
+    from oracle_lib import OracleHe
+
+    g = golden("hedrop_n6_fixture")
+    W, seed, mc_step = 8, 5, 0.5
+    n_samples, n_therm, n_init = 3, 30, 60
+    spec, h = make_handle(capi, g, n_walkers=W, seed=seed, mc_step=mc_step, max_samples=n_samples)
+    o = OracleHe(spec)
+    R0 = np.stack([g["R"] * (1.0 + 0.05 * w) for w in range(W)])
+    h.set_positions(R0)
+    h.sample_and_accumulate(n_samples, n_therm, n_init)
+    got = h.allreduce_and_fetch()
+    est = np.zeros(o.est_size())
+    acc, Rf = 0, []
+    for w in range(W):
+        r = o.sample_walker(R0[w], g["uR"], g["uI"], float(g["phiR"]), seed, w, 0, n_init, n_samples, n_therm, mc_step, est)
+        acc += r["accepted"]
+        Rf.append(r["R"])
+    want = o.unpack_est(est, W * n_samples)
+    assert got["n_acceptances"] == acc and got["n_trials"] == W * (n_init + n_samples * n_therm)
+    assert np.max(np.abs(h.get_positions() - np.stack(Rf))) < 1e-9          # open boundary: no wrapping, same chain
+    assert rel(got["O"], want["O"]) < 1e-9
+    assert abs(got["e_r"][0] - want["e_r"]) < 1e-9 * abs(want["e_r"])
+    assert rel(got["S"], want["S"]) < 1e-9 and rel(got["OER"], want["OER"]) < 1e-9
+    assert rel(got["other"], want["other"]) < 1e-9
+    # AlignCoordinates for USE_MOVE_COM_TO_ZERO systems (src/TDVMC.cpp:2569-2582): centre of mass to zero
+    Rb = h.get_positions()
+    h.wrap_positions()
+    Ra = h.get_positions()
+    assert np.max(np.abs(Ra.mean(axis=1))) < 1e-12
+    assert np.max(np.abs((Ra - Rb) + Rb.mean(axis=1, keepdims=True))) < 1e-12
+    h.close()

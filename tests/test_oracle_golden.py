@@ -109,27 +109,33 @@ def test_sampler_statistics_match_reference(golden):
     assert np.max(np.abs(est["O"] - O_ref)) / scale < 0.02
 
 
-HE_CASES = ["hebulk_n64_fixture", "hebulk_n64_equil"]
+HE_CASES = ["hebulk_n64_fixture", "hebulk_n64_equil", "hedrop_n6_fixture", "hedrop_n6_spread", "hedrop_n6_equil"]
 
 
 @pytest.mark.parametrize("name", HE_CASES)
-def test_hebulk_fixed_configuration_matches_reference(golden, name):
-    from oracle_lib import OracleHeBulk
+def test_he_family_fixed_configuration_matches_reference(golden, name):
+    from oracle_lib import OracleHe
 
     g = golden(name)
-    spec = systems.from_golden(g)
-    o = OracleHeBulk(spec)
-    r = o.evaluate(g["R"], g["uR"], g["uI"])
+    spec = systems.from_golden(g)           # also checks every boundary factor against the reference object, bit for bit
+    o = OracleHe(spec)
+    K = spec.n_splines
+    r = o.evaluate(g["R"], g["uR"], g["uI"], float(g["phiR"]))
     assert rel(r["ss"], g["spline_sums"]) < 1e-14
     assert abs(r["mcm"] - float(g["mcmillan_sum"])) <= 1e-14 * abs(float(g["mcmillan_sum"]))
-    assert rel(r["O"], g["local_operators"]) < 1e-14
+    if "const_sum" in g:
+        assert r["ext"][K + 1] == float(g["const_sum"])
+        assert abs(r["ext"][K + 2] - float(g["linear_sum"])) <= 1e-14 * abs(float(g["linear_sum"]))
+    assert rel(r["O"], g["local_operators"]) < 1e-13
     assert abs(r["exponent"] - float(g["exponent"])) < 1e-13 * abs(float(g["exponent"]))
-    assert abs(r["e_r"] - float(g["local_energy_r"])) < 1e-12 * abs(float(g["local_energy_r"]))
-    assert abs(r["e_i"] - float(g["local_energy_i"])) < 1e-12 * abs(float(g["local_energy_i"]))
+    assert abs(r["e_r"] - float(g["local_energy_r"])) < 1e-11 * abs(float(g["local_energy_r"]))
+    assert abs(r["e_i"] - float(g["local_energy_i"])) < 1e-11 * abs(float(g["local_energy_i"]))
     assert rel(r["other"], g["other_expectation_values"]) < 1e-12
     assert rel(r["drift_r"], g["drift_r"]) < RTOL and rel(r["drift_i"], g["drift_i"]) < RTOL
-    assert rel(r["sD"], g["sD"]) < 1e-14 and rel(r["sD2"], g["sD2"]) < 1e-14
-    assert rel(r["mcD"], g["mcmillan_sum_d"]) < 1e-14 and rel(r["mcD2"], g["mcmillan_sum_d2"]) < 1e-14
+    assert rel(r["tabD"][:K], g["sD"]) < 1e-14 and rel(r["tabD2"][:K], g["sD2"]) < 1e-14
+    assert rel(r["tabD"][K], g["mcmillan_sum_d"]) < 1e-14 and rel(r["tabD2"][K], g["mcmillan_sum_d2"]) < 1e-14
+    if "linear_sum_d" in g:
+        assert rel(r["tabD"][K + 2], g["linear_sum_d"]) < 1e-14 and rel(r["tabD2"][K + 2], g["linear_sum_d2"]) < 1e-14
     for m, q_ref, en_ref in zip(g["moves"], g["move_quotient"], g["move_exponent_new"]):
         q, en, _ = o.quotient(g["R"], int(m[0]), m[1:4], g["uR"])
         assert abs(en - en_ref) < 1e-12 * abs(en_ref)
@@ -137,11 +143,11 @@ def test_hebulk_fixed_configuration_matches_reference(golden, name):
 
 
 def test_hebulk_sampler_statistics_match_reference(golden):
-    from oracle_lib import OracleHeBulk
+    from oracle_lib import OracleHe
 
     g = golden("hebulk_n64_mc")
     spec = systems.he_bulk(int(g["N"]), float(g["LBOX"]), int(g["N_PARAM"]))
-    o = OracleHeBulk(spec)
+    o = OracleHe(spec)
     n_samples = 1200
     r = o.sample_walker(g["R0"], g["uR"], g["uI"], 0.0, seed=3, walker=0, step0=0, n_init=64 * 300, n_samples=n_samples,
                         n_therm=int(g["n_therm"]), mc_step=float(g["MC_STEP"]))
