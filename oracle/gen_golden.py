@@ -417,6 +417,68 @@ def gen_hedrop():
     # the chain is not stationary; sampling is pinned by replaying the oracle chain move for move instead
 
 
+def pack_eval_mixture(name, scal, arrays, moves):
+    with tempfile.TemporaryDirectory() as td:
+        cp, op = os.path.join(td, "case.txt"), os.path.join(td, "out.txt")
+        write_case(cp, "BosonMixtureCluster", scal, arrays, moves)
+        run("eval", cp, op)
+        d = parse_dump(op)
+    out = {"system": np.array("BosonMixtureCluster"), "N": np.array(scal["N"]), "DIM": np.array(3), "LBOX": np.array(scal["LBOX"]),
+           "N_PARAM": np.array(scal["N_PARAM"]), "SYSTEM_PARAMS": np.zeros(0), "time": np.array(0.0),
+           "PARTICLE_TYPES": np.asarray(arrays["PARTICLE_TYPES"], np.float64), "NURBS_GRID": np.asarray(arrays["NURBS_GRID"]),
+           "R": np.asarray(arrays["R"], np.float64).reshape(-1, 3), "uR": np.asarray(arrays["uR"], np.float64),
+           "uI": np.asarray(arrays["uI"], np.float64), "phiR": np.array(scal.get("phiR", 0.0)),
+           "phiI": np.array(scal.get("phiI", 0.0)), "moves": np.asarray(moves, np.float64).reshape(-1, 4)}
+    for k, v in d.items():
+        out[k] = v
+    T = int(d["n_pair_types"])
+    spec = tsys.boson_mixture_cluster(arrays["PARTICLE_TYPES"], [d[f"knots_{t}"] for t in range(T)],
+                                      [d[f"spline_weights_{t}"] for t in range(T)], [d[f"bc_factors_{t}"] for t in range(T)])
+    N = int(scal["N"])
+    K = 26
+    tabs = []
+    for t in range(T):
+        z = np.zeros((1, N, 3), np.longdouble)
+        tabs += [d[f"sD_{t}"].astype(np.longdouble), d[f"mcmillan_sum_d_{t}"].astype(np.longdouble)[None], z,
+                 d[f"linear_sum_d_{t}"].astype(np.longdouble)[None], d[f"log_sum_d_{t}"].astype(np.longdouble)[None]]
+    tab = np.concatenate(tabs)
+    for key, u in (("drift_r", out["uR"]), ("drift_i", out["uI"])):
+        F = np.zeros((N, 3), np.longdouble)
+        for p, row in enumerate(spec.map_rows()):
+            tt = np.zeros((N, 3), np.longdouble)
+            for k, f in row:
+                tt = tt + np.longdouble(f) * tab[k]
+            F = F + np.longdouble(u[p]) * tt
+        out[key] = F.astype(np.float64)
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(f"{name}: E_R={float(d['local_energy_r']):.12g} E_I={float(d['local_energy_i']):.12g} "
+          f"exponent={float(d['exponent']):.12g} q={d['move_quotient']}")
+    return d
+
+
+def gen_mixture():
+    """config/He4He4Na.config: two He-4 atoms and one Na, N_PARAM = 52 = 2 x 26, the config's own parameters."""
+    rng = np.random.default_rng(3)
+    cfg = json.load(open(os.path.join(REF, "config", "He4He4Na.config")))
+    N, P = int(cfg["N"]), int(cfg["N_PARAM"])
+    uR = np.array(cfg["PARAMS_REAL"], dtype=np.float64)
+    uI = 0.01 * np.sin(0.4 * np.arange(P))
+    R = read_csv_positions("particleconfiguration_3.csv").reshape(N, 3)      # the reference's 3-particle fixture
+    scal = dict(N=N, LBOX=float(cfg["LBOX"]), N_PARAM=P, phiR=float(cfg["PARAM_PHIR"]), phiI=0.0, USE_NURBS=1,
+                GR_BIN_COUNT=int(cfg["GR_BIN_COUNT"]))
+    arr = dict(R=R, uR=uR, uI=uI, NURBS_GRID=cfg["NURBS_GRID"], PARTICLE_TYPES=cfg["PARTICLE_TYPES"],
+               SYSTEM_PARAMS=cfg["SYSTEM_PARAMS"])
+    pack_eval_mixture("mixture_he4he4na_fixture", scal, arr, default_moves(R, 0.0, rng, sigma=1.0))
+    # compact and stretched triangles: McMillan cores (r < 2.0 / 4.0) and the tails (r >= 15.8 / 17.8)
+    R2 = np.array([[0.0, 0.0, 0.0], [1.7, 0.3, -0.2], [3.1, 2.0, 0.5]])
+    pack_eval_mixture("mixture_he4he4na_compact", scal, dict(arr, R=R2), default_moves(R2, 0.0, rng, sigma=1.0))
+    R3 = np.array([[0.0, 0.0, 0.0], [16.5, 1.0, -2.0], [-9.0, 17.0, 4.0]])
+    pack_eval_mixture("mixture_he4he4na_stretched", scal, dict(arr, R=R3), default_moves(R3, 0.0, rng, sigma=4.0))
+    mc = run_mc("BosonMixtureCluster", dict(scal, MC_STEP=float(cfg["MC_STEP"]), MC_NSTEPS=1, MC_NTHERMSTEPS=3 * 3000, seed=2), arr)
+    R4 = mc["R_final"].reshape(N, 3)
+    pack_eval_mixture("mixture_he4he4na_equil", scal, dict(arr, R=R4), default_moves(R4, 0.0, rng, sigma=2.0))
+
+
 def gen_min_image():
     """Reference minimum-image displacement on edge cases + random inputs (Utils.cpp:266-281, 352-382)."""
     rng = np.random.default_rng(99)
@@ -447,7 +509,7 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     if not os.path.exists(HARNESS):
         sys.exit("build the oracle first: make -C oracle/ref_build")
-    which = sys.argv[1:] or ["min_image", "bosonsbulk", "bosonsbulk_mc", "nubosonsbulkpb", "hebulk", "hedrop"]
+    which = sys.argv[1:] or ["min_image", "bosonsbulk", "bosonsbulk_mc", "nubosonsbulkpb", "hebulk", "hedrop", "mixture"]
     for w in which:
         globals()["gen_" + w]()
 

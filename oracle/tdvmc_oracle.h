@@ -150,3 +150,58 @@ int64_t oracle_he_sample_walker(const oracle_he* s, double* R, const double* uR,
 }
 #endif
 #endif
+
+/* ------------------------------------------------------------------------------------------------
+ * BosonMixtureCluster (src/PhysicalSystems/BosonMixtureCluster.cpp): open-boundary cluster of several
+ * species.  One basis set per pair type: McMillan core r^m below nodes[3], monomial-table cubic B-splines
+ * (SplineFactory::GetWeights3) on a non-uniform knot vector, constant + linear tails beyond
+ * nodes[#nodes-4], and a log term for every pair; per-species hbar^2/2m; pair potentials through
+ * IPairPotential (HFDB_He_He, KTTY_He_Na, KTTY_He_Cs).
+ * Extended sums per pair type t: ext[t*EXT + j], EXT = K + 4: [ss_0..ss_{K-1} | mcMillan | const | linear | log].
+ * ------------------------------------------------------------------------------------------------ */
+#ifndef TDVMC_ORACLE_MIX_H
+#define TDVMC_ORACLE_MIX_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { ORACLE_POT_HFDB_HE_HE = 0, ORACLE_POT_KTTY_HE_NA = 1, ORACLE_POT_KTTY_HE_CS = 2 };
+
+typedef struct oracle_mix
+{
+    int32_t n_particles, n_params, n_types, n_splines; /* n_splines per pair type (26) */
+    int32_t n_other, pad;
+    const int32_t* pair_type;   /* [N][N] correlationTypes */
+    const double* hbar;         /* [N] hbarOver2m of each particle's species (BosonMixtureCluster.cpp:113-134) */
+    const double* mass;         /* [N] */
+    const double* knots;        /* [T][K+4] */
+    const double* weights;      /* [T][K][4][4] */
+    const double* mcm;          /* [T] mcMillanFactor */
+    const int32_t* potential;   /* [T] ORACLE_POT_* */
+    const int32_t* map_ptr;     /* [P+1] rows over the T*(K+4) extended sums (BosonMixtureCluster.cpp:636-645) */
+    const int32_t* map_col;
+    const double* map_val;
+} oracle_mix;
+
+double oracle_pair_potential(int id, double r); /* HFDB.cpp:23-47, KTTY.cpp:42-87 */
+void oracle_mix_values(const oracle_mix* s, const double* R, double* ext);
+void oracle_mix_operators(const oracle_mix* s, const double* ext, double* O);
+double oracle_mix_exponent(const oracle_mix* s, const double* ext, const double* uR);
+/* CalculateExpectationValues (BosonMixtureCluster.cpp:375-673).  other: [n_other] (first six set);
+ * tabD [T*EXT][N][3], tabD2 [T*EXT][N] outputs/scratch. */
+void oracle_mix_expectation(const oracle_mix* s, const double* R, double wf, double exponent, const double* uR, const double* uI,
+                            double* e_r, double* e_i, double* other, double* drift_r, double* drift_i, double* tabD, double* tabD2);
+double oracle_mix_quotient(const oracle_mix* s, const double* R, int particle, const double* old_pos, const double* ext,
+                           double exponent, const double* uR, double* ext_new, double* exponent_new);
+int64_t oracle_mix_sweep(const oracle_mix* s, double* R, double* ext, double* exponent, const double* uR, uint64_t seed,
+                         uint32_t walker, uint64_t first_step, int64_t n_steps, double mc_step);
+int64_t oracle_mix_sample_walker(const oracle_mix* s, double* R, const double* uR, const double* uI, double phiR, uint64_t seed,
+                                 uint32_t walker, uint64_t* step_counter, int n_init, int n_samples, int n_therm,
+                                 double mc_step, double* est, double* sample_rows);
+/* mass-weighted centre of mass (BosonMixtureCluster.cpp:348-368) */
+void oracle_mix_center_of_mass(const oracle_mix* s, const double* R, double* com);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -21,6 +21,12 @@ PAIR_RULE_REFLECT = 1  # r -> 2 r_max - r beyond r_max, then r < r_max (NUBosons
 KIND_SPLINE_TABLE = 0   # BosonsBulk, NUBosonsBulkPB: monomial spline table + boundary map
 KIND_HE_BULK = 1        # HeBulk: McMillan core + uniform B-splines in the local coordinate + Aziz potential
 KIND_HE_DROP = 2        # HeDrop: open boundary, McMillan core, two uniform grids, const + linear tails, LJ potential
+KIND_MIXTURE = 3        # BosonMixtureCluster: species, per-pair-type spline tables + McMillan/const/linear/log, pair potentials
+
+POT_HFDB_HE_HE, POT_KTTY_HE_NA, POT_KTTY_HE_CS = 0, 1, 2
+# BosonMixtureCluster.h:28-36
+SPECIES = {"He3": 0, "He4": 1, "Na": 2, "Li": 3, "Cs": 4}
+SPECIES_MASS = {0: 3.0160293191, 1: 4.00260325415, 2: 22.9897692809, 4: 132.905451932}   # BosonMixtureCluster.cpp:108-135
 
 HBAR2_2M = 1.0  # src/Constants.h:12
 
@@ -204,6 +210,59 @@ def he_drop(n_particles, n_params):
                                  mcm=m, gr_bins=200, rho_bins=200, gr_max=2.0 * rt, periodic=0, potential=1, use_phi=1))
 
 
+def species_hbar_over_2m(mass):
+    """hbar^2 / (2 m u) / (A^2 k_B) with the constants of src/Constants.h:26-33 (BosonMixtureCluster.cpp:113)."""
+    hbar, u, A2m, kb = 1.054571628e-34, 1.660538782e-27, 1e-10, 1.3806504e-23
+    return hbar ** 2.0 / (2.0 * mass * u) / (A2m ** 2.0 * kb)
+
+
+def boson_mixture_cluster(particle_types, type_knots, type_weights, type_bc, n_other=403, type_mcm=None):
+    """``BosonMixtureCluster`` (BosonMixtureCluster.cpp:58-346).  ``particle_types``: the config's PARTICLE_TYPES
+    (enum values).  Species and pair types are numbered in order of first appearance (:58-102).  Per pair type the
+    caller passes the reference's knots (30), spline table (26x4x4) and boundary factors bcFactors (5x2)
+    (SetBoundaryConditions1_MM_1 / 1_EXP_2).  Parameters: 26 per pair type (:543); extended sums per type:
+    ``[ss_0..ss_25 | mcMillan | const | linear | log]``; map of :636-645."""
+    pt = [int(x) for x in particle_types]
+    N = len(pt)
+    pair_index, pair_type = {}, np.zeros((N, N), dtype=np.int32)
+    for i in range(N):
+        for j in range(i):
+            key = frozenset((pt[i], pt[j])) if pt[i] != pt[j] else (pt[i],)
+            if key not in pair_index:
+                pair_index[key] = len(pair_index)
+            pair_type[i, j] = pair_type[j, i] = pair_index[key]
+    T = len(pair_index)
+    K = 26
+    EXT = K + 4
+    MC, CO, LI, LG = K, K + 1, K + 2, K + 3
+    rows = []
+    for t in range(T):
+        bc = np.asarray(type_bc[t], dtype=np.float64)
+        b = t * EXT
+        rows.append([(b + MC, 1.0), (b + 0, bc[0][0]), (b + 1, bc[0][1])])
+        rows.append([(b + 2, 1.0), (b + 0, bc[1][0]), (b + 1, bc[1][1])])
+        rows += [[(b + i + 1, 1.0)] for i in range(2, 22)]
+        rows.append([(b + K - 3, 1.0), (b + K - 2, bc[2][0]), (b + K - 1, bc[2][1])])
+        rows.append([(b + CO, 1.0), (b + K - 2, bc[3][0]), (b + K - 1, bc[3][1])])
+        rows.append([(b + LI, 1.0), (b + K - 2, bc[4][0]), (b + K - 1, bc[4][1])])
+        rows.append([(b + LG, 1.0)])
+    ptr, col, val = _csr(rows)
+    pots = []
+    for key, t in sorted(pair_index.items(), key=lambda kv: kv[1]):
+        sp = set(key)
+        pots.append(POT_KTTY_HE_CS if 4 in sp else (POT_KTTY_HE_NA if 2 in sp else POT_HFDB_HE_HE))   # :233-282
+    mass = np.array([SPECIES_MASS[x] for x in pt])
+    hbar = np.array([species_hbar_over_2m(m) for m in mass])
+    knots = np.ascontiguousarray(type_knots, np.float64).reshape(T, K + 4)
+    weights = np.ascontiguousarray(type_weights, np.float64).reshape(T, K, 4, 4)
+    mcm = np.full(T, -4.7) if type_mcm is None else np.asarray(type_mcm, np.float64)
+    return SystemSpec("BosonMixtureCluster", N, 26 * T, 0.0, knots[0], weights[0], ptr, col, val, PAIR_RULE_CUT, np.zeros(0),
+                      n_other=n_other, tail_param=-1, kind=KIND_MIXTURE, n_ext=T * EXT,
+                      extra=dict(n_splines=K, n_types=T, pair_type=pair_type, type_knots=knots, type_weights=weights,
+                                 type_mcm=mcm, type_potential=np.array(pots, dtype=np.int32), hbar=hbar, mass=mass,
+                                 r_max=float("inf")))
+
+
 def from_golden(g):
     """Build the spec of a tests/golden fixture, taking knots and spline table from the reference dump."""
     name = str(g["system"])
@@ -212,6 +271,18 @@ def from_golden(g):
         spec = he_bulk(N, L, P)
         if spec.extra["h"] != float(g["node_point_spacing"]) or not np.array_equal(spec.extra["factors"], g["bc_factors"]):
             raise AssertionError("HeBulk set-up differs from the reference dump")
+        return spec
+    if name == "BosonMixtureCluster":
+        T = int(g["n_pair_types"])
+        spec = boson_mixture_cluster(g["PARTICLE_TYPES"], [g[f"knots_{t}"] for t in range(T)],
+                                     [g[f"spline_weights_{t}"] for t in range(T)], [g[f"bc_factors_{t}"] for t in range(T)],
+                                     n_other=len(g["other_expectation_values"]), type_mcm=[g[f"extras_{t}"][6] for t in range(T)])
+        if not np.array_equal(spec.extra["pair_type"].ravel(), g["correlation_types"].astype(np.int32)):
+            raise AssertionError("pair-type numbering differs from the reference dump")
+        ref_hb = g["type_hbar_over_2m"][g["particle_types"].astype(int)]
+        if not np.allclose(spec.extra["hbar"], ref_hb, rtol=1e-15, atol=0):
+            raise AssertionError("hbar^2/2m differs from the reference dump")
+        spec.extra["hbar"] = ref_hb
         return spec
     if name == "HeDrop":
         spec = he_drop(N, P)

@@ -28,6 +28,12 @@ class OracleHeStruct(C.Structure):
                 ("map_val", dp), ("map_const", dp), ("grad_const", dp)]
 
 
+class OracleMixStruct(C.Structure):
+    _fields_ = [("n_particles", C.c_int32), ("n_params", C.c_int32), ("n_types", C.c_int32), ("n_splines", C.c_int32),
+                ("n_other", C.c_int32), ("pad", C.c_int32), ("pair_type", ip), ("hbar", dp), ("mass", dp), ("knots", dp),
+                ("weights", dp), ("mcm", dp), ("potential", ip), ("map_ptr", ip), ("map_col", ip), ("map_val", dp)]
+
+
 def lib():
     global _LIB
     if _LIB is None:
@@ -40,6 +46,11 @@ def lib():
         L.oracle_wf_quotient.restype = C.c_double
         L.oracle_sweep.restype = C.c_int64
         L.oracle_sample_walker.restype = C.c_int64
+        L.oracle_mix_exponent.restype = C.c_double
+        L.oracle_mix_quotient.restype = C.c_double
+        L.oracle_mix_sweep.restype = C.c_int64
+        L.oracle_mix_sample_walker.restype = C.c_int64
+        L.oracle_pair_potential.restype = C.c_double
         L.oracle_he_exponent.restype = C.c_double
         L.oracle_he_quotient.restype = C.c_double
         L.oracle_he_sweep.restype = C.c_int64
@@ -262,10 +273,96 @@ class OracleHe:
         return Oracle.unpack_est(self, est, n)
 
 
+class OracleMix:
+    """BosonMixtureCluster restatement (oracle/tdvmc_oracle_mix.c) with numpy in/out."""
+
+    def __init__(self, spec, time=0.0):
+        self.spec = spec
+        e = spec.extra
+        self._keep = [np.ascontiguousarray(e["pair_type"], np.int32), np.ascontiguousarray(e["hbar"], np.float64),
+                      np.ascontiguousarray(e["mass"], np.float64), np.ascontiguousarray(e["type_knots"], np.float64),
+                      np.ascontiguousarray(e["type_weights"], np.float64), np.ascontiguousarray(e["type_mcm"], np.float64),
+                      np.ascontiguousarray(e["type_potential"], np.int32), np.ascontiguousarray(spec.map_ptr, np.int32),
+                      np.ascontiguousarray(spec.map_col, np.int32), np.ascontiguousarray(spec.map_val, np.float64)]
+        k = self._keep
+        I = lambda a: a.ctypes.data_as(ip)
+        self.sys = OracleMixStruct(spec.n_particles, spec.n_params, e["n_types"], e["n_splines"], spec.n_other, 0, I(k[0]),
+                                   _d(k[1]), _d(k[2]), _d(k[3]), _d(k[4]), _d(k[5]), I(k[6]), I(k[7]), I(k[8]), _d(k[9]))
+        self.N, self.P, self.K, self.T = spec.n_particles, spec.n_params, e["n_splines"], e["n_types"]
+        self.NE, self.NO = self.T * (self.K + 4), spec.n_other
+
+    def values(self, R):
+        R = np.ascontiguousarray(R, np.float64)
+        ext = np.zeros(self.NE)
+        lib().oracle_mix_values(C.byref(self.sys), _d(R), _d(ext))
+        return ext
+
+    def operators(self, ext):
+        O = np.zeros(self.P)
+        lib().oracle_mix_operators(C.byref(self.sys), _d(np.ascontiguousarray(ext)), _d(O))
+        return O
+
+    def exponent(self, ext, uR):
+        return lib().oracle_mix_exponent(C.byref(self.sys), _d(np.ascontiguousarray(ext)), _d(np.ascontiguousarray(uR, np.float64)))
+
+    def evaluate(self, R, uR, uI, phiR=0.0):
+        R = np.ascontiguousarray(R, np.float64)
+        uR = np.ascontiguousarray(uR, np.float64)
+        uI = np.ascontiguousarray(uI, np.float64)
+        ext = self.values(R)
+        ex = self.exponent(ext, uR)
+        er, ei = C.c_double(0), C.c_double(0)
+        other = np.zeros(self.NO)
+        dr, di = np.zeros((self.N, 3)), np.zeros((self.N, 3))
+        tD, tD2 = np.zeros((self.NE, self.N, 3)), np.zeros((self.NE, self.N))
+        lib().oracle_mix_expectation(C.byref(self.sys), _d(R), C.c_double(np.exp(ex + phiR)), C.c_double(ex), _d(uR), _d(uI),
+                                     C.byref(er), C.byref(ei), _d(other), _d(dr), _d(di), _d(tD), _d(tD2))
+        return dict(ext=ext, O=self.operators(ext), exponent=ex, e_r=er.value, e_i=ei.value, other=other, drift_r=dr,
+                    drift_i=di, tabD=tD, tabD2=tD2)
+
+    def quotient(self, R, particle, new_pos, uR):
+        R = np.array(R, np.float64)
+        uR = np.ascontiguousarray(uR, np.float64)
+        ext = self.values(R)
+        ex = self.exponent(ext, uR)
+        old = R[particle].copy()
+        R[particle] = new_pos
+        ext_new = np.zeros(self.NE)
+        en = C.c_double(0)
+        q = lib().oracle_mix_quotient(C.byref(self.sys), _d(R), int(particle), _d(old), _d(ext), C.c_double(ex), _d(uR),
+                                      _d(ext_new), C.byref(en))
+        return q, en.value, ex
+
+    def est_size(self):
+        return self.P * self.P + 3 * self.P + 2 + self.NO
+
+    def sample_walker(self, R, uR, uI, phiR, seed, walker, step0, n_init, n_samples, n_therm, mc_step, est=None):
+        R = np.array(R, np.float64)
+        if est is None:
+            est = np.zeros(self.est_size())
+        rows = np.zeros((n_samples, self.P + 2))
+        sc = C.c_uint64(step0)
+        acc = lib().oracle_mix_sample_walker(C.byref(self.sys), _d(R), _d(np.ascontiguousarray(uR, np.float64)),
+                                             _d(np.ascontiguousarray(uI, np.float64)), C.c_double(phiR), C.c_uint64(seed),
+                                             C.c_uint32(walker), C.byref(sc), n_init, n_samples, n_therm, C.c_double(mc_step),
+                                             _d(est), _d(rows))
+        return dict(R=R, est=est, rows=rows, accepted=int(acc), steps=sc.value)
+
+    def unpack_est(self, est, n):
+        return Oracle.unpack_est(self, est, n)
+
+    def center_of_mass(self, R):
+        com = np.zeros(3)
+        lib().oracle_mix_center_of_mass(C.byref(self.sys), _d(np.ascontiguousarray(R, np.float64)), _d(com))
+        return com
+
+
 OracleHeBulk = OracleHe
 
 
 def make_oracle(spec, time=0.0):
     from tdvmc_b200 import systems
 
+    if spec.kind == systems.KIND_MIXTURE:
+        return OracleMix(spec, time)
     return Oracle(spec, time) if spec.kind == systems.KIND_SPLINE_TABLE else OracleHe(spec, time)

@@ -161,3 +161,37 @@ def test_hebulk_sampler_statistics_match_reference(golden):
     m2, s2 = blocked(g["energy_r_series"])
     assert abs(m1 - m2) < 4.0 * np.hypot(s1, s2), (m1, s1, m2, s2)
     assert abs(r["accepted"] / r["steps"] - float(g["acceptance"])) < 0.015
+
+
+MIX_CASES = ["mixture_he4he4na_fixture", "mixture_he4he4na_compact", "mixture_he4he4na_stretched", "mixture_he4he4na_equil"]
+
+
+@pytest.mark.parametrize("name", MIX_CASES)
+def test_mixture_fixed_configuration_matches_reference(golden, name):
+    from oracle_lib import OracleMix
+
+    g = golden(name)
+    spec = systems.from_golden(g)     # checks the pair-type numbering and hbar^2/2m against the reference object
+    o = OracleMix(spec)
+    K, T = 26, int(g["n_pair_types"])
+    r = o.evaluate(g["R"], g["uR"], g["uI"], float(g["phiR"]))
+    for t in range(T):
+        e = r["ext"][t * (K + 4):(t + 1) * (K + 4)]
+        x = g[f"extras_{t}"]
+        assert rel(e[:K], g[f"spline_sums_{t}"]) < 1e-14 or np.all(g[f"spline_sums_{t}"] == 0)
+        for got, want in ((e[K], x[0]), (e[K + 1], x[1]), (e[K + 2], x[2]), (e[K + 3], x[3])):
+            assert abs(got - want) <= 1e-14 * max(abs(want), 1e-300)
+        b = t * (K + 4)
+        assert rel(r["tabD"][b:b + K], g[f"sD_{t}"]) < 1e-14 or np.all(g[f"sD_{t}"] == 0)
+        assert rel(r["tabD"][b + K + 3], g[f"log_sum_d_{t}"]) < 1e-14
+        assert rel(r["tabD2"][b + K + 3], g[f"log_sum_d2_{t}"]) < 1e-14
+    assert rel(r["O"], g["local_operators"]) < 1e-13
+    assert abs(r["exponent"] - float(g["exponent"])) < 1e-13 * abs(float(g["exponent"]))
+    assert abs(r["e_r"] - float(g["local_energy_r"])) < 1e-11 * abs(float(g["local_energy_r"]))
+    assert abs(r["e_i"] - float(g["local_energy_i"])) < 1e-11 * abs(float(g["local_energy_i"]))
+    assert rel(r["other"], g["other_expectation_values"]) < 1e-12
+    assert rel(r["drift_r"], g["drift_r"]) < RTOL and rel(r["drift_i"], g["drift_i"]) < RTOL
+    for m, q_ref, en_ref in zip(g["moves"], g["move_quotient"], g["move_exponent_new"]):
+        q, en, _ = o.quotient(g["R"], int(m[0]), m[1:4], g["uR"])
+        assert abs(en - en_ref) < 1e-12 * abs(en_ref)
+        assert abs(q - q_ref) <= 1e-9 * abs(q_ref)
