@@ -43,7 +43,26 @@ enum tdvmc_system_kind
                                       then spacing 0.5 up to rijTail, constant + linear tails beyond, Lennard-Jones inline,
                                       g(r) and the density profile in other[3..402]; lbox unused; wrap_positions moves the
                                       centre of mass to zero (src/TDVMC.cpp:798-809) */
+    ,
+    TDVMC_SYSTEM_MIXTURE = 3       /* BosonMixtureCluster (BosonMixtureCluster.cpp): open boundary, several species; one basis
+                                      per pair type (see tdvmc_mixture_desc), 26 parameters per pair type, other[0..5] =
+                                      {kinR part 1, part 2, kinR, V, wf, exponent}; wrap_positions moves the mass-weighted
+                                      centre of mass to zero */
 };
+
+/* Per-pair-type data of BosonMixtureCluster::InitSystem (BosonMixtureCluster.cpp:104-346), as data. */
+typedef struct tdvmc_mixture_desc
+{
+    int32_t n_pair_types;          /* T = corrFuncData.size() */
+    int32_t reserved;
+    const int32_t* pair_type;      /* [N][N] correlationTypes (:58-102) */
+    const double* hbar_over_2m;    /* [N] pp.hbarOver2m of each particle's species (:108-135) */
+    const double* mass;            /* [N] pp.mass */
+    const double* knots;           /* [T][K+4] cfd.nodes */
+    const double* spline_weights;  /* [T][K][4][4] cfd.splineWeights (SplineFactory::GetWeights3) */
+    const double* mcmillan_factor; /* [T] cfd.mcMillanFactor */
+    const int32_t* potential;      /* [T] 0 HFDB_He_He, 1 KTTY_He_Na, 2 KTTY_He_Cs (:233-282, src/Potentials) */
+} tdvmc_mixture_desc;
 
 enum tdvmc_pair_rule
 {
@@ -79,6 +98,7 @@ typedef struct tdvmc_system_desc
     const double* map_const;   /* [N_PARAM] constant part of O_p (HeBulk.cpp:383: 1.0 + ...), NULL = zeros */
     const double* grad_const;  /* [N_PARAM] constant added to every gradient component of parameter p
                                   (the literal 1 of HeBulk.cpp:351), NULL = zeros */
+    const tdvmc_mixture_desc* mixture; /* TDVMC_SYSTEM_MIXTURE only, else NULL; n_ext = T * (K + 4) */
 } tdvmc_system_desc;
 
 /* The walker ensemble owned by this rank.  The reference runs one walker per MPI rank, seeded

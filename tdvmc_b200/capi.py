@@ -18,13 +18,18 @@ dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int32)
 
 
+class MixtureDesc(C.Structure):
+    _fields_ = [("n_pair_types", C.c_int32), ("reserved", C.c_int32), ("pair_type", ip), ("hbar_over_2m", dp), ("mass", dp),
+                ("knots", dp), ("spline_weights", dp), ("mcmillan_factor", dp), ("potential", ip)]
+
+
 class SystemDesc(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("n_particles", C.c_int32), ("dim", C.c_int32), ("n_params", C.c_int32),
                 ("n_splines", C.c_int32), ("pair_rule", C.c_int32), ("tail_param", C.c_int32), ("n_other", C.c_int32),
                 ("lbox", C.c_double), ("hbar2_2m", C.c_double), ("knots", dp), ("spline_weights", dp), ("map_ptr", ip),
                 ("map_col", ip), ("map_val", dp), ("system_params", dp), ("n_system_params", C.c_int32),
                 ("system_kind", C.c_int32), ("n_ext", C.c_int32), ("reserved", C.c_int32), ("map_const", dp),
-                ("grad_const", dp)]
+                ("grad_const", dp), ("mixture", C.POINTER(MixtureDesc))]
 
 
 class EnsembleDesc(C.Structure):
@@ -121,10 +126,20 @@ class Handle:
                           sp=np.ascontiguousarray(spec.system_params, np.float64),
                           mk=np.ascontiguousarray(spec.map_const, np.float64), gk=np.ascontiguousarray(spec.grad_const, np.float64))
         k = self._keep
+        mix = None
+        if spec.kind == 3:
+            e = spec.extra
+            k.update(pt=np.ascontiguousarray(e["pair_type"], np.int32), hb=np.ascontiguousarray(e["hbar"], np.float64),
+                     ms=np.ascontiguousarray(e["mass"], np.float64), tk=np.ascontiguousarray(e["type_knots"], np.float64),
+                     tw=np.ascontiguousarray(e["type_weights"], np.float64), tm=np.ascontiguousarray(e["type_mcm"], np.float64),
+                     tp=np.ascontiguousarray(e["type_potential"], np.int32))
+            self._mix = MixtureDesc(e["n_types"], 0, k["pt"].ctypes.data_as(ip), _d(k["hb"]), _d(k["ms"]), _d(k["tk"]),
+                                    _d(k["tw"]), _d(k["tm"]), k["tp"].ctypes.data_as(ip))
+            mix = C.pointer(self._mix)
         sd = SystemDesc(C.sizeof(SystemDesc), spec.n_particles, spec.dim, spec.n_params, spec.n_splines, spec.pair_rule,
                         spec.tail_param, spec.n_other, spec.lbox, spec.hbar2_2m, _d(k["knots"]), _d(k["w"]),
                         k["mp"].ctypes.data_as(ip), k["mc"].ctypes.data_as(ip), _d(k["mv"]), _d(k["sp"]), len(k["sp"]),
-                        spec.kind, spec.n_ext, 0, _d(k["mk"]), _d(k["gk"]))
+                        spec.kind, spec.n_ext, 0, _d(k["mk"]), _d(k["gk"]), mix)
         ed = EnsembleDesc(C.sizeof(EnsembleDesc), device, self.W, first_walker, max_samples, int(keep_sample_positions),
                           seed, mc_step)
         h = _VP()

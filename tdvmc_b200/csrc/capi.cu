@@ -109,6 +109,12 @@ struct tdvmc_gpu_handle
     int N = 0, Np = 0, P = 0, K = 0, pair_rule = 0, tail_param = 0, n_other = 9, kind = 0, n_ext = 0, gr_bins = 0;
     double he_rs = 0, core_m = 0, he_hl = 0, r_split2 = 1e300, r_tail = 1e300, gr_max = 0, u_core = 0, u_const = 0, u_lin = 0;
     int n_short = 0, potential = 0, rho_bins = 0, use_phi = 0, periodic = 1;
+    // BosonMixtureCluster
+    int n_types = 0;
+    std::vector<int> mix_pair_type, mix_pot;
+    std::vector<double> mix_hbar, mix_mass, mix_knots, mix_weights, mix_mcm;
+    DevBuf<int> d_mix_pair_type, d_mix_pot;
+    DevBuf<double> d_mix_hbar, d_mix_mass, d_mix_knots, d_mix_weights, d_mix_mcm, d_mix_cub;
     std::vector<double> map_const, grad_const;
     double L = 0, hbar = 1.0;
     std::vector<double> knots, weights, map_val, sys_params, uR, uI;
@@ -256,6 +262,29 @@ void potential_ab(const tdvmc_gpu_handle* h, double& a, double& b)
 int build_static_tables(tdvmc_gpu_handle* h)
 {
     const int K = h->K;
+    if (h->kind == TDVMC_SYSTEM_MIXTURE)
+    {
+        h->periodic = 0;
+        h->use_phi = 1;
+        h->first_bin = 3;
+        h->nbins = K - 3;
+        h->uniform = 0;
+        h->ncell = 1;
+        h->h = 1.0;
+        CK(upload(h->d_mix_pair_type, h->mix_pair_type, h->stream));
+        CK(upload(h->d_mix_pot, h->mix_pot, h->stream));
+        CK(upload(h->d_mix_hbar, h->mix_hbar, h->stream));
+        CK(upload(h->d_mix_mass, h->mix_mass, h->stream));
+        CK(upload(h->d_mix_knots, h->mix_knots, h->stream));
+        CK(upload(h->d_mix_weights, h->mix_weights, h->stream));
+        CK(upload(h->d_mix_mcm, h->mix_mcm, h->stream));
+        CK(upload(h->d_map_ptr, h->map_ptr, h->stream));
+        CK(upload(h->d_map_col, h->map_col, h->stream));
+        CK(upload(h->d_map_val, h->map_val, h->stream));
+        CK(upload(h->d_map_const, h->map_const, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
     if (h->kind == TDVMC_SYSTEM_HE_BULK || h->kind == TDVMC_SYSTEM_HE_DROP)
     {
         std::vector<unsigned short> lut(1, 0);
@@ -378,6 +407,35 @@ int build_param_tables(tdvmc_gpu_handle* h)
             utI[h->map_col[j]] += h->uI[p] * h->map_val[j];
         }
     // u(r) on interval b in the local coordinate s = r - t_b, expanded exactly (long double) from the
+    if (h->kind == TDVMC_SYSTEM_MIXTURE)
+    {
+        // per pair type and knot interval: u(r) = sum_p u~[t][b-p] piece_p(b-p)(r) re-expanded around the left knot
+        const int nk = K + 4, EXT = K + 4, nb = K - 3;
+        std::vector<double> mc((size_t)h->n_types * nb * 6, 0.0);
+        for (int t = 0; t < h->n_types; t++)
+            for (int b = 3; b < K; b++)
+            {
+                long double C[4] = { 0, 0, 0, 0 };
+                for (int p = 0; p < 4; p++)
+                    for (int c = 0; c < 4; c++)
+                        C[c] += (long double)utR[t * EXT + b - p] * (long double)h->mix_weights[(((size_t)t * K + (b - p)) * 4 + p) * 4 + c];
+                const long double t0 = h->mix_knots[(size_t)t * nk + b];
+                double* q = &mc[((size_t)t * nb + (b - 3)) * 6];
+                q[0] = (double)(C[0] + t0 * (C[1] + t0 * (C[2] + t0 * C[3])));
+                q[1] = (double)(C[1] + t0 * (2 * C[2] + 3 * t0 * C[3]));
+                q[2] = (double)(C[2] + 3 * t0 * C[3]);
+                q[3] = (double)C[3];
+                q[4] = h->mix_knots[(size_t)t * nk + b];
+                q[5] = h->mix_knots[(size_t)t * nk + b + 1];
+            }
+        CK(upload(h->d_uR, h->uR, h->stream));
+        CK(upload(h->d_uI, h->uI, h->stream));
+        CK(upload(h->d_utR, utR, h->stream));
+        CK(upload(h->d_utI, utI, h->stream));
+        CK(upload(h->d_mix_cub, mc, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
     // caller's monomial table: u(r) = sum_p u~[b-p] * piece_p(b-p)(r)
     // planes: [c0,c1] | [c2,c3] | [t_lo,t_hi], nbins + 1 records each; record nbins is the constant tail
     // uR[tail_param] every pair beyond r_max contributes (BosonsBulk.cpp:532-534)
@@ -458,7 +516,10 @@ SysDev tdvmc_gpu_handle::sysdev() const
     s.L = L; s.Linv = L > 0.0 ? 1.0 / L : 0.0; s.Lhalf = L / 2.0; // src/TDVMC.cpp:535-536
     s.kind = kind; s.n_ext = n_ext; s.gr_bins = gr_bins;
     s.periodic = periodic; s.n_short = n_short; s.potential = potential; s.rho_bins = rho_bins; s.use_phi = use_phi;
-    s.rmax = kind == TDVMC_SYSTEM_HE_BULK ? L / 2.0 : (kind == TDVMC_SYSTEM_HE_DROP ? 1e300 : knots[K]); // HeBulk.cpp:54
+    s.rmax = kind == TDVMC_SYSTEM_HE_BULK ? L / 2.0 : (kind != TDVMC_SYSTEM_SPLINE_TABLE ? 1e300 : knots[K]); // HeBulk.cpp:54
+    s.n_types = n_types;
+    s.pair_type = d_mix_pair_type.p; s.hbar_n = d_mix_hbar.p; s.mass_n = d_mix_mass.p; s.t_knots = d_mix_knots.p;
+    s.t_weights = d_mix_weights.p; s.t_mcm = d_mix_mcm.p; s.t_pot = d_mix_pot.p; s.t_cub = d_mix_cub.p;
     s.hbar = hbar;
     s.r0 = he_rs; s.core_m = core_m; s.r_split2 = r_split2; s.r_tail = r_tail; s.h_large = he_hl; s.gr_max = gr_max;
     s.u_core = u_core; s.u_const = u_const; s.u_lin = u_lin;
@@ -508,9 +569,12 @@ int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed,
         return -1;
     }
     if (sd->dim != 3 || sd->n_particles < 2 || sd->n_params < 1 || sd->n_splines < 4 || ed->n_walkers < 1 || sd->n_other < 3 ||
-        sd->tail_param < -1 || sd->tail_param >= sd->n_params || (!(sd->lbox > 0.0) && sd->system_kind != TDVMC_SYSTEM_HE_DROP) || sd->n_ext < sd->n_splines ||
+        sd->tail_param < -1 || sd->tail_param >= sd->n_params || (!(sd->lbox > 0.0) && sd->system_kind != TDVMC_SYSTEM_HE_DROP && sd->system_kind != TDVMC_SYSTEM_MIXTURE) || sd->n_ext < sd->n_splines ||
         (sd->system_kind != TDVMC_SYSTEM_SPLINE_TABLE && sd->system_kind != TDVMC_SYSTEM_HE_BULK &&
-         sd->system_kind != TDVMC_SYSTEM_HE_DROP) ||
+         sd->system_kind != TDVMC_SYSTEM_HE_DROP && sd->system_kind != TDVMC_SYSTEM_MIXTURE) ||
+        (sd->system_kind == TDVMC_SYSTEM_MIXTURE &&
+         (!sd->mixture || sd->mixture->n_pair_types < 1 || sd->n_ext != sd->mixture->n_pair_types * (sd->n_splines + 4) ||
+          sd->n_ext > 96 || sd->n_particles > 8 || sd->n_other < 6)) ||
         (sd->system_kind == TDVMC_SYSTEM_SPLINE_TABLE && (!sd->knots || !sd->spline_weights || sd->n_other < 9)) ||
         (sd->system_kind == TDVMC_SYSTEM_HE_BULK && (sd->n_ext != sd->n_splines + 3 || sd->n_other != 103)) ||
         (sd->system_kind == TDVMC_SYSTEM_HE_DROP && (sd->n_ext != sd->n_splines + 3 || sd->n_other != 403)))
@@ -562,6 +626,25 @@ int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed,
     h->n_ext = sd->n_ext;
     if (sd->knots) h->knots.assign(sd->knots, sd->knots + h->K + 4);
     if (sd->spline_weights) h->weights.assign(sd->spline_weights, sd->spline_weights + (size_t)h->K * 16);
+    if (h->kind == TDVMC_SYSTEM_MIXTURE)
+    {
+        const tdvmc_mixture_desc* m = sd->mixture;
+        const int T = m->n_pair_types, N = h->N, K = h->K;
+        h->n_types = T;
+        h->mix_pair_type.assign(m->pair_type, m->pair_type + (size_t)N * N);
+        h->mix_pot.assign(m->potential, m->potential + T);
+        h->mix_hbar.assign(m->hbar_over_2m, m->hbar_over_2m + N);
+        h->mix_mass.assign(m->mass, m->mass + N);
+        h->mix_knots.assign(m->knots, m->knots + (size_t)T * (K + 4));
+        h->mix_weights.assign(m->spline_weights, m->spline_weights + (size_t)T * K * 16);
+        h->mix_mcm.assign(m->mcmillan_factor, m->mcmillan_factor + T);
+        for (int t : h->mix_pair_type)
+            if (t < 0 || t >= T)
+            {
+                h->error = "pair type out of range";
+                return bail(-1);
+            }
+    }
     h->map_const.assign(h->P, 0.0);
     h->grad_const.assign(h->P, 0.0);
     if (sd->map_const) h->map_const.assign(sd->map_const, sd->map_const + h->P);
@@ -633,6 +716,14 @@ int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed,
         return bail(-3);
     }
 
+    if (h->kind == TDVMC_SYSTEM_MIXTURE)
+    {
+        h->npp = (h->N + 1) & ~1;
+        h->wpb = 1;
+        h->resident_per_sm = 1024; // one thread per walker
+        *out = h;
+        return 0;
+    }
     // sweep geometry: as many walkers (warps) per block as keep >= 2 blocks per SM resident
     h->npp = (h->N + 1) & ~1;
     SysDev s = h->sysdev();
@@ -731,7 +822,8 @@ int tdvmc_gpu_wrap_positions(tdvmc_gpu_handle* h)
     if (!h) return -1;
     CK(cudaSetDevice(h->device));
     Timed t(h, TDVMC_KERNEL_OTHER);
-    CK(launch_wrap(h->sysdev(), h->d_pos.p, h->W, h->stream));
+    if (h->kind == TDVMC_SYSTEM_MIXTURE) CK(launch_com_mix(h->sysdev(), h->d_pos.p, h->W, h->stream));
+    else CK(launch_wrap(h->sysdev(), h->d_pos.p, h->W, h->stream));
     return 0;
 }
 
@@ -753,7 +845,7 @@ static int do_sweep(tdvmc_gpu_handle* h, long long n_steps)
     a.mc_step = h->mc_step;
     {
         Timed t(h, TDVMC_KERNEL_SWEEP);
-        CK(launch_sweep(a, h->stream));
+        CK(h->kind == TDVMC_SYSTEM_MIXTURE ? launch_sweep_mix(a, h->stream) : launch_sweep(a, h->stream));
     }
     h->step_counter += (uint64_t)n_steps;
     h->trials_local += (uint64_t)n_steps * (uint64_t)h->W;
@@ -782,7 +874,8 @@ static int do_evaluate_walkers(tdvmc_gpu_handle* h, const double* pos, int n_cfg
     a.other = h->d_other.p;
     a.exponent = h->d_exponent.p;
     Timed t(h, TDVMC_KERNEL_EVALUATE);
-    CK(h->kind != TDVMC_SYSTEM_SPLINE_TABLE ? launch_evaluate_he(a, h->stream) : launch_evaluate(a, h->stream));
+    CK(h->kind == TDVMC_SYSTEM_MIXTURE ? launch_evaluate_mix(a, h->stream)
+                                          : (h->kind != TDVMC_SYSTEM_SPLINE_TABLE ? launch_evaluate_he(a, h->stream) : launch_evaluate(a, h->stream)));
     return 0;
 }
 
@@ -991,7 +1084,8 @@ int tdvmc_gpu_evaluate_fixed(tdvmc_gpu_handle* h, const double* R, int32_t n_cfg
     a.outer_out = out.p;
     {
         Timed t(h, TDVMC_KERNEL_EVALUATE);
-        CK(h->kind != TDVMC_SYSTEM_SPLINE_TABLE ? launch_evaluate_he(a, h->stream) : launch_evaluate(a, h->stream));
+        CK(h->kind == TDVMC_SYSTEM_MIXTURE ? launch_evaluate_mix(a, h->stream)
+                                          : (h->kind != TDVMC_SYSTEM_SPLINE_TABLE ? launch_evaluate_he(a, h->stream) : launch_evaluate(a, h->stream)));
     }
     std::vector<double> hA((size_t)n_cfg * h->lda);
     CK(cudaMemcpyAsync(hA.data(), A.p, hA.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1035,7 +1129,7 @@ int tdvmc_gpu_quotient_fixed(tdvmc_gpu_handle* h, const double* R, const double*
     a.moves = mv.p;
     a.n_moves = n_moves;
     a.delta = dl.p;
-    CK(launch_quotient(a, h->stream));
+    CK(h->kind == TDVMC_SYSTEM_MIXTURE ? launch_quotient_mix(a, h->stream) : launch_quotient(a, h->stream));
     std::vector<double> d(n_moves);
     CK(cudaMemcpyAsync(d.data(), dl.p, sizeof(double) * n_moves, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));

@@ -66,6 +66,16 @@ struct SysDev
     const double* utR;       // [n_ext]  parameters in spline space, u~_k = sum_p u_p M[p][k]
     const double* utI;       // [n_ext]
     const double* map_const; // [P] constant part of O_p
+    // BosonMixtureCluster (kind 3): per-pair-type bases, per-particle species data
+    int n_types;               // pair types T
+    const int* pair_type;      // [N][N] correlationTypes
+    const double* hbar_n;      // [N] hbar^2/2m of each particle's species
+    const double* mass_n;      // [N]
+    const double* t_knots;     // [T][K+4]
+    const double* t_weights;   // [T][K][4][4] monomial spline tables (SplineFactory::GetWeights3)
+    const double* t_mcm;       // [T] McMillan exponents
+    const int* t_pot;          // [T] pair potential ids
+    const double* t_cub;       // [T][K-3][6] sweep cubics {c0,c1,c2,c3,t_lo,t_hi} per knot interval
 };
 
 // ---- minimum image -------------------------------------------------------------------------

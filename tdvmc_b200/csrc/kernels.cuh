@@ -46,7 +46,7 @@ struct EvalArgs
     double* outer_out;      // [n_cfg] or null
 };
 cudaError_t launch_evaluate(const EvalArgs& a, cudaStream_t st);
-cudaError_t launch_evaluate_he(const EvalArgs& a, cudaStream_t st); // HeBulk (evaluate_he.cu)
+cudaError_t launch_evaluate_he(const EvalArgs& a, cudaStream_t st);  // HeBulk, HeDrop (evaluate_he.cu)
 
 // single-particle move ratios for scripted moves of one configuration (quotient_fixed)
 struct QuotientArgs
@@ -58,6 +58,12 @@ struct QuotientArgs
     double* delta;       // [n] exponentNew - exponent
 };
 cudaError_t launch_quotient(const QuotientArgs& a, cudaStream_t st);
+
+// ---- BosonMixtureCluster: thread-per-walker kernels (mixture.cu) ----
+cudaError_t launch_evaluate_mix(const EvalArgs& a, cudaStream_t st); // BosonMixtureCluster (mixture.cu)
+cudaError_t launch_sweep_mix(const SweepArgs& a, cudaStream_t st);
+cudaError_t launch_quotient_mix(const QuotientArgs& a, cudaStream_t st);
+cudaError_t launch_com_mix(const SysDev& s, double* pos, int W, cudaStream_t st);
 
 // ---- K3 (table form) and K4 (contraction from tables): reference semantics (tables.cu) ----
 struct TableArgs

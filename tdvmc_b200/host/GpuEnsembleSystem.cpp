@@ -118,6 +118,7 @@ GpuEnsembleSystem::GpuEnsembleSystem(const SystemTables& tb, int walkersTotal, d
     sd.reserved = 0;
     sd.map_const = tb.map_const.empty() ? nullptr : tb.map_const.data();
     sd.grad_const = tb.grad_const.empty() ? nullptr : tb.grad_const.data();
+    sd.mixture = nullptr;
     tdvmc_ensemble_desc ed;
     ed.struct_size = sizeof(ed);
     ed.device = device;

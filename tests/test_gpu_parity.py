@@ -565,3 +565,71 @@ def test_hedrop_chain_estimators_and_com(capi, golden):
     assert np.max(np.abs(Ra.mean(axis=1))) < 1e-12
     assert np.max(np.abs((Ra - Rb) + Rb.mean(axis=1, keepdims=True))) < 1e-12
     h.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# BosonMixtureCluster (BASELINE configs[4], config/He4He4Na.config): species, pair types, log term, HFDB / KTTY
+# ---------------------------------------------------------------------------------------------------
+MIX_CASES = ["mixture_he4he4na_fixture", "mixture_he4he4na_compact", "mixture_he4he4na_stretched", "mixture_he4he4na_equil"]
+
+
+@pytest.mark.parametrize("name", MIX_CASES)
+def test_mixture_fixed_configuration(capi, golden, name):
+    from oracle_lib import OracleMix
+
+    g = golden(name)
+    spec, h = make_handle(capi, g)
+    r = h.evaluate_fixed(g["R"])
+    o = OracleMix(spec).evaluate(g["R"], g["uR"], g["uI"], float(g["phiR"]))
+    assert rel(r["ss"][0], o["ext"]) < 1e-13
+    assert rel(r["O"][0], g["local_operators"]) < RTOL
+    assert abs(r["exponent"][0] - float(g["exponent"])) < RTOL * abs(float(g["exponent"]))
+    assert abs(r["e_r"][0] - float(g["local_energy_r"])) < RTOL * abs(float(g["local_energy_r"]))
+    assert abs(r["e_i"][0] - float(g["local_energy_i"])) < RTOL * abs(float(g["local_energy_i"]))
+    assert rel(r["drift_r"][0], g["drift_r"]) < RTOL and rel(r["drift_i"][0], g["drift_i"]) < RTOL
+    want, got = g["other_expectation_values"], r["other"][0]
+    assert got.shape == want.shape
+    for k in (0, 1, 2, 3, 5):
+        assert abs(got[k] - want[k]) <= RTOL * abs(want[k]), k
+    assert abs(got[4] - want[4]) <= 1e-9 * abs(want[4])
+    assert np.all(got[6:] == 0.0)
+    q, d = h.quotient_fixed(g["R"], g["moves"])
+    d_ref = g["move_exponent_new"] - float(g["exponent"])
+    assert np.max(np.abs(d - d_ref) / np.maximum(1.0, np.abs(d_ref))) < 1e-9
+    h.close()
+
+
+def test_mixture_chain_estimators_and_com(capi, golden):
+    from oracle_lib import OracleMix
+
+    g = golden("mixture_he4he4na_equil")
+    W, seed, mc_step = 70, 12, 2.0
+    n_samples, n_therm, n_init = 3, 10, 30
+    spec, h = make_handle(capi, g, n_walkers=W, seed=seed, mc_step=mc_step, max_samples=n_samples)
+    o = OracleMix(spec)
+    R0 = np.stack([g["R"] * (1.0 + 0.01 * w) for w in range(W)])
+    h.set_positions(R0)
+    h.sample_and_accumulate(n_samples, n_therm, n_init)
+    got = h.allreduce_and_fetch()
+    est = np.zeros(o.est_size())
+    acc, Rf = 0, []
+    for w in range(W):
+        r = o.sample_walker(R0[w], g["uR"], g["uI"], float(g["phiR"]), seed, w, 0, n_init, n_samples, n_therm, mc_step, est)
+        acc += r["accepted"]
+        Rf.append(r["R"])
+    want = o.unpack_est(est, W * n_samples)
+    assert got["n_acceptances"] == acc and got["n_trials"] == W * (n_init + n_samples * n_therm)
+    assert np.max(np.abs(h.get_positions() - np.stack(Rf))) < 1e-9
+    assert rel(got["O"], want["O"]) < 1e-9
+    assert abs(got["e_r"][0] - want["e_r"]) < 1e-9 * abs(want["e_r"])
+    assert rel(got["S"], want["S"]) < 1e-9 and rel(got["OER"], want["OER"]) < 1e-9
+    assert rel(got["other"][:6], want["other"][:6]) < 1e-9
+    Rb = h.get_positions()
+    h.wrap_positions()                                   # mass-weighted centre of mass to zero
+    Ra = h.get_positions()
+    m = spec.extra["mass"]
+    assert np.max(np.abs((Ra * m[None, :, None]).sum(axis=1))) < 1e-10
+    com = (Rb * m[None, :, None]).sum(axis=1) / m.sum()
+    assert np.max(np.abs(Ra - (Rb - com[:, None, :]))) < 1e-12
+    assert np.allclose(com[0], o.center_of_mass(Rb[0]), rtol=1e-14, atol=1e-14)
+    h.close()
