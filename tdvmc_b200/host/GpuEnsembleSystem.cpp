@@ -1,5 +1,6 @@
 #include "GpuEnsembleSystem.h"
 
+#include <cmath>
 #include <stdexcept>
 
 namespace tdvmc_host
@@ -82,6 +83,106 @@ SystemTables MakeNUBosonsBulkPBTables(int N, double LBOX, int N_PARAM, const std
     return t;
 }
 
+SystemTables MakeHeBulkTables(int N, double LBOX, int N_PARAM)
+{
+    SystemTables t;
+    t.system_kind = TDVMC_SYSTEM_HE_BULK;
+    t.n_particles = N;
+    t.n_params = N_PARAM;
+    t.lbox = LBOX;
+    t.tail_param = -1;
+    t.n_other = 3 + 100; // HeBulk.cpp:42-45
+    const int K = N_PARAM - 1 + 3 + 3;
+    const double rs = 1.95, h = (LBOX / 2.0 - rs) / (double)(K - 3.0);
+    t.knots.assign(K + 4, 0.0); // unused by the He kernels (grid is (rs, h))
+    t.n_ext = K + 3;
+    const int MC = K;
+    t.map_ptr.push_back(0);
+    PushRow(t, { { MC, 1.0 }, { 0, 10.0 * h / std::pow(rs, 6.0) }, { 1, (-5.0 * h + 3.0 * rs) / (2.0 * std::pow(rs, 6.0)) } });
+    PushRow(t, { { 2, 1.0 }, { 0, 1.0 }, { 1, -1.0 / 2.0 } });
+    for (int i = 2; i < N_PARAM - 2; i++) PushRow(t, { { i + 1, 1.0 } });
+    PushRow(t, { { K - 6, 1.0 }, { K - 5, -1.0 / 2.0 }, { K - 4, 1.0 } });
+    PushRow(t, { { K - 5, -3.0 / 2.0 }, { K - 4, 0.0 } });
+    t.map_const.assign(N_PARAM, 0.0);
+    t.grad_const.assign(N_PARAM, 0.0);
+    t.map_const[N_PARAM - 1] = 1.0;  // HeBulk.cpp:383
+    t.grad_const[N_PARAM - 1] = 1.0; // HeBulk.cpp:351
+    return t;
+}
+
+SystemTables MakeHeDropTables(int N, int N_PARAM)
+{
+    SystemTables t;
+    t.system_kind = TDVMC_SYSTEM_HE_DROP;
+    t.n_particles = N;
+    t.n_params = N_PARAM;
+    t.lbox = 0.0;
+    t.tail_param = -1;
+    t.n_other = 3 + 200 + 200; // HeDrop.cpp:75-79
+    const double m = -4.7, rs = 3.0, hS = 0.1, hL = 0.5;
+    const int nS = 70, K = N_PARAM + 1 + 2, nL = K - nS, P = N_PARAM;
+    const double r2 = hS * (nS - 3.0) + rs, rt = hL * (nL - 3.0) + r2, d = 1.0 / (hS + hL);
+    t.knots.assign(K + 4, 0.0);
+    t.n_ext = K + 3;
+    const int MC = K, CO = K + 1, LI = K + 2;
+    t.map_ptr.push_back(0);
+    PushRow(t, { { MC, 1.0 }, { 0, -2.0 * m * hS * std::pow(rs, m - 1.0) }, { 1, (m * hS + 3.0 * rs) * std::pow(rs, m - 1.0) / 2.0 } });
+    PushRow(t, { { 2, 1.0 }, { 0, 1.0 }, { 1, -1.0 / 2.0 } });
+    for (int i = 2; i < nS - 4; i++) PushRow(t, { { i + 1, 1.0 } });
+    PushRow(t, { { nS - 3, 1.0 }, { nS - 1, (-hS + hL) * d }, { nS, (2.0 * hL) * d } });
+    PushRow(t, { { nS - 2, 1.0 }, { nS - 1, (-4.0 * hS) * d }, { nS, (4.0 * hL) * d } });
+    PushRow(t, { { nS + 1, 1.0 }, { nS - 1, (4.0 * hS) * d }, { nS, (-4.0 * hL) * d } });
+    PushRow(t, { { nS + 2, 1.0 }, { nS - 1, (2.0 * hS) * d }, { nS, (hS - hL) * d } });
+    for (int i = nS; i < P - 3; i++) PushRow(t, { { i + 3, 1.0 } });
+    PushRow(t, { { K - 3, 1.0 }, { K - 2, -1.0 / 2.0 }, { K - 1, 1.0 } });
+    PushRow(t, { { CO, 1.0 }, { K - 2, 3.0 / 2.0 }, { K - 1, 0.0 } });
+    PushRow(t, { { LI, 1.0 }, { K - 2, 3.0 / 2.0 * rt - hL / 2.0 }, { K - 1, 2.0 * hL } });
+    return t;
+}
+
+SystemTables MakeBosonMixtureClusterTables(int N, const std::vector<std::vector<int> >& correlationTypes,
+                                           const std::vector<double>& hbarOver2mPerParticle,
+                                           const std::vector<double>& massPerParticle,
+                                           const std::vector<MixturePairType>& pairTypes, int numOfOtherExpectationValues)
+{
+    SystemTables t;
+    const int T = (int)pairTypes.size(), K = 26, EXT = K + 4; // paramOffset = 26, BosonMixtureCluster.cpp:543
+    t.system_kind = TDVMC_SYSTEM_MIXTURE;
+    t.n_particles = N;
+    t.n_params = 26 * T;
+    t.lbox = 0.0;
+    t.tail_param = -1;
+    t.n_other = numOfOtherExpectationValues;
+    t.n_ext = T * EXT;
+    t.n_pair_types = T;
+    for (const auto& row : correlationTypes)
+        for (int c : row) t.pair_type.push_back(c);
+    t.hbar_over_2m = hbarOver2mPerParticle;
+    t.mass = massPerParticle;
+    t.map_ptr.push_back(0);
+    for (int c = 0; c < T; c++)
+    {
+        const MixturePairType& p = pairTypes[c];
+        if ((int)p.nodes.size() != K + 4) throw std::runtime_error("BosonMixtureCluster: 26 splines per pair type expected");
+        t.type_knots.insert(t.type_knots.end(), p.nodes.begin(), p.nodes.end());
+        const std::vector<double> w = FlattenWeights(p.splineWeights);
+        t.type_weights.insert(t.type_weights.end(), w.begin(), w.end());
+        t.type_mcmillan.push_back(p.mcMillanFactor);
+        t.pair_potential.push_back(p.potential);
+        const int b = c * EXT, MC = K, CO = K + 1, LI = K + 2, LG = K + 3;
+        const auto& bc = p.bcFactors; // BosonMixtureCluster.cpp:636-645
+        PushRow(t, { { b + MC, 1.0 }, { b + 0, bc[0][0] }, { b + 1, bc[0][1] } });
+        PushRow(t, { { b + 2, 1.0 }, { b + 0, bc[1][0] }, { b + 1, bc[1][1] } });
+        for (int i = 2; i < 22; i++) PushRow(t, { { b + i + 1, 1.0 } });
+        PushRow(t, { { b + K - 3, 1.0 }, { b + K - 2, bc[2][0] }, { b + K - 1, bc[2][1] } });
+        PushRow(t, { { b + CO, 1.0 }, { b + K - 2, bc[3][0] }, { b + K - 1, bc[3][1] } });
+        PushRow(t, { { b + LI, 1.0 }, { b + K - 2, bc[4][0] }, { b + K - 1, bc[4][1] } });
+        PushRow(t, { { b + LG, 1.0 } });
+    }
+    t.knots.assign(t.type_knots.begin(), t.type_knots.begin() + K + 4);
+    return t;
+}
+
 GpuEnsembleSystem::GpuEnsembleSystem(const SystemTables& tb, int walkersTotal, double MC_STEP, int MC_NSTEPS,
                                      int UPDATE_SAMPLES_EVERY_NTH_STEP, unsigned long long seed, int processRank,
                                      int numOfProcesses, int device)
@@ -100,14 +201,14 @@ GpuEnsembleSystem::GpuEnsembleSystem(const SystemTables& tb, int walkersTotal, d
     sd.n_particles = tb.n_particles;
     sd.dim = 3;
     sd.n_params = tb.n_params;
-    sd.n_splines = (int32_t)tb.knots.size() - 4;
+    sd.n_splines = tb.system_kind == TDVMC_SYSTEM_MIXTURE ? 26 : (int32_t)tb.knots.size() - 4;
     sd.pair_rule = tb.pair_rule;
     sd.tail_param = tb.tail_param;
     sd.n_other = tb.n_other;
     sd.lbox = tb.lbox;
     sd.hbar2_2m = tb.hbar2_2m;
     sd.knots = tb.knots.data();
-    sd.spline_weights = tb.spline_weights.data();
+    sd.spline_weights = tb.spline_weights.empty() ? nullptr : tb.spline_weights.data();
     sd.map_ptr = tb.map_ptr.data();
     sd.map_col = tb.map_col.data();
     sd.map_val = tb.map_val.data();
@@ -118,7 +219,21 @@ GpuEnsembleSystem::GpuEnsembleSystem(const SystemTables& tb, int walkersTotal, d
     sd.reserved = 0;
     sd.map_const = tb.map_const.empty() ? nullptr : tb.map_const.data();
     sd.grad_const = tb.grad_const.empty() ? nullptr : tb.grad_const.data();
+    tdvmc_mixture_desc md;
     sd.mixture = nullptr;
+    if (tb.system_kind == TDVMC_SYSTEM_MIXTURE)
+    {
+        md.n_pair_types = tb.n_pair_types;
+        md.reserved = 0;
+        md.pair_type = tb.pair_type.data();
+        md.hbar_over_2m = tb.hbar_over_2m.data();
+        md.mass = tb.mass.data();
+        md.knots = tb.type_knots.data();
+        md.spline_weights = tb.type_weights.data();
+        md.mcmillan_factor = tb.type_mcmillan.data();
+        md.potential = tb.pair_potential.data();
+        sd.mixture = &md;
+    }
     tdvmc_ensemble_desc ed;
     ed.struct_size = sizeof(ed);
     ed.device = device;

@@ -41,6 +41,12 @@ struct SystemTables
     int system_kind = TDVMC_SYSTEM_SPLINE_TABLE;
     int n_ext = 0;                         // 0: number of splines
     std::vector<double> map_const, grad_const; // empty: zeros
+    // BosonMixtureCluster only (system_kind == TDVMC_SYSTEM_MIXTURE)
+    int n_pair_types = 0;
+    std::vector<int32_t> pair_type;        // correlationTypes flattened [N][N]
+    std::vector<int32_t> pair_potential;   // [T] 0 HFDB_He_He, 1 KTTY_He_Na, 2 KTTY_He_Cs
+    std::vector<double> hbar_over_2m, mass; // [N]
+    std::vector<double> type_knots, type_weights, type_mcmillan;
 };
 
 // Flattens the reference's vector<vector<vector<double>>> splineWeights (SplineFactory::GetWeights3).
@@ -54,6 +60,25 @@ SystemTables MakeBosonsBulkTables(int N, double LBOX, int N_PARAM, const std::ve
 SystemTables MakeNUBosonsBulkPBTables(int N, double LBOX, int N_PARAM, const std::vector<double>& nodes,
                                       const std::vector<std::vector<std::vector<double> > >& splineWeights,
                                       const std::vector<double>& SYSTEM_PARAMS, int grBinCount);
+
+// HeBulk (HeBulk.cpp:40-70, 376-383): everything follows from N, LBOX and N_PARAM.
+SystemTables MakeHeBulkTables(int N, double LBOX, int N_PARAM);
+// HeDrop (HeDrop.cpp:71-135, 609-626): open boundary; everything follows from N and N_PARAM.
+SystemTables MakeHeDropTables(int N, int N_PARAM);
+// One pair type of BosonMixtureCluster: the reference's CorrelationFunctionData after InitSystem().
+struct MixturePairType
+{
+    std::vector<double> nodes;                                     // cfd.nodes
+    std::vector<std::vector<std::vector<double> > > splineWeights; // cfd.splineWeights
+    std::vector<std::vector<double> > bcFactors;                   // cfd.bcFactors (5 x 2)
+    double mcMillanFactor;
+    int potential;                                                 // 0 HFDB_He_He, 1 KTTY_He_Na, 2 KTTY_He_Cs
+};
+// BosonMixtureCluster (BosonMixtureCluster.cpp:58-346, 636-645); correlationTypes [N][N], hbarOver2m/mass per particle.
+SystemTables MakeBosonMixtureClusterTables(int N, const std::vector<std::vector<int> >& correlationTypes,
+                                           const std::vector<double>& hbarOver2mPerParticle,
+                                           const std::vector<double>& massPerParticle,
+                                           const std::vector<MixturePairType>& pairTypes, int numOfOtherExpectationValues);
 
 // The seven estimator arrays under the reference's global names (src/TDVMC.cpp:147-153).
 struct Estimators

@@ -3,6 +3,8 @@
 // table are read from a text file (the reference driver would pass its own SplineFactory output).
 //
 //   example_driver <tables.txt>      tables.txt: N LBOX N_PARAM n_knots, knots..., K*16 weights...
+//   example_driver --map hebulk N LBOX N_PARAM | --map hedrop N N_PARAM
+//                                    prints the parameter map the adapter builds (no GPU needed)
 //
 // Exit code 0 and one line "E_R=... acceptance=..." on success; without a CUDA device the library
 // refuses to run (no CPU fallback) and the driver prints the error and exits with code 3.
@@ -10,6 +12,8 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 #include <stdexcept>
@@ -22,6 +26,24 @@ int main(int argc, char** argv)
     {
         std::fprintf(stderr, "usage: example_driver <tables.txt>\n");
         return 2;
+    }
+    if (!std::strcmp(argv[1], "--map") && argc >= 5)
+    {
+        const bool bulk = !std::strcmp(argv[2], "hebulk");
+        SystemTables t = bulk ? MakeHeBulkTables(std::atoi(argv[3]), std::atof(argv[4]), std::atoi(argv[5]))
+                              : MakeHeDropTables(std::atoi(argv[3]), std::atoi(argv[4]));
+        std::printf("%d %d %d %d %d\n", t.system_kind, t.n_params, t.n_ext, t.n_other, (int)t.knots.size() - 4);
+        for (int p : t.map_ptr) std::printf("%d ", p);
+        std::printf("\n");
+        for (int c : t.map_col) std::printf("%d ", c);
+        std::printf("\n");
+        for (double v : t.map_val) std::printf("%.17g ", v);
+        std::printf("\n");
+        for (double v : t.map_const) std::printf("%.17g ", v);
+        std::printf("\n");
+        for (double v : t.grad_const) std::printf("%.17g ", v);
+        std::printf("\n");
+        return 0;
     }
     std::ifstream f(argv[1]);
     int N, P, nk;

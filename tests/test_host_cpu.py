@@ -193,3 +193,24 @@ def test_cpp_host_adapter_builds_and_refuses_without_gpu(tmp_path, golden):
         assert r.returncode == 0 and "E_R=" in r.stdout
     else:
         assert r.returncode == 3 and "no CUDA device" in r.stderr and "no CPU fallback" in r.stderr
+
+
+def test_cpp_he_table_builders_match_python_specs():
+    """MakeHeBulkTables / MakeHeDropTables (C++ adapter) build the same CSR parameter map, bit for bit, as
+    tdvmc_b200.systems.he_bulk / he_drop (which the golden fixtures pin against the reference)."""
+    from tdvmc_b200 import systems as tsys
+    host = os.path.join(ROOT, "tdvmc_b200", "host")
+    subprocess.check_call(["make", "-C", host, "example_driver"])
+    exe = os.path.join(host, "example_driver")
+    for args, spec in ((["hebulk", "64", "14.5", "40"], tsys.he_bulk(64, 14.5, 40)),
+                       (["hedrop", "6", "150"], tsys.he_drop(6, 150))):
+        out = subprocess.run([exe, "--map"] + args, capture_output=True, text=True, check=True).stdout.splitlines()
+        kind, P, n_ext, n_other, K = (int(x) for x in out[0].split())
+        assert (kind, P, n_ext, n_other) == (spec.kind, spec.n_params, spec.n_ext, spec.n_other)
+        assert K == spec.extra["n_splines"]
+        np.testing.assert_array_equal(np.array(out[1].split(), dtype=np.int64), spec.map_ptr)
+        np.testing.assert_array_equal(np.array(out[2].split(), dtype=np.int64), spec.map_col)
+        np.testing.assert_array_equal(np.array(out[3].split(), dtype=np.float64), spec.map_val)
+        for line, want in ((out[4], spec.map_const), (out[5], spec.grad_const)):   # empty in the adapter = zeros
+            got = np.array(line.split(), dtype=np.float64)
+            np.testing.assert_array_equal(got if got.size else np.zeros(P), want if want is not None else np.zeros(P))
