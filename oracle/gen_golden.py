@@ -13,6 +13,7 @@ this script only chooses the inputs and re-packs the text dumps as .npz.
     python oracle/gen_golden.py            # regenerate everything
 """
 import json
+import re
 import os
 import subprocess
 import sys
@@ -280,6 +281,25 @@ def gen_nubosonsbulkpb():
     R1 = mc["R_final"].reshape(N, 3)
     pack_eval("nubosonsbulkpb_n216_equil", "NUBosonsBulkPB", scal, dict(arr, R=R1),
               default_moves(R1, L, rng), keep_tables="subset", subset=(0, 7, 100, 215))
+
+
+def gen_nubosonsbulkpb_full():
+    """config/NUBosonsBulkPB3D.config at its own size: N = 1728, L = 12, N_PARAM = 200 on the config's NURBS_GRID and
+    SYSTEM_PARAMS; the shipped parameters are all zero (ideal-gas start), so a smooth non-zero set is used."""
+    rng = np.random.default_rng(1728)
+    cfg = json.loads(re.sub(r"(\d)\.(\s*[,\]\}])", r"\g<1>.0\2", open(os.path.join(REF, "config", "NUBosonsBulkPB3D.config")).read()))
+    N, P = int(cfg["N"]), int(cfg["N_PARAM"])
+    L = (N / float(cfg["RHO"])) ** (1.0 / 3.0)
+    L = float(round(L, 9))
+    grid = np.array(cfg["NURBS_GRID"], dtype=np.float64)
+    R0 = jittered_lattice(N, L, seed=6)
+    uR, uI = smooth_params(P, L / 2, w_r=0.8, c_i=1.5, w_i=0.5)
+    scal = dict(N=N, LBOX=L, N_PARAM=P, USE_NURBS=1, time=0.0, phiR=0.0, phiI=0.0, GR_BIN_COUNT=int(cfg["GR_BIN_COUNT"]))
+    arr = dict(R=R0, uR=uR, uI=uI, SYSTEM_PARAMS=cfg["SYSTEM_PARAMS"], NURBS_GRID=grid)
+    mc = run_mc("NUBosonsBulkPB", dict(scal, MC_STEP=float(cfg["MC_STEP"]), MC_NSTEPS=1, MC_NTHERMSTEPS=N * 12, seed=11), arr)
+    R1 = mc["R_final"].reshape(N, 3)
+    pack_eval("nubosonsbulkpb_n1728_equil", "NUBosonsBulkPB", scal, dict(arr, R=R1),
+              default_moves(R1, L, rng), keep_tables="subset", subset=(0, 9, 863, 1727))
 
 
 def hebulk_drift(d, uR, uI):

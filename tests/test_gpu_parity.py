@@ -18,7 +18,7 @@ from tdvmc_b200 import systems
 pytestmark = pytest.mark.gpu
 
 EVAL_CASES = ["bosonsbulk_n64_fixture", "bosonsbulk_n64_equil", "bosonsbulk_n343_lattice", "bosonsbulk_n343_equil",
-              "nubosonsbulkpb_n216_equil"]
+              "nubosonsbulkpb_n216_equil", "nubosonsbulkpb_n1728_equil"]
 RTOL = 1e-10
 
 
@@ -171,7 +171,8 @@ def test_proposal_stream_matches_oracle(capi, golden):
     h.close()
 
 
-@pytest.mark.parametrize("name,n_steps", [("bosonsbulk_n64_equil", 640), ("nubosonsbulkpb_n216_equil", 432)])
+@pytest.mark.parametrize("name,n_steps", [("bosonsbulk_n64_equil", 640), ("nubosonsbulkpb_n216_equil", 432),
+                                          ("nubosonsbulkpb_n1728_equil", 300)])
 def test_sweep_replays_oracle_chain(capi, golden, name, n_steps):
     """Same proposal stream, same accept rule: the device chain follows the oracle chain move for move."""
     g = golden(name)
@@ -307,6 +308,46 @@ def test_full_size_properties(capi, golden):
     assert np.all(np.abs(Rw) <= 3.5 + 1e-9)
     ev4 = h.evaluate_fixed(Rw[:1])
     assert abs(ev4["e_r"][0] - ev2["e_r"][0]) < 1e-9 * abs(ev2["e_r"][0])
+    h.close()
+
+
+def test_full_size_properties_config4(capi, golden):
+    """config/NUBosonsBulkPB3D.config at its own size (N=1728, L=12, P=200, reflection rule) with its own sample counts
+    (MC_NSTEPS=50, MC_NTHERMSTEPS=200) and sample reuse (UPDATE_SAMPLES_EVERY_NTH_STEP=1): the resident path."""
+    g = golden("nubosonsbulkpb_n1728_equil")
+    W, n_samples = 32, 50
+    spec, h = make_handle(capi, g, n_walkers=W, seed=5, mc_step=0.5, max_samples=n_samples, keep_sample_positions=True)
+    R0 = np.broadcast_to(g["R"], (W, 1728, 3)).copy()
+    h.set_positions(R0)
+    assert np.array_equal(h.get_positions(), R0)
+    h.sample_and_accumulate(n_samples, 200, 400)
+    a = h.allreduce_and_fetch()
+    assert a["n_samples"] == n_samples * W and a["n_trials"] == W * (400 + n_samples * 200)
+    assert 0.2 < a["n_acceptances"] / a["n_trials"] < 0.95
+    assert np.array_equal(a["S"], a["S"].T)
+    ev = np.linalg.eigvalsh(a["S"] - np.outer(a["O"], a["O"]))
+    assert ev.min() > -1e-8 * ev.max()
+    h.reevaluate_stored()                                        # src/TDVMC.cpp:1222-1303 at unchanged parameters
+    b = h.allreduce_and_fetch()
+    for k in ("O", "S", "OER", "OEI", "e_r", "e_i"):
+        assert rel(b[k], a[k]) < 1e-13, k
+    # re-evaluation at CHANGED parameters = fresh fixed evaluation of the same stored configurations (the last sample
+    # of every walker is the walker's current position)
+    u2 = g["uR"] * 1.01
+    h.set_params(u2, g["uI"], float(g["phiR"]), 0.0, float(g["time"]))
+    h.reevaluate_stored()
+    c = h.allreduce_and_fetch()
+    assert abs(c["e_r"][0] - a["e_r"][0]) > 1e-9 * abs(a["e_r"][0])
+    assert rel(c["O"], a["O"]) < 1e-13                             # O_k do not depend on the parameters
+    Rf = h.get_positions()
+    o = Oracle(spec, time=float(g["time"]))
+    ref = o.evaluate(Rf[0], u2, g["uI"], float(g["phiR"]))
+    ev2 = h.evaluate_fixed(Rf[:2])
+    assert abs(ev2["e_r"][0] - ref["e_r"]) < RTOL * abs(ref["e_r"])
+    assert abs(ev2["e_i"][0] - ref["e_i"]) < RTOL * abs(ref["e_i"])
+    assert rel(ev2["O"][0], ref["O"]) < RTOL
+    ev3 = h.evaluate_fixed(Rf[:1] + np.array([12.0, -24.0, 12.0]))
+    assert abs(ev3["e_r"][0] - ev2["e_r"][0]) < 1e-9 * abs(ev2["e_r"][0])
     h.close()
 
 

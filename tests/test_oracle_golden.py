@@ -10,7 +10,7 @@ from oracle_lib import Oracle
 from tdvmc_b200 import systems
 
 EVAL_CASES = ["bosonsbulk_n64_fixture", "bosonsbulk_n64_equil", "bosonsbulk_n343_lattice", "bosonsbulk_n343_equil",
-              "nubosonsbulkpb_n216_equil"]
+              "nubosonsbulkpb_n216_equil", "nubosonsbulkpb_n1728_equil"]
 RTOL = 1e-10  # north_star: fixed-configuration E_L, drift, O_k within 1e-10 relative
 
 
