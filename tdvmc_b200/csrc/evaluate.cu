@@ -13,11 +13,21 @@
 // a different evaluation order would differ from the reference at the 1e-10 level); only the order
 // of the sums over particles differs.
 //
-// Thread n owns particle n and walks over all partners i (positions broadcast from shared memory).
+// Every unordered pair is visited ONCE.  The pair matrix is cut into 32x32 tiles; in "shift" s, warp I
+// takes tile (I, (I+s) mod NT), so the tiles of one shift have distinct row blocks and distinct column
+// blocks.  Inside a tile lane l owns row particle 32I+l and meets column particle 32J+(l+k)%32 in step
+// k: the row force stays in the lane's registers, the column force accumulators ROTATE through the warp
+// by shuffle (lane l receives lane l+1's), so no lane ever adds into another lane's data and nothing
+// needs an atomic.  Tiles are flushed into the block's force arrays columns first, rows second, a
+// barrier after each.  The Laplacian terms are symmetric in the pair and are doubled at the end.
 // The basis sums ss[k] (needed for O_k) are a histogram over knot intervals; each warp keeps a
 // private copy and adds to it without atomics: lanes whose pair falls into the same interval are
 // ranked with match.any and take turns, so every round touches distinct addresses.
+// (evaluate_rowwise_kernel below is the first version - thread n walks all partners i, every pair seen
+// twice - kept selectable with TDVMC_EVAL_ROWWISE=1 for A/B timing.)
 #include "kernels.cuh"
+
+#include <cstdlib>
 
 namespace tdvmc
 {
@@ -55,6 +65,7 @@ struct EvalSmem
     double* py;
     double* pz;
     double* hist;
+    double* frc; // [6][NT*32]: fRx fRy fRz fIx fIy fIz per particle
     double* sstot;
     double* red;
     unsigned short* lut;
@@ -75,7 +86,7 @@ struct SmemCarver
 __host__ __device__ inline size_t eval_smem_layout(const SysDev& s, int nwarps, EvalSmem* out, unsigned char* base)
 {
     SmemCarver c = { base, 0 };
-    const int Npad = (s.N + 1) & ~1;
+    const int Npad = ((s.N + 31) >> 5) << 5; // whole tiles
     EvalSmem m;
     m.knots = c.take(s.K + 4);
     m.rec = c.take((size_t)s.nbins * kRecStride);
@@ -85,6 +96,7 @@ __host__ __device__ inline size_t eval_smem_layout(const SysDev& s, int nwarps, 
     m.py = c.take(Npad);
     m.pz = c.take(Npad);
     m.hist = c.take((size_t)nwarps * s.K);
+    m.frc = c.take((size_t)6 * Npad);
     m.sstot = c.take(s.K);
     m.red = c.take((size_t)nwarps * 8);
     m.lut = reinterpret_cast<unsigned short*>(base + c.off);
@@ -93,8 +105,275 @@ __host__ __device__ inline size_t eval_smem_layout(const SysDev& s, int nwarps, 
     return c.off;
 }
 
+// 1/r to full precision without the IEEE division sequence: hardware seed + two Newton steps.
+// Enters only the well-conditioned factors (unit vector, (D-1)/r), never the spline argument.
+__device__ __forceinline__ double rcp_refined(double r)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(r));
+    double e = fma(-r, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-r, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+
 template <bool REFLECT>
 __global__ void __launch_bounds__(384, 2) evaluate_kernel(EvalArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SysDev& s = a.s;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const int cfg = blockIdx.x;
+    const int N = s.N, K = s.K, P = s.P;
+
+    EvalSmem m;
+    eval_smem_layout(s, nwarps, &m, smem_raw);
+
+    for (int i = tid; i < K + 4; i += blockDim.x) m.knots[i] = s.knots[i];
+    for (int i = tid; i < s.nbins * kRecStride; i += blockDim.x) m.rec[i] = s.rec[i];
+    for (int i = tid; i < K; i += blockDim.x)
+    {
+        m.utR[i] = s.utR[i];
+        m.utI[i] = s.utI[i];
+    }
+    for (int i = tid; i < s.ncell; i += blockDim.x) m.lut[i] = s.lut[i];
+    const double* gpos = a.pos + (size_t)cfg * 3 * s.Np;
+    const int NT = (N + 31) >> 5; // tiles of 32 particles
+    for (int i = tid; i < NT * 32; i += blockDim.x)
+    {
+        const bool v = i < N;
+        m.px[i] = v ? gpos[i] : 0.0;
+        m.py[i] = v ? gpos[s.Np + i] : 0.0;
+        m.pz[i] = v ? gpos[2 * s.Np + i] : 0.0;
+    }
+    for (int i = tid; i < 6 * NT * 32; i += blockDim.x) m.frc[i] = 0.0;
+    for (int i = tid; i < nwarps * K; i += blockDim.x) m.hist[i] = 0.0;
+    __syncthreads();
+
+    double* hist = m.hist + (size_t)warp * K;
+    const double rmax = s.rmax;
+    const double pot_a = s.pot_a;
+    const int NP32 = NT * 32;
+    double* fRx = m.frc;
+    double* fRy = fRx + NP32;
+    double* fRz = fRy + NP32;
+    double* fIx = fRz + NP32;
+    double* fIy = fIx + NP32;
+    double* fIz = fIy + NP32;
+
+    double lapR = 0.0, lapI = 0.0;
+    int vcount = 0, outer = 0;
+
+    const int half = NT >> 1;
+    const bool nt_even = (NT & 1) == 0;
+    for (int sft = 0; sft <= half; sft++)
+    {
+        // diagonal tiles: rotations 1..16 (16 by the lower half only) cover each pair of the tile once
+        const int kfirst = sft == 0 ? 1 : 0;
+        const int klast = sft == 0 ? 16 : 31;
+        for (int base = 0; base < NT; base += nwarps)
+        {
+            const int I = base + warp;
+            // NT even: the shift NT/2 pairs block I with I+NT/2 from both sides - the lower half takes it
+            const bool tile = (I < NT) && !(nt_even && sft == half && sft != 0 && I >= half);
+            int J = I + sft;
+            if (J >= NT) J -= NT;
+            const int n = 32 * I + lane;
+            double rRx = 0.0, rRy = 0.0, rRz = 0.0, rIx = 0.0, rIy = 0.0, rIz = 0.0; // force on the row particle
+            double cRx = 0.0, cRy = 0.0, cRz = 0.0, cIx = 0.0, cIy = 0.0, cIz = 0.0; // rotating column accumulators
+            if (tile)
+            {
+                const bool vn = n < N;
+                const double xn = m.px[n], yn = m.py[n], zn = m.pz[n];
+                for (int k = kfirst; k <= klast; k++)
+                {
+                    if (k > kfirst)
+                    {
+                        const int src = (lane + 1) & 31;
+                        cRx = __shfl_sync(FULL_MASK, cRx, src);
+                        cRy = __shfl_sync(FULL_MASK, cRy, src);
+                        cRz = __shfl_sync(FULL_MASK, cRz, src);
+                        cIx = __shfl_sync(FULL_MASK, cIx, src);
+                        cIy = __shfl_sync(FULL_MASK, cIy, src);
+                        cIz = __shfl_sync(FULL_MASK, cIz, src);
+                    }
+                    const int i = 32 * J + ((lane + k) & 31);
+                    double vx, vy, vz;
+                    double r = disp_exact(s, xn, yn, zn, m.px[i], m.py[i], m.pz[i], vx, vy, vz); // R[n] - R[i]
+                    const bool pair = vn && (i < N) && (sft != 0 || k < 16 || lane < 16);
+                    bool inside;
+                    if (REFLECT)
+                    {
+                        if (!(r < rmax)) r = 2 * rmax - r; // NUBosonsBulkPB.cpp:250-253, 331-335
+                        inside = r < rmax;
+                    }
+                    else
+                    {
+                        inside = r <= rmax; // BosonsBulk.cpp:195, 257
+                    }
+                    const bool act = pair && inside;
+                    if (pair && !inside) outer++;      // BosonsBulk.cpp:207-210
+                    if (act && (r < pot_a)) vcount++;  // BosonsBulk.cpp:268-271
+
+                    int bin = 0;
+                    double val[4] = { 0.0, 0.0, 0.0, 0.0 };
+                    if (act)
+                    {
+                        bin = find_bin_exact(s, m.knots, m.lut, r);
+                        const double* w = m.rec + (size_t)(bin - s.first_bin) * kRecStride;
+                        const double r2 = r * r;
+                        const double rinv = rcp_refined(r);
+                        const double f2 = 2.0 * rinv; // (DIM - 1) / r, BosonsBulk.cpp:319-322
+                        double gR = 0.0, gI = 0.0;
+#pragma unroll
+                        for (int p = 0; p < 4; p++)
+                        {
+                            const double2 w01 = *reinterpret_cast<const double2*>(w + p * 4);
+                            const double2 w23 = *reinterpret_cast<const double2*>(w + p * 4 + 2);
+                            const double d1 = w01.y + 2.0 * w23.x * r + 3.0 * w23.y * r2; // BosonsBulk.cpp:299
+                            const double d2 = 2.0 * w23.x + 6.0 * w23.y * r;              // BosonsBulk.cpp:301
+                            const double uRk = m.utR[bin - p], uIk = m.utI[bin - p];
+                            const double t2 = d2 + f2 * d1;
+                            gR = fma(uRk, d1, gR);
+                            gI = fma(uIk, d1, gI);
+                            lapR = fma(uRk, t2, lapR);
+                            lapI = fma(uIk, t2, lapI);
+                            val[p] = w01.x + w01.y * r + w23.x * r2 + w23.y * (r2 * r); // BosonsBulk.cpp:204
+                        }
+                        const double ex = vx * rinv, ey = vy * rinv, ez = vz * rinv; // unreflected vec / (reflected) r
+                        rRx = fma(gR, ex, rRx);
+                        rRy = fma(gR, ey, rRy);
+                        rRz = fma(gR, ez, rRz);
+                        rIx = fma(gI, ex, rIx);
+                        rIy = fma(gI, ey, rIy);
+                        rIz = fma(gI, ez, rIz);
+                        cRx = fma(-gR, ex, cRx); // the partner sees the opposite unit vector
+                        cRy = fma(-gR, ey, cRy);
+                        cRz = fma(-gR, ez, cRz);
+                        cIx = fma(-gI, ex, cIx);
+                        cIy = fma(-gI, ey, cIy);
+                        cIz = fma(-gI, ez, cIz);
+                    }
+                    warp_hist_add4(hist, bin, act, val, lane);
+                }
+                const int ic = 32 * J + ((lane + klast) & 31); // the column whose accumulator ended up in this lane
+                fRx[ic] += cRx;
+                fRy[ic] += cRy;
+                fRz[ic] += cRz;
+                fIx[ic] += cIx;
+                fIy[ic] += cIy;
+                fIz[ic] += cIz;
+            }
+            __syncthreads();
+            if (tile)
+            {
+                fRx[n] += rRx;
+                fRy[n] += rRy;
+                fRz[n] += rRz;
+                fIx[n] += rIx;
+                fIy[n] += rIy;
+                fIz[n] += rIz;
+            }
+            __syncthreads();
+        }
+    }
+    lapR *= 2.0; // each pair enters the Laplacian of both partners with the same value
+    lapI *= 2.0;
+
+    double R1 = 0.0, I1 = 0.0, RI = 0.0;
+    for (int n = tid; n < N; n += blockDim.x)
+    {
+        const double ax = fRx[n], ay = fRy[n], az = fRz[n], bx = fIx[n], by = fIy[n], bz = fIz[n];
+        R1 += ax * ax + ay * ay + az * az;          // VectorNorm2, BosonsBulk.cpp:418-419
+        I1 += bx * bx + by * by + bz * bz;
+        RI += ax * bx + ay * by + az * bz;          // kineticSumR1I1 / 2, BosonsBulk.cpp:417
+        if (a.drift_r)
+        {
+            double* d = a.drift_r + ((size_t)cfg * N + n) * 3;
+            d[0] = ax; d[1] = ay; d[2] = az;
+        }
+        if (a.drift_i)
+        {
+            double* d = a.drift_i + ((size_t)cfg * N + n) * 3;
+            d[0] = bx; d[1] = by; d[2] = bz;
+        }
+    }
+
+    // block reduction (fixed order -> deterministic)
+    R1 = warp_sum(R1);
+    I1 = warp_sum(I1);
+    RI = warp_sum(RI);
+    lapR = warp_sum(lapR);
+    lapI = warp_sum(lapI);
+    vcount = warp_sum_int(vcount);
+    outer = warp_sum_int(outer);
+    if (lane == 0)
+    {
+        double* r = m.red + warp * 8;
+        r[0] = R1; r[1] = I1; r[2] = RI; r[3] = lapR; r[4] = lapI; r[5] = (double)vcount; r[6] = (double)outer;
+    }
+    __syncthreads();
+
+    for (int k = tid; k < K; k += blockDim.x)
+    {
+        double t = 0.0;
+        for (int w = 0; w < nwarps; w++) t += m.hist[(size_t)w * K + k];
+        m.sstot[k] = t;
+        if (a.ss_out) a.ss_out[(size_t)cfg * K + k] = t;
+    }
+    __syncthreads();
+
+    const long long row = a.row0 + (long long)cfg * a.row_stride;
+    double* Arow = a.A + (size_t)row * a.lda;
+    double epart = 0.0;
+    for (int p = tid; p < P; p += blockDim.x)
+    {
+        double o = 0.0;
+        for (int j = s.map_ptr[p]; j < s.map_ptr[p + 1]; j++) o += s.map_val[j] * m.sstot[s.map_col[j]]; // BosonsBulk.cpp:158-177
+        Arow[p] = o;
+        epart = fma(s.uR[p], o, epart); // BosonsBulk.cpp:526-529
+    }
+    epart = warp_sum(epart);
+    if (lane == 0) m.red[warp * 8 + 7] = epart;
+    __syncthreads();
+
+    if (tid == 0)
+    {
+        double t[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+        for (int w = 0; w < nwarps; w++)
+            for (int q = 0; q < 8; q++) t[q] += m.red[w * 8 + q];
+        const double outer_sum = t[6];
+        const double v_int = s.pot_b * t[5];
+        const double exponent = t[7] + s.uR[s.tail_param] * outer_sum; // BosonsBulk.cpp:532-536
+        const double kR1 = t[0], kI1 = t[1], kRI = 2.0 * t[2], kR2 = t[3], kI2 = t[4];
+        const double kin_r = -(kR1 - kI1 + kR2) * s.hbar; // BosonsBulk.cpp:422
+        const double kin_i = -(kRI + kI2) * s.hbar;       // BosonsBulk.cpp:423
+        const double e_r = kin_r + v_int;                 // :425, external potential is zero (:344-347)
+        const double e_i = kin_i;
+        Arow[P] = e_r;
+        Arow[P + 1] = e_i;
+        Arow[P + 2] = 1.0;
+        double* o = a.other + (size_t)row * s.n_other;   // BosonsBulk.cpp:449-457
+        o[0] = kin_r;
+        o[1] = v_int;
+        o[2] = exp(exponent + s.phiR);
+        o[3] = exponent;
+        o[4] = kR1;
+        o[5] = kI1;
+        o[6] = kR2;
+        o[7] = kI2;
+        o[8] = kRI;
+        if (a.exponent) a.exponent[row] = exponent;
+        if (a.outer_out) a.outer_out[cfg] = outer_sum;
+    }
+}
+
+template <bool REFLECT>
+__global__ void __launch_bounds__(384, 2) evaluate_rowwise_kernel(EvalArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SysDev& s = a.s;
@@ -294,27 +573,38 @@ size_t evaluate_smem_bytes(const SysDev& s)
     return eval_smem_layout(s, evaluate_threads(s) / 32, nullptr, nullptr);
 }
 
+static bool eval_rowwise()
+{
+    static int v = -1;
+    if (v < 0)
+    {
+        const char* e = getenv("TDVMC_EVAL_ROWWISE"); // A/B timing knob: 1 = first version of the kernel
+        v = (e && atoi(e) == 1) ? 1 : 0;
+    }
+    return v == 1;
+}
+
+template <typename KernelT>
+static cudaError_t launch_eval_kernel(KernelT kernel, const EvalArgs& a, int threads, size_t smem, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    kernel<<<a.n_cfg, threads, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_evaluate(const EvalArgs& a, cudaStream_t st)
 {
     if (a.n_cfg <= 0) return cudaSuccess;
     const int threads = evaluate_threads(a.s);
     const size_t smem = evaluate_smem_bytes(a.s);
-    cudaError_t e;
-    if (a.s.pair_rule == 1)
-    {
-        e = cudaFuncSetAttribute(evaluate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        cudaFuncSetAttribute(evaluate_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        evaluate_kernel<true><<<a.n_cfg, threads, smem, st>>>(a);
-    }
-    else
-    {
-        e = cudaFuncSetAttribute(evaluate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        cudaFuncSetAttribute(evaluate_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        evaluate_kernel<false><<<a.n_cfg, threads, smem, st>>>(a);
-    }
-    return cudaGetLastError();
+    const bool refl = a.s.pair_rule == 1;
+    if (eval_rowwise())
+        return refl ? launch_eval_kernel(evaluate_rowwise_kernel<true>, a, threads, smem, st)
+                    : launch_eval_kernel(evaluate_rowwise_kernel<false>, a, threads, smem, st);
+    return refl ? launch_eval_kernel(evaluate_kernel<true>, a, threads, smem, st)
+                : launch_eval_kernel(evaluate_kernel<false>, a, threads, smem, st);
 }
 
 } // namespace tdvmc

@@ -213,6 +213,7 @@ __global__ void __launch_bounds__(kSweepMaxThreads, kSweepMinBlocks) sweep_kerne
             // quotient = exp(2 delta) must be finite and >= U (src/TDVMC.cpp:886-913), in the log domain
             const double two_delta = 2.0 * delta;
             const bool accept = (two_delta >= log_u) && (two_delta <= 709.782712893384);
+            __syncwarp(); // every lane has read the old positions before lane 0 overwrites one
             if (accept)
             {
                 if (lane == 0)
@@ -370,7 +371,19 @@ int sweep_blocks_per_sm(const SysDev& s, int wpb, int npp)
     int nb = 0;
     const int u = sweep_unroll();
     const void* fn = u == 1 ? sweep_fn<1>(s) : (u == 4 ? sweep_fn<4>(s) : sweep_fn<2>(s));
-    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static int optin = -1;
+    if (optin < 0)
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) optin = 48 * 1024;
+    }
+    if (smem > (size_t)optin) return 0;
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return 0;
+    }
     cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, wpb * 32, smem) != cudaSuccess) return 0;
     return nb;
