@@ -18,6 +18,11 @@
 // 16-byte slots of a bank row), uniform knots need no t_lo load, positions are kept wrapped into
 // the first cell so the minimum image is min(|d|, L - |d|) (3 FP64 ops per coordinate instead of 4),
 // and the square root drops the final correctly-rounding step (2 ulp are irrelevant for sampling).
+// Not kept: 64-bit fixed-point coordinates (the two's-complement difference IS the minimum image, which
+// moves 9 of 26 FP64 instructions per pair to the integer pipe and three I2F.F64.S64).  Measured equal
+// (14.01 vs 14.07 ms per launch): the conversions issue at 14 lanes/clk/SM (profiles/microbench/
+// conv_throughput.cu) and with five warps per scheduler they serialise with the FP64 work instead of
+// overlapping it (ncu: FP64 53 % + conversion unit 49 %).
 // A second capture (profiles/r01c_sweep_ncu.txt) still had 80 % shared-memory wavefronts: a random
 // LDS.128 is served quarter-warp by quarter-warp, and two of eight lanes hitting the same 16-byte
 // slot of a bank row with different records serialise.  The coefficient planes are therefore
@@ -64,12 +69,10 @@ __device__ __forceinline__ double sqrt_fast(double x)
 {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double t = x * y;
-    const double e = fma(-t, y, 1.0);
+    const double t = x * y;               // ~ sqrt(x)
+    const double e = fma(-t, y, 1.0);     // 1 - x y^2
     const double p = fma(e, 0.375, 0.5);
-    const double ye = y * e;
-    const double y1 = fma(ye, p, y);
-    return x * y1;
+    return fma(t * e, p, t);              // t (1 + e/2 + 3 e^2/8)
 }
 
 // pair term of the exponent at distance r, with the system's cut rule
@@ -88,8 +91,8 @@ __device__ __forceinline__ double pair_u(const SysDev& s, const double2* __restr
         if (r >= s.r_tail) return fma(s.u_lin, r, s.u_const); // const + linear tails, HeDrop.cpp:732-737
         r -= s.r0;
     }
-    // floor(r * inv) via the rounding constant; the integer sits in the low word
-    const double y = fma(r, UNIFORM ? s.inv_h : s.inv_cell, -0.5) + kMagic;
+    // floor(r * inv) via the rounding constant, added with round-down in the same FMA; the integer sits in the low word
+    const double y = __fma_rd(r, UNIFORM ? s.inv_h : s.inv_cell, kMagic);
     const int c = __double2loint(y);
     double t;
     int j;
