@@ -195,6 +195,32 @@ int tdvmc_gpu_accumulate_fixed(tdvmc_gpu_handle* h, const double* O, const doubl
 int tdvmc_gpu_proposals(tdvmc_gpu_handle* h, int32_t global_walker, int64_t first_step, int32_t n, int32_t* particle,
                         double* disp, double* log_u);
 
+/* ---- additional observables: g(r) and S(k) of the bulk spline systems ----
+ * Replaces IPhysicalSystem::CalculateAdditionalSystemProperties (BosonsBulk.cpp:474-520,
+ * NUBosonsBulkPB.cpp:597-639) and the driver loop around it (src/TDVMC.cpp:1332-1388, 1438-1444).
+ * The description is data the reference's InitSystem() builds (BosonsBulk.cpp:124-153). */
+typedef struct tdvmc_observable_desc
+{
+    int32_t gr_count;          /* pairDistribution.grid.count (Grid.cpp:21; 0: no g(r)) */
+    int32_t n_shells;          /* numOfkValues (BosonsBulk.cpp:55; 0: no S(k)) */
+    double gr_spacing;         /* pairDistribution.grid.spacing */
+    double gr_max;             /* pairDistribution.grid.max */
+    double gr_weight;          /* per pair: DIM/(N-1) (BosonsBulk.cpp:481) or 1 (NUBosonsBulkPB.cpp:611) */
+    const double* gr_scaling;  /* [gr_count] scalingGrid (ObservableVsOnGridWithScaling.cpp:19-44) */
+    const int32_t* shell_ptr;  /* [n_shells+1] first wave vector of every shell */
+    const double* kvec;        /* [shell_ptr[n_shells]][3] kValues, already times 2 pi / LBOX (BosonsBulk.cpp:127-137) */
+} tdvmc_observable_desc;
+/* sys->CalculateAdditionalSystemProperties(R, ...) for n_cfg caller-given configurations R[n_cfg][N][3]:
+ * gr[n_cfg][gr_count] (pairDistribution values), sk[n_cfg][n_shells] (structureFactor values). */
+int tdvmc_gpu_observables_fixed(tdvmc_gpu_handle* h, const tdvmc_observable_desc* od, const double* R, int32_t n_cfg,
+                                double* gr, double* sk);
+/* ParallelCalculateAdditionalSystemProperties (src/TDVMC.cpp:1438-1444): n_init steps
+ * (MC_NADDITIONALINITIALIZATIONSTEPS), then n_samples x (n_therm steps + observables) per resident walker;
+ * gr[gr_count], sk[n_shells] = mean over samples, walkers and ranks (additionalObservablesMean after
+ * MPIMethods::ReduceToAverage); identical on every rank. */
+int tdvmc_gpu_sample_observables(tdvmc_gpu_handle* h, const tdvmc_observable_desc* od, int32_t n_samples, int32_t n_therm,
+                                 int32_t n_init, double* gr, double* sk);
+
 /* ---- measurement hooks ---- */
 enum tdvmc_kernel_id
 {

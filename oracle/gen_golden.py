@@ -302,6 +302,40 @@ def gen_nubosonsbulkpb_full():
               default_moves(R1, L, rng), keep_tables="subset", subset=(0, 9, 863, 1727))
 
 
+def gen_observables():
+    """g(r) and S(k) (CalculateAdditionalSystemProperties) of stored configurations, and the reference's own sampled
+    means (src/TDVMC.cpp:1332-1388) for a statistical check.  Configurations and parameters come from the evaluation
+    fixtures, so the observable fixtures stay small."""
+    def one(name, src, system, extra_scal, mc):
+        g = np.load(os.path.join(GOLDEN, src + ".npz"))
+        scal = dict(N=int(g["N"]), LBOX=float(g["LBOX"]), N_PARAM=int(g["N_PARAM"]), time=float(g["time"]),
+                    phiR=float(g["phiR"]), phiI=float(g["phiI"]), **extra_scal, **mc)
+        arr = dict(R=g["R"], uR=g["uR"], uI=g["uI"], SYSTEM_PARAMS=g["SYSTEM_PARAMS"])
+        if "NURBS_GRID" in g.files:
+            arr["NURBS_GRID"] = g["NURBS_GRID"]
+        with tempfile.TemporaryDirectory() as td:
+            cp, op = os.path.join(td, "case.txt"), os.path.join(td, "out.txt")
+            write_case(cp, system, scal, arr)
+            run("obs", cp, op)
+            d = parse_dump(op)
+        out = {"source": np.array(src), "system": np.array(system), **{k: np.asarray(v) for k, v in d.items()}}
+        for k, v in mc.items():
+            out[k] = np.array(v)
+        # pair weight: BosonsBulk.cpp:481 (1/(N-1)*DIM), NUBosonsBulkPB.cpp:611 (1)
+        out["gr_weight"] = np.array(1.0 / float(scal["N"] - 1) * 3 if system == "BosonsBulk" else 1.0)
+        out["GR_BIN_COUNT"] = np.array(extra_scal["GR_BIN_COUNT"])
+        out["N"], out["LBOX"] = np.array(scal["N"]), np.array(scal["LBOX"])
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+        print(f"{name}: gr_count={int(d['gr_count'])} shells={len(d['k_shell_sizes'])} "
+              f"kvecs={int(np.sum(d['k_shell_sizes']))} sk[:3]={d['sk_fixed'][:3]}")
+
+    one("bosonsbulk_n64_obs", "bosonsbulk_n64_equil", "BosonsBulk", dict(GR_BIN_COUNT=50),
+        dict(MC_STEP=0.4, MC_NADDITIONALSTEPS=4000, MC_NADDITIONALTHERMSTEPS=64, MC_NADDITIONALINITIALIZATIONSTEPS=6400, seed=5))
+    one("bosonsbulk_n343_obs", "bosonsbulk_n343_equil", "BosonsBulk", dict(GR_BIN_COUNT=100), {})
+    one("nubosonsbulkpb_n216_obs", "nubosonsbulkpb_n216_equil", "NUBosonsBulkPB", dict(GR_BIN_COUNT=50, USE_NURBS=1),
+        dict(MC_STEP=0.5, MC_NADDITIONALSTEPS=1500, MC_NADDITIONALTHERMSTEPS=216, MC_NADDITIONALINITIALIZATIONSTEPS=4320, seed=6))
+
+
 def hebulk_drift(d, uR, uI):
     """Drift from the REFERENCE's HeBulk tables with its parameter map (HeBulk.cpp:319-356), long double."""
     sD = d["sD"].astype(np.longdouble)
@@ -529,7 +563,8 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     if not os.path.exists(HARNESS):
         sys.exit("build the oracle first: make -C oracle/ref_build")
-    which = sys.argv[1:] or ["min_image", "bosonsbulk", "bosonsbulk_mc", "nubosonsbulkpb", "hebulk", "hedrop", "mixture"]
+    which = sys.argv[1:] or ["min_image", "bosonsbulk", "bosonsbulk_mc", "nubosonsbulkpb", "nubosonsbulkpb_full", "hebulk", "hedrop",
+                             "mixture", "observables"]
     for w in which:
         globals()["gen_" + w]()
 

@@ -472,16 +472,73 @@ int ModeNic(const std::string& in, const std::string& out)
 
 } // namespace
 
+// Additional observables (BosonsBulk.cpp:474-520, NUBosonsBulkPB.cpp:597-639): g(r) and S(k) of the case's
+// configuration, then the reference's own sampling loop for them (src/TDVMC.cpp:1332-1388) with the
+// MC_NADDITIONAL* counts of the case.
+template <class S>
+void DumpObservableSetup(Dump& d, S* s)
+{
+    d.scalar("gr_spacing", s->pairDistribution.grid.spacing);
+    d.scalar("gr_max", s->pairDistribution.grid.max);
+    d.scalar("gr_count", (double)s->pairDistribution.grid.count);
+    d.vec("gr_scaling", s->pairDistribution.scalingGrid);
+    d.vec("gr_fixed", s->pairDistribution.observablesV[0].values);
+    d.vec("sk_fixed", s->structureFactor.observablesV[0].values);
+    d.vec("k_norms", s->kNorms);
+    std::vector<double> flat, sizes;
+    for (int k = 0; k < s->numOfkValues; k++)
+    {
+        sizes.push_back((double)s->kValues[k].size());
+        for (auto& v : s->kValues[k])
+            for (double x : v) flat.push_back(x);
+    }
+    d.vec("k_shell_sizes", sizes);
+    d.vec("k_vectors", flat);
+}
+
+int ModeObs(const Case& c, const std::string& out)
+{
+    SetupReference(c);
+    Dump d(out);
+    sys->CalculateWavefunction(R, uR, uI, phiR, phiI);
+    sys->CalculateAdditionalSystemProperties(R, uR, uI, phiR, phiI);
+    if (auto s = dynamic_cast<PhysicalSystems::BosonsBulk*>(sys)) DumpObservableSetup(d, s);
+    else if (auto s = dynamic_cast<PhysicalSystems::NUBosonsBulkPB*>(sys)) DumpObservableSetup(d, s);
+    else
+    {
+        std::cerr << "obs: system without g(r)/S(k) observables" << std::endl;
+        return 2;
+    }
+    MC_NADDITIONALSTEPS = c.i("MC_NADDITIONALSTEPS", 0);
+    MC_NADDITIONALTHERMSTEPS = c.i("MC_NADDITIONALTHERMSTEPS", 1);
+    MC_NADDITIONALINITIALIZATIONSTEPS = c.i("MC_NADDITIONALINITIALIZATIONSTEPS", 0);
+    mc_nadditionalsteps = MC_NADDITIONALSTEPS;
+    if (MC_NADDITIONALSTEPS > 0)
+    {
+        generator = std::mt19937_64((unsigned long long)c.i("seed", 1));
+        nTrials = 0;
+        nAcceptances = 0;
+        CalculateAdditionalSystemProperties(R, uR, uI, phiR, phiI);
+        auto gr = dynamic_cast<Observables::ObservableVsOnGrid*>(additionalObservablesMean.observables[0]);
+        auto sk = dynamic_cast<Observables::ObservableVsOnGrid*>(additionalObservablesMean.observables[1]);
+        d.vec("gr_mean", gr->observablesV[0].values);
+        d.vec("sk_mean", sk->observablesV[0].values);
+        d.scalar("acceptance", (double)nAcceptances / (double)nTrials);
+    }
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
     if (argc < 3)
     {
-        std::cerr << "usage: ref_harness eval|mc <case> <out> | bench <case> | nic <in> <out>" << std::endl;
+        std::cerr << "usage: ref_harness eval|mc|obs <case> <out> | bench <case> | nic <in> <out>" << std::endl;
         return 2;
     }
     std::string mode = argv[1];
     if (mode == "eval" && argc >= 4) return ModeEval(ReadCase(argv[2]), argv[3]);
     if (mode == "mc" && argc >= 4) return ModeMC(ReadCase(argv[2]), argv[3], false);
+    if (mode == "obs" && argc >= 4) return ModeObs(ReadCase(argv[2]), argv[3]);
     if (mode == "bench") return ModeMC(ReadCase(argv[2]), "", true);
     if (mode == "nic" && argc >= 4) return ModeNic(argv[2], argv[3]);
     std::cerr << "bad arguments" << std::endl;

@@ -384,3 +384,43 @@ int64_t oracle_sample_walker(const oracle_system* s, double* R, const double* uR
     free(sD2);
     return accepted;
 }
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Additional observables: BosonsBulk.cpp:474-520, NUBosonsBulkPB.cpp:597-639
+ * ---------------------------------------------------------------------------------------------- */
+void oracle_observables(double lbox, int n_particles, const double* R, int gr_count, double gr_spacing, double gr_max,
+                        double gr_weight, const double* gr_scaling, int n_shells, const int32_t* shell_ptr,
+                        const double* kvec, double* gr, double* sk)
+{
+    const int N = n_particles;
+    for (int b = 0; b < gr_count; b++) gr[b] = 0.0;
+    for (int i = 0; i < N; i++)
+    {
+        for (int j = 0; j < i; j++)
+        {
+            double vec[3];
+            const double r = oracle_min_image(lbox, 3, R + 3 * i, R + 3 * j, vec); /* BosonsBulk.cpp:486 */
+            if (r < gr_max)
+            {
+                const int bin = (int)floor(r / gr_spacing); /* Grid.cpp:58-59 */
+                if (bin < gr_count) gr[bin] += gr_weight / gr_scaling[bin];
+            }
+        }
+    }
+    for (int k = 0; k < n_shells; k++)
+    {
+        double c = 0.0, s = 0.0;
+        for (int i = 0; i < N; i++) /* the reference's loop order is i, k, kn; each shell's sum sees i outermost */
+        {
+            for (int q = shell_ptr[k]; q < shell_ptr[k + 1]; q++)
+            {
+                const double* kv = kvec + 3 * q;
+                const double arg = kv[0] * R[3 * i] + kv[1] * R[3 * i + 1] + kv[2] * R[3 * i + 2];
+                c += cos(arg);
+                s += sin(arg);
+            }
+        }
+        sk[k] = (c * c + s * s) / ((double)(N * (shell_ptr[k + 1] - shell_ptr[k])));
+    }
+}

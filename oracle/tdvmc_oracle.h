@@ -113,6 +113,17 @@ int64_t oracle_sample_walker(const oracle_system* s, double* R, const double* uR
 extern "C" {
 #endif
 
+/* BosonsBulk.cpp:474-520 / NUBosonsBulkPB.cpp:597-639 (CalculateAdditionalSystemProperties) for one configuration:
+ *   gr[bin] += weight / scaling[bin] for every pair i > j with r < gr_max, bin = floor(r / spacing)
+ *              (Grid.cpp:52-61, ObservableVsOnGridWithScaling.cpp:47-52); pairs whose bin falls beyond gr_count
+ *              (possible because count = (max-min)/spacing truncates, Grid.cpp:21) are dropped - the reference
+ *              writes them past the end of its vector;
+ *   sk[k]   = ((sum_{i,kn} cos k_kn.R_i)^2 + (sum_{i,kn} sin k_kn.R_i)^2) / (N n_k).
+ * kvec holds the wave vectors already multiplied by 2 pi / L (BosonsBulk.cpp:127-137), shell by shell. */
+void oracle_observables(double lbox, int n_particles, const double* R, int gr_count, double gr_spacing, double gr_max,
+                        double gr_weight, const double* gr_scaling, int n_shells, const int32_t* shell_ptr,
+                        const double* kvec, double* gr, double* sk);
+
 typedef struct oracle_he
 {
     int32_t n_particles, n_params, n_splines, n_short; /* n_short: numberOfShortSplines (HeBulk: = n_splines) */

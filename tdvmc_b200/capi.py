@@ -44,6 +44,12 @@ class Estimators(C.Structure):
                 ("n_acceptances", C.c_int64), ("n_trials", C.c_int64), ("n_samples", C.c_int64)]
 
 
+class ObservableDesc(C.Structure):
+    """tdvmc_observable_desc"""
+    _fields_ = [("gr_count", C.c_int32), ("n_shells", C.c_int32), ("gr_spacing", C.c_double), ("gr_max", C.c_double),
+                ("gr_weight", C.c_double), ("gr_scaling", dp), ("shell_ptr", ip), ("kvec", dp)]
+
+
 # every symbol include/tdvmc_gpu.h declares: (name, restype, argtypes)
 _VP = C.c_void_p
 SYMBOLS = [
@@ -69,6 +75,8 @@ SYMBOLS = [
     ("tdvmc_gpu_min_image", C.c_int, [_VP, C.c_double, dp, dp, C.c_int32, dp, dp]),
     ("tdvmc_gpu_accumulate_fixed", C.c_int, [_VP, dp, dp, dp, C.c_int64, dp, dp, dp, dp]),
     ("tdvmc_gpu_proposals", C.c_int, [_VP, C.c_int32, C.c_int64, C.c_int32, ip, dp, dp]),
+    ("tdvmc_gpu_observables_fixed", C.c_int, [_VP, C.POINTER(ObservableDesc), dp, C.c_int32, dp, dp]),
+    ("tdvmc_gpu_sample_observables", C.c_int, [_VP, C.POINTER(ObservableDesc), C.c_int32, C.c_int32, C.c_int32, dp, dp]),
     ("tdvmc_gpu_profile", C.c_int, [_VP, C.c_int32, C.c_int32]),
     ("tdvmc_gpu_kernel_stats", C.c_int, [_VP, C.c_int32, C.POINTER(C.c_int64), dp]),
     ("tdvmc_gpu_synchronize", C.c_int, [_VP]),
@@ -236,6 +244,32 @@ class Handle:
         d = np.empty(len(moves))
         self._ck(self.lib.tdvmc_gpu_quotient_fixed(self.h, _d(R), _d(moves), len(moves), _d(q), _d(d)), "quotient_fixed")
         return q, d
+
+    @staticmethod
+    def _observable_desc(obs):
+        keep = [np.ascontiguousarray(obs.gr_scaling, np.float64), np.ascontiguousarray(obs.shell_ptr, np.int32),
+                np.ascontiguousarray(obs.kvec, np.float64)]
+        od = ObservableDesc(int(obs.gr_count), int(obs.n_shells), float(obs.gr_spacing), float(obs.gr_max), float(obs.gr_weight),
+                            _d(keep[0]), keep[1].ctypes.data_as(ip), _d(keep[2]))
+        return od, keep
+
+    def observables_fixed(self, obs, R):
+        """g(r) and S(k) of given configurations; obs: tdvmc_b200.observables.ObservableSpec."""
+        R = np.ascontiguousarray(R, np.float64).reshape(-1, self.N, 3)
+        od, keep = self._observable_desc(obs)
+        gr = np.empty((len(R), obs.gr_count))
+        sk = np.empty((len(R), obs.n_shells))
+        self._ck(self.lib.tdvmc_gpu_observables_fixed(self.h, C.byref(od), _d(R), len(R), _d(gr), _d(sk)), "observables_fixed")
+        return gr, sk
+
+    def sample_observables(self, obs, n_samples, n_therm, n_init):
+        """The reference's end-of-run observable pass over the resident walkers: mean g(r), S(k)."""
+        od, keep = self._observable_desc(obs)
+        gr = np.empty(obs.gr_count)
+        sk = np.empty(obs.n_shells)
+        self._ck(self.lib.tdvmc_gpu_sample_observables(self.h, C.byref(od), int(n_samples), int(n_therm), int(n_init), _d(gr), _d(sk)),
+                 "sample_observables")
+        return gr, sk
 
     def tables_fixed(self, R):
         R = np.ascontiguousarray(R, np.float64).reshape(self.N, 3)

@@ -1273,6 +1273,151 @@ int tdvmc_gpu_accumulate_fixed(tdvmc_gpu_handle* h, const double* O, const doubl
     return 0;
 }
 
+// ---- additional observables (observables.cu) ----
+namespace
+{
+struct ObsDevice
+{
+    DevBuf<int> shell_ptr;
+    DevBuf<double> kvec;
+    int n_kvec = 0;
+};
+
+int check_observable_desc(tdvmc_gpu_handle* h, const tdvmc_observable_desc* od)
+{
+    if (!od) return fail(h, "observables: null description");
+    if (h->kind == TDVMC_SYSTEM_MIXTURE) return fail(h, "observables: g(r)/S(k) are defined for the one-species systems");
+    if (od->gr_count < 0 || od->n_shells < 0 || (od->gr_count == 0 && od->n_shells == 0))
+        return fail(h, "observables: empty description");
+    if (od->gr_count > 0 && (!(od->gr_spacing > 0.0) || !(od->gr_max > 0.0) || !od->gr_scaling))
+        return fail(h, "observables: bad g(r) grid");
+    if (od->n_shells > 0)
+    {
+        if (!od->shell_ptr || !od->kvec || od->shell_ptr[0] != 0) return fail(h, "observables: bad wave-vector shells");
+        for (int k = 0; k < od->n_shells; k++)
+            if (od->shell_ptr[k + 1] <= od->shell_ptr[k]) return fail(h, "observables: empty wave-vector shell");
+    }
+    return 0;
+}
+
+int upload_observable_desc(tdvmc_gpu_handle* h, const tdvmc_observable_desc* od, ObsDevice& d)
+{
+    d.n_kvec = od->n_shells > 0 ? od->shell_ptr[od->n_shells] : 0;
+    CK(d.shell_ptr.alloc((size_t)od->n_shells + 1));
+    CK(d.kvec.alloc((size_t)3 * d.n_kvec + 1));
+    if (od->n_shells > 0)
+    {
+        CK(cudaMemcpyAsync(d.shell_ptr.p, od->shell_ptr, ((size_t)od->n_shells + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(d.kvec.p, od->kvec, (size_t)3 * d.n_kvec * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+    return 0;
+}
+
+ObsArgs make_obs_args(tdvmc_gpu_handle* h, const tdvmc_observable_desc* od, const ObsDevice& d)
+{
+    ObsArgs a;
+    memset(&a, 0, sizeof(a));
+    a.s = h->sysdev();
+    a.gr_count = od->gr_count;
+    a.gr_spacing = od->gr_spacing;
+    a.gr_max = od->gr_max;
+    a.n_shells = od->n_shells;
+    a.n_kvec = d.n_kvec;
+    a.shell_ptr = d.shell_ptr.p;
+    a.kvec = d.kvec.p;
+    return a;
+}
+} // namespace
+
+int tdvmc_gpu_observables_fixed(tdvmc_gpu_handle* h, const tdvmc_observable_desc* od, const double* R, int32_t n_cfg, double* gr,
+                                double* sk)
+{
+    if (!h || !R || n_cfg < 1) return h ? fail(h, "observables_fixed: bad arguments") : -1;
+    if (int rc = check_observable_desc(h, od)) return rc;
+    CK(cudaSetDevice(h->device));
+    ObsDevice d;
+    if (int rc = upload_observable_desc(h, od, d)) return rc;
+    DevBuf<double> aos, pos, skr;
+    DevBuf<unsigned long long> grr;
+    CK(aos.alloc((size_t)n_cfg * h->N * 3));
+    CK(pos.alloc((size_t)n_cfg * 3 * h->Np));
+    CK(grr.alloc((size_t)n_cfg * od->gr_count + 1));
+    CK(skr.alloc((size_t)n_cfg * od->n_shells + 1));
+    CK(cudaMemsetAsync(pos.p, 0, pos.n * sizeof(double), h->stream));
+    CK(cudaMemcpyAsync(aos.p, R, aos.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(launch_transpose_in(aos.p, pos.p, n_cfg, h->N, h->Np, h->stream));
+    ObsArgs a = make_obs_args(h, od, d);
+    a.pos = pos.p;
+    a.n_cfg = n_cfg;
+    a.accumulate = 0;
+    a.gr_rows = grr.p;
+    a.sk_rows = skr.p;
+    {
+        Timed t(h, TDVMC_KERNEL_OTHER);
+        CK(launch_observables(a, h->stream));
+    }
+    std::vector<unsigned long long> cnt((size_t)n_cfg * od->gr_count);
+    if (!cnt.empty()) CK(cudaMemcpyAsync(cnt.data(), grr.p, cnt.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    if (sk && od->n_shells > 0)
+        CK(cudaMemcpyAsync(sk, skr.p, (size_t)n_cfg * od->n_shells * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (gr)
+        for (int c = 0; c < n_cfg; c++)
+            for (int b = 0; b < od->gr_count; b++) // ObservableVsOnGridWithScaling.cpp:51, once per counted pair
+                gr[(size_t)c * od->gr_count + b] = (double)cnt[(size_t)c * od->gr_count + b] * (od->gr_weight / od->gr_scaling[b]);
+    return 0;
+}
+
+int tdvmc_gpu_sample_observables(tdvmc_gpu_handle* h, const tdvmc_observable_desc* od, int32_t n_samples, int32_t n_therm,
+                                 int32_t n_init, double* gr, double* sk)
+{
+    if (!h) return -1;
+    if (int rc = need_params(h)) return rc;
+    if (int rc = check_observable_desc(h, od)) return rc;
+    if (n_samples < 1 || n_therm < 0 || n_init < 0) return fail(h, "sample_observables: bad step counts");
+    CK(cudaSetDevice(h->device));
+    ObsDevice d;
+    if (int rc = upload_observable_desc(h, od, d)) return rc;
+    DevBuf<double> skr, sum;
+    DevBuf<unsigned long long> grr;
+    const int ncol = od->gr_count + od->n_shells;
+    CK(grr.alloc((size_t)h->W * od->gr_count + 1));
+    CK(skr.alloc((size_t)h->W * od->n_shells + 1));
+    CK(sum.alloc((size_t)ncol + 1));
+    CK(cudaMemsetAsync(grr.p, 0, grr.n * sizeof(unsigned long long), h->stream));
+    CK(cudaMemsetAsync(skr.p, 0, skr.n * sizeof(double), h->stream));
+    ObsArgs a = make_obs_args(h, od, d);
+    a.pos = h->d_pos.p;
+    a.n_cfg = h->W;
+    a.accumulate = 1;
+    a.gr_rows = grr.p;
+    a.sk_rows = skr.p;
+    if (int rc = do_sweep(h, n_init)) return rc; // src/TDVMC.cpp:1338-1341
+    for (int m = 0; m < n_samples; m++)
+    {
+        if (int rc = do_sweep(h, n_therm)) return rc; // :1344-1347
+        Timed t(h, TDVMC_KERNEL_OTHER);
+        CK(launch_observables(a, h->stream)); // :1349
+    }
+    CK(launch_obs_reduce(grr.p, skr.p, h->W, od->gr_count, od->n_shells, sum.p, h->stream));
+    const double n_local = (double)n_samples * (double)h->W;
+    CK(cudaMemcpyAsync(sum.p + ncol, &n_local, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (h->comm) // MPIMethods::ReduceToAverage(additionalObservablesMean), src/TDVMC.cpp:1443
+    {
+        int rc = g_nccl.AllReduce(sum.p, sum.p, (size_t)ncol + 1, kNcclDouble, kNcclSum, h->comm, h->stream);
+        if (rc != 0) return fail(h, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"), rc);
+    }
+    std::vector<double> hs((size_t)ncol + 1);
+    CK(cudaMemcpyAsync(hs.data(), sum.p, hs.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const double inv = 1.0 / hs[ncol]; // equal weights: the running mean of :1358-1361 and the mean over ranks
+    if (gr)
+        for (int b = 0; b < od->gr_count; b++) gr[b] = hs[b] * (od->gr_weight / od->gr_scaling[b]) * inv;
+    if (sk)
+        for (int k = 0; k < od->n_shells; k++) sk[k] = hs[od->gr_count + k] * inv;
+    return 0;
+}
+
 int tdvmc_gpu_proposals(tdvmc_gpu_handle* h, int32_t global_walker, int64_t first_step, int32_t n, int32_t* particle,
                         double* disp, double* log_u)
 {

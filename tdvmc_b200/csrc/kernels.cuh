@@ -119,6 +119,25 @@ cudaError_t launch_acc_finish(const AccFinishArgs& a, cudaStream_t st);
 
 // ---- small utilities (util.cu) ----
 cudaError_t launch_wrap(const SysDev& s, double* pos, int W, cudaStream_t st);
+// ---- additional observables g(r), S(k) (observables.cu) ----
+struct ObsArgs
+{
+    SysDev s;
+    const double* pos;            // [n_cfg][3][Np]
+    int n_cfg;
+    int accumulate;               // 1: add into the configuration's rows, 0: overwrite
+    int gr_count;
+    double gr_spacing, gr_max;
+    int n_shells, n_kvec;
+    const int* shell_ptr;         // [n_shells + 1]
+    const double* kvec;           // [n_kvec][3]
+    unsigned long long* gr_rows;  // [n_cfg][gr_count] pair counts
+    double* sk_rows;              // [n_cfg][n_shells]
+};
+cudaError_t launch_observables(const ObsArgs& a, cudaStream_t st);
+cudaError_t launch_obs_reduce(const unsigned long long* gr_rows, const double* sk_rows, int n_rows, int gr_count, int n_shells,
+                              double* out, cudaStream_t st);
+
 cudaError_t launch_min_image(const SysDev& s, double L, const double* a, const double* b, int n, double* norm, double* disp,
                              cudaStream_t st);
 cudaError_t launch_proposals(uint64_t seed, uint32_t walker, uint64_t first_step, int n, int n_particles, double mc_step,

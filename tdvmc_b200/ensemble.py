@@ -63,6 +63,15 @@ class GpuEnsembleSystem:
         self.handle.reevaluate_stored()
         return self._fetch()
 
+    def ParallelCalculateAdditionalSystemProperties(self, uR, uI, phiR, phiI, observables, MC_NADDITIONALSTEPS,
+                                                    MC_NADDITIONALTHERMSTEPS, MC_NADDITIONALINITIALIZATIONSTEPS, time=0.0):
+        """src/TDVMC.cpp:1438-1444: the end-of-run observable pass; returns the reference's additionalObservablesMean
+        as ``dict(pairDistribution=g(r), structureFactor=S(k))``; observables: tdvmc_b200.observables.ObservableSpec."""
+        self.handle.set_params(uR, uI, phiR, phiI, time)
+        gr, sk = self.handle.sample_observables(observables, MC_NADDITIONALSTEPS, MC_NADDITIONALTHERMSTEPS,
+                                                MC_NADDITIONALINITIALIZATIONSTEPS)
+        return dict(pairDistribution=gr, structureFactor=sk)
+
     def GetExponent(self):
         return self.handle.last_exponent()
 

@@ -342,6 +342,49 @@ Estimators GpuEnsembleSystem::ParallelUpdateExpectationValuesForGivenSamples(con
     return Fetch();
 }
 
+ObservableTables MakePairDistributionGrid(double rMax, int numOfPairDistributionValues, double weight)
+{
+    ObservableTables t;
+    t.grMax = rMax;
+    t.grSpacing = rMax / numOfPairDistributionValues;
+    t.grCount = (int)((rMax - 0.0) / t.grSpacing); // Grid.cpp:21 (truncates)
+    t.grWeight = weight;
+    t.grScaling.assign(t.grCount, 0.0);
+    for (int i = 0; i < t.grCount; i++) t.grScaling[i] = 4.0 * M_PI * std::pow(t.grSpacing * (i + 1), 3.0) / 3.0;
+    for (int i = t.grCount - 1; i > 0; i--) t.grScaling[i] = t.grScaling[i] - t.grScaling[i - 1];
+    return t;
+}
+
+AdditionalObservables GpuEnsembleSystem::ParallelCalculateAdditionalSystemProperties(
+    const std::vector<double>& uR, const std::vector<double>& uI, double phiR, double phiI, const ObservableTables& obs,
+    int MC_NADDITIONALSTEPS, int MC_NADDITIONALTHERMSTEPS, int MC_NADDITIONALINITIALIZATIONSTEPS, double time)
+{
+    Check(tdvmc_gpu_set_params(handle, uR.data(), uI.data(), phiR, phiI, time), "set_params");
+    std::vector<int32_t> ptr(1, 0);
+    std::vector<double> kv;
+    for (const auto& shell : obs.kValues)
+    {
+        for (const auto& k : shell) kv.insert(kv.end(), k.begin(), k.begin() + 3);
+        ptr.push_back((int32_t)(kv.size() / 3));
+    }
+    tdvmc_observable_desc od;
+    od.gr_count = obs.grCount;
+    od.n_shells = (int32_t)obs.kValues.size();
+    od.gr_spacing = obs.grSpacing;
+    od.gr_max = obs.grMax;
+    od.gr_weight = obs.grWeight;
+    od.gr_scaling = obs.grScaling.data();
+    od.shell_ptr = ptr.data();
+    od.kvec = kv.data();
+    AdditionalObservables out;
+    out.pairDistribution.assign(od.gr_count, 0.0);
+    out.structureFactor.assign(od.n_shells, 0.0);
+    Check(tdvmc_gpu_sample_observables(handle, &od, MC_NADDITIONALSTEPS, MC_NADDITIONALTHERMSTEPS, MC_NADDITIONALINITIALIZATIONSTEPS,
+                                       out.pairDistribution.data(), out.structureFactor.data()),
+          "sample_observables");
+    return out;
+}
+
 double GpuEnsembleSystem::GetExponent()
 {
     double x = 0.0;

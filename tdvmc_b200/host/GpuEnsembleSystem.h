@@ -80,6 +80,23 @@ SystemTables MakeBosonMixtureClusterTables(int N, const std::vector<std::vector<
                                            const std::vector<double>& massPerParticle,
                                            const std::vector<MixturePairType>& pairTypes, int numOfOtherExpectationValues);
 
+// g(r) / S(k) description: what BosonsBulk::InitSystem builds (BosonsBulk.cpp:124-153).
+struct ObservableTables
+{
+    int grCount = 0;                 // pairDistribution.grid.count
+    double grSpacing = 0, grMax = 0; // pairDistribution.grid.spacing / .max
+    double grWeight = 1;             // DIM/(N-1) (BosonsBulk.cpp:481) or 1 (NUBosonsBulkPB.cpp:611)
+    std::vector<double> grScaling;   // pairDistribution.scalingGrid
+    std::vector<std::vector<std::vector<double> > > kValues; // [numOfkValues][kn][3], already times 2 pi / LBOX
+};
+// Grid::Init + InitScaling for the pair distribution (Grid.cpp:16-31, ObservableVsOnGridWithScaling.cpp:19-44)
+ObservableTables MakePairDistributionGrid(double rMax, int numOfPairDistributionValues, double weight);
+
+struct AdditionalObservables
+{
+    std::vector<double> pairDistribution, structureFactor;
+};
+
 // The seven estimator arrays under the reference's global names (src/TDVMC.cpp:147-153).
 struct Estimators
 {
@@ -127,6 +144,12 @@ public:
     Estimators ParallelUpdateExpectationValuesForGivenSamples(const std::vector<double>& uR, const std::vector<double>& uI,
                                                               double phiR, double phiI, double time);
     double GetExponent();
+    // ParallelCalculateAdditionalSystemProperties (src/TDVMC.cpp:1438-1444) for the bulk spline systems: the mean
+    // pairDistribution / structureFactor values (additionalObservablesMean.observables[0], [1]) over samples, walkers, ranks.
+    AdditionalObservables ParallelCalculateAdditionalSystemProperties(const std::vector<double>& uR, const std::vector<double>& uI,
+                                                                      double phiR, double phiI, const ObservableTables& obs,
+                                                                      int MC_NADDITIONALSTEPS, int MC_NADDITIONALTHERMSTEPS,
+                                                                      int MC_NADDITIONALINITIALIZATIONSTEPS, double time);
 
 private:
     void Check(int rc, const char* what);

@@ -360,6 +360,20 @@ class OracleMix:
 OracleHeBulk = OracleHe
 
 
+def oracle_observables(lbox, R, obs):
+    """oracle_observables (oracle/tdvmc_oracle.c) for one configuration; obs: tdvmc_b200.observables.ObservableSpec."""
+    R = np.ascontiguousarray(R, np.float64)
+    sc = np.ascontiguousarray(obs.gr_scaling, np.float64)
+    ptr = np.ascontiguousarray(obs.shell_ptr, np.int32)
+    kv = np.ascontiguousarray(obs.kvec, np.float64)
+    gr = np.zeros(obs.gr_count)
+    sk = np.zeros(obs.n_shells)
+    lib().oracle_observables(C.c_double(lbox), C.c_int(R.shape[0]), _d(R), C.c_int(obs.gr_count), C.c_double(obs.gr_spacing),
+                             C.c_double(obs.gr_max), C.c_double(obs.gr_weight), _d(sc), C.c_int(obs.n_shells),
+                             ptr.ctypes.data_as(ip), _d(kv), _d(gr), _d(sk))
+    return gr, sk
+
+
 def make_oracle(spec, time=0.0):
     from tdvmc_b200 import systems
 

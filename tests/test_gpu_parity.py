@@ -545,6 +545,42 @@ def test_hebulk_statistics_match_reference_sampler(capi, golden):
     h.close()
 
 
+@pytest.mark.parametrize("name", ["hebulk_n64_equil", "hedrop_n6_equil"])
+def test_stored_sample_reevaluation_he_systems(capi, golden, name):
+    """UpdateExpectationValuesForGivenSamples (src/TDVMC.cpp:1222-1303) for the He systems: stored configurations,
+    re-evaluated at unchanged parameters (idempotent) and at new parameters (equals a fresh evaluation of them)."""
+    g = golden(name)
+    W, n_samples = 6, 3
+    spec, h = make_handle(capi, g, n_walkers=W, seed=21, mc_step=float(g["MC_STEP"]) if "MC_STEP" in g else 0.3,
+                          max_samples=n_samples, keep_sample_positions=True)
+    h.set_positions(np.stack([g["R"] + 0.001 * w for w in range(W)]))
+    h.sample_and_accumulate(n_samples, 40, 20)
+    a = h.allreduce_and_fetch()
+    h.reevaluate_stored()
+    b = h.allreduce_and_fetch()
+    for k in ("O", "S", "OER", "OEI", "e_r", "e_i", "other"):
+        assert rel(b[k], a[k]) < 1e-13, k
+    u2, ui2 = g["uR"] * 0.97, g["uI"] + 0.01
+    h.set_params(u2, ui2, float(g["phiR"]), float(g["phiI"]), float(g["time"]))
+    h.reevaluate_stored()
+    c = h.allreduce_and_fetch()
+    # the last stored sample of every walker is its current position: compare its share through a second handle
+    Rf = h.get_positions()
+    ev = h.evaluate_fixed(Rf)
+    h2 = capi.Handle(spec, W, seed=21, max_samples=1)
+    h2.set_params(u2, ui2, float(g["phiR"]), float(g["phiI"]), float(g["time"]))
+    h2.set_positions(Rf)
+    h2.sample_and_accumulate(1, 0, 0)                                 # zero moves: evaluates the given positions
+    d = h2.allreduce_and_fetch()
+    assert abs(d["e_r"][0] - ev["e_r"].mean()) < 1e-12 * abs(d["e_r"][0])
+    assert abs(c["e_r"][0] - a["e_r"][0]) > 1e-9 * abs(a["e_r"][0])  # parameters did change the energy
+    P = spec.n_params
+    free = np.arange(P - 1) if name.startswith("hebulk") else np.arange(P)   # HeBulk's last operator is the constant 1
+    assert rel(c["O"][free], a["O"][free]) < 1e-13                            # O_k do not depend on the parameters
+    h.close()
+    h2.close()
+
+
 # ---------------------------------------------------------------------------------------------------
 # HeDrop (BASELINE configs[0], config/drop_6.config): open boundary, two spline grids, const/linear tails, LJ
 # ---------------------------------------------------------------------------------------------------
@@ -673,4 +709,80 @@ def test_mixture_chain_estimators_and_com(capi, golden):
     com = (Rb * m[None, :, None]).sum(axis=1) / m.sum()
     assert np.max(np.abs(Ra - (Rb - com[:, None, :]))) < 1e-12
     assert np.allclose(com[0], o.center_of_mass(Rb[0]), rtol=1e-14, atol=1e-14)
+    h.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# additional observables g(r), S(k): CalculateAdditionalSystemProperties (BosonsBulk.cpp:474-520,
+# NUBosonsBulkPB.cpp:597-639) and the driver loop around it (src/TDVMC.cpp:1332-1388, 1438-1444)
+# ---------------------------------------------------------------------------------------------------
+OBS_CASES = ["bosonsbulk_n64_obs", "bosonsbulk_n343_obs", "nubosonsbulkpb_n216_obs"]
+
+
+@pytest.mark.parametrize("name", OBS_CASES)
+def test_observables_fixed_match_reference(capi, golden, name):
+    from tdvmc_b200 import observables
+    g = golden(name)
+    src = golden(str(g["source"]))
+    obs = observables.from_golden(g)
+    spec, h = make_handle(capi, src)
+    R = np.stack([src["R"], src["R"][::-1].copy()])          # particle order does not matter
+    gr, sk = h.observables_fixed(obs, R)
+    for c in range(2):
+        assert np.max(np.abs(gr[c] - g["gr_fixed"])) <= 1e-12 * np.max(np.abs(g["gr_fixed"]))
+        assert np.max(np.abs(sk[c] - g["sk_fixed"])) <= 1e-10 * np.max(np.abs(g["sk_fixed"]))
+    h.close()
+
+
+def test_sample_observables_replay_oracle(capi, golden):
+    """The observable pass over the resident walkers equals the oracle chain + oracle observables, sample by sample."""
+    from oracle_lib import oracle_observables
+    from tdvmc_b200 import observables
+    g = golden("bosonsbulk_n64_obs")
+    src = golden(str(g["source"]))
+    obs = observables.from_golden(g)
+    W, seed, mc_step = 3, 31, 0.4
+    n_samples, n_therm, n_init = 4, 40, 25
+    spec, h = make_handle(capi, src, n_walkers=W, seed=seed, mc_step=mc_step)
+    o = Oracle(spec, time=float(src["time"]))
+    R0 = np.stack([src["R"] + 0.002 * w for w in range(W)])
+    h.set_positions(R0)
+    gr, sk = h.sample_observables(obs, n_samples, n_therm, n_init)
+    gr_ref, sk_ref = np.zeros(obs.gr_count), np.zeros(obs.n_shells)
+    for w in range(W):
+        R, step = R0[w].copy(), 0
+        R, _ = o.sweep(R, src["uR"], seed, w, step, n_init, mc_step)
+        step += n_init
+        for m in range(n_samples):
+            R, _ = o.sweep(R, src["uR"], seed, w, step, n_therm, mc_step)
+            step += n_therm
+            a, b = oracle_observables(spec.lbox, R, obs)
+            gr_ref += a
+            sk_ref += b
+    gr_ref /= W * n_samples
+    sk_ref /= W * n_samples
+    assert np.max(np.abs(gr - gr_ref)) <= 1e-12 * np.max(gr_ref)
+    assert np.max(np.abs(sk - sk_ref)) <= 1e-9 * np.max(sk_ref)
+    h.close()
+
+
+@pytest.mark.parametrize("name", ["bosonsbulk_n64_obs", "nubosonsbulkpb_n216_obs"])
+def test_sample_observables_statistics_match_reference(capi, golden, name):
+    """Mean g(r) and S(k) agree with the reference's own end-of-run pass (its sampler, its RNG) within error bars:
+    pair counts per bin are close to Poisson, |rho_k|^2 close to exponential; x4 for autocorrelation."""
+    from tdvmc_b200 import observables
+    g = golden(name)
+    src = golden(str(g["source"]))
+    obs = observables.from_golden(g)
+    W, n_samples = 256, 8
+    spec, h = make_handle(capi, src, n_walkers=W, seed=77, mc_step=float(g["MC_STEP"]))
+    h.set_positions(np.broadcast_to(src["R"], (W, spec.n_particles, 3)).copy())
+    gr, sk = h.sample_observables(obs, n_samples, int(g["MC_NADDITIONALTHERMSTEPS"]), int(g["MC_NADDITIONALINITIALIZATIONSTEPS"]))
+    n_ref, n_gpu = float(g["MC_NADDITIONALSTEPS"]) / 4.0, W * n_samples / 4.0
+    q = obs.gr_weight / obs.gr_scaling
+    sig_gr = np.sqrt(np.maximum(g["gr_mean"], q) * q * (1.0 / n_ref + 1.0 / n_gpu))
+    assert np.all(np.abs(gr - g["gr_mean"]) < 6.0 * sig_gr), np.max(np.abs(gr - g["gr_mean"]) / sig_gr)
+    n_k = np.diff(obs.shell_ptr)
+    sig_sk = np.maximum(g["sk_mean"], 0.05) * np.sqrt(1.0 / n_ref + 1.0 / n_gpu)
+    assert np.all(np.abs(sk - g["sk_mean"]) < 6.0 * sig_sk), np.max(np.abs(sk - g["sk_mean"]) / sig_sk)
     h.close()

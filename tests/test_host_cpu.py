@@ -41,6 +41,7 @@ def test_struct_layouts_match_header_sizes():
     # 8 int32 + 2 double + 6 pointers + 2 int32 ; uint32 + 5 int32 + uint64 + double ; 7 pointers + 3 int64
     assert C.sizeof(capi.SystemDesc) == 8 * 4 + 2 * 8 + 6 * 8 + 4 * 4 + 3 * 8
     assert C.sizeof(capi.MixtureDesc) == 2 * 4 + 7 * 8
+    assert C.sizeof(capi.ObservableDesc) == 2 * 4 + 3 * 8 + 3 * 8
     assert C.sizeof(capi.EnsembleDesc) == 6 * 4 + 8 + 8
     assert C.sizeof(capi.Estimators) == 7 * 8 + 3 * 8
 

@@ -195,3 +195,42 @@ def test_mixture_fixed_configuration_matches_reference(golden, name):
         q, en, _ = o.quotient(g["R"], int(m[0]), m[1:4], g["uR"])
         assert abs(en - en_ref) < 1e-12 * abs(en_ref)
         assert abs(q - q_ref) <= 1e-9 * abs(q_ref)
+
+
+# ---------------------------------------------------------------------------------------------------
+# additional observables g(r), S(k) (BosonsBulk.cpp:474-520, NUBosonsBulkPB.cpp:597-639)
+# ---------------------------------------------------------------------------------------------------
+OBS_CASES = ["bosonsbulk_n64_obs", "bosonsbulk_n343_obs", "nubosonsbulkpb_n216_obs"]
+
+
+@pytest.mark.parametrize("name", OBS_CASES)
+def test_observables_oracle_matches_reference(golden, name):
+    from oracle_lib import oracle_observables
+    from tdvmc_b200 import observables
+    g = golden(name)
+    src = golden(str(g["source"]))
+    obs = observables.from_golden(g)
+    gr, sk = oracle_observables(float(g["LBOX"]), src["R"], obs)
+    assert np.max(np.abs(gr - g["gr_fixed"])) <= 1e-12 * np.max(np.abs(g["gr_fixed"]))
+    assert np.max(np.abs(sk - g["sk_fixed"])) <= 1e-11 * np.max(np.abs(g["sk_fixed"]))
+    # every pair inside the grid is counted once: sum_b gr[b] scaling[b] / weight = number of pairs with r < max
+    # (minus those the reference drops past the end of its vector)
+    n_pairs = np.sum(gr * obs.gr_scaling) / obs.gr_weight
+    assert abs(n_pairs - round(n_pairs)) < 1e-6 and 0 < n_pairs <= int(g["N"]) * (int(g["N"]) - 1) / 2
+
+
+@pytest.mark.parametrize("name", OBS_CASES)
+def test_observable_grid_builder_matches_reference(golden, name):
+    """pair_distribution_grid / wave_vectors rebuild the reference's grid, shell volumes and scaled wave vectors."""
+    from tdvmc_b200 import observables
+    g = golden(name)
+    count, spacing, scaling = observables.pair_distribution_grid(float(g["gr_max"]), int(g["GR_BIN_COUNT"]) if str(g["system"]) == "BosonsBulk"
+                                                                 else int(g["gr_count"]))
+    assert count == int(g["gr_count"]) and spacing == float(g["gr_spacing"])
+    assert np.max(np.abs(scaling - g["gr_scaling"])) <= 1e-15 * np.max(g["gr_scaling"])
+    obs = observables.from_golden(g)
+    L = float(g["LBOX"])
+    ints = np.rint(obs.kvec * L / (2 * np.pi)).astype(int)
+    shells = [ints[obs.shell_ptr[k]:obs.shell_ptr[k + 1]].tolist() for k in range(obs.n_shells)]
+    ptr, kv = observables.wave_vectors(shells, L)
+    assert np.array_equal(ptr, obs.shell_ptr) and np.array_equal(kv, obs.kvec)
