@@ -1,0 +1,116 @@
+#!/usr/bin/env python3
+"""Throughput of the BASELINE configs that are parity cases rather than the headline (configs 1, 2, 4, 5),
+through the same C ABI as bench.py.  One JSON line per config: walker-steps/s and samples/s of a
+ParallelUpdateExpectationValues pass with the config's own MC_NTHERMSTEPS : 1 evaluation ratio, the share of the sweep and
+evaluation kernels, and the unmodified reference timed on ONE host core with the same counts (oracle/_ref/ref_harness).
+
+    python profiles/bench_configs.py [--configs 1,2,4,5] [--reps 3] > profiles/rNN_configs.jsonl
+
+Not a bench.py line: the headline metric is quoted on config 3 only.  The ensemble sizes follow SURVEY.md 8(d)
+(W = 2^20 / N for configs 1, 2, 5; W = 512 for config 4), samples per walker per pass are capped at 8."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tdvmc_b200 import capi, systems  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+
+# config file -> (fixture, system, MC_STEP, MC_NTHERMSTEPS, MC_NINITIALIZATIONSTEPS, walkers)
+CONFIGS = {
+    1: ("config/drop_6.config", "hedrop_n6_equil", "HeDrop", 0.5, 50, 1000, (1 << 20) // 6),
+    2: ("config/bulk_64.config", "hebulk_n64_equil", "HeBulk", 0.3, 100, 100, (1 << 20) // 64),
+    4: ("config/NUBosonsBulkPB3D.config", "nubosonsbulkpb_n1728_equil", "NUBosonsBulkPB", 0.5, 200, 400, 512),
+    5: ("config/He4He4Na.config", "mixture_he4he4na_equil", "BosonMixtureCluster", 4.0, 20, 1000, (1 << 20) // 3),
+}
+SAMPLES = 8
+
+
+def reference_one_core(g, system, mc_step, n_therm, n_init, n_samples):
+    """The unmodified reference, one walker on one core, same counts; returns (proposals/s, samples/s) or None."""
+    if not os.path.exists(HARNESS):
+        return None
+    scal = dict(N=int(g["N"]), DIM=3, LBOX=float(g["LBOX"]), N_PARAM=int(g["N_PARAM"]), MC_STEP=mc_step, MC_NSTEPS=n_samples,
+                MC_NTHERMSTEPS=n_therm, MC_NINITIALIZATIONSTEPS=n_init, seed=1, phiR=float(g["phiR"]), phiI=float(g["phiI"]))
+    arrays = dict(R=g["R"], uR=g["uR"], uI=g["uI"])
+    for key in ("SYSTEM_PARAMS", "NURBS_GRID", "PARTICLE_TYPES"):
+        if key in g.files and np.size(g[key]):
+            arrays[key] = g[key]
+    if "NURBS_GRID" in arrays:
+        scal["USE_NURBS"] = 1
+        scal["GR_BIN_COUNT"] = 400 if system == "BosonMixtureCluster" else len(g["other_expectation_values"]) - 9
+    with tempfile.TemporaryDirectory() as td:
+        case = os.path.join(td, "case.txt")
+        with open(case, "w") as f:
+            f.write(f"system {system}\nconfigdir {ROOT}/oracle/_ref/config/\n")
+            for k, v in scal.items():
+                f.write(f"{k} {v!r}\n")
+            for k, v in arrays.items():
+                f.write(k + " " + " ".join(repr(float(x)) for x in np.asarray(v).ravel()) + "\n")
+        r = subprocess.run([HARNESS, "bench", case], capture_output=True, text=True, cwd=td)
+        if r.returncode != 0:
+            return None
+        trials, secs, samples = r.stdout.split()[:3]
+        return float(trials) / float(secs), float(samples) / float(secs)
+
+
+def run_config(idx, reps):
+    path, fixture, system, mc_step, n_therm, n_init, W = CONFIGS[idx]
+    g = np.load(os.path.join(GOLDEN, fixture + ".npz"))
+    spec = systems.from_golden(g)
+    N = spec.n_particles
+    h = capi.Handle(spec, W, seed=1, mc_step=mc_step, max_samples=SAMPLES)
+    h.set_params(g["uR"], g["uI"], float(g["phiR"]), float(g["phiI"]), float(g["time"]))
+    rng = np.random.default_rng(idx)
+    R = g["R"][None] + rng.uniform(-0.01, 0.01, (W, N, 3))
+    h.set_positions(R)
+    h.sweep(20 * N)
+    h.synchronize()
+    for _ in range(2):
+        h.sample_and_accumulate(SAMPLES, n_therm, n_init)
+        out = h.allreduce_and_fetch()
+    h.profile(True, True)
+    h.synchronize()
+    h.timer_start()
+    for _ in range(reps):
+        h.sample_and_accumulate(SAMPLES, n_therm, n_init)
+        out = h.allreduce_and_fetch()
+    ms = h.timer_stop()
+    stats = h.kernel_stats()
+    h.profile(False, False)
+    per_sm, sms = h.resident_walkers()
+    steps = float(W) * (n_init + SAMPLES * n_therm) * reps
+    line = {"config": path, "system": system, "N": N, "N_PARAM": spec.n_params, "walkers": W, "MC_STEP": mc_step,
+            "MC_NTHERMSTEPS": n_therm, "MC_NINITIALIZATIONSTEPS": n_init, "samples_per_walker_per_pass": SAMPLES,
+            "walker_steps_per_s": steps / (ms * 1e-3), "samples_per_s": float(W) * SAMPLES * reps / (ms * 1e-3),
+            "ms_per_pass": ms / reps, "sweep_ms": stats["sweep"][1] / reps, "evaluate_ms": stats["evaluate"][1] / reps,
+            "accumulate_ms": stats["accumulate"][1] / reps, "resident_walkers_per_sm": per_sm,
+            "acceptance": out["n_acceptances"] / out["n_trials"], "local_energy_r": float(out["e_r"][0])}
+    h.close()
+    ref = reference_one_core(g, system, mc_step, n_therm, n_init, SAMPLES)
+    if ref:
+        line["reference_one_core"] = {"walker_steps_per_s": ref[0], "samples_per_s": ref[1],
+                                      "note": "unmodified reference (oracle/_ref/ref_harness bench), one walker, one core, same counts"}
+        line["walker_steps_ratio_vs_one_core"] = line["walker_steps_per_s"] / ref[0]
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="1,2,4,5")
+    ap.add_argument("--reps", type=int, default=3)
+    a = ap.parse_args()
+    for idx in [int(x) for x in a.configs.split(",")]:
+        print(json.dumps(run_config(idx, a.reps)), flush=True)
+
+
+if __name__ == "__main__":
+    main()

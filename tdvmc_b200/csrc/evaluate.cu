@@ -118,8 +118,10 @@ __device__ __forceinline__ double rcp_refined(double r)
     return y;
 }
 
-template <bool REFLECT>
-__global__ void __launch_bounds__(384, 2) evaluate_kernel(EvalArgs a)
+// WIDE: 24 warps and one block per SM for configurations whose shared-memory footprint leaves room for one block
+// anyway (N = 1728: positions + forces alone are 125 KB); otherwise 12 warps, two blocks per SM.
+template <bool REFLECT, bool WIDE>
+__global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kernel(EvalArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SysDev& s = a.s;
@@ -562,17 +564,6 @@ __global__ void __launch_bounds__(384, 2) evaluate_rowwise_kernel(EvalArgs a)
     }
 }
 
-int evaluate_threads(const SysDev& s)
-{
-    int t = ((s.N + 31) / 32) * 32;
-    return t > 384 ? 384 : t;
-}
-
-size_t evaluate_smem_bytes(const SysDev& s)
-{
-    return eval_smem_layout(s, evaluate_threads(s) / 32, nullptr, nullptr);
-}
-
 static bool eval_rowwise()
 {
     static int v = -1;
@@ -582,6 +573,26 @@ static bool eval_rowwise()
         v = (e && atoi(e) == 1) ? 1 : 0;
     }
     return v == 1;
+}
+
+// two blocks of <= 12 warps per SM when they fit, else one block of <= 24 warps
+static bool evaluate_wide(const SysDev& s)
+{
+    int nt = (s.N + 31) / 32;
+    if (nt <= 12) return false;
+    return 2 * (eval_smem_layout(s, 12, nullptr, nullptr) + 1024) > (size_t)227 * 1024;
+}
+
+int evaluate_threads(const SysDev& s)
+{
+    int t = ((s.N + 31) / 32) * 32;
+    const int cap = (evaluate_wide(s) && !eval_rowwise()) ? 768 : 384;
+    return t > cap ? cap : t;
+}
+
+size_t evaluate_smem_bytes(const SysDev& s)
+{
+    return eval_smem_layout(s, evaluate_threads(s) / 32, nullptr, nullptr);
 }
 
 template <typename KernelT>
@@ -603,8 +614,11 @@ cudaError_t launch_evaluate(const EvalArgs& a, cudaStream_t st)
     if (eval_rowwise())
         return refl ? launch_eval_kernel(evaluate_rowwise_kernel<true>, a, threads, smem, st)
                     : launch_eval_kernel(evaluate_rowwise_kernel<false>, a, threads, smem, st);
-    return refl ? launch_eval_kernel(evaluate_kernel<true>, a, threads, smem, st)
-                : launch_eval_kernel(evaluate_kernel<false>, a, threads, smem, st);
+    if (evaluate_wide(a.s))
+        return refl ? launch_eval_kernel(evaluate_kernel<true, true>, a, threads, smem, st)
+                    : launch_eval_kernel(evaluate_kernel<false, true>, a, threads, smem, st);
+    return refl ? launch_eval_kernel(evaluate_kernel<true, false>, a, threads, smem, st)
+                : launch_eval_kernel(evaluate_kernel<false, false>, a, threads, smem, st);
 }
 
 } // namespace tdvmc
