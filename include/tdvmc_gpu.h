@@ -158,6 +158,11 @@ int tdvmc_gpu_sample_and_accumulate(tdvmc_gpu_handle* h, int32_t n_samples, int3
 /* UpdateExpectationValuesForGivenSamples (src/TDVMC.cpp:1222-1303): re-evaluate the stored samples at the
  * current parameters (recomputed from the stored R) and accumulate.  Needs keep_sample_positions. */
 int tdvmc_gpu_reevaluate_stored(tdvmc_gpu_handle* h);
+/* UpdateSamplesConsecutive (src/TDVMC.cpp:975-983) with UpdateSample (:948-961): the next n_update stored samples
+ * of every walker (ring order, cursor = currentSampleIndexForUpdate) each advance by n_therm Metropolis steps at the
+ * current parameters.  Follow with tdvmc_gpu_reevaluate_stored (the driver does, :3675-3677).  Every slot draws its
+ * own stretch of the walker's proposal stream. */
+int tdvmc_gpu_update_stored(tdvmc_gpu_handle* h, int32_t n_update, int32_t n_therm);
 /* ReduceToAverage x7 + nAcceptances (src/TDVMC.cpp:1182-1188, 3727): one packed all-reduce over the
  * communicator (if any), division by the global sample count; every rank receives the averages. */
 int tdvmc_gpu_allreduce_and_fetch(tdvmc_gpu_handle* h, tdvmc_estimators* out);

@@ -65,6 +65,7 @@ SYMBOLS = [
     ("tdvmc_gpu_sweep", C.c_int, [_VP, C.c_int64]),
     ("tdvmc_gpu_sample_and_accumulate", C.c_int, [_VP, C.c_int32, C.c_int32, C.c_int32]),
     ("tdvmc_gpu_reevaluate_stored", C.c_int, [_VP]),
+    ("tdvmc_gpu_update_stored", C.c_int, [_VP, C.c_int32, C.c_int32]),
     ("tdvmc_gpu_allreduce_and_fetch", C.c_int, [_VP, C.POINTER(Estimators)]),
     ("tdvmc_gpu_last_exponent", C.c_int, [_VP, dp]),
     ("tdvmc_gpu_comm_unique_id", C.c_int, [C.POINTER(C.c_uint8)]),
@@ -204,6 +205,9 @@ class Handle:
 
     def reevaluate_stored(self):
         self._ck(self.lib.tdvmc_gpu_reevaluate_stored(self.h), "reevaluate_stored")
+
+    def update_stored(self, n_update, n_therm):
+        self._ck(self.lib.tdvmc_gpu_update_stored(self.h, int(n_update), int(n_therm)), "update_stored")
 
     def allreduce_and_fetch(self, out=None):
         P = self.P

@@ -144,6 +144,7 @@ struct tdvmc_gpu_handle
     long long rows_cap = 0;    // padded row capacity of d_A
     long long rows_used = 0;   // samples of the last accumulation
     int stored_samples = 0;    // samples per walker kept in d_samp_pos
+    int update_cursor = 0;     // currentSampleIndexForUpdate (src/TDVMC.cpp:975-983)
     double* h_est = nullptr;   // pinned
     size_t est_len = 0;
     bool est_valid = false;
@@ -827,12 +828,12 @@ int tdvmc_gpu_wrap_positions(tdvmc_gpu_handle* h)
     return 0;
 }
 
-static int do_sweep(tdvmc_gpu_handle* h, long long n_steps)
+static int do_sweep(tdvmc_gpu_handle* h, long long n_steps, double* pos = nullptr)
 {
     if (n_steps <= 0) return 0;
     SweepArgs a;
     a.s = h->sysdev();
-    a.pos = h->d_pos.p;
+    a.pos = pos ? pos : h->d_pos.p;
     a.accepted = h->d_accepted.p;
     a.W = h->W;
     a.first_walker = h->first_walker;
@@ -935,7 +936,7 @@ int tdvmc_gpu_sample_and_accumulate(tdvmc_gpu_handle* h, int32_t n_samples, int3
             CK(cudaMemcpyAsync(h->d_samp_pos.p + (size_t)m * h->W * 3 * h->Np, h->d_pos.p, (size_t)h->W * 3 * h->Np * sizeof(double),
                                cudaMemcpyDeviceToDevice, h->stream));
     }
-    if (h->keep_positions) h->stored_samples = n_samples;
+    if (h->keep_positions) h->stored_samples = n_samples; // the update cursor keeps running, as :556 sets it only once
     return do_accumulate(h, h->d_A.p, h->d_other.p, M); // :1103-1109
 }
 
@@ -948,6 +949,24 @@ int tdvmc_gpu_reevaluate_stored(tdvmc_gpu_handle* h)
     const long long M = (long long)h->stored_samples * h->W;
     if (int rc = do_evaluate_walkers(h, h->d_samp_pos.p, (int)M, 0)) return rc; // src/TDVMC.cpp:1244-1262
     return do_accumulate(h, h->d_A.p, h->d_other.p, M);
+}
+
+int tdvmc_gpu_update_stored(tdvmc_gpu_handle* h, int32_t n_update, int32_t n_therm)
+{
+    if (!h) return -1;
+    if (int rc = need_params(h)) return rc;
+    if (!h->keep_positions || h->stored_samples < 1) return fail(h, "update_stored: no stored samples (keep_sample_positions)");
+    if (n_update < 0 || n_therm < 0) return fail(h, "update_stored: negative count");
+    CK(cudaSetDevice(h->device));
+    for (int i = 0; i < n_update; i++) // UpdateSamplesConsecutive, src/TDVMC.cpp:975-983
+    {
+        const int slot = h->update_cursor % h->stored_samples;
+        // UpdateSample (:948-961): MC_NTHERMSTEPS Metropolis steps on the stored configuration at the current
+        // parameters; the stored tables are recomputed from R by reevaluate_stored, so nothing else is refreshed here
+        if (int rc = do_sweep(h, n_therm, h->d_samp_pos.p + (size_t)slot * h->W * 3 * h->Np)) return rc;
+        h->update_cursor = (slot + 1) % h->stored_samples;
+    }
+    return 0;
 }
 
 int tdvmc_gpu_allreduce_and_fetch(tdvmc_gpu_handle* h, tdvmc_estimators* out)

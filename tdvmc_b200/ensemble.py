@@ -72,6 +72,11 @@ class GpuEnsembleSystem:
                                                 MC_NADDITIONALINITIALIZATIONSTEPS)
         return dict(pairDistribution=gr, structureFactor=sk)
 
+    def UpdateSamplesConsecutive(self, nrOfSamplesToUpdate, uR, uI, phiR, phiI, MC_NTHERMSTEPS, time=0.0):
+        """src/TDVMC.cpp:975-983: the next stored samples of every walker advance by MC_NTHERMSTEPS steps."""
+        self.handle.set_params(uR, uI, phiR, phiI, time)
+        self.handle.update_stored(nrOfSamplesToUpdate, MC_NTHERMSTEPS)
+
     def GetExponent(self):
         return self.handle.last_exponent()
 

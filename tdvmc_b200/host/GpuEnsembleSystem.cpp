@@ -385,6 +385,14 @@ AdditionalObservables GpuEnsembleSystem::ParallelCalculateAdditionalSystemProper
     return out;
 }
 
+void GpuEnsembleSystem::UpdateSamplesConsecutive(int nrOfSamplesToUpdate, const std::vector<double>& uR,
+                                                 const std::vector<double>& uI, double phiR, double phiI, int MC_NTHERMSTEPS,
+                                                 double time)
+{
+    Check(tdvmc_gpu_set_params(handle, uR.data(), uI.data(), phiR, phiI, time), "set_params");
+    Check(tdvmc_gpu_update_stored(handle, nrOfSamplesToUpdate, MC_NTHERMSTEPS), "update_stored");
+}
+
 double GpuEnsembleSystem::GetExponent()
 {
     double x = 0.0;

@@ -143,6 +143,10 @@ public:
                                                int MC_NINITIALIZATIONSTEPS, double time);
     Estimators ParallelUpdateExpectationValuesForGivenSamples(const std::vector<double>& uR, const std::vector<double>& uI,
                                                               double phiR, double phiI, double time);
+    // UpdateSamplesConsecutive (src/TDVMC.cpp:975-983): the next nrOfSamplesToUpdate stored samples of every walker
+    // advance by MC_NTHERMSTEPS steps at the given parameters; call ParallelUpdateExpectationValuesForGivenSamples next.
+    void UpdateSamplesConsecutive(int nrOfSamplesToUpdate, const std::vector<double>& uR, const std::vector<double>& uI,
+                                  double phiR, double phiI, int MC_NTHERMSTEPS, double time);
     double GetExponent();
     // ParallelCalculateAdditionalSystemProperties (src/TDVMC.cpp:1438-1444) for the bulk spline systems: the mean
     // pairDistribution / structureFactor values (additionalObservablesMean.observables[0], [1]) over samples, walkers, ranks.

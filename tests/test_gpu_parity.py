@@ -351,6 +351,57 @@ def test_full_size_properties_config4(capi, golden):
     h.close()
 
 
+def test_update_stored_samples_replays_oracle(capi, golden):
+    """UpdateSamplesConsecutive + UpdateExpectationValuesForGivenSamples (src/TDVMC.cpp:975-983, 1222-1303): stored
+    samples advance at NEW parameters in ring order, then all are re-evaluated; the oracle replays every chain."""
+    g = golden("bosonsbulk_n64_equil")
+    W, seed, mc_step = 3, 13, 0.4
+    n_samples, n_therm, n_init = 3, 48, 30
+    spec, h = make_handle(capi, g, n_walkers=W, seed=seed, mc_step=mc_step, max_samples=n_samples, keep_sample_positions=True)
+    o = Oracle(spec, time=float(g["time"]))
+    R0 = np.stack([g["R"] + 0.002 * w for w in range(W)])
+    h.set_positions(R0)
+    h.sample_and_accumulate(n_samples, n_therm, n_init)
+    u2, ui2 = g["uR"] * 1.03, g["uI"] * 0.9
+    h.set_params(u2, ui2, float(g["phiR"]), float(g["phiI"]), float(g["time"]))
+    h.update_stored(4, n_therm)                      # ring: slots 0, 1, 2, 0
+    h.reevaluate_stored()
+    got = h.allreduce_and_fetch()
+    P = spec.n_params
+    O = np.zeros(P)
+    S = np.zeros((P, P))
+    er = ei = 0.0
+    acc = 0
+    for w in range(W):
+        R, a = o.sweep(R0[w], g["uR"], seed, w, 0, n_init, mc_step)
+        acc += a
+        step, stored = n_init, []
+        for m in range(n_samples):
+            R, a = o.sweep(R, g["uR"], seed, w, step, n_therm, mc_step)
+            acc += a
+            step += n_therm
+            stored.append(R.copy())
+        for slot in (0, 1, 2, 0):
+            stored[slot], a = o.sweep(stored[slot], u2, seed, w, step, n_therm, mc_step)
+            acc += a
+            step += n_therm
+        for Rm in stored:
+            ev = o.evaluate(Rm, u2, ui2, float(g["phiR"]))
+            O += ev["O"]
+            S += np.outer(ev["O"], ev["O"])
+            er += ev["e_r"]
+            ei += ev["e_i"]
+    M = W * n_samples
+    assert got["n_samples"] == M
+    assert got["n_trials"] == W * (n_init + n_samples * n_therm + 4 * n_therm)
+    assert got["n_acceptances"] == acc
+    assert rel(got["O"], O / M) < 1e-9
+    assert rel(got["S"], S / M) < 1e-9
+    assert abs(got["e_r"][0] - er / M) < 1e-9 * abs(er / M)
+    assert abs(got["e_i"][0] - ei / M) < 1e-9 * abs(ei / M)
+    h.close()
+
+
 def test_errors_are_loud(capi, golden):
     g = golden("bosonsbulk_n64_fixture")
     spec = systems.from_golden(g)
