@@ -336,6 +336,45 @@ def gen_observables():
         dict(MC_STEP=0.5, MC_NADDITIONALSTEPS=1500, MC_NADDITIONALTHERMSTEPS=216, MC_NADDITIONALINITIALIZATIONSTEPS=4320, seed=6))
 
 
+def gen_evolution():
+    """Imaginary-time evolution by the reference's own time-step functions (ref_harness evolve): BosonsBulk N = 64,
+    Euler steps with the Cholesky solve, several RNG seeds -> mean and spread of the parameter trajectories and of
+    the energies (north_star level 2: time-evolved parameters agree statistically), plus the first step's
+    estimators and derivatives of one seed to pin the host-side restatement of SolveForParametersDot."""
+    g = np.load(os.path.join(GOLDEN, "bosonsbulk_n64_equil.npz"))
+    P = int(g["N_PARAM"])
+    seeds = list(range(1, 25))
+    base = dict(N=64, LBOX=4.0, N_PARAM=P, time=0.0, phiR=0.0, phiI=0.0, MC_STEP=0.4, MC_NSTEPS=1024, MC_NTHERMSTEPS=32,
+                MC_NINITIALIZATIONSTEPS=64, IMAGINARY_TIME=1, TIMESTEP=2e-4, time_steps=30, equilibration_steps=6400)
+    arr = dict(R=g["R"], uR=g["uR"], uI=np.zeros(P), SYSTEM_PARAMS=[1.0, 1.0])
+    def one(sd):
+        with tempfile.TemporaryDirectory() as td:
+            cp, op = os.path.join(td, "case.txt"), os.path.join(td, "out.txt")
+            write_case(cp, "BosonsBulk", dict(base, seed=sd), arr)
+            run("evolve", cp, op)
+            return parse_dump(op)
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=max(1, (os.cpu_count() or 2) - 1)) as ex:   # each run is its own process
+        runs = list(ex.map(one, seeds))
+    for sd, r in zip(seeds, runs):
+        assert float(r["cholesky_failed"]) == 0.0
+        print(f"evolve seed {sd}: E {r['energy_r_t'][0]:.3f} -> {r['energy_r_t'][-1]:.3f}")
+    uR_t = np.stack([r["uR_t"] for r in runs])            # [seed][step][P]
+    e_t = np.stack([r["energy_r_t"] for r in runs])
+    first = runs[0]
+    out = {k: np.array(v) for k, v in base.items()}
+    out.update(system=np.array("BosonsBulk"), source=np.array("bosonsbulk_n64_equil"), seeds=np.array(seeds),
+               SYSTEM_PARAMS=np.array([1.0, 1.0]), uR0=g["uR"], uR_t_mean=uR_t.mean(axis=0), uR_t_std=uR_t.std(axis=0, ddof=1),
+               energy_r_t_mean=e_t.mean(axis=0), energy_r_t_std=e_t.std(axis=0, ddof=1),
+               phiR_t_mean=np.stack([r["phiR_t"] for r in runs]).mean(axis=0),
+               acceptance=np.mean([float(r["acceptance"]) for r in runs]))
+    for k in ("first_O", "first_S", "first_OER", "first_OEI", "first_ER", "first_EI", "first_uDotR", "first_uDotI",
+              "first_phiDotR", "first_phiDotI"):
+        out[k] = first[k]
+    np.savez_compressed(os.path.join(GOLDEN, "bosonsbulk_n64_evolution.npz"), **out)
+
+
 def hebulk_drift(d, uR, uI):
     """Drift from the REFERENCE's HeBulk tables with its parameter map (HeBulk.cpp:319-356), long double."""
     sD = d["sD"].astype(np.longdouble)
@@ -564,7 +603,7 @@ def main():
     if not os.path.exists(HARNESS):
         sys.exit("build the oracle first: make -C oracle/ref_build")
     which = sys.argv[1:] or ["min_image", "bosonsbulk", "bosonsbulk_mc", "nubosonsbulkpb", "nubosonsbulkpb_full", "hebulk", "hedrop",
-                             "mixture", "observables"]
+                             "mixture", "observables", "evolution"]
     for w in which:
         globals()["gen_" + w]()
 

@@ -528,17 +528,85 @@ int ModeObs(const Case& c, const std::string& out)
     return 0;
 }
 
+// Imaginary- or real-time evolution with the reference's own time-step pieces: ParallelUpdateExpectationValues
+// (src/TDVMC.cpp:1152-1220), SolveForParametersDot with the Cholesky path (:1713-1763: IncludePhi system, scaling
+// preconditioner, +0.001 regularisation) and CalculateNextParametersEuler (:1834-1853).  Records the parameters and
+// energies after every step, and the first step's estimators with the resulting derivatives.
+int ModeEvolve(const Case& c, const std::string& out)
+{
+    SetupReference(c);
+    IMAGINARY_TIME = c.i("IMAGINARY_TIME", 1);
+    LINEAR_EQUATION_SOLVER_TYPE = 0;
+    USE_PRECONDITIONING = 1;
+    USE_PARAM_START = 0;
+    USE_PARAM_END = 0;
+    USED_PARAM_COUNT = N_PARAM;
+    const int nSteps = c.i("time_steps", 10);
+    const double dt = c.d("TIMESTEP", 1e-3);
+    generator = std::mt19937_64((unsigned long long)c.i("seed", 1));
+    Dump d(out);
+    std::streambuf* old = std::cout.rdbuf();
+    std::ostringstream sink;
+    std::cout.rdbuf(sink.rdbuf());
+    isRootRank = true; // CalculateNextParametersEuler works on the root rank only (:1836)
+    MPIMethods::isRootRank = true; // as mainMPI sets them (:3019-3022)
+    MPIMethods::numOfProcesses = 1;
+    MPIMethods::processRank = 0;
+    MPIMethods::rootRank = 0;
+    sys->CalculateWavefunction(R, uR, uI, phiR, phiI);
+    for (int i = 0; i < c.i("equilibration_steps", 0); i++) DoMetropolisStep(R, uR, uI, phiR, phiI);
+    std::vector<std::vector<double> > uRt, uIt;
+    std::vector<double> eR, eI, phiRt;
+    for (int step = 0; step < nSteps; step++)
+    {
+        ParallelUpdateExpectationValues(R, uR, uI, phiR, phiI, true);
+        eR.push_back(localEnergyR);
+        eI.push_back(localEnergyI);
+        if (step == 0)
+        {
+            d.vec("first_O", localOperators);
+            d.mat("first_S", localOperatorsMatrix);
+            d.vec("first_OER", localOperatorlocalEnergyR);
+            d.vec("first_OEI", localOperatorlocalEnergyI);
+            d.scalar("first_ER", localEnergyR);
+            d.scalar("first_EI", localEnergyI);
+            std::vector<double> uDotR, uDotI;
+            double phiDotR = 0, phiDotI = 0;
+            SolveForParametersDot(uDotR, uDotI, &phiDotR, &phiDotI);
+            d.vec("first_uDotR", uDotR);
+            d.vec("first_uDotI", uDotI);
+            d.scalar("first_phiDotR", phiDotR);
+            d.scalar("first_phiDotI", phiDotI);
+        }
+        CalculateNextParametersEuler(dt, uR, uI, &phiR, &phiI);
+        uRt.push_back(uR);
+        uIt.push_back(uI);
+        phiRt.push_back(phiR);
+    }
+    std::cout.rdbuf(old);
+    isRootRank = false;
+    d.mat("uR_t", uRt);
+    d.mat("uI_t", uIt);
+    d.vec("phiR_t", phiRt);
+    d.vec("energy_r_t", eR);
+    d.vec("energy_i_t", eI);
+    d.scalar("acceptance", (double)nAcceptances / (double)nTrials);
+    d.scalar("cholesky_failed", doNotAcceptStep ? 1.0 : 0.0);
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
     if (argc < 3)
     {
-        std::cerr << "usage: ref_harness eval|mc|obs <case> <out> | bench <case> | nic <in> <out>" << std::endl;
+        std::cerr << "usage: ref_harness eval|mc|obs|evolve <case> <out> | bench <case> | nic <in> <out>" << std::endl;
         return 2;
     }
     std::string mode = argv[1];
     if (mode == "eval" && argc >= 4) return ModeEval(ReadCase(argv[2]), argv[3]);
     if (mode == "mc" && argc >= 4) return ModeMC(ReadCase(argv[2]), argv[3], false);
     if (mode == "obs" && argc >= 4) return ModeObs(ReadCase(argv[2]), argv[3]);
+    if (mode == "evolve" && argc >= 4) return ModeEvolve(ReadCase(argv[2]), argv[3]);
     if (mode == "bench") return ModeMC(ReadCase(argv[2]), "", true);
     if (mode == "nic" && argc >= 4) return ModeNic(argv[2], argv[3]);
     std::cerr << "bad arguments" << std::endl;
