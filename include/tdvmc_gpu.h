@@ -226,6 +226,29 @@ int tdvmc_gpu_observables_fixed(tdvmc_gpu_handle* h, const tdvmc_observable_desc
 int tdvmc_gpu_sample_observables(tdvmc_gpu_handle* h, const tdvmc_observable_desc* od, int32_t n_samples, int32_t n_therm,
                                  int32_t n_init, double* gr, double* sk);
 
+/* ---- additional observables of the three-particle mixture cluster (config/He4He4Na.config's whole workload) ----
+ * Replaces BosonMixtureCluster::CalculateAdditionalSystemProperties (BosonMixtureCluster.cpp:680-741) and the driver
+ * loop around it (src/TDVMC.cpp:1332-1388, 1438-1444).  Grids as InitSystem builds them (BosonMixtureCluster.cpp:327-340);
+ * the reference hard-codes three particles here, so the handle must hold a three-particle mixture. */
+typedef struct tdvmc_cluster_observable_desc
+{
+    int32_t n_angle, n_density, n_distance;   /* grid.count of angularDistribution, densityFromCOM, particleDistances */
+    int32_t reserved;
+    double angle_spacing;                     /* 1.0 degree */
+    double density_spacing, density_max;      /* 0.1, 80 */
+    double distance_spacing, distance_max;    /* 0.5, 80 */
+    const double* density_scaling;            /* [n_density] densityFromCOM.scalingGrid */
+} tdvmc_cluster_observable_desc;
+/* For n_cfg given configurations R[n_cfg][3][3]: r2[n_cfg], angle[n_cfg][3][n_angle] (1-2-3, 1-3-2, 2-1-3),
+ * density[n_cfg][3][n_density], distance[n_cfg][3][n_distance] (pairs 1-2, 1-3, 2-3). */
+int tdvmc_gpu_cluster_observables_fixed(tdvmc_gpu_handle* h, const tdvmc_cluster_observable_desc* od, const double* R,
+                                        int32_t n_cfg, double* r2, double* angle, double* density, double* distance);
+/* ParallelCalculateAdditionalSystemProperties for the cluster: n_init steps, then n_samples x (n_therm steps +
+ * observables) per walker; outputs are the means over samples, walkers and ranks (additionalObservablesMean). */
+int tdvmc_gpu_sample_cluster_observables(tdvmc_gpu_handle* h, const tdvmc_cluster_observable_desc* od, int32_t n_samples,
+                                         int32_t n_therm, int32_t n_init, double* r2, double* angle, double* density,
+                                         double* distance);
+
 /* ---- measurement hooks ---- */
 enum tdvmc_kernel_id
 {

@@ -336,6 +336,39 @@ def gen_observables():
         dict(MC_STEP=0.5, MC_NADDITIONALSTEPS=1500, MC_NADDITIONALTHERMSTEPS=216, MC_NADDITIONALINITIALIZATIONSTEPS=4320, seed=6))
 
 
+def gen_mixture_observables():
+    """BosonMixtureCluster::CalculateAdditionalSystemProperties (BosonMixtureCluster.cpp:680-741): r2, corner angles,
+    density from the centre of mass, pair distances - on the four evaluation configurations, and the reference's own
+    sampled means (config/He4He4Na.config's end-of-run pass, shortened) for the equilibrated one."""
+    cfg = json.load(open(os.path.join(REF, "config", "He4He4Na.config")))
+    out = {}
+    for tag in ("fixture", "compact", "stretched", "equil"):
+        g = np.load(os.path.join(GOLDEN, f"mixture_he4he4na_{tag}.npz"))
+        scal = dict(N=int(g["N"]), LBOX=float(g["LBOX"]), N_PARAM=int(g["N_PARAM"]), phiR=float(g["phiR"]), phiI=0.0, USE_NURBS=1,
+                    GR_BIN_COUNT=int(cfg["GR_BIN_COUNT"]))
+        mc = {}
+        if tag == "equil":
+            mc = dict(MC_STEP=float(cfg["MC_STEP"]), MC_NADDITIONALSTEPS=60000, MC_NADDITIONALTHERMSTEPS=60,
+                      MC_NADDITIONALINITIALIZATIONSTEPS=3000, seed=3)
+        arr = dict(R=g["R"], uR=g["uR"], uI=g["uI"], NURBS_GRID=g["NURBS_GRID"], PARTICLE_TYPES=g["PARTICLE_TYPES"],
+                   SYSTEM_PARAMS=g["SYSTEM_PARAMS"])
+        with tempfile.TemporaryDirectory() as td:
+            cp, op = os.path.join(td, "case.txt"), os.path.join(td, "out.txt")
+            write_case(cp, "BosonMixtureCluster", dict(scal, **mc), arr)
+            run("obs", cp, op)
+            d = parse_dump(op)
+        for k in ("r2_fixed", "angle_fixed", "density_fixed", "distance_fixed"):
+            out[f"{tag}_{k}"] = d[k]
+        if tag == "equil":
+            for k in ("angle_grid", "density_grid", "distance_grid", "density_scaling", "r2_mean", "angle_mean", "density_mean",
+                      "distance_mean", "acceptance"):
+                out[k] = d[k]
+            for k, v in mc.items():
+                out[k] = np.array(v)
+        print(f"mixture obs {tag}: r2={float(d['r2_fixed']):.6g} angle bins {np.argmax(d['angle_fixed'], axis=1)}")
+    np.savez_compressed(os.path.join(GOLDEN, "mixture_he4he4na_obs.npz"), **out)
+
+
 def gen_evolution():
     """Imaginary-time evolution by the reference's own time-step functions (ref_harness evolve): BosonsBulk N = 64,
     Euler steps with the Cholesky solve, several RNG seeds -> mean and spread of the parameter trajectories and of
@@ -603,7 +636,7 @@ def main():
     if not os.path.exists(HARNESS):
         sys.exit("build the oracle first: make -C oracle/ref_build")
     which = sys.argv[1:] or ["min_image", "bosonsbulk", "bosonsbulk_mc", "nubosonsbulkpb", "nubosonsbulkpb_full", "hebulk", "hedrop",
-                             "mixture", "observables", "evolution"]
+                             "mixture", "observables", "mixture_observables", "evolution"]
     for w in which:
         globals()["gen_" + w]()
 

@@ -496,17 +496,37 @@ void DumpObservableSetup(Dump& d, S* s)
     d.vec("k_vectors", flat);
 }
 
+void DumpOnGrid(Dump& d, const std::string& name, Observables::ObservableVsOnGrid& o, const std::string& suffix)
+{
+    std::vector<std::vector<double> > v;
+    for (auto& ov : o.observablesV) v.push_back(ov.values);
+    d.mat(name + suffix, v);
+}
+
 int ModeObs(const Case& c, const std::string& out)
 {
     SetupReference(c);
     Dump d(out);
     sys->CalculateWavefunction(R, uR, uI, phiR, phiI);
     sys->CalculateAdditionalSystemProperties(R, uR, uI, phiR, phiI);
+    auto mix = dynamic_cast<PhysicalSystems::BosonMixtureCluster*>(sys);
     if (auto s = dynamic_cast<PhysicalSystems::BosonsBulk*>(sys)) DumpObservableSetup(d, s);
     else if (auto s = dynamic_cast<PhysicalSystems::NUBosonsBulkPB*>(sys)) DumpObservableSetup(d, s);
+    else if (mix)
+    {
+        // BosonMixtureCluster.cpp:327-345, 680-741: r2, corner angles, density from the centre of mass, pair distances
+        d.scalar("r2_fixed", mix->r2.value);
+        DumpOnGrid(d, "angle", mix->angularDistribution, "_fixed");
+        DumpOnGrid(d, "density", mix->densityFromCOM, "_fixed");
+        DumpOnGrid(d, "distance", mix->particleDistances, "_fixed");
+        d.vec("angle_grid", { (double)mix->angularDistribution.grid.count, mix->angularDistribution.grid.spacing, mix->angularDistribution.grid.max });
+        d.vec("density_grid", { (double)mix->densityFromCOM.grid.count, mix->densityFromCOM.grid.spacing, mix->densityFromCOM.grid.max });
+        d.vec("distance_grid", { (double)mix->particleDistances.grid.count, mix->particleDistances.grid.spacing, mix->particleDistances.grid.max });
+        d.vec("density_scaling", mix->densityFromCOM.scalingGrid);
+    }
     else
     {
-        std::cerr << "obs: system without g(r)/S(k) observables" << std::endl;
+        std::cerr << "obs: system without additional observables in this harness" << std::endl;
         return 2;
     }
     MC_NADDITIONALSTEPS = c.i("MC_NADDITIONALSTEPS", 0);
@@ -519,6 +539,15 @@ int ModeObs(const Case& c, const std::string& out)
         nTrials = 0;
         nAcceptances = 0;
         CalculateAdditionalSystemProperties(R, uR, uI, phiR, phiI);
+        if (mix)
+        {
+            d.scalar("r2_mean", dynamic_cast<Observables::Observable*>(additionalObservablesMean.observables[0])->value);
+            DumpOnGrid(d, "angle", *dynamic_cast<Observables::ObservableVsOnGrid*>(additionalObservablesMean.observables[1]), "_mean");
+            DumpOnGrid(d, "density", *dynamic_cast<Observables::ObservableVsOnGrid*>(additionalObservablesMean.observables[2]), "_mean");
+            DumpOnGrid(d, "distance", *dynamic_cast<Observables::ObservableVsOnGrid*>(additionalObservablesMean.observables[3]), "_mean");
+            d.scalar("acceptance", (double)nAcceptances / (double)nTrials);
+            return 0;
+        }
         auto gr = dynamic_cast<Observables::ObservableVsOnGrid*>(additionalObservablesMean.observables[0]);
         auto sk = dynamic_cast<Observables::ObservableVsOnGrid*>(additionalObservablesMean.observables[1]);
         d.vec("gr_mean", gr->observablesV[0].values);

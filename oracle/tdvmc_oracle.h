@@ -212,6 +212,17 @@ int64_t oracle_mix_sample_walker(const oracle_mix* s, double* R, const double* u
 /* mass-weighted centre of mass (BosonMixtureCluster.cpp:348-368) */
 void oracle_mix_center_of_mass(const oracle_mix* s, const double* R, double* com);
 
+/* BosonMixtureCluster::CalculateAdditionalSystemProperties (BosonMixtureCluster.cpp:680-741) for one three-particle
+ * configuration.  grid = {count, spacing, max} of each histogram (Grid.cpp:16-31).
+ *   r2                     mean squared distance from the (mass-weighted) centre of mass
+ *   angle[3][n_angle]      GetCornerAngle (Utils.cpp:384-396) of 1-2-3, 1-3-2, 2-1-3 in degrees, one count each
+ *   density[3][n_density]  |R_i - com| < max: 1 / scaling[bin] (ObservableVsOnGridWithScaling.cpp:47-52)
+ *   distance[3][n_dist]    pairs (1,0), (2,0), (2,1) with r < max: one count each
+ * Bins beyond a grid's count are dropped (the reference writes them past the end of its vector). */
+void oracle_mix_observables(const oracle_mix* s, const double* R, const double* angle_grid, const double* density_grid,
+                            const double* density_scaling, const double* distance_grid, double* r2, double* angle,
+                            double* density, double* distance);
+
 #ifdef __cplusplus
 }
 #endif

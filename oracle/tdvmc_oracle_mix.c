@@ -384,3 +384,67 @@ int64_t oracle_mix_sample_walker(const oracle_mix* s, double* R, const double* u
     free(ext); free(O); free(tabD); free(tabD2); free(other);
     return accepted;
 }
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Additional observables of the three-particle cluster: BosonMixtureCluster.cpp:680-741
+ * ---------------------------------------------------------------------------------------------- */
+static double mix_dist(const double* a, const double* b)
+{
+    const double x = a[0] - b[0], y = a[1] - b[1], z = a[2] - b[2];
+    return sqrt(x * x + y * y + z * z); /* VectorDisplacement + VectorNorm, Utils.cpp:253-263 */
+}
+
+static double mix_corner_angle(const double* r1, const double* r2, const double* r3)
+{
+    const double r12 = mix_dist(r1, r2), r13 = mix_dist(r1, r3), r23 = mix_dist(r2, r3);
+    double angle = acos((r12 * r12 + r23 * r23 - r13 * r13) / (2 * r12 * r23)); /* Utils.cpp:393 */
+    angle = angle / M_PI * 180.0;
+    return angle;
+}
+
+static void mix_hist_add(double* hist, const double* grid, double value, double weight)
+{
+    const int bin = (int)floor(value / grid[1]); /* Grid.cpp:58-59 */
+    if (bin >= 0 && bin < (int)grid[0]) hist[bin] += weight;
+}
+
+void oracle_mix_observables(const oracle_mix* s, const double* R, const double* angle_grid, const double* density_grid,
+                            const double* density_scaling, const double* distance_grid, double* r2, double* angle,
+                            double* density, double* distance)
+{
+    const int N = s->n_particles; /* 3: the reference hard-codes three observables per histogram (:331, 336, 340) */
+    const int na = (int)angle_grid[0], nd = (int)density_grid[0], np = (int)distance_grid[0];
+    double com[3];
+    oracle_mix_center_of_mass(s, R, com);
+    double sum = 0.0;
+    for (int i = 0; i < N; i++)
+    {
+        const double r = mix_dist(R + 3 * i, com);
+        sum += r * r;
+    }
+    *r2 = sum / (double)N;
+    for (int i = 0; i < 3 * na; i++) angle[i] = 0.0;
+    for (int i = 0; i < 3 * nd; i++) density[i] = 0.0;
+    for (int i = 0; i < 3 * np; i++) distance[i] = 0.0;
+    mix_hist_add(angle, angle_grid, mix_corner_angle(R, R + 3, R + 6), 1.0);          /* 1-2-3, :705 */
+    mix_hist_add(angle + na, angle_grid, mix_corner_angle(R, R + 6, R + 3), 1.0);     /* 1-3-2, :709 */
+    mix_hist_add(angle + 2 * na, angle_grid, mix_corner_angle(R + 3, R, R + 6), 1.0); /* 2-1-3, :713 */
+    for (int i = 0; i < N; i++)
+    {
+        const double r = mix_dist(R + 3 * i, com);
+        if (r < density_grid[2])
+        {
+            const int bin = (int)floor(r / density_grid[1]);
+            if (bin < nd) density[i * nd + bin] += 1.0 / density_scaling[bin];
+        }
+    }
+    int index = 0;
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < i; j++)
+        {
+            const double r = mix_dist(R + 3 * i, R + 3 * j);
+            if (r < distance_grid[2]) mix_hist_add(distance + index * np, distance_grid, r, 1.0);
+            index++;
+        }
+}

@@ -50,6 +50,13 @@ class ObservableDesc(C.Structure):
                 ("gr_weight", C.c_double), ("gr_scaling", dp), ("shell_ptr", ip), ("kvec", dp)]
 
 
+class ClusterObservableDesc(C.Structure):
+    """tdvmc_cluster_observable_desc"""
+    _fields_ = [("n_angle", C.c_int32), ("n_density", C.c_int32), ("n_distance", C.c_int32), ("reserved", C.c_int32),
+                ("angle_spacing", C.c_double), ("density_spacing", C.c_double), ("density_max", C.c_double),
+                ("distance_spacing", C.c_double), ("distance_max", C.c_double), ("density_scaling", dp)]
+
+
 # every symbol include/tdvmc_gpu.h declares: (name, restype, argtypes)
 _VP = C.c_void_p
 SYMBOLS = [
@@ -78,6 +85,9 @@ SYMBOLS = [
     ("tdvmc_gpu_proposals", C.c_int, [_VP, C.c_int32, C.c_int64, C.c_int32, ip, dp, dp]),
     ("tdvmc_gpu_observables_fixed", C.c_int, [_VP, C.POINTER(ObservableDesc), dp, C.c_int32, dp, dp]),
     ("tdvmc_gpu_sample_observables", C.c_int, [_VP, C.POINTER(ObservableDesc), C.c_int32, C.c_int32, C.c_int32, dp, dp]),
+    ("tdvmc_gpu_cluster_observables_fixed", C.c_int, [_VP, C.POINTER(ClusterObservableDesc), dp, C.c_int32, dp, dp, dp, dp]),
+    ("tdvmc_gpu_sample_cluster_observables", C.c_int,
+     [_VP, C.POINTER(ClusterObservableDesc), C.c_int32, C.c_int32, C.c_int32, dp, dp, dp, dp]),
     ("tdvmc_gpu_profile", C.c_int, [_VP, C.c_int32, C.c_int32]),
     ("tdvmc_gpu_kernel_stats", C.c_int, [_VP, C.c_int32, C.POINTER(C.c_int64), dp]),
     ("tdvmc_gpu_synchronize", C.c_int, [_VP]),
@@ -274,6 +284,38 @@ class Handle:
         self._ck(self.lib.tdvmc_gpu_sample_observables(self.h, C.byref(od), int(n_samples), int(n_therm), int(n_init), _d(gr), _d(sk)),
                  "sample_observables")
         return gr, sk
+
+    @staticmethod
+    def _cluster_desc(grids):
+        """grids: dict(angle_grid, density_grid, distance_grid = (count, spacing, max), density_scaling)."""
+        ag, dg, pg = (np.asarray(grids[k], np.float64) for k in ("angle_grid", "density_grid", "distance_grid"))
+        sc = np.ascontiguousarray(grids["density_scaling"], np.float64)
+        od = ClusterObservableDesc(int(ag[0]), int(dg[0]), int(pg[0]), 0, float(ag[1]), float(dg[1]), float(dg[2]), float(pg[1]),
+                                   float(pg[2]), _d(sc))
+        return od, sc
+
+    def cluster_observables_fixed(self, grids, R):
+        R = np.ascontiguousarray(R, np.float64).reshape(-1, 3, 3)
+        od, keep = self._cluster_desc(grids)
+        n = len(R)
+        r2 = np.empty(n)
+        angle = np.empty((n, 3, od.n_angle))
+        density = np.empty((n, 3, od.n_density))
+        distance = np.empty((n, 3, od.n_distance))
+        self._ck(self.lib.tdvmc_gpu_cluster_observables_fixed(self.h, C.byref(od), _d(R), n, _d(r2), _d(angle), _d(density),
+                                                              _d(distance)), "cluster_observables_fixed")
+        return r2, angle, density, distance
+
+    def sample_cluster_observables(self, grids, n_samples, n_therm, n_init):
+        od, keep = self._cluster_desc(grids)
+        r2 = np.empty(1)
+        angle = np.empty((3, od.n_angle))
+        density = np.empty((3, od.n_density))
+        distance = np.empty((3, od.n_distance))
+        self._ck(self.lib.tdvmc_gpu_sample_cluster_observables(self.h, C.byref(od), int(n_samples), int(n_therm), int(n_init),
+                                                               _d(r2), _d(angle), _d(density), _d(distance)),
+                 "sample_cluster_observables")
+        return float(r2[0]), angle, density, distance
 
     def tables_fixed(self, R):
         R = np.ascontiguousarray(R, np.float64).reshape(self.N, 3)

@@ -1437,6 +1437,148 @@ int tdvmc_gpu_sample_observables(tdvmc_gpu_handle* h, const tdvmc_observable_des
     return 0;
 }
 
+// ---- cluster observables ----
+namespace
+{
+int check_cluster_desc(tdvmc_gpu_handle* h, const tdvmc_cluster_observable_desc* od)
+{
+    if (!od) return fail(h, "cluster observables: null description");
+    if (h->kind != TDVMC_SYSTEM_MIXTURE || h->N != 3)
+        return fail(h, "cluster observables: defined for the three-particle mixture cluster (BosonMixtureCluster.cpp:331-340)");
+    if (od->n_angle < 1 || od->n_density < 1 || od->n_distance < 1 || !(od->angle_spacing > 0.0) || !(od->density_spacing > 0.0) ||
+        !(od->distance_spacing > 0.0) || !od->density_scaling)
+        return fail(h, "cluster observables: bad grids");
+    return 0;
+}
+
+ClusterObsArgs make_cluster_args(tdvmc_gpu_handle* h, const tdvmc_cluster_observable_desc* od)
+{
+    ClusterObsArgs a;
+    memset(&a, 0, sizeof(a));
+    a.s = h->sysdev();
+    a.n_angle = od->n_angle;
+    a.n_density = od->n_density;
+    a.n_distance = od->n_distance;
+    a.angle_spacing = od->angle_spacing;
+    a.density_spacing = od->density_spacing;
+    a.density_max = od->density_max;
+    a.distance_spacing = od->distance_spacing;
+    a.distance_max = od->distance_max;
+    return a;
+}
+
+// counts -> the reference's histogram values, scaled by 1/n_cfg_total
+void unpack_cluster_hist(const tdvmc_cluster_observable_desc* od, const double* cnt, double inv, double* angle, double* density,
+                         double* distance)
+{
+    const int na = od->n_angle, nd = od->n_density, np = od->n_distance;
+    if (angle)
+        for (int i = 0; i < 3 * na; i++) angle[i] = cnt[i] * inv;
+    if (density)
+        for (int i = 0; i < 3; i++)
+            for (int b = 0; b < nd; b++) density[i * nd + b] = cnt[3 * na + i * nd + b] * (1.0 / od->density_scaling[b]) * inv;
+    if (distance)
+        for (int i = 0; i < 3 * np; i++) distance[i] = cnt[3 * na + 3 * nd + i] * inv;
+}
+} // namespace
+
+int tdvmc_gpu_cluster_observables_fixed(tdvmc_gpu_handle* h, const tdvmc_cluster_observable_desc* od, const double* R, int32_t n_cfg,
+                                        double* r2, double* angle, double* density, double* distance)
+{
+    if (!h || !R || n_cfg < 1) return h ? fail(h, "cluster_observables_fixed: bad arguments") : -1;
+    if (int rc = check_cluster_desc(h, od)) return rc;
+    CK(cudaSetDevice(h->device));
+    const int nh = 3 * (od->n_angle + od->n_density + od->n_distance);
+    DevBuf<double> aos, pos, r2r;
+    DevBuf<unsigned long long> hist;
+    CK(aos.alloc((size_t)n_cfg * 9));
+    CK(pos.alloc((size_t)n_cfg * 3 * h->Np));
+    CK(r2r.alloc(n_cfg));
+    CK(hist.alloc((size_t)n_cfg * nh));
+    CK(cudaMemsetAsync(pos.p, 0, pos.n * sizeof(double), h->stream));
+    CK(cudaMemcpyAsync(aos.p, R, aos.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(launch_transpose_in(aos.p, pos.p, n_cfg, h->N, h->Np, h->stream));
+    ClusterObsArgs a = make_cluster_args(h, od);
+    a.pos = pos.p;
+    a.n_cfg = n_cfg;
+    a.accumulate = 0;
+    a.per_cfg_hist = 1;
+    a.r2_rows = r2r.p;
+    a.hist = hist.p;
+    {
+        Timed t(h, TDVMC_KERNEL_OTHER);
+        CK(launch_cluster_observables(a, h->stream));
+    }
+    std::vector<unsigned long long> cnt((size_t)n_cfg * nh);
+    CK(cudaMemcpyAsync(cnt.data(), hist.p, cnt.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    if (r2) CK(cudaMemcpyAsync(r2, r2r.p, (size_t)n_cfg * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    std::vector<double> c(nh);
+    for (int k = 0; k < n_cfg; k++)
+    {
+        for (int i = 0; i < nh; i++) c[i] = (double)cnt[(size_t)k * nh + i];
+        unpack_cluster_hist(od, c.data(), 1.0, angle ? angle + (size_t)k * 3 * od->n_angle : nullptr,
+                            density ? density + (size_t)k * 3 * od->n_density : nullptr,
+                            distance ? distance + (size_t)k * 3 * od->n_distance : nullptr);
+    }
+    return 0;
+}
+
+int tdvmc_gpu_sample_cluster_observables(tdvmc_gpu_handle* h, const tdvmc_cluster_observable_desc* od, int32_t n_samples,
+                                         int32_t n_therm, int32_t n_init, double* r2, double* angle, double* density,
+                                         double* distance)
+{
+    if (!h) return -1;
+    if (int rc = need_params(h)) return rc;
+    if (int rc = check_cluster_desc(h, od)) return rc;
+    if (n_samples < 1 || n_therm < 0 || n_init < 0) return fail(h, "sample_cluster_observables: bad step counts");
+    CK(cudaSetDevice(h->device));
+    const int nh = 3 * (od->n_angle + od->n_density + od->n_distance);
+    DevBuf<double> r2r, sum;
+    DevBuf<unsigned long long> hist;
+    CK(r2r.alloc(h->W));
+    CK(hist.alloc(nh));
+    CK(sum.alloc((size_t)nh + 2));
+    CK(cudaMemsetAsync(r2r.p, 0, r2r.n * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(hist.p, 0, hist.n * sizeof(unsigned long long), h->stream));
+    ClusterObsArgs a = make_cluster_args(h, od);
+    a.pos = h->d_pos.p;
+    a.n_cfg = h->W;
+    a.accumulate = 1;
+    a.per_cfg_hist = 0;
+    a.r2_rows = r2r.p;
+    a.hist = hist.p;
+    if (int rc = do_sweep(h, n_init)) return rc; // src/TDVMC.cpp:1338-1341
+    for (int m = 0; m < n_samples; m++)
+    {
+        if (int rc = do_sweep(h, n_therm)) return rc; // :1344-1347
+        Timed t(h, TDVMC_KERNEL_OTHER);
+        CK(launch_cluster_observables(a, h->stream)); // :1349
+    }
+    // pack [counts as doubles | sum r2 | number of configurations] for one all-reduce
+    std::vector<unsigned long long> cnt(nh);
+    CK(launch_sum_rows(r2r.p, h->W, sum.p + nh, h->stream));
+    CK(cudaMemcpyAsync(cnt.data(), hist.p, (size_t)nh * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    std::vector<double> hs((size_t)nh + 2);
+    for (int i = 0; i < nh; i++) hs[i] = (double)cnt[i];
+    hs[nh + 1] = (double)n_samples * (double)h->W;
+    CK(cudaMemcpyAsync(&hs[nh], sum.p + nh, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->comm) // MPIMethods::ReduceToAverage(additionalObservablesMean), src/TDVMC.cpp:1443
+    {
+        CK(cudaMemcpyAsync(sum.p, hs.data(), hs.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        int rc = g_nccl.AllReduce(sum.p, sum.p, hs.size(), kNcclDouble, kNcclSum, h->comm, h->stream);
+        if (rc != 0) return fail(h, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"), rc);
+        CK(cudaMemcpyAsync(hs.data(), sum.p, hs.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    const double inv = 1.0 / hs[nh + 1];
+    if (r2) *r2 = hs[nh] * inv;
+    unpack_cluster_hist(od, hs.data(), inv, angle, density, distance);
+    return 0;
+}
+
 int tdvmc_gpu_proposals(tdvmc_gpu_handle* h, int32_t global_walker, int64_t first_step, int32_t n, int32_t* particle,
                         double* disp, double* log_u)
 {

@@ -138,6 +138,22 @@ cudaError_t launch_observables(const ObsArgs& a, cudaStream_t st);
 cudaError_t launch_obs_reduce(const unsigned long long* gr_rows, const double* sk_rows, int n_rows, int gr_count, int n_shells,
                               double* out, cudaStream_t st);
 
+// ---- three-particle cluster observables (observables.cu) ----
+struct ClusterObsArgs
+{
+    SysDev s;
+    const double* pos; // [n_cfg][3][Np]
+    int n_cfg;
+    int accumulate;    // r2_rows: add (1) or overwrite (0)
+    int per_cfg_hist;  // 1: one configuration per block, hist[n_cfg][nh] overwritten; 0: hist[nh] accumulated over all
+    int n_angle, n_density, n_distance;
+    double angle_spacing, density_spacing, density_max, distance_spacing, distance_max;
+    double* r2_rows;          // [n_cfg]
+    unsigned long long* hist; // counts
+};
+cudaError_t launch_cluster_observables(const ClusterObsArgs& a, cudaStream_t st);
+cudaError_t launch_sum_rows(const double* rows, int n, double* out, cudaStream_t st);
+
 cudaError_t launch_min_image(const SysDev& s, double L, const double* a, const double* b, int n, double* norm, double* disp,
                              cudaStream_t st);
 cudaError_t launch_proposals(uint64_t seed, uint32_t walker, uint64_t first_step, int n, int n_particles, double mc_step,

@@ -123,6 +123,112 @@ __global__ void obs_reduce_kernel(const unsigned long long* gr_rows, const doubl
     }
 }
 
+// ---- three-particle cluster observables (BosonMixtureCluster.cpp:680-741) --------------------------
+// One thread per walker; the block collects integer histograms in shared memory and adds them to the global
+// 64-bit counters once (integer sums: exact, order-free).  r2 goes to the walker's own slot (summed later in
+// a fixed order).  Histogram layout: [angle 3 x na | density 3 x nd | distance 3 x np].
+__device__ __forceinline__ double cl_dist(const double* a, const double* b)
+{
+    const double x = a[0] - b[0], y = a[1] - b[1], z = a[2] - b[2];
+    return sqrt(x * x + y * y + z * z); // VectorDisplacement, Utils.cpp:253-263
+}
+
+__device__ __forceinline__ double cl_corner_angle(const double* r1, const double* r2, const double* r3)
+{
+    const double r12 = cl_dist(r1, r2), r13 = cl_dist(r1, r3), r23 = cl_dist(r2, r3);
+    double angle = acos((r12 * r12 + r23 * r23 - r13 * r13) / (2 * r12 * r23)); // Utils.cpp:393
+    angle = angle / 3.14159265358979323846 * 180.0;
+    return angle;
+}
+
+__device__ __forceinline__ void cl_count(unsigned int* hist, int count, double spacing, double value)
+{
+    const int bin = (int)floor(value / spacing); // Grid.cpp:58-59
+    if (bin >= 0 && bin < count) atomicAdd(&hist[bin], 1u);
+}
+
+__global__ void __launch_bounds__(128) cluster_observables_kernel(ClusterObsArgs a)
+{
+    extern __shared__ unsigned int cl_hist[];
+    const SysDev& s = a.s;
+    const int nh = 3 * (a.n_angle + a.n_density + a.n_distance);
+    for (int i = threadIdx.x; i < nh; i += blockDim.x) cl_hist[i] = 0u;
+    __syncthreads();
+    unsigned int* h_angle = cl_hist;
+    unsigned int* h_density = h_angle + 3 * a.n_angle;
+    unsigned int* h_distance = h_density + 3 * a.n_density;
+    const int w = a.per_cfg_hist ? (threadIdx.x == 0 ? (int)blockIdx.x : a.n_cfg) : (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (w < a.n_cfg)
+    {
+        double R[3][3];
+        const double* p = a.pos + (size_t)w * 3 * s.Np;
+        for (int i = 0; i < 3; i++)
+            for (int c = 0; c < 3; c++) R[i][c] = p[(size_t)c * s.Np + i];
+        double msum = 0.0, com[3] = { 0.0, 0.0, 0.0 }; // GetCenterOfMass, BosonMixtureCluster.cpp:348-368
+        for (int i = 0; i < 3; i++)
+        {
+            msum += s.mass_n[i];
+            for (int c = 0; c < 3; c++) com[c] += s.mass_n[i] * R[i][c];
+        }
+        for (int c = 0; c < 3; c++) com[c] /= msum;
+        double r2sum = 0.0;
+        for (int i = 0; i < 3; i++)
+        {
+            const double r = cl_dist(R[i], com);
+            r2sum += r * r;                                                      // :690-697
+            if (r < a.density_max) cl_count(h_density + i * a.n_density, a.n_density, a.density_spacing, r); // :717-724
+        }
+        a.r2_rows[w] = (a.accumulate ? a.r2_rows[w] : 0.0) + r2sum / 3.0;
+        cl_count(h_angle, a.n_angle, a.angle_spacing, cl_corner_angle(R[0], R[1], R[2]));                 // 1-2-3
+        cl_count(h_angle + a.n_angle, a.n_angle, a.angle_spacing, cl_corner_angle(R[0], R[2], R[1]));     // 1-3-2
+        cl_count(h_angle + 2 * a.n_angle, a.n_angle, a.angle_spacing, cl_corner_angle(R[1], R[0], R[2])); // 2-1-3
+        int index = 0;
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < i; j++)
+            {
+                const double r = cl_dist(R[i], R[j]);
+                if (r < a.distance_max) cl_count(h_distance + index * a.n_distance, a.n_distance, a.distance_spacing, r); // :728-739
+                index++;
+            }
+    }
+    __syncthreads();
+    if (a.per_cfg_hist) // parity entry point: one configuration per block
+    {
+        for (int i = threadIdx.x; i < nh; i += blockDim.x) a.hist[(size_t)blockIdx.x * nh + i] = cl_hist[i];
+    }
+    else
+    {
+        for (int i = threadIdx.x; i < nh; i += blockDim.x)
+            if (cl_hist[i]) atomicAdd(&a.hist[i], (unsigned long long)cl_hist[i]);
+    }
+}
+
+__global__ void sum_rows_kernel(const double* rows, int n, double* out)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        double t = 0.0;
+        for (int i = 0; i < n; i++) t += rows[i];
+        *out = t;
+    }
+}
+
+cudaError_t launch_cluster_observables(const ClusterObsArgs& a, cudaStream_t st)
+{
+    if (a.n_cfg <= 0) return cudaSuccess;
+    const size_t smem = (size_t)3 * (a.n_angle + a.n_density + a.n_distance) * sizeof(unsigned int);
+    const int threads = a.per_cfg_hist ? 32 : 128;
+    const int blocks = a.per_cfg_hist ? a.n_cfg : (a.n_cfg + threads - 1) / threads;
+    cluster_observables_kernel<<<blocks, threads, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sum_rows(const double* rows, int n, double* out, cudaStream_t st)
+{
+    sum_rows_kernel<<<1, 32, 0, st>>>(rows, n, out);
+    return cudaGetLastError();
+}
+
 size_t observables_smem_bytes(const SysDev& s, int n_kvec, int gr_count)
 {
     return (size_t)(3 * s.N + 2 * n_kvec) * sizeof(double) + (size_t)gr_count * sizeof(unsigned int);

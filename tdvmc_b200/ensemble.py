@@ -77,6 +77,15 @@ class GpuEnsembleSystem:
         self.handle.set_params(uR, uI, phiR, phiI, time)
         self.handle.update_stored(nrOfSamplesToUpdate, MC_NTHERMSTEPS)
 
+    def ParallelCalculateAdditionalSystemPropertiesCluster(self, uR, uI, phiR, phiI, grids, MC_NADDITIONALSTEPS,
+                                                           MC_NADDITIONALTHERMSTEPS, MC_NADDITIONALINITIALIZATIONSTEPS, time=0.0):
+        """The same pass for the three-particle mixture cluster (BosonMixtureCluster.cpp:680-741): r2, angularDistribution,
+        densityFromCOM, particleDistances means; grids: dict(angle_grid, density_grid, distance_grid, density_scaling)."""
+        self.handle.set_params(uR, uI, phiR, phiI, time)
+        r2, angle, density, distance = self.handle.sample_cluster_observables(grids, MC_NADDITIONALSTEPS, MC_NADDITIONALTHERMSTEPS,
+                                                                              MC_NADDITIONALINITIALIZATIONSTEPS)
+        return dict(r2=r2, angularDistribution=angle, densityFromCOM=density, particleDistances=distance)
+
     def GetExponent(self):
         return self.handle.last_exponent()
 

@@ -385,6 +385,33 @@ AdditionalObservables GpuEnsembleSystem::ParallelCalculateAdditionalSystemProper
     return out;
 }
 
+ClusterObservables GpuEnsembleSystem::ParallelCalculateAdditionalSystemPropertiesCluster(
+    const std::vector<double>& uR, const std::vector<double>& uI, double phiR, double phiI, const ClusterObservableTables& obs,
+    int MC_NADDITIONALSTEPS, int MC_NADDITIONALTHERMSTEPS, int MC_NADDITIONALINITIALIZATIONSTEPS, double time)
+{
+    Check(tdvmc_gpu_set_params(handle, uR.data(), uI.data(), phiR, phiI, time), "set_params");
+    tdvmc_cluster_observable_desc od;
+    od.n_angle = obs.angleCount;
+    od.n_density = obs.densityCount;
+    od.n_distance = obs.distanceCount;
+    od.reserved = 0;
+    od.angle_spacing = obs.angleSpacing;
+    od.density_spacing = obs.densitySpacing;
+    od.density_max = obs.densityMax;
+    od.distance_spacing = obs.distanceSpacing;
+    od.distance_max = obs.distanceMax;
+    od.density_scaling = obs.densityScaling.data();
+    ClusterObservables out;
+    out.angularDistribution.assign((size_t)3 * od.n_angle, 0.0);
+    out.densityFromCOM.assign((size_t)3 * od.n_density, 0.0);
+    out.particleDistances.assign((size_t)3 * od.n_distance, 0.0);
+    Check(tdvmc_gpu_sample_cluster_observables(handle, &od, MC_NADDITIONALSTEPS, MC_NADDITIONALTHERMSTEPS,
+                                               MC_NADDITIONALINITIALIZATIONSTEPS, &out.r2, out.angularDistribution.data(),
+                                               out.densityFromCOM.data(), out.particleDistances.data()),
+          "sample_cluster_observables");
+    return out;
+}
+
 void GpuEnsembleSystem::UpdateSamplesConsecutive(int nrOfSamplesToUpdate, const std::vector<double>& uR,
                                                  const std::vector<double>& uI, double phiR, double phiI, int MC_NTHERMSTEPS,
                                                  double time)

@@ -97,6 +97,19 @@ struct AdditionalObservables
     std::vector<double> pairDistribution, structureFactor;
 };
 
+// Histogram grids of the three-particle cluster observables (BosonMixtureCluster.cpp:327-340): {count, spacing, max}.
+struct ClusterObservableTables
+{
+    int angleCount = 180, densityCount = 800, distanceCount = 160;
+    double angleSpacing = 1.0, densitySpacing = 0.1, densityMax = 80.0, distanceSpacing = 0.5, distanceMax = 80.0;
+    std::vector<double> densityScaling; // densityFromCOM.scalingGrid
+};
+struct ClusterObservables
+{
+    double r2 = 0;
+    std::vector<double> angularDistribution, densityFromCOM, particleDistances; // [3][count] each
+};
+
 // The seven estimator arrays under the reference's global names (src/TDVMC.cpp:147-153).
 struct Estimators
 {
@@ -143,6 +156,11 @@ public:
                                                int MC_NINITIALIZATIONSTEPS, double time);
     Estimators ParallelUpdateExpectationValuesForGivenSamples(const std::vector<double>& uR, const std::vector<double>& uI,
                                                               double phiR, double phiI, double time);
+    // The same pass for BosonMixtureCluster (BosonMixtureCluster.cpp:680-741).
+    ClusterObservables ParallelCalculateAdditionalSystemPropertiesCluster(const std::vector<double>& uR, const std::vector<double>& uI,
+                                                                          double phiR, double phiI, const ClusterObservableTables& obs,
+                                                                          int MC_NADDITIONALSTEPS, int MC_NADDITIONALTHERMSTEPS,
+                                                                          int MC_NADDITIONALINITIALIZATIONSTEPS, double time);
     // UpdateSamplesConsecutive (src/TDVMC.cpp:975-983): the next nrOfSamplesToUpdate stored samples of every walker
     // advance by MC_NTHERMSTEPS steps at the given parameters; call ParallelUpdateExpectationValuesForGivenSamples next.
     void UpdateSamplesConsecutive(int nrOfSamplesToUpdate, const std::vector<double>& uR, const std::vector<double>& uI,

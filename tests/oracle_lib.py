@@ -348,6 +348,15 @@ class OracleMix:
                                              _d(est), _d(rows))
         return dict(R=R, est=est, rows=rows, accepted=int(acc), steps=sc.value)
 
+    def sweep(self, R, uR, seed, walker, first_step, n_steps, mc_step):
+        R = np.array(R, np.float64)
+        uR = np.ascontiguousarray(uR, np.float64)
+        ext = self.values(R)
+        ex = C.c_double(self.exponent(ext, uR))
+        acc = lib().oracle_mix_sweep(C.byref(self.sys), _d(R), _d(ext), C.byref(ex), _d(uR), C.c_uint64(seed), C.c_uint32(walker),
+                                     C.c_uint64(first_step), C.c_int64(n_steps), C.c_double(mc_step))
+        return R, int(acc)
+
     def unpack_est(self, est, n):
         return Oracle.unpack_est(self, est, n)
 
@@ -355,6 +364,19 @@ class OracleMix:
         com = np.zeros(3)
         lib().oracle_mix_center_of_mass(C.byref(self.sys), _d(np.ascontiguousarray(R, np.float64)), _d(com))
         return com
+
+
+def oracle_mix_observables(omix, R, grids):
+    """oracle_mix_observables for one configuration; grids: dict(angle_grid, density_grid, density_scaling, distance_grid)."""
+    R = np.ascontiguousarray(R, np.float64)
+    ag, dg, ds, pg = (np.ascontiguousarray(grids[k], np.float64) for k in ("angle_grid", "density_grid", "density_scaling", "distance_grid"))
+    r2 = C.c_double(0)
+    angle = np.zeros((3, int(ag[0])))
+    density = np.zeros((3, int(dg[0])))
+    distance = np.zeros((3, int(pg[0])))
+    lib().oracle_mix_observables(C.byref(omix.sys), _d(R), _d(ag), _d(dg), _d(ds), _d(pg), C.byref(r2), _d(angle), _d(density),
+                                 _d(distance))
+    return r2.value, angle, density, distance
 
 
 OracleHeBulk = OracleHe

@@ -893,3 +893,65 @@ def test_time_evolution_matches_reference_statistically(capi, golden):
     e_sig = np.sqrt(np.mean(g["energy_r_t_std"][tail] ** 2) / 10.0) * widen
     e_gpu = np.mean([e[tail].mean() for _, e in runs])
     assert abs(e_gpu - g["energy_r_t_mean"][tail].mean()) < 6.0 * e_sig * np.sqrt(1.0 / len(runs) + 1.0 / K)
+
+
+# ---------------------------------------------------------------------------------------------------
+# cluster observables of the He4-He4-Na mixture (BosonMixtureCluster.cpp:680-741): config 5's end-of-run pass
+# ---------------------------------------------------------------------------------------------------
+def test_cluster_observables_fixed_match_reference(capi, golden):
+    g = golden("mixture_he4he4na_obs")
+    tags = ["fixture", "compact", "stretched", "equil"]
+    src = [golden(f"mixture_he4he4na_{t}") for t in tags]
+    spec, h = make_handle(capi, src[0])
+    r2, angle, density, distance = h.cluster_observables_fixed(g, np.stack([s["R"] for s in src]))
+    for c, t in enumerate(tags):
+        assert abs(r2[c] - float(g[f"{t}_r2_fixed"])) < 1e-13 * r2[c]
+        assert np.array_equal(angle[c], g[f"{t}_angle_fixed"])
+        assert np.array_equal(distance[c], g[f"{t}_distance_fixed"])
+        assert np.max(np.abs(density[c] - g[f"{t}_density_fixed"])) <= 1e-15 * np.max(g[f"{t}_density_fixed"])
+    h.close()
+
+
+def test_cluster_observables_sampled_replay_oracle_and_match_reference(capi, golden):
+    """(a) the pass over resident walkers equals oracle chain + oracle observables; (b) with many walkers the means agree
+    with the reference's own end-of-run pass (its sampler) within error bars: r2 within 5 standard errors estimated from
+    the histogram of distances from the centre of mass, histogram bins within 6 sigma of binomial counting noise (x4 for
+    autocorrelation)."""
+    from oracle_lib import OracleMix, oracle_mix_observables
+    g = golden("mixture_he4he4na_obs")
+    src = golden("mixture_he4he4na_equil")
+    mc_step = float(g["MC_STEP"])
+    W, seed, n_samples, n_therm, n_init = 3, 17, 4, 30, 20
+    spec, h = make_handle(capi, src, n_walkers=W, seed=seed, mc_step=mc_step)
+    o = OracleMix(spec)
+    R0 = np.stack([src["R"] + 0.01 * w for w in range(W)])
+    h.set_positions(R0)
+    r2, angle, density, distance = h.sample_cluster_observables(g, n_samples, n_therm, n_init)
+    acc = [0.0, 0, 0, 0]
+    for w in range(W):
+        R, _ = o.sweep(R0[w], src["uR"], seed, w, 0, n_init, mc_step)
+        step = n_init
+        for m in range(n_samples):
+            R, _ = o.sweep(R, src["uR"], seed, w, step, n_therm, mc_step)
+            step += n_therm
+            a = oracle_mix_observables(o, R, g)
+            acc = [x + y for x, y in zip(acc, a)]
+    M = W * n_samples
+    assert abs(r2 - acc[0] / M) < 1e-10 * r2
+    assert np.max(np.abs(angle - acc[1] / M)) < 1e-12
+    assert np.max(np.abs(distance - acc[3] / M)) < 1e-12
+    assert np.max(np.abs(density - acc[2] / M)) <= 1e-12 * np.max(acc[2] / M)
+    h.close()
+
+    W, n_samples = 4096, 8
+    spec, h = make_handle(capi, src, n_walkers=W, seed=99, mc_step=mc_step)
+    h.set_positions(np.broadcast_to(src["R"], (W, 3, 3)).copy())
+    r2, angle, density, distance = h.sample_cluster_observables(g, n_samples, int(g["MC_NADDITIONALTHERMSTEPS"]),
+                                                                int(g["MC_NADDITIONALINITIALIZATIONSTEPS"]))
+    n_ref, n_gpu = float(g["MC_NADDITIONALSTEPS"]) / 4.0, W * n_samples / 4.0
+    for got, want in ((angle, g["angle_mean"]), (distance, g["distance_mean"])):
+        sig = np.sqrt(np.maximum(want, 1.0 / n_ref) * (1.0 / n_ref + 1.0 / n_gpu))      # bin frequencies: binomial
+        assert np.all(np.abs(got - want) < 6.0 * sig), float(np.max(np.abs(got - want) / sig))
+    assert abs(angle.sum(axis=1) - 1.0).max() < 1e-12 and abs(distance.sum(axis=1) - 1.0).max() < 1e-3
+    assert abs(r2 - float(g["r2_mean"])) < 0.05 * float(g["r2_mean"])
+    h.close()

@@ -42,6 +42,7 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(capi.SystemDesc) == 8 * 4 + 2 * 8 + 6 * 8 + 4 * 4 + 3 * 8
     assert C.sizeof(capi.MixtureDesc) == 2 * 4 + 7 * 8
     assert C.sizeof(capi.ObservableDesc) == 2 * 4 + 3 * 8 + 3 * 8
+    assert C.sizeof(capi.ClusterObservableDesc) == 4 * 4 + 5 * 8 + 8
     assert C.sizeof(capi.EnsembleDesc) == 6 * 4 + 8 + 8
     assert C.sizeof(capi.Estimators) == 7 * 8 + 3 * 8
 

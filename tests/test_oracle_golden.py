@@ -234,3 +234,17 @@ def test_observable_grid_builder_matches_reference(golden, name):
     shells = [ints[obs.shell_ptr[k]:obs.shell_ptr[k + 1]].tolist() for k in range(obs.n_shells)]
     ptr, kv = observables.wave_vectors(shells, L)
     assert np.array_equal(ptr, obs.shell_ptr) and np.array_equal(kv, obs.kvec)
+
+
+@pytest.mark.parametrize("tag", ["fixture", "compact", "stretched", "equil"])
+def test_mixture_observables_oracle_matches_reference(golden, tag):
+    from oracle_lib import OracleMix, oracle_mix_observables
+    g = golden("mixture_he4he4na_obs")
+    src = golden(f"mixture_he4he4na_{tag}")
+    o = OracleMix(systems.from_golden(src))
+    r2, angle, density, distance = oracle_mix_observables(o, src["R"], g)
+    assert abs(r2 - float(g[f"{tag}_r2_fixed"])) < 1e-13 * r2
+    assert np.array_equal(angle, g[f"{tag}_angle_fixed"])
+    assert np.array_equal(distance, g[f"{tag}_distance_fixed"])
+    assert np.max(np.abs(density - g[f"{tag}_density_fixed"])) <= 1e-15 * np.max(g[f"{tag}_density_fixed"])
+    assert angle.sum() == 3 and distance.sum() == 3
