@@ -336,6 +336,27 @@ def gen_observables():
         dict(MC_STEP=0.5, MC_NADDITIONALSTEPS=1500, MC_NADDITIONALTHERMSTEPS=216, MC_NADDITIONALINITIALIZATIONSTEPS=4320, seed=6))
 
 
+def gen_he_observables():
+    """HeBulk / HeDrop CalculateAdditionalSystemProperties (HeBulk.cpp:413-448, HeDrop.cpp:655-702): the other expectation
+    values followed by S(k) per shell (and r2 for the droplet), on the equilibrated evaluation configurations."""
+    for name, system in (("hebulk_n64_equil", "HeBulk"), ("hedrop_n6_equil", "HeDrop")):
+        g = np.load(os.path.join(GOLDEN, name + ".npz"))
+        scal = dict(N=int(g["N"]), LBOX=float(g["LBOX"]), N_PARAM=int(g["N_PARAM"]), phiR=float(g["phiR"]), phiI=float(g["phiI"]))
+        arr = dict(R=g["R"], uR=g["uR"], uI=g["uI"])
+        with tempfile.TemporaryDirectory() as td:
+            cp, op = os.path.join(td, "case.txt"), os.path.join(td, "out.txt")
+            write_case(cp, system, scal, arr)
+            run("obs", cp, op)
+            d = parse_dump(op)
+        n_other = int(d["n_other"])
+        n_sh = len(d["k_shell_sizes"])
+        out = dict(source=np.array(name), system=np.array(system), LBOX=g["LBOX"], N=g["N"], n_other=np.array(n_other),
+                   other_fixed=d["additional_fixed"][:n_other], sk_fixed=d["additional_fixed"][n_other:n_other + n_sh],
+                   tail_fixed=d["additional_fixed"][n_other + n_sh:], k_shell_sizes=d["k_shell_sizes"], k_vectors=d["k_vectors"])
+        np.savez_compressed(os.path.join(GOLDEN, name.replace("_equil", "_obs") + ".npz"), **out)
+        print(f"{name}: n_other={n_other} shells={n_sh} kvecs={int(np.sum(d['k_shell_sizes']))} tail={out['tail_fixed']}")
+
+
 def gen_mixture_observables():
     """BosonMixtureCluster::CalculateAdditionalSystemProperties (BosonMixtureCluster.cpp:680-741): r2, corner angles,
     density from the centre of mass, pair distances - on the four evaluation configurations, and the reference's own
@@ -636,7 +657,7 @@ def main():
     if not os.path.exists(HARNESS):
         sys.exit("build the oracle first: make -C oracle/ref_build")
     which = sys.argv[1:] or ["min_image", "bosonsbulk", "bosonsbulk_mc", "nubosonsbulkpb", "nubosonsbulkpb_full", "hebulk", "hedrop",
-                             "mixture", "observables", "mixture_observables", "evolution"]
+                             "mixture", "observables", "he_observables", "mixture_observables", "evolution"]
     for w in which:
         globals()["gen_" + w]()
 

@@ -512,6 +512,26 @@ int ModeObs(const Case& c, const std::string& out)
     auto mix = dynamic_cast<PhysicalSystems::BosonMixtureCluster*>(sys);
     if (auto s = dynamic_cast<PhysicalSystems::BosonsBulk*>(sys)) DumpObservableSetup(d, s);
     else if (auto s = dynamic_cast<PhysicalSystems::NUBosonsBulkPB*>(sys)) DumpObservableSetup(d, s);
+    else if (dynamic_cast<PhysicalSystems::HeBulk*>(sys) || dynamic_cast<PhysicalSystems::HeDrop*>(sys))
+    {
+        // HeBulk.cpp:413-448 / HeDrop.cpp:655-702: [otherExpectationValues | S(k) per shell | (HeDrop) r2]
+        d.vec("additional_fixed", sys->GetAdditionalSystemProperties());
+        d.scalar("n_other", (double)sys->GetNumOfOtherExpectationValues());
+        std::vector<double> flat, sizes;
+        auto dumpK = [&](const std::vector<std::vector<std::vector<double> > >& kv, int nk) {
+            for (int k = 0; k < nk; k++)
+            {
+                sizes.push_back((double)kv[k].size());
+                for (auto& v : kv[k])
+                    for (double x : v) flat.push_back(x);
+            }
+        };
+        if (auto s = dynamic_cast<PhysicalSystems::HeBulk*>(sys)) dumpK(s->kValues, s->numOfkValues);
+        if (auto s = dynamic_cast<PhysicalSystems::HeDrop*>(sys)) dumpK(s->kValues, s->numOfkValues);
+        d.vec("k_shell_sizes", sizes);
+        d.vec("k_vectors", flat);
+        return 0;
+    }
     else if (mix)
     {
         // BosonMixtureCluster.cpp:327-345, 680-741: r2, corner angles, density from the centre of mass, pair distances

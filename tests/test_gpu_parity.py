@@ -955,3 +955,18 @@ def test_cluster_observables_sampled_replay_oracle_and_match_reference(capi, gol
     assert abs(angle.sum(axis=1) - 1.0).max() < 1e-12 and abs(distance.sum(axis=1) - 1.0).max() < 1e-3
     assert abs(r2 - float(g["r2_mean"])) < 0.05 * float(g["r2_mean"])
     h.close()
+
+
+@pytest.mark.parametrize("name", ["hebulk_n64_obs", "hedrop_n6_obs"])
+def test_he_structure_factor_matches_reference(capi, golden, name):
+    """S(k) of the He systems' CalculateAdditionalSystemProperties (HeBulk.cpp:432-447: 300 shells, 3976 wave vectors;
+    HeDrop.cpp:674-689) through the same observables kernel (no g(r) grid: their g(r) lives in the other values)."""
+    from tdvmc_b200 import observables
+    g = golden(name)
+    src = golden(str(g["source"]))
+    ptr = np.concatenate([[0], np.cumsum(g["k_shell_sizes"].astype(np.int64))]).astype(np.int32)
+    obs = observables.ObservableSpec(0, 1.0, 1.0, 1.0, np.ones(1), ptr, g["k_vectors"].reshape(-1, 3))
+    spec, h = make_handle(capi, src)
+    _, sk = h.observables_fixed(obs, src["R"][None])
+    assert np.max(np.abs(sk[0] - g["sk_fixed"])) <= 1e-10 * np.max(np.abs(g["sk_fixed"]))
+    h.close()

@@ -248,3 +248,17 @@ def test_mixture_observables_oracle_matches_reference(golden, tag):
     assert np.array_equal(distance, g[f"{tag}_distance_fixed"])
     assert np.max(np.abs(density - g[f"{tag}_density_fixed"])) <= 1e-15 * np.max(g[f"{tag}_density_fixed"])
     assert angle.sum() == 3 and distance.sum() == 3
+
+
+@pytest.mark.parametrize("name", ["hebulk_n64_obs", "hedrop_n6_obs"])
+def test_he_structure_factor_oracle_matches_reference(golden, name):
+    """S(k) part of HeBulk / HeDrop CalculateAdditionalSystemProperties (HeBulk.cpp:432-447, HeDrop.cpp:674-689)."""
+    from oracle_lib import oracle_observables
+    from tdvmc_b200 import observables
+    g = golden(name)
+    src = golden(str(g["source"]))
+    ptr = np.concatenate([[0], np.cumsum(g["k_shell_sizes"].astype(np.int64))]).astype(np.int32)
+    obs = observables.ObservableSpec(0, 1.0, 1.0, 1.0, np.ones(1), ptr, g["k_vectors"].reshape(-1, 3))
+    _, sk = oracle_observables(float(g["LBOX"]), src["R"], obs)
+    assert np.max(np.abs(sk - g["sk_fixed"])) <= 1e-11 * np.max(np.abs(g["sk_fixed"]))
+    assert np.array_equal(g["other_fixed"], src["other_expectation_values"])      # the first block is the ordinary "other" values
