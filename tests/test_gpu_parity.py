@@ -402,6 +402,45 @@ def test_update_stored_samples_replays_oracle(capi, golden):
     h.close()
 
 
+@pytest.mark.parametrize("N", [2, 3, 33, 65, 96, 128, 400, 416, 700])
+def test_evaluate_tile_schedule_edge_sizes(capi, golden, N):
+    """The evaluation kernel's 32x32 tile schedule at particle counts that hit its corner cases - a single partial tile,
+    odd and even tile counts (the half shift), partial last tiles, more tiles than warps (N = 400, 416: several tiles
+    per warp and shift; 700: the 24-warp variant) - against the pinned oracle on random configurations in the N = 64
+    fixture's box and spline table (density is irrelevant to the arithmetic)."""
+    g = golden("bosonsbulk_n64_equil")
+    L, P = float(g["LBOX"]), int(g["N_PARAM"])
+    spec = systems.bosons_bulk(N, L, P, g["SYSTEM_PARAMS"], weights=g["spline_weights"])
+    h = capi.Handle(spec, 2)
+    h.set_params(g["uR"], g["uI"], float(g["phiR"]), float(g["phiI"]), float(g["time"]))
+    rng = np.random.default_rng(N)
+    R = rng.uniform(-L / 2, L / 2, (2, N, 3))
+    if N <= 3:
+        R *= 0.3                                                  # keep the few particles inside each other's cut
+    R[1] += rng.integers(-2, 3, (N, 3)) * L                      # second configuration: unwrapped images
+    ev = h.evaluate_fixed(R)
+    o = Oracle(spec, time=float(g["time"]))
+    for c in range(2):
+        ref = o.evaluate(R[c], g["uR"], g["uI"], float(g["phiR"]))
+        assert rel(ev["O"][c], ref["O"]) < RTOL
+        assert abs(ref["e_r"]) > 0 and abs(ev["e_r"][c] - ref["e_r"]) < RTOL * abs(ref["e_r"])
+        assert abs(ev["e_i"][c] - ref["e_i"]) < RTOL * max(abs(ref["e_i"]), abs(ref["e_r"]))
+        assert abs(ev["exponent"][c] - ref["exponent"]) < RTOL * abs(ref["exponent"])
+        scale = np.max(np.abs(ref["drift_r"])) + 1e-300
+        assert np.max(np.abs(ev["drift_r"][c] - ref["drift_r"])) < RTOL * scale * 10
+        assert np.max(np.abs(ev["drift_i"][c] - ref["drift_i"])) < RTOL * (np.max(np.abs(ref["drift_i"])) + 1e-300) * 10
+    # the sweep at the same sizes: chain replay for a few steps
+    h.set_positions(R[:, :, :])
+    h.sweep(40)
+    Rg = h.get_positions()
+    for c in range(2):
+        Rr, _ = o.sweep(R[c], g["uR"], 1, c, 0, 40, 0.5)
+        d = Rg[c] - Rr
+        d -= L * np.round(d / L)
+        assert np.max(np.abs(d)) < 1e-9
+    h.close()
+
+
 def test_errors_are_loud(capi, golden):
     g = golden("bosonsbulk_n64_fixture")
     spec = systems.from_golden(g)
@@ -479,6 +518,11 @@ ens = GpuEnsembleSystem(spec, W, mc_step=0.4, seed=21, rank=rank, world=world, d
 R = np.stack([g["R"] + 0.002 * w for w in range(W)])
 ens.SetPositions(R[ens.first_walker:ens.first_walker + ens.n_local])
 e = ens.ParallelUpdateExpectationValues(g["uR"], g["uI"], float(g["phiR"]), float(g["phiI"]), 2, 64, 32, float(g["time"]))
+from tdvmc_b200 import observables
+go = np.load(os.path.join(root, "tests", "golden", "bosonsbulk_n64_obs.npz"))
+o = ens.ParallelCalculateAdditionalSystemProperties(g["uR"], g["uI"], float(g["phiR"]), float(g["phiI"]),
+                                                    observables.from_golden(go), 3, 40, 20, float(g["time"]))
+e["pairDistribution"], e["structureFactor"] = o["pairDistribution"], o["structureFactor"]
 np.savez(os.path.join(tmp, f"rank{rank}.npz"), **{k: np.asarray(v) for k, v in e.items()})
 ens.close()
 """
@@ -502,9 +546,12 @@ def test_two_gpu_allreduce_matches_single_gpu(capi, golden, tmp_path):
     h.set_positions(np.stack([g["R"] + 0.002 * w for w in range(10)]))
     h.sample_and_accumulate(2, 64, 32)
     one = h.allreduce_and_fetch()
+    from tdvmc_b200 import observables
+    gr1, sk1 = h.sample_observables(observables.from_golden(golden("bosonsbulk_n64_obs")), 3, 40, 20)
     h.close()
     for r in range(2):
         two = np.load(tmp_path / f"rank{r}.npz")
+        assert rel(two["pairDistribution"], gr1) < 1e-13 and rel(two["structureFactor"], sk1) < 1e-12
         assert int(two["nSamples"]) == 20 and int(two["nTrials"]) == one["n_trials"]
         assert int(two["nAcceptances"]) == one["n_acceptances"]
         assert rel(two["localOperators"], one["O"]) < 1e-13
