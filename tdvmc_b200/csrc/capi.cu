@@ -733,7 +733,7 @@ int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed,
     int best_wpb = 1, best_res = 0, best_score = -1;
     for (int wpb = 1; wpb <= kSweepMaxThreads / 32; wpb++)
     {
-        const int res = sweep_blocks_per_sm(s, wpb, h->npp) * wpb; // walkers resident per SM
+        const int res = sweep_blocks_per_sm(s, wpb, h->npp) * wpb; // warps resident per SM
         const int score = res >= 4 ? (res / 4) * 4 * 2 + (res % 4 == 0 ? 1 : 0) : res;
         if (score >= best_score && res > 0) // ties: the larger block shares one copy of the coefficient planes
         {
@@ -751,7 +751,7 @@ int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed,
             best_res = sweep_blocks_per_sm(s, wpb, h->npp) * wpb;
         }
     }
-    h->resident_per_sm = best_res;
+    h->resident_per_sm = best_res * sweep_walkers_per_warp(s); // walkers
     if (best_res == 0)
     {
         h->error = "system does not fit the sweep kernel's shared memory";

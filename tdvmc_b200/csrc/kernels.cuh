@@ -17,7 +17,7 @@ struct SweepArgs
     unsigned long long* accepted; // [W]
     int W;                        // local walkers
     int first_walker;             // global id of local walker 0
-    int wpb;                      // walkers (= warps) per block
+    int wpb;                      // warps per block (one walker per warp; 2 or 4 for systems of <= 16 / <= 8 particles)
     int npp;                      // padded row length of the shared-memory position arrays
     int pos_offset;               // byte offset of the position arrays in dynamic shared memory
     uint64_t seed;
@@ -27,6 +27,7 @@ struct SweepArgs
 };
 cudaError_t launch_sweep(SweepArgs a, cudaStream_t st);
 int sweep_blocks_per_sm(const SysDev& s, int wpb, int npp);
+int sweep_walkers_per_warp(const SysDev& s);
 
 // ---- K2+K3+K4: fused evaluation of one configuration per block (evaluate.cu) ----
 struct EvalArgs

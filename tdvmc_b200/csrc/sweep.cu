@@ -75,6 +75,21 @@ __device__ __forceinline__ double sqrt_fast(double x)
     return fma(t * e, p, t);              // t (1 + e/2 + 3 e^2/8)
 }
 
+// sum over the GROUP lanes of a walker (all lanes of the warp take part)
+template <int GROUP>
+__device__ __forceinline__ double group_sum(double v)
+{
+#pragma unroll
+    for (int o = GROUP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+    return v;
+}
+
+// lanes per walker for a system of N particles
+static inline int sweep_group(const SysDev& s)
+{
+    return s.N <= 8 ? 8 : (s.N <= 16 ? 16 : 32);
+}
+
 // pair term of the exponent at distance r, with the system's cut rule
 template <bool UNIFORM, bool REFLECT, int STRIDE, bool HE = false>
 __device__ __forceinline__ double pair_u(const SysDev& s, const double2* __restrict__ c01p, const double2* __restrict__ c23p,
@@ -118,13 +133,18 @@ __device__ __forceinline__ double pair_u(const SysDev& s, const double2* __restr
     return v;
 }
 
-template <bool UNIFORM, bool REFLECT, int UNROLL, bool HE = false, bool OPEN = false>
+// GROUP = lanes per walker (32, or 16 / 8 for systems of at most 16 / 8 particles, where a whole warp per walker would
+// leave most lanes without a partner: HeDrop's six atoms run four walkers per warp).
+template <bool UNIFORM, bool REFLECT, int UNROLL, bool HE = false, bool OPEN = false, int GROUP = 32>
 __global__ void __launch_bounds__(kSweepMaxThreads, kSweepMinBlocks) sweep_kernel(SweepArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SysDev& s = a.s;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    constexpr int WPW = 32 / GROUP;          // walkers per warp
+    const int gl = lane & (GROUP - 1);       // lane within the walker's group
+    const int grp = lane / GROUP;
     const int Npp = a.npp;
     const int nrec = s.nbins + 1;
 
@@ -153,16 +173,15 @@ __global__ void __launch_bounds__(kSweepMaxThreads, kSweepMinBlocks) sweep_kerne
     const double2* c23p = c23s + (lane & (kCubCopies - 1));
     const double2* ttp = tts;
 
-    const int w = blockIdx.x * a.wpb + warp; // local walker
-    double* px = pos_base + (size_t)warp * 3 * Npp;
+    const int w = (blockIdx.x * a.wpb + warp) * WPW + grp; // local walker
+    double* px = pos_base + (size_t)(warp * WPW + grp) * 3 * Npp;
     double* py = px + Npp;
     double* pz = py + Npp;
     const bool have = w < a.W;
-    double* gpos = a.pos + (size_t)(have ? w : 0) * 3 * s.Np;
+    double* gpos = a.pos + (size_t)(have ? w : 0) * 3 * s.Np; // a group without a walker idles on a copy of walker 0
     const double L = s.L, Linv = s.Linv, Lhalf = s.Lhalf;
-    if (have)
     {
-        for (int i = lane; i < s.N; i += 32) // positions live wrapped into the first cell during the sweep
+        for (int i = gl; i < s.N; i += GROUP) // positions live wrapped into the first cell during the sweep
         {
             px[i] = OPEN ? gpos[i] : wrap_fast(gpos[i], L, Linv);
             py[i] = OPEN ? gpos[s.Np + i] : wrap_fast(gpos[s.Np + i], L, Linv);
@@ -170,29 +189,29 @@ __global__ void __launch_bounds__(kSweepMaxThreads, kSweepMinBlocks) sweep_kerne
         }
     }
     __syncthreads();
-    if (!have) return;
+    if (GROUP == 32 && !have) return; // (smaller groups stay: the warp's shuffles need every lane)
 
     const uint32_t gw = (uint32_t)(a.first_walker + w);
     const int N = s.N;
     unsigned long long n_acc = 0;
 
-    for (long long t0 = 0; t0 < a.n_steps; t0 += 32)
+    for (long long t0 = 0; t0 < a.n_steps; t0 += GROUP)
     {
-        // every lane draws the proposal of one of the next 32 steps
+        // every lane draws the proposal of one of its walker's next GROUP steps
         Proposal mine;
         mine.particle = 0;
         mine.dx = mine.dy = mine.dz = 0.0;
         mine.log_u = 0.0;
-        if (t0 + lane < a.n_steps) mine = make_proposal(a.seed, gw, a.first_step + (uint64_t)(t0 + lane), N, a.mc_step);
-        const int nsub = (int)min(32ll, a.n_steps - t0);
+        if (t0 + gl < a.n_steps) mine = make_proposal(a.seed, gw, a.first_step + (uint64_t)(t0 + gl), N, a.mc_step);
+        const int nsub = (int)min((long long)GROUP, a.n_steps - t0);
 
         for (int sidx = 0; sidx < nsub; sidx++)
         {
-            const int p = __shfl_sync(FULL_MASK, mine.particle, sidx);
-            const double ddx = __shfl_sync(FULL_MASK, mine.dx, sidx);
-            const double ddy = __shfl_sync(FULL_MASK, mine.dy, sidx);
-            const double ddz = __shfl_sync(FULL_MASK, mine.dz, sidx);
-            const double log_u = __shfl_sync(FULL_MASK, mine.log_u, sidx);
+            const int p = __shfl_sync(FULL_MASK, mine.particle, sidx, GROUP);
+            const double ddx = __shfl_sync(FULL_MASK, mine.dx, sidx, GROUP);
+            const double ddy = __shfl_sync(FULL_MASK, mine.dy, sidx, GROUP);
+            const double ddz = __shfl_sync(FULL_MASK, mine.dz, sidx, GROUP);
+            const double log_u = __shfl_sync(FULL_MASK, mine.log_u, sidx, GROUP);
 
             const double ox = px[p], oy = py[p], oz = pz[p];
             const double nx = OPEN ? ox + ddx : wrap_fast(ox + ddx, L, Linv); // src/TDVMC.cpp:872-875, kept in the first cell
@@ -201,7 +220,7 @@ __global__ void __launch_bounds__(kSweepMaxThreads, kSweepMinBlocks) sweep_kerne
 
             double delta = 0.0;
 #pragma unroll UNROLL
-            for (int i = lane; i < N; i += 32)
+            for (int i = gl; i < N; i += GROUP)
             {
                 const double xi = px[i], yi = py[i], zi = pz[i];
                 const double r_old = sqrt_fast(dist2<OPEN>(xi - ox, yi - oy, zi - oz, Lhalf));
@@ -211,7 +230,7 @@ __global__ void __launch_bounds__(kSweepMaxThreads, kSweepMinBlocks) sweep_kerne
                 const double d = u_new - u_old;
                 if (i != p) delta += d;
             }
-            delta = warp_sum(delta);
+            delta = group_sum<GROUP>(delta);
 
             // quotient = exp(2 delta) must be finite and >= U (src/TDVMC.cpp:886-913), in the log domain
             const double two_delta = 2.0 * delta;
@@ -219,7 +238,7 @@ __global__ void __launch_bounds__(kSweepMaxThreads, kSweepMinBlocks) sweep_kerne
             __syncwarp(); // every lane has read the old positions before lane 0 overwrites one
             if (accept)
             {
-                if (lane == 0)
+                if (gl == 0)
                 {
                     px[p] = nx;
                     py[p] = ny;
@@ -231,13 +250,14 @@ __global__ void __launch_bounds__(kSweepMaxThreads, kSweepMinBlocks) sweep_kerne
         }
     }
 
-    for (int i = lane; i < N; i += 32)
+    if (!have) return;
+    for (int i = gl; i < N; i += GROUP)
     {
         gpos[i] = px[i];
         gpos[s.Np + i] = py[i];
         gpos[2 * s.Np + i] = pz[i];
     }
-    if (lane == 0) a.accepted[w] += n_acc;
+    if (gl == 0) a.accepted[w] += n_acc;
 }
 
 // exponentNew - exponent for scripted moves of one configuration: the ratio evaluator of the sweep,
@@ -306,17 +326,7 @@ size_t sweep_smem_bytes(const SysDev& s, int wpb, int npp, size_t* pos_offset)
     if (!s.uniform) off += nrec * sizeof(double2) + (size_t)s.ncell * sizeof(unsigned short);
     off = (off + 15) & ~(size_t)15;
     *pos_offset = off;
-    return off + (size_t)wpb * 3 * npp * sizeof(double);
-}
-
-template <bool U, bool R, int UNROLL, bool HE = false, bool OPEN = false>
-static cudaError_t launch_one(const SweepArgs& a, int grid, int threads, size_t smem, cudaStream_t st)
-{
-    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<U, R, UNROLL, HE, OPEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    cudaFuncSetAttribute(sweep_kernel<U, R, UNROLL, HE, OPEN>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    sweep_kernel<U, R, UNROLL, HE, OPEN><<<grid, threads, smem, st>>>(a);
-    return cudaGetLastError();
+    return off + (size_t)wpb * (32 / sweep_group(s)) * 3 * npp * sizeof(double);
 }
 
 static int sweep_unroll()
@@ -331,25 +341,26 @@ static int sweep_unroll()
     return u;
 }
 
-template <int UNROLL>
-static const void* sweep_fn(const SysDev& s)
+// the kernel instance for a system: (uniform knots, reflection rule, He family, open boundary) x unroll x lanes per walker
+template <int UNROLL, int GROUP>
+static const void* sweep_fn_ug(const SysDev& s)
 {
     const bool refl = s.pair_rule == 1;
-    if (s.kind == 1) return (const void*)sweep_kernel<true, false, UNROLL, true>;
-    if (s.kind == 2) return (const void*)sweep_kernel<false, false, UNROLL, true, true>;
-    return s.uniform ? (refl ? (const void*)sweep_kernel<true, true, UNROLL> : (const void*)sweep_kernel<true, false, UNROLL>)
-                     : (refl ? (const void*)sweep_kernel<false, true, UNROLL> : (const void*)sweep_kernel<false, false, UNROLL>);
+    if (s.kind == 1) return (const void*)sweep_kernel<true, false, UNROLL, true, false, GROUP>;
+    if (s.kind == 2) return (const void*)sweep_kernel<false, false, UNROLL, true, true, GROUP>;
+    return s.uniform ? (refl ? (const void*)sweep_kernel<true, true, UNROLL, false, false, GROUP>
+                             : (const void*)sweep_kernel<true, false, UNROLL, false, false, GROUP>)
+                     : (refl ? (const void*)sweep_kernel<false, true, UNROLL, false, false, GROUP>
+                             : (const void*)sweep_kernel<false, false, UNROLL, false, false, GROUP>);
 }
 
-template <int UNROLL>
-static cudaError_t launch_unroll(const SweepArgs& a, int grid, int threads, size_t smem, cudaStream_t st)
+static const void* sweep_fn(const SysDev& s)
 {
-    const bool refl = a.s.pair_rule == 1;
-    if (a.s.kind == 1) return launch_one<true, false, UNROLL, true>(a, grid, threads, smem, st);
-    if (a.s.kind == 2) return launch_one<false, false, UNROLL, true, true>(a, grid, threads, smem, st);
-    if (a.s.uniform)
-        return refl ? launch_one<true, true, UNROLL>(a, grid, threads, smem, st) : launch_one<true, false, UNROLL>(a, grid, threads, smem, st);
-    return refl ? launch_one<false, true, UNROLL>(a, grid, threads, smem, st) : launch_one<false, false, UNROLL>(a, grid, threads, smem, st);
+    const int g = sweep_group(s);
+    if (g == 8) return sweep_fn_ug<1, 8>(s);   // one partner per lane at most: nothing to unroll
+    if (g == 16) return sweep_fn_ug<1, 16>(s);
+    const int u = sweep_unroll();
+    return u == 1 ? sweep_fn_ug<1, 32>(s) : (u == 4 ? sweep_fn_ug<4, 32>(s) : sweep_fn_ug<2, 32>(s));
 }
 
 cudaError_t launch_sweep(SweepArgs a, cudaStream_t st)
@@ -357,14 +368,20 @@ cudaError_t launch_sweep(SweepArgs a, cudaStream_t st)
     size_t pos_off;
     size_t smem = sweep_smem_bytes(a.s, a.wpb, a.npp, &pos_off);
     a.pos_offset = (int)pos_off;
-    int grid = (a.W + a.wpb - 1) / a.wpb;
+    const int per_block = a.wpb * (32 / sweep_group(a.s)); // walkers per block
+    int grid = (a.W + per_block - 1) / per_block;
     int threads = a.wpb * 32;
-    switch (sweep_unroll())
-    {
-    case 1: return launch_unroll<1>(a, grid, threads, smem, st);
-    case 4: return launch_unroll<4>(a, grid, threads, smem, st);
-    default: return launch_unroll<2>(a, grid, threads, smem, st);
-    }
+    const void* fn = sweep_fn(a.s);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    void* args[] = { &a };
+    return cudaLaunchKernel(fn, dim3(grid), dim3(threads), args, smem, st);
+}
+
+int sweep_walkers_per_warp(const SysDev& s)
+{
+    return 32 / sweep_group(s);
 }
 
 int sweep_blocks_per_sm(const SysDev& s, int wpb, int npp)
@@ -372,8 +389,7 @@ int sweep_blocks_per_sm(const SysDev& s, int wpb, int npp)
     size_t pos_off;
     size_t smem = sweep_smem_bytes(s, wpb, npp, &pos_off);
     int nb = 0;
-    const int u = sweep_unroll();
-    const void* fn = u == 1 ? sweep_fn<1>(s) : (u == 4 ? sweep_fn<4>(s) : sweep_fn<2>(s));
+    const void* fn = sweep_fn(s);
     static int optin = -1;
     if (optin < 0)
     {
