@@ -108,11 +108,53 @@ def reference_step(cases, cpus):
     return trials, secs
 
 
+_PORT_WORKER = r"""
+import ctypes as C, os, sys, time
+import numpy as np
+root, seed = sys.argv[1], int(sys.argv[2])
+sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests"))
+import bench
+from oracle_lib import Oracle
+spec, uR, uI, R = bench.golden_spec()
+o = Oracle(spec)
+t0 = time.perf_counter()
+r = o.sample_walker(R, uR, uI, 0.0, seed, seed, 0, bench.MC_NINIT, bench.MC_NSTEPS, bench.MC_NTHERMSTEPS, bench.MC_STEP)
+print(bench.STEPS_PER_WALKER, time.perf_counter() - t0, bench.MC_NSTEPS)
+"""
+
+
+def port_step(cpus):
+    """Fallback when oracle/_ref was not built (no /root/reference on the build host): the plain-C restatement of the
+    reference's algorithm (oracle/tdvmc_oracle.c), one walker's pass per physical core."""
+    procs = [subprocess.Popen(["taskset", "-c", str(cpu), sys.executable, "-c", _PORT_WORKER, ROOT, str(i + 1)],
+                              stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for i, cpu in enumerate(cpus)]
+    trials, secs = 0, 0.0
+    for p in procs:
+        out = p.communicate()[0].split()
+        if p.returncode != 0 or len(out) < 3:
+            raise RuntimeError("oracle port failed (build it: make -C oracle)")
+        trials += int(out[0])
+        secs = max(secs, float(out[1]))
+    return trials, secs
+
+
+REFERENCE_KIND = "reference"
+
+
 def run_reference(steps, warmup, tmpdir, spec, uR, uI, R):
+    global REFERENCE_KIND
     harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
-    if not os.path.exists(harness):
-        raise RuntimeError("oracle/_ref/ref_harness missing: build it with `make -C oracle ref` where /root/reference exists")
     cpus = physical_cores()
+    if not os.path.exists(harness):
+        REFERENCE_KIND = "port"
+        for _ in range(warmup):
+            port_step(cpus)
+        trials, secs = 0, 0.0
+        for _ in range(steps):
+            t, sec = port_step(cpus)
+            trials += t
+            secs += sec
+        return trials, secs, len(cpus)
     cases = []
     for i, _ in enumerate(cpus):
         path = os.path.join(tmpdir, f"case_{i}.txt")
@@ -135,14 +177,15 @@ def reference_main(args, rank):
     with tempfile.TemporaryDirectory() as td:
         trials, secs, cores = run_reference(args.steps, args.warmup, td, spec, uR, uI, R)
     value = trials / secs
-    sample = (f"{cores} single-rank processes of the unmodified reference (one per physical core, taskset-pinned, "
+    what = "the unmodified reference" if REFERENCE_KIND == "reference" else "the plain-C port of the reference (oracle/tdvmc_oracle.c)"
+    sample = (f"{cores} single-rank processes of {what} (one per physical core, taskset-pinned, "
               f"serial MPI shim), each one walker's pass per step: {STEPS_PER_WALKER} proposals + {MC_NSTEPS} evaluations")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "walker-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config({"walkers": cores}),
             "time_steps_per_s": args.steps / secs,
-            "cpu_baseline": {"value": value, "unit": "walker-steps/s", "cores": cores, "kind": "reference", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "walker-steps/s", "cores": cores, "kind": REFERENCE_KIND, "sample": sample},
             "e2e": {"value": value, "unit": "walker-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -390,12 +433,14 @@ def main():
         if world == 1:
             try:
                 with tempfile.TemporaryDirectory() as td:
-                    trials, secs, cores = run_reference(1, 0, td, spec, uR, uI, R_seed)
-                cpu_baseline = {"value": trials / secs, "unit": "walker-steps/s", "cores": cores, "kind": "reference",
-                                "sample": f"{cores} pinned single-rank processes of the unmodified reference, one walker's pass each "
-                                          f"({STEPS_PER_WALKER} proposals + {MC_NSTEPS} evaluations), {secs:.2f} s"}
+                    trials, secs, cores = run_reference(3, 0, td, spec, uR, uI, R_seed)
+                what = "the unmodified reference" if REFERENCE_KIND == "reference" else "the plain-C port of the reference"
+                cpu_baseline = {"value": trials / secs, "unit": "walker-steps/s", "cores": cores, "kind": REFERENCE_KIND,
+                                "sample": f"{cores} pinned single-rank processes of {what}, three passes of one walker each "
+                                          f"({STEPS_PER_WALKER} proposals + {MC_NSTEPS} evaluations per pass), {secs:.2f} s wall, "
+                                          f"{secs * cores:.0f} core-seconds"}
             except Exception as ex:  # the baseline is a report, never the product
-                cpu_baseline = {"value": None, "unit": "walker-steps/s", "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
+                cpu_baseline = {"value": None, "unit": "walker-steps/s", "cores": 0, "kind": REFERENCE_KIND, "sample": f"failed: {ex}"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "walker-steps/s", "n_gpus": world, "steps": args.steps,
