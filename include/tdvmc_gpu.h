@@ -34,20 +34,19 @@ typedef struct tdvmc_gpu_handle tdvmc_gpu_handle;
 
 enum tdvmc_system_kind
 {
-    TDVMC_SYSTEM_SPLINE_TABLE = 0, /* BosonsBulk, NUBosonsBulkPB: monomial spline table + boundary-condition map */
-    TDVMC_SYSTEM_HE_BULK = 1       /* HeBulk (HeBulk.cpp): McMillan r^-5 core below rijSplit = 1.95, uniform cubic B-splines
-                                      in the local coordinate above it, Aziz HFD-B(He) inline, g(r) in other[3..102];
-                                      knots / spline_weights are not used (may be NULL) */
-    ,
-    TDVMC_SYSTEM_HE_DROP = 2       /* HeDrop (HeDrop.cpp): open boundary, McMillan r^-4.7 core below 3.0, 70 splines of spacing 0.1
-                                      then spacing 0.5 up to rijTail, constant + linear tails beyond, Lennard-Jones inline,
-                                      g(r) and the density profile in other[3..402]; lbox unused; wrap_positions moves the
-                                      centre of mass to zero (src/TDVMC.cpp:798-809) */
-    ,
-    TDVMC_SYSTEM_MIXTURE = 3       /* BosonMixtureCluster (BosonMixtureCluster.cpp): open boundary, several species; one basis
-                                      per pair type (see tdvmc_mixture_desc), 26 parameters per pair type, other[0..5] =
-                                      {kinR part 1, part 2, kinR, V, wf, exponent}; wrap_positions moves the mass-weighted
-                                      centre of mass to zero */
+    /* BosonsBulk, NUBosonsBulkPB: the caller's monomial spline table + boundary-condition map */
+    TDVMC_SYSTEM_SPLINE_TABLE = 0,
+    /* HeBulk (HeBulk.cpp): McMillan r^-5 core below rijSplit = 1.95, uniform cubic B-splines in the local coordinate
+     * above it, Aziz HFD-B(He) inline, g(r) in other[3..102]; knots / spline_weights are not used (may be NULL) */
+    TDVMC_SYSTEM_HE_BULK = 1,
+    /* HeDrop (HeDrop.cpp): open boundary, McMillan r^-4.7 core below 3.0, 70 splines of spacing 0.1 then spacing 0.5 up
+     * to rijTail, constant + linear tails beyond, Lennard-Jones inline, g(r) and the density profile in other[3..402];
+     * lbox unused; wrap_positions moves the centre of mass to zero (src/TDVMC.cpp:798-809) */
+    TDVMC_SYSTEM_HE_DROP = 2,
+    /* BosonMixtureCluster (BosonMixtureCluster.cpp): open boundary, several species; one basis per pair type (see
+     * tdvmc_mixture_desc), 26 parameters per pair type, other[0..5] = {kinR part 1, part 2, kinR, V, wf, exponent};
+     * wrap_positions moves the mass-weighted centre of mass to zero */
+    TDVMC_SYSTEM_MIXTURE = 3
 };
 
 /* Per-pair-type data of BosonMixtureCluster::InitSystem (BosonMixtureCluster.cpp:104-346), as data. */
