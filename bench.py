@@ -343,6 +343,32 @@ def main():
     step(True)
     ms_e2e = timed(args.steps, True)
 
+    # BASELINE's second metric, TDVMC time-steps/s: a whole time step of the outer loop (src/TDVMC.cpp:3419-3923) as the
+    # driver would run it against this library - parameters in, estimator pass, packed all-reduce, fetch, the small
+    # parameter solve on the host with LAPACK (numpy.linalg: BuildSystemOfEquations + scaling preconditioner + Cholesky,
+    # tdvmc_b200/timestep.py) and the Euler update fed back into the next step.  Every rank solves redundantly.
+    from tdvmc_b200 import timestep
+    cur = {"uR": uR.copy(), "uI": uI.copy(), "phiR": 0.0, "phiI": 0.0}
+
+    def time_step():
+        nonlocal out
+        h.set_params(cur["uR"], cur["uI"], cur["phiR"], cur["phiI"], 0.0)
+        h.sample_and_accumulate(MC_NSTEPS, MC_NTHERMSTEPS, MC_NINIT)
+        out = h.allreduce_and_fetch(out)
+        est = dict(localOperators=out["O"], localOperatorsMatrix=out["S"], localOperatorlocalEnergyR=out["OER"],
+                   localOperatorlocalEnergyI=out["OEI"], localEnergyR=float(out["e_r"][0]), localEnergyI=float(out["e_i"][0]))
+        cur["uR"], cur["uI"], cur["phiR"], cur["phiI"] = timestep.euler_step(1e-7, cur["uR"], cur["uI"], cur["phiR"], cur["phiI"],
+                                                                             est, imaginary_time=0, lapack=True, min_scaling=1e-12)
+        h.flush_l2()
+
+    time_step()
+    barrier()
+    h.timer_start()
+    for _ in range(args.steps):
+        time_step()
+    ms_ts = max_over_ranks(h.timer_stop())
+    barrier()
+
     proposals = float(W) * world * STEPS_PER_WALKER * args.steps
     value = proposals / (ms_total * 1e-3)
     e2e_value = proposals / (ms_e2e * 1e-3)
@@ -448,7 +474,10 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config({"walkers_per_gpu": W, "walkers": W * world, "parallelism": f"walkers x{world}",
                                            "l2": "flushed between steps (256 MiB memset); walker state is 29 MB per GPU"}),
-                "time_steps_per_s": args.steps / (ms_total * 1e-3),
+                "time_steps_per_s": args.steps / (ms_ts * 1e-3),
+                "time_step": {"ms": ms_ts / args.steps, "samples_per_time_step": W * world * MC_NSTEPS,
+                              "includes": "set_params, estimator pass, all-reduce, fetch, host LAPACK solve of S u' = F "
+                                          "(P = 201, numpy.linalg), Euler update; every rank solves redundantly"},
                 "e2e": {"value": e2e_value, "unit": "walker-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,

@@ -60,17 +60,28 @@ def cholesky_solve(A, rhs_list):
     return out
 
 
-def solve_for_parameters_dot(est, imaginary_time=1, use_preconditioning=True, regularization=0.001):
-    """SolveForParametersDot with LINEAR_EQUATION_SOLVER_TYPE = 0: returns (uDotR, uDotI, phiDotR, phiDotI)."""
+def solve_for_parameters_dot(est, imaginary_time=1, use_preconditioning=True, regularization=0.001, lapack=False,
+                             min_scaling=0.0):
+    """SolveForParametersDot with LINEAR_EQUATION_SOLVER_TYPE = 0: returns (uDotR, uDotI, phiDotR, phiDotI).
+    lapack=True factorises with numpy's LAPACK (dpotrf/dpotrs through numpy.linalg) instead of the reference's
+    hand-written loops - same matrix, same right-hand sides, results equal to rounding."""
     A, b_r, b_i = build_system_of_equations(est, imaginary_time)
     scal = np.ones(len(b_r))
     if use_preconditioning:
-        scal = np.sqrt(np.diag(A)).copy()
+        scal = np.sqrt(np.maximum(np.diag(A), 0.0))
+        if min_scaling > 0.0:            # a parameter whose operator never varied (empty knot interval): the reference would
+            scal = np.maximum(scal, min_scaling)   # divide by zero here; callers that cannot rule it out pass a floor
         A = A / np.outer(scal, scal)
         b_r = b_r / scal
         b_i = b_i / scal
     A = A + regularization * np.eye(len(b_r))
-    u_r, u_i = cholesky_solve(A, [b_r, b_i])
+    if lapack:
+        L = np.linalg.cholesky(A)
+        y = np.linalg.solve(L, np.stack([b_r, b_i], axis=1))
+        x = np.linalg.solve(L.T, y)
+        u_r, u_i = x[:, 0], x[:, 1]
+    else:
+        u_r, u_i = cholesky_solve(A, [b_r, b_i])
     O = np.asarray(est["localOperators"], np.float64)
     phi_r = -float(np.dot(O, u_r))      # CalculatePhiDot runs BEFORE the scalings are divided out (:1743-1752)
     phi_i = -float(np.dot(O, u_i))

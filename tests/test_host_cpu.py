@@ -231,6 +231,8 @@ def test_timestep_solver_matches_reference(golden):
     assert np.max(np.abs(u_i - g["first_uDotI"])) < 1e-9 * max(np.max(np.abs(g["first_uDotI"])), 1e-300) + 1e-12
     assert abs(p_r - float(g["first_phiDotR"])) < 1e-9 * abs(float(g["first_phiDotR"]))
     assert abs(p_i - float(g["first_phiDotI"])) < 1e-9 * max(abs(float(g["first_phiDotI"])), 1.0)
+    v_r, v_i, q_r, q_i = timestep.solve_for_parameters_dot(est, imaginary_time=int(g["IMAGINARY_TIME"]), lapack=True)
+    assert np.max(np.abs(v_r - u_r)) < 1e-9 * scale and abs(q_r - p_r) < 1e-9 * abs(p_r)
     # numpy's own solver agrees with the hand-written Cholesky
     A, b_r, _ = timestep.build_system_of_equations(est, 1)
     s = np.sqrt(np.diag(A))
