@@ -243,6 +243,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--walkers-per-gpu", type=int, default=0, help="0: one full wave of the sweep kernel")
+    ap.add_argument("--total-walkers", type=int, default=0,
+                    help="fixed ensemble split over the GPUs (strong scaling); default: fixed walkers per GPU (weak)")
     ap.add_argument("--no-exhibits", action="store_true", help="skip the K3/K4/K5 roofline exhibits and the CPU baseline")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -273,6 +275,10 @@ def main():
     per_sm, sms = probe.resident_walkers()
     probe.close()
     W = args.walkers_per_gpu or per_sm * sms
+    scaling = "weak"
+    if args.total_walkers > 0:
+        W = max(1, args.total_walkers // world)
+        scaling = "strong"
     first = rank * W
     h = capi.Handle(spec, W, seed=1, mc_step=MC_STEP, first_walker=first, max_samples=MC_NSTEPS, device=local_rank)
     if world > 1:
@@ -455,6 +461,21 @@ def main():
                         "achieved": syrk_flops / t_acc / 1e12, "peak": dgemm_tf, "unit": "TFLOP/s",
                         "frac": syrk_flops / t_acc / 1e12 / dgemm_tf, "peak_source": "cuBLAS DGEMM 4096^3 measured in this run",
                         "dmma_probe_tflops": dmma_peak, "flop_convention": "symmetric: M (P+3)(P+4)", "ms": t_acc * 1e3})
+        # the same kernel at M = 2^16 and 2^20 (the sample counts of config 4's S-matrix)
+        for logm in (16, 20):
+            Mx = 1 << logm
+            reps = Mx // M if Mx > M else 1
+            Ox = np.tile(O, (reps, 1))[:Mx] if Mx > M else O[:Mx]
+            erx, eix = np.resize(er, Mx), np.resize(ei, Mx)
+            h.profile(True, True)
+            h.accumulate_fixed(Ox, erx, eix)
+            stx = h.kernel_stats()
+            h.profile(False, False)
+            tx = stx["accumulate"][1] / stx["accumulate"][0] * 1e-3
+            fl = float(Mx) * (N_PARAM + 3) * (N_PARAM + 4)
+            kernels.append({"kernel": f"syrk_kernel (K5, M=2^{logm})", "bound": "tensor", "achieved": fl / tx / 1e12, "peak": dgemm_tf,
+                            "unit": "TFLOP/s", "frac": fl / tx / 1e12 / dgemm_tf, "ms": tx * 1e3})
+            del Ox
         # CPU baseline: the unmodified reference on this box's host cores, one pass per core
         if world == 1:
             try:
@@ -470,7 +491,7 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "walker-steps/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": scaling,
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config({"walkers_per_gpu": W, "walkers": W * world, "parallelism": f"walkers x{world}",
                                            "l2": "flushed between steps (256 MiB memset); walker state is 29 MB per GPU"}),
