@@ -23,6 +23,10 @@
 // (14.01 vs 14.07 ms per launch): the conversions issue at 14 lanes/clk/SM (profiles/microbench/
 // conv_throughput.cu) and with five warps per scheduler they serialise with the FP64 work instead of
 // overlapping it (ncu: FP64 53 % + conversion unit 49 %).
+// Also not kept: deciding the fold on the integer pipe (64-bit compare of |d|'s bits with those of L/2, then ONE FP64
+// add |d| - (wrap ? L : 0)): 21 instead of 24 FP64 instructions per pair but 48 instead of 36 instructions in all,
+// and the launch went from 13.7 to 15.4 ms - with five warps per scheduler the issue slots matter as much as the
+// FP64 pipe.
 // A second capture (profiles/r01c_sweep_ncu.txt) still had 80 % shared-memory wavefronts: a random
 // LDS.128 is served quarter-warp by quarter-warp, and two of eight lanes hitting the same 16-byte
 // slot of a bank row with different records serialise.  The coefficient planes are therefore
