@@ -731,7 +731,7 @@ int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed,
     // Walkers (warps) per block: as many as fit, but a multiple of 4 per SM -- the four SM sub-partitions
     // each run resident/4 warps and the slowest one sets the pace (measured: 20 walkers/SM beat 21 by 13 %).
     int best_wpb = 1, best_res = 0, best_score = -1;
-    for (int wpb = 1; wpb <= kSweepMaxThreads / 32; wpb++)
+    for (int wpb = 1; wpb <= sweep_max_threads(s) / 32; wpb++)
     {
         const int res = sweep_blocks_per_sm(s, wpb, h->npp) * wpb; // warps resident per SM
         const int score = res >= 4 ? (res / 4) * 4 * 2 + (res % 4 == 0 ? 1 : 0) : res;
@@ -745,7 +745,7 @@ int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed,
     if (const char* e = getenv("TDVMC_SWEEP_WPB")) // tuning knob
     {
         const int wpb = atoi(e);
-        if (wpb >= 1 && wpb <= kSweepMaxThreads / 32 && sweep_blocks_per_sm(s, wpb, h->npp) > 0)
+        if (wpb >= 1 && wpb <= sweep_max_threads(s) / 32 && sweep_blocks_per_sm(s, wpb, h->npp) > 0)
         {
             best_wpb = wpb;
             best_res = sweep_blocks_per_sm(s, wpb, h->npp) * wpb;

@@ -6,7 +6,8 @@
 namespace tdvmc
 {
 
-constexpr int kSweepMaxThreads = 704; // up to 22 walkers (warps) per block -> at most 93 registers per thread
+constexpr int kSweepMaxThreads = 704;      // packed small systems (8 / 16 lanes per walker): up to 22 warps, 93 registers
+constexpr int kSweepMaxThreadsWarp = 640;  // one warp per walker: up to 20 warps per block, which lets the kernel take 94 registers
 constexpr int kSweepMinBlocks = 1;
 
 // ---- K1: Metropolis sweep (sweep.cu) ----
@@ -28,6 +29,7 @@ struct SweepArgs
 cudaError_t launch_sweep(SweepArgs a, cudaStream_t st);
 int sweep_blocks_per_sm(const SysDev& s, int wpb, int npp);
 int sweep_walkers_per_warp(const SysDev& s);
+int sweep_max_threads(const SysDev& s);
 
 // ---- K2+K3+K4: fused evaluation of one configuration per block (evaluate.cu) ----
 struct EvalArgs

@@ -140,7 +140,7 @@ __device__ __forceinline__ double pair_u(const SysDev& s, const double2* __restr
 // GROUP = lanes per walker (32, or 16 / 8 for systems of at most 16 / 8 particles, where a whole warp per walker would
 // leave most lanes without a partner: HeDrop's six atoms run four walkers per warp).
 template <bool UNIFORM, bool REFLECT, int UNROLL, bool HE = false, bool OPEN = false, int GROUP = 32>
-__global__ void __launch_bounds__(kSweepMaxThreads, kSweepMinBlocks) sweep_kernel(SweepArgs a)
+__global__ void __launch_bounds__(GROUP == 32 ? kSweepMaxThreadsWarp : kSweepMaxThreads, kSweepMinBlocks) sweep_kernel(SweepArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SysDev& s = a.s;
@@ -386,6 +386,11 @@ cudaError_t launch_sweep(SweepArgs a, cudaStream_t st)
 int sweep_walkers_per_warp(const SysDev& s)
 {
     return 32 / sweep_group(s);
+}
+
+int sweep_max_threads(const SysDev& s)
+{
+    return sweep_group(s) == 32 ? kSweepMaxThreadsWarp : kSweepMaxThreads;
 }
 
 int sweep_blocks_per_sm(const SysDev& s, int wpb, int npp)
