@@ -40,7 +40,7 @@ FLOP_PER_EVALUATION = 5.0e6
 BYTES_PER_TABLE = 8 * 203 * N * 4 + 24 * N                  # 2 236 360 (K3 table kernel)
 METRIC = "walker-steps/s"
 # dram__bytes_read.sum + dram__bytes_write.sum of one sweep_kernel launch (2960 walkers) from the ncu --set full capture
-# profiles/r01e_sweep_ncu.txt (24.50 MB read, 0 written); algorithmic traffic is 2 x 8.2 KB per walker per launch = 48.7 MB (the write-back stays in L2)
+# profiles/r01f_sweep_ncu.txt (24.50 MB read, 0 written); algorithmic traffic is 2 x 8.2 KB per walker per launch = 48.7 MB (the write-back stays in L2)
 SWEEP_DRAM_BYTES_PER_LAUNCH_NCU = 24.5e6
 
 
