@@ -391,42 +391,48 @@ def gen_mixture_observables():
 
 
 def gen_evolution():
-    """Imaginary-time evolution by the reference's own time-step functions (ref_harness evolve): BosonsBulk N = 64,
-    Euler steps with the Cholesky solve, several RNG seeds -> mean and spread of the parameter trajectories and of
-    the energies (north_star level 2: time-evolved parameters agree statistically), plus the first step's
-    estimators and derivatives of one seed to pin the host-side restatement of SolveForParametersDot."""
+    """Time evolution by the reference's own time-step functions (ref_harness evolve): BosonsBulk N = 64, Euler steps
+    with the Cholesky solve, 24 RNG seeds -> mean and spread of the parameter trajectories and of the energies
+    (north_star level 2: time-evolved parameters agree statistically), plus the first step's estimators and
+    derivatives of one seed to pin the host-side restatement of SolveForParametersDot.  Two runs: imaginary time
+    (30 steps of 2e-4: the real parts relax) and real time (12 steps of 1e-4 - explicit Euler is only stable for a
+    short stretch in real time - in which the imaginary parts grow out of zero)."""
     g = np.load(os.path.join(GOLDEN, "bosonsbulk_n64_equil.npz"))
     P = int(g["N_PARAM"])
     seeds = list(range(1, 25))
-    base = dict(N=64, LBOX=4.0, N_PARAM=P, time=0.0, phiR=0.0, phiI=0.0, MC_STEP=0.4, MC_NSTEPS=1024, MC_NTHERMSTEPS=32,
-                MC_NINITIALIZATIONSTEPS=64, IMAGINARY_TIME=1, TIMESTEP=2e-4, time_steps=30, equilibration_steps=6400)
-    arr = dict(R=g["R"], uR=g["uR"], uI=np.zeros(P), SYSTEM_PARAMS=[1.0, 1.0])
-    def one(sd):
-        with tempfile.TemporaryDirectory() as td:
-            cp, op = os.path.join(td, "case.txt"), os.path.join(td, "out.txt")
-            write_case(cp, "BosonsBulk", dict(base, seed=sd), arr)
-            run("evolve", cp, op)
-            return parse_dump(op)
+    for name, imag, dt, nsteps in (("bosonsbulk_n64_evolution", 1, 2e-4, 30), ("bosonsbulk_n64_evolution_realtime", 0, 1e-4, 12)):
+        base = dict(N=64, LBOX=4.0, N_PARAM=P, time=0.0, phiR=0.0, phiI=0.0, MC_STEP=0.4, MC_NSTEPS=1024, MC_NTHERMSTEPS=32,
+                    MC_NINITIALIZATIONSTEPS=64, IMAGINARY_TIME=imag, TIMESTEP=dt, time_steps=nsteps, equilibration_steps=6400)
+        arr = dict(R=g["R"], uR=g["uR"], uI=np.zeros(P), SYSTEM_PARAMS=[1.0, 1.0])
 
-    from concurrent.futures import ThreadPoolExecutor
-    with ThreadPoolExecutor(max_workers=max(1, (os.cpu_count() or 2) - 1)) as ex:   # each run is its own process
-        runs = list(ex.map(one, seeds))
-    for sd, r in zip(seeds, runs):
-        assert float(r["cholesky_failed"]) == 0.0
-        print(f"evolve seed {sd}: E {r['energy_r_t'][0]:.3f} -> {r['energy_r_t'][-1]:.3f}")
-    uR_t = np.stack([r["uR_t"] for r in runs])            # [seed][step][P]
-    e_t = np.stack([r["energy_r_t"] for r in runs])
-    first = runs[0]
-    out = {k: np.array(v) for k, v in base.items()}
-    out.update(system=np.array("BosonsBulk"), source=np.array("bosonsbulk_n64_equil"), seeds=np.array(seeds),
-               SYSTEM_PARAMS=np.array([1.0, 1.0]), uR0=g["uR"], uR_t_mean=uR_t.mean(axis=0), uR_t_std=uR_t.std(axis=0, ddof=1),
-               energy_r_t_mean=e_t.mean(axis=0), energy_r_t_std=e_t.std(axis=0, ddof=1),
-               phiR_t_mean=np.stack([r["phiR_t"] for r in runs]).mean(axis=0),
-               acceptance=np.mean([float(r["acceptance"]) for r in runs]))
-    for k in ("first_O", "first_S", "first_OER", "first_OEI", "first_ER", "first_EI", "first_uDotR", "first_uDotI",
-              "first_phiDotR", "first_phiDotI"):
-        out[k] = first[k]
-    np.savez_compressed(os.path.join(GOLDEN, "bosonsbulk_n64_evolution.npz"), **out)
+        def one(sd):
+            with tempfile.TemporaryDirectory() as td:
+                cp, op = os.path.join(td, "case.txt"), os.path.join(td, "out.txt")
+                write_case(cp, "BosonsBulk", dict(base, seed=sd), arr)
+                run("evolve", cp, op)
+                return parse_dump(op)
+
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=max(1, (os.cpu_count() or 2) - 1)) as ex:   # each run is its own process
+            runs = list(ex.map(one, seeds))
+        for sd, r in zip(seeds, runs):
+            assert float(r["cholesky_failed"]) == 0.0
+        print(f"{name}: E {np.mean([r['energy_r_t'][0] for r in runs]):.3f} -> {np.mean([r['energy_r_t'][-1] for r in runs]):.3f}")
+        uR_t = np.stack([r["uR_t"] for r in runs])            # [seed][step][P]
+        uI_t = np.stack([r["uI_t"] for r in runs])
+        e_t = np.stack([r["energy_r_t"] for r in runs])
+        first = runs[0]
+        out = {k: np.array(v) for k, v in base.items()}
+        out.update(system=np.array("BosonsBulk"), source=np.array("bosonsbulk_n64_equil"), seeds=np.array(seeds),
+                   SYSTEM_PARAMS=np.array([1.0, 1.0]), uR0=g["uR"], uR_t_mean=uR_t.mean(axis=0), uR_t_std=uR_t.std(axis=0, ddof=1),
+                   uI_t_mean=uI_t.mean(axis=0), uI_t_std=uI_t.std(axis=0, ddof=1),
+                   energy_r_t_mean=e_t.mean(axis=0), energy_r_t_std=e_t.std(axis=0, ddof=1),
+                   phiR_t_mean=np.stack([r["phiR_t"] for r in runs]).mean(axis=0),
+                   acceptance=np.mean([float(r["acceptance"]) for r in runs]))
+        for k in ("first_O", "first_S", "first_OER", "first_OEI", "first_ER", "first_EI", "first_uDotR", "first_uDotI",
+                  "first_phiDotR", "first_phiDotI"):
+            out[k] = first[k]
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
 
 
 def hebulk_drift(d, uR, uI):

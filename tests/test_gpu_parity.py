@@ -889,23 +889,26 @@ def test_sample_observables_statistics_match_reference(capi, golden, name):
 # ---------------------------------------------------------------------------------------------------
 # north_star level 2: time-evolved variational parameters agree statistically with the reference
 # ---------------------------------------------------------------------------------------------------
-def test_time_evolution_matches_reference_statistically(capi, golden):
-    """30 imaginary-time Euler steps (the reference's ParallelUpdateExpectationValues -> SolveForParametersDot ->
-    CalculateNextParametersEuler loop) with the estimators coming from the GPU ensemble; the reference ran the same
-    loop with its own sampler for 24 seeds.  With the same number of samples per step a device run is one more draw
+@pytest.mark.parametrize("name", ["bosonsbulk_n64_evolution", "bosonsbulk_n64_evolution_realtime"])
+def test_time_evolution_matches_reference_statistically(capi, golden, name):
+    """Euler time steps (the reference's ParallelUpdateExpectationValues -> SolveForParametersDot ->
+    CalculateNextParametersEuler loop) with the estimators coming from the GPU ensemble, in imaginary time (30 steps, the
+    real parts relax) and in real time (12 steps, the imaginary parts grow out of zero); the reference ran the same
+    loops with its own sampler for 24 seeds.  With the same number of samples per step a device run is one more draw
     from the same distribution of trajectories.  Stated error bars: sigma = the reference's seed-to-seed spread per
-    parameter, widened for the uncertainty of its mean.  (a) every parameter of every device run within 6 sigma
-    (Student t, 23 degrees of freedom: p ~ 4e-6 per comparison); (b) over five device seeds the normalised deviations
-    have unit spread (rms within [0.7, 1.4]) - the device trajectories scatter like the reference's, no more, no less;
-    (c) the energy of the last ten steps agrees within its error bar."""
+    parameter, widened for the uncertainty of its mean.  (a) every parameter (real and imaginary part) of every device
+    run within 6 sigma (Student t, 23 degrees of freedom: p ~ 4e-6 per comparison); (b) over five device seeds the
+    normalised deviations have unit spread (rms within [0.7, 1.4]) - the device trajectories scatter like the
+    reference's, no more, no less; (c) the energy of the last steps agrees within its error bar; (d) the parameters
+    moved by > 20 sigma, so this is not noise compared with noise."""
     from tdvmc_b200 import timestep
     from tdvmc_b200.ensemble import GpuEnsembleSystem
-    g = golden("bosonsbulk_n64_evolution")
+    g = golden(name)
     src = golden(str(g["source"]))
     spec = systems.bosons_bulk(int(g["N"]), float(g["LBOX"]), int(g["N_PARAM"]), g["SYSTEM_PARAMS"], weights=src["spline_weights"])
     W = 64
     n_samples = int(g["MC_NSTEPS"]) // W                            # same samples per time step as the reference
-    dt, steps = float(g["TIMESTEP"]), int(g["time_steps"])
+    dt, steps, imag = float(g["TIMESTEP"]), int(g["time_steps"]), int(g["IMAGINARY_TIME"])
 
     def evolve(seed):
         ens = GpuEnsembleSystem(spec, W, mc_step=float(g["MC_STEP"]), mc_nsteps=n_samples, seed=seed)
@@ -913,33 +916,39 @@ def test_time_evolution_matches_reference_statistically(capi, golden):
         uR, uI, phiR, phiI = g["uR0"].copy(), np.zeros(spec.n_params), 0.0, 0.0
         ens.BroadcastNewParameters(uR, uI, phiR, phiI)
         ens.DoMetropolisSteps(int(g["equilibration_steps"]))
-        traj, energies = [], []
+        tr, ti, energies = [], [], []
         for _ in range(steps):
             est = ens.ParallelUpdateExpectationValues(uR, uI, phiR, phiI, n_samples, int(g["MC_NTHERMSTEPS"]),
                                                       int(g["MC_NINITIALIZATIONSTEPS"]))
             energies.append(est["localEnergyR"])
-            uR, uI, phiR, phiI = timestep.euler_step(dt, uR, uI, phiR, phiI, est, imaginary_time=int(g["IMAGINARY_TIME"]))
-            traj.append(uR.copy())
+            uR, uI, phiR, phiI = timestep.euler_step(dt, uR, uI, phiR, phiI, est, imaginary_time=imag)
+            tr.append(uR.copy())
+            ti.append(uI.copy())
         ens.handle.close()
-        return np.array(traj), np.array(energies)
+        return np.array(tr), np.array(ti), np.array(energies)
 
     runs = [evolve(seed) for seed in (4242, 100, 101, 102, 103)]
     K = len(g["seeds"])
     widen = np.sqrt(1.0 + 1.0 / K)
     checked = (steps // 3, 2 * steps // 3, steps - 1)
-    for t in checked:
-        sig = np.maximum(g["uR_t_std"][t], 1e-6) * widen
-        z = np.stack([(traj[t] - g["uR_t_mean"][t]) / sig for traj, _ in runs])          # [seed][param]
-        assert np.abs(z).max() < 6.0, (t, float(np.abs(z).max()))
-        rms = float(np.sqrt(np.mean(z ** 2)))
-        assert 0.7 < rms < 1.4, (t, rms)
-    # the trajectory is not noise: the parameters moved by many sigma from where they started
-    moved = np.abs(g["uR_t_mean"][-1] - g["uR0"]) / np.maximum(g["uR_t_std"][-1], 1e-6)
+    parts = [("uR", 0)] + ([("uI", 1)] if imag == 0 else [])
+    for key, idx in parts:
+        for t in checked:
+            sig = np.maximum(g[key + "_t_std"][t], 1e-7) * widen
+            z = np.stack([(run[idx][t] - g[key + "_t_mean"][t]) / sig for run in runs])          # [seed][param]
+            assert np.abs(z).max() < 6.0, (key, t, float(np.abs(z).max()))
+            rms = float(np.sqrt(np.mean(z ** 2)))
+            assert 0.7 < rms < 1.4, (key, t, rms)
+    moving = "uI" if imag == 0 else "uR"
+    start = np.zeros(spec.n_params) if imag == 0 else g["uR0"]
+    moved = np.abs(g[moving + "_t_mean"][-1] - start) / np.maximum(g[moving + "_t_std"][-1], 1e-7)
     assert moved.max() > 20.0
-    tail = slice(steps - 10, steps)
-    e_sig = np.sqrt(np.mean(g["energy_r_t_std"][tail] ** 2) / 10.0) * widen
-    e_gpu = np.mean([e[tail].mean() for _, e in runs])
+    n_tail = min(10, steps // 2)
+    tail = slice(steps - n_tail, steps)
+    e_sig = np.sqrt(np.mean(g["energy_r_t_std"][tail] ** 2) / n_tail) * widen
+    e_gpu = np.mean([run[2][tail].mean() for run in runs])
     assert abs(e_gpu - g["energy_r_t_mean"][tail].mean()) < 6.0 * e_sig * np.sqrt(1.0 / len(runs) + 1.0 / K)
+
 
 
 # ---------------------------------------------------------------------------------------------------
