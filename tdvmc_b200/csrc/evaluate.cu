@@ -174,16 +174,20 @@ __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kerne
     const bool nt_even = (NT & 1) == 0;
     for (int sft = 0; sft <= half; sft++)
     {
-        // diagonal tiles: rotations 1..16 (16 by the lower half only) cover each pair of the tile once
-        const int kfirst = sft == 0 ? 1 : 0;
-        const int klast = sft == 0 ? 16 : 31;
+        // NT even: the shift NT/2 pairs block I with I+NT/2 from both sides; warps I and I+NT/2 share that tile
+        // (rotations 0..15 and 16..31) instead of one of them idling
+        const bool shared_shift = nt_even && sft == half && sft != 0;
         for (int base = 0; base < NT; base += nwarps)
         {
-            const int I = base + warp;
-            // NT even: the shift NT/2 pairs block I with I+NT/2 from both sides - the lower half takes it
-            const bool tile = (I < NT) && !(nt_even && sft == half && sft != 0 && I >= half);
+            const int Iw = base + warp;
+            const bool tile = Iw < NT;
+            const bool second = shared_shift && Iw >= half;
+            const int I = second ? Iw - half : Iw;
             int J = I + sft;
             if (J >= NT) J -= NT;
+            // diagonal tiles: rotations 1..16 (16 by the lower half only) cover each pair of the tile once
+            const int kfirst = sft == 0 ? 1 : (second ? 16 : 0);
+            const int klast = sft == 0 ? 16 : (shared_shift && !second ? 15 : 31);
             const int n = 32 * I + lane;
             double rRx = 0.0, rRy = 0.0, rRz = 0.0, rIx = 0.0, rIy = 0.0, rIz = 0.0; // force on the row particle
             double cRx = 0.0, cRy = 0.0, cRz = 0.0, cIx = 0.0, cIy = 0.0, cIz = 0.0; // rotating column accumulators
@@ -262,25 +266,35 @@ __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kerne
                     }
                     warp_hist_add4(hist, bin, act, val, lane);
                 }
-                const int ic = 32 * J + ((lane + klast) & 31); // the column whose accumulator ended up in this lane
-                fRx[ic] += cRx;
-                fRy[ic] += cRy;
-                fRz[ic] += cRz;
-                fIx[ic] += cIx;
-                fIy[ic] += cIy;
-                fIz[ic] += cIz;
             }
-            __syncthreads();
-            if (tile)
+            // flush: columns first, rows second; in the shared shift the two warps of a tile take turns
+            const int ic = 32 * J + ((lane + klast) & 31); // the column whose accumulator ended up in this lane
+            for (int role = 0; role < (shared_shift ? 2 : 1); role++)
             {
-                fRx[n] += rRx;
-                fRy[n] += rRy;
-                fRz[n] += rRz;
-                fIx[n] += rIx;
-                fIy[n] += rIy;
-                fIz[n] += rIz;
+                if (tile && (int)second == role)
+                {
+                    fRx[ic] += cRx;
+                    fRy[ic] += cRy;
+                    fRz[ic] += cRz;
+                    fIx[ic] += cIx;
+                    fIy[ic] += cIy;
+                    fIz[ic] += cIz;
+                }
+                __syncthreads();
             }
-            __syncthreads();
+            for (int role = 0; role < (shared_shift ? 2 : 1); role++)
+            {
+                if (tile && (int)second == role)
+                {
+                    fRx[n] += rRx;
+                    fRy[n] += rRy;
+                    fRz[n] += rRz;
+                    fIx[n] += rIx;
+                    fIy[n] += rIy;
+                    fIz[n] += rIz;
+                }
+                __syncthreads();
+            }
         }
     }
     lapR *= 2.0; // each pair enters the Laplacian of both partners with the same value
