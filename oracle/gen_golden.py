@@ -266,6 +266,28 @@ def gen_bosonsbulk_mc():
     print(f"bosonsbulk_n64_mc: <E_R>={float(d['local_energy_r']):.8g} acc={out['acceptance']:.4f}")
 
 
+def gen_bosonsbulk_mc_headline():
+    """The same at the headline size: N = 343, L = 7, N_PARAM = 201, the parameters bench.py uses, MC_STEP = 0.5; the
+    reference's single chain, 1500 samples a sweep apart.  (O_k, S, F are left out: 40 401 numbers that the N = 64
+    fixture already pins; the energies, the acceptance and a few operators are what a sampler can get wrong.)"""
+    g = np.load(os.path.join(GOLDEN, "bosonsbulk_n343_equil.npz"))
+    N, L, P = 343, 7.0, 201
+    uR, uI = tsys.smooth_params(P, L / 2)
+    scal = dict(N=N, LBOX=L, N_PARAM=P, time=0.0, phiR=0.0, phiI=0.0, MC_STEP=0.5,
+                MC_NINITIALIZATIONSTEPS=343 * 60, MC_NSTEPS=1500, MC_NTHERMSTEPS=343, seed=12)
+    arr = dict(R=g["R"], uR=uR, uI=uI, SYSTEM_PARAMS=[1.0, 1.0])
+    d = run_mc("BosonsBulk", scal, arr)
+    er = d["energy_r_series"]
+    out = dict(N=np.array(N), LBOX=np.array(L), N_PARAM=np.array(P), MC_STEP=np.array(0.5), SYSTEM_PARAMS=np.array([1.0, 1.0]),
+               uR=uR, uI=uI, n_samples=np.array(len(er)), n_therm=np.array(343), n_init=np.array(343 * 60),
+               energy_r_series=er, energy_i_series=d["energy_i_series"], local_energy_r=d["local_energy_r"],
+               local_energy_i=d["local_energy_i"], local_operators=d["local_operators"],
+               other_expectation_values=d["other_expectation_values"],
+               acceptance=np.array(float(d["n_acceptances"]) / float(d["n_trials"])))
+    np.savez_compressed(os.path.join(GOLDEN, "bosonsbulk_n343_mc.npz"), **out)
+    print(f"bosonsbulk_n343_mc: <E_R>={float(d['local_energy_r']):.8g} <E_I>={float(d['local_energy_i']):.8g} acc={out['acceptance']:.4f}")
+
+
 def gen_nubosonsbulkpb():
     rng = np.random.default_rng(4)
     # reduced copy of config/NUBosonsBulkPB3D.config: rho=1, L=6, non-uniform knot grid on [0, 3]
@@ -662,7 +684,7 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     if not os.path.exists(HARNESS):
         sys.exit("build the oracle first: make -C oracle/ref_build")
-    which = sys.argv[1:] or ["min_image", "bosonsbulk", "bosonsbulk_mc", "nubosonsbulkpb", "nubosonsbulkpb_full", "hebulk", "hedrop",
+    which = sys.argv[1:] or ["min_image", "bosonsbulk", "bosonsbulk_mc", "bosonsbulk_mc_headline", "nubosonsbulkpb", "nubosonsbulkpb_full", "hebulk", "hedrop",
                              "mixture", "observables", "he_observables", "mixture_observables", "evolution"]
     for w in which:
         globals()["gen_" + w]()

@@ -268,6 +268,34 @@ def test_ensemble_statistics_match_reference_sampler(capi, golden):
     h.close()
 
 
+def test_headline_size_statistics_match_reference_sampler(capi, golden):
+    """The headline workload's size and parameters (N = 343, L = 7, N_PARAM = 201, MC_STEP = 0.5): ensemble means of
+    E^R, E^I, the acceptance rate and the operators O_k against the reference's own single-chain sampler, within stated
+    error bars (blocking of the reference series into 15 blocks; the device ensemble has 4096 samples from 1024
+    independent walkers, its error is taken from the reference's per-sample variance, x2 for correlation)."""
+    g = golden("bosonsbulk_n343_mc")
+    src = golden("bosonsbulk_n343_equil")
+    spec = systems.bosons_bulk(343, 7.0, 201, g["SYSTEM_PARAMS"], weights=src["spline_weights"])
+    W, n_samples = 1024, 4
+    h = capi.Handle(spec, W, seed=31337, mc_step=float(g["MC_STEP"]), max_samples=n_samples)
+    h.set_params(g["uR"], g["uI"], 0.0, 0.0, 0.0)
+    h.set_positions(np.broadcast_to(src["R"], (W, 343, 3)).copy())
+    h.sample_and_accumulate(n_samples, int(g["n_therm"]), int(g["n_init"]))
+    got = h.allreduce_and_fetch()
+    h.close()
+    nb = 15
+    for key, series in (("e_r", g["energy_r_series"]), ("e_i", g["energy_i_series"])):
+        b = series[:len(series) // nb * nb].reshape(nb, -1).mean(axis=1)
+        m_ref, s_ref = b.mean(), b.std(ddof=1) / np.sqrt(nb)
+        s_gpu = np.sqrt(np.var(series) / (W * n_samples)) * 2.0
+        assert abs(got[key][0] - m_ref) < 4.5 * np.hypot(s_ref, s_gpu), (key, got[key][0], m_ref, s_ref, s_gpu)
+    assert abs(got["n_acceptances"] / got["n_trials"] - float(g["acceptance"])) < 0.005
+    # operators: relative agreement where the reference's mean is well away from zero (pair counts per interval)
+    ref_o = g["local_operators"]
+    big = np.abs(ref_o) > 0.05 * np.max(np.abs(ref_o))
+    assert np.max(np.abs(got["O"][big] - ref_o[big]) / np.abs(ref_o[big])) < 0.03
+
+
 def test_full_size_properties(capi, golden):
     """BASELINE size (N=343, P=201): size-independent properties of the resident path."""
     g = golden("bosonsbulk_n343_equil")
