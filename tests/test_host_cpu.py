@@ -243,3 +243,33 @@ def test_timestep_solver_matches_reference(golden, name):
     s = np.sqrt(np.diag(A))
     x = np.linalg.solve(A / np.outer(s, s) + 0.001 * np.eye(len(s)), b_r / s) / s
     assert np.max(np.abs(x - u_r)) <= 1e-8 * scale
+
+
+def test_recorded_bench_line_has_the_contract_keys():
+    """The last committed bench line (profiles/) carries every key the measurement contract asks for, with consistent
+    values: guards the format bench.py prints (it cannot run without a GPU)."""
+    import glob
+    import json
+    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_bench.json")))
+    assert paths, "no committed bench line under profiles/"
+    d = json.loads(open(paths[-1]).read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["metric"] == "walker-steps/s" and d["unit"] == "walker-steps/s" and d["dtype"] == "f64" and d["vs_baseline"] is None
+    assert d["warmup"] >= 3 and d["higher_is_better"] is True and d["scaling"] in ("weak", "strong")
+    assert "workload" in d["config"] and "model" not in d["config"]
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in d["e2e"], k
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] <= d["value"] * 1.02
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in d["roofline"], k
+    assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
+    for k in ("value", "unit", "cores", "kind", "sample"):
+        assert k in d["cpu_baseline"], k
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["gpu_launches"] > 0
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    # value = proposals of all walkers / time
+    steps = d["config"]["proposals_per_walker_per_step"] * d["config"]["walkers"] * d["steps"]
+    assert abs(steps / (d["ms_per_step"] * d["steps"] * 1e-3) - d["value"]) < 1e-6 * d["value"]
