@@ -5,9 +5,12 @@ spline table, boundary-condition map, cut-off rule, pair potential -- as plain d
 handed to the CUDA library through ``tdvmc_system_desc`` (include/tdvmc_gpu.h).  Systems are data,
 not kernels: the device code is driven by the flags in this description.
 
-Covered so far:
-  * ``BosonsBulk``      src/PhysicalSystems/BosonsBulk.cpp:49-156   (config 3, headline)
-  * ``NUBosonsBulkPB``  src/PhysicalSystems/NUBosonsBulkPB.cpp:53-216 (config 4)
+The five systems of the BASELINE configs:
+  * ``BosonsBulk``           src/PhysicalSystems/BosonsBulk.cpp:49-156          (config 3, headline)
+  * ``NUBosonsBulkPB``       src/PhysicalSystems/NUBosonsBulkPB.cpp:53-216      (config 4)
+  * ``HeBulk``               src/PhysicalSystems/HeBulk.cpp:40-70, 376-383      (config 2)
+  * ``HeDrop``               src/PhysicalSystems/HeDrop.cpp:71-135, 609-626     (config 1)
+  * ``BosonMixtureCluster``  src/PhysicalSystems/BosonMixtureCluster.cpp:58-346 (config 5)
 """
 from dataclasses import dataclass, field
 
