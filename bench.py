@@ -350,13 +350,22 @@ def main():
     ms_e2e = timed(args.steps, True)
 
     # BASELINE's second metric, TDVMC time-steps/s: a whole time step of the outer loop (src/TDVMC.cpp:3419-3923) as the
-    # driver would run it against this library - parameters in, estimator pass, packed all-reduce, fetch, the small
-    # parameter solve on the host with LAPACK (numpy.linalg: BuildSystemOfEquations + scaling preconditioner + Cholesky,
-    # tdvmc_b200/timestep.py) and the Euler update fed back into the next step.  Every rank solves redundantly.
+    # driver would run it against this library - parameters in, estimator pass, packed all-reduce, the parameter solve
+    # (BuildSystemOfEquations + scaling preconditioner + Cholesky) and the Euler update fed back into the next step.
+    # (a) solve on the device (tdvmc_gpu_euler_step, solve.cu): 2P + 5 doubles leave the GPU per step;
+    # (b) estimators fetched (328 KB) and solved on the host with LAPACK (numpy.linalg, tdvmc_b200/timestep.py).
+    # Every rank solves redundantly in both.
     from tdvmc_b200 import timestep
     cur = {"uR": uR.copy(), "uI": uI.copy(), "phiR": 0.0, "phiI": 0.0}
 
-    def time_step():
+    def time_step_device():
+        h.set_params(cur["uR"], cur["uI"], cur["phiR"], cur["phiI"], 0.0)
+        h.sample_and_accumulate(MC_NSTEPS, MC_NTHERMSTEPS, MC_NINIT)
+        cur["uR"], cur["uI"], cur["phiR"], cur["phiI"], _ = h.euler_step(1e-7, cur["uR"], cur["uI"], cur["phiR"], cur["phiI"],
+                                                                         imaginary_time=0, min_scaling=1e-12)
+        h.flush_l2()
+
+    def time_step_host():
         nonlocal out
         h.set_params(cur["uR"], cur["uI"], cur["phiR"], cur["phiI"], 0.0)
         h.sample_and_accumulate(MC_NSTEPS, MC_NTHERMSTEPS, MC_NINIT)
@@ -367,13 +376,21 @@ def main():
                                                                              est, imaginary_time=0, lapack=True, min_scaling=1e-12)
         h.flush_l2()
 
-    time_step()
-    barrier()
-    h.timer_start()
-    for _ in range(args.steps):
-        time_step()
-    ms_ts = max_over_ranks(h.timer_stop())
-    barrier()
+    def timed_time_steps(fn):
+        fn()
+        barrier()
+        h.timer_start()
+        for _ in range(args.steps):
+            fn()
+        ms = max_over_ranks(h.timer_stop())
+        barrier()
+        return ms
+
+    ms_ts_host = timed_time_steps(time_step_host)
+    h.profile(True, True)
+    ms_ts = timed_time_steps(time_step_device)
+    n_solve, ms_solve = h.kernel_stats()["solve"]
+    h.profile(False, False)
 
     proposals = float(W) * world * STEPS_PER_WALKER * args.steps
     value = proposals / (ms_total * 1e-3)
@@ -497,8 +514,11 @@ def main():
                                            "l2": "flushed between steps (256 MiB memset); walker state is 29 MB per GPU"}),
                 "time_steps_per_s": args.steps / (ms_ts * 1e-3),
                 "time_step": {"ms": ms_ts / args.steps, "samples_per_time_step": W * world * MC_NSTEPS,
-                              "includes": "set_params, estimator pass, all-reduce, fetch, host LAPACK solve of S u' = F "
-                                          "(P = 201, numpy.linalg), Euler update; every rank solves redundantly"},
+                              "includes": "set_params, estimator pass, all-reduce, Cholesky solve of S u' = F on the device "
+                                          "(P = 201, solve_kernel), Euler update, parameter feedback; every rank solves redundantly",
+                              "solve_kernel_ms": ms_solve / max(n_solve, 1),
+                              "with_host_lapack_solve": {"ms": ms_ts_host / args.steps,
+                                                         "time_steps_per_s": args.steps / (ms_ts_host * 1e-3)}},
                 "e2e": {"value": e2e_value, "unit": "walker-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,

@@ -168,6 +168,45 @@ int tdvmc_gpu_allreduce_and_fetch(tdvmc_gpu_handle* h, tdvmc_estimators* out);
 /* sys->GetExponent() of the first local walker's last sample, for NormalizeWavefunction (src/TDVMC.cpp:3763). */
 int tdvmc_gpu_last_exponent(tdvmc_gpu_handle* h, double* exponent);
 
+/* ---- parameter derivatives and the Euler step on the device ---- */
+/* Options of SolveForParametersDot with LINEAR_EQUATION_SOLVER_TYPE = 0 (src/TDVMC.cpp:1713-1763). */
+typedef struct tdvmc_solver_desc
+{
+    uint32_t struct_size;
+    int32_t imaginary_time;      /* IMAGINARY_TIME: 0 real time, 1 imaginary time (the -1 rotation is not offered) */
+    int32_t use_preconditioning; /* USE_PRECONDITIONING: scale by sqrt(diag), src/TDVMC.cpp:1684-1701 */
+    int32_t force_global_scratch;/* tests: factorise in global memory even when P fits shared memory */
+    double regularization;       /* RegularizeEquationSystem; the reference hard-codes 0.001 (src/TDVMC.cpp:1737) */
+    double min_scaling;          /* 0 = reference behaviour; > 0 floors the scalings (a parameter whose operator never varied) */
+} tdvmc_solver_desc;
+/* What the root rank of the reference holds after SolveForParametersDot (+ the energies the driver logs each step). */
+typedef struct tdvmc_parameters_dot
+{
+    double* u_dot_r;             /* [P] */
+    double* u_dot_i;             /* [P] */
+    double phi_dot_r, phi_dot_i;
+    double local_energy_r, local_energy_i; /* <E^R>, <E^I> of the estimators the system was built from */
+    int32_t not_positive_definite; /* the reference logs "NOT POSITIVE SEMI DEFINITE" and sets doNotAcceptStep (:1577-1589) */
+} tdvmc_parameters_dot;
+/* SolveForParametersDot (Cholesky branch: BuildSystemOfEquationsForParametersIncludePhi src/TDVMC.cpp:1506-1537,
+ * PreconditionEquationSystemByScaling :1684-1701, RegularizeEquationSystem :1703-1711, PerformCholeskyDecomposition
+ * :1560-1592, SolveCholeskyDecomposedEquationSystem :1594-1622, CalculatePhiDot :1658-1682) on the estimators of the
+ * last accumulation, all-reduced in place first if a communicator is bound; nothing but 2P + 5 doubles leaves the
+ * device.  Every rank solves redundantly and receives the same result (the reference solves on the root and
+ * broadcasts, :506-512). */
+int tdvmc_gpu_solve_parameters_dot(tdvmc_gpu_handle* h, const tdvmc_solver_desc* sd, tdvmc_parameters_dot* out);
+/* CalculateNextParametersEuler (src/TDVMC.cpp:1834-1853) + BroadcastNewParameters (:506-512): solve as above,
+ * uR += uDotR dt, uI += uDotI dt, phi += phiDot dt on the caller's arrays (in place), and make the new parameters
+ * current on the device as tdvmc_gpu_set_params(uR, uI, phiR, phiI, time) would.  If the matrix was not positive
+ * definite the parameters are still updated, as in the reference; the flag is in dot->not_positive_definite.
+ * dot may be NULL. */
+int tdvmc_gpu_euler_step(tdvmc_gpu_handle* h, const tdvmc_solver_desc* sd, double dt, double time, double* uR, double* uI,
+                         double* phiR, double* phiI, tdvmc_parameters_dot* dot);
+/* The same solve on estimators given by the caller (averages, as tdvmc_estimators holds them): parity entry point
+ * against the reference's own SolveForParametersDot. */
+int tdvmc_gpu_solve_fixed(tdvmc_gpu_handle* h, const tdvmc_solver_desc* sd, const tdvmc_estimators* est,
+                          tdvmc_parameters_dot* out);
+
 /* ---- communicator (replaces MPI_COMM_WORLD for the reduce; src/MPIMethods.h) ---- */
 #define TDVMC_GPU_UNIQUE_ID_BYTES 128
 int tdvmc_gpu_comm_unique_id(uint8_t id[TDVMC_GPU_UNIQUE_ID_BYTES]);          /* rank 0, then broadcast by the host */
@@ -257,7 +296,8 @@ enum tdvmc_kernel_id
     TDVMC_KERNEL_TABLES = 3,
     TDVMC_KERNEL_CONTRACT = 4,
     TDVMC_KERNEL_OTHER = 5,
-    TDVMC_KERNEL_COUNT = 6
+    TDVMC_KERNEL_SOLVE = 6,
+    TDVMC_KERNEL_COUNT = 7
 };
 /* Per-kernel CUDA-event timing on the library's stream. enable=1 starts, stats are cumulative since the last reset. */
 int tdvmc_gpu_profile(tdvmc_gpu_handle* h, int32_t enable, int32_t reset);

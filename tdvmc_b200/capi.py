@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtdvmc_b200.so")
 
 UNIQUE_ID_BYTES = 128
-KERNELS = {"sweep": 0, "evaluate": 1, "accumulate": 2, "tables": 3, "contract": 4, "other": 5}
+KERNELS = {"sweep": 0, "evaluate": 1, "accumulate": 2, "tables": 3, "contract": 4, "other": 5, "solve": 6}
 
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int32)
@@ -42,6 +42,18 @@ class Estimators(C.Structure):
     _fields_ = [("local_operators", dp), ("local_energy_r", dp), ("local_energy_i", dp), ("local_operators_matrix", dp),
                 ("local_operator_energy_r", dp), ("local_operator_energy_i", dp), ("other_expectation_values", dp),
                 ("n_acceptances", C.c_int64), ("n_trials", C.c_int64), ("n_samples", C.c_int64)]
+
+
+class SolverDesc(C.Structure):
+    """tdvmc_solver_desc"""
+    _fields_ = [("struct_size", C.c_uint32), ("imaginary_time", C.c_int32), ("use_preconditioning", C.c_int32),
+                ("force_global_scratch", C.c_int32), ("regularization", C.c_double), ("min_scaling", C.c_double)]
+
+
+class ParametersDot(C.Structure):
+    """tdvmc_parameters_dot"""
+    _fields_ = [("u_dot_r", dp), ("u_dot_i", dp), ("phi_dot_r", C.c_double), ("phi_dot_i", C.c_double),
+                ("local_energy_r", C.c_double), ("local_energy_i", C.c_double), ("not_positive_definite", C.c_int32)]
 
 
 class ObservableDesc(C.Structure):
@@ -74,6 +86,9 @@ SYMBOLS = [
     ("tdvmc_gpu_reevaluate_stored", C.c_int, [_VP]),
     ("tdvmc_gpu_update_stored", C.c_int, [_VP, C.c_int32, C.c_int32]),
     ("tdvmc_gpu_allreduce_and_fetch", C.c_int, [_VP, C.POINTER(Estimators)]),
+    ("tdvmc_gpu_solve_parameters_dot", C.c_int, [_VP, C.POINTER(SolverDesc), C.POINTER(ParametersDot)]),
+    ("tdvmc_gpu_euler_step", C.c_int, [_VP, C.POINTER(SolverDesc), C.c_double, C.c_double, dp, dp, dp, dp, C.POINTER(ParametersDot)]),
+    ("tdvmc_gpu_solve_fixed", C.c_int, [_VP, C.POINTER(SolverDesc), C.POINTER(Estimators), C.POINTER(ParametersDot)]),
     ("tdvmc_gpu_last_exponent", C.c_int, [_VP, dp]),
     ("tdvmc_gpu_comm_unique_id", C.c_int, [C.POINTER(C.c_uint8)]),
     ("tdvmc_gpu_comm_init", C.c_int, [_VP, C.POINTER(C.c_uint8), C.c_int32, C.c_int32]),
@@ -229,6 +244,49 @@ class Handle:
         self._ck(self.lib.tdvmc_gpu_allreduce_and_fetch(self.h, C.byref(est)), "allreduce_and_fetch")
         out["n_acceptances"], out["n_trials"], out["n_samples"] = est.n_acceptances, est.n_trials, est.n_samples
         return out
+
+    # ---- parameter derivatives / Euler step on the device ----
+    @staticmethod
+    def _solver_desc(imaginary_time=1, use_preconditioning=True, regularization=0.001, min_scaling=0.0, force_global=False):
+        return SolverDesc(C.sizeof(SolverDesc), int(imaginary_time), int(bool(use_preconditioning)), int(bool(force_global)),
+                          float(regularization), float(min_scaling))
+
+    def _dot_out(self):
+        o = dict(u_dot_r=np.empty(self.P), u_dot_i=np.empty(self.P))
+        return o, ParametersDot(_d(o["u_dot_r"]), _d(o["u_dot_i"]), 0.0, 0.0, 0.0, 0.0, 0)
+
+    @staticmethod
+    def _dot_fill(o, pd):
+        o.update(phi_dot_r=pd.phi_dot_r, phi_dot_i=pd.phi_dot_i, e_r=pd.local_energy_r, e_i=pd.local_energy_i,
+                 not_positive_definite=bool(pd.not_positive_definite))
+        return o
+
+    def solve_parameters_dot(self, **kw):
+        """SolveForParametersDot (Cholesky branch) on the device-resident estimators of the last accumulation."""
+        sd = self._solver_desc(**kw)
+        o, pd = self._dot_out()
+        self._ck(self.lib.tdvmc_gpu_solve_parameters_dot(self.h, C.byref(sd), C.byref(pd)), "solve_parameters_dot")
+        return self._dot_fill(o, pd)
+
+    def solve_fixed(self, est, **kw):
+        """The same solve on caller-given averages: est has O, S, OER, OEI, e_r, e_i (as allreduce_and_fetch returns)."""
+        sd = self._solver_desc(**kw)
+        o, pd = self._dot_out()
+        k = {n: np.ascontiguousarray(np.atleast_1d(est[n]), np.float64) for n in ("O", "S", "OER", "OEI", "e_r", "e_i")}
+        e = Estimators(_d(k["O"]), _d(k["e_r"]), _d(k["e_i"]), _d(k["S"]), _d(k["OER"]), _d(k["OEI"]), None, 0, 0, 0)
+        self._ck(self.lib.tdvmc_gpu_solve_fixed(self.h, C.byref(sd), C.byref(e), C.byref(pd)), "solve_fixed")
+        return self._dot_fill(o, pd)
+
+    def euler_step(self, dt, uR, uI, phiR, phiI, time=0.0, **kw):
+        """CalculateNextParametersEuler + parameter feedback; returns (uR, uI, phiR, phiI, dot)."""
+        sd = self._solver_desc(**kw)
+        o, pd = self._dot_out()
+        uR = np.array(uR, np.float64)
+        uI = np.array(uI, np.float64)
+        pr, pi = C.c_double(phiR), C.c_double(phiI)
+        self._ck(self.lib.tdvmc_gpu_euler_step(self.h, C.byref(sd), dt, time, _d(uR), _d(uI), C.byref(pr), C.byref(pi),
+                                               C.byref(pd)), "euler_step")
+        return uR, uI, pr.value, pi.value, self._dot_fill(o, pd)
 
     def last_exponent(self):
         x = C.c_double(0)

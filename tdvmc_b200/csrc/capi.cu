@@ -148,6 +148,10 @@ struct tdvmc_gpu_handle
     double* h_est = nullptr;   // pinned
     size_t est_len = 0;
     bool est_valid = false;
+    bool est_reduced = false;  // d_est already holds the sum over all ranks
+    DevBuf<double> d_sol, d_solve_L, d_est_fixed; // solve.cu: result, global factor scratch, caller-given estimators
+    double* h_sol = nullptr;   // pinned, 2P + 5
+    int smem_optin = 48 * 1024;
 
     // communicator
     void* comm = nullptr;
@@ -609,6 +613,7 @@ int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed,
         return bail(-2);
     }
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
+    if (cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device) != cudaSuccess) h->smem_optin = 48 * 1024;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
     {
         h->error = "cudaStreamCreate failed";
@@ -777,6 +782,7 @@ void tdvmc_gpu_destroy(tdvmc_gpu_handle* h)
     if (h->timer0) cudaEventDestroy(h->timer0);
     if (h->timer1) cudaEventDestroy(h->timer1);
     if (h->h_est) cudaFreeHost(h->h_est);
+    if (h->h_sol) cudaFreeHost(h->h_sol);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -913,6 +919,7 @@ static int do_accumulate(tdvmc_gpu_handle* h, const double* A, const double* oth
     }
     h->rows_used = M;
     h->est_valid = true;
+    h->est_reduced = false;
     return 0;
 }
 
@@ -969,19 +976,26 @@ int tdvmc_gpu_update_stored(tdvmc_gpu_handle* h, int32_t n_update, int32_t n_the
     return 0;
 }
 
+// One packed in-place all-reduce per accumulation (an in-place sum must not be applied twice): fetch and solve share it.
+static int ensure_reduced(tdvmc_gpu_handle* h)
+{
+    if (h->comm && !h->est_reduced)
+    {
+        int rc = g_nccl.AllReduce(h->d_est.p, h->d_est.p, h->est_len, kNcclDouble, kNcclSum, h->comm, h->stream);
+        if (rc != 0) return fail(h, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"), rc);
+    }
+    h->est_reduced = true;
+    return 0;
+}
+
 int tdvmc_gpu_allreduce_and_fetch(tdvmc_gpu_handle* h, tdvmc_estimators* out)
 {
     if (!h || !out) return h ? fail(h, "allreduce_and_fetch: null argument") : -1;
     if (!h->est_valid) return fail(h, "allreduce_and_fetch: nothing accumulated yet");
     CK(cudaSetDevice(h->device));
-    if (h->comm)
-    {
-        int rc = g_nccl.AllReduce(h->d_est.p, h->d_est.p, h->est_len, kNcclDouble, kNcclSum, h->comm, h->stream);
-        if (rc != 0) return fail(h, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"), rc);
-    }
+    if (int rc = ensure_reduced(h)) return rc;
     CK(cudaMemcpyAsync(h->h_est, h->d_est.p, h->est_len * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    h->est_valid = !h->comm; // an in-place all-reduce must not be applied twice
     const int P = h->P;
     const double* S = h->h_est;
     const double* FR = S + (size_t)P * P;
@@ -1009,6 +1023,104 @@ int tdvmc_gpu_allreduce_and_fetch(tdvmc_gpu_handle* h, tdvmc_estimators* out)
     out->n_trials = (int64_t)llround(cnt[1]);
     out->n_samples = (int64_t)llround(n);
     return 0;
+}
+
+// ---- parameter derivatives on the device (solve.cu) ----
+
+static int do_solve(tdvmc_gpu_handle* h, const tdvmc_solver_desc* sd, const double* d_est, tdvmc_parameters_dot* out)
+{
+    if (sd->struct_size != sizeof(tdvmc_solver_desc)) return fail(h, "solver desc: struct_size mismatch");
+    if (sd->imaginary_time != 0 && sd->imaginary_time != 1)
+        return fail(h, "solver: IMAGINARY_TIME must be 0 or 1 (the time rotation of src/TDVMC.cpp:1448-1504 is not offered)");
+    if (h->P > 1024) return fail(h, "solver: N_PARAM > 1024");
+    const int P = h->P;
+    CK(h->d_sol.ensure(2 * (size_t)P + 5));
+    CK(h->d_solve_L.ensure((size_t)P * (P + 1) / 2));
+    if (!h->h_sol) CK(cudaMallocHost((void**)&h->h_sol, (2 * (size_t)P + 5) * sizeof(double)));
+    SolveArgs a;
+    memset(&a, 0, sizeof(a));
+    a.est = d_est;
+    a.cnt_offset = (int)(h->est_len - 3);
+    a.P = P;
+    a.imaginary_time = sd->imaginary_time;
+    a.use_preconditioning = sd->use_preconditioning;
+    a.regularization = sd->regularization;
+    a.min_scaling = sd->min_scaling;
+    a.L_global = h->d_solve_L.p;
+    a.force_global = sd->force_global_scratch;
+    a.out = h->d_sol.p;
+    {
+        Timed t(h, TDVMC_KERNEL_SOLVE);
+        CK(launch_solve(a, h->smem_optin, h->stream));
+    }
+    CK(cudaMemcpyAsync(h->h_sol, h->d_sol.p, (2 * (size_t)P + 5) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (out)
+    {
+        if (out->u_dot_r) memcpy(out->u_dot_r, h->h_sol, P * sizeof(double));
+        if (out->u_dot_i) memcpy(out->u_dot_i, h->h_sol + P, P * sizeof(double));
+        const double* tail = h->h_sol + 2 * (size_t)P;
+        out->phi_dot_r = tail[0];
+        out->phi_dot_i = tail[1];
+        out->not_positive_definite = tail[2] != 0.0 ? 1 : 0;
+        out->local_energy_r = tail[3];
+        out->local_energy_i = tail[4];
+    }
+    return 0;
+}
+
+int tdvmc_gpu_solve_parameters_dot(tdvmc_gpu_handle* h, const tdvmc_solver_desc* sd, tdvmc_parameters_dot* out)
+{
+    if (!h || !sd || !out) return h ? fail(h, "solve_parameters_dot: null argument") : -1;
+    if (!h->est_valid) return fail(h, "solve_parameters_dot: nothing accumulated yet");
+    CK(cudaSetDevice(h->device));
+    if (int rc = ensure_reduced(h)) return rc;
+    return do_solve(h, sd, h->d_est.p, out);
+}
+
+int tdvmc_gpu_euler_step(tdvmc_gpu_handle* h, const tdvmc_solver_desc* sd, double dt, double time, double* uR, double* uI,
+                         double* phiR, double* phiI, tdvmc_parameters_dot* dot)
+{
+    if (!h || !sd || !uR || !uI || !phiR || !phiI) return h ? fail(h, "euler_step: null argument") : -1;
+    if (!h->est_valid) return fail(h, "euler_step: nothing accumulated yet");
+    CK(cudaSetDevice(h->device));
+    if (int rc = ensure_reduced(h)) return rc;
+    tdvmc_parameters_dot local;
+    memset(&local, 0, sizeof(local));
+    tdvmc_parameters_dot* d = dot ? dot : &local;
+    if (int rc = do_solve(h, sd, h->d_est.p, d)) return rc;
+    const double* x = h->h_sol;
+    for (int i = 0; i < h->P; i++) // uR = uR + uDotR * dt (src/TDVMC.cpp:1846-1847)
+    {
+        uR[i] = uR[i] + x[i] * dt;
+        uI[i] = uI[i] + x[h->P + i] * dt;
+    }
+    *phiR = *phiR + d->phi_dot_r * dt;
+    *phiI = *phiI + d->phi_dot_i * dt;
+    return tdvmc_gpu_set_params(h, uR, uI, *phiR, *phiI, time);
+}
+
+int tdvmc_gpu_solve_fixed(tdvmc_gpu_handle* h, const tdvmc_solver_desc* sd, const tdvmc_estimators* est, tdvmc_parameters_dot* out)
+{
+    if (!h || !sd || !est || !out) return h ? fail(h, "solve_fixed: null argument") : -1;
+    if (!est->local_operators || !est->local_operators_matrix || !est->local_operator_energy_r || !est->local_operator_energy_i ||
+        !est->local_energy_r || !est->local_energy_i)
+        return fail(h, "solve_fixed: estimators incomplete");
+    CK(cudaSetDevice(h->device));
+    const int P = h->P;
+    // the packed layout with a sample count of one: sums == averages, the kernel's division by n is exact
+    std::vector<double> e(h->est_len, 0.0);
+    memcpy(e.data(), est->local_operators_matrix, (size_t)P * P * sizeof(double));
+    double* p = e.data() + (size_t)P * P;
+    memcpy(p, est->local_operator_energy_r, P * sizeof(double));
+    memcpy(p + P, est->local_operator_energy_i, P * sizeof(double));
+    memcpy(p + 2 * P, est->local_operators, P * sizeof(double));
+    p[3 * P] = *est->local_energy_r;
+    p[3 * P + 1] = *est->local_energy_i;
+    e[h->est_len - 1] = 1.0;
+    CK(upload(h->d_est_fixed, e, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return do_solve(h, sd, h->d_est_fixed.p, out);
 }
 
 int tdvmc_gpu_last_exponent(tdvmc_gpu_handle* h, double* exponent)

@@ -120,6 +120,23 @@ struct AccFinishArgs
 };
 cudaError_t launch_acc_finish(const AccFinishArgs& a, cudaStream_t st);
 
+// ---- parameter linear solve on the device (solve.cu) ----
+struct SolveArgs
+{
+    const double* est;     // packed estimator SUMS: S[P*P] | F_R[P] | F_I[P] | O[P] | E_R | E_I | other | acc | trials | samples
+    int cnt_offset;        // index of `acc` in est
+    int P;
+    int imaginary_time;    // IMAGINARY_TIME: 0 real time, 1 imaginary time
+    int use_preconditioning;
+    double regularization; // 0.001 in the reference (src/TDVMC.cpp:1737)
+    double min_scaling;    // 0: reference behaviour
+    double* L_global;      // [P (P + 1) / 2] scratch for P too large for shared memory
+    int L_in_smem;         // set by the launcher
+    int force_global;      // tests: exercise the global-memory variant at small P
+    double* out;           // uDotR[P] | uDotI[P] | phiDotR | phiDotI | not-positive-definite flag | <E^R> | <E^I>
+};
+cudaError_t launch_solve(SolveArgs a, int smem_optin, cudaStream_t st);
+
 // ---- small utilities (util.cu) ----
 cudaError_t launch_wrap(const SysDev& s, double* pos, int W, cudaStream_t st);
 // ---- additional observables g(r), S(k) (observables.cu) ----

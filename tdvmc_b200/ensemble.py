@@ -86,6 +86,27 @@ class GpuEnsembleSystem:
                                                                               MC_NADDITIONALINITIALIZATIONSTEPS)
         return dict(r2=r2, angularDistribution=angle, densityFromCOM=density, particleDistances=distance)
 
+    # -- parameter derivatives and the Euler step, solved on the device ------------------------------
+    def SampleExpectationValues(self, uR, uI, phiR, phiI, MC_NSTEPS, MC_NTHERMSTEPS, MC_NINITIALIZATIONSTEPS=0, time=0.0):
+        """ParallelUpdateExpectationValues without the fetch: the estimator sums stay on the device for
+        SolveForParametersDot / CalculateNextParametersEuler below."""
+        self.handle.set_params(uR, uI, phiR, phiI, time)
+        self.handle.sample_and_accumulate(MC_NSTEPS, MC_NTHERMSTEPS, MC_NINITIALIZATIONSTEPS)
+
+    def SolveForParametersDot(self, IMAGINARY_TIME=1, USE_PRECONDITIONING=1, regularization=0.001):
+        """src/TDVMC.cpp:1713-1763 (Cholesky branch) on the all-reduced device estimators:
+        returns (uDotR, uDotI, phiDotR, phiDotI, info)."""
+        d = self.handle.solve_parameters_dot(imaginary_time=IMAGINARY_TIME, use_preconditioning=USE_PRECONDITIONING,
+                                             regularization=regularization)
+        return d["u_dot_r"], d["u_dot_i"], d["phi_dot_r"], d["phi_dot_i"], d
+
+    def CalculateNextParametersEuler(self, dt, uR, uI, phiR, phiI, IMAGINARY_TIME=1, USE_PRECONDITIONING=1, time=0.0,
+                                     regularization=0.001):
+        """src/TDVMC.cpp:1834-1853 + BroadcastNewParameters (:506-512): returns the new (uR, uI, phiR, phiI, info) and
+        leaves them current on the device; info carries <E^R>, <E^I> of the step and doNotAcceptStep."""
+        return self.handle.euler_step(dt, uR, uI, phiR, phiI, time=time, imaginary_time=IMAGINARY_TIME,
+                                      use_preconditioning=USE_PRECONDITIONING, regularization=regularization)
+
     def GetExponent(self):
         return self.handle.last_exponent()
 

@@ -1,6 +1,7 @@
 #include "GpuEnsembleSystem.h"
 
 #include <cmath>
+#include <cstring>
 #include <stdexcept>
 
 namespace tdvmc_host
@@ -340,6 +341,54 @@ Estimators GpuEnsembleSystem::ParallelUpdateExpectationValuesForGivenSamples(con
     Check(tdvmc_gpu_set_params(handle, uR.data(), uI.data(), phiR, phiI, time), "set_params");
     Check(tdvmc_gpu_reevaluate_stored(handle), "reevaluate_stored");
     return Fetch();
+}
+
+void GpuEnsembleSystem::SampleExpectationValues(const std::vector<double>& uR, const std::vector<double>& uI, double phiR,
+                                                double phiI, int MC_NSTEPS, int MC_NTHERMSTEPS, int MC_NINITIALIZATIONSTEPS,
+                                                double time)
+{
+    Check(tdvmc_gpu_set_params(handle, uR.data(), uI.data(), phiR, phiI, time), "set_params");
+    Check(tdvmc_gpu_sample_and_accumulate(handle, MC_NSTEPS, MC_NTHERMSTEPS, MC_NINITIALIZATIONSTEPS), "sample_and_accumulate");
+}
+
+static tdvmc_solver_desc MakeSolverDesc(int IMAGINARY_TIME, int USE_PRECONDITIONING)
+{
+    tdvmc_solver_desc sd;
+    memset(&sd, 0, sizeof(sd));
+    sd.struct_size = sizeof(sd);
+    sd.imaginary_time = IMAGINARY_TIME;
+    sd.use_preconditioning = USE_PRECONDITIONING;
+    sd.regularization = 0.001; // src/TDVMC.cpp:1737
+    return sd;
+}
+
+bool GpuEnsembleSystem::SolveForParametersDot(std::vector<double>& uDotR, std::vector<double>& uDotI, double* phiDotR,
+                                              double* phiDotI, int IMAGINARY_TIME, int USE_PRECONDITIONING)
+{
+    const tdvmc_solver_desc sd = MakeSolverDesc(IMAGINARY_TIME, USE_PRECONDITIONING);
+    uDotR.assign(P, 0.0);
+    uDotI.assign(P, 0.0);
+    tdvmc_parameters_dot d;
+    memset(&d, 0, sizeof(d));
+    d.u_dot_r = uDotR.data();
+    d.u_dot_i = uDotI.data();
+    Check(tdvmc_gpu_solve_parameters_dot(handle, &sd, &d), "solve_parameters_dot");
+    *phiDotR = d.phi_dot_r;
+    *phiDotI = d.phi_dot_i;
+    return d.not_positive_definite != 0;
+}
+
+bool GpuEnsembleSystem::CalculateNextParametersEuler(double dt, std::vector<double>& uR, std::vector<double>& uI, double* phiR,
+                                                     double* phiI, int IMAGINARY_TIME, int USE_PRECONDITIONING, double time,
+                                                     double* localEnergyR, double* localEnergyI)
+{
+    const tdvmc_solver_desc sd = MakeSolverDesc(IMAGINARY_TIME, USE_PRECONDITIONING);
+    tdvmc_parameters_dot d;
+    memset(&d, 0, sizeof(d));
+    Check(tdvmc_gpu_euler_step(handle, &sd, dt, time, uR.data(), uI.data(), phiR, phiI, &d), "euler_step");
+    if (localEnergyR) *localEnergyR = d.local_energy_r;
+    if (localEnergyI) *localEnergyI = d.local_energy_i;
+    return d.not_positive_definite != 0;
 }
 
 ObservableTables MakePairDistributionGrid(double rMax, int numOfPairDistributionValues, double weight)

@@ -166,6 +166,20 @@ public:
     void UpdateSamplesConsecutive(int nrOfSamplesToUpdate, const std::vector<double>& uR, const std::vector<double>& uI,
                                   double phiR, double phiI, int MC_NTHERMSTEPS, double time);
     double GetExponent();
+
+    // ---- parameter derivatives on the device ----
+    // ParallelUpdateExpectationValues without the fetch: the estimator sums stay in HBM for the two calls below.
+    void SampleExpectationValues(const std::vector<double>& uR, const std::vector<double>& uI, double phiR, double phiI,
+                                 int MC_NSTEPS, int MC_NTHERMSTEPS, int MC_NINITIALIZATIONSTEPS, double time);
+    // SolveForParametersDot, LINEAR_EQUATION_SOLVER_TYPE = 0 (src/TDVMC.cpp:1713-1763), on the all-reduced estimators;
+    // returns true if the matrix was not positive definite (the reference's doNotAcceptStep, :1577-1589).
+    bool SolveForParametersDot(std::vector<double>& uDotR, std::vector<double>& uDotI, double* phiDotR, double* phiDotI,
+                               int IMAGINARY_TIME, int USE_PRECONDITIONING);
+    // CalculateNextParametersEuler (src/TDVMC.cpp:1834-1853) followed by BroadcastNewParameters (:506-512): every rank
+    // ends with the same new parameters, current on its device.  localEnergyR/I (may be null) receive <E> of the step.
+    bool CalculateNextParametersEuler(double dt, std::vector<double>& uR, std::vector<double>& uI, double* phiR, double* phiI,
+                                      int IMAGINARY_TIME, int USE_PRECONDITIONING, double time, double* localEnergyR,
+                                      double* localEnergyI);
     // ParallelCalculateAdditionalSystemProperties (src/TDVMC.cpp:1438-1444) for the bulk spline systems: the mean
     // pairDistribution / structureFactor values (additionalObservablesMean.observables[0], [1]) over samples, walkers, ranks.
     AdditionalObservables ParallelCalculateAdditionalSystemProperties(const std::vector<double>& uR, const std::vector<double>& uI,

@@ -6,7 +6,7 @@
 //   example_driver --map hebulk N LBOX N_PARAM | --map hedrop N N_PARAM
 //                                    prints the parameter map the adapter builds (no GPU needed)
 //
-// Exit code 0 and one line "E_R=... acceptance=..." on success; without a CUDA device the library
+// Exit code 0, one line "E_R=... acceptance=..." and one line "EULER ..." (parameters after one device-solved Euler step) on success; without a CUDA device the library
 // refuses to run (no CPU fallback) and the driver prints the error and exits with code 3.
 #include "GpuEnsembleSystem.h"
 
@@ -80,6 +80,11 @@ int main(int argc, char** argv)
         Estimators e = gpu.ParallelUpdateExpectationValues(uR, uI, 0.0, 0.0, MC_NSTEPS, MC_NTHERMSTEPS, MC_NINIT, 0.0);
         std::printf("E_R=%.12g acceptance=%.4f samples=%lld exponent=%.10g\n", e.localEnergyR,
                     (double)e.nAcceptances / (double)e.nTrials, e.nSamples, gpu.GetExponent());
+        // one imaginary-time Euler step solved on the device from the estimators that are still resident there
+        // (CalculateNextParametersEuler, src/TDVMC.cpp:1834-1853)
+        double phiR = 0.0, phiI = 0.0, eR = 0.0, eI = 0.0;
+        const bool notPD = gpu.CalculateNextParametersEuler(1e-4, uR, uI, &phiR, &phiI, 1, 1, 1e-4, &eR, &eI);
+        std::printf("EULER uR0=%.17g uRlast=%.17g phiR=%.17g E_R=%.17g notPD=%d\n", uR[0], uR[P - 1], phiR, eR, notPD ? 1 : 0);
     }
     catch (const std::exception& ex)
     {

@@ -520,6 +520,11 @@ def test_cpp_host_adapter_matches_python_path(capi, golden, tmp_path):
     h.sample_and_accumulate(2, N, 10 * N)
     e_py = h.allreduce_and_fetch()["e_r"][0]
     assert abs(e_cpp - e_py) < 1e-9 * abs(e_py)
+    # the Euler step the driver took with the device solve: same chain, same estimators -> same new parameters
+    u2, _, phi2, _, dot = h.euler_step(1e-4, uR, np.zeros(P), 0.0, 0.0, time=1e-4, imaginary_time=1)
+    euler = dict(kv.split("=") for kv in r.stdout.split("EULER ")[1].split())
+    assert float(euler["uR0"]) == u2[0] and float(euler["uRlast"]) == u2[-1] and float(euler["phiR"]) == phi2
+    assert float(euler["E_R"]) == dot["e_r"] and int(euler["notPD"]) == 0
     h.close()
 
 
@@ -1054,3 +1059,135 @@ def test_he_structure_factor_matches_reference(capi, golden, name):
     _, sk = h.observables_fixed(obs, src["R"][None])
     assert np.max(np.abs(sk[0] - g["sk_fixed"])) <= 1e-10 * np.max(np.abs(g["sk_fixed"]))
     h.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# SolveForParametersDot / CalculateNextParametersEuler on the device
+# ---------------------------------------------------------------------------------------------------
+def _solve_in_reference_order(O, S, OER, OEI, ER, EI, imaginary_time, eps=0.001):
+    """SolveForParametersDot, Cholesky branch, in scalar Python floats with the reference's loop order
+    (src/TDVMC.cpp:1506-1537, 1560-1622, 1658-1711): IEEE double, no fused operations - what g++ -O3 computes."""
+    import math
+    P = len(O)
+    O = [float(x) for x in O]
+    if imaginary_time == 0:
+        bR = [float(OEI[i]) - EI * O[i] for i in range(P)]
+        bI = [-float(OER[i]) + ER * O[i] for i in range(P)]
+    else:
+        bR = [-float(OER[i]) + ER * O[i] for i in range(P)]
+        bI = [-float(OEI[i]) for i in range(P)]
+    A = [[0.0] * P for _ in range(P)]
+    for i in range(P):
+        for j in range(i + 1):
+            A[i][j] = float(S[i][j]) - O[i] * O[j]
+            A[j][i] = A[i][j]
+    sc = [math.sqrt(A[i][i]) for i in range(P)]
+    for i in range(P):
+        for j in range(P):
+            A[i][j] /= (sc[i] * sc[j])
+        bR[i] /= sc[i]
+        bI[i] /= sc[i]
+    for i in range(P):
+        A[i][i] += eps
+    for i in range(P):
+        Ai = A[i]
+        for j in range(i + 1):
+            s = Ai[j]
+            Aj = A[j]
+            for k in range(j):
+                s -= Ai[k] * Aj[k]
+            if i > j:
+                Ai[j] = s / Aj[j]
+            elif s > 0:
+                Ai[i] = math.sqrt(s)
+    sols = []
+    for rhs in (bR, bI):
+        tmp = [0.0] * P
+        for i in range(P):
+            s = 0.0
+            for j in range(i):
+                s += A[i][j] * tmp[j]
+            tmp[i] = 1.0 / A[i][i] * (rhs[i] - s)
+        x = [0.0] * P
+        for i in range(P - 1, -1, -1):
+            s = 0.0
+            for j in range(P - 1, i, -1):
+                s += A[j][i] * x[j]
+            x[i] = 1.0 / A[i][i] * (tmp[i] - s)
+        sols.append(x)
+    pr = pi = 0.0
+    for i in range(P):
+        pr -= O[i] * sols[0][i]
+        pi -= O[i] * sols[1][i]
+    if imaginary_time == 0:
+        pi -= ER
+    else:
+        pr -= ER
+    return (np.array([sols[0][i] / sc[i] for i in range(P)]), np.array([sols[1][i] / sc[i] for i in range(P)]), pr, pi)
+
+
+@pytest.mark.parametrize("name", ["bosonsbulk_n64_evolution", "bosonsbulk_n64_evolution_realtime"])
+def test_device_solver_matches_reference(capi, golden, name):
+    """tdvmc_gpu_solve_fixed on the reference's own first-step estimators reproduces the derivatives the reference's
+    SolveForParametersDot computed from them (ref_harness evolve, printed at 17 digits): the kernel applies the
+    reference's operations in the reference's order, so the agreement is to the last bit, in shared memory and in the
+    global-memory variant alike."""
+    g = golden(name)
+    src = golden(str(g["source"]))
+    spec = systems.bosons_bulk(int(g["N"]), float(g["LBOX"]), int(g["N_PARAM"]), g["SYSTEM_PARAMS"], weights=src["spline_weights"])
+    h = capi.Handle(spec, 4)
+    est = dict(O=g["first_O"], S=g["first_S"], OER=g["first_OER"], OEI=g["first_OEI"], e_r=g["first_ER"], e_i=g["first_EI"])
+    imag = int(g["IMAGINARY_TIME"])
+    for force_global in (False, True):
+        d = h.solve_fixed(est, imaginary_time=imag, force_global=force_global)
+        assert not d["not_positive_definite"]
+        assert np.array_equal(d["u_dot_r"], g["first_uDotR"]) and np.array_equal(d["u_dot_i"], g["first_uDotI"]), \
+            (rel(d["u_dot_r"], g["first_uDotR"]), rel(d["u_dot_i"], g["first_uDotI"]))
+        assert d["phi_dot_r"] == float(g["first_phiDotR"]) and d["phi_dot_i"] == float(g["first_phiDotI"])
+        assert d["e_r"] == float(g["first_ER"]) and d["e_i"] == float(g["first_EI"])
+    # a matrix that is not positive definite is reported, as the reference's doNotAcceptStep
+    bad = dict(est, S=np.outer(g["first_O"], g["first_O"]) - np.eye(len(g["first_O"])))
+    d = h.solve_fixed(bad, imaginary_time=imag, use_preconditioning=False)
+    assert d["not_positive_definite"]
+    with pytest.raises(capi.TdvmcError, match="IMAGINARY_TIME"):
+        h.solve_fixed(est, imaginary_time=-1)
+    h.close()
+
+
+def test_device_euler_step_at_headline_size(capi, golden):
+    """P = 201 (BASELINE config 3): SolveForParametersDot on the device-resident estimators of a sampling pass equals
+    the reference-order scalar solve of the fetched estimators bit for bit and the numpy mirror to rounding; the Euler
+    step leaves the device at the new parameters (evaluation equals a handle set to them by hand)."""
+    from tdvmc_b200 import timestep
+    g = golden("bosonsbulk_n343_equil")
+    W = 296
+    spec, h = make_handle(capi, g, n_walkers=W, seed=11, mc_step=0.5, max_samples=2)
+    h.set_positions(np.broadcast_to(g["R"], (W, 343, 3)).copy())
+    h.sample_and_accumulate(2, 343, 343)
+    d = h.solve_parameters_dot(imaginary_time=1, min_scaling=1e-12)
+    a = h.allreduce_and_fetch()                                   # fetch after the solve: the sums are still there
+    assert d["e_r"] == a["e_r"][0] and d["e_i"] == a["e_i"][0]
+    diag = np.diag(a["S"]) - a["O"] ** 2
+    if diag.min() > 0:                                            # (an operator that never varied has no reference answer)
+        ur, ui, pr, pi = _solve_in_reference_order(a["O"], a["S"], a["OER"], a["OEI"], float(a["e_r"][0]), float(a["e_i"][0]), 1)
+        assert np.array_equal(d["u_dot_r"], ur) and np.array_equal(d["u_dot_i"], ui), (rel(d["u_dot_r"], ur), rel(d["u_dot_i"], ui))
+        assert d["phi_dot_r"] == pr and d["phi_dot_i"] == pi
+    est = dict(localOperators=a["O"], localOperatorsMatrix=a["S"], localOperatorlocalEnergyR=a["OER"],
+               localOperatorlocalEnergyI=a["OEI"], localEnergyR=float(a["e_r"][0]), localEnergyI=float(a["e_i"][0]))
+    vr, vi, qr, qi = timestep.solve_for_parameters_dot(est, imaginary_time=1, min_scaling=1e-12, lapack=True)
+    scale = np.max(np.abs(vr))
+    assert np.max(np.abs(d["u_dot_r"] - vr)) < 1e-8 * scale and np.max(np.abs(d["u_dot_i"] - vi)) < 1e-8 * max(np.max(np.abs(vi)), scale)
+    assert abs(d["phi_dot_r"] - qr) < 1e-8 * abs(qr)
+    dt = 1e-4
+    uR, uI, phiR, phiI, d2 = h.euler_step(dt, g["uR"], g["uI"], float(g["phiR"]), float(g["phiI"]), imaginary_time=1, min_scaling=1e-12)
+    assert np.array_equal(d2["u_dot_r"], d["u_dot_r"])
+    assert np.array_equal(uR, g["uR"] + d["u_dot_r"] * dt) and np.array_equal(uI, g["uI"] + d["u_dot_i"] * dt)
+    assert phiR == float(g["phiR"]) + d["phi_dot_r"] * dt
+    e_new = h.evaluate_fixed(g["R"][None])
+    h2 = capi.Handle(spec, 4)
+    h2.set_params(uR, uI, phiR, phiI, 0.0)
+    e_ref = h2.evaluate_fixed(g["R"][None])
+    assert e_new["e_r"][0] == e_ref["e_r"][0] and e_new["exponent"][0] == e_ref["exponent"][0]
+    assert e_new["e_r"][0] != float(g["local_energy_r"])          # the parameters did move
+    h.close()
+    h2.close()

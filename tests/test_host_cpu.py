@@ -45,6 +45,8 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(capi.ClusterObservableDesc) == 4 * 4 + 5 * 8 + 8
     assert C.sizeof(capi.EnsembleDesc) == 6 * 4 + 8 + 8
     assert C.sizeof(capi.Estimators) == 7 * 8 + 3 * 8
+    assert C.sizeof(capi.SolverDesc) == 4 * 4 + 2 * 8
+    assert C.sizeof(capi.ParametersDot) == 2 * 8 + 4 * 8 + 8
 
 
 def test_no_cpu_fallback_without_a_device(golden):
