@@ -523,8 +523,10 @@ def test_cpp_host_adapter_matches_python_path(capi, golden, tmp_path):
     # the Euler step the driver took with the device solve: same chain, same estimators -> same new parameters
     u2, _, phi2, _, dot = h.euler_step(1e-4, uR, np.zeros(P), 0.0, 0.0, time=1e-4, imaginary_time=1)
     euler = dict(kv.split("=") for kv in r.stdout.split("EULER ")[1].split())
-    assert float(euler["uR0"]) == u2[0] and float(euler["uRlast"]) == u2[-1] and float(euler["phiR"]) == phi2
-    assert float(euler["E_R"]) == dot["e_r"] and int(euler["notPD"]) == 0
+    # (the driver builds uR with std::exp/std::pow, numpy may differ in the last bit: same tolerance as E_R above)
+    for key, want in (("uR0", u2[0]), ("uRlast", u2[-1]), ("phiR", phi2), ("E_R", dot["e_r"])):
+        assert abs(float(euler[key]) - want) < 1e-9 * abs(want), key
+    assert abs(u2[0] - uR[0]) > 1e-9 * abs(uR[0]) and int(euler["notPD"]) == 0    # the step did move the parameters
     h.close()
 
 
