@@ -680,12 +680,110 @@ def gen_min_image():
     print(f"min_image_reference: {len(rows)} cases")
 
 
+def boxradial_drift(d, uR, uI):
+    """Drift from the REFERENCE's four tables, contracted as NUBosonsBulkPBBoxAndRadial.cpp:461-523 does (long double),
+    including its use of the box table sD[K-1] for the last radial parameter's gradient (:493-497)."""
+    sD, sDr = d["sD"].astype(np.longdouble), d["sD_rad"].astype(np.longdouble)   # [K][N][3]
+    K = sD.shape[0]
+    P = len(uR)
+    PR = P // 2
+    out = []
+    for u in (uR, uI):
+        u = np.asarray(u, np.longdouble)
+        F = np.einsum("k,kna->na", u[:PR], sDr[1:PR + 1]) + u[1] * sDr[0]
+        F = F + u[PR - 1] * sDr[K - 2] / np.longdouble(-2.0) + u[PR - 1] * sD[K - 1]
+        F = F + np.einsum("k,kna->na", u[PR:], sD[1:PR + 1]) + u[PR + 1] * sD[0] + u[P - 1] * sD[K - 2] + u[P - 1] * sD[K - 1]
+        out.append(F.astype(np.float64))
+    return out
+
+
+def boxradial_params(P, half):
+    """Smooth non-zero parameters for both bases (the shipped config starts from zeros)."""
+    PR = P // 2
+    x = np.arange(PR) * half / (PR - 1)
+    uR = np.concatenate([-0.5 * np.exp(-((x / 0.5) ** 2)), 0.04 * np.exp(-(((x - 0.6 * half) / (0.25 * half)) ** 2))])
+    uI = np.concatenate([0.05 * np.exp(-(((x - 0.5 * half) / (0.2 * half)) ** 2)), -0.02 * np.exp(-((x / (0.4 * half)) ** 2))])
+    return uR, uI
+
+
+def pack_eval_boxradial(name, scal, arrays, moves):
+    system = "NUBosonsBulkPBBoxAndRadial"
+    with tempfile.TemporaryDirectory() as td:
+        cp, op = os.path.join(td, "case.txt"), os.path.join(td, "out.txt")
+        write_case(cp, system, scal, arrays, moves)
+        run("eval", cp, op)
+        d = parse_dump(op)
+    out = {"system": np.array(system), "N": np.array(scal["N"]), "DIM": np.array(3), "LBOX": np.array(scal["LBOX"]),
+           "N_PARAM": np.array(scal["N_PARAM"]), "SYSTEM_PARAMS": np.asarray(arrays["SYSTEM_PARAMS"], np.float64),
+           "NURBS_GRID": np.asarray(arrays["NURBS_GRID"], np.float64), "time": np.array(scal.get("time", 0.0)),
+           "R": np.asarray(arrays["R"], np.float64).reshape(-1, 3), "uR": np.asarray(arrays["uR"], np.float64),
+           "uI": np.asarray(arrays["uI"], np.float64), "phiR": np.array(scal.get("phiR", 0.0)),
+           "phiI": np.array(scal.get("phiI", 0.0)), "moves": np.asarray(moves, np.float64).reshape(-1, 4)}
+    for k in ("exponent", "exponent_wf", "wf", "local_energy_r", "local_energy_i", "local_operators", "local_operator_energy_r",
+              "local_operator_energy_i", "other_expectation_values", "local_operators_matrix_diag", "local_operators_matrix_row3",
+              "knots", "knots_rad", "spline_weights", "spline_weights_rad", "spline_sums", "spline_sums_rad", "max_distance_rad",
+              "half_length", "other_local_operators", "gr_bins", "gr_bin_volumes", "gr_node_point_spacing", "move_quotient",
+              "move_exponent_new", "sD", "sD2", "sD_rad", "sD2_rad"):
+        out[k] = d[k]
+    out["drift_r"], out["drift_i"] = boxradial_drift(d, out["uR"], out["uI"])
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(f"{name}: E_R={float(d['local_energy_r']):.12g} E_I={float(d['local_energy_i']):.12g} "
+          f"exponent={float(d['exponent']):.12g} q={d['move_quotient']}")
+    return d
+
+
+def gen_boxradial():
+    """NUBosonsBulkPBBoxAndRadial (config/NUBosonsBulkPBBoxAndRadial3D.config at its own size: N = 27,
+    rho = 1 -> L = 3, N_PARAM = 100 on the config's 51-point grid, SYSTEM_PARAMS = [0.1, 50], GR_BIN_COUNT = 400), plus a
+    64-particle case on a non-uniform grid.  Fixtures: the jittered start-up lattice, an equilibrated snapshot, a sampling run."""
+    rng = np.random.default_rng(27)
+    cfg = json.loads(re.sub(r"(\d)\.(\s*[,\]\}])", r"\g<1>.0\2",
+                            open(os.path.join(REF, "config", "NUBosonsBulkPBBoxAndRadial3D.config")).read()))
+    N, P = int(cfg["N"]), int(cfg["N_PARAM"])
+    L = float(round((N / float(cfg["RHO"])) ** (1.0 / 3.0), 9))
+    grid = np.array(cfg["NURBS_GRID"], dtype=np.float64)
+    uR, uI = boxradial_params(P, L / 2)
+    scal = dict(N=N, LBOX=L, N_PARAM=P, USE_NURBS=1, time=0.0, phiR=0.05, phiI=0.0, GR_BIN_COUNT=int(cfg["GR_BIN_COUNT"]))
+    arr = dict(uR=uR, uI=uI, SYSTEM_PARAMS=cfg["SYSTEM_PARAMS"], NURBS_GRID=grid)
+    # (A perfect lattice cannot be a fixture: a displacement component of exactly zero sends the reference's
+    #  lower_bound to bin 2 and its loop to splineWeights[-1] (:258-266) - it crashes.  Jittered start instead.)
+    Rj = jittered_lattice(N, L, seed=27)
+    pack_eval_boxradial("boxradial_n27_jittered", scal, dict(arr, R=Rj), default_moves(Rj, L, rng))
+    R0 = jittered_lattice(N, L, seed=28)
+    mcs = dict(scal, MC_STEP=float(cfg["MC_STEP"]), MC_NSTEPS=1, MC_NTHERMSTEPS=N * 200, seed=12)
+    mc = run_mc("NUBosonsBulkPBBoxAndRadial", mcs, dict(arr, R=R0))
+    R1 = mc["R_final"].reshape(N, 3)
+    pack_eval_boxradial("boxradial_n27_equil", scal, dict(arr, R=R1), default_moves(R1, L, rng))
+    # sampling run of the reference's own Metropolis loop at these parameters: estimators + series for error bars
+    mc2 = run_mc("NUBosonsBulkPBBoxAndRadial", dict(mcs, MC_NSTEPS=4000, MC_NTHERMSTEPS=N, MC_NINITIALIZATIONSTEPS=N * 50, seed=13),
+                 dict(arr, R=R1))
+    np.savez_compressed(os.path.join(GOLDEN, "boxradial_n27_mc.npz"), source=np.array("boxradial_n27_equil"),
+                        MC_STEP=np.array(mcs["MC_STEP"]), MC_NSTEPS=np.array(4000), MC_NTHERMSTEPS=np.array(N),
+                        local_energy_r=mc2["local_energy_r"], local_energy_i=mc2["local_energy_i"],
+                        local_operators=mc2["local_operators"], energy_r_series=mc2["energy_r_series"],
+                        energy_i_series=mc2["energy_i_series"], other_expectation_values=mc2["other_expectation_values"][:3],
+                        acceptance=np.array(float(mc2["n_acceptances"]) / float(mc2["n_trials"])))
+    print("boxradial_n27_mc: E_R=%.6f acceptance=%.3f" % (float(mc2["local_energy_r"]), float(mc2["n_acceptances"]) / float(mc2["n_trials"])))
+    # 64 particles (more than one warp's worth), non-uniform grid, time-switched potential
+    N2, L2, P2 = 64, 4.0, 60
+    x = np.linspace(0.0, 1.0, P2 // 2 + 1)
+    grid2 = 2.0 * (0.4 * x + 0.6 * x ** 2)
+    grid2[-1] = 2.0
+    uR2, uI2 = boxradial_params(P2, L2 / 2)
+    scal2 = dict(N=N2, LBOX=L2, N_PARAM=P2, USE_NURBS=1, time=1.0, phiR=0.0, phiI=0.0, GR_BIN_COUNT=50)
+    arr2 = dict(uR=uR2, uI=uI2, SYSTEM_PARAMS=[0.1, 50.0, 0.5, 0.3, 20.0], NURBS_GRID=grid2)
+    R2 = jittered_lattice(N2, L2, seed=29)
+    mc3 = run_mc("NUBosonsBulkPBBoxAndRadial", dict(scal2, MC_STEP=0.4, MC_NSTEPS=1, MC_NTHERMSTEPS=N2 * 100, seed=14), dict(arr2, R=R2))
+    R3 = mc3["R_final"].reshape(N2, 3)
+    pack_eval_boxradial("boxradial_n64_equil", scal2, dict(arr2, R=R3), default_moves(R3, L2, rng))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     if not os.path.exists(HARNESS):
         sys.exit("build the oracle first: make -C oracle/ref_build")
     which = sys.argv[1:] or ["min_image", "bosonsbulk", "bosonsbulk_mc", "bosonsbulk_mc_headline", "nubosonsbulkpb", "nubosonsbulkpb_full", "hebulk", "hedrop",
-                             "mixture", "observables", "he_observables", "mixture_observables", "evolution"]
+                             "mixture", "observables", "he_observables", "mixture_observables", "evolution", "boxradial"]
     for w in which:
         globals()["gen_" + w]()
 

@@ -235,6 +235,26 @@ void DumpSystemInternals(Dump& d)
     {
         DumpSplineInternals(d, s);
     }
+    else if (auto s = dynamic_cast<PhysicalSystems::NUBosonsBulkPBBoxAndRadial*>(sys))
+    {
+        // two bases on the same knots: radial splines in r_ij and "box" splines in |x_ij|, |y_ij|, |z_ij|
+        d.vec("knots", s->nodes);
+        d.vec("knots_rad", s->nodesRad);
+        d.ten("spline_weights", s->splineWeights);
+        d.ten("spline_weights_rad", s->splineWeightsRad);
+        d.vec("spline_sums", s->splineSums);
+        d.vec("spline_sums_rad", s->splineSumsRad);
+        d.scalar("max_distance_rad", s->maxDistanceRad);
+        d.scalar("half_length", s->halfLength);
+        d.ten("sD", s->splineSumsD);
+        d.mat("sD2", s->splineSumsD2);
+        d.ten("sD_rad", s->splineSumsDRad);
+        d.mat("sD2_rad", s->splineSumsD2Rad);
+        d.vec("other_local_operators", s->otherLocalOperators);
+        d.vec("gr_bins", s->grBins);
+        d.vec("gr_bin_volumes", s->grBinVolumes);
+        d.scalar("gr_node_point_spacing", s->grNodePointSpacing);
+    }
     else if (auto s = dynamic_cast<PhysicalSystems::BosonMixtureCluster*>(sys))
     {
         std::vector<double> pt, ct, mass, hb;

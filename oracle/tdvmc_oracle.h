@@ -93,6 +93,36 @@ int64_t oracle_sample_walker(const oracle_system* s, double* R, const double* uR
                              uint64_t seed, uint32_t walker, uint64_t* step_counter, int n_init, int n_samples,
                              int n_therm, double mc_step, double* est, double* sample_rows);
 
+/* ------------------------------------------------------------------------------------------------
+ * NUBosonsBulkPBBoxAndRadial (tdvmc_oracle_br.c): radial + box spline bases on one knot vector
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct oracle_br
+{
+    int32_t n_particles, n_params, n_splines, gr_bins; /* K = N_PARAM/2 + 3 splines per basis */
+    double lbox;
+    double r_max;       /* maxDistanceRad = nodesRad[size - 4] (NUBosonsBulkPBBoxAndRadial.cpp:96) */
+    double pot_a, pot_b; /* Gauss potential b exp(-(r/a)^2/2), time switch applied (:290-297) */
+    double gr_max, gr_spacing; /* halfLength, halfLength / grBinCount (:146-147) */
+    const double* gr_volumes;  /* [gr_bins] shell volumes (:149-169) */
+    const double* knots;       /* [K + 4] */
+    const double* weights;     /* [K][4][4] */
+    const int32_t* map_ptr;    /* CSR of RefreshLocalOperators (:193-211) over ext = [ssRad | ss] */
+    const int32_t* map_col;
+    const double* map_val;
+} oracle_br;
+void oracle_br_values(const oracle_br* s, const double* R, double* ext);
+void oracle_br_operators(const oracle_br* s, const double* ext, double* O);
+double oracle_br_exponent(const oracle_br* s, const double* ext, const double* uR);
+void oracle_br_expectation(const oracle_br* s, const double* R, double wf, const double* uR, const double* uI, double* e_r,
+                           double* e_i, double* other, double* drift_r, double* drift_i, double* tabD, double* tabD2);
+double oracle_br_quotient(const oracle_br* s, const double* R, int particle, const double* old_pos, const double* ext,
+                          double exponent, const double* uR, double* ext_new, double* exponent_new);
+int64_t oracle_br_sweep(const oracle_br* s, double* R, double* ext, double* exponent, const double* uR, uint64_t seed,
+                        uint32_t walker, uint64_t first_step, int64_t n_steps, double mc_step);
+int64_t oracle_br_sample_walker(const oracle_br* s, double* R, const double* uR, const double* uI, double phiR, uint64_t seed,
+                                uint32_t walker, uint64_t* step_counter, int n_init, int n_samples, int n_therm, double mc_step,
+                                double* est, double* sample_rows);
+
 #ifdef __cplusplus
 }
 #endif

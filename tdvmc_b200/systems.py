@@ -11,6 +11,8 @@ The five systems of the BASELINE configs:
   * ``HeBulk``               src/PhysicalSystems/HeBulk.cpp:40-70, 376-383      (config 2)
   * ``HeDrop``               src/PhysicalSystems/HeDrop.cpp:71-135, 609-626     (config 1)
   * ``BosonMixtureCluster``  src/PhysicalSystems/BosonMixtureCluster.cpp:58-346 (config 5)
+and, widening per SURVEY.md section 8(f) rank 4:
+  * ``NUBosonsBulkPBBoxAndRadial``  src/PhysicalSystems/NUBosonsBulkPBBoxAndRadial.cpp:36-191 (the "radial+box splines" system)
 """
 from dataclasses import dataclass, field
 
@@ -25,6 +27,7 @@ KIND_SPLINE_TABLE = 0   # BosonsBulk, NUBosonsBulkPB: monomial spline table + bo
 KIND_HE_BULK = 1        # HeBulk: McMillan core + uniform B-splines in the local coordinate + Aziz potential
 KIND_HE_DROP = 2        # HeDrop: open boundary, McMillan core, two uniform grids, const + linear tails, LJ potential
 KIND_MIXTURE = 3        # BosonMixtureCluster: species, per-pair-type spline tables + McMillan/const/linear/log, pair potentials
+KIND_BOX_RADIAL = 4     # NUBosonsBulkPBBoxAndRadial: radial splines in r_ij + "box" splines in |x_ij|, |y_ij|, |z_ij|, Gauss potential
 
 POT_HFDB_HE_HE, POT_KTTY_HE_NA, POT_KTTY_HE_CS = 0, 1, 2
 # BosonMixtureCluster.h:28-36
@@ -147,6 +150,44 @@ def nu_bosons_bulk_pb(n_particles, lbox, n_params, nurbs_grid, system_params=(0.
     return SystemSpec("NUBosonsBulkPB", n_particles, n_params, float(lbox), knots, np.ascontiguousarray(weights), ptr, col, val,
                       PAIR_RULE_REFLECT, np.asarray(system_params, dtype=np.float64), n_other=9 + int(gr_bin_count),
                       tail_param=n_params - 1)
+
+
+def nu_bosons_bulk_pb_box_and_radial(n_particles, lbox, n_params, nurbs_grid, system_params=(0.1, 50.0), gr_bin_count=400,
+                                     weights=None):
+    """``NUBosonsBulkPBBoxAndRadial`` (NUBosonsBulkPBBoxAndRadial.cpp:36-191).
+
+    ``SetNodes`` (:36-62) mirrors the same NURBS grid into ``nodes`` (box splines, argument ``|x_ij|`` per coordinate) and
+    ``nodesRad`` (radial splines, argument ``r_ij < maxDistanceRad``), so one knot vector and one spline table serve both
+    bases (without ``USE_NURBS`` the reference reads the empty ``nodesRad``, :96 - the grid is mandatory).  ``N_PARAM/2``
+    parameters each (:84-85), ``K = N_PARAM/2 + 3`` splines each (:88-89).  Extended sums ``[ssRad_0..K-1 | ss_0..K-1]``;
+    map of ``RefreshLocalOperators`` (:193-211): ``O_i = ssRad[i+1]``, ``O_1 += ssRad[0]``,
+    ``O_{PR-1} += ssRad[K-2]/(-2) + ssRad[K-1]``; ``O_{PR+i} = ss[i+1]``, ``O_{PR+1} += ss[0]``, ``O_{P-1} += ss[K-2] + ss[K-1]``.
+    One deviation the reference has and this reproduces: the drift contracts the LAST radial spline's parameter with the
+    box table ``sD[K-1]`` instead of ``sDRad[K-1]`` (:493-497), the Laplacian does not (:498-499) -- ``extra["grad_swap"]``.
+    ``otherExpectationValues`` = kinetic, potential, wf, then ``GR_BIN_COUNT`` g(r) bins weighted by 1/shell volume (:574-580).
+    Gauss pair potential ``b exp(-(r/a)^2/2)`` inside ``maxDistanceRad`` with the time switch of :290-297."""
+    if n_params % 2:
+        raise ValueError("NUBosonsBulkPBBoxAndRadial splits N_PARAM evenly between the radial and the box basis")
+    PR = n_params // 2
+    knots = splines.extend_knots_mirrored(nurbs_grid)
+    K = len(knots) - 4
+    if K != PR + 3:
+        raise ValueError(f"NUBosonsBulkPBBoxAndRadial needs K = N_PARAM/2 + 3, got K={K}, N_PARAM={n_params}")
+    if weights is None:
+        weights = splines.bspline_monomial_weights(knots)
+    rows = [[(i + 1, 1.0)] for i in range(PR)]
+    rows[1].append((0, 1.0))
+    rows[PR - 1] += [(K - 2, 1.0 / (-2.0)), (K - 1, 1.0)]
+    rows += [[(K + i + 1, 1.0)] for i in range(PR)]
+    rows[PR + 1].append((K, 1.0))
+    rows[n_params - 1] += [(K + K - 2, 1.0), (K + K - 1, 1.0)]
+    ptr, col, val = _csr(rows)
+    half = lbox / 2.0
+    return SystemSpec("NUBosonsBulkPBBoxAndRadial", n_particles, n_params, float(lbox), knots, np.ascontiguousarray(weights),
+                      ptr, col, val, PAIR_RULE_CUT, np.asarray(system_params, dtype=np.float64), n_other=3 + int(gr_bin_count),
+                      tail_param=-1, kind=KIND_BOX_RADIAL, n_ext=2 * K,
+                      extra=dict(n_splines=K, gr_bins=int(gr_bin_count), half=half, gr_spacing=half / float(gr_bin_count),
+                                 grad_swap=(K - 1, 2 * K - 1, PR - 1)))
 
 
 def he_bulk(n_particles, lbox, n_params):
@@ -304,6 +345,11 @@ def from_golden(g):
     elif name == "NUBosonsBulkPB":
         spec = nu_bosons_bulk_pb(N, L, P, g["NURBS_GRID"], g["SYSTEM_PARAMS"], weights=g["spline_weights"],
                                  gr_bin_count=len(g["other_expectation_values"]) - 9)
+    elif name == "NUBosonsBulkPBBoxAndRadial":
+        spec = nu_bosons_bulk_pb_box_and_radial(N, L, P, g["NURBS_GRID"], g["SYSTEM_PARAMS"], weights=g["spline_weights"],
+                                                gr_bin_count=len(g["other_expectation_values"]) - 3)
+        if not (np.array_equal(g["knots"], g["knots_rad"]) and np.array_equal(g["spline_weights"], g["spline_weights_rad"])):
+            raise AssertionError("the reference's radial and box bases are expected to share knots and table")
     else:
         raise ValueError(name)
     if not np.array_equal(spec.knots, g["knots"]):

@@ -34,6 +34,13 @@ class OracleMixStruct(C.Structure):
                 ("weights", dp), ("mcm", dp), ("potential", ip), ("map_ptr", ip), ("map_col", ip), ("map_val", dp)]
 
 
+class OracleBRStruct(C.Structure):
+    _fields_ = [("n_particles", C.c_int32), ("n_params", C.c_int32), ("n_splines", C.c_int32), ("gr_bins", C.c_int32),
+                ("lbox", C.c_double), ("r_max", C.c_double), ("pot_a", C.c_double), ("pot_b", C.c_double), ("gr_max", C.c_double),
+                ("gr_spacing", C.c_double), ("gr_volumes", dp), ("knots", dp), ("weights", dp), ("map_ptr", ip), ("map_col", ip),
+                ("map_val", dp)]
+
+
 def lib():
     global _LIB
     if _LIB is None:
@@ -55,6 +62,10 @@ def lib():
         L.oracle_he_quotient.restype = C.c_double
         L.oracle_he_sweep.restype = C.c_int64
         L.oracle_he_sample_walker.restype = C.c_int64
+        L.oracle_br_exponent.restype = C.c_double
+        L.oracle_br_quotient.restype = C.c_double
+        L.oracle_br_sweep.restype = C.c_int64
+        L.oracle_br_sample_walker.restype = C.c_int64
         _LIB = L
     return _LIB
 
@@ -273,6 +284,103 @@ class OracleHe:
         return Oracle.unpack_est(self, est, n)
 
 
+def br_shell_volumes(half, n_bins):
+    """grBinVolumes of NUBosonsBulkPBBoxAndRadial::InitSystem (:146-169), same operations in the same order."""
+    import math
+    spacing = half / float(n_bins)
+    v = [4.0 * math.pi * math.pow(spacing * (i + 1), 3.0) / 3.0 for i in range(n_bins)]
+    for i in range(n_bins - 1, 0, -1):
+        v[i] = v[i] - v[i - 1]
+    return np.array(v), spacing
+
+
+class OracleBR:
+    """NUBosonsBulkPBBoxAndRadial restatement (oracle/tdvmc_oracle_br.c) with numpy in/out; ext = [ssRad | ss]."""
+
+    def __init__(self, spec, time=0.0):
+        self.spec = spec
+        e = spec.extra
+        a, b = spec.potential(time)
+        vol, spacing = br_shell_volumes(e["half"], e["gr_bins"])
+        self._keep = [vol, np.ascontiguousarray(spec.knots, np.float64), np.ascontiguousarray(spec.weights, np.float64),
+                      np.ascontiguousarray(spec.map_ptr, np.int32), np.ascontiguousarray(spec.map_col, np.int32),
+                      np.ascontiguousarray(spec.map_val, np.float64)]
+        k = self._keep
+        self.sys = OracleBRStruct(spec.n_particles, spec.n_params, e["n_splines"], e["gr_bins"], spec.lbox, spec.r_max, a, b,
+                                  e["half"], spacing, _d(k[0]), _d(k[1]), _d(k[2]), k[3].ctypes.data_as(ip),
+                                  k[4].ctypes.data_as(ip), _d(k[5]))
+        self.N, self.P, self.K = spec.n_particles, spec.n_params, e["n_splines"]
+        self.NE, self.NO = 2 * self.K, 3 + e["gr_bins"]
+
+    def values(self, R):
+        ext = np.zeros(self.NE)
+        lib().oracle_br_values(C.byref(self.sys), _d(np.ascontiguousarray(R, np.float64)), _d(ext))
+        return ext
+
+    def operators(self, ext):
+        O = np.zeros(self.P)
+        lib().oracle_br_operators(C.byref(self.sys), _d(np.ascontiguousarray(ext)), _d(O))
+        return O
+
+    def exponent(self, ext, uR):
+        return lib().oracle_br_exponent(C.byref(self.sys), _d(np.ascontiguousarray(ext)), _d(np.ascontiguousarray(uR, np.float64)))
+
+    def evaluate(self, R, uR, uI, phiR=0.0):
+        R = np.ascontiguousarray(R, np.float64)
+        uR = np.ascontiguousarray(uR, np.float64)
+        uI = np.ascontiguousarray(uI, np.float64)
+        ext = self.values(R)
+        ex = self.exponent(ext, uR)
+        er, ei = C.c_double(0), C.c_double(0)
+        other = np.zeros(self.NO)
+        dr, di = np.zeros((self.N, 3)), np.zeros((self.N, 3))
+        tD, tD2 = np.zeros((self.NE, self.N, 3)), np.zeros((self.NE, self.N))
+        lib().oracle_br_expectation(C.byref(self.sys), _d(R), C.c_double(np.exp(ex + phiR)), _d(uR), _d(uI), C.byref(er),
+                                    C.byref(ei), _d(other), _d(dr), _d(di), _d(tD), _d(tD2))
+        return dict(ext=ext, O=self.operators(ext), exponent=ex, e_r=er.value, e_i=ei.value, other=other, drift_r=dr,
+                    drift_i=di, tabD=tD, tabD2=tD2)
+
+    def quotient(self, R, particle, new_pos, uR):
+        R = np.array(R, np.float64)
+        uR = np.ascontiguousarray(uR, np.float64)
+        ext = self.values(R)
+        ex = self.exponent(ext, uR)
+        old = R[particle].copy()
+        R[particle] = new_pos
+        ext_new = np.zeros(self.NE)
+        en = C.c_double(0)
+        q = lib().oracle_br_quotient(C.byref(self.sys), _d(R), int(particle), _d(old), _d(ext), C.c_double(ex), _d(uR),
+                                     _d(ext_new), C.byref(en))
+        return q, en.value, ex
+
+    def sweep(self, R, uR, seed, walker, first_step, n_steps, mc_step):
+        R = np.array(R, np.float64)
+        uR = np.ascontiguousarray(uR, np.float64)
+        ext = self.values(R)
+        ex = C.c_double(self.exponent(ext, uR))
+        acc = lib().oracle_br_sweep(C.byref(self.sys), _d(R), _d(ext), C.byref(ex), _d(uR), C.c_uint64(seed), C.c_uint32(walker),
+                                    C.c_uint64(first_step), C.c_int64(n_steps), C.c_double(mc_step))
+        return R, int(acc)
+
+    def est_size(self):
+        return self.P * self.P + 3 * self.P + 2 + self.NO
+
+    def sample_walker(self, R, uR, uI, phiR, seed, walker, step0, n_init, n_samples, n_therm, mc_step, est=None):
+        R = np.array(R, np.float64)
+        if est is None:
+            est = np.zeros(self.est_size())
+        rows = np.zeros((n_samples, self.P + 2))
+        sc = C.c_uint64(step0)
+        acc = lib().oracle_br_sample_walker(C.byref(self.sys), _d(R), _d(np.ascontiguousarray(uR, np.float64)),
+                                            _d(np.ascontiguousarray(uI, np.float64)), C.c_double(phiR), C.c_uint64(seed),
+                                            C.c_uint32(walker), C.byref(sc), n_init, n_samples, n_therm, C.c_double(mc_step),
+                                            _d(est), _d(rows))
+        return dict(R=R, est=est, rows=rows, accepted=int(acc), steps=sc.value)
+
+    def unpack_est(self, est, n):
+        return Oracle.unpack_est(self, est, n)
+
+
 class OracleMix:
     """BosonMixtureCluster restatement (oracle/tdvmc_oracle_mix.c) with numpy in/out."""
 
@@ -401,4 +509,6 @@ def make_oracle(spec, time=0.0):
 
     if spec.kind == systems.KIND_MIXTURE:
         return OracleMix(spec, time)
+    if spec.kind == systems.KIND_BOX_RADIAL:
+        return OracleBR(spec, time)
     return Oracle(spec, time) if spec.kind == systems.KIND_SPLINE_TABLE else OracleHe(spec, time)

@@ -262,3 +262,63 @@ def test_he_structure_factor_oracle_matches_reference(golden, name):
     _, sk = oracle_observables(float(g["LBOX"]), src["R"], obs)
     assert np.max(np.abs(sk - g["sk_fixed"])) <= 1e-11 * np.max(np.abs(g["sk_fixed"]))
     assert np.array_equal(g["other_fixed"], src["other_expectation_values"])      # the first block is the ordinary "other" values
+
+
+# ---------------------------------------------------------------------------------------------------
+# NUBosonsBulkPBBoxAndRadial: radial + box spline bases
+# ---------------------------------------------------------------------------------------------------
+BR_CASES = ["boxradial_n27_jittered", "boxradial_n27_equil", "boxradial_n64_equil"]
+
+
+@pytest.mark.parametrize("name", BR_CASES)
+def test_boxradial_fixed_configuration_matches_reference(golden, name):
+    from oracle_lib import OracleBR, br_shell_volumes
+
+    g = golden(name)
+    spec = systems.from_golden(g)     # checks knots (and that the reference's two bases share knots and table)
+    o = OracleBR(spec, time=float(g["time"]))
+    K = spec.extra["n_splines"]
+    assert spec.r_max == float(g["max_distance_rad"]) and spec.extra["half"] == float(g["half_length"])
+    vol, spacing = br_shell_volumes(spec.extra["half"], spec.extra["gr_bins"])
+    assert np.array_equal(vol, g["gr_bin_volumes"]) and spacing == float(g["gr_node_point_spacing"])
+    r = o.evaluate(g["R"], g["uR"], g["uI"], float(g["phiR"]))
+    assert rel(r["ext"][:K], g["spline_sums_rad"]) < 1e-13 and rel(r["ext"][K:], g["spline_sums"]) < 1e-13
+    # the four tables: same operations in the same order as the reference -> bit for bit
+    assert np.array_equal(r["tabD"][:K], g["sD_rad"]) and np.array_equal(r["tabD"][K:], g["sD"])
+    assert np.array_equal(r["tabD2"][:K], g["sD2_rad"]) and np.array_equal(r["tabD2"][K:], g["sD2"])
+    assert rel(r["O"], g["local_operators"]) < 1e-13
+    assert abs(r["exponent"] - float(g["exponent"])) < 1e-13 * abs(float(g["exponent"]))
+    assert abs(r["e_r"] - float(g["local_energy_r"])) < 1e-12 * abs(float(g["local_energy_r"]))
+    assert abs(r["e_i"] - float(g["local_energy_i"])) < 1e-12 * abs(float(g["local_energy_i"]))
+    assert rel(r["other"], g["other_expectation_values"]) < 1e-12
+    assert np.array_equal(r["other"][3:], g["gr_bins"])
+    assert rel(r["drift_r"], g["drift_r"]) < RTOL and rel(r["drift_i"], g["drift_i"]) < RTOL
+    for m, q_ref, en_ref in zip(g["moves"], g["move_quotient"], g["move_exponent_new"]):
+        q, en, _ = o.quotient(g["R"], int(m[0]), m[1:4], g["uR"])
+        assert abs(en - en_ref) < 1e-12 * abs(en_ref)
+        assert abs(q - q_ref) <= 1e-9 * abs(q_ref)
+
+
+def test_boxradial_sampler_statistics_match_reference(golden):
+    """Oracle sampler (Philox proposals) against the reference's own Metropolis run (mt19937_64) at the config's size:
+    energy within 4 combined standard errors (blocked), acceptance within 0.01, <O_k> profile within 2 % of its scale."""
+    from oracle_lib import OracleBR
+
+    g = golden("boxradial_n27_mc")
+    src = golden(str(g["source"]))
+    spec = systems.from_golden(src)
+    o = OracleBR(spec, time=float(src["time"]))
+    n_samples = 3000
+    r = o.sample_walker(src["R"], src["uR"], src["uI"], float(src["phiR"]), seed=21, walker=0, step0=0, n_init=27 * 50,
+                        n_samples=n_samples, n_therm=int(g["MC_NTHERMSTEPS"]), mc_step=float(g["MC_STEP"]))
+
+    def blocked(x, nb=20):
+        b = x[:len(x) // nb * nb].reshape(nb, -1).mean(axis=1)
+        return b.mean(), b.std(ddof=1) / np.sqrt(nb)
+
+    m1, s1 = blocked(r["rows"][:, spec.n_params])
+    m2, s2 = blocked(g["energy_r_series"])
+    assert abs(m1 - m2) < 4.0 * np.hypot(s1, s2), (m1, s1, m2, s2)
+    assert abs(r["accepted"] / r["steps"] - float(g["acceptance"])) < 0.01
+    est = o.unpack_est(r["est"], n_samples)
+    assert np.max(np.abs(est["O"] - g["local_operators"])) / np.abs(g["local_operators"]).max() < 0.02
