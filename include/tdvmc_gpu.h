@@ -46,7 +46,14 @@ enum tdvmc_system_kind
     /* BosonMixtureCluster (BosonMixtureCluster.cpp): open boundary, several species; one basis per pair type (see
      * tdvmc_mixture_desc), 26 parameters per pair type, other[0..5] = {kinR part 1, part 2, kinR, V, wf, exponent};
      * wrap_positions moves the mass-weighted centre of mass to zero */
-    TDVMC_SYSTEM_MIXTURE = 3
+    TDVMC_SYSTEM_MIXTURE = 3,
+    /* NUBosonsBulkPBBoxAndRadial (NUBosonsBulkPBBoxAndRadial.cpp): periodic; a radial spline basis in r_ij inside
+     * maxDistanceRad = knots[K] AND a "box" spline basis in |x_ij|, |y_ij|, |z_ij|, both on the caller's knots / spline
+     * table (SetNodes mirrors the same grid into both, :36-62); n_splines = K = N_PARAM/2 + 3, n_ext = 2K with the sums
+     * ordered [ssRad | ss], map = RefreshLocalOperators (:193-211); Gauss pair potential b exp(-(r/a)^2/2) from
+     * system_params {a, b [, t, a2, b2]}; other[0..2] = {kinetic, potential, wf}, other[3..] = g(r) bins on
+     * (0, lbox/2) weighted by 1/shell volume (n_other = 3 + GR_BIN_COUNT) */
+    TDVMC_SYSTEM_BOX_RADIAL = 4
 };
 
 /* Per-pair-type data of BosonMixtureCluster::InitSystem (BosonMixtureCluster.cpp:104-346), as data. */

@@ -149,6 +149,8 @@ struct tdvmc_gpu_handle
     size_t est_len = 0;
     bool est_valid = false;
     bool est_reduced = false;  // d_est already holds the sum over all ranks
+    DevBuf<double> d_ugR, d_ugI, d_gr_vol; // NUBosonsBulkPBBoxAndRadial: drift-side u~, g(r) shell volumes
+    double gr_spacing = 0;
     DevBuf<double> d_sol, d_solve_L, d_est_fixed; // solve.cu: result, global factor scratch, caller-given estimators
     double* h_sol = nullptr;   // pinned, 2P + 5
     int smem_optin = 48 * 1024;
@@ -396,6 +398,18 @@ int build_static_tables(tdvmc_gpu_handle* h)
     CK(upload(h->d_map_ptr, h->map_ptr, h->stream));
     CK(upload(h->d_map_col, h->map_col, h->stream));
     CK(upload(h->d_map_val, h->map_val, h->stream));
+    if (h->kind == TDVMC_SYSTEM_BOX_RADIAL)
+    {
+        // NUBosonsBulkPBBoxAndRadial::InitSystem :146-169: g(r) over (0, halfLength), bins weighted by 1 / shell volume
+        h->gr_bins = h->n_other - 3;
+        h->gr_max = h->L / 2.0;
+        h->gr_spacing = h->gr_max / (double)h->gr_bins;
+        std::vector<double> vol(h->gr_bins);
+        for (int i = 0; i < h->gr_bins; i++) vol[i] = 4.0 * M_PI * pow(h->gr_spacing * (i + 1), 3.0) / 3.0;
+        for (int i = h->gr_bins - 1; i > 0; i--) vol[i] = vol[i] - vol[i - 1];
+        h->use_phi = 1;
+        CK(upload(h->d_gr_vol, vol, h->stream));
+    }
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -438,6 +452,50 @@ int build_param_tables(tdvmc_gpu_handle* h)
         CK(upload(h->d_utR, utR, h->stream));
         CK(upload(h->d_utI, utI, h->stream));
         CK(upload(h->d_mix_cub, mc, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    if (h->kind == TDVMC_SYSTEM_BOX_RADIAL)
+    {
+        // two plane sets on the same knots: radial (u~[0..K)) then box (u~[K..2K)); record nbins of either is the zero
+        // tail (no radial term beyond maxDistanceRad, :640; a box argument never exceeds knots[K] = L/2)
+        const int nrec = h->nbins + 1;
+        std::vector<double> cub((size_t)2 * nrec * 6, 0.0);
+        for (int set = 0; set < 2; set++)
+        {
+            double* c = cub.data() + (size_t)set * nrec * 6;
+            const double* ut = utR.data() + (size_t)set * K;
+            for (int rec = 0; rec < h->nbins; rec++)
+            {
+                const int b = fb + rec;
+                long double C[4] = { 0, 0, 0, 0 };
+                for (int p = 0; p < 4; p++)
+                    for (int q = 0; q < 4; q++)
+                        C[q] += (long double)ut[b - p] * (long double)h->weights[((size_t)(b - p) * 4 + p) * 4 + q];
+                const long double t0 = h->knots[b];
+                c[(size_t)rec * 2 + 0] = (double)(C[0] + t0 * (C[1] + t0 * (C[2] + t0 * C[3])));
+                c[(size_t)rec * 2 + 1] = (double)(C[1] + t0 * (2 * C[2] + 3 * t0 * C[3]));
+                c[(size_t)(nrec + rec) * 2 + 0] = (double)(C[2] + 3 * t0 * C[3]);
+                c[(size_t)(nrec + rec) * 2 + 1] = (double)C[3];
+                c[(size_t)(2 * nrec + rec) * 2 + 0] = h->knots[b];
+                c[(size_t)(2 * nrec + rec) * 2 + 1] = h->knots[b + 1];
+            }
+            c[(size_t)(2 * nrec + h->nbins) * 2 + 0] = h->knots[K];
+            c[(size_t)(2 * nrec + h->nbins) * 2 + 1] = 1e300;
+        }
+        // the drift's view of the parameters: sD[K-1] (box) stands in for sDRad[K-1] (NUBosonsBulkPBBoxAndRadial.cpp:493-497)
+        std::vector<double> ugR(utR), ugI(utI);
+        ugR[2 * K - 1] += ugR[K - 1];
+        ugI[2 * K - 1] += ugI[K - 1];
+        ugR[K - 1] = 0.0;
+        ugI[K - 1] = 0.0;
+        CK(upload(h->d_uR, h->uR, h->stream));
+        CK(upload(h->d_uI, h->uI, h->stream));
+        CK(upload(h->d_utR, utR, h->stream));
+        CK(upload(h->d_utI, utI, h->stream));
+        CK(upload(h->d_ugR, ugR, h->stream));
+        CK(upload(h->d_ugI, ugI, h->stream));
+        CK(upload(h->d_cub, cub, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         return 0;
     }
@@ -521,7 +579,7 @@ SysDev tdvmc_gpu_handle::sysdev() const
     s.L = L; s.Linv = L > 0.0 ? 1.0 / L : 0.0; s.Lhalf = L / 2.0; // src/TDVMC.cpp:535-536
     s.kind = kind; s.n_ext = n_ext; s.gr_bins = gr_bins;
     s.periodic = periodic; s.n_short = n_short; s.potential = potential; s.rho_bins = rho_bins; s.use_phi = use_phi;
-    s.rmax = kind == TDVMC_SYSTEM_HE_BULK ? L / 2.0 : (kind != TDVMC_SYSTEM_SPLINE_TABLE ? 1e300 : knots[K]); // HeBulk.cpp:54
+    s.rmax = kind == TDVMC_SYSTEM_HE_BULK ? L / 2.0 : ((kind != TDVMC_SYSTEM_SPLINE_TABLE && kind != TDVMC_SYSTEM_BOX_RADIAL) ? 1e300 : knots[K]); // HeBulk.cpp:54
     s.n_types = n_types;
     s.pair_type = d_mix_pair_type.p; s.hbar_n = d_mix_hbar.p; s.mass_n = d_mix_mass.p; s.t_knots = d_mix_knots.p;
     s.t_weights = d_mix_weights.p; s.t_mcm = d_mix_mcm.p; s.t_pot = d_mix_pot.p; s.t_cub = d_mix_cub.p;
@@ -535,7 +593,8 @@ SysDev tdvmc_gpu_handle::sysdev() const
             s.g0R += uR[p] * grad_const[p];
             s.g0I += uI[p] * grad_const[p];
         }
-    if (kind == TDVMC_SYSTEM_SPLINE_TABLE) potential_ab(this, s.pot_a, s.pot_b);
+    if (kind == TDVMC_SYSTEM_SPLINE_TABLE || kind == TDVMC_SYSTEM_BOX_RADIAL) potential_ab(this, s.pot_a, s.pot_b);
+    s.ugR = d_ugR.p; s.ugI = d_ugI.p; s.gr_vol = d_gr_vol.p; s.gr_spacing = gr_spacing;
     s.phiR = phiR;
     s.inv_cell = kind == TDVMC_SYSTEM_HE_DROP ? ncell / (r_tail - he_rs) : ncell / s.rmax;
     s.h = h; s.inv_h = 1.0 / h;
@@ -576,7 +635,11 @@ int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed,
     if (sd->dim != 3 || sd->n_particles < 2 || sd->n_params < 1 || sd->n_splines < 4 || ed->n_walkers < 1 || sd->n_other < 3 ||
         sd->tail_param < -1 || sd->tail_param >= sd->n_params || (!(sd->lbox > 0.0) && sd->system_kind != TDVMC_SYSTEM_HE_DROP && sd->system_kind != TDVMC_SYSTEM_MIXTURE) || sd->n_ext < sd->n_splines ||
         (sd->system_kind != TDVMC_SYSTEM_SPLINE_TABLE && sd->system_kind != TDVMC_SYSTEM_HE_BULK &&
-         sd->system_kind != TDVMC_SYSTEM_HE_DROP && sd->system_kind != TDVMC_SYSTEM_MIXTURE) ||
+         sd->system_kind != TDVMC_SYSTEM_HE_DROP && sd->system_kind != TDVMC_SYSTEM_MIXTURE &&
+         sd->system_kind != TDVMC_SYSTEM_BOX_RADIAL) ||
+        (sd->system_kind == TDVMC_SYSTEM_BOX_RADIAL &&
+         (!sd->knots || !sd->spline_weights || sd->n_ext != 2 * sd->n_splines || (sd->n_params & 1) ||
+          sd->n_splines != sd->n_params / 2 + 3 || sd->n_other < 4 || sd->n_system_params < 2)) ||
         (sd->system_kind == TDVMC_SYSTEM_MIXTURE &&
          (!sd->mixture || sd->mixture->n_pair_types < 1 || sd->n_ext != sd->mixture->n_pair_types * (sd->n_splines + 4) ||
           sd->n_ext > 96 || sd->n_particles > 8 || sd->n_other < 6)) ||
@@ -730,6 +793,22 @@ int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed,
         *out = h;
         return 0;
     }
+    if (h->kind == TDVMC_SYSTEM_BOX_RADIAL)
+    {
+        // one warp per walker, 16 (or as many as fit) walkers per block; the tables are a few KB
+        h->npp = (h->N + 1) & ~1;
+        h->wpb = 16;
+        const SysDev sb = h->sysdev();
+        while (h->wpb > 1 && !sweep_br_fits(sb, h->wpb, h->npp, h->smem_optin)) h->wpb /= 2;
+        if (!sweep_br_fits(sb, h->wpb, h->npp, h->smem_optin))
+        {
+            h->error = "system does not fit the sweep kernel's shared memory";
+            return bail(-3);
+        }
+        h->resident_per_sm = 64;
+        *out = h;
+        return 0;
+    }
     // sweep geometry: as many walkers (warps) per block as keep >= 2 blocks per SM resident
     h->npp = (h->N + 1) & ~1;
     SysDev s = h->sysdev();
@@ -852,7 +931,8 @@ static int do_sweep(tdvmc_gpu_handle* h, long long n_steps, double* pos = nullpt
     a.mc_step = h->mc_step;
     {
         Timed t(h, TDVMC_KERNEL_SWEEP);
-        CK(h->kind == TDVMC_SYSTEM_MIXTURE ? launch_sweep_mix(a, h->stream) : launch_sweep(a, h->stream));
+        CK(h->kind == TDVMC_SYSTEM_MIXTURE ? launch_sweep_mix(a, h->stream)
+                                          : (h->kind == TDVMC_SYSTEM_BOX_RADIAL ? launch_sweep_br(a, h->stream) : launch_sweep(a, h->stream)));
     }
     h->step_counter += (uint64_t)n_steps;
     h->trials_local += (uint64_t)n_steps * (uint64_t)h->W;
@@ -865,6 +945,13 @@ int tdvmc_gpu_sweep(tdvmc_gpu_handle* h, int64_t n_steps)
     if (int rc = need_params(h)) return rc;
     CK(cudaSetDevice(h->device));
     return do_sweep(h, n_steps);
+}
+
+static cudaError_t launch_evaluate_any(int kind, const EvalArgs& a, cudaStream_t st)
+{
+    if (kind == TDVMC_SYSTEM_MIXTURE) return launch_evaluate_mix(a, st);
+    if (kind == TDVMC_SYSTEM_BOX_RADIAL) return launch_evaluate_br(a, st);
+    return kind != TDVMC_SYSTEM_SPLINE_TABLE ? launch_evaluate_he(a, st) : launch_evaluate(a, st);
 }
 
 static int do_evaluate_walkers(tdvmc_gpu_handle* h, const double* pos, int n_cfg, long long row0)
@@ -881,8 +968,7 @@ static int do_evaluate_walkers(tdvmc_gpu_handle* h, const double* pos, int n_cfg
     a.other = h->d_other.p;
     a.exponent = h->d_exponent.p;
     Timed t(h, TDVMC_KERNEL_EVALUATE);
-    CK(h->kind == TDVMC_SYSTEM_MIXTURE ? launch_evaluate_mix(a, h->stream)
-                                          : (h->kind != TDVMC_SYSTEM_SPLINE_TABLE ? launch_evaluate_he(a, h->stream) : launch_evaluate(a, h->stream)));
+    CK(launch_evaluate_any(h->kind, a, h->stream));
     return 0;
 }
 
@@ -1215,8 +1301,7 @@ int tdvmc_gpu_evaluate_fixed(tdvmc_gpu_handle* h, const double* R, int32_t n_cfg
     a.outer_out = out.p;
     {
         Timed t(h, TDVMC_KERNEL_EVALUATE);
-        CK(h->kind == TDVMC_SYSTEM_MIXTURE ? launch_evaluate_mix(a, h->stream)
-                                          : (h->kind != TDVMC_SYSTEM_SPLINE_TABLE ? launch_evaluate_he(a, h->stream) : launch_evaluate(a, h->stream)));
+        CK(launch_evaluate_any(h->kind, a, h->stream));
     }
     std::vector<double> hA((size_t)n_cfg * h->lda);
     CK(cudaMemcpyAsync(hA.data(), A.p, hA.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1260,7 +1345,8 @@ int tdvmc_gpu_quotient_fixed(tdvmc_gpu_handle* h, const double* R, const double*
     a.moves = mv.p;
     a.n_moves = n_moves;
     a.delta = dl.p;
-    CK(h->kind == TDVMC_SYSTEM_MIXTURE ? launch_quotient_mix(a, h->stream) : launch_quotient(a, h->stream));
+    CK(h->kind == TDVMC_SYSTEM_MIXTURE ? launch_quotient_mix(a, h->stream)
+                                      : (h->kind == TDVMC_SYSTEM_BOX_RADIAL ? launch_quotient_br(a, h->stream) : launch_quotient(a, h->stream)));
     std::vector<double> d(n_moves);
     CK(cudaMemcpyAsync(d.data(), dl.p, sizeof(double) * n_moves, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));

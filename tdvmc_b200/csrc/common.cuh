@@ -28,7 +28,7 @@ struct SysDev
     int nbins;        // K - first_bin
     int ncell;        // cells of the uniform bin lookup grid
     int uniform;      // != 0: knots are a uniform grid, interval index = floor(r / h)
-    int kind;         // TDVMC_SYSTEM_*: 0 spline table (BosonsBulk, NUBosonsBulkPB), 1 HeBulk, 2 HeDrop
+    int kind;         // TDVMC_SYSTEM_*: 0 spline table (BosonsBulk, NUBosonsBulkPB), 1 HeBulk, 2 HeDrop, 3 mixture, 4 box + radial
     int periodic;     // 1: minimum image in the box, 0: open boundary (HeDrop)
     int n_short;      // He family: splines on the short grid (HeDrop: 70; HeBulk: all)
     int potential;    // He family: 0 Aziz HFD-B(He) (HeBulk.cpp:187-195), 1 Lennard-Jones sigma=4 eps=3.56 (HeDrop.cpp:389-394)
@@ -76,6 +76,12 @@ struct SysDev
     const double* t_mcm;       // [T] McMillan exponents
     const int* t_pot;          // [T] pair potential ids
     const double* t_cub;       // [T][K-3][6] sweep cubics {c0,c1,c2,c3,t_lo,t_hi} per knot interval
+    // NUBosonsBulkPBBoxAndRadial (kind 4): ext = [ssRad (K) | ss (K)] on one knot vector; cub holds the radial planes
+    // followed by the box planes
+    const double* ugR;         // [n_ext] u~ as the DRIFT uses it: the last radial spline's parameter multiplies the box
+    const double* ugI;         //         table (NUBosonsBulkPBBoxAndRadial.cpp:493-497); the Laplacian uses utR / utI
+    const double* gr_vol;      // [gr_bins] g(r) shell volumes (:149-169)
+    double gr_spacing;         // grNodePointSpacing (:147)
 };
 
 // ---- minimum image -------------------------------------------------------------------------

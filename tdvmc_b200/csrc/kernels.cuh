@@ -68,6 +68,12 @@ cudaError_t launch_sweep_mix(const SweepArgs& a, cudaStream_t st);
 cudaError_t launch_quotient_mix(const QuotientArgs& a, cudaStream_t st);
 cudaError_t launch_com_mix(const SysDev& s, double* pos, int W, cudaStream_t st);
 
+// ---- NUBosonsBulkPBBoxAndRadial: radial + box spline bases (boxradial.cu) ----
+cudaError_t launch_evaluate_br(const EvalArgs& a, cudaStream_t st);
+cudaError_t launch_sweep_br(SweepArgs a, cudaStream_t st);
+cudaError_t launch_quotient_br(const QuotientArgs& a, cudaStream_t st);
+int sweep_br_fits(const SysDev& s, int wpb, int npp, int smem_optin);
+
 // ---- K3 (table form) and K4 (contraction from tables): reference semantics (tables.cu) ----
 struct TableArgs
 {

@@ -33,51 +33,14 @@
 // replicated eight times, copy c in slot c of every 128-byte row, and lane l reads copy l % 8: each
 // quarter-warp covers the eight slots exactly once, whatever the record indices are.
 #include "kernels.cuh"
+#include "sweep_math.cuh"
 
 #include <cstdlib>
 
 namespace tdvmc
 {
 
-constexpr double kMagic = 6755399441055744.0; // 2^52 + 2^51: (x + kMagic) - kMagic rounds x to nearest
 constexpr int kCubCopies = 8;                 // shared-memory replicas of the coefficient planes (one per 16-byte slot)
-
-// x - L * rint(x / L): into [-L/2, L/2]
-__device__ __forceinline__ double wrap_fast(double d, double L, double Linv)
-{
-    double k = fma(d, Linv, kMagic) - kMagic;
-    return fma(-k, L, d);
-}
-
-// squared minimum-image distance of two points that both lie in the first cell (|d| <= L per coordinate):
-// min(|d|, L - |d|) = L/2 - ||d| - L/2|, two FP64 adds with free |.| modifiers and no select
-__device__ __forceinline__ double mi2_wrapped(double dx, double dy, double dz, double Lhalf)
-{
-    const double mx = Lhalf - fabs(fabs(dx) - Lhalf);
-    const double my = Lhalf - fabs(fabs(dy) - Lhalf);
-    const double mz = Lhalf - fabs(fabs(dz) - Lhalf);
-    return fma(mz, mz, fma(my, my, mx * mx));
-}
-
-// squared pair distance: minimum image of wrapped points, or the plain difference for open boundaries
-template <bool OPEN>
-__device__ __forceinline__ double dist2(double dx, double dy, double dz, double Lhalf)
-{
-    if (OPEN) return fma(dz, dz, fma(dy, dy, dx * dx));
-    return mi2_wrapped(dx, dy, dz, Lhalf);
-}
-
-// sqrt(x) to ~2 ulp: MUFU.RSQ64H seed (22 bits) + one third-order step; x == 0 gives NaN, which the
-// callers discard (it only happens for the moved particle against itself)
-__device__ __forceinline__ double sqrt_fast(double x)
-{
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double t = x * y;               // ~ sqrt(x)
-    const double e = fma(-t, y, 1.0);     // 1 - x y^2
-    const double p = fma(e, 0.375, 0.5);
-    return fma(t * e, p, t);              // t (1 + e/2 + 3 e^2/8)
-}
 
 // sum over the GROUP lanes of a walker (all lanes of the warp take part)
 template <int GROUP>

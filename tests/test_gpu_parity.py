@@ -1193,3 +1193,118 @@ def test_device_euler_step_at_headline_size(capi, golden):
     assert e_new["e_r"][0] != float(g["local_energy_r"])          # the parameters did move
     h.close()
     h2.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# NUBosonsBulkPBBoxAndRadial (radial + box spline bases) through the same C ABI
+# ---------------------------------------------------------------------------------------------------
+BR_CASES = ["boxradial_n27_jittered", "boxradial_n27_equil", "boxradial_n64_equil"]
+
+
+@pytest.mark.parametrize("name", BR_CASES)
+def test_boxradial_fixed_configuration(capi, golden, name):
+    """Local energy, drift, O_k, basis sums, g(r) bins and the scripted-move quotient against the reference's own
+    evaluation (config/NUBosonsBulkPBBoxAndRadial3D.config at its own size, and a 64-particle non-uniform-grid case)."""
+    from oracle_lib import OracleBR
+
+    g = golden(name)
+    spec, h = make_handle(capi, g)
+    K = spec.extra["n_splines"]
+    r = h.evaluate_fixed(g["R"][None])
+    assert abs(r["e_r"][0] - float(g["local_energy_r"])) < RTOL * abs(float(g["local_energy_r"]))
+    assert abs(r["e_i"][0] - float(g["local_energy_i"])) < RTOL * abs(float(g["local_energy_i"]))
+    assert rel(r["O"][0], g["local_operators"]) < RTOL
+    assert abs(r["exponent"][0] - float(g["exponent"])) < RTOL * abs(float(g["exponent"]))
+    assert rel(r["ss"][0][:K], g["spline_sums_rad"]) < 1e-12 and rel(r["ss"][0][K:], g["spline_sums"]) < 1e-12
+    assert rel(r["other"][0][:3], g["other_expectation_values"][:3]) < RTOL
+    assert rel(r["other"][0][3:], g["gr_bins"]) < 1e-13 and g["gr_bins"].sum() > 0
+    scale = max(np.abs(g["drift_r"]).max(), np.abs(g["drift_i"]).max())
+    assert np.abs(r["drift_r"][0] - g["drift_r"]).max() < RTOL * scale
+    assert np.abs(r["drift_i"][0] - g["drift_i"]).max() < RTOL * scale
+    # the drift really carries the reference's box-for-radial substitution (NUBosonsBulkPBBoxAndRadial.cpp:493-497):
+    # contracting the reference's own tables the "corrected" way moves it by far more than the tolerance
+    PR = spec.n_params // 2
+    fixed = g["drift_r"] + g["uR"][PR - 1] * (g["sD_rad"][K - 1] - g["sD"][K - 1])
+    assert np.abs(fixed - g["drift_r"]).max() > 1e3 * RTOL * scale
+    q, d = h.quotient_fixed(g["R"], g["moves"])
+    assert rel(q, g["move_quotient"]) < 1e-9
+    o = OracleBR(spec, time=float(g["time"]))
+    for m, dd in zip(g["moves"], d):
+        _, en, ex = o.quotient(g["R"], int(m[0]), m[1:4], g["uR"])
+        assert abs(dd - (en - ex)) < 1e-10 * max(abs(en), 1.0)
+    h.close()
+
+
+@pytest.mark.parametrize("name,n_steps", [("boxradial_n27_equil", 27 * 40), ("boxradial_n64_equil", 64 * 10)])
+def test_boxradial_sweep_replays_oracle_chain(capi, golden, name, n_steps):
+    from oracle_lib import OracleBR
+
+    g = golden(name)
+    W, seed, mc_step, first = 3, 31, 0.35, 7
+    spec, h = make_handle(capi, g, n_walkers=W, seed=seed, mc_step=mc_step, first_walker=first)
+    o = OracleBR(spec, time=float(g["time"]))
+    R0 = np.stack([g["R"] + 0.003 * w for w in range(W)])
+    h.set_positions(R0)
+    h.sweep(n_steps // 3)
+    h.sweep(n_steps - n_steps // 3)
+    R_gpu = h.get_positions()
+    for w in range(W):
+        R_ref, acc = o.sweep(R0[w], g["uR"], seed, first + w, 0, n_steps, mc_step)
+        d = R_gpu[w] - R_ref
+        d -= spec.lbox * np.round(d / spec.lbox)
+        assert np.max(np.abs(d)) < 1e-9, w
+        assert 0.2 * n_steps < acc < n_steps
+    h.close()
+
+
+def test_boxradial_estimators_match_oracle(capi, golden):
+    """A whole UpdateExpectationValues pass (sweeps, evaluations, S / F accumulation, g(r) bins, counters) against the
+    oracle driven by the same proposal stream."""
+    from oracle_lib import OracleBR
+
+    g = golden("boxradial_n27_equil")
+    W, seed, mc_step = 6, 17, 0.5
+    n_samples, n_therm, n_init = 3, 27, 54
+    spec, h = make_handle(capi, g, n_walkers=W, seed=seed, mc_step=mc_step, max_samples=n_samples)
+    o = OracleBR(spec, time=float(g["time"]))
+    R0 = np.stack([g["R"] + 0.002 * w for w in range(W)])
+    h.set_positions(R0)
+    h.sample_and_accumulate(n_samples, n_therm, n_init)
+    got = h.allreduce_and_fetch()
+    est = np.zeros(o.est_size())
+    acc = 0
+    for w in range(W):
+        acc += o.sample_walker(R0[w], g["uR"], g["uI"], float(g["phiR"]), seed, w, 0, n_init, n_samples, n_therm, mc_step, est)["accepted"]
+    want = o.unpack_est(est, W * n_samples)
+    assert got["n_samples"] == W * n_samples and got["n_trials"] == W * (n_init + n_samples * n_therm)
+    assert got["n_acceptances"] == acc
+    for k in ("O", "S", "OER", "OEI"):
+        assert rel(got[k], want[k]) < 1e-9, k
+    assert abs(got["e_r"][0] - want["e_r"]) < 1e-9 * abs(want["e_r"])
+    assert abs(got["e_i"][0] - want["e_i"]) < 1e-9 * abs(want["e_i"])
+    assert rel(got["other"][:2], want["other"][:2]) < 1e-9 and rel(got["other"][3:], want["other"][3:]) < 1e-12
+    # the solve of section 8(f) rank 3 runs on this system's estimators as well (P = 100)
+    d = h.solve_parameters_dot(imaginary_time=1, min_scaling=1e-12)
+    assert np.all(np.isfinite(d["u_dot_r"])) and d["e_r"] == got["e_r"][0]
+    h.close()
+
+
+def test_boxradial_statistics_match_reference_sampler(capi, golden):
+    """Ensemble energy, acceptance and <O_k> against the reference's own Metropolis run of this system (mt19937_64
+    stream, 4000 samples): within 4 combined standard errors / 0.01 / 2 % of the profile's scale."""
+    g = golden("boxradial_n27_mc")
+    src = golden(str(g["source"]))
+    W = 1024
+    spec, h = make_handle(capi, src, n_walkers=W, seed=99, mc_step=float(g["MC_STEP"]), max_samples=4)
+    h.set_positions(np.broadcast_to(src["R"], (W, 27, 3)).copy())
+    h.sample_and_accumulate(4, 27 * 4, 27 * 100)
+    got = h.allreduce_and_fetch()
+    er = g["energy_r_series"]
+    nb = 20
+    b = er[:len(er) // nb * nb].reshape(nb, -1).mean(axis=1)
+    m_ref, s_ref = b.mean(), b.std(ddof=1) / np.sqrt(nb)
+    s_gpu = np.std(er) / np.sqrt(W)            # W independent walkers: at least W independent samples
+    assert abs(got["e_r"][0] - m_ref) < 4.0 * np.hypot(s_ref, s_gpu), (got["e_r"][0], m_ref, s_ref, s_gpu)
+    assert abs(got["n_acceptances"] / got["n_trials"] - float(g["acceptance"])) < 0.01
+    assert np.max(np.abs(got["O"] - g["local_operators"])) / np.abs(g["local_operators"]).max() < 0.02
+    h.close()
