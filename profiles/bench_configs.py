@@ -30,6 +30,8 @@ CONFIGS = {
     2: ("config/bulk_64.config", "hebulk_n64_equil", "HeBulk", 0.3, 100, 100, (1 << 20) // 64),
     4: ("config/NUBosonsBulkPB3D.config", "nubosonsbulkpb_n1728_equil", "NUBosonsBulkPB", 0.5, 200, 400, 512),
     5: ("config/He4He4Na.config", "mixture_he4he4na_equil", "BosonMixtureCluster", 4.0, 20, 1000, (1 << 20) // 3),
+    # SURVEY 8(f) rank 4 (not a BASELINE config): the radial + box spline system at its shipped size
+    6: ("config/NUBosonsBulkPBBoxAndRadial3D.config", "boxradial_n27_equil", "NUBosonsBulkPBBoxAndRadial", 0.5, 125, 250, (1 << 20) // 27),
 }
 SAMPLES = 8
 
@@ -46,7 +48,8 @@ def reference_one_core(g, system, mc_step, n_therm, n_init, n_samples):
             arrays[key] = g[key]
     if "NURBS_GRID" in arrays:
         scal["USE_NURBS"] = 1
-        scal["GR_BIN_COUNT"] = 400 if system == "BosonMixtureCluster" else len(g["other_expectation_values"]) - 9
+        scal["GR_BIN_COUNT"] = 400 if system == "BosonMixtureCluster" else len(g["other_expectation_values"]) - (
+            3 if system == "NUBosonsBulkPBBoxAndRadial" else 9)
     with tempfile.TemporaryDirectory() as td:
         case = os.path.join(td, "case.txt")
         with open(case, "w") as f:

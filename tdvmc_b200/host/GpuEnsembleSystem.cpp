@@ -84,6 +84,41 @@ SystemTables MakeNUBosonsBulkPBTables(int N, double LBOX, int N_PARAM, const std
     return t;
 }
 
+SystemTables MakeNUBosonsBulkPBBoxAndRadialTables(int N, double LBOX, int N_PARAM, const std::vector<double>& nodes,
+                                                  const std::vector<std::vector<std::vector<double> > >& splineWeights,
+                                                  const std::vector<double>& SYSTEM_PARAMS, int grBinCount)
+{
+    SystemTables t;
+    t.system_kind = TDVMC_SYSTEM_BOX_RADIAL;
+    t.n_particles = N;
+    t.n_params = N_PARAM;
+    t.lbox = LBOX;
+    t.tail_param = -1;
+    t.n_other = 3 + (grBinCount == 0 ? 400 : grBinCount); // NUBosonsBulkPBBoxAndRadial.cpp:72-78
+    t.knots = nodes;
+    t.spline_weights = FlattenWeights(splineWeights);
+    t.system_params = SYSTEM_PARAMS;
+    const int K = (int)nodes.size() - 4, PR = N_PARAM / 2;
+    if (N_PARAM % 2 || K != PR + 3)
+        throw std::runtime_error("NUBosonsBulkPBBoxAndRadial: numberOfSplines must equal N_PARAM / 2 + 3 (NUBosonsBulkPBBoxAndRadial.cpp:84-89)");
+    t.n_ext = 2 * K; // [splineSumsRad | splineSums]
+    // RefreshLocalOperators (:193-211)
+    t.map_ptr.push_back(0);
+    for (int i = 0; i < PR; i++)
+    {
+        if (i == 1) PushRow(t, { { 2, 1.0 }, { 0, 1.0 } });
+        else if (i == PR - 1) PushRow(t, { { PR, 1.0 }, { K - 2, 1.0 / (-2.0) }, { K - 1, 1.0 } });
+        else PushRow(t, { { i + 1, 1.0 } });
+    }
+    for (int i = 0; i < PR; i++)
+    {
+        if (i == 1) PushRow(t, { { K + 2, 1.0 }, { K, 1.0 } });
+        else if (i == PR - 1) PushRow(t, { { K + PR, 1.0 }, { K + K - 2, 1.0 }, { K + K - 1, 1.0 } });
+        else PushRow(t, { { K + i + 1, 1.0 } });
+    }
+    return t;
+}
+
 SystemTables MakeHeBulkTables(int N, double LBOX, int N_PARAM)
 {
     SystemTables t;

@@ -60,6 +60,11 @@ SystemTables MakeBosonsBulkTables(int N, double LBOX, int N_PARAM, const std::ve
 SystemTables MakeNUBosonsBulkPBTables(int N, double LBOX, int N_PARAM, const std::vector<double>& nodes,
                                       const std::vector<std::vector<std::vector<double> > >& splineWeights,
                                       const std::vector<double>& SYSTEM_PARAMS, int grBinCount);
+// NUBosonsBulkPBBoxAndRadial (NUBosonsBulkPBBoxAndRadial.cpp:64-191, 193-211): nodes == nodesRad and
+// splineWeights == splineWeightsRad after SetNodes (:36-62), so one knot vector and one table are passed.
+SystemTables MakeNUBosonsBulkPBBoxAndRadialTables(int N, double LBOX, int N_PARAM, const std::vector<double>& nodes,
+                                                  const std::vector<std::vector<std::vector<double> > >& splineWeights,
+                                                  const std::vector<double>& SYSTEM_PARAMS, int grBinCount);
 
 // HeBulk (HeBulk.cpp:40-70, 376-383): everything follows from N, LBOX and N_PARAM.
 SystemTables MakeHeBulkTables(int N, double LBOX, int N_PARAM);

@@ -3,7 +3,7 @@
 // table are read from a text file (the reference driver would pass its own SplineFactory output).
 //
 //   example_driver <tables.txt>      tables.txt: N LBOX N_PARAM n_knots, knots..., K*16 weights...
-//   example_driver --map hebulk N LBOX N_PARAM | --map hedrop N N_PARAM
+//   example_driver --map hebulk N LBOX N_PARAM | --map hedrop N N_PARAM | --map boxradial N LBOX N_PARAM
 //                                    prints the parameter map the adapter builds (no GPU needed)
 //
 // Exit code 0, one line "E_R=... acceptance=..." and one line "EULER ..." (parameters after one device-solved Euler step) on success; without a CUDA device the library
@@ -30,8 +30,28 @@ int main(int argc, char** argv)
     if (!std::strcmp(argv[1], "--map") && argc >= 5)
     {
         const bool bulk = !std::strcmp(argv[2], "hebulk");
-        SystemTables t = bulk ? MakeHeBulkTables(std::atoi(argv[3]), std::atof(argv[4]), std::atoi(argv[5]))
-                              : MakeHeDropTables(std::atoi(argv[3]), std::atoi(argv[4]));
+        SystemTables t;
+        if (!std::strcmp(argv[2], "boxradial") && argc >= 6)
+        {
+            // uniform grid of N_PARAM/2 + 1 points on [0, LBOX/2], mirrored by three knots on either side (SetNodes,
+            // NUBosonsBulkPBBoxAndRadial.cpp:36-62); the table itself does not enter the map
+            const int P = std::atoi(argv[5]), n = P / 2 + 1;
+            const double L = std::atof(argv[4]);
+            std::vector<double> grid(n), nodes;
+            for (int i = 0; i < n; i++) grid[i] = (L / 2) * i / (n - 1);
+            nodes = grid;
+            for (int i = 0; i < 3; i++)
+            {
+                nodes.insert(nodes.begin(), -grid[i + 1]);
+                nodes.push_back(2.0 * grid[n - 1] - grid[n - 2 - i]);
+            }
+            const int K = (int)nodes.size() - 4;
+            std::vector<std::vector<std::vector<double> > > w(K, std::vector<std::vector<double> >(4, std::vector<double>(4, 0.0)));
+            t = MakeNUBosonsBulkPBBoxAndRadialTables(std::atoi(argv[3]), L, P, nodes, w, { 0.1, 50.0 }, 400);
+        }
+        else
+            t = bulk ? MakeHeBulkTables(std::atoi(argv[3]), std::atof(argv[4]), std::atoi(argv[5]))
+                     : MakeHeDropTables(std::atoi(argv[3]), std::atoi(argv[4]));
         std::printf("%d %d %d %d %d\n", t.system_kind, t.n_params, t.n_ext, t.n_other, (int)t.knots.size() - 4);
         for (int p : t.map_ptr) std::printf("%d ", p);
         std::printf("\n");

@@ -200,14 +200,17 @@ def test_cpp_host_adapter_builds_and_refuses_without_gpu(tmp_path, golden):
 
 
 def test_cpp_he_table_builders_match_python_specs():
-    """MakeHeBulkTables / MakeHeDropTables (C++ adapter) build the same CSR parameter map, bit for bit, as
-    tdvmc_b200.systems.he_bulk / he_drop (which the golden fixtures pin against the reference)."""
+    """MakeHeBulkTables / MakeHeDropTables / MakeNUBosonsBulkPBBoxAndRadialTables (C++ adapter) build the same CSR parameter
+    map, bit for bit, as tdvmc_b200.systems.he_bulk / he_drop / nu_bosons_bulk_pb_box_and_radial (which the golden fixtures
+    pin against the reference)."""
     from tdvmc_b200 import systems as tsys
     host = os.path.join(ROOT, "tdvmc_b200", "host")
     subprocess.check_call(["make", "-C", host, "example_driver"])
     exe = os.path.join(host, "example_driver")
+    br = tsys.nu_bosons_bulk_pb_box_and_radial(27, 3.0, 100, np.linspace(0.0, 1.5, 51), weights=np.zeros((53, 4, 4)))
     for args, spec in ((["hebulk", "64", "14.5", "40"], tsys.he_bulk(64, 14.5, 40)),
-                       (["hedrop", "6", "150"], tsys.he_drop(6, 150))):
+                       (["hedrop", "6", "150"], tsys.he_drop(6, 150)),
+                       (["boxradial", "27", "3.0", "100"], br)):
         out = subprocess.run([exe, "--map"] + args, capture_output=True, text=True, check=True).stdout.splitlines()
         kind, P, n_ext, n_other, K = (int(x) for x in out[0].split())
         assert (kind, P, n_ext, n_other) == (spec.kind, spec.n_params, spec.n_ext, spec.n_other)
