@@ -558,6 +558,12 @@ go = np.load(os.path.join(root, "tests", "golden", "bosonsbulk_n64_obs.npz"))
 o = ens.ParallelCalculateAdditionalSystemProperties(g["uR"], g["uI"], float(g["phiR"]), float(g["phiI"]),
                                                     observables.from_golden(go), 3, 40, 20, float(g["time"]))
 e["pairDistribution"], e["structureFactor"] = o["pairDistribution"], o["structureFactor"]
+# a second pass whose estimators are NOT fetched: the Euler step all-reduces them itself and solves on every rank;
+# the fetch that follows must see the same (once-reduced) sums
+ens.SampleExpectationValues(g["uR"], g["uI"], float(g["phiR"]), float(g["phiI"]), 2, 64, 0, float(g["time"]))
+u2, _, p2, _, info = ens.CalculateNextParametersEuler(1e-4, g["uR"], g["uI"], float(g["phiR"]), float(g["phiI"]), IMAGINARY_TIME=1)
+e2 = ens._fetch()
+e["euler_uR"], e["euler_phiR"], e["euler_e_r"], e["second_e_r"], e["second_n"] = u2, p2, info["e_r"], e2["localEnergyR"], e2["nSamples"]
 np.savez(os.path.join(tmp, f"rank{rank}.npz"), **{k: np.asarray(v) for k, v in e.items()})
 ens.close()
 """
@@ -583,9 +589,20 @@ def test_two_gpu_allreduce_matches_single_gpu(capi, golden, tmp_path):
     one = h.allreduce_and_fetch()
     from tdvmc_b200 import observables
     gr1, sk1 = h.sample_observables(observables.from_golden(golden("bosonsbulk_n64_obs")), 3, 40, 20)
+    h.sample_and_accumulate(2, 64, 0)
+    u1, _, p1, _, info1 = h.euler_step(1e-4, g["uR"], g["uI"], float(g["phiR"]), float(g["phiI"]), imaginary_time=1)
     h.close()
+    ranks = [np.load(tmp_path / f"rank{r}.npz") for r in range(2)]
+    assert np.array_equal(ranks[0]["euler_uR"], ranks[1]["euler_uR"])          # every rank solved the same system
     for r in range(2):
-        two = np.load(tmp_path / f"rank{r}.npz")
+        two = ranks[r]
+        # device solve after the in-library all-reduce: same derivatives as one GPU holding all walkers (the sums
+        # differ by the all-reduce's rounding), and the later fetch saw the once-reduced estimators
+        du2, du1 = (two["euler_uR"] - g["uR"]) / 1e-4, (u1 - g["uR"]) / 1e-4
+        assert np.max(np.abs(du2 - du1)) < 1e-8 * np.max(np.abs(du1))
+        assert abs(float(two["euler_phiR"]) - p1) < 1e-9 * abs(p1)
+        assert float(two["euler_e_r"]) == float(two["second_e_r"]) and int(two["second_n"]) == 20
+        assert abs(float(two["second_e_r"]) - info1["e_r"]) < 1e-13 * abs(info1["e_r"])
         assert rel(two["pairDistribution"], gr1) < 1e-13 and rel(two["structureFactor"], sk1) < 1e-12
         assert int(two["nSamples"]) == 20 and int(two["nTrials"]) == one["n_trials"]
         assert int(two["nAcceptances"]) == one["n_acceptances"]
