@@ -60,12 +60,15 @@ enum tdvmc_system_kind
 typedef struct tdvmc_mixture_desc
 {
     int32_t n_pair_types;          /* T = corrFuncData.size() */
-    int32_t reserved;
+    int32_t spline_order;          /* 3 (or 0): BosonMixtureCluster, cubic; 4: BosonMixtureCluster_4thorder (quartic splines,
+                                    * SplineFactory::GetWeights4, rijSplit = nodes[4], rijTail = nodes[size - 5];
+                                    * BosonMixtureCluster_4thorder.cpp:138-153).  For order 4 pass K = numberOfSplines = 28:
+                                    * the 27 splines of the table plus a zero spline, and one padding knot after the 32 nodes */
     const int32_t* pair_type;      /* [N][N] correlationTypes (:58-102) */
     const double* hbar_over_2m;    /* [N] pp.hbarOver2m of each particle's species (:108-135) */
     const double* mass;            /* [N] pp.mass */
-    const double* knots;           /* [T][K+4] cfd.nodes */
-    const double* spline_weights;  /* [T][K][4][4] cfd.splineWeights (SplineFactory::GetWeights3) */
+    const double* knots;           /* [T][K+order+1] cfd.nodes */
+    const double* spline_weights;  /* [T][K][order+1][order+1] cfd.splineWeights (SplineFactory::GetWeights3 / GetWeights4) */
     const double* mcmillan_factor; /* [T] cfd.mcMillanFactor */
     const int32_t* potential;      /* [T] 0 HFDB_He_He, 1 KTTY_He_Na, 2 KTTY_He_Cs (:233-282, src/Potentials) */
 } tdvmc_mixture_desc;

@@ -592,13 +592,14 @@ def gen_hedrop():
     # the chain is not stationary; sampling is pinned by replaying the oracle chain move for move instead
 
 
-def pack_eval_mixture(name, scal, arrays, moves):
+def pack_eval_mixture(name, scal, arrays, moves, order=3):
+    system = "BosonMixtureCluster" if order == 3 else "BosonMixtureCluster_4thorder"
     with tempfile.TemporaryDirectory() as td:
         cp, op = os.path.join(td, "case.txt"), os.path.join(td, "out.txt")
-        write_case(cp, "BosonMixtureCluster", scal, arrays, moves)
+        write_case(cp, system, scal, arrays, moves)
         run("eval", cp, op)
         d = parse_dump(op)
-    out = {"system": np.array("BosonMixtureCluster"), "N": np.array(scal["N"]), "DIM": np.array(3), "LBOX": np.array(scal["LBOX"]),
+    out = {"system": np.array(system), "N": np.array(scal["N"]), "DIM": np.array(3), "LBOX": np.array(scal["LBOX"]),
            "N_PARAM": np.array(scal["N_PARAM"]), "SYSTEM_PARAMS": np.zeros(0), "time": np.array(0.0),
            "PARTICLE_TYPES": np.asarray(arrays["PARTICLE_TYPES"], np.float64), "NURBS_GRID": np.asarray(arrays["NURBS_GRID"]),
            "R": np.asarray(arrays["R"], np.float64).reshape(-1, 3), "uR": np.asarray(arrays["uR"], np.float64),
@@ -608,9 +609,9 @@ def pack_eval_mixture(name, scal, arrays, moves):
         out[k] = v
     T = int(d["n_pair_types"])
     spec = tsys.boson_mixture_cluster(arrays["PARTICLE_TYPES"], [d[f"knots_{t}"] for t in range(T)],
-                                      [d[f"spline_weights_{t}"] for t in range(T)], [d[f"bc_factors_{t}"] for t in range(T)])
+                                      [d[f"spline_weights_{t}"] for t in range(T)], [d[f"bc_factors_{t}"] for t in range(T)],
+                                      order=order)
     N = int(scal["N"])
-    K = 26
     tabs = []
     for t in range(T):
         z = np.zeros((1, N, 3), np.longdouble)
@@ -652,6 +653,33 @@ def gen_mixture():
     mc = run_mc("BosonMixtureCluster", dict(scal, MC_STEP=float(cfg["MC_STEP"]), MC_NSTEPS=1, MC_NTHERMSTEPS=3 * 3000, seed=2), arr)
     R4 = mc["R_final"].reshape(N, 3)
     pack_eval_mixture("mixture_he4he4na_equil", scal, dict(arr, R=R4), default_moves(R4, 0.0, rng, sigma=2.0))
+
+
+def gen_mixture_4th():
+    """config/He4He4Na_4thOrder.config (BosonMixtureCluster_4thorder): the same He4-He4-Na trimer on quartic splines
+    (SplineFactory::GetWeights4, 28 splines and three boundary factors per pair type), the config's own grid.  Its shipped
+    PARAMS_REAL is a placeholder, so the cubic config's optimised parameters are used (same 2 x 26 layout)."""
+    rng = np.random.default_rng(34)
+    cfg = json.load(open(os.path.join(REF, "config", "He4He4Na_4thOrder.config")))
+    cfg3 = json.load(open(os.path.join(REF, "config", "He4He4Na.config")))
+    N, P = int(cfg["N"]), int(cfg["N_PARAM"])
+    uR = np.array(cfg["PARAMS_REAL"], dtype=np.float64)
+    if len(uR) != P or not np.any(uR):
+        uR = np.array(cfg3["PARAMS_REAL"], dtype=np.float64)
+    uI = 0.01 * np.sin(0.4 * np.arange(P))
+    R = read_csv_positions("particleconfiguration_3.csv").reshape(N, 3)
+    scal = dict(N=N, LBOX=float(cfg["LBOX"]), N_PARAM=P, phiR=float(cfg.get("PARAM_PHIR", 0.0)), phiI=0.0, USE_NURBS=1,
+                GR_BIN_COUNT=int(cfg["GR_BIN_COUNT"]))
+    arr = dict(R=R, uR=uR, uI=uI, NURBS_GRID=cfg["NURBS_GRID"], PARTICLE_TYPES=cfg["PARTICLE_TYPES"],
+               SYSTEM_PARAMS=cfg["SYSTEM_PARAMS"])
+    pack_eval_mixture("mixture4_he4he4na_fixture", scal, arr, default_moves(R, 0.0, rng, sigma=1.0), order=4)
+    R2 = np.array([[0.0, 0.0, 0.0], [1.7, 0.3, -0.2], [3.1, 2.0, 0.5]])          # inside the McMillan cores
+    pack_eval_mixture("mixture4_he4he4na_compact", scal, dict(arr, R=R2), default_moves(R2, 0.0, rng, sigma=1.0), order=4)
+    R3 = np.array([[0.0, 0.0, 0.0], [22.5, 1.0, -2.0], [-9.0, 24.0, 4.0]])       # out on the tails
+    pack_eval_mixture("mixture4_he4he4na_stretched", scal, dict(arr, R=R3), default_moves(R3, 0.0, rng, sigma=4.0), order=4)
+    mc = run_mc("BosonMixtureCluster_4thorder", dict(scal, MC_STEP=float(cfg["MC_STEP"]), MC_NSTEPS=1, MC_NTHERMSTEPS=3 * 3000, seed=2), arr)
+    R4 = mc["R_final"].reshape(N, 3)
+    pack_eval_mixture("mixture4_he4he4na_equil", scal, dict(arr, R=R4), default_moves(R4, 0.0, rng, sigma=2.0), order=4)
 
 
 def gen_min_image():
@@ -783,7 +811,7 @@ def main():
     if not os.path.exists(HARNESS):
         sys.exit("build the oracle first: make -C oracle/ref_build")
     which = sys.argv[1:] or ["min_image", "bosonsbulk", "bosonsbulk_mc", "bosonsbulk_mc_headline", "nubosonsbulkpb", "nubosonsbulkpb_full", "hebulk", "hedrop",
-                             "mixture", "observables", "he_observables", "mixture_observables", "evolution", "boxradial"]
+                             "mixture", "observables", "he_observables", "mixture_observables", "evolution", "boxradial", "mixture_4th"]
     for w in which:
         globals()["gen_" + w]()
 

@@ -223,6 +223,44 @@ void DumpSplineInternals(Dump& d, S* s)
     d.vec("other_local_operators", s->otherLocalOperators);
 }
 
+// BosonMixtureCluster and BosonMixtureCluster_4thorder share their member names (per-pair-type CorrelationFunctionData)
+template <class S>
+void DumpMixtureInternals(Dump& d, S* s)
+{
+        std::vector<double> pt, ct, mass, hb;
+        for (int t : s->particleTypes) pt.push_back(t);
+        for (auto& row : s->correlationTypes)
+            for (int t : row) ct.push_back(t);
+        for (auto& pp : s->particleProperties)
+        {
+            mass.push_back(pp.mass);
+            hb.push_back(pp.hbarOver2m);
+        }
+        d.vec("particle_types", pt);
+        d.vec("correlation_types", ct);
+        d.vec("type_mass", mass);
+        d.vec("type_hbar_over_2m", hb);
+        d.scalar("n_pair_types", (double)s->corrFuncData.size());
+        for (size_t c = 0; c < s->corrFuncData.size(); c++)
+        {
+            auto& f = s->corrFuncData[c];
+            std::string q = "_" + std::to_string(c);
+            d.vec("knots" + q, f.nodes);
+            d.ten("spline_weights" + q, f.splineWeights);
+            d.mat("bc_factors" + q, f.bcFactors);
+            d.vec("spline_sums" + q, f.splineSums);
+            d.vec("extras" + q, { f.mcMillanSum, f.constSum, f.linearSum, f.logSum, f.rijSplit, f.rijTail, f.mcMillanFactor });
+            d.ten("sD" + q, f.splineSumsD);
+            d.mat("sD2" + q, f.splineSumsD2);
+            d.mat("mcmillan_sum_d" + q, f.mcMillanSumD);
+            d.vec("mcmillan_sum_d2" + q, f.mcMillanSumD2);
+            d.mat("linear_sum_d" + q, f.linearSumD);
+            d.vec("linear_sum_d2" + q, f.linearSumD2);
+            d.mat("log_sum_d" + q, f.logSumD);
+            d.vec("log_sum_d2" + q, f.logSumD2);
+        }
+    }
+
 void DumpSystemInternals(Dump& d)
 {
     if (auto s = dynamic_cast<PhysicalSystems::BosonsBulk*>(sys))
@@ -257,38 +295,11 @@ void DumpSystemInternals(Dump& d)
     }
     else if (auto s = dynamic_cast<PhysicalSystems::BosonMixtureCluster*>(sys))
     {
-        std::vector<double> pt, ct, mass, hb;
-        for (int t : s->particleTypes) pt.push_back(t);
-        for (auto& row : s->correlationTypes)
-            for (int t : row) ct.push_back(t);
-        for (auto& pp : s->particleProperties)
-        {
-            mass.push_back(pp.mass);
-            hb.push_back(pp.hbarOver2m);
-        }
-        d.vec("particle_types", pt);
-        d.vec("correlation_types", ct);
-        d.vec("type_mass", mass);
-        d.vec("type_hbar_over_2m", hb);
-        d.scalar("n_pair_types", (double)s->corrFuncData.size());
-        for (size_t c = 0; c < s->corrFuncData.size(); c++)
-        {
-            auto& f = s->corrFuncData[c];
-            std::string q = "_" + std::to_string(c);
-            d.vec("knots" + q, f.nodes);
-            d.ten("spline_weights" + q, f.splineWeights);
-            d.mat("bc_factors" + q, f.bcFactors);
-            d.vec("spline_sums" + q, f.splineSums);
-            d.vec("extras" + q, { f.mcMillanSum, f.constSum, f.linearSum, f.logSum, f.rijSplit, f.rijTail, f.mcMillanFactor });
-            d.ten("sD" + q, f.splineSumsD);
-            d.mat("sD2" + q, f.splineSumsD2);
-            d.mat("mcmillan_sum_d" + q, f.mcMillanSumD);
-            d.vec("mcmillan_sum_d2" + q, f.mcMillanSumD2);
-            d.mat("linear_sum_d" + q, f.linearSumD);
-            d.vec("linear_sum_d2" + q, f.linearSumD2);
-            d.mat("log_sum_d" + q, f.logSumD);
-            d.vec("log_sum_d2" + q, f.logSumD2);
-        }
+        DumpMixtureInternals(d, s);
+    }
+    else if (auto s = dynamic_cast<PhysicalSystems::BosonMixtureCluster_4thorder*>(sys))
+    {
+        DumpMixtureInternals(d, s);
     }
     else if (auto s = dynamic_cast<PhysicalSystems::HeDrop*>(sys))
     {

@@ -211,12 +211,12 @@ enum { ORACLE_POT_HFDB_HE_HE = 0, ORACLE_POT_KTTY_HE_NA = 1, ORACLE_POT_KTTY_HE_
 typedef struct oracle_mix
 {
     int32_t n_particles, n_params, n_types, n_splines; /* n_splines per pair type (26) */
-    int32_t n_other, pad;
+    int32_t n_other, order;     /* spline order: 3 (0 also means 3) or 4 (BosonMixtureCluster_4thorder) */
     const int32_t* pair_type;   /* [N][N] correlationTypes */
     const double* hbar;         /* [N] hbarOver2m of each particle's species (BosonMixtureCluster.cpp:113-134) */
     const double* mass;         /* [N] */
-    const double* knots;        /* [T][K+4] */
-    const double* weights;      /* [T][K][4][4] */
+    const double* knots;        /* [T][K+order+1] */
+    const double* weights;      /* [T][K][order+1][order+1] */
     const double* mcm;          /* [T] mcMillanFactor */
     const int32_t* potential;   /* [T] ORACLE_POT_* */
     const int32_t* map_ptr;     /* [P+1] rows over the T*(K+4) extended sums (BosonMixtureCluster.cpp:636-645) */

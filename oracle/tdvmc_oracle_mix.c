@@ -14,6 +14,33 @@
 #define CO(s) ((s)->n_splines + 1)
 #define LI(s) ((s)->n_splines + 2)
 #define LG(s) ((s)->n_splines + 3)
+/* spline order: 3 = BosonMixtureCluster (GetWeights3), 4 = BosonMixtureCluster_4thorder (GetWeights4, five pieces of degree
+ * four; rijSplit = nodes[4], rijTail = nodes[size - 5]: BosonMixtureCluster_4thorder.cpp:138-153).  For order 4 the spec
+ * carries the reference's phantom 28th spline as a zero spline behind one padding knot, so rijTail = knots[K - 1]. */
+#define ORD(s) ((s)->order == 4 ? 4 : 3)
+#define NKN(s) ((s)->n_splines + ORD(s) + 1)
+#define WSZ(s) ((ORD(s) + 1) * (ORD(s) + 1))
+#define RS(s, knots) ((knots)[ORD(s)])
+#define RT(s, knots) ((knots)[(s)->n_splines - (ORD(s) - 3)])
+
+/* piece p of spline k: value, first and second derivative of its monomial form at r, in the reference's expressions */
+static double piece_val(const oracle_mix* s, const double* q, double r)
+{
+    const double r2 = r * r, r3 = r2 * r;
+    if (ORD(s) == 4) return q[0] + q[1] * r + q[2] * r2 + q[3] * r3 + q[4] * (r2 * r2); /* _4thorder.cpp:894 */
+    return q[0] + q[1] * r + q[2] * r2 + q[3] * r3;
+}
+static double piece_d1(const oracle_mix* s, const double* q, double r)
+{
+    const double r2 = r * r;
+    if (ORD(s) == 4) return q[1] + 2.0 * q[2] * r + 3.0 * q[3] * r2 + 4.0 * q[4] * (r2 * r); /* _4thorder.cpp:503 */
+    return q[1] + 2.0 * q[2] * r + 3.0 * q[3] * r2;
+}
+static double piece_d2(const oracle_mix* s, const double* q, double r)
+{
+    if (ORD(s) == 4) return 2.0 * q[2] + 6.0 * q[3] * r + 12.0 * q[4] * (r * r); /* _4thorder.cpp:505 */
+    return 2.0 * q[2] + 6.0 * q[3] * r;
+}
 
 static double hfdb(double r) /* HFDB.cpp:23-47 with the HFDB_He_He constants */
 {
@@ -97,11 +124,11 @@ static int find_bin(const double* knots, int nk, double r) /* lower_bound(nodes,
 /* value contributions of one pair of type t; core_inclusive: '<=' in CalculateWavefunction (:869), '<' in WFChange (:967) */
 static void add_values(const oracle_mix* s, int t, double r, double* ext, int core_inclusive)
 {
-    const int K = s->n_splines, nk = K + 4;
+    const int K = s->n_splines, nk = NKN(s), np = ORD(s) + 1;
     const double* knots = s->knots + (size_t)t * nk;
-    const double* w = s->weights + (size_t)t * K * 16;
+    const double* w = s->weights + (size_t)t * K * WSZ(s);
     double* e = ext + (size_t)t * EXT(s);
-    const double rs = knots[3], rt = knots[nk - 4];
+    const double rs = RS(s, knots), rt = RT(s, knots);
     if (core_inclusive ? (r <= rs) : (r < rs))
     {
         e[MC(s)] += pow(r, s->mcm[t]);
@@ -114,11 +141,10 @@ static void add_values(const oracle_mix* s, int t, double r, double* ext, int co
     else
     {
         int bin = find_bin(knots, nk, r);
-        double r2 = r * r, r3 = r2 * r;
-        for (int p = 0; p < 4; p++)
+        for (int p = 0; p < np; p++)
         {
-            const double* q = w + ((size_t)(bin - p) * 4 + p) * 4;
-            e[bin - p] += q[0] + q[1] * r + q[2] * r2 + q[3] * r3;
+            const double* q = w + ((size_t)(bin - p) * np + p) * np;
+            e[bin - p] += piece_val(s, q, r);
         }
     }
     e[LG(s)] += log(r);
@@ -174,9 +200,9 @@ void oracle_mix_center_of_mass(const oracle_mix* s, const double* R, double* com
 void oracle_mix_expectation(const oracle_mix* s, const double* R, double wf, double exponent, const double* uR, const double* uI,
                             double* e_r, double* e_i, double* other, double* drift_r, double* drift_i, double* tabD, double* tabD2)
 {
-    const int N = s->n_particles, P = s->n_params, K = s->n_splines, nk = K + 4, NE = s->n_types * EXT(s);
+    const int N = s->n_particles, P = s->n_params, K = s->n_splines, nk = NKN(s), NE = s->n_types * EXT(s), np = ORD(s) + 1;
     double potential = 0, kin_r = 0, kin_i = 0, kin1 = 0, kin2 = 0;
-    double vec[3], evec[3], tmp1[4], tmp2[4];
+    double vec[3], evec[3], tmp1[5], tmp2[5];
     memset(tabD, 0, sizeof(double) * (size_t)NE * N * 3);
     memset(tabD2, 0, sizeof(double) * (size_t)NE * N);
 #define TD(k, n, a) tabD[((size_t)(k) * N + (n)) * 3 + (a)]
@@ -187,9 +213,9 @@ void oracle_mix_expectation(const oracle_mix* s, const double* R, double wf, dou
         {
             const int t = s->pair_type[n * N + i];
             const double* knots = s->knots + (size_t)t * nk;
-            const double* w = s->weights + (size_t)t * K * 16;
+            const double* w = s->weights + (size_t)t * K * WSZ(s);
             const int base = t * EXT(s);
-            const double m = s->mcm[t], rs = knots[3], rt = knots[nk - 4];
+            const double m = s->mcm[t], rs = RS(s, knots), rt = RT(s, knots);
             double r = displacement(R + 3 * n, R + 3 * i, vec);
             if (i < n) potential += oracle_pair_potential(s->potential[t], r);
             if (i == n) continue;
@@ -208,16 +234,15 @@ void oracle_mix_expectation(const oracle_mix* s, const double* R, double wf, dou
             else
             {
                 int bin = find_bin(knots, nk, r);
-                double r2 = r * r;
-                for (int p = 0; p < 4; p++)
+                for (int p = 0; p < np; p++)
                 {
-                    const double* q = w + ((size_t)(bin - p) * 4 + p) * 4;
-                    tmp1[3 - p] = q[1] + 2.0 * q[2] * r + 3.0 * q[3] * r2;
-                    tmp2[3 - p] = 2.0 * q[2] + 6.0 * q[3] * r;
+                    const double* q = w + ((size_t)(bin - p) * np + p) * np;
+                    tmp1[np - 1 - p] = piece_d1(s, q, r);
+                    tmp2[np - 1 - p] = piece_d2(s, q, r);
                 }
                 for (int a = 0; a < 3; a++)
-                    for (int b = 0; b < 4; b++) TD(base + bin - b, n, a) += tmp1[3 - b] * evec[a];
-                for (int b = 0; b < 4; b++) TD2(base + bin - b, n) += tmp2[3 - b] + 2.0 / r * tmp1[3 - b];
+                    for (int b = 0; b < np; b++) TD(base + bin - b, n, a) += tmp1[np - 1 - b] * evec[a];
+                for (int b = 0; b < np; b++) TD2(base + bin - b, n) += tmp2[np - 1 - b] + 2.0 / r * tmp1[np - 1 - b];
             }
             for (int a = 0; a < 3; a++) TD(base + LG(s), n, a) += 1.0 / r * evec[a]; /* :515-519 */
             TD2(base + LG(s), n) += pow(r, -2);

@@ -19,7 +19,7 @@ ip = C.POINTER(C.c_int32)
 
 
 class MixtureDesc(C.Structure):
-    _fields_ = [("n_pair_types", C.c_int32), ("reserved", C.c_int32), ("pair_type", ip), ("hbar_over_2m", dp), ("mass", dp),
+    _fields_ = [("n_pair_types", C.c_int32), ("spline_order", C.c_int32), ("pair_type", ip), ("hbar_over_2m", dp), ("mass", dp),
                 ("knots", dp), ("spline_weights", dp), ("mcmillan_factor", dp), ("potential", ip)]
 
 
@@ -167,7 +167,7 @@ class Handle:
                      ms=np.ascontiguousarray(e["mass"], np.float64), tk=np.ascontiguousarray(e["type_knots"], np.float64),
                      tw=np.ascontiguousarray(e["type_weights"], np.float64), tm=np.ascontiguousarray(e["type_mcm"], np.float64),
                      tp=np.ascontiguousarray(e["type_potential"], np.int32))
-            self._mix = MixtureDesc(e["n_types"], 0, k["pt"].ctypes.data_as(ip), _d(k["hb"]), _d(k["ms"]), _d(k["tk"]),
+            self._mix = MixtureDesc(e["n_types"], int(e.get("order", 3)), k["pt"].ctypes.data_as(ip), _d(k["hb"]), _d(k["ms"]), _d(k["tk"]),
                                     _d(k["tw"]), _d(k["tm"]), k["tp"].ctypes.data_as(ip))
             mix = C.pointer(self._mix)
         sd = SystemDesc(C.sizeof(SystemDesc), spec.n_particles, spec.dim, spec.n_params, spec.n_splines, spec.pair_rule,

@@ -110,7 +110,7 @@ struct tdvmc_gpu_handle
     double he_rs = 0, core_m = 0, he_hl = 0, r_split2 = 1e300, r_tail = 1e300, gr_max = 0, u_core = 0, u_const = 0, u_lin = 0;
     int n_short = 0, potential = 0, rho_bins = 0, use_phi = 0, periodic = 1;
     // BosonMixtureCluster
-    int n_types = 0;
+    int n_types = 0, mix_order = 3;
     std::vector<int> mix_pair_type, mix_pot;
     std::vector<double> mix_hbar, mix_mass, mix_knots, mix_weights, mix_mcm;
     DevBuf<int> d_mix_pair_type, d_mix_pot;
@@ -273,8 +273,8 @@ int build_static_tables(tdvmc_gpu_handle* h)
     {
         h->periodic = 0;
         h->use_phi = 1;
-        h->first_bin = 3;
-        h->nbins = K - 3;
+        h->first_bin = h->mix_order;
+        h->nbins = K - 2 * h->mix_order + 3;
         h->uniform = 0;
         h->ncell = 1;
         h->h = 1.0;
@@ -429,23 +429,31 @@ int build_param_tables(tdvmc_gpu_handle* h)
     if (h->kind == TDVMC_SYSTEM_MIXTURE)
     {
         // per pair type and knot interval: u(r) = sum_p u~[t][b-p] piece_p(b-p)(r) re-expanded around the left knot
-        const int nk = K + 4, EXT = K + 4, nb = K - 3;
-        std::vector<double> mc((size_t)h->n_types * nb * 6, 0.0);
+        // (Taylor shift of the degree-`ord` monomial sum, long double); intervals ord .. K - (ord - 3) - 1
+        const int ord = h->mix_order, np = ord + 1, nk = K + ord + 1, EXT = K + 4, nb = K - 2 * ord + 3, stride = ord + 3;
+        std::vector<double> mc((size_t)h->n_types * nb * stride, 0.0);
         for (int t = 0; t < h->n_types; t++)
-            for (int b = 3; b < K; b++)
+            for (int b = ord; b < ord + nb; b++)
             {
-                long double C[4] = { 0, 0, 0, 0 };
-                for (int p = 0; p < 4; p++)
-                    for (int c = 0; c < 4; c++)
-                        C[c] += (long double)utR[t * EXT + b - p] * (long double)h->mix_weights[(((size_t)t * K + (b - p)) * 4 + p) * 4 + c];
+                long double C[5] = { 0, 0, 0, 0, 0 };
+                for (int p = 0; p < np; p++)
+                    for (int c = 0; c < np; c++)
+                        C[c] += (long double)utR[t * EXT + b - p] * (long double)h->mix_weights[(((size_t)t * K + (b - p)) * np + p) * np + c];
                 const long double t0 = h->mix_knots[(size_t)t * nk + b];
-                double* q = &mc[((size_t)t * nb + (b - 3)) * 6];
-                q[0] = (double)(C[0] + t0 * (C[1] + t0 * (C[2] + t0 * C[3])));
-                q[1] = (double)(C[1] + t0 * (2 * C[2] + 3 * t0 * C[3]));
-                q[2] = (double)(C[2] + 3 * t0 * C[3]);
-                q[3] = (double)C[3];
-                q[4] = h->mix_knots[(size_t)t * nk + b];
-                q[5] = h->mix_knots[(size_t)t * nk + b + 1];
+                double* q = &mc[((size_t)t * nb + (b - ord)) * stride];
+                for (int j = 0; j <= ord; j++) // q_j = sum_{c >= j} binom(c, j) C_c t0^(c-j), Horner in t0
+                {
+                    long double acc = 0;
+                    for (int c = ord; c >= j; c--)
+                    {
+                        long double binom = 1;
+                        for (int i = 0; i < j; i++) binom = binom * (c - i) / (i + 1);
+                        acc = acc * t0 + binom * C[c];
+                    }
+                    q[j] = (double)acc;
+                }
+                q[ord + 1] = h->mix_knots[(size_t)t * nk + b];
+                q[ord + 2] = h->mix_knots[(size_t)t * nk + b + 1];
             }
         CK(upload(h->d_uR, h->uR, h->stream));
         CK(upload(h->d_uI, h->uI, h->stream));
@@ -581,6 +589,7 @@ SysDev tdvmc_gpu_handle::sysdev() const
     s.periodic = periodic; s.n_short = n_short; s.potential = potential; s.rho_bins = rho_bins; s.use_phi = use_phi;
     s.rmax = kind == TDVMC_SYSTEM_HE_BULK ? L / 2.0 : ((kind != TDVMC_SYSTEM_SPLINE_TABLE && kind != TDVMC_SYSTEM_BOX_RADIAL) ? 1e300 : knots[K]); // HeBulk.cpp:54
     s.n_types = n_types;
+    s.spline_order = mix_order;
     s.pair_type = d_mix_pair_type.p; s.hbar_n = d_mix_hbar.p; s.mass_n = d_mix_mass.p; s.t_knots = d_mix_knots.p;
     s.t_weights = d_mix_weights.p; s.t_mcm = d_mix_mcm.p; s.t_pot = d_mix_pot.p; s.t_cub = d_mix_cub.p;
     s.hbar = hbar;
@@ -699,13 +708,25 @@ int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed,
     {
         const tdvmc_mixture_desc* m = sd->mixture;
         const int T = m->n_pair_types, N = h->N, K = h->K;
+        if (m->spline_order != 0 && m->spline_order != 3 && m->spline_order != 4)
+        {
+            h->error = "mixture: spline_order must be 3 or 4";
+            return bail(-1);
+        }
+        h->mix_order = m->spline_order == 4 ? 4 : 3;
+        const int ord = h->mix_order;
+        if (K < 2 * ord)
+        {
+            h->error = "mixture: too few splines for the spline order";
+            return bail(-1);
+        }
         h->n_types = T;
         h->mix_pair_type.assign(m->pair_type, m->pair_type + (size_t)N * N);
         h->mix_pot.assign(m->potential, m->potential + T);
         h->mix_hbar.assign(m->hbar_over_2m, m->hbar_over_2m + N);
         h->mix_mass.assign(m->mass, m->mass + N);
-        h->mix_knots.assign(m->knots, m->knots + (size_t)T * (K + 4));
-        h->mix_weights.assign(m->spline_weights, m->spline_weights + (size_t)T * K * 16);
+        h->mix_knots.assign(m->knots, m->knots + (size_t)T * (K + ord + 1));
+        h->mix_weights.assign(m->spline_weights, m->spline_weights + (size_t)T * K * (ord + 1) * (ord + 1));
         h->mix_mcm.assign(m->mcmillan_factor, m->mcmillan_factor + T);
         for (int t : h->mix_pair_type)
             if (t < 0 || t >= T)

@@ -68,14 +68,15 @@ struct SysDev
     const double* map_const; // [P] constant part of O_p
     // BosonMixtureCluster (kind 3): per-pair-type bases, per-particle species data
     int n_types;               // pair types T
+    int spline_order;          // 3 (BosonMixtureCluster) or 4 (BosonMixtureCluster_4thorder)
     const int* pair_type;      // [N][N] correlationTypes
     const double* hbar_n;      // [N] hbar^2/2m of each particle's species
     const double* mass_n;      // [N]
-    const double* t_knots;     // [T][K+4]
-    const double* t_weights;   // [T][K][4][4] monomial spline tables (SplineFactory::GetWeights3)
+    const double* t_knots;     // [T][K+order+1]
+    const double* t_weights;   // [T][K][order+1][order+1] monomial spline tables (SplineFactory::GetWeights3 / GetWeights4)
     const double* t_mcm;       // [T] McMillan exponents
     const int* t_pot;          // [T] pair potential ids
-    const double* t_cub;       // [T][K-3][6] sweep cubics {c0,c1,c2,c3,t_lo,t_hi} per knot interval
+    const double* t_cub;       // [T][K-2*order+3][order+3] sweep polynomials {c0..c_order, t_lo, t_hi} per knot interval
     // NUBosonsBulkPBBoxAndRadial (kind 4): ext = [ssRad (K) | ss (K)] on one knot vector; cub holds the radial planes
     // followed by the box planes
     const double* ugR;         // [n_ext] u~ as the DRIFT uses it: the last radial spline's parameter multiplies the box

@@ -6,6 +6,11 @@
 // (the reference's SplineFactory table, passed by the caller), constant + linear tails beyond knots[K], a log term
 // for every pair; per-species hbar^2/2m; pair potentials HFDB_He_He / KTTY_He_Na / KTTY_He_Cs (src/Potentials).
 // Extended sums per type: ext[t*(K+4) + j] = [ss_0..ss_{K-1} | mcMillan | const | linear | log].
+//
+// ORDER = 3: BosonMixtureCluster (cubic splines, four overlapping pieces, SplineFactory::GetWeights3);
+// ORDER = 4: BosonMixtureCluster_4thorder (quartic, five pieces, GetWeights4; rijSplit = nodes[4], rijTail = nodes[size-5],
+// BosonMixtureCluster_4thorder.cpp:138-153, :498-517, :890-895).  Knots per type: K + ORDER + 1; for ORDER = 4 the caller
+// passes the reference's never-filled 28th spline as a zero spline behind one padding knot (rijTail = knots[K-1]).
 #include "kernels.cuh"
 
 namespace tdvmc
@@ -93,12 +98,14 @@ __device__ __forceinline__ int mix_find_bin(const double* __restrict__ knots, in
     return lo - 1;
 }
 
+template <int ORDER>
 __global__ void __launch_bounds__(64) evaluate_mix_kernel(EvalArgs a)
 {
     const SysDev& s = a.s;
     const int cfg = blockIdx.x * blockDim.x + threadIdx.x;
     if (cfg >= a.n_cfg) return;
-    const int N = s.N, K = s.K, P = s.P, nk = K + 4, EXT = K + 4, NE = s.n_ext;
+    constexpr int NP = ORDER + 1; // pieces per spline = coefficients per piece
+    const int N = s.N, K = s.K, P = s.P, nk = K + ORDER + 1, EXT = K + 4, NE = s.n_ext;
     const int MC = K, CO = K + 1, LI = K + 2, LG = K + 3;
 
     double px[kMixMaxN], py[kMixMaxN], pz[kMixMaxN];
@@ -121,10 +128,10 @@ __global__ void __launch_bounds__(64) evaluate_mix_kernel(EvalArgs a)
             if (i == n) continue;
             const int t = s.pair_type[n * N + i];
             const double* knots = s.t_knots + (size_t)t * nk;
-            const double* w = s.t_weights + (size_t)t * K * 16;
+            const double* w = s.t_weights + (size_t)t * K * NP * NP;
             const double* uR = s.utR + t * EXT;
             const double* uI = s.utI + t * EXT;
-            const double m = s.t_mcm[t], rs = knots[3], rt = knots[nk - 4];
+            const double m = s.t_mcm[t], rs = knots[ORDER], rt = knots[K - (ORDER - 3)];
             const double vx = px[n] - px[i], vy = py[n] - py[i], vz = pz[n] - pz[i]; // VectorDisplacement, Utils.cpp:253-263
             const double r = sqrt(vx * vx + vy * vy + vz * vz);
             const double ex = vx / r, ey = vy / r, ez = vz / r;
@@ -155,11 +162,16 @@ __global__ void __launch_bounds__(64) evaluate_mix_kernel(EvalArgs a)
                 const double r2 = r * r;
                 const double f2 = 2.0 / r;
 #pragma unroll
-                for (int p = 0; p < 4; p++)
+                for (int p = 0; p < NP; p++)
                 {
-                    const double* q = w + ((size_t)(bin - p) * 4 + p) * 4;
-                    const double d1 = q[1] + 2.0 * q[2] * r + 3.0 * q[3] * r2; // :489-492
-                    const double d2 = 2.0 * q[2] + 6.0 * q[3] * r;
+                    const double* q = w + ((size_t)(bin - p) * NP + p) * NP;
+                    double d1 = q[1] + 2.0 * q[2] * r + 3.0 * q[3] * r2; // :489-492
+                    double d2 = 2.0 * q[2] + 6.0 * q[3] * r;
+                    if (ORDER == 4) // BosonMixtureCluster_4thorder.cpp:503-505 (rni3 = rni2 * rni)
+                    {
+                        d1 = d1 + 4.0 * q[NP - 1] * (r2 * r);
+                        d2 = d2 + 12.0 * q[NP - 1] * r2;
+                    }
                     gR = fma(uR[bin - p], d1, gR);
                     gI = fma(uI[bin - p], d1, gI);
                     lR = fma(uR[bin - p], d2 + f2 * d1, lR);
@@ -186,10 +198,12 @@ __global__ void __launch_bounds__(64) evaluate_mix_kernel(EvalArgs a)
                     const int bin = mix_find_bin(knots, nk, r);
                     const double r2 = r * r, r3 = r2 * r;
 #pragma unroll
-                    for (int p = 0; p < 4; p++)
+                    for (int p = 0; p < NP; p++)
                     {
-                        const double* q = w + ((size_t)(bin - p) * 4 + p) * 4;
-                        e[bin - p] += q[0] + q[1] * r + q[2] * r2 + q[3] * r3;
+                        const double* q = w + ((size_t)(bin - p) * NP + p) * NP;
+                        double v = q[0] + q[1] * r + q[2] * r2 + q[3] * r3;
+                        if (ORDER == 4) v = v + q[NP - 1] * (r2 * r2); // BosonMixtureCluster_4thorder.cpp:890-894
+                        e[bin - p] += v;
                     }
                 }
                 e[LG] += log(r);
@@ -245,31 +259,38 @@ cudaError_t launch_evaluate_mix(const EvalArgs& a, cudaStream_t st)
 {
     if (a.n_cfg <= 0) return cudaSuccess;
     if (a.s.N > kMixMaxN || a.s.n_ext > kMixMaxExt) return cudaErrorInvalidValue;
-    evaluate_mix_kernel<<<(a.n_cfg + 63) / 64, 64, 0, st>>>(a);
+    if (a.s.spline_order == 4) evaluate_mix_kernel<4><<<(a.n_cfg + 63) / 64, 64, 0, st>>>(a);
+    else evaluate_mix_kernel<3><<<(a.n_cfg + 63) / 64, 64, 0, st>>>(a);
     return cudaGetLastError();
 }
 
-// pair term of the exponent: sum_j u~_j phi_j(r) for pair type t (sweep form)
+// pair term of the exponent: sum_j u~_j phi_j(r) for pair type t (sweep form): per knot interval the ORDER + 1 Taylor
+// coefficients around the left knot, then {t_lo, t_hi}
+template <int ORDER>
 __device__ __forceinline__ double mix_pair_u(const SysDev& s, int t, double r)
 {
-    const int K = s.K, nk = K + 4, EXT = K + 4, nb = K - 3;
+    const int K = s.K, nk = K + ORDER + 1, EXT = K + 4, nb = K - 2 * ORDER + 3;
+    constexpr int STRIDE = ORDER + 3;
     const double* knots = s.t_knots + (size_t)t * nk;
     const double* u = s.utR + t * EXT;
-    const double rs = knots[3], rt = knots[nk - 4];
+    const double rs = knots[ORDER], rt = knots[K - (ORDER - 3)];
     double v;
     if (r < rs) v = u[K] * pow(r, s.t_mcm[t]);
     else if (r >= rt) v = fma(u[K + 2], r, u[K + 1]);
     else
     {
-        int j = mix_find_bin(knots, nk, r) - 3;
+        int j = mix_find_bin(knots, nk, r) - ORDER;
         j = max(0, min(j, nb - 1));
-        const double* q = s.t_cub + ((size_t)t * nb + j) * 6;
-        const double x = r - q[4];
-        v = fma(fma(fma(q[3], x, q[2]), x, q[1]), x, q[0]);
+        const double* q = s.t_cub + ((size_t)t * nb + j) * STRIDE;
+        const double x = r - q[ORDER + 1];
+        v = q[ORDER];
+#pragma unroll
+        for (int c = ORDER - 1; c >= 0; c--) v = fma(v, x, q[c]);
     }
     return fma(u[K + 3], log(r), v);
 }
 
+template <int ORDER>
 __global__ void __launch_bounds__(64) sweep_mix_kernel(SweepArgs a)
 {
     const SysDev& s = a.s;
@@ -309,7 +330,7 @@ __global__ void __launch_bounds__(64) sweep_mix_kernel(SweepArgs a)
             const double r_old = sqrt(dx * dx + dy * dy + dz * dz);
             dx = px[i] - nx; dy = py[i] - ny; dz = pz[i] - nz;
             const double r_new = sqrt(dx * dx + dy * dy + dz * dz);
-            delta += mix_pair_u(s, ct, r_new) - mix_pair_u(s, ct, r_old);
+            delta += mix_pair_u<ORDER>(s, ct, r_new) - mix_pair_u<ORDER>(s, ct, r_old);
         }
         const double two_delta = 2.0 * delta;
         if ((two_delta >= pr.log_u) && (two_delta <= 709.782712893384))
@@ -337,10 +358,12 @@ __global__ void __launch_bounds__(64) sweep_mix_kernel(SweepArgs a)
 cudaError_t launch_sweep_mix(const SweepArgs& a, cudaStream_t st)
 {
     if (a.s.N > kMixMaxN) return cudaErrorInvalidValue;
-    sweep_mix_kernel<<<(a.W + 63) / 64, 64, 0, st>>>(a);
+    if (a.s.spline_order == 4) sweep_mix_kernel<4><<<(a.W + 63) / 64, 64, 0, st>>>(a);
+    else sweep_mix_kernel<3><<<(a.W + 63) / 64, 64, 0, st>>>(a);
     return cudaGetLastError();
 }
 
+template <int ORDER>
 __global__ void quotient_mix_kernel(QuotientArgs a)
 {
     const SysDev& s = a.s;
@@ -361,7 +384,7 @@ __global__ void quotient_mix_kernel(QuotientArgs a)
         const double r_old = sqrt(dx * dx + dy * dy + dz * dz);
         dx = px[i] - nx; dy = py[i] - ny; dz = pz[i] - nz;
         const double r_new = sqrt(dx * dx + dy * dy + dz * dz);
-        delta += mix_pair_u(s, ct, r_new) - mix_pair_u(s, ct, r_old);
+        delta += mix_pair_u<ORDER>(s, ct, r_new) - mix_pair_u<ORDER>(s, ct, r_old);
     }
     a.delta[mv] = delta;
 }
@@ -369,7 +392,8 @@ __global__ void quotient_mix_kernel(QuotientArgs a)
 cudaError_t launch_quotient_mix(const QuotientArgs& a, cudaStream_t st)
 {
     if (a.n_moves <= 0) return cudaSuccess;
-    quotient_mix_kernel<<<(a.n_moves + 63) / 64, 64, 0, st>>>(a);
+    if (a.s.spline_order == 4) quotient_mix_kernel<4><<<(a.n_moves + 63) / 64, 64, 0, st>>>(a);
+    else quotient_mix_kernel<3><<<(a.n_moves + 63) / 64, 64, 0, st>>>(a);
     return cudaGetLastError();
 }
 

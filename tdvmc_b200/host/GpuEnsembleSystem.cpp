@@ -28,6 +28,15 @@ void PushRow(SystemTables& t, std::initializer_list<std::pair<int, double> > row
     }
     t.map_ptr.push_back((int32_t)t.map_col.size());
 }
+void PushRow(SystemTables& t, const std::vector<std::pair<int, double> >& row)
+{
+    for (const auto& e : row)
+    {
+        t.map_col.push_back(e.first);
+        t.map_val.push_back(e.second);
+    }
+    t.map_ptr.push_back((int32_t)t.map_col.size());
+}
 } // namespace
 
 SystemTables MakeBosonsBulkTables(int N, double LBOX, int N_PARAM, const std::vector<double>& nodes,
@@ -179,11 +188,15 @@ SystemTables MakeHeDropTables(int N, int N_PARAM)
 SystemTables MakeBosonMixtureClusterTables(int N, const std::vector<std::vector<int> >& correlationTypes,
                                            const std::vector<double>& hbarOver2mPerParticle,
                                            const std::vector<double>& massPerParticle,
-                                           const std::vector<MixturePairType>& pairTypes, int numOfOtherExpectationValues)
+                                           const std::vector<MixturePairType>& pairTypes, int numOfOtherExpectationValues,
+                                           int splineOrder)
 {
+    if (splineOrder != 3 && splineOrder != 4) throw std::runtime_error("BosonMixtureCluster: spline order 3 or 4");
     SystemTables t;
-    const int T = (int)pairTypes.size(), K = 26, EXT = K + 4; // paramOffset = 26, BosonMixtureCluster.cpp:543
+    // paramOffset = 26 (BosonMixtureCluster.cpp:543); numberOfSplines = 26 cubic, 28 quartic (_4thorder.cpp:138-146)
+    const int T = (int)pairTypes.size(), ord = splineOrder, nb = ord - 1, K = 26 + 2 * (ord - 3), EXT = K + 4;
     t.system_kind = TDVMC_SYSTEM_MIXTURE;
+    t.spline_order = ord;
     t.n_particles = N;
     t.n_params = 26 * T;
     t.lbox = 0.0;
@@ -199,23 +212,38 @@ SystemTables MakeBosonMixtureClusterTables(int N, const std::vector<std::vector<
     for (int c = 0; c < T; c++)
     {
         const MixturePairType& p = pairTypes[c];
-        if ((int)p.nodes.size() != K + 4) throw std::runtime_error("BosonMixtureCluster: 26 splines per pair type expected");
-        t.type_knots.insert(t.type_knots.end(), p.nodes.begin(), p.nodes.end());
-        const std::vector<double> w = FlattenWeights(p.splineWeights);
+        std::vector<double> nodes = p.nodes;
+        std::vector<double> w = FlattenWeights(p.splineWeights);
+        if (ord == 4 && (int)nodes.size() == K + ord)
+        {
+            // 32 nodes carry 27 quartic splines; the reference's 28th never receives a term (see tdvmc_gpu.h): zero
+            // spline behind one padding knot
+            nodes.push_back(nodes.back() + 1.0);
+            w.resize((size_t)K * (ord + 1) * (ord + 1), 0.0);
+        }
+        if ((int)nodes.size() != K + ord + 1 || (int)w.size() != K * (ord + 1) * (ord + 1))
+            throw std::runtime_error("BosonMixtureCluster: 26 (cubic) / 28 (quartic) splines per pair type expected");
+        t.type_knots.insert(t.type_knots.end(), nodes.begin(), nodes.end());
         t.type_weights.insert(t.type_weights.end(), w.begin(), w.end());
         t.type_mcmillan.push_back(p.mcMillanFactor);
         t.pair_potential.push_back(p.potential);
         const int b = c * EXT, MC = K, CO = K + 1, LI = K + 2, LG = K + 3;
-        const auto& bc = p.bcFactors; // BosonMixtureCluster.cpp:636-645
-        PushRow(t, { { b + MC, 1.0 }, { b + 0, bc[0][0] }, { b + 1, bc[0][1] } });
-        PushRow(t, { { b + 2, 1.0 }, { b + 0, bc[1][0] }, { b + 1, bc[1][1] } });
-        for (int i = 2; i < 22; i++) PushRow(t, { { b + i + 1, 1.0 } });
-        PushRow(t, { { b + K - 3, 1.0 }, { b + K - 2, bc[2][0] }, { b + K - 1, bc[2][1] } });
-        PushRow(t, { { b + CO, 1.0 }, { b + K - 2, bc[3][0] }, { b + K - 1, bc[3][1] } });
-        PushRow(t, { { b + LI, 1.0 }, { b + K - 2, bc[4][0] }, { b + K - 1, bc[4][1] } });
+        const auto& bc = p.bcFactors; // BosonMixtureCluster.cpp:636-645, BosonMixtureCluster_4thorder.cpp:641-650
+        auto row = [&](int lead, int r, int first) {
+            std::vector<std::pair<int, double> > e;
+            e.push_back({ lead, 1.0 });
+            for (int j = 0; j < nb; j++) e.push_back({ first + j, bc[r][j] });
+            PushRow(t, e);
+        };
+        row(b + MC, 0, b);
+        row(b + nb, 1, b);
+        for (int i = 2; i < 22; i++) PushRow(t, { { b + i + nb - 1, 1.0 } });
+        row(b + K - nb - 1, 2, b + K - nb);
+        row(b + CO, 3, b + K - nb);
+        row(b + LI, 4, b + K - nb);
         PushRow(t, { { b + LG, 1.0 } });
     }
-    t.knots.assign(t.type_knots.begin(), t.type_knots.begin() + K + 4);
+    t.knots.assign(t.type_knots.begin(), t.type_knots.begin() + K + ord + 1);
     return t;
 }
 
@@ -237,7 +265,7 @@ GpuEnsembleSystem::GpuEnsembleSystem(const SystemTables& tb, int walkersTotal, d
     sd.n_particles = tb.n_particles;
     sd.dim = 3;
     sd.n_params = tb.n_params;
-    sd.n_splines = tb.system_kind == TDVMC_SYSTEM_MIXTURE ? 26 : (int32_t)tb.knots.size() - 4;
+    sd.n_splines = tb.system_kind == TDVMC_SYSTEM_MIXTURE ? 26 + 2 * (tb.spline_order - 3) : (int32_t)tb.knots.size() - 4;
     sd.pair_rule = tb.pair_rule;
     sd.tail_param = tb.tail_param;
     sd.n_other = tb.n_other;
@@ -260,7 +288,7 @@ GpuEnsembleSystem::GpuEnsembleSystem(const SystemTables& tb, int walkersTotal, d
     if (tb.system_kind == TDVMC_SYSTEM_MIXTURE)
     {
         md.n_pair_types = tb.n_pair_types;
-        md.reserved = 0;
+        md.spline_order = tb.spline_order;
         md.pair_type = tb.pair_type.data();
         md.hbar_over_2m = tb.hbar_over_2m.data();
         md.mass = tb.mass.data();

@@ -43,6 +43,7 @@ struct SystemTables
     std::vector<double> map_const, grad_const; // empty: zeros
     // BosonMixtureCluster only (system_kind == TDVMC_SYSTEM_MIXTURE)
     int n_pair_types = 0;
+    int spline_order = 3;                  // 4: BosonMixtureCluster_4thorder
     std::vector<int32_t> pair_type;        // correlationTypes flattened [N][N]
     std::vector<int32_t> pair_potential;   // [T] 0 HFDB_He_He, 1 KTTY_He_Na, 2 KTTY_He_Cs
     std::vector<double> hbar_over_2m, mass; // [N]
@@ -75,7 +76,7 @@ struct MixturePairType
 {
     std::vector<double> nodes;                                     // cfd.nodes
     std::vector<std::vector<std::vector<double> > > splineWeights; // cfd.splineWeights
-    std::vector<std::vector<double> > bcFactors;                   // cfd.bcFactors (5 x 2)
+    std::vector<std::vector<double> > bcFactors;                   // cfd.bcFactors (5 x 2; 5 x 3 for the 4th-order class)
     double mcMillanFactor;
     int potential;                                                 // 0 HFDB_He_He, 1 KTTY_He_Na, 2 KTTY_He_Cs
 };
@@ -83,7 +84,8 @@ struct MixturePairType
 SystemTables MakeBosonMixtureClusterTables(int N, const std::vector<std::vector<int> >& correlationTypes,
                                            const std::vector<double>& hbarOver2mPerParticle,
                                            const std::vector<double>& massPerParticle,
-                                           const std::vector<MixturePairType>& pairTypes, int numOfOtherExpectationValues);
+                                           const std::vector<MixturePairType>& pairTypes, int numOfOtherExpectationValues,
+                                           int splineOrder = 3); // 4: BosonMixtureCluster_4thorder (bcFactors 5 x 3)
 
 // g(r) / S(k) description: what BosonsBulk::InitSystem builds (BosonsBulk.cpp:124-153).
 struct ObservableTables

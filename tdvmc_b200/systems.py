@@ -260,12 +260,17 @@ def species_hbar_over_2m(mass):
     return hbar ** 2.0 / (2.0 * mass * u) / (A2m ** 2.0 * kb)
 
 
-def boson_mixture_cluster(particle_types, type_knots, type_weights, type_bc, n_other=403, type_mcm=None):
-    """``BosonMixtureCluster`` (BosonMixtureCluster.cpp:58-346).  ``particle_types``: the config's PARTICLE_TYPES
-    (enum values).  Species and pair types are numbered in order of first appearance (:58-102).  Per pair type the
-    caller passes the reference's knots (30), spline table (26x4x4) and boundary factors bcFactors (5x2)
-    (SetBoundaryConditions1_MM_1 / 1_EXP_2).  Parameters: 26 per pair type (:543); extended sums per type:
-    ``[ss_0..ss_25 | mcMillan | const | linear | log]``; map of :636-645."""
+def boson_mixture_cluster(particle_types, type_knots, type_weights, type_bc, n_other=403, type_mcm=None, order=3):
+    """``BosonMixtureCluster`` (BosonMixtureCluster.cpp:58-346) and, with ``order=4``, ``BosonMixtureCluster_4thorder``
+    (BosonMixtureCluster_4thorder.cpp:104-346, config/He4He4Na_4thOrder.config).  ``particle_types``: the config's
+    PARTICLE_TYPES (enum values).  Species and pair types are numbered in order of first appearance (:58-102).  Per pair
+    type the caller passes the reference's knots (K + order + 1), spline table (K x (order+1) x (order+1),
+    SplineFactory::GetWeights3 / GetWeights4) and boundary factors bcFactors (5 x (order-1); SetBoundaryConditions1_MM_1 /
+    1_EXP_2 and their _4thorder twins).  K = 26 cubic / 28 quartic splines; 26 parameters per pair type either way (:543);
+    extended sums per type: ``[ss_0..ss_{K-1} | mcMillan | const | linear | log]``; map of :636-645 (4th order: :641-650, the
+    plain operators are ``ss[i + 2]``)."""
+    if order not in (3, 4):
+        raise ValueError("spline order must be 3 or 4")
     pt = [int(x) for x in particle_types]
     N = len(pt)
     pair_index, pair_type = {}, np.zeros((N, N), dtype=np.int32)
@@ -276,19 +281,22 @@ def boson_mixture_cluster(particle_types, type_knots, type_weights, type_bc, n_o
                 pair_index[key] = len(pair_index)
             pair_type[i, j] = pair_type[j, i] = pair_index[key]
     T = len(pair_index)
-    K = 26
+    nb = order - 1                 # boundary factors per row: the first / last nb splines are tied to their neighbours
+    K = 26 + (order - 3) * 2
     EXT = K + 4
     MC, CO, LI, LG = K, K + 1, K + 2, K + 3
     rows = []
     for t in range(T):
         bc = np.asarray(type_bc[t], dtype=np.float64)
         b = t * EXT
-        rows.append([(b + MC, 1.0), (b + 0, bc[0][0]), (b + 1, bc[0][1])])
-        rows.append([(b + 2, 1.0), (b + 0, bc[1][0]), (b + 1, bc[1][1])])
-        rows += [[(b + i + 1, 1.0)] for i in range(2, 22)]
-        rows.append([(b + K - 3, 1.0), (b + K - 2, bc[2][0]), (b + K - 1, bc[2][1])])
-        rows.append([(b + CO, 1.0), (b + K - 2, bc[3][0]), (b + K - 1, bc[3][1])])
-        rows.append([(b + LI, 1.0), (b + K - 2, bc[4][0]), (b + K - 1, bc[4][1])])
+        first = [(b + j, bc[0][j]) for j in range(nb)]
+        rows.append([(b + MC, 1.0)] + first)
+        rows.append([(b + nb, 1.0)] + [(b + j, bc[1][j]) for j in range(nb)])
+        rows += [[(b + i + nb - 1, 1.0)] for i in range(2, 22)]
+        last = lambda r: [(b + K - nb + j, bc[r][j]) for j in range(nb)]
+        rows.append([(b + K - nb - 1, 1.0)] + last(2))
+        rows.append([(b + CO, 1.0)] + last(3))
+        rows.append([(b + LI, 1.0)] + last(4))
         rows.append([(b + LG, 1.0)])
     ptr, col, val = _csr(rows)
     pots = []
@@ -297,14 +305,24 @@ def boson_mixture_cluster(particle_types, type_knots, type_weights, type_bc, n_o
         pots.append(POT_KTTY_HE_CS if 4 in sp else (POT_KTTY_HE_NA if 2 in sp else POT_HFDB_HE_HE))   # :233-282
     mass = np.array([SPECIES_MASS[x] for x in pt])
     hbar = np.array([species_hbar_over_2m(m) for m in mass])
-    knots = np.ascontiguousarray(type_knots, np.float64).reshape(T, K + 4)
-    weights = np.ascontiguousarray(type_weights, np.float64).reshape(T, K, 4, 4)
+    knots = np.ascontiguousarray(type_knots, np.float64).reshape(T, -1)
+    weights = np.ascontiguousarray(type_weights, np.float64).reshape(T, -1, order + 1, order + 1)
+    if order == 4 and knots.shape[1] == K + order and weights.shape[1] == K - 1:
+        # The reference sizes its sums for numberOfSplines = 28 (BosonMixtureCluster_4thorder.cpp:138-146) while the
+        # config's 32 knots carry 27 quartic splines (SplineFactory.cpp:112-114): spline 27 never receives a term but
+        # is a column of the operator map (:647-649).  Kept as a zero spline behind one padding knot, so that the
+        # layout stays [K splines | extras]; rijTail = nodes[size - 5] is knots[K - 1] of the padded vector.
+        knots = np.concatenate([knots, knots[:, -1:] + 1.0], axis=1)
+        weights = np.concatenate([weights, np.zeros((T, 1, order + 1, order + 1))], axis=1)
+    if knots.shape[1] != K + order + 1 or weights.shape[1] != K:
+        raise ValueError(f"expected {K} splines on {K + order + 1} knots per pair type")
     mcm = np.full(T, -4.7) if type_mcm is None else np.asarray(type_mcm, np.float64)
-    return SystemSpec("BosonMixtureCluster", N, 26 * T, 0.0, knots[0], weights[0], ptr, col, val, PAIR_RULE_CUT, np.zeros(0),
+    name = "BosonMixtureCluster" if order == 3 else "BosonMixtureCluster_4thorder"
+    return SystemSpec(name, N, 26 * T, 0.0, knots[0], weights[0], ptr, col, val, PAIR_RULE_CUT, np.zeros(0),
                       n_other=n_other, tail_param=-1, kind=KIND_MIXTURE, n_ext=T * EXT,
                       extra=dict(n_splines=K, n_types=T, pair_type=pair_type, type_knots=knots, type_weights=weights,
                                  type_mcm=mcm, type_potential=np.array(pots, dtype=np.int32), hbar=hbar, mass=mass,
-                                 r_max=float("inf")))
+                                 r_max=float("inf"), order=order))
 
 
 def from_golden(g):
@@ -316,11 +334,12 @@ def from_golden(g):
         if spec.extra["h"] != float(g["node_point_spacing"]) or not np.array_equal(spec.extra["factors"], g["bc_factors"]):
             raise AssertionError("HeBulk set-up differs from the reference dump")
         return spec
-    if name == "BosonMixtureCluster":
+    if name in ("BosonMixtureCluster", "BosonMixtureCluster_4thorder"):
         T = int(g["n_pair_types"])
         spec = boson_mixture_cluster(g["PARTICLE_TYPES"], [g[f"knots_{t}"] for t in range(T)],
                                      [g[f"spline_weights_{t}"] for t in range(T)], [g[f"bc_factors_{t}"] for t in range(T)],
-                                     n_other=len(g["other_expectation_values"]), type_mcm=[g[f"extras_{t}"][6] for t in range(T)])
+                                     n_other=len(g["other_expectation_values"]), type_mcm=[g[f"extras_{t}"][6] for t in range(T)],
+                                     order=3 if name == "BosonMixtureCluster" else 4)
         if not np.array_equal(spec.extra["pair_type"].ravel(), g["correlation_types"].astype(np.int32)):
             raise AssertionError("pair-type numbering differs from the reference dump")
         ref_hb = g["type_hbar_over_2m"][g["particle_types"].astype(int)]

@@ -30,7 +30,7 @@ class OracleHeStruct(C.Structure):
 
 class OracleMixStruct(C.Structure):
     _fields_ = [("n_particles", C.c_int32), ("n_params", C.c_int32), ("n_types", C.c_int32), ("n_splines", C.c_int32),
-                ("n_other", C.c_int32), ("pad", C.c_int32), ("pair_type", ip), ("hbar", dp), ("mass", dp), ("knots", dp),
+                ("n_other", C.c_int32), ("order", C.c_int32), ("pair_type", ip), ("hbar", dp), ("mass", dp), ("knots", dp),
                 ("weights", dp), ("mcm", dp), ("potential", ip), ("map_ptr", ip), ("map_col", ip), ("map_val", dp)]
 
 
@@ -394,7 +394,8 @@ class OracleMix:
                       np.ascontiguousarray(spec.map_col, np.int32), np.ascontiguousarray(spec.map_val, np.float64)]
         k = self._keep
         I = lambda a: a.ctypes.data_as(ip)
-        self.sys = OracleMixStruct(spec.n_particles, spec.n_params, e["n_types"], e["n_splines"], spec.n_other, 0, I(k[0]),
+        self.sys = OracleMixStruct(spec.n_particles, spec.n_params, e["n_types"], e["n_splines"], spec.n_other,
+                                   int(e.get("order", 3)), I(k[0]),
                                    _d(k[1]), _d(k[2]), _d(k[3]), _d(k[4]), _d(k[5]), I(k[6]), I(k[7]), I(k[8]), _d(k[9]))
         self.N, self.P, self.K, self.T = spec.n_particles, spec.n_params, e["n_splines"], e["n_types"]
         self.NE, self.NO = self.T * (self.K + 4), spec.n_other

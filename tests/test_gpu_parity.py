@@ -798,9 +798,11 @@ def test_hedrop_chain_estimators_and_com(capi, golden):
 # BosonMixtureCluster (BASELINE configs[4], config/He4He4Na.config): species, pair types, log term, HFDB / KTTY
 # ---------------------------------------------------------------------------------------------------
 MIX_CASES = ["mixture_he4he4na_fixture", "mixture_he4he4na_compact", "mixture_he4he4na_stretched", "mixture_he4he4na_equil"]
+# BosonMixtureCluster_4thorder (config/He4He4Na_4thOrder.config): quartic splines, same kernels
+MIX4_CASES = ["mixture4_he4he4na_fixture", "mixture4_he4he4na_compact", "mixture4_he4he4na_stretched", "mixture4_he4he4na_equil"]
 
 
-@pytest.mark.parametrize("name", MIX_CASES)
+@pytest.mark.parametrize("name", MIX_CASES + MIX4_CASES)
 def test_mixture_fixed_configuration(capi, golden, name):
     from oracle_lib import OracleMix
 
@@ -826,10 +828,11 @@ def test_mixture_fixed_configuration(capi, golden, name):
     h.close()
 
 
-def test_mixture_chain_estimators_and_com(capi, golden):
+@pytest.mark.parametrize("name", ["mixture_he4he4na_equil", "mixture4_he4he4na_equil"])
+def test_mixture_chain_estimators_and_com(capi, golden, name):
     from oracle_lib import OracleMix
 
-    g = golden("mixture_he4he4na_equil")
+    g = golden(name)
     W, seed, mc_step = 70, 12, 2.0
     n_samples, n_therm, n_init = 3, 10, 30
     spec, h = make_handle(capi, g, n_walkers=W, seed=seed, mc_step=mc_step, max_samples=n_samples)

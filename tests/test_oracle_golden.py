@@ -166,14 +166,19 @@ def test_hebulk_sampler_statistics_match_reference(golden):
 MIX_CASES = ["mixture_he4he4na_fixture", "mixture_he4he4na_compact", "mixture_he4he4na_stretched", "mixture_he4he4na_equil"]
 
 
-@pytest.mark.parametrize("name", MIX_CASES)
+MIX4_CASES = ["mixture4_he4he4na_fixture", "mixture4_he4he4na_compact", "mixture4_he4he4na_stretched", "mixture4_he4he4na_equil"]
+
+
+@pytest.mark.parametrize("name", MIX_CASES + MIX4_CASES)
 def test_mixture_fixed_configuration_matches_reference(golden, name):
+    """BosonMixtureCluster (cubic splines) and BosonMixtureCluster_4thorder (quartic)."""
     from oracle_lib import OracleMix
 
     g = golden(name)
     spec = systems.from_golden(g)     # checks the pair-type numbering and hbar^2/2m against the reference object
     o = OracleMix(spec)
-    K, T = 26, int(g["n_pair_types"])
+    K, T = spec.extra["n_splines"], int(g["n_pair_types"])
+    assert K == (26 if name in MIX_CASES else 28) and g[f"spline_sums_0"].shape == (K,)
     r = o.evaluate(g["R"], g["uR"], g["uI"], float(g["phiR"]))
     for t in range(T):
         e = r["ext"][t * (K + 4):(t + 1) * (K + 4)]
