@@ -30,14 +30,21 @@ struct BrAcc
     double gR, gI, lR, lI;
 };
 
+struct BrEvalTables // block-shared copies in shared memory
+{
+    const double* knots;
+    const double* rec;
+    const unsigned short* lut;
+};
+
 template <bool RADIAL>
-__device__ __forceinline__ void br_pieces(const SysDev& s, const double* __restrict__ knots, double x, double f2, bool values,
+__device__ __forceinline__ void br_pieces(const SysDev& s, const BrEvalTables& tb, double x, double f2, bool values,
                                           double* __restrict__ ext, const double* __restrict__ ugR,
                                           const double* __restrict__ ugI, const double* __restrict__ ulR,
                                           const double* __restrict__ ulI, BrAcc& acc)
 {
-    const int bin = find_bin_exact(s, knots, s.lut, x);
-    const double* rec = s.rec + (size_t)(bin - s.first_bin) * kRecStride;
+    const int bin = find_bin_exact(s, tb.knots, tb.lut, x);
+    const double* rec = tb.rec + (size_t)(bin - s.first_bin) * kRecStride;
     const double x2 = x * x, x3 = x2 * x;
 #pragma unroll
     for (int p = 0; p < 4; p++)
@@ -52,7 +59,8 @@ __device__ __forceinline__ void br_pieces(const SysDev& s, const double* __restr
         const double l = RADIAL ? d2 + f2 * d1 : d2;         // :373 (secondDerivativeFactor / rni * tmp1), :411
         acc.lR = fma(ulR[k], l, acc.lR);
         acc.lI = fma(ulI[k], l, acc.lI);
-        if (values) atomicAdd(&ext[k], w0 + w1 * x + w2 * x2 + w3 * x3); // :240, :255
+        const double v = w0 + w1 * x + w2 * x2 + w3 * x3;    // :240, :255 (computed by every lane: no divergent path)
+        if (values) atomicAdd(&ext[k], v);
     }
 }
 
@@ -63,13 +71,32 @@ __global__ void __launch_bounds__(kBrWarps * 32) evaluate_br_kernel(EvalArgs a)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cfg = blockIdx.x * kBrWarps + warp;
     const int N = s.N, K = s.K, P = s.P, NE = 2 * K, NG = s.gr_bins;
-    // per-warp shared memory: positions [3][Np] | ext [2K] | g(r) counts [NG] (as 32-bit integers)
+    // block-shared tables (first capture: the L1 path of the global-memory tables was the limit, 86 %):
+    // knots [K+4 (+pad)] | rec [nbins][18] | u~ drift R, I and plain R, I [4][2K] | lut; then per warp:
+    // positions [3][Np] | ext [2K] | g(r) counts [NG] (as 32-bit integers)
+    const int nk = (K + 4 + 1) & ~1;
+    double* sk = br_sm;
+    double* srec = sk + nk;
+    double* su = srec + (size_t)s.nbins * kRecStride;
+    unsigned short* slut = reinterpret_cast<unsigned short*>(su + 4 * NE);
+    double* warp_base = su + 4 * NE + ((s.ncell + 3) / 4);
+    for (int i = threadIdx.x; i < K + 4; i += blockDim.x) sk[i] = s.knots[i];
+    for (int i = threadIdx.x; i < s.nbins * kRecStride; i += blockDim.x) srec[i] = s.rec[i];
+    for (int i = threadIdx.x; i < NE; i += blockDim.x)
+    {
+        su[i] = s.ugR[i];
+        su[NE + i] = s.ugI[i];
+        su[2 * NE + i] = s.utR[i];
+        su[3 * NE + i] = s.utI[i];
+    }
+    for (int i = threadIdx.x; i < s.ncell; i += blockDim.x) slut[i] = s.lut[i];
     const int per_warp = 3 * s.Np + NE + (NG + 1) / 2;
-    double* px = br_sm + (size_t)warp * per_warp;
+    double* px = warp_base + (size_t)warp * per_warp;
     double* py = px + s.Np;
     double* pz = py + s.Np;
     double* ext = pz + s.Np;
     unsigned* grc = reinterpret_cast<unsigned*>(ext + NE);
+    __syncthreads();
     if (cfg >= a.n_cfg) return; // whole warps leave together; no block-wide barrier below
 
     const double* gpos = a.pos + (size_t)cfg * 3 * s.Np;
@@ -83,11 +110,14 @@ __global__ void __launch_bounds__(kBrWarps * 32) evaluate_br_kernel(EvalArgs a)
     for (int k = lane; k < NG; k += 32) grc[k] = 0u;
     __syncwarp();
 
-    const double* knots = s.knots;
-    const double* ugRr = s.ugR;
-    const double* ugIr = s.ugI;
-    const double* ulRr = s.utR;
-    const double* ulIr = s.utI;
+    BrEvalTables knots; // (named after its first use below)
+    knots.knots = sk;
+    knots.rec = srec;
+    knots.lut = slut;
+    const double* ugRr = su;
+    const double* ugIr = su + NE;
+    const double* ulRr = su + 2 * NE;
+    const double* ulIr = su + 3 * NE;
     double potential = 0.0, R1 = 0.0, I1 = 0.0, R1I1 = 0.0, R2 = 0.0, I2 = 0.0;
     for (int n = lane; n < N; n += 32)
     {
@@ -104,20 +134,21 @@ __global__ void __launch_bounds__(kBrWarps * 32) evaluate_br_kernel(EvalArgs a)
                 const double grBinInterval = r / s.gr_spacing;
                 atomicAdd(&grc[(int)grBinInterval], 1u);
             }
-            if (r < s.rmax)
             {
-                if (lower) // Gauss potential :326-328
-                {
-                    const double ra = r / s.pot_a;
-                    potential += s.pot_b * exp(-(ra * ra) / 2.0);
-                }
+                // radial basis inside maxDistanceRad (:346-376), Gauss potential for i < n (:326-328).  Every lane runs
+                // the same instructions; a lane whose pair is outside evaluates the last interval and is masked out.
+                const bool inside = r < s.rmax;
+                const double ra = r / s.pot_a;
+                const double pot = s.pot_b * exp(-(ra * ra) / 2.0);
+                if (lower && inside) potential += pot;
                 BrAcc acc = { 0.0, 0.0, 0.0, 0.0 };
-                br_pieces<true>(s, knots, r, 2.0 / r, lower, ext, ugRr, ugIr, ulRr, ulIr, acc);
+                br_pieces<true>(s, knots, inside ? r : s.rmax, 2.0 / r, lower && inside, ext, ugRr, ugIr, ulRr, ulIr, acc);
                 const double ex = vx / r, ey = vy / r, ez = vz / r; // :361-364
-                fRx = fma(acc.gR, ex, fRx); fRy = fma(acc.gR, ey, fRy); fRz = fma(acc.gR, ez, fRz);
-                fIx = fma(acc.gI, ex, fIx); fIy = fma(acc.gI, ey, fIy); fIz = fma(acc.gI, ez, fIz);
-                lR += acc.lR;
-                lI += acc.lI;
+                const double gR = inside ? acc.gR : 0.0, gI = inside ? acc.gI : 0.0;
+                fRx = fma(gR, ex, fRx); fRy = fma(gR, ey, fRy); fRz = fma(gR, ez, fRz);
+                fIx = fma(gI, ex, fIx); fIy = fma(gI, ey, fIy); fIz = fma(gI, ez, fIz);
+                lR += inside ? acc.lR : 0.0;
+                lI += inside ? acc.lI : 0.0;
             }
             // box basis, one coordinate at a time (:378-416); sign = vecrni[a] < 0 ? -1 : 1
             {
@@ -206,7 +237,8 @@ cudaError_t launch_evaluate_br(const EvalArgs& a, cudaStream_t st)
 {
     if (a.n_cfg <= 0) return cudaSuccess;
     const size_t per_warp = (size_t)3 * a.s.Np + 2 * a.s.K + (a.s.gr_bins + 1) / 2;
-    const size_t smem = per_warp * kBrWarps * sizeof(double);
+    const size_t shared = (size_t)((a.s.K + 4 + 1) & ~1) + (size_t)a.s.nbins * kRecStride + 8 * (size_t)a.s.K + (a.s.ncell + 3) / 4;
+    const size_t smem = (shared + per_warp * kBrWarps) * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(evaluate_br_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     evaluate_br_kernel<<<(a.n_cfg + kBrWarps - 1) / kBrWarps, kBrWarps * 32, smem, st>>>(a);
@@ -216,21 +248,24 @@ cudaError_t launch_evaluate_br(const EvalArgs& a, cudaStream_t st)
 // ---- sweep ----------------------------------------------------------------------------------------------------------
 // u(x) on the interval that holds x: planes [c0,c1] | [c2,c3] | [t_lo,t_hi] of nrec double2 each (record nrec - 1 of the
 // radial set is the zero tail beyond maxDistanceRad); lut gives the starting interval, the loop only walks upwards
+template <int STRIDE>
 __device__ __forceinline__ double br_cubic(const double2* __restrict__ c01p, const double2* __restrict__ c23p,
                                            const double2* __restrict__ ttp, const unsigned short* __restrict__ lut, int ncell,
                                            double inv_cell, int first_bin, double x)
 {
-    const int c = (int)(x * inv_cell);
+    // floor(x * inv_cell) through the rounding constant (round-down FMA, integer in the low word): no F2I conversion,
+    // which issues at a quarter of the FP64 rate (profiles/microbench/conv_throughput.cu)
+    const int c = __double2loint(__fma_rd(x, inv_cell, kMagic));
     int j = (int)lut[max(0, min(c, ncell - 1))] - first_bin;
-    double2 tt = ttp[j];
+    double2 tt = ttp[j * STRIDE];
     while (x > tt.y)
     {
         j++;
-        tt = ttp[j];
+        tt = ttp[j * STRIDE];
     }
     const double t = x - tt.x;
-    const double2 c01 = c01p[j];
-    const double2 c23 = c23p[j];
+    const double2 c01 = c01p[j * STRIDE];
+    const double2 c23 = c23p[j * STRIDE];
     return fma(fma(fma(c23.y, t, c23.x), t, c01.y), t, c01.x);
 }
 
@@ -242,17 +277,21 @@ struct BrTables
     double inv_cell;
 };
 
-// pair term of the exponent between two points wrapped into the first cell
+// pair term of the exponent between two points wrapped into the first cell; STRIDE = 8: shared-memory planes replicated
+// eight times, copy c in 16-byte slot c of every 128-byte row, the pointers in t select this lane's copy (a random
+// LDS.128 is served quarter-warp by quarter-warp: each quarter then covers the eight slots once - the cure of sweep.cu;
+// first capture of this kernel: 87 % shared-memory wavefronts, 37 % of them bank conflicts)
+template <int STRIDE>
 __device__ __forceinline__ double br_pair_u(const BrTables& t, double dx, double dy, double dz, double Lhalf)
 {
     const double mx = Lhalf - fabs(fabs(dx) - Lhalf); // |minimum-image component|
     const double my = Lhalf - fabs(fabs(dy) - Lhalf);
     const double mz = Lhalf - fabs(fabs(dz) - Lhalf);
     const double r = sqrt_fast(fma(mz, mz, fma(my, my, mx * mx)));
-    double u = br_cubic(t.r01, t.r23, t.rtt, t.lut, t.ncell, t.inv_cell, t.first_bin, r); // zero beyond maxDistanceRad
-    u += br_cubic(t.b01, t.b23, t.btt, t.lut, t.ncell, t.inv_cell, t.first_bin, mx);
-    u += br_cubic(t.b01, t.b23, t.btt, t.lut, t.ncell, t.inv_cell, t.first_bin, my);
-    u += br_cubic(t.b01, t.b23, t.btt, t.lut, t.ncell, t.inv_cell, t.first_bin, mz);
+    double u = br_cubic<STRIDE>(t.r01, t.r23, t.rtt, t.lut, t.ncell, t.inv_cell, t.first_bin, r); // zero beyond maxDistanceRad
+    u += br_cubic<STRIDE>(t.b01, t.b23, t.btt, t.lut, t.ncell, t.inv_cell, t.first_bin, mx);
+    u += br_cubic<STRIDE>(t.b01, t.b23, t.btt, t.lut, t.ncell, t.inv_cell, t.first_bin, my);
+    u += br_cubic<STRIDE>(t.b01, t.b23, t.btt, t.lut, t.ncell, t.inv_cell, t.first_bin, mz);
     return u;
 }
 
@@ -273,28 +312,32 @@ __device__ __forceinline__ BrTables br_tables_global(const SysDev& s)
     return t;
 }
 
-__global__ void __launch_bounds__(512) sweep_br_kernel(SweepArgs a)
+constexpr int kBrCopies = 8;
+
+__global__ void __launch_bounds__(256, 3) sweep_br_kernel(SweepArgs a)
 {
     extern __shared__ __align__(16) unsigned char br_raw[];
     const SysDev& s = a.s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nrec = s.nbins + 1, Npp = a.npp;
-    // shared memory: six planes of nrec double2 | lut | positions
+    // shared memory: six planes of nrec x 8 copies double2 | lut | positions
     double2* planes = reinterpret_cast<double2*>(br_raw);
-    unsigned short* lut = reinterpret_cast<unsigned short*>(planes + 6 * (size_t)nrec);
+    unsigned short* lut = reinterpret_cast<unsigned short*>(planes + 6 * (size_t)nrec * kBrCopies);
     double* pos_base = reinterpret_cast<double*>(br_raw + a.pos_offset);
     {
         const double2* g = reinterpret_cast<const double2*>(s.cub);
-        for (int i = threadIdx.x; i < 6 * nrec; i += blockDim.x) planes[i] = g[i];
+        for (int i = threadIdx.x; i < 6 * nrec * kBrCopies; i += blockDim.x) planes[i] = g[i / kBrCopies];
         for (int i = threadIdx.x; i < s.ncell; i += blockDim.x) lut[i] = s.lut[i];
     }
+    const int copy = lane & (kBrCopies - 1);
+    const size_t plane = (size_t)nrec * kBrCopies;
     BrTables t;
-    t.r01 = planes;
-    t.r23 = planes + nrec;
-    t.rtt = planes + 2 * nrec;
-    t.b01 = planes + 3 * nrec;
-    t.b23 = planes + 4 * nrec;
-    t.btt = planes + 5 * nrec;
+    t.r01 = planes + copy;
+    t.r23 = planes + plane + copy;
+    t.rtt = planes + 2 * plane + copy;
+    t.b01 = planes + 3 * plane + copy;
+    t.b23 = planes + 4 * plane + copy;
+    t.btt = planes + 5 * plane + copy;
     t.lut = lut;
     t.ncell = s.ncell;
     t.first_bin = s.first_bin;
@@ -343,7 +386,7 @@ __global__ void __launch_bounds__(512) sweep_br_kernel(SweepArgs a)
             {
                 if (i == p) continue;
                 const double xi = px[i], yi = py[i], zi = pz[i];
-                delta += br_pair_u(t, xi - nx, yi - ny, zi - nz, Lhalf) - br_pair_u(t, xi - ox, yi - oy, zi - oz, Lhalf);
+                delta += br_pair_u<kBrCopies>(t, xi - nx, yi - ny, zi - nz, Lhalf) - br_pair_u<kBrCopies>(t, xi - ox, yi - oy, zi - oz, Lhalf);
             }
             delta = warp_sum(delta);
             const double two_delta = 2.0 * delta; // quotient = exp(2 delta) finite and >= U (src/TDVMC.cpp:886-913)
@@ -373,7 +416,7 @@ __global__ void __launch_bounds__(512) sweep_br_kernel(SweepArgs a)
 
 static size_t sweep_br_smem(const SysDev& s, int wpb, int npp, size_t* pos_offset)
 {
-    size_t off = (size_t)6 * (s.nbins + 1) * sizeof(double2) + (size_t)s.ncell * sizeof(unsigned short);
+    size_t off = (size_t)6 * (s.nbins + 1) * kBrCopies * sizeof(double2) + (size_t)s.ncell * sizeof(unsigned short);
     off = (off + 15) & ~(size_t)15;
     *pos_offset = off;
     return off + (size_t)wpb * 3 * npp * sizeof(double);
@@ -417,7 +460,7 @@ __global__ void quotient_br_kernel(QuotientArgs a)
     {
         if (i == p) continue;
         const double xi = wrap_fast(px[i], L, Linv), yi = wrap_fast(py[i], L, Linv), zi = wrap_fast(pz[i], L, Linv);
-        delta += br_pair_u(t, xi - nx, yi - ny, zi - nz, Lhalf) - br_pair_u(t, xi - ox, yi - oy, zi - oz, Lhalf);
+        delta += br_pair_u<1>(t, xi - nx, yi - ny, zi - nz, Lhalf) - br_pair_u<1>(t, xi - ox, yi - oy, zi - oz, Lhalf);
     }
     delta = warp_sum(delta);
     if (lane == 0) a.delta[mv] = delta;

@@ -816,9 +816,9 @@ int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed,
     }
     if (h->kind == TDVMC_SYSTEM_BOX_RADIAL)
     {
-        // one warp per walker, 16 (or as many as fit) walkers per block; the tables are a few KB
+        // one warp per walker, 8 (or as many as fit) walkers per block, three blocks per SM
         h->npp = (h->N + 1) & ~1;
-        h->wpb = 16;
+        h->wpb = 8;
         const SysDev sb = h->sysdev();
         while (h->wpb > 1 && !sweep_br_fits(sb, h->wpb, h->npp, h->smem_optin)) h->wpb /= 2;
         if (!sweep_br_fits(sb, h->wpb, h->npp, h->smem_optin))
@@ -826,7 +826,7 @@ int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed,
             h->error = "system does not fit the sweep kernel's shared memory";
             return bail(-3);
         }
-        h->resident_per_sm = 64;
+        h->resident_per_sm = 24;
         *out = h;
         return 0;
     }
