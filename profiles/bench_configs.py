@@ -32,6 +32,7 @@ CONFIGS = {
     5: ("config/He4He4Na.config", "mixture_he4he4na_equil", "BosonMixtureCluster", 4.0, 20, 1000, (1 << 20) // 3),
     # SURVEY 8(f) rank 4 (not a BASELINE config): the radial + box spline system at its shipped size
     6: ("config/NUBosonsBulkPBBoxAndRadial3D.config", "boxradial_n27_equil", "NUBosonsBulkPBBoxAndRadial", 0.5, 125, 250, (1 << 20) // 27),
+    7: ("config/He4He4Na_4thOrder.config", "mixture4_he4he4na_equil", "BosonMixtureCluster_4thorder", 4.0, 20, 1000, (1 << 20) // 3),
 }
 SAMPLES = 8
 
@@ -48,7 +49,7 @@ def reference_one_core(g, system, mc_step, n_therm, n_init, n_samples):
             arrays[key] = g[key]
     if "NURBS_GRID" in arrays:
         scal["USE_NURBS"] = 1
-        scal["GR_BIN_COUNT"] = 400 if system == "BosonMixtureCluster" else len(g["other_expectation_values"]) - (
+        scal["GR_BIN_COUNT"] = 400 if system.startswith("BosonMixtureCluster") else len(g["other_expectation_values"]) - (
             3 if system == "NUBosonsBulkPBBoxAndRadial" else 9)
     with tempfile.TemporaryDirectory() as td:
         case = os.path.join(td, "case.txt")
