@@ -195,14 +195,46 @@ def reference_main(args, rank):
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons DURING the timed region.  NVML in-process (nvidia_ml_py), one sample every 20 ms plus
+    one at start and one at finish, so that even a half-second region on a busy 8-GPU box has samples (a freshly spawned
+    `nvidia-smi -lms` needs longer than that to print its first line; it stays as the fallback)."""
     FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASON_BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], threading.Event()
+        self.sm, self.mx, self.reasons, self.proc, self.nvml = [], 0.0, set(), None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _sample(self):
+        try:
+            n = self.nvml
+            self.sm.append(float(n.nvmlDeviceGetClockInfo(self.dev, n.NVML_CLOCK_SM)))
+            try:
+                mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.dev))
+            except Exception:
+                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev))
+            for name, bit in self.REASON_BITS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
 
     def run(self):
+        if self.nvml is not None:
+            self._sample()
+            while not self.stop_flag.wait(0.02):
+                self._sample()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
@@ -214,12 +246,15 @@ class ClockSampler(threading.Thread):
             pass
 
     def finish(self):
+        if self.nvml is not None:
+            self._sample()
         self.stop_flag.set()
         try:
-            self.proc.terminate()
+            if self.proc is not None:
+                self.proc.terminate()
         except Exception:
             pass
-        sm, mx, reasons = [], 0.0, set()
+        sm, mx, reasons = list(self.sm), self.mx, set(self.reasons)
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
@@ -230,7 +265,7 @@ class ClockSampler(threading.Thread):
             except (ValueError, IndexError):
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
