@@ -682,6 +682,36 @@ def gen_mixture_4th():
     pack_eval_mixture("mixture4_he4he4na_equil", scal, dict(arr, R=R4), default_moves(R4, 0.0, rng, sigma=2.0), order=4)
 
 
+def gen_more_configs():
+    """Further shipped configs of systems that are already covered, for the paths the BASELINE configs do not reach:
+    config/He3He4Cs.config (BosonMixtureCluster with THREE pair types, N_PARAM = 78, He-3 mass, KTTY He-Cs potential) and
+    config/drop_20.config (HeDrop with 20 atoms: a whole warp per walker in the sweep instead of 8 lanes)."""
+    rng = np.random.default_rng(78)
+    cfg = json.load(open(os.path.join(REF, "config", "He3He4Cs.config")))
+    N, P = int(cfg["N"]), int(cfg["N_PARAM"])
+    uR = np.array(cfg["PARAMS_REAL"], dtype=np.float64)
+    uI = 0.01 * np.sin(0.3 * np.arange(P))
+    scal = dict(N=N, LBOX=float(cfg.get("LBOX", 10.0)), N_PARAM=P, phiR=float(cfg.get("PARAM_PHIR", 0.0)), phiI=0.0, USE_NURBS=1,
+                GR_BIN_COUNT=int(cfg["GR_BIN_COUNT"]))
+    R = np.array([[0.0, 0.0, 0.0], [6.5, 1.0, -1.5], [-2.0, 7.5, 3.0]])
+    arr = dict(R=R, uR=uR, uI=uI, NURBS_GRID=cfg["NURBS_GRID"], PARTICLE_TYPES=cfg["PARTICLE_TYPES"], SYSTEM_PARAMS=cfg["SYSTEM_PARAMS"])
+    mc = run_mc("BosonMixtureCluster", dict(scal, MC_STEP=float(cfg["MC_STEP"]), MC_NSTEPS=1, MC_NTHERMSTEPS=3 * 3000, seed=5), arr)
+    R1 = mc["R_final"].reshape(N, 3)
+    pack_eval_mixture("mixture_he3he4cs_equil", scal, dict(arr, R=R1), default_moves(R1, 0.0, rng, sigma=2.0))
+    cfg = json.load(open(os.path.join(REF, "config", "drop_20.config")))
+    N, P = int(cfg["N"]), int(cfg["N_PARAM"])
+    uR = np.array(cfg["PARAMS_REAL"], dtype=np.float64)
+    uI = 0.01 * np.cos(0.2 * np.arange(P))
+    g = (np.arange(3) - 1.0) * 4.2
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    R = (np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1) + rng.uniform(-0.4, 0.4, (27, 3)))[:N]
+    scal = dict(N=N, LBOX=40.0, N_PARAM=P, phiR=float(cfg.get("PARAM_PHIR", 0.0)), phiI=0.0, GR_BIN_COUNT=200, RHO_BIN_COUNT=200)
+    arr = dict(R=R, uR=uR, uI=uI)
+    mc = run_mc("HeDrop", dict(scal, MC_STEP=float(cfg["MC_STEP"]), MC_NSTEPS=1, MC_NTHERMSTEPS=N * 300, seed=6), arr)
+    R1 = mc["R_final"].reshape(N, 3)
+    pack_eval_hedrop("hedrop_n20_equil", scal, dict(arr, R=R1), default_moves(R1, 0.0, rng, sigma=0.5))
+
+
 def gen_min_image():
     """Reference minimum-image displacement on edge cases + random inputs (Utils.cpp:266-281, 352-382)."""
     rng = np.random.default_rng(99)
@@ -811,7 +841,7 @@ def main():
     if not os.path.exists(HARNESS):
         sys.exit("build the oracle first: make -C oracle/ref_build")
     which = sys.argv[1:] or ["min_image", "bosonsbulk", "bosonsbulk_mc", "bosonsbulk_mc_headline", "nubosonsbulkpb", "nubosonsbulkpb_full", "hebulk", "hedrop",
-                             "mixture", "observables", "he_observables", "mixture_observables", "evolution", "boxradial", "mixture_4th"]
+                             "mixture", "observables", "he_observables", "mixture_observables", "evolution", "boxradial", "mixture_4th", "more_configs"]
     for w in which:
         globals()["gen_" + w]()
 

@@ -734,7 +734,7 @@ def test_stored_sample_reevaluation_he_systems(capi, golden, name):
 # ---------------------------------------------------------------------------------------------------
 # HeDrop (BASELINE configs[0], config/drop_6.config): open boundary, two spline grids, const/linear tails, LJ
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["hedrop_n6_fixture", "hedrop_n6_spread", "hedrop_n6_equil"])
+@pytest.mark.parametrize("name", ["hedrop_n6_fixture", "hedrop_n6_spread", "hedrop_n6_equil", "hedrop_n20_equil"])
 def test_hedrop_fixed_configuration(capi, golden, name):
     g = golden(name)
     spec, h = make_handle(capi, g)
@@ -760,10 +760,11 @@ def test_hedrop_fixed_configuration(capi, golden, name):
     h.close()
 
 
-def test_hedrop_chain_estimators_and_com(capi, golden):
+@pytest.mark.parametrize("name", ["hedrop_n6_fixture", "hedrop_n20_equil"])   # 8 lanes per walker / a whole warp per walker
+def test_hedrop_chain_estimators_and_com(capi, golden, name):
     from oracle_lib import OracleHe
 
-    g = golden("hedrop_n6_fixture")
+    g = golden(name)
     W, seed, mc_step = 8, 5, 0.5
     n_samples, n_therm, n_init = 3, 30, 60
     spec, h = make_handle(capi, g, n_walkers=W, seed=seed, mc_step=mc_step, max_samples=n_samples)
@@ -797,7 +798,8 @@ def test_hedrop_chain_estimators_and_com(capi, golden):
 # ---------------------------------------------------------------------------------------------------
 # BosonMixtureCluster (BASELINE configs[4], config/He4He4Na.config): species, pair types, log term, HFDB / KTTY
 # ---------------------------------------------------------------------------------------------------
-MIX_CASES = ["mixture_he4he4na_fixture", "mixture_he4he4na_compact", "mixture_he4he4na_stretched", "mixture_he4he4na_equil"]
+MIX_CASES = ["mixture_he4he4na_fixture", "mixture_he4he4na_compact", "mixture_he4he4na_stretched", "mixture_he4he4na_equil",
+             "mixture_he3he4cs_equil"]   # config/He3He4Cs.config: three pair types (N_PARAM = 78), He-3, KTTY He-Cs
 # BosonMixtureCluster_4thorder (config/He4He4Na_4thOrder.config): quartic splines, same kernels
 MIX4_CASES = ["mixture4_he4he4na_fixture", "mixture4_he4he4na_compact", "mixture4_he4he4na_stretched", "mixture4_he4he4na_equil"]
 
@@ -828,7 +830,7 @@ def test_mixture_fixed_configuration(capi, golden, name):
     h.close()
 
 
-@pytest.mark.parametrize("name", ["mixture_he4he4na_equil", "mixture4_he4he4na_equil"])
+@pytest.mark.parametrize("name", ["mixture_he4he4na_equil", "mixture4_he4he4na_equil", "mixture_he3he4cs_equil"])
 def test_mixture_chain_estimators_and_com(capi, golden, name):
     from oracle_lib import OracleMix
 

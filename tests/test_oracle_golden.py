@@ -109,7 +109,8 @@ def test_sampler_statistics_match_reference(golden):
     assert np.max(np.abs(est["O"] - O_ref)) / scale < 0.02
 
 
-HE_CASES = ["hebulk_n64_fixture", "hebulk_n64_equil", "hedrop_n6_fixture", "hedrop_n6_spread", "hedrop_n6_equil"]
+HE_CASES = ["hebulk_n64_fixture", "hebulk_n64_equil", "hedrop_n6_fixture", "hedrop_n6_spread", "hedrop_n6_equil",
+            "hedrop_n20_equil"]   # config/drop_20.config
 
 
 @pytest.mark.parametrize("name", HE_CASES)
@@ -163,7 +164,8 @@ def test_hebulk_sampler_statistics_match_reference(golden):
     assert abs(r["accepted"] / r["steps"] - float(g["acceptance"])) < 0.015
 
 
-MIX_CASES = ["mixture_he4he4na_fixture", "mixture_he4he4na_compact", "mixture_he4he4na_stretched", "mixture_he4he4na_equil"]
+MIX_CASES = ["mixture_he4he4na_fixture", "mixture_he4he4na_compact", "mixture_he4he4na_stretched", "mixture_he4he4na_equil",
+             "mixture_he3he4cs_equil"]   # config/He3He4Cs.config: three pair types, KTTY He-Cs
 
 
 MIX4_CASES = ["mixture4_he4he4na_fixture", "mixture4_he4he4na_compact", "mixture4_he4he4na_stretched", "mixture4_he4he4na_equil"]
