@@ -712,6 +712,88 @@ def gen_more_configs():
     pack_eval_hedrop("hedrop_n20_equil", scal, dict(arr, R=R1), default_moves(R1, 0.0, rng, sigma=0.5))
 
 
+def pack_eval_inhcontact(name, scal, arrays, moves):
+    system = "InhContactBosons"
+    x = np.asarray(arrays["R"], np.float64).reshape(-1)
+    with tempfile.TemporaryDirectory() as td:
+        cp, op = os.path.join(td, "case.txt"), os.path.join(td, "out.txt")
+        write_case(cp, system, scal, dict(arrays, R=x), moves)
+        run("eval", cp, op)
+        d = parse_dump(op)
+    R3 = np.zeros((len(x), 3))
+    R3[:, 0] = x
+    out = {"system": np.array(system), "N": np.array(scal["N"]), "DIM": np.array(1), "LBOX": np.array(scal["LBOX"]),
+           "N_PARAM": np.array(scal["N_PARAM"]), "SYSTEM_PARAMS": np.asarray(arrays["SYSTEM_PARAMS"], np.float64),
+           "time": np.array(scal.get("time", 0.0)), "R": R3, "uR": np.asarray(arrays["uR"], np.float64),
+           "uI": np.asarray(arrays["uI"], np.float64), "phiR": np.array(scal.get("phiR", 0.0)), "phiI": np.array(scal.get("phiI", 0.0)),
+           "moves": np.asarray(moves, np.float64).reshape(-1, 4)}
+    for k, v in d.items():
+        out[k] = v
+    spec = tsys.from_golden(out)
+    tab = np.concatenate([d["sD_spf"][:, :, 0], d["sD_pc"][:, :, 0]]).astype(np.longdouble)      # [K1 + K2][N]
+    cg = np.longdouble(-2.0 * float(d["gamma"]) * float(d["node_spacing_pc"]))
+    K1 = spec.extra["n_splines_spf"]
+    for key, u, contact in (("drift_r", out["uR"], cg), ("drift_i", out["uI"], np.longdouble(0))):
+        F = contact * tab[K1]                                   # InhContactBosons.cpp:595-602: real part only
+        for p, row in enumerate(spec.map_rows()):
+            t = np.zeros(tab.shape[1], np.longdouble)
+            for k, f in row:
+                t = t + np.longdouble(f) * tab[k]
+            F = F + np.longdouble(u[p]) * t
+        D = np.zeros((len(x), 3))
+        D[:, 0] = F.astype(np.float64)
+        out[key] = D
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(f"{name}: E_R={float(d['local_energy_r']):.12g} E_I={float(d['local_energy_i']):.12g} "
+          f"exponent={float(d['exponent']):.12g} q={d['move_quotient']}")
+    return d
+
+
+def gen_inhcontact():
+    """InhContactBosons (the one-body WFParts system of config/InhContactBosons.config, the only
+    shipped config of the current format): N = 3, L = 3, N_PARAM = 62 as shipped, with the contact interaction and the
+    lattice potential switched on (the shipped SYSTEM_PARAMS leave both at zero), a square-well variant, and N = 20."""
+    rng = np.random.default_rng(62)
+    cfg = json.loads(re.sub(r"(\d)\.(\s*[,\]\}])", r"\g<1>.0\2",
+                            open(os.path.join(REF, "config", "InhContactBosons.config")).read()))   # "0." literals
+    N, P, L = int(cfg["N"]), int(cfg["N_PARAM"]), float(cfg["LBOX"])
+    k = np.arange(P)
+    uR = np.where(k < P // 2, 0.3 * np.cos(2 * np.pi * k / (P // 2)), -0.4 * np.exp(-((k - P // 2) / 6.0) ** 2))
+    uI = 0.03 * np.sin(0.37 * k)
+
+    def moves1d(x, n=6, sigma=0.5):
+        out = []
+        for _ in range(n):
+            p = int(rng.integers(0, len(x)))
+            out.append([p, x[p] + rng.normal(0, sigma), 0.0, 0.0])
+        return out
+
+    scal = dict(N=N, DIM=1, LBOX=L, N_PARAM=P, phiR=0.02, phiI=0.0, GR_BIN_COUNT=int(cfg["GR_BIN_COUNT"]),
+                RHO_BIN_COUNT=int(cfg["RHO_BIN_COUNT"]), time=0.0)
+    x0 = np.array([-1.1, 0.2, 0.9])
+    arr = dict(R=x0, uR=uR, uI=uI, SYSTEM_PARAMS=[0.0, 10.0, 1.0, 2.0])
+    pack_eval_inhcontact("inhcontact_n3_fixture", scal, arr, moves1d(x0))
+    pack_eval_inhcontact("inhcontact_n3_well", scal, dict(arr, SYSTEM_PARAMS=[0.8, 5.0, 2.0, 1.5]), moves1d(x0))
+    mcs = dict(scal, MC_STEP=float(cfg["MC_STEP"]), MC_NSTEPS=1, MC_NTHERMSTEPS=N * 500, seed=31)
+    mc = run_mc("InhContactBosons", mcs, arr)
+    x1 = mc["R_final"].reshape(N)
+    pack_eval_inhcontact("inhcontact_n3_equil", scal, dict(arr, R=x1), moves1d(x1))
+    mc2 = run_mc("InhContactBosons", dict(mcs, MC_NSTEPS=6000, MC_NTHERMSTEPS=3 * N, MC_NINITIALIZATIONSTEPS=N * 200, seed=32), dict(arr, R=x1))
+    np.savez_compressed(os.path.join(GOLDEN, "inhcontact_n3_mc.npz"), source=np.array("inhcontact_n3_equil"),
+                        MC_STEP=np.array(mcs["MC_STEP"]), MC_NSTEPS=np.array(6000), MC_NTHERMSTEPS=np.array(3 * N),
+                        local_energy_r=mc2["local_energy_r"], local_energy_i=mc2["local_energy_i"],
+                        local_operators=mc2["local_operators"], energy_r_series=mc2["energy_r_series"],
+                        acceptance=np.array(float(mc2["n_acceptances"]) / float(mc2["n_trials"])))
+    print("inhcontact_n3_mc: E_R=%.6f acceptance=%.3f" % (float(mc2["local_energy_r"]), float(mc2["n_acceptances"]) / float(mc2["n_trials"])))
+    N2, L2 = 20, 20.0
+    x2 = (np.arange(N2) + 0.5) * (L2 / N2) - L2 / 2 + rng.uniform(-0.2, 0.2, N2)
+    scal2 = dict(scal, N=N2, LBOX=L2)
+    arr2 = dict(arr, R=x2, SYSTEM_PARAMS=[0.0, 4.0, 1.0, 1.0])
+    mc3 = run_mc("InhContactBosons", dict(scal2, MC_STEP=0.5, MC_NSTEPS=1, MC_NTHERMSTEPS=N2 * 200, seed=33), arr2)
+    x3 = mc3["R_final"].reshape(N2)
+    pack_eval_inhcontact("inhcontact_n20_equil", scal2, dict(arr2, R=x3), moves1d(x3))
+
+
 def gen_min_image():
     """Reference minimum-image displacement on edge cases + random inputs (Utils.cpp:266-281, 352-382)."""
     rng = np.random.default_rng(99)
@@ -841,7 +923,7 @@ def main():
     if not os.path.exists(HARNESS):
         sys.exit("build the oracle first: make -C oracle/ref_build")
     which = sys.argv[1:] or ["min_image", "bosonsbulk", "bosonsbulk_mc", "bosonsbulk_mc_headline", "nubosonsbulkpb", "nubosonsbulkpb_full", "hebulk", "hedrop",
-                             "mixture", "observables", "he_observables", "mixture_observables", "evolution", "boxradial", "mixture_4th", "more_configs"]
+                             "mixture", "observables", "he_observables", "mixture_observables", "evolution", "boxradial", "mixture_4th", "more_configs", "inhcontact"]
     for w in which:
         globals()["gen_" + w]()
 

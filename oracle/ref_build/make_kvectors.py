@@ -26,3 +26,9 @@ with open(os.path.join(out, "kVectors.json"), "w") as f:   # the name HeBulk / H
     json.dump({"data": [sorted(shells[k]) for k in keys]}, f)
 with open(os.path.join(out, "kNorm3D.csv"), "w") as f:
     f.write("\n".join(repr(math.sqrt(k)) for k in keys) + "\n")
+
+# one-dimensional shells for the 1-D systems (InhContactBosons reads kVectors1D.json / kNorm1D.csv, InhContactBosons.cpp:170-171)
+with open(os.path.join(out, "kVectors1D.json"), "w") as f:
+    json.dump({"data": [[[k]] for k in range(1, 401)]}, f)
+with open(os.path.join(out, "kNorm1D.csv"), "w") as f:
+    f.write("\n".join(repr(float(k)) for k in range(1, 401)) + "\n")

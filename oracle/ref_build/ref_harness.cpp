@@ -293,6 +293,26 @@ void DumpSystemInternals(Dump& d)
         d.vec("gr_bin_volumes", s->grBinVolumes);
         d.scalar("gr_node_point_spacing", s->grNodePointSpacing);
     }
+    else if (auto s = dynamic_cast<PhysicalSystems::InhContactBosons*>(sys))
+    {
+        // one-dimensional: single-particle function (spf) on [0, L] + pair correlation (pc) on [0, L/2]
+        auto part = [&](const std::string& q, WFParts::SplinedFunction& f) {
+            d.vec("knots_" + q, f.nodes);
+            d.ten("spline_weights_" + q, f.splineWeights);
+            d.mat("bc_start_" + q, f.bcFactorsStart);
+            d.mat("bc_end_" + q, f.bcFactorsEnd);
+            d.vec("np_" + q, { (double)f.np1, (double)f.np2, (double)f.np3, (double)f.numberOfSplines });
+            d.scalar("node_spacing_" + q, f.nodeSpacing);
+            d.vec("spline_sums_" + q, f.splineSums);
+            d.ten("sD_" + q, f.splineSumsD);
+            d.mat("sD2_" + q, f.splineSumsD2);
+        };
+        part("spf", s->spf);
+        part("pc", s->pc);
+        d.scalar("gamma", s->gamma);
+        d.scalar("max_distance", s->maxDistance);
+        d.vec("other_local_operators", s->otherLocalOperators);
+    }
     else if (auto s = dynamic_cast<PhysicalSystems::BosonMixtureCluster*>(sys))
     {
         DumpMixtureInternals(d, s);

@@ -123,6 +123,40 @@ int64_t oracle_br_sample_walker(const oracle_br* s, double* R, const double* uR,
                                 uint32_t walker, uint64_t* step_counter, int n_init, int n_samples, int n_therm, double mc_step,
                                 double* est, double* sample_rows);
 
+/* ------------------------------------------------------------------------------------------------
+ * InhContactBosons (tdvmc_oracle_inh.c): one-dimensional, single-particle + pair-correlation splines
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct oracle_inh
+{
+    int32_t n_particles, n_params, n_splines_spf, n_splines_pc; /* K1, K2 */
+    double lbox;
+    double r_max;      /* maxDistance = pc.nodes[size - 4] (InhContactBosons.cpp:100) */
+    double h_pc;       /* pc.nodeSpacing */
+    double gamma;      /* contact strength (:25-29) */
+    double pot_range, pot_strength; /* square well, SYSTEM_PARAMS[0], [1] (:327-334) */
+    double ext_k, ext_v0;           /* lattice potential k^2 V0 sin^2(k x), SYSTEM_PARAMS[2], [3] (:448-467) */
+    double hbar2_2m;
+    const double* knots_spf;   /* [K1 + 4] */
+    const double* weights_spf; /* [K1][4][4] */
+    const double* knots_pc;    /* [K2 + 4] */
+    const double* weights_pc;  /* [K2][4][4] */
+    const int32_t* map_ptr;    /* CSR of RefreshLocalOperators (:208-247) over ext = [ss_spf | ss_pc] */
+    const int32_t* map_col;
+    const double* map_val;
+} oracle_inh;
+void oracle_inh_values(const oracle_inh* s, const double* R, double* ext);
+void oracle_inh_operators(const oracle_inh* s, const double* ext, double* O);
+double oracle_inh_exponent(const oracle_inh* s, const double* ext, const double* uR);
+void oracle_inh_expectation(const oracle_inh* s, const double* R, double wf, double exponent, const double* uR, const double* uI,
+                            double* e_r, double* e_i, double* other, double* drift_r, double* drift_i, double* tabD, double* tabD2);
+double oracle_inh_quotient(const oracle_inh* s, const double* R, int particle, const double* old_pos, const double* ext,
+                           double exponent, const double* uR, double* ext_new, double* exponent_new);
+int64_t oracle_inh_sweep(const oracle_inh* s, double* R, double* ext, double* exponent, const double* uR, uint64_t seed,
+                         uint32_t walker, uint64_t first_step, int64_t n_steps, double mc_step);
+int64_t oracle_inh_sample_walker(const oracle_inh* s, double* R, const double* uR, const double* uI, double phiR, uint64_t seed,
+                                 uint32_t walker, uint64_t* step_counter, int n_init, int n_samples, int n_therm, double mc_step,
+                                 double* est, double* sample_rows);
+
 #ifdef __cplusplus
 }
 #endif

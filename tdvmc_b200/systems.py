@@ -13,6 +13,8 @@ The five systems of the BASELINE configs:
   * ``BosonMixtureCluster``  src/PhysicalSystems/BosonMixtureCluster.cpp:58-346 (config 5)
 and, widening per SURVEY.md section 8(f) rank 4:
   * ``NUBosonsBulkPBBoxAndRadial``  src/PhysicalSystems/NUBosonsBulkPBBoxAndRadial.cpp:36-191 (the "radial+box splines" system)
+  * ``BosonMixtureCluster_4thorder`` src/PhysicalSystems/BosonMixtureCluster_4thorder.cpp (quartic splines)
+  * ``InhContactBosons``            src/PhysicalSystems/InhContactBosons.cpp:64-247 (1-D, one-body + pair splines)
 """
 from dataclasses import dataclass, field
 
@@ -27,6 +29,7 @@ KIND_SPLINE_TABLE = 0   # BosonsBulk, NUBosonsBulkPB: monomial spline table + bo
 KIND_HE_BULK = 1        # HeBulk: McMillan core + uniform B-splines in the local coordinate + Aziz potential
 KIND_HE_DROP = 2        # HeDrop: open boundary, McMillan core, two uniform grids, const + linear tails, LJ potential
 KIND_MIXTURE = 3        # BosonMixtureCluster: species, per-pair-type spline tables + McMillan/const/linear/log, pair potentials
+KIND_INH_CONTACT = 5    # InhContactBosons: ONE-dimensional, single-particle spline function + pair-correlation splines
 KIND_BOX_RADIAL = 4     # NUBosonsBulkPBBoxAndRadial: radial splines in r_ij + "box" splines in |x_ij|, |y_ij|, |z_ij|, Gauss potential
 
 POT_HFDB_HE_HE, POT_KTTY_HE_NA, POT_KTTY_HE_CS = 0, 1, 2
@@ -188,6 +191,40 @@ def nu_bosons_bulk_pb_box_and_radial(n_particles, lbox, n_params, nurbs_grid, sy
                       tail_param=-1, kind=KIND_BOX_RADIAL, n_ext=2 * K,
                       extra=dict(n_splines=K, gr_bins=int(gr_bin_count), half=half, gr_spacing=half / float(gr_bin_count),
                                  grad_swap=(K - 1, 2 * K - 1, PR - 1)))
+
+
+def inh_contact_bosons(n_particles, lbox, n_params, system_params, spf, pc):
+    """``InhContactBosons`` (InhContactBosons.cpp:64-247), one-dimensional.  ``spf`` / ``pc``: dicts with the reference's
+    ``knots``, ``weights`` (SplineFactory::GetWeights3), ``bc_start``, ``bc_end`` (SetBoundaryConditions3_1D_*), ``np``
+    = (np1, np2, np3, numberOfSplines) and ``node_spacing`` of the single-particle function (argument: the coordinate
+    shifted into [0, L]) and of the pair correlation (argument: minimum-image distance <= L/2).  Extended sums
+    ``[ss_spf | ss_pc]``; map of ``RefreshLocalOperators`` (:208-247): the first three single-particle operators take the
+    first AND the last three splines (periodicity), the pair part has start and end boundary rows.  The exponent carries
+    the parameter-free contact term ``-2 gamma h_pc ss_pc[0]`` (:764), ``gamma = SYSTEM_PARAMS[1] * SYSTEM_PARAMS[2] * pi``
+    if ``SYSTEM_PARAMS[0] == 0`` (:25-29).  Coordinates travel as R[N][3] with the coordinate in component 0."""
+    sp = np.asarray(system_params, dtype=np.float64)
+    if len(sp) != 4:
+        raise ValueError("InhContactBosons: the four-entry SYSTEM_PARAMS {range, strength, k, V0} is supported")
+    k1, k2 = int(spf["np"][3]), int(pc["np"][3])
+    s1, s2, s3 = (int(x) for x in spf["np"][:3])
+    p1, p2, p3 = (int(x) for x in pc["np"][:3])
+    if n_params != s3 + p3:
+        raise ValueError(f"InhContactBosons needs N_PARAM = {s3 + p3}, got {n_params}")
+    bs, be = np.asarray(spf["bc_start"], np.float64), np.asarray(spf["bc_end"], np.float64)
+    rows = [[(j, bs[i][j]) for j in range(3)] + [(k1 - 3 + j, be[i][j]) for j in range(3)] for i in range(s1)]
+    rows += [[(3 + (i - s1), 1.0)] for i in range(s1, s2)]
+    bs, be = np.asarray(pc["bc_start"], np.float64), np.asarray(pc["bc_end"], np.float64)
+    rows += [[(k1 + j, bs[i][j]) for j in range(3)] for i in range(p1)]
+    rows += [[(k1 + 3 + (i - p1), 1.0)] for i in range(p1, p2)]
+    rows += [[(k1 + k2 - 3 + j, be[i][j]) for j in range(3)] for i in range(p3 - p2)]
+    ptr, col, val = _csr(rows)
+    gamma = (float(sp[1]) if sp[0] == 0.0 else 0.0) * (float(sp[2]) * np.pi)   # gamma *= potentialK * kf (:29)
+    knots = np.concatenate([np.asarray(spf["knots"], np.float64), np.asarray(pc["knots"], np.float64)])
+    weights = np.concatenate([np.asarray(spf["weights"], np.float64).reshape(k1, 4, 4), np.asarray(pc["weights"], np.float64).reshape(k2, 4, 4)])
+    return SystemSpec("InhContactBosons", n_particles, n_params, float(lbox), knots, np.ascontiguousarray(weights), ptr, col, val,
+                      PAIR_RULE_CUT, sp, n_other=9, dim=1, tail_param=-1, kind=KIND_INH_CONTACT, n_ext=k1 + k2,
+                      extra=dict(n_splines=k1 + k2, n_splines_spf=k1, n_splines_pc=k2, h_pc=float(pc["node_spacing"]), gamma=gamma,
+                                 r_max=float(np.asarray(pc["knots"])[-4])))
 
 
 def he_bulk(n_particles, lbox, n_params):
@@ -364,6 +401,13 @@ def from_golden(g):
     elif name == "NUBosonsBulkPB":
         spec = nu_bosons_bulk_pb(N, L, P, g["NURBS_GRID"], g["SYSTEM_PARAMS"], weights=g["spline_weights"],
                                  gr_bin_count=len(g["other_expectation_values"]) - 9)
+    elif name == "InhContactBosons":
+        part = lambda q: dict(knots=g["knots_" + q], weights=g["spline_weights_" + q], bc_start=g["bc_start_" + q],
+                              bc_end=g["bc_end_" + q], np=g["np_" + q], node_spacing=float(g["node_spacing_" + q]))
+        spec = inh_contact_bosons(N, L, P, g["SYSTEM_PARAMS"], part("spf"), part("pc"))
+        if spec.extra["gamma"] != float(g["gamma"]) or spec.r_max != float(g["max_distance"]):
+            raise AssertionError("InhContactBosons set-up differs from the reference dump")
+        return spec
     elif name == "NUBosonsBulkPBBoxAndRadial":
         spec = nu_bosons_bulk_pb_box_and_radial(N, L, P, g["NURBS_GRID"], g["SYSTEM_PARAMS"], weights=g["spline_weights"],
                                                 gr_bin_count=len(g["other_expectation_values"]) - 3)

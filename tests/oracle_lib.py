@@ -41,6 +41,14 @@ class OracleBRStruct(C.Structure):
                 ("map_val", dp)]
 
 
+class OracleInhStruct(C.Structure):
+    _fields_ = [("n_particles", C.c_int32), ("n_params", C.c_int32), ("n_splines_spf", C.c_int32), ("n_splines_pc", C.c_int32),
+                ("lbox", C.c_double), ("r_max", C.c_double), ("h_pc", C.c_double), ("gamma", C.c_double), ("pot_range", C.c_double),
+                ("pot_strength", C.c_double), ("ext_k", C.c_double), ("ext_v0", C.c_double), ("hbar2_2m", C.c_double),
+                ("knots_spf", dp), ("weights_spf", dp), ("knots_pc", dp), ("weights_pc", dp), ("map_ptr", ip), ("map_col", ip),
+                ("map_val", dp)]
+
+
 def lib():
     global _LIB
     if _LIB is None:
@@ -62,6 +70,10 @@ def lib():
         L.oracle_he_quotient.restype = C.c_double
         L.oracle_he_sweep.restype = C.c_int64
         L.oracle_he_sample_walker.restype = C.c_int64
+        L.oracle_inh_exponent.restype = C.c_double
+        L.oracle_inh_quotient.restype = C.c_double
+        L.oracle_inh_sweep.restype = C.c_int64
+        L.oracle_inh_sample_walker.restype = C.c_int64
         L.oracle_br_exponent.restype = C.c_double
         L.oracle_br_quotient.restype = C.c_double
         L.oracle_br_sweep.restype = C.c_int64
@@ -381,6 +393,95 @@ class OracleBR:
         return Oracle.unpack_est(self, est, n)
 
 
+class OracleInh:
+    """InhContactBosons restatement (oracle/tdvmc_oracle_inh.c), one-dimensional; R is [N][3] with the coordinate in
+    component 0; ext = [ss_spf | ss_pc]."""
+
+    def __init__(self, spec, time=0.0):
+        self.spec = spec
+        e = spec.extra
+        k1, k2 = e["n_splines_spf"], e["n_splines_pc"]
+        kn = np.ascontiguousarray(spec.knots, np.float64)
+        w = np.ascontiguousarray(spec.weights, np.float64).reshape(-1)
+        self._keep = [np.ascontiguousarray(kn[:k1 + 4]), np.ascontiguousarray(w[:k1 * 16]), np.ascontiguousarray(kn[k1 + 4:]),
+                      np.ascontiguousarray(w[k1 * 16:]), np.ascontiguousarray(spec.map_ptr, np.int32),
+                      np.ascontiguousarray(spec.map_col, np.int32), np.ascontiguousarray(spec.map_val, np.float64)]
+        k = self._keep
+        sp = spec.system_params
+        self.sys = OracleInhStruct(spec.n_particles, spec.n_params, k1, k2, spec.lbox, spec.r_max, e["h_pc"], e["gamma"],
+                                   float(sp[0]), float(sp[1]), float(sp[2]), float(sp[3]), spec.hbar2_2m, _d(k[0]), _d(k[1]),
+                                   _d(k[2]), _d(k[3]), k[4].ctypes.data_as(ip), k[5].ctypes.data_as(ip), _d(k[6]))
+        self.N, self.P, self.NE, self.NO = spec.n_particles, spec.n_params, k1 + k2, 9
+
+    def values(self, R):
+        ext = np.zeros(self.NE)
+        lib().oracle_inh_values(C.byref(self.sys), _d(np.ascontiguousarray(R, np.float64)), _d(ext))
+        return ext
+
+    def operators(self, ext):
+        O = np.zeros(self.P)
+        lib().oracle_inh_operators(C.byref(self.sys), _d(np.ascontiguousarray(ext)), _d(O))
+        return O
+
+    def exponent(self, ext, uR):
+        return lib().oracle_inh_exponent(C.byref(self.sys), _d(np.ascontiguousarray(ext)), _d(np.ascontiguousarray(uR, np.float64)))
+
+    def evaluate(self, R, uR, uI, phiR=0.0):
+        R = np.ascontiguousarray(R, np.float64)
+        uR = np.ascontiguousarray(uR, np.float64)
+        uI = np.ascontiguousarray(uI, np.float64)
+        ext = self.values(R)
+        ex = self.exponent(ext, uR)
+        er, ei = C.c_double(0), C.c_double(0)
+        other = np.zeros(self.NO)
+        dr, di = np.zeros((self.N, 3)), np.zeros((self.N, 3))
+        tD, tD2 = np.zeros((self.NE, self.N)), np.zeros((self.NE, self.N))
+        lib().oracle_inh_expectation(C.byref(self.sys), _d(R), C.c_double(np.exp(ex + phiR)), C.c_double(ex), _d(uR), _d(uI),
+                                     C.byref(er), C.byref(ei), _d(other), _d(dr), _d(di), _d(tD), _d(tD2))
+        return dict(ext=ext, O=self.operators(ext), exponent=ex, e_r=er.value, e_i=ei.value, other=other, drift_r=dr,
+                    drift_i=di, tabD=tD, tabD2=tD2)
+
+    def quotient(self, R, particle, new_pos, uR):
+        R = np.array(R, np.float64)
+        uR = np.ascontiguousarray(uR, np.float64)
+        ext = self.values(R)
+        ex = self.exponent(ext, uR)
+        old = R[particle].copy()
+        R[particle] = new_pos
+        ext_new = np.zeros(self.NE)
+        en = C.c_double(0)
+        q = lib().oracle_inh_quotient(C.byref(self.sys), _d(R), int(particle), _d(old), _d(ext), C.c_double(ex), _d(uR),
+                                      _d(ext_new), C.byref(en))
+        return q, en.value, ex
+
+    def sweep(self, R, uR, seed, walker, first_step, n_steps, mc_step):
+        R = np.array(R, np.float64)
+        uR = np.ascontiguousarray(uR, np.float64)
+        ext = self.values(R)
+        ex = C.c_double(self.exponent(ext, uR))
+        acc = lib().oracle_inh_sweep(C.byref(self.sys), _d(R), _d(ext), C.byref(ex), _d(uR), C.c_uint64(seed), C.c_uint32(walker),
+                                     C.c_uint64(first_step), C.c_int64(n_steps), C.c_double(mc_step))
+        return R, int(acc)
+
+    def est_size(self):
+        return self.P * self.P + 3 * self.P + 2 + self.NO
+
+    def sample_walker(self, R, uR, uI, phiR, seed, walker, step0, n_init, n_samples, n_therm, mc_step, est=None):
+        R = np.array(R, np.float64)
+        if est is None:
+            est = np.zeros(self.est_size())
+        rows = np.zeros((n_samples, self.P + 2))
+        sc = C.c_uint64(step0)
+        acc = lib().oracle_inh_sample_walker(C.byref(self.sys), _d(R), _d(np.ascontiguousarray(uR, np.float64)),
+                                             _d(np.ascontiguousarray(uI, np.float64)), C.c_double(phiR), C.c_uint64(seed),
+                                             C.c_uint32(walker), C.byref(sc), n_init, n_samples, n_therm, C.c_double(mc_step),
+                                             _d(est), _d(rows))
+        return dict(R=R, est=est, rows=rows, accepted=int(acc), steps=sc.value)
+
+    def unpack_est(self, est, n):
+        return Oracle.unpack_est(self, est, n)
+
+
 class OracleMix:
     """BosonMixtureCluster restatement (oracle/tdvmc_oracle_mix.c) with numpy in/out."""
 
@@ -512,4 +613,6 @@ def make_oracle(spec, time=0.0):
         return OracleMix(spec, time)
     if spec.kind == systems.KIND_BOX_RADIAL:
         return OracleBR(spec, time)
+    if spec.kind == systems.KIND_INH_CONTACT:
+        return OracleInh(spec, time)
     return Oracle(spec, time) if spec.kind == systems.KIND_SPLINE_TABLE else OracleHe(spec, time)

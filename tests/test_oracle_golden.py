@@ -329,3 +329,62 @@ def test_boxradial_sampler_statistics_match_reference(golden):
     assert abs(r["accepted"] / r["steps"] - float(g["acceptance"])) < 0.01
     est = o.unpack_est(r["est"], n_samples)
     assert np.max(np.abs(est["O"] - g["local_operators"])) / np.abs(g["local_operators"]).max() < 0.02
+
+
+# ---------------------------------------------------------------------------------------------------
+# InhContactBosons: one-dimensional, single-particle function + pair correlation
+# ---------------------------------------------------------------------------------------------------
+INH_CASES = ["inhcontact_n3_fixture", "inhcontact_n3_well", "inhcontact_n3_equil", "inhcontact_n20_equil"]
+
+
+@pytest.mark.parametrize("name", INH_CASES)
+def test_inhcontact_fixed_configuration_matches_reference(golden, name):
+    from oracle_lib import OracleInh
+
+    g = golden(name)
+    spec = systems.from_golden(g)     # checks gamma and maxDistance against the reference object
+    o = OracleInh(spec)
+    K1 = spec.extra["n_splines_spf"]
+    r = o.evaluate(g["R"], g["uR"], g["uI"], float(g["phiR"]))
+    assert rel(r["ext"][:K1], g["spline_sums_spf"]) < 1e-13 and rel(r["ext"][K1:], g["spline_sums_pc"]) < 1e-13
+    assert np.array_equal(r["tabD"][:K1], g["sD_spf"][:, :, 0]) and np.array_equal(r["tabD"][K1:], g["sD_pc"][:, :, 0])
+    assert np.array_equal(r["tabD2"][:K1], g["sD2_spf"]) and np.array_equal(r["tabD2"][K1:], g["sD2_pc"])
+    assert rel(r["O"], g["local_operators"]) < 1e-13
+    assert abs(r["exponent"] - float(g["exponent"])) < 1e-12 * max(abs(float(g["exponent"])), 1.0)
+    assert abs(r["e_r"] - float(g["local_energy_r"])) < 1e-12 * abs(float(g["local_energy_r"]))
+    assert abs(r["e_i"] - float(g["local_energy_i"])) < 1e-12 * abs(float(g["local_energy_i"]))
+    assert rel(r["other"], g["other_expectation_values"]) < 1e-12
+    assert rel(r["drift_r"], g["drift_r"]) < RTOL and rel(r["drift_i"], g["drift_i"]) < RTOL
+    for m, q_ref, en_ref in zip(g["moves"], g["move_quotient"], g["move_exponent_new"]):
+        q, en, _ = o.quotient(g["R"], int(m[0]), m[1:4], g["uR"])
+        assert abs(en - en_ref) < 1e-12 * max(abs(en_ref), 1.0)
+        assert abs(q - q_ref) <= 1e-9 * abs(q_ref)
+
+
+def test_inhcontact_sampler_statistics_match_reference(golden):
+    from oracle_lib import OracleInh
+
+    g = golden("inhcontact_n3_mc")
+    src = golden(str(g["source"]))
+    spec = systems.from_golden(src)
+    o = OracleInh(spec)
+    n_samples = 6000
+    r = o.sample_walker(src["R"], src["uR"], src["uI"], float(src["phiR"]), seed=77, walker=0, step0=0, n_init=600,
+                        n_samples=n_samples, n_therm=int(g["MC_NTHERMSTEPS"]), mc_step=float(g["MC_STEP"]))
+
+    def blocked(x, nb=20):
+        b = x[:len(x) // nb * nb].reshape(nb, -1).mean(axis=1)
+        return b.mean(), b.std(ddof=1) / np.sqrt(nb)
+
+    m1, s1 = blocked(r["rows"][:, spec.n_params])
+    m2, s2 = blocked(g["energy_r_series"])
+    assert abs(m1 - m2) < 4.0 * np.hypot(s1, s2), (m1, s1, m2, s2)
+    assert abs(r["accepted"] / r["steps"] - float(g["acceptance"])) < 0.015
+    # <O_k>: three particles give noisy operators - compare each with its own blocked standard error (both runs have
+    # the same number of samples, hence sqrt(2)), 5 sigma
+    rows = r["rows"][:, :spec.n_params]
+    nb = 20
+    blocks = rows[:len(rows) // nb * nb].reshape(nb, -1, spec.n_params).mean(axis=1)
+    sem = blocks.std(axis=0, ddof=1) / np.sqrt(nb)
+    dev = np.abs(rows.mean(axis=0) - g["local_operators"]) / (np.sqrt(2.0) * np.maximum(sem, 1e-6))
+    assert dev.max() < 5.0, dev.max()
