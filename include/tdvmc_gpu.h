@@ -53,7 +53,14 @@ enum tdvmc_system_kind
      * ordered [ssRad | ss], map = RefreshLocalOperators (:193-211); Gauss pair potential b exp(-(r/a)^2/2) from
      * system_params {a, b [, t, a2, b2]}; other[0..2] = {kinetic, potential, wf}, other[3..] = g(r) bins on
      * (0, lbox/2) weighted by 1/shell volume (n_other = 3 + GR_BIN_COUNT) */
-    TDVMC_SYSTEM_BOX_RADIAL = 4
+    TDVMC_SYSTEM_BOX_RADIAL = 4,
+    /* InhContactBosons (InhContactBosons.cpp): ONE-dimensional (dim = 1; positions still travel as [N][3], coordinate in
+     * component 0), periodic; a single-particle spline function of the coordinate shifted into [0, lbox] and a
+     * pair-correlation spline function of the minimum-image distance.  knots = [spf.nodes | pc.nodes], spline_weights =
+     * [spf.splineWeights | pc.splineWeights], n_splines = K1 + K2 with K1 in n_splines_first, n_ext = K1 + K2, map =
+     * RefreshLocalOperators (:208-247); system_params = the config's four {range, strength, k, V0} (square well or, with
+     * range 0, contact strength gamma = strength k pi, :25-29; lattice potential, :448-467); n_other = 9; n_particles <= 32 */
+    TDVMC_SYSTEM_INH_CONTACT = 5
 };
 
 /* Per-pair-type data of BosonMixtureCluster::InitSystem (BosonMixtureCluster.cpp:104-346), as data. */
@@ -103,7 +110,7 @@ typedef struct tdvmc_system_desc
     /* Columns of the map: the K spline sums plus analytic basis sums.  He family: n_ext = K + 3, columns K, K+1, K+2 are
      * the McMillan, constant and linear sums (HeBulk.cpp:376-383, HeDrop.cpp:609-626).  Spline-table systems: n_ext = K. */
     int32_t n_ext;
-    int32_t reserved;
+    int32_t n_splines_first;   /* TDVMC_SYSTEM_INH_CONTACT: K1, the splines of the single-particle function; else 0 */
     const double* map_const;   /* [N_PARAM] constant part of O_p (HeBulk.cpp:383: 1.0 + ...), NULL = zeros */
     const double* grad_const;  /* [N_PARAM] constant added to every gradient component of parameter p
                                   (the literal 1 of HeBulk.cpp:351), NULL = zeros */

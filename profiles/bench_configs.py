@@ -33,6 +33,7 @@ CONFIGS = {
     # SURVEY 8(f) rank 4 (not a BASELINE config): the radial + box spline system at its shipped size
     6: ("config/NUBosonsBulkPBBoxAndRadial3D.config", "boxradial_n27_equil", "NUBosonsBulkPBBoxAndRadial", 0.5, 125, 250, (1 << 20) // 27),
     7: ("config/He4He4Na_4thOrder.config", "mixture4_he4he4na_equil", "BosonMixtureCluster_4thorder", 4.0, 20, 1000, (1 << 20) // 3),
+    8: ("config/InhContactBosons.config", "inhcontact_n3_equil", "InhContactBosons", 0.5, 100, 1000, (1 << 20) // 3),
 }
 SAMPLES = 8
 
@@ -41,9 +42,12 @@ def reference_one_core(g, system, mc_step, n_therm, n_init, n_samples):
     """The unmodified reference, one walker on one core, same counts; returns (proposals/s, samples/s) or None."""
     if not os.path.exists(HARNESS):
         return None
-    scal = dict(N=int(g["N"]), DIM=3, LBOX=float(g["LBOX"]), N_PARAM=int(g["N_PARAM"]), MC_STEP=mc_step, MC_NSTEPS=n_samples,
+    dim = int(g["DIM"]) if "DIM" in g.files else 3
+    scal = dict(N=int(g["N"]), DIM=dim, LBOX=float(g["LBOX"]), N_PARAM=int(g["N_PARAM"]), MC_STEP=mc_step, MC_NSTEPS=n_samples,
                 MC_NTHERMSTEPS=n_therm, MC_NINITIALIZATIONSTEPS=n_init, seed=1, phiR=float(g["phiR"]), phiI=float(g["phiI"]))
-    arrays = dict(R=g["R"], uR=g["uR"], uI=g["uI"])
+    arrays = dict(R=g["R"][:, :dim], uR=g["uR"], uI=g["uI"])
+    if system == "InhContactBosons":
+        scal.update(GR_BIN_COUNT=50, RHO_BIN_COUNT=50)
     for key in ("SYSTEM_PARAMS", "NURBS_GRID", "PARTICLE_TYPES"):
         if key in g.files and np.size(g[key]):
             arrays[key] = g[key]

@@ -28,7 +28,7 @@ class SystemDesc(C.Structure):
                 ("n_splines", C.c_int32), ("pair_rule", C.c_int32), ("tail_param", C.c_int32), ("n_other", C.c_int32),
                 ("lbox", C.c_double), ("hbar2_2m", C.c_double), ("knots", dp), ("spline_weights", dp), ("map_ptr", ip),
                 ("map_col", ip), ("map_val", dp), ("system_params", dp), ("n_system_params", C.c_int32),
-                ("system_kind", C.c_int32), ("n_ext", C.c_int32), ("reserved", C.c_int32), ("map_const", dp),
+                ("system_kind", C.c_int32), ("n_ext", C.c_int32), ("n_splines_first", C.c_int32), ("map_const", dp),
                 ("grad_const", dp), ("mixture", C.POINTER(MixtureDesc))]
 
 
@@ -173,7 +173,7 @@ class Handle:
         sd = SystemDesc(C.sizeof(SystemDesc), spec.n_particles, spec.dim, spec.n_params, spec.n_splines, spec.pair_rule,
                         spec.tail_param, spec.n_other, spec.lbox, spec.hbar2_2m, _d(k["knots"]), _d(k["w"]),
                         k["mp"].ctypes.data_as(ip), k["mc"].ctypes.data_as(ip), _d(k["mv"]), _d(k["sp"]), len(k["sp"]),
-                        spec.kind, spec.n_ext, 0, _d(k["mk"]), _d(k["gk"]), mix)
+                        spec.kind, spec.n_ext, int(spec.extra.get("n_splines_spf", 0)), _d(k["mk"]), _d(k["gk"]), mix)
         ed = EnsembleDesc(C.sizeof(EnsembleDesc), device, self.W, first_walker, max_samples, int(keep_sample_positions),
                           seed, mc_step)
         h = _VP()

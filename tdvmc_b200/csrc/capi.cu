@@ -355,6 +355,24 @@ int build_static_tables(tdvmc_gpu_handle* h)
         return 0;
     }
     CK(upload(h->d_map_const, h->map_const, h->stream));
+    if (h->kind == TDVMC_SYSTEM_INH_CONTACT)
+    {
+        // two knot vectors and the raw spline table; interval lookup is a binary search in the kernels (GetBinIndex)
+        h->periodic = 1;
+        h->use_phi = 1;
+        h->first_bin = 3;
+        h->nbins = K - 6;
+        h->uniform = 0;
+        h->ncell = 1;
+        h->h = 1.0;
+        CK(upload(h->d_knots, h->knots, h->stream));
+        CK(upload(h->d_rec, h->weights, h->stream));
+        CK(upload(h->d_map_ptr, h->map_ptr, h->stream));
+        CK(upload(h->d_map_col, h->map_col, h->stream));
+        CK(upload(h->d_map_val, h->map_val, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
     const std::vector<double>& t = h->knots;
     // first interval a distance can fall in: knots[first_bin] <= 0 < knots[first_bin + 1]
     int fb = 0;
@@ -460,6 +478,48 @@ int build_param_tables(tdvmc_gpu_handle* h)
         CK(upload(h->d_utR, utR, h->stream));
         CK(upload(h->d_utI, utI, h->stream));
         CK(upload(h->d_mix_cub, mc, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    if (h->kind == TDVMC_SYSTEM_INH_CONTACT)
+    {
+        // contact term of the exponent, -2 gamma h_pc ss_pc[0] (InhContactBosons.cpp:764, gradient / Laplacian :595-602):
+        // a parameter-free coefficient of the first pair spline, real part only
+        const int K1 = h->n_short, K2 = K - K1;
+        const double* k1 = h->knots.data();
+        const double* k2 = k1 + K1 + 4;
+        const double gamma = (h->sys_params[0] == 0.0 ? h->sys_params[1] : 0.0) * (h->sys_params[2] * M_PI); // :25-29
+        const double h_pc = k2[4] - k2[3]; // pc.nodeSpacing of the default grid (:91-95)
+        h->u_const = -2.0 * gamma * h_pc;
+        h->u_core = gamma;
+        utR[K1] += h->u_const;
+        std::vector<double> cub((size_t)(K - 6) * 6, 0.0);
+        for (int part = 0; part < 2; part++)
+        {
+            const int Kp = part ? K2 : K1, off = part ? K1 : 0;
+            const double* kn = part ? k2 : k1;
+            double* c = cub.data() + (size_t)(part ? (K1 - 3) * 6 : 0);
+            for (int b = 3; b < Kp; b++)
+            {
+                long double C[4] = { 0, 0, 0, 0 };
+                for (int p = 0; p < 4; p++)
+                    for (int q = 0; q < 4; q++)
+                        C[q] += (long double)utR[off + b - p] * (long double)h->weights[((size_t)(off + b - p) * 4 + p) * 4 + q];
+                const long double t0 = kn[b];
+                double* o = c + (size_t)(b - 3) * 6;
+                o[0] = (double)(C[0] + t0 * (C[1] + t0 * (C[2] + t0 * C[3])));
+                o[1] = (double)(C[1] + t0 * (2 * C[2] + 3 * t0 * C[3]));
+                o[2] = (double)(C[2] + 3 * t0 * C[3]);
+                o[3] = (double)C[3];
+                o[4] = kn[b];
+                o[5] = kn[b + 1];
+            }
+        }
+        CK(upload(h->d_uR, h->uR, h->stream));
+        CK(upload(h->d_uI, h->uI, h->stream));
+        CK(upload(h->d_utR, utR, h->stream));
+        CK(upload(h->d_utI, utI, h->stream));
+        CK(upload(h->d_cub, cub, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         return 0;
     }
@@ -604,6 +664,16 @@ SysDev tdvmc_gpu_handle::sysdev() const
         }
     if (kind == TDVMC_SYSTEM_SPLINE_TABLE || kind == TDVMC_SYSTEM_BOX_RADIAL) potential_ab(this, s.pot_a, s.pot_b);
     s.ugR = d_ugR.p; s.ugI = d_ugI.p; s.gr_vol = d_gr_vol.p; s.gr_spacing = gr_spacing;
+    if (kind == TDVMC_SYSTEM_INH_CONTACT)
+    {
+        s.rmax = knots[(size_t)n_short + 4 + (K - n_short)]; // pc.nodes[size - 4] (InhContactBosons.cpp:100)
+        s.pot_a = sys_params[0];
+        s.pot_b = sys_params[1];
+        s.ext_k = sys_params[2];
+        s.ext_v0 = sys_params[3];
+        s.gamma = u_core;
+        s.exp_const = u_const;
+    }
     s.phiR = phiR;
     s.inv_cell = kind == TDVMC_SYSTEM_HE_DROP ? ncell / (r_tail - he_rs) : ncell / s.rmax;
     s.h = h; s.inv_h = 1.0 / h;
@@ -641,11 +711,15 @@ int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed,
         g_create_error = "struct_size mismatch (ABI version)";
         return -1;
     }
-    if (sd->dim != 3 || sd->n_particles < 2 || sd->n_params < 1 || sd->n_splines < 4 || ed->n_walkers < 1 || sd->n_other < 3 ||
+    if ((sd->dim != 3 && !(sd->dim == 1 && sd->system_kind == TDVMC_SYSTEM_INH_CONTACT)) || sd->n_particles < 2 || sd->n_params < 1 || sd->n_splines < 4 || ed->n_walkers < 1 || sd->n_other < 3 ||
         sd->tail_param < -1 || sd->tail_param >= sd->n_params || (!(sd->lbox > 0.0) && sd->system_kind != TDVMC_SYSTEM_HE_DROP && sd->system_kind != TDVMC_SYSTEM_MIXTURE) || sd->n_ext < sd->n_splines ||
         (sd->system_kind != TDVMC_SYSTEM_SPLINE_TABLE && sd->system_kind != TDVMC_SYSTEM_HE_BULK &&
          sd->system_kind != TDVMC_SYSTEM_HE_DROP && sd->system_kind != TDVMC_SYSTEM_MIXTURE &&
-         sd->system_kind != TDVMC_SYSTEM_BOX_RADIAL) ||
+         sd->system_kind != TDVMC_SYSTEM_BOX_RADIAL && sd->system_kind != TDVMC_SYSTEM_INH_CONTACT) ||
+        (sd->system_kind == TDVMC_SYSTEM_INH_CONTACT &&
+         (sd->dim != 1 || !sd->knots || !sd->spline_weights || sd->n_ext != sd->n_splines || sd->n_splines_first < 4 ||
+          sd->n_splines - sd->n_splines_first < 4 || sd->n_system_params != 4 || sd->n_other != 9 || sd->n_particles > 32 ||
+          sd->n_ext > 96)) ||
         (sd->system_kind == TDVMC_SYSTEM_BOX_RADIAL &&
          (!sd->knots || !sd->spline_weights || sd->n_ext != 2 * sd->n_splines || (sd->n_params & 1) ||
           sd->n_splines != sd->n_params / 2 + 3 || sd->n_other < 4 || sd->n_system_params < 2)) ||
@@ -702,7 +776,8 @@ int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed,
     h->hbar = sd->hbar2_2m;
     h->kind = sd->system_kind;
     h->n_ext = sd->n_ext;
-    if (sd->knots) h->knots.assign(sd->knots, sd->knots + h->K + 4);
+    if (sd->knots) h->knots.assign(sd->knots, sd->knots + h->K + (sd->system_kind == TDVMC_SYSTEM_INH_CONTACT ? 8 : 4));
+    if (sd->system_kind == TDVMC_SYSTEM_INH_CONTACT) h->n_short = sd->n_splines_first;
     if (sd->spline_weights) h->weights.assign(sd->spline_weights, sd->spline_weights + (size_t)h->K * 16);
     if (h->kind == TDVMC_SYSTEM_MIXTURE)
     {
@@ -750,7 +825,7 @@ int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed,
             return bail(-1);
         }
     h->sys_params.assign(sd->system_params, sd->system_params + sd->n_system_params);
-    if (h->sys_params.size() > 2 && h->sys_params.size() < 5)
+    if (h->kind != TDVMC_SYSTEM_INH_CONTACT && h->sys_params.size() > 2 && h->sys_params.size() < 5)
     {
         h->error = "SYSTEM_PARAMS needs 2 or 5 entries";
         return bail(-1);
@@ -806,7 +881,7 @@ int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed,
         return bail(-3);
     }
 
-    if (h->kind == TDVMC_SYSTEM_MIXTURE)
+    if (h->kind == TDVMC_SYSTEM_MIXTURE || h->kind == TDVMC_SYSTEM_INH_CONTACT)
     {
         h->npp = (h->N + 1) & ~1;
         h->wpb = 1;
@@ -953,7 +1028,8 @@ static int do_sweep(tdvmc_gpu_handle* h, long long n_steps, double* pos = nullpt
     {
         Timed t(h, TDVMC_KERNEL_SWEEP);
         CK(h->kind == TDVMC_SYSTEM_MIXTURE ? launch_sweep_mix(a, h->stream)
-                                          : (h->kind == TDVMC_SYSTEM_BOX_RADIAL ? launch_sweep_br(a, h->stream) : launch_sweep(a, h->stream)));
+           : h->kind == TDVMC_SYSTEM_INH_CONTACT ? launch_sweep_inh(a, h->stream)
+           : h->kind == TDVMC_SYSTEM_BOX_RADIAL ? launch_sweep_br(a, h->stream) : launch_sweep(a, h->stream));
     }
     h->step_counter += (uint64_t)n_steps;
     h->trials_local += (uint64_t)n_steps * (uint64_t)h->W;
@@ -972,6 +1048,7 @@ static cudaError_t launch_evaluate_any(int kind, const EvalArgs& a, cudaStream_t
 {
     if (kind == TDVMC_SYSTEM_MIXTURE) return launch_evaluate_mix(a, st);
     if (kind == TDVMC_SYSTEM_BOX_RADIAL) return launch_evaluate_br(a, st);
+    if (kind == TDVMC_SYSTEM_INH_CONTACT) return launch_evaluate_inh(a, st);
     return kind != TDVMC_SYSTEM_SPLINE_TABLE ? launch_evaluate_he(a, st) : launch_evaluate(a, st);
 }
 
@@ -1367,7 +1444,8 @@ int tdvmc_gpu_quotient_fixed(tdvmc_gpu_handle* h, const double* R, const double*
     a.n_moves = n_moves;
     a.delta = dl.p;
     CK(h->kind == TDVMC_SYSTEM_MIXTURE ? launch_quotient_mix(a, h->stream)
-                                      : (h->kind == TDVMC_SYSTEM_BOX_RADIAL ? launch_quotient_br(a, h->stream) : launch_quotient(a, h->stream)));
+       : h->kind == TDVMC_SYSTEM_INH_CONTACT ? launch_quotient_inh(a, h->stream)
+       : h->kind == TDVMC_SYSTEM_BOX_RADIAL ? launch_quotient_br(a, h->stream) : launch_quotient(a, h->stream));
     std::vector<double> d(n_moves);
     CK(cudaMemcpyAsync(d.data(), dl.p, sizeof(double) * n_moves, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));

@@ -83,6 +83,11 @@ struct SysDev
     const double* ugI;         //         table (NUBosonsBulkPBBoxAndRadial.cpp:493-497); the Laplacian uses utR / utI
     const double* gr_vol;      // [gr_bins] g(r) shell volumes (:149-169)
     double gr_spacing;         // grNodePointSpacing (:147)
+    // InhContactBosons (kind 5, one-dimensional): n_short = K1 splines of the single-particle function, then K - K1 of the
+    // pair correlation; knots [K1+4 | K2+4]; rec = the raw spline table [K][4][4]; cub = [K1-3 | K2-3] interval records
+    double gamma;              // contact strength (InhContactBosons.cpp:25-29); pot_a / pot_b = square-well range / strength
+    double ext_k, ext_v0;      // lattice potential k^2 V0 sin^2(k x), SYSTEM_PARAMS[2], [3] (:448-467)
+    double exp_const;          // -2 gamma h_pc: coefficient of ss_pc[0] in the exponent (:764)
 };
 
 // ---- minimum image -------------------------------------------------------------------------

@@ -74,6 +74,11 @@ cudaError_t launch_sweep_br(SweepArgs a, cudaStream_t st);
 cudaError_t launch_quotient_br(const QuotientArgs& a, cudaStream_t st);
 int sweep_br_fits(const SysDev& s, int wpb, int npp, int smem_optin);
 
+// ---- InhContactBosons: one-dimensional, thread-per-walker kernels (inhcontact.cu) ----
+cudaError_t launch_evaluate_inh(const EvalArgs& a, cudaStream_t st);
+cudaError_t launch_sweep_inh(const SweepArgs& a, cudaStream_t st);
+cudaError_t launch_quotient_inh(const QuotientArgs& a, cudaStream_t st);
+
 // ---- K3 (table form) and K4 (contraction from tables): reference semantics (tables.cu) ----
 struct TableArgs
 {

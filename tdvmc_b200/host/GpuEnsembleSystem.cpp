@@ -128,6 +128,54 @@ SystemTables MakeNUBosonsBulkPBBoxAndRadialTables(int N, double LBOX, int N_PARA
     return t;
 }
 
+SystemTables MakeInhContactBosonsTables(int N, double LBOX, int N_PARAM, const std::vector<double>& SYSTEM_PARAMS,
+                                        const SplinedFunctionTables& spf, const SplinedFunctionTables& pc)
+{
+    if (SYSTEM_PARAMS.size() != 4) throw std::runtime_error("InhContactBosons: the four-entry SYSTEM_PARAMS {range, strength, k, V0} is supported");
+    const int K1 = (int)spf.nodes.size() - 4, K2 = (int)pc.nodes.size() - 4;
+    if (N_PARAM != spf.np3 + pc.np3) throw std::runtime_error("InhContactBosons: wrong number of parameters (InhContactBosons.cpp:122-130)");
+    SystemTables t;
+    t.system_kind = TDVMC_SYSTEM_INH_CONTACT;
+    t.dim = 1;
+    t.n_particles = N;
+    t.n_params = N_PARAM;
+    t.lbox = LBOX;
+    t.tail_param = -1;
+    t.n_other = 9;
+    t.n_splines_first = K1;
+    t.n_ext = K1 + K2;
+    t.system_params = SYSTEM_PARAMS;
+    t.knots = spf.nodes;
+    t.knots.insert(t.knots.end(), pc.nodes.begin(), pc.nodes.end());
+    t.spline_weights = FlattenWeights(spf.splineWeights);
+    const std::vector<double> w2 = FlattenWeights(pc.splineWeights);
+    t.spline_weights.insert(t.spline_weights.end(), w2.begin(), w2.end());
+    // RefreshLocalOperators (InhContactBosons.cpp:208-247)
+    t.map_ptr.push_back(0);
+    for (int i = 0; i < spf.np1; i++)
+    {
+        std::vector<std::pair<int, double> > e;
+        for (int j = 0; j < 3; j++) e.push_back({ j, spf.bcFactorsStart[i][j] });
+        for (int j = 0; j < 3; j++) e.push_back({ K1 - 3 + j, spf.bcFactorsEnd[i][j] });
+        PushRow(t, e);
+    }
+    for (int i = spf.np1; i < spf.np2; i++) PushRow(t, { { 3 + (i - spf.np1), 1.0 } });
+    for (int i = 0; i < pc.np1; i++)
+    {
+        std::vector<std::pair<int, double> > e;
+        for (int j = 0; j < 3; j++) e.push_back({ K1 + j, pc.bcFactorsStart[i][j] });
+        PushRow(t, e);
+    }
+    for (int i = pc.np1; i < pc.np2; i++) PushRow(t, { { K1 + 3 + (i - pc.np1), 1.0 } });
+    for (int i = 0; i < pc.np3 - pc.np2; i++)
+    {
+        std::vector<std::pair<int, double> > e;
+        for (int j = 0; j < 3; j++) e.push_back({ K1 + K2 - 3 + j, pc.bcFactorsEnd[i][j] });
+        PushRow(t, e);
+    }
+    return t;
+}
+
 SystemTables MakeHeBulkTables(int N, double LBOX, int N_PARAM)
 {
     SystemTables t;
@@ -263,9 +311,10 @@ GpuEnsembleSystem::GpuEnsembleSystem(const SystemTables& tb, int walkersTotal, d
     tdvmc_system_desc sd;
     sd.struct_size = sizeof(sd);
     sd.n_particles = tb.n_particles;
-    sd.dim = 3;
+    sd.dim = tb.dim;
     sd.n_params = tb.n_params;
-    sd.n_splines = tb.system_kind == TDVMC_SYSTEM_MIXTURE ? 26 + 2 * (tb.spline_order - 3) : (int32_t)tb.knots.size() - 4;
+    sd.n_splines = tb.system_kind == TDVMC_SYSTEM_MIXTURE ? 26 + 2 * (tb.spline_order - 3)
+                   : (int32_t)tb.knots.size() - (tb.system_kind == TDVMC_SYSTEM_INH_CONTACT ? 8 : 4);
     sd.pair_rule = tb.pair_rule;
     sd.tail_param = tb.tail_param;
     sd.n_other = tb.n_other;
@@ -280,7 +329,7 @@ GpuEnsembleSystem::GpuEnsembleSystem(const SystemTables& tb, int walkersTotal, d
     sd.n_system_params = (int32_t)tb.system_params.size();
     sd.system_kind = tb.system_kind;
     sd.n_ext = tb.n_ext > 0 ? tb.n_ext : sd.n_splines;
-    sd.reserved = 0;
+    sd.n_splines_first = tb.n_splines_first;
     sd.map_const = tb.map_const.empty() ? nullptr : tb.map_const.data();
     sd.grad_const = tb.grad_const.empty() ? nullptr : tb.grad_const.data();
     tdvmc_mixture_desc md;

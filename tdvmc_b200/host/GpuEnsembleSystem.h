@@ -44,6 +44,8 @@ struct SystemTables
     // BosonMixtureCluster only (system_kind == TDVMC_SYSTEM_MIXTURE)
     int n_pair_types = 0;
     int spline_order = 3;                  // 4: BosonMixtureCluster_4thorder
+    int dim = 3;                           // 1: InhContactBosons (positions still [walker][particle][3], coordinate first)
+    int n_splines_first = 0;               // InhContactBosons: splines of the single-particle function
     std::vector<int32_t> pair_type;        // correlationTypes flattened [N][N]
     std::vector<int32_t> pair_potential;   // [T] 0 HFDB_He_He, 1 KTTY_He_Na, 2 KTTY_He_Cs
     std::vector<double> hbar_over_2m, mass; // [N]
@@ -66,6 +68,17 @@ SystemTables MakeNUBosonsBulkPBTables(int N, double LBOX, int N_PARAM, const std
 SystemTables MakeNUBosonsBulkPBBoxAndRadialTables(int N, double LBOX, int N_PARAM, const std::vector<double>& nodes,
                                                   const std::vector<std::vector<std::vector<double> > >& splineWeights,
                                                   const std::vector<double>& SYSTEM_PARAMS, int grBinCount);
+// One WFParts::SplinedFunction of InhContactBosons after InitSystem() (WFParts/SplinedFunction.h:11-33).
+struct SplinedFunctionTables
+{
+    std::vector<double> nodes;
+    std::vector<std::vector<std::vector<double> > > splineWeights;
+    std::vector<std::vector<double> > bcFactorsStart, bcFactorsEnd;
+    int np1 = 0, np2 = 0, np3 = 0;
+};
+// InhContactBosons (InhContactBosons.cpp:64-247), one-dimensional: spf = single-particle function, pc = pair correlation.
+SystemTables MakeInhContactBosonsTables(int N, double LBOX, int N_PARAM, const std::vector<double>& SYSTEM_PARAMS,
+                                        const SplinedFunctionTables& spf, const SplinedFunctionTables& pc);
 
 // HeBulk (HeBulk.cpp:40-70, 376-383): everything follows from N, LBOX and N_PARAM.
 SystemTables MakeHeBulkTables(int N, double LBOX, int N_PARAM);

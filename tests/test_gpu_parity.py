@@ -1343,3 +1343,88 @@ def test_boxradial_statistics_match_reference_sampler(capi, golden):
     assert abs(got["n_acceptances"] / got["n_trials"] - float(g["acceptance"])) < 0.01
     assert np.max(np.abs(got["O"] - g["local_operators"])) / np.abs(g["local_operators"]).max() < 0.02
     h.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# InhContactBosons - the one-dimensional one-body + pair-spline system of the shipped
+# config/InhContactBosons*.config - through the same C ABI (system kind 5, dim = 1)
+# ---------------------------------------------------------------------------------------------------
+INH_CASES = ["inhcontact_n3_fixture", "inhcontact_n3_well", "inhcontact_n3_equil", "inhcontact_n20_equil"]
+
+
+@pytest.mark.parametrize("name", INH_CASES)
+def test_inhcontact_fixed_configuration(capi, golden, name):
+    from oracle_lib import OracleInh
+
+    g = golden(name)
+    spec, h = make_handle(capi, g)
+    K1 = spec.extra["n_splines_spf"]
+    r = h.evaluate_fixed(g["R"][None])
+    assert abs(r["e_r"][0] - float(g["local_energy_r"])) < RTOL * abs(float(g["local_energy_r"]))
+    assert abs(r["e_i"][0] - float(g["local_energy_i"])) < RTOL * abs(float(g["local_energy_i"]))
+    assert rel(r["O"][0], g["local_operators"]) < RTOL
+    assert abs(r["exponent"][0] - float(g["exponent"])) < RTOL * max(abs(float(g["exponent"])), 1.0)
+    assert rel(r["ss"][0][:K1], g["spline_sums_spf"]) < 1e-13 and rel(r["ss"][0][K1:], g["spline_sums_pc"]) < 1e-13
+    assert rel(r["other"][0], g["other_expectation_values"]) < RTOL
+    assert rel(r["drift_r"][0], g["drift_r"]) < RTOL and rel(r["drift_i"][0], g["drift_i"]) < RTOL
+    assert np.all(r["drift_r"][0][:, 1:] == 0.0)
+    q, d = h.quotient_fixed(g["R"], g["moves"])
+    d_ref = g["move_exponent_new"] - float(g["exponent"])
+    assert np.max(np.abs(d - d_ref) / np.maximum(1.0, np.abs(d_ref))) < 1e-10
+    assert rel(q, g["move_quotient"]) < 1e-9
+    h.close()
+
+
+@pytest.mark.parametrize("name", ["inhcontact_n3_equil", "inhcontact_n20_equil"])
+def test_inhcontact_chain_and_estimators_match_oracle(capi, golden, name):
+    """Chain replay (same proposal stream: the first Gaussian component moves the one coordinate) and a whole
+    UpdateExpectationValues pass against the oracle."""
+    from oracle_lib import OracleInh
+
+    g = golden(name)
+    N = int(g["N"])
+    W, seed, mc_step = 40, 23, 0.5
+    n_samples, n_therm, n_init = 3, 4 * N, 10 * N
+    spec, h = make_handle(capi, g, n_walkers=W, seed=seed, mc_step=mc_step, max_samples=n_samples)
+    o = OracleInh(spec)
+    R0 = np.stack([g["R"] + np.array([0.004 * w, 0.0, 0.0]) for w in range(W)])
+    h.set_positions(R0)
+    h.sample_and_accumulate(n_samples, n_therm, n_init)
+    got = h.allreduce_and_fetch()
+    est = np.zeros(o.est_size())
+    acc, Rf = 0, []
+    for w in range(W):
+        r = o.sample_walker(R0[w], g["uR"], g["uI"], float(g["phiR"]), seed, w, 0, n_init, n_samples, n_therm, mc_step, est)
+        acc += r["accepted"]
+        Rf.append(r["R"])
+    want = o.unpack_est(est, W * n_samples)
+    assert got["n_acceptances"] == acc and got["n_trials"] == W * (n_init + n_samples * n_therm)
+    assert 0.3 * got["n_trials"] < acc < got["n_trials"]
+    assert np.max(np.abs(h.get_positions() - np.stack(Rf))) < 1e-9
+    for k in ("O", "S", "OER", "OEI"):
+        assert rel(got[k], want[k]) < 1e-9, k
+    assert abs(got["e_r"][0] - want["e_r"]) < 1e-9 * abs(want["e_r"])
+    assert abs(got["e_i"][0] - want["e_i"]) < 1e-9 * max(abs(want["e_i"]), 1e-3 * abs(want["e_r"]))
+    assert rel(got["other"], want["other"]) < 1e-9
+    d = h.solve_parameters_dot(imaginary_time=1, min_scaling=1e-12)      # the device solve runs on this system too (P = 62)
+    assert d["e_r"] == got["e_r"][0] and np.all(np.isfinite(d["u_dot_r"]))
+    h.close()
+
+
+def test_inhcontact_statistics_match_reference_sampler(capi, golden):
+    """Ensemble energy and acceptance against the reference's own Metropolis run (mt19937_64 stream, 6000 samples)."""
+    g = golden("inhcontact_n3_mc")
+    src = golden(str(g["source"]))
+    W = 4096
+    spec, h = make_handle(capi, src, n_walkers=W, seed=5, mc_step=float(g["MC_STEP"]), max_samples=4)
+    h.set_positions(np.broadcast_to(src["R"], (W, 3, 3)).copy())
+    h.sample_and_accumulate(4, 3 * 10, 3 * 300)
+    got = h.allreduce_and_fetch()
+    er = g["energy_r_series"]
+    nb = 20
+    b = er[:len(er) // nb * nb].reshape(nb, -1).mean(axis=1)
+    m_ref, s_ref = b.mean(), b.std(ddof=1) / np.sqrt(nb)
+    s_gpu = np.std(er) / np.sqrt(W)
+    assert abs(got["e_r"][0] - m_ref) < 4.0 * np.hypot(s_ref, s_gpu), (got["e_r"][0], m_ref, s_ref, s_gpu)
+    assert abs(got["n_acceptances"] / got["n_trials"] - float(g["acceptance"])) < 0.015
+    h.close()
