@@ -107,6 +107,72 @@ class GpuEnsembleSystem:
         return self.handle.euler_step(dt, uR, uI, phiR, phiI, time=time, imaginary_time=IMAGINARY_TIME,
                                       use_preconditioning=USE_PRECONDITIONING, regularization=regularization)
 
+    # -- the explicit multi-stage integrators: the same solve after every stage, estimators never fetched --------------
+    def _stage(self, uR, uI, phiR, phiI, sampling, time, solver):
+        """One intermediate stage: estimators at the given parameters (fresh sampling with the MC counts in `sampling`,
+        or re-evaluation of the stored samples when `sampling` is None), then SolveForParametersDot on the device."""
+        if sampling is None:
+            self.handle.set_params(uR, uI, phiR, phiI, time)
+            self.handle.reevaluate_stored()                       # ParallelUpdateExpectationValuesForGivenSamples(..., true)
+        else:
+            self.SampleExpectationValues(uR, uI, phiR, phiI, *sampling, time=time)   # ParallelUpdateExpectationValues(..., true)
+        return self.handle.solve_parameters_dot(**solver)
+
+    def _predictor_corrector(self, dt, uR, uI, phiR, phiI, pc_steps, sampling, time, solver):
+        uR, uI = np.asarray(uR, np.float64), np.asarray(uI, np.float64)
+        dt_2 = dt / 2.0
+        d0 = self.handle.solve_parameters_dot(**solver)
+        tR, tI = uR + d0["u_dot_r"] * dt, uI + d0["u_dot_i"] * dt
+        tpR, tpI = phiR + d0["phi_dot_r"] * dt, phiI + d0["phi_dot_i"] * dt
+        for _ in range(pc_steps):
+            d1 = self._stage(tR, tI, tpR, tpI, sampling, time, solver)
+            tR, tI = uR + (d0["u_dot_r"] + d1["u_dot_r"]) * dt_2, uI + (d0["u_dot_i"] + d1["u_dot_i"]) * dt_2
+            tpR, tpI = phiR + (d0["phi_dot_r"] + d1["phi_dot_r"]) * dt_2, phiI + (d0["phi_dot_i"] + d1["phi_dot_i"]) * dt_2
+        self.handle.set_params(tR, tI, tpR, tpI, time)
+        return tR, tI, tpR, tpI, d0
+
+    def _rk4(self, dt, uR, uI, phiR, phiI, sampling, time, solver):
+        uR, uI = np.asarray(uR, np.float64), np.asarray(uI, np.float64)
+        dt_2 = dt / 2.0
+        d = [self.handle.solve_parameters_dot(**solver)]
+        for step in (dt_2, dt_2, dt):
+            k = d[-1]
+            d.append(self._stage(uR + k["u_dot_r"] * step, uI + k["u_dot_i"] * step, phiR + k["phi_dot_r"] * step,
+                                 phiI + k["phi_dot_i"] * step, sampling, time, solver))
+        comb = lambda key: (d[0][key] + d[1][key] * 2.0 + d[2][key] * 2.0 + d[3][key]) / 6.0
+        nR, nI = uR + comb("u_dot_r") * dt, uI + comb("u_dot_i") * dt
+        npR, npI = phiR + comb("phi_dot_r") * dt, phiI + comb("phi_dot_i") * dt
+        self.handle.set_params(nR, nI, npR, npI, time)
+        return nR, nI, npR, npI, d[0]
+
+    @staticmethod
+    def _solver(IMAGINARY_TIME, USE_PRECONDITIONING, regularization):
+        return dict(imaginary_time=IMAGINARY_TIME, use_preconditioning=USE_PRECONDITIONING, regularization=regularization)
+
+    def CalculateNextParametersPC(self, dt, uR, uI, phiR, phiI, MC_NSTEPS, MC_NTHERMSTEPS, MC_NINITIALIZATIONSTEPS=0,
+                                  IMAGINARY_TIME=1, USE_PRECONDITIONING=1, time=0.0, regularization=0.001):
+        """src/TDVMC.cpp:1855-1910 (ODE_SOLVER_TYPE 1): predictor-corrector, one corrector with a fresh sampling pass.  Like
+        the Euler step it starts from the estimators of the current parameters already accumulated on the device."""
+        return self._predictor_corrector(dt, uR, uI, phiR, phiI, 1, (MC_NSTEPS, MC_NTHERMSTEPS, MC_NINITIALIZATIONSTEPS), time,
+                                         self._solver(IMAGINARY_TIME, USE_PRECONDITIONING, regularization))
+
+    def CalculateNextParametersPCReuseSamples(self, dt, uR, uI, phiR, phiI, IMAGINARY_TIME=1, USE_PRECONDITIONING=1, time=0.0,
+                                              regularization=0.001):
+        """src/TDVMC.cpp:1912-1967: six correctors on the stored samples (needs update_samples_every_nth_step > 0)."""
+        return self._predictor_corrector(dt, uR, uI, phiR, phiI, 6, None, time,
+                                         self._solver(IMAGINARY_TIME, USE_PRECONDITIONING, regularization))
+
+    def CalculateNextParametersRK4(self, dt, uR, uI, phiR, phiI, MC_NSTEPS, MC_NTHERMSTEPS, MC_NINITIALIZATIONSTEPS=0,
+                                   IMAGINARY_TIME=1, USE_PRECONDITIONING=1, time=0.0, regularization=0.001):
+        """src/TDVMC.cpp:1969-2035: classical Runge-Kutta, a fresh sampling pass per stage."""
+        return self._rk4(dt, uR, uI, phiR, phiI, (MC_NSTEPS, MC_NTHERMSTEPS, MC_NINITIALIZATIONSTEPS), time,
+                         self._solver(IMAGINARY_TIME, USE_PRECONDITIONING, regularization))
+
+    def CalculateNextParametersRK4ReuseSamples(self, dt, uR, uI, phiR, phiI, IMAGINARY_TIME=1, USE_PRECONDITIONING=1, time=0.0,
+                                               regularization=0.001):
+        """src/TDVMC.cpp:2037-2103: Runge-Kutta on the stored samples."""
+        return self._rk4(dt, uR, uI, phiR, phiI, None, time, self._solver(IMAGINARY_TIME, USE_PRECONDITIONING, regularization))
+
     def GetExponent(self):
         return self.handle.last_exponent()
 

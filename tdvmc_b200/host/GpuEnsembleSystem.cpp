@@ -503,6 +503,123 @@ bool GpuEnsembleSystem::CalculateNextParametersEuler(double dt, std::vector<doub
     return d.not_positive_definite != 0;
 }
 
+GpuEnsembleSystem::Dot GpuEnsembleSystem::SolveNow(int IMAGINARY_TIME, int USE_PRECONDITIONING)
+{
+    Dot d;
+    d.notPD = SolveForParametersDot(d.uR, d.uI, &d.phiR, &d.phiI, IMAGINARY_TIME, USE_PRECONDITIONING);
+    return d;
+}
+
+// one intermediate stage: estimators at the given parameters (fresh sampling, or the stored samples if mcCounts is null),
+// then the solve on the device
+GpuEnsembleSystem::Dot GpuEnsembleSystem::Stage(const std::vector<double>& uR, const std::vector<double>& uI, double phiR,
+                                                 double phiI, const int* mcCounts, int IMAGINARY_TIME, int USE_PRECONDITIONING,
+                                                 double time)
+{
+    if (mcCounts) SampleExpectationValues(uR, uI, phiR, phiI, mcCounts[0], mcCounts[1], mcCounts[2], time);
+    else
+    {
+        Check(tdvmc_gpu_set_params(handle, uR.data(), uI.data(), phiR, phiI, time), "set_params");
+        Check(tdvmc_gpu_reevaluate_stored(handle), "reevaluate_stored");
+    }
+    return SolveNow(IMAGINARY_TIME, USE_PRECONDITIONING);
+}
+
+bool GpuEnsembleSystem::PredictorCorrector(double dt, std::vector<double>& uR, std::vector<double>& uI, double* phiR, double* phiI,
+                                           int pcSteps, const int* mcCounts, int IMAGINARY_TIME, int USE_PRECONDITIONING,
+                                           double time)
+{
+    const double dt_2 = dt / 2.0;
+    const Dot d0 = SolveNow(IMAGINARY_TIME, USE_PRECONDITIONING);
+    bool bad = d0.notPD;
+    std::vector<double> tR(P), tI(P);
+    for (int i = 0; i < P; i++)
+    {
+        tR[i] = uR[i] + d0.uR[i] * dt;
+        tI[i] = uI[i] + d0.uI[i] * dt;
+    }
+    double tpR = *phiR + d0.phiR * dt, tpI = *phiI + d0.phiI * dt;
+    for (int s = 0; s < pcSteps; s++)
+    {
+        const Dot d1 = Stage(tR, tI, tpR, tpI, mcCounts, IMAGINARY_TIME, USE_PRECONDITIONING, time);
+        bad = bad || d1.notPD;
+        for (int i = 0; i < P; i++)
+        {
+            tR[i] = uR[i] + (d0.uR[i] + d1.uR[i]) * dt_2;
+            tI[i] = uI[i] + (d0.uI[i] + d1.uI[i]) * dt_2;
+        }
+        tpR = *phiR + (d0.phiR + d1.phiR) * dt_2;
+        tpI = *phiI + (d0.phiI + d1.phiI) * dt_2;
+    }
+    uR = tR;
+    uI = tI;
+    *phiR = tpR;
+    *phiI = tpI;
+    Check(tdvmc_gpu_set_params(handle, uR.data(), uI.data(), *phiR, *phiI, time), "set_params");
+    return bad;
+}
+
+bool GpuEnsembleSystem::RungeKutta4(double dt, std::vector<double>& uR, std::vector<double>& uI, double* phiR, double* phiI,
+                                    const int* mcCounts, int IMAGINARY_TIME, int USE_PRECONDITIONING, double time)
+{
+    const double steps[3] = { dt / 2.0, dt / 2.0, dt };
+    std::vector<Dot> d;
+    d.push_back(SolveNow(IMAGINARY_TIME, USE_PRECONDITIONING));
+    std::vector<double> tR(P), tI(P);
+    for (int k = 0; k < 3; k++)
+    {
+        const Dot& c = d.back();
+        for (int i = 0; i < P; i++)
+        {
+            tR[i] = uR[i] + c.uR[i] * steps[k];
+            tI[i] = uI[i] + c.uI[i] * steps[k];
+        }
+        d.push_back(Stage(tR, tI, *phiR + c.phiR * steps[k], *phiI + c.phiI * steps[k], mcCounts, IMAGINARY_TIME,
+                          USE_PRECONDITIONING, time));
+    }
+    bool bad = false;
+    for (const Dot& x : d) bad = bad || x.notPD;
+    for (int i = 0; i < P; i++) // src/TDVMC.cpp:2030-2031
+    {
+        uR[i] = uR[i] + ((d[0].uR[i] + d[1].uR[i] * 2.0 + d[2].uR[i] * 2.0 + d[3].uR[i]) / 6.0) * dt;
+        uI[i] = uI[i] + ((d[0].uI[i] + d[1].uI[i] * 2.0 + d[2].uI[i] * 2.0 + d[3].uI[i]) / 6.0) * dt;
+    }
+    *phiR = *phiR + ((d[0].phiR + d[1].phiR * 2.0 + d[2].phiR * 2.0 + d[3].phiR) / 6.0) * dt;
+    *phiI = *phiI + ((d[0].phiI + d[1].phiI * 2.0 + d[2].phiI * 2.0 + d[3].phiI) / 6.0) * dt;
+    Check(tdvmc_gpu_set_params(handle, uR.data(), uI.data(), *phiR, *phiI, time), "set_params");
+    return bad;
+}
+
+bool GpuEnsembleSystem::CalculateNextParametersPC(double dt, std::vector<double>& uR, std::vector<double>& uI, double* phiR,
+                                                  double* phiI, int MC_NSTEPS, int MC_NTHERMSTEPS, int MC_NINITIALIZATIONSTEPS,
+                                                  int IMAGINARY_TIME, int USE_PRECONDITIONING, double time)
+{
+    const int mc[3] = { MC_NSTEPS, MC_NTHERMSTEPS, MC_NINITIALIZATIONSTEPS };
+    return PredictorCorrector(dt, uR, uI, phiR, phiI, 1, mc, IMAGINARY_TIME, USE_PRECONDITIONING, time);
+}
+
+bool GpuEnsembleSystem::CalculateNextParametersPCReuseSamples(double dt, std::vector<double>& uR, std::vector<double>& uI,
+                                                              double* phiR, double* phiI, int IMAGINARY_TIME,
+                                                              int USE_PRECONDITIONING, double time)
+{
+    return PredictorCorrector(dt, uR, uI, phiR, phiI, 6, nullptr, IMAGINARY_TIME, USE_PRECONDITIONING, time);
+}
+
+bool GpuEnsembleSystem::CalculateNextParametersRK4(double dt, std::vector<double>& uR, std::vector<double>& uI, double* phiR,
+                                                   double* phiI, int MC_NSTEPS, int MC_NTHERMSTEPS, int MC_NINITIALIZATIONSTEPS,
+                                                   int IMAGINARY_TIME, int USE_PRECONDITIONING, double time)
+{
+    const int mc[3] = { MC_NSTEPS, MC_NTHERMSTEPS, MC_NINITIALIZATIONSTEPS };
+    return RungeKutta4(dt, uR, uI, phiR, phiI, mc, IMAGINARY_TIME, USE_PRECONDITIONING, time);
+}
+
+bool GpuEnsembleSystem::CalculateNextParametersRK4ReuseSamples(double dt, std::vector<double>& uR, std::vector<double>& uI,
+                                                               double* phiR, double* phiI, int IMAGINARY_TIME,
+                                                               int USE_PRECONDITIONING, double time)
+{
+    return RungeKutta4(dt, uR, uI, phiR, phiI, nullptr, IMAGINARY_TIME, USE_PRECONDITIONING, time);
+}
+
 ObservableTables MakePairDistributionGrid(double rMax, int numOfPairDistributionValues, double weight)
 {
     ObservableTables t;

@@ -200,6 +200,22 @@ public:
     bool CalculateNextParametersEuler(double dt, std::vector<double>& uR, std::vector<double>& uI, double* phiR, double* phiI,
                                       int IMAGINARY_TIME, int USE_PRECONDITIONING, double time, double* localEnergyR,
                                       double* localEnergyI);
+    // The explicit multi-stage integrators composed from device stages - fresh sampling (MC counts given) or re-evaluation of
+    // the stored samples (ReuseSamples), each followed by the device solve; no estimator is fetched.  All start from the
+    // estimators of (uR, uI) already accumulated on the device and leave the new parameters current there.  Return value:
+    // some stage's matrix was not positive definite.
+    //   CalculateNextParametersPC              src/TDVMC.cpp:1855-1910     CalculateNextParametersRK4              :1969-2035
+    //   CalculateNextParametersPCReuseSamples  :1912-1967                  CalculateNextParametersRK4ReuseSamples  :2037-2103
+    bool CalculateNextParametersPC(double dt, std::vector<double>& uR, std::vector<double>& uI, double* phiR, double* phiI,
+                                   int MC_NSTEPS, int MC_NTHERMSTEPS, int MC_NINITIALIZATIONSTEPS, int IMAGINARY_TIME,
+                                   int USE_PRECONDITIONING, double time);
+    bool CalculateNextParametersPCReuseSamples(double dt, std::vector<double>& uR, std::vector<double>& uI, double* phiR,
+                                               double* phiI, int IMAGINARY_TIME, int USE_PRECONDITIONING, double time);
+    bool CalculateNextParametersRK4(double dt, std::vector<double>& uR, std::vector<double>& uI, double* phiR, double* phiI,
+                                    int MC_NSTEPS, int MC_NTHERMSTEPS, int MC_NINITIALIZATIONSTEPS, int IMAGINARY_TIME,
+                                    int USE_PRECONDITIONING, double time);
+    bool CalculateNextParametersRK4ReuseSamples(double dt, std::vector<double>& uR, std::vector<double>& uI, double* phiR,
+                                                double* phiI, int IMAGINARY_TIME, int USE_PRECONDITIONING, double time);
     // ParallelCalculateAdditionalSystemProperties (src/TDVMC.cpp:1438-1444) for the bulk spline systems: the mean
     // pairDistribution / structureFactor values (additionalObservablesMean.observables[0], [1]) over samples, walkers, ranks.
     AdditionalObservables ParallelCalculateAdditionalSystemProperties(const std::vector<double>& uR, const std::vector<double>& uI,
@@ -210,6 +226,19 @@ public:
 private:
     void Check(int rc, const char* what);
     Estimators Fetch();
+    struct Dot
+    {
+        std::vector<double> uR, uI;
+        double phiR = 0, phiI = 0;
+        bool notPD = false;
+    };
+    Dot Stage(const std::vector<double>& uR, const std::vector<double>& uI, double phiR, double phiI, const int* mcCounts,
+              int IMAGINARY_TIME, int USE_PRECONDITIONING, double time);
+    Dot SolveNow(int IMAGINARY_TIME, int USE_PRECONDITIONING);
+    bool PredictorCorrector(double dt, std::vector<double>& uR, std::vector<double>& uI, double* phiR, double* phiI, int pcSteps,
+                            const int* mcCounts, int IMAGINARY_TIME, int USE_PRECONDITIONING, double time);
+    bool RungeKutta4(double dt, std::vector<double>& uR, std::vector<double>& uI, double* phiR, double* phiI, const int* mcCounts,
+                     int IMAGINARY_TIME, int USE_PRECONDITIONING, double time);
 
     tdvmc_gpu_handle* handle = nullptr;
     int N = 0, P = 0, nOther = 9;

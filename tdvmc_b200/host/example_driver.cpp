@@ -105,6 +105,11 @@ int main(int argc, char** argv)
         double phiR = 0.0, phiI = 0.0, eR = 0.0, eI = 0.0;
         const bool notPD = gpu.CalculateNextParametersEuler(1e-4, uR, uI, &phiR, &phiI, 1, 1, 1e-4, &eR, &eI);
         std::printf("EULER uR0=%.17g uRlast=%.17g phiR=%.17g E_R=%.17g notPD=%d\n", uR[0], uR[P - 1], phiR, eR, notPD ? 1 : 0);
+        // and one Runge-Kutta step (CalculateNextParametersRK4, src/TDVMC.cpp:1969-2035): four device stages, each a
+        // sampling pass followed by the device solve
+        gpu.SampleExpectationValues(uR, uI, phiR, phiI, MC_NSTEPS, MC_NTHERMSTEPS, 0, 1e-4);
+        const bool notPD4 = gpu.CalculateNextParametersRK4(1e-4, uR, uI, &phiR, &phiI, MC_NSTEPS, MC_NTHERMSTEPS, 0, 1, 1, 2e-4);
+        std::printf("RK4 uR0=%.17g uRlast=%.17g phiR=%.17g notPD=%d\n", uR[0], uR[P - 1], phiR, notPD4 ? 1 : 0);
     }
     catch (const std::exception& ex)
     {

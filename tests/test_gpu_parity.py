@@ -522,11 +522,21 @@ def test_cpp_host_adapter_matches_python_path(capi, golden, tmp_path):
     assert abs(e_cpp - e_py) < 1e-9 * abs(e_py)
     # the Euler step the driver took with the device solve: same chain, same estimators -> same new parameters
     u2, _, phi2, _, dot = h.euler_step(1e-4, uR, np.zeros(P), 0.0, 0.0, time=1e-4, imaginary_time=1)
-    euler = dict(kv.split("=") for kv in r.stdout.split("EULER ")[1].split())
+    euler = dict(kv.split("=") for kv in r.stdout.split("EULER ")[1].splitlines()[0].split())
     # (the driver builds uR with std::exp/std::pow, numpy may differ in the last bit: same tolerance as E_R above)
     for key, want in (("uR0", u2[0]), ("uRlast", u2[-1]), ("phiR", phi2), ("E_R", dot["e_r"])):
         assert abs(float(euler[key]) - want) < 1e-9 * abs(want), key
     assert abs(u2[0] - uR[0]) > 1e-9 * abs(uR[0]) and int(euler["notPD"]) == 0    # the step did move the parameters
+    # ... and the Runge-Kutta step that followed (four device stages in the C++ adapter and in the Python mirror)
+    from tdvmc_b200.ensemble import GpuEnsembleSystem
+    ens = GpuEnsembleSystem.__new__(GpuEnsembleSystem)
+    ens.handle = h
+    ens.SampleExpectationValues(u2, np.zeros(P), phi2, 0.0, 2, N, 0, time=1e-4)
+    u4, _, phi4, _, _ = ens.CalculateNextParametersRK4(1e-4, u2, np.zeros(P), phi2, 0.0, 2, N, 0, IMAGINARY_TIME=1, time=2e-4)
+    rk4 = dict(kv.split("=") for kv in r.stdout.split("RK4 ")[1].splitlines()[0].split())
+    for key, want in (("uR0", u4[0]), ("uRlast", u4[-1]), ("phiR", phi4)):
+        assert abs(float(rk4[key]) - want) < 1e-9 * abs(want), key
+    assert abs(u4[0] - u2[0]) > 1e-9 * abs(u2[0]) and int(rk4["notPD"]) == 0
     h.close()
 
 
@@ -1428,3 +1438,68 @@ def test_inhcontact_statistics_match_reference_sampler(capi, golden):
     assert abs(got["e_r"][0] - m_ref) < 4.0 * np.hypot(s_ref, s_gpu), (got["e_r"][0], m_ref, s_ref, s_gpu)
     assert abs(got["n_acceptances"] / got["n_trials"] - float(g["acceptance"])) < 0.015
     h.close()
+
+
+@pytest.mark.parametrize("method", ["PC", "PCReuseSamples", "RK4", "RK4ReuseSamples"])
+def test_multistage_integrators_on_device_match_host_mirror(capi, golden, method):
+    """CalculateNextParametersPC / PCReuseSamples / RK4 / RK4ReuseSamples (src/TDVMC.cpp:1855-2103) composed from device
+    stages (sampling or stored-sample re-evaluation + solve_kernel, nothing fetched) against the same composition with
+    every stage's estimators fetched and solved by the host mirror of the reference's SolveForParametersDot: two
+    ensembles with the same seed walk the same chains, so the results agree to the solver's rounding."""
+    from tdvmc_b200 import timestep
+    from tdvmc_b200.ensemble import GpuEnsembleSystem
+    g = golden("bosonsbulk_n64_evolution")
+    src = golden(str(g["source"]))
+    spec = systems.bosons_bulk(int(g["N"]), float(g["LBOX"]), int(g["N_PARAM"]), g["SYSTEM_PARAMS"], weights=src["spline_weights"])
+    W, n_samples, n_therm, n_init, dt = 64, 4, 64, 32, 2e-3
+    reuse = method.endswith("ReuseSamples")
+    mc = (n_samples, n_therm, n_init)
+    uR0, uI0 = g["uR0"].copy(), 0.01 * np.sin(np.arange(spec.n_params))
+
+    def make():
+        ens = GpuEnsembleSystem(spec, W, mc_step=float(g["MC_STEP"]), mc_nsteps=n_samples, seed=8,
+                                update_samples_every_nth_step=1 if reuse else 0)
+        ens.SetPositions(np.broadcast_to(src["R"], (W, spec.n_particles, 3)).copy())
+        ens.BroadcastNewParameters(uR0, uI0, 0.0, 0.0)
+        ens.DoMetropolisSteps(640)
+        return ens
+
+    dev = make()
+    dev.SampleExpectationValues(uR0, uI0, 0.0, 0.0, *mc)
+    args = () if reuse else mc
+    uR1, uI1, pR1, pI1, _ = getattr(dev, "CalculateNextParameters" + method)(dt, uR0, uI0, 0.0, 0.0, *args, IMAGINARY_TIME=0)
+    e_dev = dev.handle.evaluate_fixed(src["R"][None])                    # the new parameters are current on the device
+    dev.close()
+
+    host = make()
+    est = host.ParallelUpdateExpectationValues(uR0, uI0, 0.0, 0.0, *mc)
+    solve = lambda e: timestep.solve_for_parameters_dot(e, imaginary_time=0)
+
+    def stage(u_r, u_i, p_r, p_i):
+        if reuse:
+            return solve(host.ParallelUpdateExpectationValuesForGivenSamples(u_r, u_i, p_r, p_i))
+        return solve(host.ParallelUpdateExpectationValues(u_r, u_i, p_r, p_i, *mc))
+
+    d0 = solve(est)
+    if method.startswith("PC"):
+        t = (uR0 + d0[0] * dt, uI0 + d0[1] * dt, 0.0 + d0[2] * dt, 0.0 + d0[3] * dt)
+        for _ in range(6 if reuse else 1):
+            d1 = stage(*t)
+            t = (uR0 + (d0[0] + d1[0]) * (dt / 2), uI0 + (d0[1] + d1[1]) * (dt / 2), (d0[2] + d1[2]) * (dt / 2), (d0[3] + d1[3]) * (dt / 2))
+        want = t
+    else:
+        d = [d0]
+        for step in (dt / 2, dt / 2, dt):
+            k = d[-1]
+            d.append(stage(uR0 + k[0] * step, uI0 + k[1] * step, k[2] * step, k[3] * step))
+        comb = lambda j: (d[0][j] + d[1][j] * 2.0 + d[2][j] * 2.0 + d[3][j]) / 6.0
+        want = (uR0 + comb(0) * dt, uI0 + comb(1) * dt, comb(2) * dt, comb(3) * dt)
+    host.close()
+    moved = np.max(np.abs(want[0] - uR0)) + np.max(np.abs(want[1] - uI0))
+    assert moved > 1e-6
+    assert np.max(np.abs(uR1 - want[0])) < 1e-8 * moved and np.max(np.abs(uI1 - want[1])) < 1e-8 * moved
+    assert abs(pR1 - want[2]) < 1e-8 * max(abs(want[2]), 1e-12) and abs(pI1 - want[3]) < 1e-8 * max(abs(want[3]), 1e-12)
+    h2 = capi.Handle(spec, 4)
+    h2.set_params(uR1, uI1, pR1, pI1, 0.0)
+    assert h2.evaluate_fixed(src["R"][None])["e_r"][0] == e_dev["e_r"][0]
+    h2.close()
