@@ -3,7 +3,7 @@
 // table are read from a text file (the reference driver would pass its own SplineFactory output).
 //
 //   example_driver <tables.txt>      tables.txt: N LBOX N_PARAM n_knots, knots..., K*16 weights...
-//   example_driver --map hebulk N LBOX N_PARAM | --map hedrop N N_PARAM | --map boxradial N LBOX N_PARAM
+//   example_driver --map hebulk N LBOX N_PARAM | --map hedrop N N_PARAM | --map boxradial N LBOX N_PARAM | --map file <f>
 //                                    prints the parameter map the adapter builds (no GPU needed)
 //
 // Exit code 0, one line "E_R=... acceptance=..." and one line "EULER ..." (parameters after one device-solved Euler step) on success; without a CUDA device the library
@@ -17,6 +17,7 @@
 #include <fstream>
 #include <iostream>
 #include <stdexcept>
+#include <string>
 
 using namespace tdvmc_host;
 
@@ -27,7 +28,7 @@ int main(int argc, char** argv)
         std::fprintf(stderr, "usage: example_driver <tables.txt>\n");
         return 2;
     }
-    if (!std::strcmp(argv[1], "--map") && argc >= 5)
+    if (!std::strcmp(argv[1], "--map") && argc >= 4)
     {
         const bool bulk = !std::strcmp(argv[2], "hebulk");
         SystemTables t;
@@ -49,10 +50,73 @@ int main(int argc, char** argv)
             std::vector<std::vector<std::vector<double> > > w(K, std::vector<std::vector<double> >(4, std::vector<double>(4, 0.0)));
             t = MakeNUBosonsBulkPBBoxAndRadialTables(std::atoi(argv[3]), L, P, nodes, w, { 0.1, 50.0 }, 400);
         }
+        else if (!std::strcmp(argv[2], "file") && argc >= 4)
+        {
+            // builders that need the reference's own boundary factors: read them from a text file
+            //   mixture <order> <N> <T> / N*N correlationTypes / per type: nk knots..., 5 x (order-1) bcFactors, mcMillan, potential
+            //   inhcontact <N> <LBOX> <N_PARAM> / 4 SYSTEM_PARAMS / spf then pc: nk knots..., 3x3 bcStart rows count + values,
+            //              bcEnd rows count + values, np1 np2 np3
+            std::ifstream in(argv[3]);
+            std::string what;
+            in >> what;
+            if (what == "mixture")
+            {
+                int order, N, T;
+                in >> order >> N >> T;
+                std::vector<std::vector<int> > ct(N, std::vector<int>(N));
+                for (auto& row : ct)
+                    for (int& c : row) in >> c;
+                std::vector<MixturePairType> types(T);
+                for (auto& p : types)
+                {
+                    int nk;
+                    in >> nk;
+                    p.nodes.resize(nk);
+                    for (double& x : p.nodes) in >> x;
+                    const int K = nk - order - 1;
+                    p.splineWeights.assign(K, std::vector<std::vector<double> >(order + 1, std::vector<double>(order + 1, 0.0)));
+                    p.bcFactors.assign(5, std::vector<double>(order - 1));
+                    for (auto& row : p.bcFactors)
+                        for (double& x : row) in >> x;
+                    in >> p.mcMillanFactor >> p.potential;
+                }
+                t = MakeBosonMixtureClusterTables(N, ct, std::vector<double>(N, 1.0), std::vector<double>(N, 1.0), types, 403, order);
+            }
+            else
+            {
+                int N, P;
+                double L;
+                in >> N >> L >> P;
+                std::vector<double> sp(4);
+                for (double& x : sp) in >> x;
+                SplinedFunctionTables part[2];
+                for (auto& f : part)
+                {
+                    int nk, ns, ne;
+                    in >> nk;
+                    f.nodes.resize(nk);
+                    for (double& x : f.nodes) in >> x;
+                    f.splineWeights.assign(nk - 4, std::vector<std::vector<double> >(4, std::vector<double>(4, 0.0)));
+                    in >> ns;
+                    f.bcFactorsStart.assign(ns, std::vector<double>(3));
+                    for (auto& row : f.bcFactorsStart)
+                        for (double& x : row) in >> x;
+                    in >> ne;
+                    f.bcFactorsEnd.assign(ne, std::vector<double>(3));
+                    for (auto& row : f.bcFactorsEnd)
+                        for (double& x : row) in >> x;
+                    in >> f.np1 >> f.np2 >> f.np3;
+                }
+                t = MakeInhContactBosonsTables(N, L, P, sp, part[0], part[1]);
+            }
+            if (!in) return 2;
+        }
         else
             t = bulk ? MakeHeBulkTables(std::atoi(argv[3]), std::atof(argv[4]), std::atoi(argv[5]))
                      : MakeHeDropTables(std::atoi(argv[3]), std::atoi(argv[4]));
-        std::printf("%d %d %d %d %d\n", t.system_kind, t.n_params, t.n_ext, t.n_other, (int)t.knots.size() - 4);
+        std::printf("%d %d %d %d %d\n", t.system_kind, t.n_params, t.n_ext, t.n_other,
+                    t.system_kind == TDVMC_SYSTEM_MIXTURE ? 26 + 2 * (t.spline_order - 3)
+                                                          : (int)t.knots.size() - (t.system_kind == TDVMC_SYSTEM_INH_CONTACT ? 8 : 4));
         for (int p : t.map_ptr) std::printf("%d ", p);
         std::printf("\n");
         for (int c : t.map_col) std::printf("%d ", c);

@@ -278,3 +278,38 @@ def test_recorded_bench_line_has_the_contract_keys():
     # value = proposals of all walkers / time
     steps = d["config"]["proposals_per_walker_per_step"] * d["config"]["walkers"] * d["steps"]
     assert abs(steps / (d["ms_per_step"] * d["steps"] * 1e-3) - d["value"]) < 1e-6 * d["value"]
+
+
+@pytest.mark.parametrize("name", ["mixture_he4he4na_equil", "mixture_he3he4cs_equil", "mixture4_he4he4na_equil", "inhcontact_n20_equil"])
+def test_cpp_table_builders_with_reference_boundary_factors(golden, tmp_path, name):
+    """MakeBosonMixtureClusterTables (cubic and quartic) and MakeInhContactBosonsTables (C++ adapter), fed the reference's
+    own knots and boundary factors from the fixtures, build the same CSR parameter map bit for bit as the Python specs
+    (which the golden fixtures pin against the reference)."""
+    from tdvmc_b200 import systems as tsys
+    g = golden(name)
+    spec = tsys.from_golden(g)
+    host = os.path.join(ROOT, "tdvmc_b200", "host")
+    subprocess.check_call(["make", "-C", host, "example_driver"])
+    f = tmp_path / "in.txt"
+    fl = lambda a: " ".join(repr(float(x)) for x in np.asarray(a).ravel())
+    with open(f, "w") as out:
+        if spec.kind == tsys.KIND_MIXTURE:
+            T, order = int(g["n_pair_types"]), int(spec.extra["order"])
+            out.write(f"mixture {order} {spec.n_particles} {T}\n")
+            out.write(" ".join(str(int(x)) for x in g["correlation_types"]) + "\n")
+            pots = spec.extra["type_potential"]
+            for t in range(T):
+                out.write(f"{len(g[f'knots_{t}'])} {fl(g[f'knots_{t}'])}\n{fl(g[f'bc_factors_{t}'])}\n{float(g[f'extras_{t}'][6])!r} {int(pots[t])}\n")
+        else:
+            out.write(f"inhcontact {spec.n_particles} {spec.lbox!r} {spec.n_params}\n{fl(g['SYSTEM_PARAMS'])}\n")
+            for q in ("spf", "pc"):
+                bs, be, npq = g["bc_start_" + q], g["bc_end_" + q], g["np_" + q]
+                out.write(f"{len(g['knots_' + q])} {fl(g['knots_' + q])}\n{len(bs)} {fl(bs)}\n{len(be)} {fl(be)}\n"
+                          f"{int(npq[0])} {int(npq[1])} {int(npq[2])}\n")
+    r = subprocess.run([os.path.join(host, "example_driver"), "--map", "file", str(f)], capture_output=True, text=True, check=True)
+    o = r.stdout.splitlines()
+    kind, P, n_ext, n_other, K = (int(x) for x in o[0].split())
+    assert (kind, P, n_ext) == (spec.kind, spec.n_params, spec.n_ext) and K == spec.n_splines
+    np.testing.assert_array_equal(np.array(o[1].split(), dtype=np.int64), spec.map_ptr)
+    np.testing.assert_array_equal(np.array(o[2].split(), dtype=np.int64), spec.map_col)
+    np.testing.assert_array_equal(np.array(o[3].split(), dtype=np.float64), spec.map_val)
