@@ -7,7 +7,10 @@ namespace tdvmc
 {
 
 constexpr int kSweepMaxThreads = 704;      // packed small systems (8 / 16 lanes per walker): up to 22 warps, 93 registers
-constexpr int kSweepMaxThreadsWarp = 640;  // one warp per walker: up to 20 warps per block, which lets the kernel take 94 registers
+#ifndef TDVMC_SWEEP_THREADS
+#define TDVMC_SWEEP_THREADS 640
+#endif
+constexpr int kSweepMaxThreadsWarp = TDVMC_SWEEP_THREADS;  // one warp per walker: up to 20 warps per block, which lets the kernel take 94 registers
 constexpr int kSweepMinBlocks = 1;
 
 // ---- K1: Metropolis sweep (sweep.cu) ----

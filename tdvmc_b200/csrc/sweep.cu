@@ -40,7 +40,10 @@
 namespace tdvmc
 {
 
-constexpr int kCubCopies = 8;                 // shared-memory replicas of the coefficient planes (one per 16-byte slot)
+#ifndef TDVMC_CUB_COPIES
+#define TDVMC_CUB_COPIES 8
+#endif
+constexpr int kCubCopies = TDVMC_CUB_COPIES;  // shared-memory replicas of the coefficient planes (one per 16-byte slot)
 
 // sum over the GROUP lanes of a walker (all lanes of the warp take part)
 template <int GROUP>
