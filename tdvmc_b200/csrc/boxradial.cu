@@ -110,10 +110,10 @@ __global__ void __launch_bounds__(kBrWarps * 32) evaluate_br_kernel(EvalArgs a)
     for (int k = lane; k < NG; k += 32) grc[k] = 0u;
     __syncwarp();
 
-    BrEvalTables knots; // (named after its first use below)
-    knots.knots = sk;
-    knots.rec = srec;
-    knots.lut = slut;
+    BrEvalTables tb;
+    tb.knots = sk;
+    tb.rec = srec;
+    tb.lut = slut;
     const double* ugRr = su;
     const double* ugIr = su + NE;
     const double* ulRr = su + 2 * NE;
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kBrWarps * 32) evaluate_br_kernel(EvalArgs a)
                 const double pot = s.pot_b * exp(-(ra * ra) / 2.0);
                 if (lower && inside) potential += pot;
                 BrAcc acc = { 0.0, 0.0, 0.0, 0.0 };
-                br_pieces<true>(s, knots, inside ? r : s.rmax, 2.0 / r, lower && inside, ext, ugRr, ugIr, ulRr, ulIr, acc);
+                br_pieces<true>(s, tb, inside ? r : s.rmax, 2.0 / r, lower && inside, ext, ugRr, ugIr, ulRr, ulIr, acc);
                 const double ex = vx / r, ey = vy / r, ez = vz / r; // :361-364
                 const double gR = inside ? acc.gR : 0.0, gI = inside ? acc.gI : 0.0;
                 fRx = fma(gR, ex, fRx); fRy = fma(gR, ey, fRy); fRz = fma(gR, ez, fRz);
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kBrWarps * 32) evaluate_br_kernel(EvalArgs a)
             // box basis, one coordinate at a time (:378-416); sign = vecrni[a] < 0 ? -1 : 1
             {
                 BrAcc acc = { 0.0, 0.0, 0.0, 0.0 };
-                br_pieces<false>(s, knots, fabs(vx), 0.0, lower, ext + K, ugRr + K, ugIr + K, ulRr + K, ulIr + K, acc);
+                br_pieces<false>(s, tb, fabs(vx), 0.0, lower, ext + K, ugRr + K, ugIr + K, ulRr + K, ulIr + K, acc);
                 const double sg = vx < 0 ? -1.0 : 1.0;
                 fRx = fma(acc.gR, sg, fRx);
                 fIx = fma(acc.gI, sg, fIx);
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(kBrWarps * 32) evaluate_br_kernel(EvalArgs a)
             }
             {
                 BrAcc acc = { 0.0, 0.0, 0.0, 0.0 };
-                br_pieces<false>(s, knots, fabs(vy), 0.0, lower, ext + K, ugRr + K, ugIr + K, ulRr + K, ulIr + K, acc);
+                br_pieces<false>(s, tb, fabs(vy), 0.0, lower, ext + K, ugRr + K, ugIr + K, ulRr + K, ulIr + K, acc);
                 const double sg = vy < 0 ? -1.0 : 1.0;
                 fRy = fma(acc.gR, sg, fRy);
                 fIy = fma(acc.gI, sg, fIy);
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kBrWarps * 32) evaluate_br_kernel(EvalArgs a)
             }
             {
                 BrAcc acc = { 0.0, 0.0, 0.0, 0.0 };
-                br_pieces<false>(s, knots, fabs(vz), 0.0, lower, ext + K, ugRr + K, ugIr + K, ulRr + K, ulIr + K, acc);
+                br_pieces<false>(s, tb, fabs(vz), 0.0, lower, ext + K, ugRr + K, ugIr + K, ulRr + K, ulIr + K, acc);
                 const double sg = vz < 0 ? -1.0 : 1.0;
                 fRz = fma(acc.gR, sg, fRz);
                 fIz = fma(acc.gI, sg, fIz);
