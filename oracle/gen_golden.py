@@ -140,6 +140,14 @@ def bc_rows(d, system, P, K):
     return rows
 
 
+def pad3(a):
+    """[N][DIM] -> [N][3], unused coordinates zero: positions and drifts travel three-dimensional over the C ABI."""
+    a = np.asarray(a, np.float64)
+    out = np.zeros((a.shape[0], 3))
+    out[:, :a.shape[1]] = a
+    return out
+
+
 def pack_eval(name, system, scal, arrays, moves, keep_tables="full", subset=(0, 1, 2, 3)):
     with tempfile.TemporaryDirectory() as td:
         cp, op = os.path.join(td, "case.txt"), os.path.join(td, "out.txt")
@@ -148,11 +156,11 @@ def pack_eval(name, system, scal, arrays, moves, keep_tables="full", subset=(0, 
         d = parse_dump(op)
     out = {
         "system": np.array(system),
-        "N": np.array(scal["N"]), "DIM": np.array(3), "LBOX": np.array(scal["LBOX"]),
+        "N": np.array(scal["N"]), "DIM": np.array(scal.get("DIM", 3)), "LBOX": np.array(scal["LBOX"]),
         "N_PARAM": np.array(scal["N_PARAM"]),
         "SYSTEM_PARAMS": np.asarray(arrays["SYSTEM_PARAMS"], np.float64),
         "time": np.array(scal.get("time", 0.0)),
-        "R": np.asarray(arrays["R"], np.float64).reshape(-1, 3),
+        "R": pad3(np.asarray(arrays["R"], np.float64).reshape(-1, scal.get("DIM", 3))),
         "uR": np.asarray(arrays["uR"], np.float64), "uI": np.asarray(arrays["uI"], np.float64),
         "phiR": np.array(scal.get("phiR", 0.0)), "phiI": np.array(scal.get("phiI", 0.0)),
         "moves": np.asarray(moves, np.float64).reshape(-1, 4),
@@ -167,7 +175,7 @@ def pack_eval(name, system, scal, arrays, moves, keep_tables="full", subset=(0, 
         if k in d:
             out[k] = d[k]
     FR, FI = contract_drift(d, out["uR"], out["uI"], system)
-    out["drift_r"], out["drift_i"] = FR, FI
+    out["drift_r"], out["drift_i"] = pad3(FR), pad3(FI)
     sD, sD2 = d["sD"], d["sD2"]
     # particle-weighted checksums of the full tables (plain sums cancel pairwise by antisymmetry)
     wn = 1.0 + 0.5 * np.sin(np.arange(sD.shape[1]))
@@ -794,6 +802,56 @@ def gen_inhcontact():
     pack_eval_inhcontact("inhcontact_n20_equil", scal2, dict(arr2, R=x3), moves1d(x3))
 
 
+def gen_lowdim():
+    """The two spline-table systems in one and two dimensions, from the reference's own low-dimensional configs:
+    config/BosonsBulk2D.config (N = 16, L = 4, N_PARAM = 40), config/NUBosonsBulkPB2D.config (N = 25, N_PARAM = 100, grid up
+    to the half diagonal), config/Rydberg2D.config (NUBosonsBulkPB, N = 50, grid to L/2: the reflection rule is active) and
+    config/BosonsBulk1D.config (N = 20, N_PARAM = 100)."""
+    rng = np.random.default_rng(2)
+
+    def load(name):
+        t = open(os.path.join(REF, "config", name)).read()
+        return json.loads(re.sub(r"(\d)\.(\s*[,\]\}])", r"\g<1>.0\2", t))
+
+    def lattice(N, L, D):
+        m = int(np.ceil(N ** (1.0 / D) - 1e-9))
+        g = (np.arange(m) + 0.5) * (L / m) - L / 2
+        X = np.stack(np.meshgrid(*([g] * D), indexing="ij"), axis=-1).reshape(-1, D)[:N]      # first N sites if N != m^D
+        return X + rng.uniform(-0.05, 0.05, X.shape) * (L / m)
+
+    def moves_d(R, D, n=6, sigma=0.4):
+        out = []
+        for _ in range(n):
+            p = int(rng.integers(0, R.shape[0]))
+            new = np.zeros(3)
+            new[:D] = R[p] + rng.normal(0, sigma, D)
+            out.append([p] + list(new))
+        return out
+
+    for cfgname, system, tag, L in (("BosonsBulk2D.config", "BosonsBulk", "bosonsbulk2d_n16", 4.0),
+                                    ("NUBosonsBulkPB2D.config", "NUBosonsBulkPB", "nubosonsbulkpb2d_n25", 5.0),
+                                    ("Rydberg2D.config", "NUBosonsBulkPB", "rydberg2d_n50", None),
+                                    ("BosonsBulk1D.config", "BosonsBulk", "bosonsbulk1d_n20", 20.0)):
+        cfg = load(cfgname)
+        N, D, P = int(cfg["N"]), int(cfg["DIM"]), int(cfg["N_PARAM"])
+        L = float(cfg["LBOX"]) if L is None else L
+        nurbs = system == "NUBosonsBulkPB"
+        grid = np.array(cfg["NURBS_GRID"], dtype=np.float64) if nurbs else None
+        rmax = float(grid[-1]) if nurbs else L / 2
+        uR, uI = smooth_params(P, rmax, w_r=0.3 * rmax, c_i=0.5 * rmax, w_i=0.2 * rmax)
+        scal = dict(N=N, DIM=D, LBOX=L, N_PARAM=P, USE_NURBS=1 if nurbs else 0, time=0.0, phiR=0.03, phiI=0.0,
+                    GR_BIN_COUNT=int(cfg.get("GR_BIN_COUNT") or 50))
+        arr = dict(uR=uR, uI=uI, SYSTEM_PARAMS=cfg["SYSTEM_PARAMS"])
+        if nurbs:
+            arr["NURBS_GRID"] = grid
+        R0 = lattice(N, L, D)
+        mc = run_mc(system, dict(scal, MC_STEP=float(cfg["MC_STEP"]), MC_NSTEPS=1, MC_NTHERMSTEPS=N * 100, seed=3), dict(arr, R=R0))
+        R1 = mc["R_final"].reshape(N, D)
+        mv = moves_d(R1, D)
+        # (the harness reads DIM coordinates of a move and ignores the zero padding)
+        pack_eval(tag + "_equil", system, scal, dict(arr, R=R1), mv)
+
+
 def gen_min_image():
     """Reference minimum-image displacement on edge cases + random inputs (Utils.cpp:266-281, 352-382)."""
     rng = np.random.default_rng(99)
@@ -923,7 +981,7 @@ def main():
     if not os.path.exists(HARNESS):
         sys.exit("build the oracle first: make -C oracle/ref_build")
     which = sys.argv[1:] or ["min_image", "bosonsbulk", "bosonsbulk_mc", "bosonsbulk_mc_headline", "nubosonsbulkpb", "nubosonsbulkpb_full", "hebulk", "hedrop",
-                             "mixture", "observables", "he_observables", "mixture_observables", "evolution", "boxradial", "mixture_4th", "more_configs", "inhcontact"]
+                             "mixture", "observables", "he_observables", "mixture_observables", "evolution", "boxradial", "mixture_4th", "more_configs", "inhcontact", "lowdim"]
     for w in which:
         globals()["gen_" + w]()
 

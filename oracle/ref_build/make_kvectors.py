@@ -32,3 +32,16 @@ with open(os.path.join(out, "kVectors1D.json"), "w") as f:
     json.dump({"data": [[[k]] for k in range(1, 401)]}, f)
 with open(os.path.join(out, "kNorm1D.csv"), "w") as f:
     f.write("\n".join(repr(float(k)) for k in range(1, 401)) + "\n")
+
+# two-dimensional shells (BosonsBulk / NUBosonsBulkPB with DIM = 2 read kVectors2D.json / kNorm2D.csv)
+shells2 = {}
+for x in range(m + 1):
+    for y in range(m + 1):
+        n2 = x * x + y * y
+        if 0 < n2 <= m * m:
+            shells2.setdefault(n2, []).append([x, y])
+keys2 = sorted(shells2)[:120]
+with open(os.path.join(out, "kVectors2D.json"), "w") as f:
+    json.dump({"data": [sorted(shells2[k]) for k in keys2]}, f)
+with open(os.path.join(out, "kNorm2D.csv"), "w") as f:
+    f.write("\n".join(repr(math.sqrt(k)) for k in keys2) + "\n")

@@ -108,7 +108,7 @@ struct tdvmc_gpu_handle
     // system (host copies)
     int N = 0, Np = 0, P = 0, K = 0, pair_rule = 0, tail_param = 0, n_other = 9, kind = 0, n_ext = 0, gr_bins = 0;
     double he_rs = 0, core_m = 0, he_hl = 0, r_split2 = 1e300, r_tail = 1e300, gr_max = 0, u_core = 0, u_const = 0, u_lin = 0;
-    int n_short = 0, potential = 0, rho_bins = 0, use_phi = 0, periodic = 1;
+    int n_short = 0, potential = 0, rho_bins = 0, use_phi = 0, periodic = 1, dim = 3;
     // BosonMixtureCluster
     int n_types = 0, mix_order = 3;
     std::vector<int> mix_pair_type, mix_pot;
@@ -646,6 +646,7 @@ SysDev tdvmc_gpu_handle::sysdev() const
     s.first_bin = first_bin; s.nbins = nbins; s.ncell = ncell; s.uniform = uniform;
     s.L = L; s.Linv = L > 0.0 ? 1.0 / L : 0.0; s.Lhalf = L / 2.0; // src/TDVMC.cpp:535-536
     s.kind = kind; s.n_ext = n_ext; s.gr_bins = gr_bins;
+    s.dim = dim; s.dm1 = dim - 1.0;
     s.periodic = periodic; s.n_short = n_short; s.potential = potential; s.rho_bins = rho_bins; s.use_phi = use_phi;
     s.rmax = kind == TDVMC_SYSTEM_HE_BULK ? L / 2.0 : ((kind != TDVMC_SYSTEM_SPLINE_TABLE && kind != TDVMC_SYSTEM_BOX_RADIAL) ? 1e300 : knots[K]); // HeBulk.cpp:54
     s.n_types = n_types;
@@ -711,7 +712,8 @@ int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed,
         g_create_error = "struct_size mismatch (ABI version)";
         return -1;
     }
-    if ((sd->dim != 3 && !(sd->dim == 1 && sd->system_kind == TDVMC_SYSTEM_INH_CONTACT)) || sd->n_particles < 2 || sd->n_params < 1 || sd->n_splines < 4 || ed->n_walkers < 1 || sd->n_other < 3 ||
+    if ((sd->dim != 3 && !(sd->dim == 1 && sd->system_kind == TDVMC_SYSTEM_INH_CONTACT) &&
+         !((sd->dim == 1 || sd->dim == 2) && sd->system_kind == TDVMC_SYSTEM_SPLINE_TABLE)) || sd->n_particles < 2 || sd->n_params < 1 || sd->n_splines < 4 || ed->n_walkers < 1 || sd->n_other < 3 ||
         sd->tail_param < -1 || sd->tail_param >= sd->n_params || (!(sd->lbox > 0.0) && sd->system_kind != TDVMC_SYSTEM_HE_DROP && sd->system_kind != TDVMC_SYSTEM_MIXTURE) || sd->n_ext < sd->n_splines ||
         (sd->system_kind != TDVMC_SYSTEM_SPLINE_TABLE && sd->system_kind != TDVMC_SYSTEM_HE_BULK &&
          sd->system_kind != TDVMC_SYSTEM_HE_DROP && sd->system_kind != TDVMC_SYSTEM_MIXTURE &&
@@ -775,6 +777,7 @@ int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed,
     h->L = sd->lbox;
     h->hbar = sd->hbar2_2m;
     h->kind = sd->system_kind;
+    h->dim = sd->dim;
     h->n_ext = sd->n_ext;
     if (sd->knots) h->knots.assign(sd->knots, sd->knots + h->K + (sd->system_kind == TDVMC_SYSTEM_INH_CONTACT ? 8 : 4));
     if (sd->system_kind == TDVMC_SYSTEM_INH_CONTACT) h->n_short = sd->n_splines_first;
@@ -1648,6 +1651,7 @@ ObsArgs make_obs_args(tdvmc_gpu_handle* h, const tdvmc_observable_desc* od, cons
 int tdvmc_gpu_observables_fixed(tdvmc_gpu_handle* h, const tdvmc_observable_desc* od, const double* R, int32_t n_cfg, double* gr,
                                 double* sk)
 {
+    if (h && h->dim != 3) return fail(h, "observables: the g(r) / S(k) pass is offered for DIM = 3 only");
     if (!h || !R || n_cfg < 1) return h ? fail(h, "observables_fixed: bad arguments") : -1;
     if (int rc = check_observable_desc(h, od)) return rc;
     CK(cudaSetDevice(h->device));
@@ -1687,6 +1691,7 @@ int tdvmc_gpu_observables_fixed(tdvmc_gpu_handle* h, const tdvmc_observable_desc
 int tdvmc_gpu_sample_observables(tdvmc_gpu_handle* h, const tdvmc_observable_desc* od, int32_t n_samples, int32_t n_therm,
                                  int32_t n_init, double* gr, double* sk)
 {
+    if (h && h->dim != 3) return fail(h, "observables: the g(r) / S(k) pass is offered for DIM = 3 only");
     if (!h) return -1;
     if (int rc = need_params(h)) return rc;
     if (int rc = check_observable_desc(h, od)) return rc;

@@ -36,6 +36,8 @@ struct SysDev
     int use_phi;      // wf = exp(exponent + phiR) (HeDrop.cpp:783) or exp(exponent) (HeBulk.cpp:500)
     int n_ext;        // columns of the parameter map: K spline sums + analytic extras
     int gr_bins;      // g(r) bins carried in other[] (HeBulk: 100)
+    int dim;          // DIM of the spline-table systems (1, 2 or 3; unused coordinates stay zero), else 3
+    double dm1;       // DIM - 1: secondDerivativeFactor of BosonsBulk.cpp:319, NUBosonsBulkPB.cpp:392
     double L, Linv, Lhalf;   // LBOX, 1/LBOX, LBOX/2 (src/TDVMC.cpp:535-536)
     double rmax;             // maxDistance = knots[K]
     double hbar;             // HBAR2_2M

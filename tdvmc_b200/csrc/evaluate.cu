@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kerne
                         const double* w = m.rec + (size_t)(bin - s.first_bin) * kRecStride;
                         const double r2 = r * r;
                         const double rinv = rcp_refined(r);
-                        const double f2 = 2.0 * rinv; // (DIM - 1) / r, BosonsBulk.cpp:319-322
+                        const double f2 = s.dm1 * rinv; // (DIM - 1) / r, BosonsBulk.cpp:319-322
                         double gR = 0.0, gI = 0.0;
 #pragma unroll
                         for (int p = 0; p < 4; p++)
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(384, 2) evaluate_rowwise_kernel(EvalArgs a)
                 const double* w = m.rec + (size_t)(bin - s.first_bin) * kRecStride;
                 const double r2 = r * r;
                 const double rinv = 1.0 / r;
-                const double f2 = 2.0 * rinv; // (DIM - 1) / r, BosonsBulk.cpp:319-322
+                const double f2 = s.dm1 * rinv; // (DIM - 1) / r, BosonsBulk.cpp:319-322
                 double gR = 0.0, gI = 0.0;
 #pragma unroll
                 for (int p = 0; p < 4; p++)

@@ -182,11 +182,13 @@ __global__ void __launch_bounds__(GROUP == 32 ? kSweepMaxThreadsWarp : kSweepMax
             const double ddy = __shfl_sync(FULL_MASK, mine.dy, sidx, GROUP);
             const double ddz = __shfl_sync(FULL_MASK, mine.dz, sidx, GROUP);
             const double log_u = __shfl_sync(FULL_MASK, mine.log_u, sidx, GROUP);
+            // DIM < 3 (BosonsBulk / NUBosonsBulkPB in one or two dimensions): src/TDVMC.cpp:872-875 moves DIM coordinates
+            const double ddy_ = s.dim > 1 ? ddy : 0.0, ddz_ = s.dim > 2 ? ddz : 0.0;
 
             const double ox = px[p], oy = py[p], oz = pz[p];
             const double nx = OPEN ? ox + ddx : wrap_fast(ox + ddx, L, Linv); // src/TDVMC.cpp:872-875, kept in the first cell
-            const double ny = OPEN ? oy + ddy : wrap_fast(oy + ddy, L, Linv);
-            const double nz = OPEN ? oz + ddz : wrap_fast(oz + ddz, L, Linv);
+            const double ny = OPEN ? oy + ddy_ : wrap_fast(oy + ddy_, L, Linv);
+            const double nz = OPEN ? oz + ddz_ : wrap_fast(oz + ddz_, L, Linv);
 
             double delta = 0.0;
 #pragma unroll UNROLL

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kTabWarps * 32) tables_kernel(TableArgs a, int
                 const double* w = m.rec + (size_t)(bin - s.first_bin) * kRecStride;
                 const double r2 = r * r;
                 const double ex = vx / r, ey = vy / r, ez = vz / r; // BosonsBulk.cpp:304-307
-                const double f2 = 2.0 / r;                          // secondDerivativeFactor / rni
+                const double f2 = s.dm1 / r;                        // secondDerivativeFactor / rni
 #pragma unroll
                 for (int p = 0; p < 4; p++)
                 {

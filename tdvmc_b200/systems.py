@@ -111,7 +111,7 @@ def _csr(rows):
     return ptr, np.array(col, dtype=np.int32), np.array(val, dtype=np.float64)
 
 
-def bosons_bulk(n_particles, lbox, n_params, system_params=(1.0, 1.0), nurbs_grid=None, weights=None):
+def bosons_bulk(n_particles, lbox, n_params, system_params=(1.0, 1.0), nurbs_grid=None, weights=None, dim=3):
     """``BosonsBulk`` (BosonsBulk.cpp:49-156).
 
     Knots: uniform ``(i L/2)/(P-1)``, i=-3..P+2 (:61-67) or a mirrored NURBS grid (:35-44).
@@ -130,11 +130,11 @@ def bosons_bulk(n_particles, lbox, n_params, system_params=(1.0, 1.0), nurbs_gri
     rows += [[(K - 3, 1.0), (K - 1, 1.0)], [(K - 2, 1.0)]]
     ptr, col, val = _csr(rows)
     return SystemSpec("BosonsBulk", n_particles, n_params, float(lbox), knots, np.ascontiguousarray(weights), ptr, col, val,
-                      PAIR_RULE_CUT, np.asarray(system_params, dtype=np.float64), n_other=9, tail_param=n_params - 1)
+                      PAIR_RULE_CUT, np.asarray(system_params, dtype=np.float64), n_other=9, tail_param=n_params - 1, dim=int(dim))
 
 
 def nu_bosons_bulk_pb(n_particles, lbox, n_params, nurbs_grid, system_params=(0.0, 0.0, 0.0, 0.1, 50.0),
-                      gr_bin_count=400, weights=None):
+                      gr_bin_count=400, weights=None, dim=3):
     """``NUBosonsBulkPB`` (NUBosonsBulkPB.cpp:53-216): non-uniform knots, periodic-box reflection.
 
     ``K = P + 3`` (:71); map ``O_i = ss[i+1]``, ``O_1 += ss[0]``, ``O_{P-1} += ss[K-2] + ss[K-1]`` (:219-232);
@@ -152,7 +152,7 @@ def nu_bosons_bulk_pb(n_particles, lbox, n_params, nurbs_grid, system_params=(0.
     ptr, col, val = _csr(rows)
     return SystemSpec("NUBosonsBulkPB", n_particles, n_params, float(lbox), knots, np.ascontiguousarray(weights), ptr, col, val,
                       PAIR_RULE_REFLECT, np.asarray(system_params, dtype=np.float64), n_other=9 + int(gr_bin_count),
-                      tail_param=n_params - 1)
+                      tail_param=n_params - 1, dim=int(dim))
 
 
 def nu_bosons_bulk_pb_box_and_radial(n_particles, lbox, n_params, nurbs_grid, system_params=(0.1, 50.0), gr_bin_count=400,
@@ -396,11 +396,12 @@ def from_golden(g):
         if not np.array_equal(np.array(mine), ref) or spec.extra["r_tail"] != float(g["rij_tail"]):
             raise AssertionError("HeDrop set-up differs from the reference dump")
         return spec
+    dim = int(g["DIM"]) if "DIM" in getattr(g, "files", g) else 3
     if name == "BosonsBulk":
-        spec = bosons_bulk(N, L, P, g["SYSTEM_PARAMS"], weights=g["spline_weights"])
+        spec = bosons_bulk(N, L, P, g["SYSTEM_PARAMS"], weights=g["spline_weights"], dim=dim)
     elif name == "NUBosonsBulkPB":
         spec = nu_bosons_bulk_pb(N, L, P, g["NURBS_GRID"], g["SYSTEM_PARAMS"], weights=g["spline_weights"],
-                                 gr_bin_count=len(g["other_expectation_values"]) - 9)
+                                 gr_bin_count=len(g["other_expectation_values"]) - 9, dim=dim)
     elif name == "InhContactBosons":
         part = lambda q: dict(knots=g["knots_" + q], weights=g["spline_weights_" + q], bc_start=g["bc_start_" + q],
                               bc_end=g["bc_end_" + q], np=g["np_" + q], node_spacing=float(g["node_spacing_" + q]))

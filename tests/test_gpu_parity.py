@@ -1503,3 +1503,74 @@ def test_multistage_integrators_on_device_match_host_mirror(capi, golden, method
     h2.set_params(uR1, uI1, pR1, pI1, 0.0)
     assert h2.evaluate_fixed(src["R"][None])["e_r"][0] == e_dev["e_r"][0]
     h2.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# BosonsBulk / NUBosonsBulkPB with DIM = 2 and DIM = 1 (config/BosonsBulk2D, NUBosonsBulkPB2D, Rydberg2D, BosonsBulk1D):
+# same kernels, unused coordinates zero, secondDerivativeFactor = DIM - 1, DIM Gaussian components per move
+# ---------------------------------------------------------------------------------------------------
+LOWDIM_CASES = ["bosonsbulk2d_n16_equil", "nubosonsbulkpb2d_n25_equil", "rydberg2d_n50_equil", "bosonsbulk1d_n20_equil"]
+
+
+@pytest.mark.parametrize("name", LOWDIM_CASES)
+def test_low_dimensional_fixed_configuration(capi, golden, name):
+    g = golden(name)
+    D = int(g["DIM"])
+    spec, h = make_handle(capi, g)
+    r = h.evaluate_fixed(g["R"])
+    assert rel(r["ss"][0], g["spline_sums"]) < 1e-13 and r["outer"][0] == float(g["outer_sum"])
+    assert rel(r["O"][0], g["local_operators"]) < RTOL
+    assert abs(r["exponent"][0] - float(g["exponent"])) < RTOL * abs(float(g["exponent"]))
+    assert abs(r["e_r"][0] - float(g["local_energy_r"])) < RTOL * abs(float(g["local_energy_r"]))
+    assert abs(r["e_i"][0] - float(g["local_energy_i"])) < RTOL * abs(float(g["local_energy_i"]))
+    for key, u in (("drift_r", g["uR"]), ("drift_i", g["uI"])):
+        scale = max(np.max(np.abs(g[key])), drift_term_scale(spec, g["R"], u))
+        assert np.max(np.abs(r[key][0] - g[key])) < RTOL * scale, key
+        assert np.all(r[key][0][:, D:] == 0.0)
+    want, got = g["other_expectation_values"], r["other"][0]
+    for k in (0, 1, 2, 3, 6, 7):                                   # kinetic, potential, wf, exponent, Laplacian sums
+        assert abs(got[k] - want[k]) <= RTOL * max(abs(want[k]), abs(want[0])), k
+    sD, sD2 = h.tables_fixed(g["R"])
+    assert rel(sD[:, :, :D], g["sD"]) < 1e-13 and np.all(sD[:, :, D:] == 0.0) and rel(sD2, g["sD2"]) < 1e-13
+    q, d = h.quotient_fixed(g["R"], g["moves"])
+    d_ref = g["move_exponent_new"] - float(g["exponent"])
+    assert np.max(np.abs(d - d_ref)) < 5e-8 and np.max(np.abs(q / g["move_quotient"] - 1.0)) < 1e-7
+    with pytest.raises(capi.TdvmcError, match="DIM = 3"):
+        from tdvmc_b200 import observables
+        h.observables_fixed(observables.from_golden(golden("bosonsbulk_n64_obs")), g["R"][None])
+    h.close()
+
+
+@pytest.mark.parametrize("name", ["bosonsbulk2d_n16_equil", "rydberg2d_n50_equil", "bosonsbulk1d_n20_equil"])
+def test_low_dimensional_chain_and_estimators_match_oracle(capi, golden, name):
+    g = golden(name)
+    D, N = int(g["DIM"]), int(g["N"])
+    W, seed, mc_step = 5, 19, 0.4
+    n_samples, n_therm, n_init = 3, 2 * N, 4 * N
+    spec, h = make_handle(capi, g, n_walkers=W, seed=seed, mc_step=mc_step, max_samples=n_samples)
+    o = Oracle(spec, time=float(g["time"]))
+    shift = np.zeros(3)
+    shift[0] = 0.002
+    R0 = np.stack([g["R"] + shift * w for w in range(W)])
+    h.set_positions(R0)
+    h.sample_and_accumulate(n_samples, n_therm, n_init)
+    got = h.allreduce_and_fetch()
+    est = np.zeros(o.est_size())
+    acc, Rf = 0, []
+    for w in range(W):
+        r = o.sample_walker(np.ascontiguousarray(R0[w][:, :D]), g["uR"], g["uI"], float(g["phiR"]), seed, w, 0, n_init, n_samples,
+                            n_therm, mc_step, est)
+        acc += r["accepted"]
+        Rf.append(r["R"])
+    want = o.unpack_est(est, W * n_samples)
+    assert got["n_acceptances"] == acc and got["n_trials"] == W * (n_init + n_samples * n_therm) and acc > 0.2 * got["n_trials"]
+    Rg = h.get_positions()
+    assert np.all(Rg[:, :, D:] == 0.0)                             # the unused coordinates never move
+    dlt = Rg[:, :, :D] - np.stack(Rf)
+    dlt -= spec.lbox * np.round(dlt / spec.lbox)
+    assert np.max(np.abs(dlt)) < 1e-9
+    for k in ("O", "S", "OER", "OEI"):
+        assert rel(got[k], want[k]) < 1e-9, k
+    assert abs(got["e_r"][0] - want["e_r"]) < 1e-9 * abs(want["e_r"])
+    assert abs(got["e_i"][0] - want["e_i"]) < 1e-9 * max(abs(want["e_i"]), 1e-3 * abs(want["e_r"]))
+    h.close()

@@ -388,3 +388,31 @@ def test_inhcontact_sampler_statistics_match_reference(golden):
     sem = blocks.std(axis=0, ddof=1) / np.sqrt(nb)
     dev = np.abs(rows.mean(axis=0) - g["local_operators"]) / (np.sqrt(2.0) * np.maximum(sem, 1e-6))
     assert dev.max() < 5.0, dev.max()
+
+
+# ---------------------------------------------------------------------------------------------------
+# BosonsBulk / NUBosonsBulkPB in one and two dimensions (the reference's own low-dimensional configs)
+# ---------------------------------------------------------------------------------------------------
+LOWDIM_CASES = ["bosonsbulk2d_n16_equil", "nubosonsbulkpb2d_n25_equil", "rydberg2d_n50_equil", "bosonsbulk1d_n20_equil"]
+
+
+@pytest.mark.parametrize("name", LOWDIM_CASES)
+def test_low_dimensional_fixed_configuration_matches_reference(golden, name):
+    g = golden(name)
+    spec = systems.from_golden(g)
+    D = int(g["DIM"])
+    assert spec.dim == D and D < 3 and np.all(g["R"][:, D:] == 0.0)
+    o = Oracle(spec, time=float(g["time"]))
+    R = np.ascontiguousarray(g["R"][:, :D])
+    r = o.evaluate(R, g["uR"], g["uI"], float(g["phiR"]))
+    assert rel(r["ss"], g["spline_sums"]) < 1e-14 and r["outer"] == float(g["outer_sum"])
+    assert rel(r["O"], g["local_operators"]) < 1e-14
+    assert abs(r["exponent"] - float(g["exponent"])) < 1e-12 * abs(float(g["exponent"]))
+    assert rel(r["e_r"], g["local_energy_r"]) < 1e-12 and rel(r["e_i"], g["local_energy_i"]) < 1e-12
+    assert rel(r["other"], g["other_expectation_values"][:9]) < 1e-12
+    assert rel(r["drift_r"], g["drift_r"][:, :D]) < RTOL and rel(r["drift_i"], g["drift_i"][:, :D]) < RTOL
+    assert r["sD"].shape == g["sD"].shape == (spec.n_splines, spec.n_particles, D)
+    assert np.array_equal(r["sD"], g["sD"]) and np.array_equal(r["sD2"], g["sD2"])
+    for m, q_ref, en_ref in zip(g["moves"], g["move_quotient"], g["move_exponent_new"]):
+        q, en, _ = o.quotient(R, int(m[0]), m[1:1 + D], g["uR"])
+        assert abs(en - en_ref) < 1e-12 * abs(en_ref) and abs(q - q_ref) < 1e-10 * q_ref
