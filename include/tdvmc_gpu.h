@@ -91,8 +91,9 @@ typedef struct tdvmc_system_desc
 {
     uint32_t struct_size;      /* sizeof(tdvmc_system_desc), for ABI evolution */
     int32_t n_particles;       /* N */
-    int32_t dim;               /* DIM: 3; also 1 or 2 for TDVMC_SYSTEM_SPLINE_TABLE (config/BosonsBulk2D, NUBosonsBulkPB2D, Rydberg2D,
-                                * BosonsBulk1D ...) and 1 for TDVMC_SYSTEM_INH_CONTACT.  Positions always travel as [N][3]; the
+    int32_t dim;               /* DIM: 3; also 1 or 2 for TDVMC_SYSTEM_SPLINE_TABLE and TDVMC_SYSTEM_BOX_RADIAL (config/BosonsBulk2D,
+                                * NUBosonsBulkPB2D, Rydberg2D, BosonsBulk1D, NUBosonsBulkPBBoxAndRadial2D ...) and 1 for
+                                * TDVMC_SYSTEM_INH_CONTACT.  Positions always travel as [N][3]; the
                                 * unused coordinates must be zero and stay zero */
     int32_t n_params;          /* N_PARAM */
     int32_t n_splines;         /* K = #knots - 4 (BosonsBulk.cpp:71) */

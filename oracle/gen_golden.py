@@ -852,6 +852,30 @@ def gen_lowdim():
         pack_eval(tag + "_equil", system, scal, dict(arr, R=R1), mv)
 
 
+def gen_boxradial_2d():
+    """config/NUBosonsBulkPBBoxAndRadial2D.config at its own size: N = 25, DIM = 2, rho = 1 -> L = 5, N_PARAM = 100."""
+    rng = np.random.default_rng(25)
+    cfg = json.loads(re.sub(r"(\d)\.(\s*[,\]\}])", r"\g<1>.0\2",
+                            open(os.path.join(REF, "config", "NUBosonsBulkPBBoxAndRadial2D.config")).read()))
+    N, P, D = int(cfg["N"]), int(cfg["N_PARAM"]), int(cfg["DIM"])
+    L = float(round((N / float(cfg["RHO"])) ** (1.0 / D), 9))
+    grid = np.array(cfg["NURBS_GRID"], dtype=np.float64)
+    uR, uI = boxradial_params(P, L / 2)
+    scal = dict(N=N, DIM=D, LBOX=L, N_PARAM=P, USE_NURBS=1, time=0.0, phiR=0.0, phiI=0.0, GR_BIN_COUNT=int(cfg["GR_BIN_COUNT"]))
+    arr = dict(uR=uR, uI=uI, SYSTEM_PARAMS=cfg["SYSTEM_PARAMS"], NURBS_GRID=grid)
+    g1 = (np.arange(5) + 0.5) * (L / 5) - L / 2
+    X, Y = np.meshgrid(g1, g1, indexing="ij")
+    R0 = np.stack([X.ravel(), Y.ravel()], axis=1) + rng.uniform(-0.05, 0.05, (N, 2))
+    mc = run_mc("NUBosonsBulkPBBoxAndRadial", dict(scal, MC_STEP=float(cfg["MC_STEP"]), MC_NSTEPS=1, MC_NTHERMSTEPS=N * 200, seed=15),
+                dict(arr, R=R0))
+    R1 = mc["R_final"].reshape(N, D)
+    moves = []
+    for _ in range(6):
+        p = int(rng.integers(0, N))
+        moves.append([p] + list(R1[p] + rng.normal(0, 0.4, D)) + [0.0])
+    pack_eval_boxradial("boxradial2d_n25_equil", scal, dict(arr, R=R1), moves)
+
+
 def gen_min_image():
     """Reference minimum-image displacement on edge cases + random inputs (Utils.cpp:266-281, 352-382)."""
     rng = np.random.default_rng(99)
@@ -911,10 +935,11 @@ def pack_eval_boxradial(name, scal, arrays, moves):
         write_case(cp, system, scal, arrays, moves)
         run("eval", cp, op)
         d = parse_dump(op)
-    out = {"system": np.array(system), "N": np.array(scal["N"]), "DIM": np.array(3), "LBOX": np.array(scal["LBOX"]),
+    D = int(scal.get("DIM", 3))
+    out = {"system": np.array(system), "N": np.array(scal["N"]), "DIM": np.array(D), "LBOX": np.array(scal["LBOX"]),
            "N_PARAM": np.array(scal["N_PARAM"]), "SYSTEM_PARAMS": np.asarray(arrays["SYSTEM_PARAMS"], np.float64),
            "NURBS_GRID": np.asarray(arrays["NURBS_GRID"], np.float64), "time": np.array(scal.get("time", 0.0)),
-           "R": np.asarray(arrays["R"], np.float64).reshape(-1, 3), "uR": np.asarray(arrays["uR"], np.float64),
+           "R": pad3(np.asarray(arrays["R"], np.float64).reshape(-1, D)), "uR": np.asarray(arrays["uR"], np.float64),
            "uI": np.asarray(arrays["uI"], np.float64), "phiR": np.array(scal.get("phiR", 0.0)),
            "phiI": np.array(scal.get("phiI", 0.0)), "moves": np.asarray(moves, np.float64).reshape(-1, 4)}
     for k in ("exponent", "exponent_wf", "wf", "local_energy_r", "local_energy_i", "local_operators", "local_operator_energy_r",
@@ -923,7 +948,7 @@ def pack_eval_boxradial(name, scal, arrays, moves):
               "half_length", "other_local_operators", "gr_bins", "gr_bin_volumes", "gr_node_point_spacing", "move_quotient",
               "move_exponent_new", "sD", "sD2", "sD_rad", "sD2_rad"):
         out[k] = d[k]
-    out["drift_r"], out["drift_i"] = boxradial_drift(d, out["uR"], out["uI"])
+    out["drift_r"], out["drift_i"] = (pad3(x) for x in boxradial_drift(d, out["uR"], out["uI"]))
     np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
     print(f"{name}: E_R={float(d['local_energy_r']):.12g} E_I={float(d['local_energy_i']):.12g} "
           f"exponent={float(d['exponent']):.12g} q={d['move_quotient']}")
@@ -981,7 +1006,7 @@ def main():
     if not os.path.exists(HARNESS):
         sys.exit("build the oracle first: make -C oracle/ref_build")
     which = sys.argv[1:] or ["min_image", "bosonsbulk", "bosonsbulk_mc", "bosonsbulk_mc_headline", "nubosonsbulkpb", "nubosonsbulkpb_full", "hebulk", "hedrop",
-                             "mixture", "observables", "he_observables", "mixture_observables", "evolution", "boxradial", "mixture_4th", "more_configs", "inhcontact", "lowdim"]
+                             "mixture", "observables", "he_observables", "mixture_observables", "evolution", "boxradial", "mixture_4th", "more_configs", "inhcontact", "lowdim", "boxradial_2d"]
     for w in which:
         globals()["gen_" + w]()
 

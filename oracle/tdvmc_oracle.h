@@ -99,6 +99,7 @@ int64_t oracle_sample_walker(const oracle_system* s, double* R, const double* uR
 typedef struct oracle_br
 {
     int32_t n_particles, n_params, n_splines, gr_bins; /* K = N_PARAM/2 + 3 splines per basis */
+    int32_t dim, pad;  /* DIM (3, or 2 / 1: R stays [N][3] with the unused coordinates zero) */
     double lbox;
     double r_max;       /* maxDistanceRad = nodesRad[size - 4] (NUBosonsBulkPBBoxAndRadial.cpp:96) */
     double pot_a, pot_b; /* Gauss potential b exp(-(r/a)^2/2), time switch applied (:290-297) */

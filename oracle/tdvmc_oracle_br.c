@@ -48,7 +48,7 @@ void oracle_br_values(const oracle_br* s, const double* R, double* ext)
             double vec[3];
             const double rni = oracle_min_image(s->lbox, 3, R + 3 * n, R + 3 * i, vec);
             if (rni < s->r_max) br_add_values(s, rni, ext);
-            for (int a = 0; a < 3; a++) br_add_values(s, fabs(vec[a]), ext + K);
+            for (int a = 0; a < s->dim; a++) br_add_values(s, fabs(vec[a]), ext + K);
         }
 }
 
@@ -122,11 +122,11 @@ void oracle_br_expectation(const oracle_br* s, const double* R, double wf, const
                 for (int c = 0; c < 3; c++) evec[c] = vec[c] / rni;
                 for (int c = 0; c < 3; c++)
                     for (int q = 0; q < 4; q++) sDr[((size_t)(bin - q) * N + n) * 3 + c] += tmp1[3 - q] * evec[c];
-                const double secondDerivativeFactor = 3 - 1.0;
+                const double secondDerivativeFactor = s->dim - 1.0;
                 for (int q = 0; q < 4; q++) sD2r[(size_t)(bin - q) * N + n] += tmp2[3 - q] + secondDerivativeFactor / rni * tmp1[3 - q];
             }
             if (i != n) /* :378-416 box basis, per coordinate */
-                for (int c = 0; c < 3; c++)
+                for (int c = 0; c < s->dim; c++)
                 {
                     const double rnia = fabs(vec[c]);
                     const int bin = br_bin(s, rnia);
@@ -251,10 +251,10 @@ double oracle_br_quotient(const oracle_br* s, const double* R, int particle, con
         double vec[3];
         double rni = oracle_min_image(s->lbox, 3, R + 3 * i, old_pos, vec);
         if (rni < s->r_max) br_add_values(s, rni, oldb);
-        for (int a = 0; a < 3; a++) br_add_values(s, fabs(vec[a]), oldb + K);
+        for (int a = 0; a < s->dim; a++) br_add_values(s, fabs(vec[a]), oldb + K);
         rni = oracle_min_image(s->lbox, 3, R + 3 * i, R + 3 * particle, vec);
         if (rni < s->r_max) br_add_values(s, rni, newb);
-        for (int a = 0; a < 3; a++) br_add_values(s, fabs(vec[a]), newb + K);
+        for (int a = 0; a < s->dim; a++) br_add_values(s, fabs(vec[a]), newb + K);
     }
     for (int k = 0; k < 2 * K; k++) ext_new[k] = fmax(0.0, ext[k] - oldb[k] + newb[k]); /* :713-720 */
     free(oldb);
@@ -292,7 +292,7 @@ int64_t oracle_br_sweep(const oracle_br* s, double* R, double* ext, double* expo
         for (int a = 0; a < 3; a++)
         {
             old_pos[a] = R[(size_t)p * 3 + a];
-            R[(size_t)p * 3 + a] += disp[a];
+            if (a < s->dim) R[(size_t)p * 3 + a] += disp[a];
         }
         const double q = oracle_br_quotient(s, R, p, old_pos, ext, *exponent, uR, ext_new, &exponent_new);
         int ok = 1, force = 0;

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kBrWarps * 32) evaluate_br_kernel(EvalArgs a)
                 const double pot = s.pot_b * exp(-(ra * ra) / 2.0);
                 if (lower && inside) potential += pot;
                 BrAcc acc = { 0.0, 0.0, 0.0, 0.0 };
-                br_pieces<true>(s, tb, inside ? r : s.rmax, 2.0 / r, lower && inside, ext, ugRr, ugIr, ulRr, ulIr, acc);
+                br_pieces<true>(s, tb, inside ? r : s.rmax, s.dm1 / r, lower && inside, ext, ugRr, ugIr, ulRr, ulIr, acc);
                 const double ex = vx / r, ey = vy / r, ez = vz / r; // :361-364
                 const double gR = inside ? acc.gR : 0.0, gI = inside ? acc.gI : 0.0;
                 fRx = fma(gR, ex, fRx); fRy = fma(gR, ey, fRy); fRz = fma(gR, ez, fRz);
@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(kBrWarps * 32) evaluate_br_kernel(EvalArgs a)
                 lR += acc.lR;
                 lI += acc.lI;
             }
+            if (s.dim > 1) // (the reference loops a < DIM, :378)
             {
                 BrAcc acc = { 0.0, 0.0, 0.0, 0.0 };
                 br_pieces<false>(s, tb, fabs(vy), 0.0, lower, ext + K, ugRr + K, ugIr + K, ulRr + K, ulIr + K, acc);
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(kBrWarps * 32) evaluate_br_kernel(EvalArgs a)
                 lR += acc.lR;
                 lI += acc.lI;
             }
+            if (s.dim > 2)
             {
                 BrAcc acc = { 0.0, 0.0, 0.0, 0.0 };
                 br_pieces<false>(s, tb, fabs(vz), 0.0, lower, ext + K, ugRr + K, ugIr + K, ulRr + K, ulIr + K, acc);
@@ -378,9 +380,11 @@ __global__ void __launch_bounds__(256, 3) sweep_br_kernel(SweepArgs a)
             const double ddz = __shfl_sync(FULL_MASK, mine.dz, sidx);
             const double log_u = __shfl_sync(FULL_MASK, mine.log_u, sidx);
             const double ox = px[p], oy = py[p], oz = pz[p];
+            const double ddy_ = s.dim > 1 ? ddy : 0.0, ddz_ = s.dim > 2 ? ddz : 0.0; // DIM coordinates move; an unused
+            // coordinate contributes the same box-spline constant u_box(0) to the old and the new exponent
             const double nx = wrap_fast(ox + ddx, L, Linv); // src/TDVMC.cpp:872-875, kept in the first cell
-            const double ny = wrap_fast(oy + ddy, L, Linv);
-            const double nz = wrap_fast(oz + ddz, L, Linv);
+            const double ny = wrap_fast(oy + ddy_, L, Linv);
+            const double nz = wrap_fast(oz + ddz_, L, Linv);
             double delta = 0.0;
             for (int i = lane; i < N; i += 32)
             {

@@ -423,7 +423,9 @@ int build_static_tables(tdvmc_gpu_handle* h)
         h->gr_max = h->L / 2.0;
         h->gr_spacing = h->gr_max / (double)h->gr_bins;
         std::vector<double> vol(h->gr_bins);
-        for (int i = 0; i < h->gr_bins; i++) vol[i] = 4.0 * M_PI * pow(h->gr_spacing * (i + 1), 3.0) / 3.0;
+        for (int i = 0; i < h->gr_bins; i++)
+            vol[i] = h->dim == 3 ? 4.0 * M_PI * pow(h->gr_spacing * (i + 1), 3.0) / 3.0
+                                 : (h->dim == 2 ? M_PI * pow(h->gr_spacing * (i + 1), 2.0) : 2.0 * (h->gr_spacing * (i + 1)));
         for (int i = h->gr_bins - 1; i > 0; i--) vol[i] = vol[i] - vol[i - 1];
         h->use_phi = 1;
         CK(upload(h->d_gr_vol, vol, h->stream));
@@ -713,7 +715,8 @@ int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed,
         return -1;
     }
     if ((sd->dim != 3 && !(sd->dim == 1 && sd->system_kind == TDVMC_SYSTEM_INH_CONTACT) &&
-         !((sd->dim == 1 || sd->dim == 2) && sd->system_kind == TDVMC_SYSTEM_SPLINE_TABLE)) || sd->n_particles < 2 || sd->n_params < 1 || sd->n_splines < 4 || ed->n_walkers < 1 || sd->n_other < 3 ||
+         !((sd->dim == 1 || sd->dim == 2) && (sd->system_kind == TDVMC_SYSTEM_SPLINE_TABLE || sd->system_kind == TDVMC_SYSTEM_BOX_RADIAL))) ||
+        sd->n_particles < 2 || sd->n_params < 1 || sd->n_splines < 4 || ed->n_walkers < 1 || sd->n_other < 3 ||
         sd->tail_param < -1 || sd->tail_param >= sd->n_params || (!(sd->lbox > 0.0) && sd->system_kind != TDVMC_SYSTEM_HE_DROP && sd->system_kind != TDVMC_SYSTEM_MIXTURE) || sd->n_ext < sd->n_splines ||
         (sd->system_kind != TDVMC_SYSTEM_SPLINE_TABLE && sd->system_kind != TDVMC_SYSTEM_HE_BULK &&
          sd->system_kind != TDVMC_SYSTEM_HE_DROP && sd->system_kind != TDVMC_SYSTEM_MIXTURE &&

@@ -156,7 +156,7 @@ def nu_bosons_bulk_pb(n_particles, lbox, n_params, nurbs_grid, system_params=(0.
 
 
 def nu_bosons_bulk_pb_box_and_radial(n_particles, lbox, n_params, nurbs_grid, system_params=(0.1, 50.0), gr_bin_count=400,
-                                     weights=None):
+                                     weights=None, dim=3):
     """``NUBosonsBulkPBBoxAndRadial`` (NUBosonsBulkPBBoxAndRadial.cpp:36-191).
 
     ``SetNodes`` (:36-62) mirrors the same NURBS grid into ``nodes`` (box splines, argument ``|x_ij|`` per coordinate) and
@@ -188,7 +188,7 @@ def nu_bosons_bulk_pb_box_and_radial(n_particles, lbox, n_params, nurbs_grid, sy
     half = lbox / 2.0
     return SystemSpec("NUBosonsBulkPBBoxAndRadial", n_particles, n_params, float(lbox), knots, np.ascontiguousarray(weights),
                       ptr, col, val, PAIR_RULE_CUT, np.asarray(system_params, dtype=np.float64), n_other=3 + int(gr_bin_count),
-                      tail_param=-1, kind=KIND_BOX_RADIAL, n_ext=2 * K,
+                      tail_param=-1, kind=KIND_BOX_RADIAL, n_ext=2 * K, dim=int(dim),
                       extra=dict(n_splines=K, gr_bins=int(gr_bin_count), half=half, gr_spacing=half / float(gr_bin_count),
                                  grad_swap=(K - 1, 2 * K - 1, PR - 1)))
 
@@ -366,6 +366,7 @@ def from_golden(g):
     """Build the spec of a tests/golden fixture, taking knots and spline table from the reference dump."""
     name = str(g["system"])
     N, L, P = int(g["N"]), float(g["LBOX"]), int(g["N_PARAM"])
+    dim = int(g["DIM"]) if "DIM" in getattr(g, "files", g) else 3
     if name == "HeBulk":
         spec = he_bulk(N, L, P)
         if spec.extra["h"] != float(g["node_point_spacing"]) or not np.array_equal(spec.extra["factors"], g["bc_factors"]):
@@ -396,7 +397,6 @@ def from_golden(g):
         if not np.array_equal(np.array(mine), ref) or spec.extra["r_tail"] != float(g["rij_tail"]):
             raise AssertionError("HeDrop set-up differs from the reference dump")
         return spec
-    dim = int(g["DIM"]) if "DIM" in getattr(g, "files", g) else 3
     if name == "BosonsBulk":
         spec = bosons_bulk(N, L, P, g["SYSTEM_PARAMS"], weights=g["spline_weights"], dim=dim)
     elif name == "NUBosonsBulkPB":
@@ -411,7 +411,7 @@ def from_golden(g):
         return spec
     elif name == "NUBosonsBulkPBBoxAndRadial":
         spec = nu_bosons_bulk_pb_box_and_radial(N, L, P, g["NURBS_GRID"], g["SYSTEM_PARAMS"], weights=g["spline_weights"],
-                                                gr_bin_count=len(g["other_expectation_values"]) - 3)
+                                                gr_bin_count=len(g["other_expectation_values"]) - 3, dim=dim)
         if not (np.array_equal(g["knots"], g["knots_rad"]) and np.array_equal(g["spline_weights"], g["spline_weights_rad"])):
             raise AssertionError("the reference's radial and box bases are expected to share knots and table")
     else:

@@ -36,6 +36,7 @@ class OracleMixStruct(C.Structure):
 
 class OracleBRStruct(C.Structure):
     _fields_ = [("n_particles", C.c_int32), ("n_params", C.c_int32), ("n_splines", C.c_int32), ("gr_bins", C.c_int32),
+                ("dim", C.c_int32), ("pad", C.c_int32),
                 ("lbox", C.c_double), ("r_max", C.c_double), ("pot_a", C.c_double), ("pot_b", C.c_double), ("gr_max", C.c_double),
                 ("gr_spacing", C.c_double), ("gr_volumes", dp), ("knots", dp), ("weights", dp), ("map_ptr", ip), ("map_col", ip),
                 ("map_val", dp)]
@@ -296,11 +297,16 @@ class OracleHe:
         return Oracle.unpack_est(self, est, n)
 
 
-def br_shell_volumes(half, n_bins):
+def br_shell_volumes(half, n_bins, dim=3):
     """grBinVolumes of NUBosonsBulkPBBoxAndRadial::InitSystem (:146-169), same operations in the same order."""
     import math
     spacing = half / float(n_bins)
-    v = [4.0 * math.pi * math.pow(spacing * (i + 1), 3.0) / 3.0 for i in range(n_bins)]
+    if dim == 3:
+        v = [4.0 * math.pi * math.pow(spacing * (i + 1), 3.0) / 3.0 for i in range(n_bins)]
+    elif dim == 2:
+        v = [math.pi * math.pow(spacing * (i + 1), 2.0) for i in range(n_bins)]
+    else:
+        v = [2.0 * (spacing * (i + 1)) for i in range(n_bins)]
     for i in range(n_bins - 1, 0, -1):
         v[i] = v[i] - v[i - 1]
     return np.array(v), spacing
@@ -313,12 +319,12 @@ class OracleBR:
         self.spec = spec
         e = spec.extra
         a, b = spec.potential(time)
-        vol, spacing = br_shell_volumes(e["half"], e["gr_bins"])
+        vol, spacing = br_shell_volumes(e["half"], e["gr_bins"], spec.dim)
         self._keep = [vol, np.ascontiguousarray(spec.knots, np.float64), np.ascontiguousarray(spec.weights, np.float64),
                       np.ascontiguousarray(spec.map_ptr, np.int32), np.ascontiguousarray(spec.map_col, np.int32),
                       np.ascontiguousarray(spec.map_val, np.float64)]
         k = self._keep
-        self.sys = OracleBRStruct(spec.n_particles, spec.n_params, e["n_splines"], e["gr_bins"], spec.lbox, spec.r_max, a, b,
+        self.sys = OracleBRStruct(spec.n_particles, spec.n_params, e["n_splines"], e["gr_bins"], spec.dim, 0, spec.lbox, spec.r_max, a, b,
                                   e["half"], spacing, _d(k[0]), _d(k[1]), _d(k[2]), k[3].ctypes.data_as(ip),
                                   k[4].ctypes.data_as(ip), _d(k[5]))
         self.N, self.P, self.K = spec.n_particles, spec.n_params, e["n_splines"]

@@ -274,7 +274,8 @@ def test_he_structure_factor_oracle_matches_reference(golden, name):
 # ---------------------------------------------------------------------------------------------------
 # NUBosonsBulkPBBoxAndRadial: radial + box spline bases
 # ---------------------------------------------------------------------------------------------------
-BR_CASES = ["boxradial_n27_jittered", "boxradial_n27_equil", "boxradial_n64_equil"]
+BR_CASES = ["boxradial_n27_jittered", "boxradial_n27_equil", "boxradial_n64_equil",
+            "boxradial2d_n25_equil"]   # config/NUBosonsBulkPBBoxAndRadial2D.config (DIM = 2)
 
 
 @pytest.mark.parametrize("name", BR_CASES)
@@ -286,12 +287,14 @@ def test_boxradial_fixed_configuration_matches_reference(golden, name):
     o = OracleBR(spec, time=float(g["time"]))
     K = spec.extra["n_splines"]
     assert spec.r_max == float(g["max_distance_rad"]) and spec.extra["half"] == float(g["half_length"])
-    vol, spacing = br_shell_volumes(spec.extra["half"], spec.extra["gr_bins"])
+    vol, spacing = br_shell_volumes(spec.extra["half"], spec.extra["gr_bins"], spec.dim)
     assert np.array_equal(vol, g["gr_bin_volumes"]) and spacing == float(g["gr_node_point_spacing"])
     r = o.evaluate(g["R"], g["uR"], g["uI"], float(g["phiR"]))
     assert rel(r["ext"][:K], g["spline_sums_rad"]) < 1e-13 and rel(r["ext"][K:], g["spline_sums"]) < 1e-13
     # the four tables: same operations in the same order as the reference -> bit for bit
-    assert np.array_equal(r["tabD"][:K], g["sD_rad"]) and np.array_equal(r["tabD"][K:], g["sD"])
+    D = spec.dim
+    assert np.array_equal(r["tabD"][:K, :, :D], g["sD_rad"]) and np.array_equal(r["tabD"][K:, :, :D], g["sD"])
+    assert np.all(r["tabD"][:, :, D:] == 0.0)
     assert np.array_equal(r["tabD2"][:K], g["sD2_rad"]) and np.array_equal(r["tabD2"][K:], g["sD2"])
     assert rel(r["O"], g["local_operators"]) < 1e-13
     assert abs(r["exponent"] - float(g["exponent"])) < 1e-13 * abs(float(g["exponent"]))
