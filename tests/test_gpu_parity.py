@@ -482,7 +482,20 @@ def test_errors_are_loud(capi, golden):
         h.allreduce_and_fetch()                       # nothing accumulated
     with pytest.raises(capi.TdvmcError):
         h.reevaluate_stored()                         # no stored samples
+    with pytest.raises(capi.TdvmcError, match="nothing accumulated"):
+        h.solve_parameters_dot()                      # the device solve needs estimators
+    with pytest.raises(capi.TdvmcError, match="nothing accumulated"):
+        h.euler_step(1e-3, g["uR"], g["uI"], 0.0, 0.0)
     h.close()
+    # system descriptions the library does not offer are refused at creation, not later
+    bad = systems.from_golden(g)
+    bad.dim = 4
+    with pytest.raises(capi.TdvmcError, match="invalid system"):
+        capi.Handle(bad, 2)
+    inh = systems.from_golden(golden("inhcontact_n3_equil"))
+    inh.system_params = np.concatenate([inh.system_params, [0.0] * 5])     # the pulse extensions of GetExternalPotential
+    with pytest.raises(capi.TdvmcError, match="invalid system"):
+        capi.Handle(inh, 2)
 
 
 def test_cpp_host_adapter_matches_python_path(capi, golden, tmp_path):
