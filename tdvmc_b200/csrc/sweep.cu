@@ -57,6 +57,7 @@ __device__ __forceinline__ double group_sum(double v)
 // lanes per walker for a system of N particles
 static inline int sweep_group(const SysDev& s)
 {
+    if (s.dim < 3 && s.kind == 0) return 32; // the low-dimensional instance exists for whole-warp walkers only
     return s.N <= 8 ? 8 : (s.N <= 16 ? 16 : 32);
 }
 
@@ -105,7 +106,10 @@ __device__ __forceinline__ double pair_u(const SysDev& s, const double2* __restr
 
 // GROUP = lanes per walker (32, or 16 / 8 for systems of at most 16 / 8 particles, where a whole warp per walker would
 // leave most lanes without a partner: HeDrop's six atoms run four walkers per warp).
-template <bool UNIFORM, bool REFLECT, int UNROLL, bool HE = false, bool OPEN = false, int GROUP = 32>
+// LOWDIM: BosonsBulk / NUBosonsBulkPB with DIM = 1 or 2 (unused coordinates zero, only DIM Gaussian components move a
+// particle, src/TDVMC.cpp:872-875) - a separate instance, because even two predicated moves per proposal batch perturb the
+// register allocation of the three-dimensional kernel (measured: 651 vs 664 M walker-steps/s on the same GPU).
+template <bool UNIFORM, bool REFLECT, int UNROLL, bool HE = false, bool OPEN = false, int GROUP = 32, bool LOWDIM = false>
 __global__ void __launch_bounds__(GROUP == 32 ? kSweepMaxThreadsWarp : kSweepMaxThreads, kSweepMinBlocks) sweep_kernel(SweepArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -173,6 +177,11 @@ __global__ void __launch_bounds__(GROUP == 32 ? kSweepMaxThreadsWarp : kSweepMax
         mine.dx = mine.dy = mine.dz = 0.0;
         mine.log_u = 0.0;
         if (t0 + gl < a.n_steps) mine = make_proposal(a.seed, gw, a.first_step + (uint64_t)(t0 + gl), N, a.mc_step);
+        if (LOWDIM)
+        {
+            if (s.dim < 3) mine.dz = 0.0;
+            if (s.dim < 2) mine.dy = 0.0;
+        }
         const int nsub = (int)min((long long)GROUP, a.n_steps - t0);
 
         for (int sidx = 0; sidx < nsub; sidx++)
@@ -182,13 +191,11 @@ __global__ void __launch_bounds__(GROUP == 32 ? kSweepMaxThreadsWarp : kSweepMax
             const double ddy = __shfl_sync(FULL_MASK, mine.dy, sidx, GROUP);
             const double ddz = __shfl_sync(FULL_MASK, mine.dz, sidx, GROUP);
             const double log_u = __shfl_sync(FULL_MASK, mine.log_u, sidx, GROUP);
-            // DIM < 3 (BosonsBulk / NUBosonsBulkPB in one or two dimensions): src/TDVMC.cpp:872-875 moves DIM coordinates
-            const double ddy_ = s.dim > 1 ? ddy : 0.0, ddz_ = s.dim > 2 ? ddz : 0.0;
 
             const double ox = px[p], oy = py[p], oz = pz[p];
             const double nx = OPEN ? ox + ddx : wrap_fast(ox + ddx, L, Linv); // src/TDVMC.cpp:872-875, kept in the first cell
-            const double ny = OPEN ? oy + ddy_ : wrap_fast(oy + ddy_, L, Linv);
-            const double nz = OPEN ? oz + ddz_ : wrap_fast(oz + ddz_, L, Linv);
+            const double ny = OPEN ? oy + ddy : wrap_fast(oy + ddy, L, Linv);
+            const double nz = OPEN ? oz + ddz : wrap_fast(oz + ddz, L, Linv);
 
             double delta = 0.0;
 #pragma unroll UNROLL
@@ -320,6 +327,11 @@ static const void* sweep_fn_ug(const SysDev& s)
     const bool refl = s.pair_rule == 1;
     if (s.kind == 1) return (const void*)sweep_kernel<true, false, UNROLL, true, false, GROUP>;
     if (s.kind == 2) return (const void*)sweep_kernel<false, false, UNROLL, true, true, GROUP>;
+    if (s.dim < 3 && GROUP == 32 && UNROLL == 2) // (low-dimensional systems always run the default instance shape)
+        return s.uniform ? (refl ? (const void*)sweep_kernel<true, true, 2, false, false, 32, true>
+                                 : (const void*)sweep_kernel<true, false, 2, false, false, 32, true>)
+                         : (refl ? (const void*)sweep_kernel<false, true, 2, false, false, 32, true>
+                                 : (const void*)sweep_kernel<false, false, 2, false, false, 32, true>);
     return s.uniform ? (refl ? (const void*)sweep_kernel<true, true, UNROLL, false, false, GROUP>
                              : (const void*)sweep_kernel<true, false, UNROLL, false, false, GROUP>)
                      : (refl ? (const void*)sweep_kernel<false, true, UNROLL, false, false, GROUP>
@@ -328,6 +340,7 @@ static const void* sweep_fn_ug(const SysDev& s)
 
 static const void* sweep_fn(const SysDev& s)
 {
+    if (s.dim < 3 && s.kind == 0) return sweep_fn_ug<2, 32>(s);
     const int g = sweep_group(s);
     if (g == 8) return sweep_fn_ug<1, 8>(s);   // one partner per lane at most: nothing to unroll
     if (g == 16) return sweep_fn_ug<1, 16>(s);
