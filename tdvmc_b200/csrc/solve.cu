@@ -10,11 +10,11 @@
 //   CalculatePhiDot                                :1658-1682
 //
 // One CTA.  The lower triangle lives packed (row i at i(i+1)/2) in shared memory when it fits (P <= 230), else in a
-// global scratch buffer that stays in L2.  The factorisation is right-looking (column j is scaled, then subtracted from
-// the trailing triangle), which applies the products l_ik l_jk to element (i, j) in the order k = 0, 1, ... j-1 - the
-// order of the reference's `sum -= matrix[i][k] * matrix[j][k]` loop - and the two substitutions are column-oriented
-// for the same reason, so with -fmad=false every rounding step is the reference's and the result is bit-identical to
-// the host code it replaces (IEEE sqrt and division on both sides).  P <= 1024 (one thread per unknown in the solves).
+// global scratch buffer that stays in L2.  The factorisation goes column by column with one thread per row, each element
+// formed by the reference's own `sum -= matrix[i][k] * matrix[j][k]` loop (k ascending), and the two substitutions are
+// column-oriented so that every row's sum grows in the reference's order; with -fmad=false every rounding step is the
+// reference's and the result is bit-identical to the host code it replaces (IEEE sqrt and division on both sides).
+// P <= 1024 (one thread per unknown).
 #include "kernels.cuh"
 
 namespace tdvmc
@@ -97,33 +97,78 @@ __global__ void __launch_bounds__(1024, 1) solve_kernel(SolveArgs a)
     }
     __syncthreads();
 
-    // Cholesky, right-looking.  A pivot that is not positive leaves the ORIGINAL diagonal entry in place, as the
-    // reference does (:1577-1589, it only logs and sets doNotAcceptStep); the flag goes back to the caller.
-    for (int j = 0; j < P; j++)
+    // Cholesky, thread i owns row i: s = A[i][j] - sum_{k<j} L[i][k] L[j][k] with k ascending in registers - literally
+    // the reference's inner loop (:1568-1573), so the rounding sequence is its own; the rows j are read by every thread at
+    // the same address (broadcast), row i is private.  Each sum is one dependent chain of FP64 subtractions (about 40
+    // cycles per link), so kColBlock columns advance together: their chains are independent up to k = j0 and share the
+    // load of L[i][k]; then the columns of the block are finished in order, each adding its new term to the chains of
+    // the columns after it.  Two barriers per column (pivot known, column complete).  A pivot that is not positive
+    // leaves the ORIGINAL diagonal entry in place, as the reference does (:1577-1589, it only logs and sets
+    // doNotAcceptStep); the flag goes back to the caller.
+    // (History, P = 201: right-looking rank-1 updates by 32-wide rows 0.44 ms - 1.8 M warp-instructions, half the
+    // lanes idle, profiles/r01g_solve_ncu.txt; one column at a time with this row ownership 0.46 ms - the chain.)
+    constexpr int kColBlock = 4;
+    double* pivot = col; // col[0]: the pivot of the current column
+    for (int j0 = 0; j0 < P; j0 += kColBlock)
     {
-        const double piv = Lp[tri(j, j)];
-        double d;
-        if (piv > 0.0) d = sqrt(piv);
-        else
+        const int i = tid;
+        const int nb = min(kColBlock, P - j0);
+        const bool row = i >= j0 && i < P;
+        double sdot[kColBlock];
+        const double* ri = Lp + tri(row ? i : 0, 0);
+        if (row)
         {
-            d = diag0[j];
-            if (tid == 0) s_flag = 1;
+            const double* rj[kColBlock];
+#pragma unroll
+            for (int c = 0; c < kColBlock; c++)
+            {
+                const int j = min(j0 + c, P - 1);
+                rj[c] = Lp + tri(j, 0);
+                sdot[c] = (c < nb && i >= j0 + c) ? ri[j0 + c] : 0.0;
+            }
+#pragma unroll 2
+            for (int k = 0; k < j0; k++)
+            {
+                const double l = ri[k];
+#pragma unroll
+                for (int c = 0; c < kColBlock; c++) sdot[c] -= l * rj[c][k];
+            }
         }
-        for (int i = j + 1 + tid; i < P; i += T)
+#pragma unroll
+        for (int c = 0; c < kColBlock; c++)
         {
-            const double l = Lp[tri(i, j)] / d;
-            Lp[tri(i, j)] = l;
-            col[i] = l;
+            if (c < nb) // (uniform over the block)
+            {
+                const int j = j0 + c;
+                if (row && i == j)
+                {
+                    double d;
+                    if (sdot[c] > 0.0) d = sqrt(sdot[c]);
+                    else
+                    {
+                        d = diag0[j];
+                        s_flag = 1;
+                    }
+                    pivot[0] = d;
+                    Lp[tri(j, j)] = d;
+                }
+                __syncthreads();
+                double lij = 0.0;
+                if (row && i > j)
+                {
+                    lij = sdot[c] / pivot[0];
+                    Lp[tri(i, j)] = lij;
+                }
+                __syncthreads();
+                // the new column enters the chains of the block's later columns as their term k = j
+                if (row)
+                {
+#pragma unroll
+                    for (int c2 = c + 1; c2 < kColBlock; c2++)
+                        if (c2 < nb && i >= j0 + c2) sdot[c2] -= lij * Lp[tri(j0 + c2, j)];
+                }
+            }
         }
-        __syncthreads(); // every thread has read the pivot, the column is complete
-        if (tid == 0) Lp[tri(j, j)] = d;
-        for (int i = j + 1 + warp; i < P; i += nwarp)
-        {
-            const double li = col[i];
-            double* row = Lp + tri(i, 0);
-            for (int k = j + 1 + lane; k <= i; k += 32) row[k] = row[k] - li * col[k];
-        }
-        __syncthreads();
     }
 
     // forward substitution L y = b, both right-hand sides; thread i owns the running sum of row i
