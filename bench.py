@@ -91,8 +91,9 @@ def write_reference_case(path, spec, uR, uI, R, seed):
 
 
 def reference_step(cases, cpus):
-    """Every host core runs ONE walker's pass (1000 + 2 x 5000 proposals, 2 evaluations + the reference's
-    estimator accumulation) through the reference's own code; returns (proposals, seconds of the slowest)."""
+    """Every host core runs ONE walker's pass through the reference's own code: 1000 initialization proposals (untimed,
+    uncounted), then 2 x 5000 proposals and 2 evaluations + the reference's estimator accumulation (timed, counted);
+    returns (counted proposals, seconds of the slowest)."""
     harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
     procs = []
     for case, cpu in zip(cases, cpus):
@@ -179,7 +180,9 @@ def reference_main(args, rank):
     value = trials / secs
     what = "the unmodified reference" if REFERENCE_KIND == "reference" else "the plain-C port of the reference (oracle/tdvmc_oracle.c)"
     sample = (f"{cores} single-rank processes of {what} (one per physical core, taskset-pinned, "
-              f"serial MPI shim), each one walker's pass per step: {STEPS_PER_WALKER} proposals + {MC_NSTEPS} evaluations")
+              f"serial MPI shim), each one walker's pass per step: {MC_NINIT} initialization proposals run BEFORE the clock starts, "
+              f"then {MC_NSTEPS * MC_NTHERMSTEPS} timed and counted proposals + {MC_NSTEPS} evaluations with the reference's "
+              f"estimator accumulation (ref_harness.cpp ModeMC); the rate is proposals counted / seconds timed")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "walker-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -536,7 +539,8 @@ def main():
                 what = "the unmodified reference" if REFERENCE_KIND == "reference" else "the plain-C port of the reference"
                 cpu_baseline = {"value": trials / secs, "unit": "walker-steps/s", "cores": cores, "kind": REFERENCE_KIND,
                                 "sample": f"{cores} pinned single-rank processes of {what}, three passes of one walker each "
-                                          f"({STEPS_PER_WALKER} proposals + {MC_NSTEPS} evaluations per pass), {secs:.2f} s wall, "
+                                          f"({MC_NSTEPS * MC_NTHERMSTEPS} timed proposals + {MC_NSTEPS} evaluations per pass, the {MC_NINIT} "
+                                          f"initialization proposals before the clock), {secs:.2f} s wall, "
                                           f"{secs * cores:.0f} core-seconds"}
             except Exception as ex:  # the baseline is a report, never the product
                 cpu_baseline = {"value": None, "unit": "walker-steps/s", "cores": 0, "kind": REFERENCE_KIND, "sample": f"failed: {ex}"}

@@ -31,6 +31,7 @@ KEYS = [
     "smsp__warps_active.avg.per_cycle_active",
 ]
 STALL = "smsp__average_warps_issue_stalled_"
+PCSAMP = "smsp__pcsamp_warps_issue_stalled_"
 
 
 def main():
@@ -45,15 +46,28 @@ def main():
         for h, u in zip(hdr, units):
             if h in KEYS:
                 lines.append(f"   {h:90s} {d[h]:>18s} {u}")
-        stalls = []
+        # warp-state samples of the PC sampler: share of all samples per stall reason (what DESIGN.md quotes)
+        samp = {}
         for h in hdr:
-            if h.startswith(STALL) and h.endswith("_per_warp_active.pct"):
+            if h.startswith(PCSAMP) and not h.endswith("_not_issued"):
                 try:
-                    stalls.append((float(d[h].replace(",", "")), h[len(STALL):-len("_per_warp_active.pct")]))
+                    samp[h[len(PCSAMP):]] = float(d[h].replace(",", ""))
                 except ValueError:
                     pass
-        stalls.sort(reverse=True)
-        lines.append("   stall reasons (% of warp-active cycles): " + ", ".join(f"{n}={v:.1f}" for v, n in stalls[:8]))
+        tot = sum(samp.values())
+        if tot > 0:
+            top = sorted(samp.items(), key=lambda kv: -kv[1])[:8]
+            lines.append("   stall reasons (% of warp-state samples): " + ", ".join(f"{n}={100 * v / tot:.1f}" for n, v in top if v > 0))
+        ratios = []
+        for h in hdr:
+            if h.startswith(STALL) and h.endswith("_per_issue_active.ratio"):
+                try:
+                    ratios.append((float(d[h].replace(",", "")), h[len(STALL):-len("_per_issue_active.ratio")]))
+                except ValueError:
+                    pass
+        ratios.sort(reverse=True)
+        if ratios:
+            lines.append("   warps stalled per issued instruction: " + ", ".join(f"{n}={v:.2f}" for v, n in ratios[:8] if v > 0))
     text = "\n".join(lines)
     print(text)
     if len(sys.argv) > 2:

@@ -49,12 +49,33 @@ def drift_term_scale(spec, R, u):
     return float(np.max(np.where(inside, np.abs(up), 0.0).sum(axis=1)))
 
 
+def record_core(parity_log, test, name, r, g, exponent_floor=0.0):
+    """north_star level 1 for one fixture: O_k, exponent, E^R, E^I and the drift within RTOL of the reference's own
+    evaluation, each relative to its own magnitude (the drift: to max |F| over particles and components)."""
+    parity_log.check(test, name, "O_k", np.max(np.abs(r["O"][0] - g["local_operators"])), np.max(np.abs(g["local_operators"])), RTOL)
+    parity_log.check(test, name, "exponent", abs(r["exponent"][0] - float(g["exponent"])), max(abs(float(g["exponent"])), exponent_floor), RTOL)
+    for key, gk in (("e_r", "local_energy_r"), ("e_i", "local_energy_i")):
+        if float(g[gk]) == 0.0:
+            assert r[key][0] == 0.0
+            continue
+        parity_log.check(test, name, key, abs(r[key][0] - float(g[gk])), abs(float(g[gk])), RTOL)
+    for key in ("drift_r", "drift_i"):
+        fmax = np.max(np.abs(g[key]))
+        if fmax == 0.0:
+            assert np.all(r[key][0] == 0.0)
+            continue
+        parity_log.check(test, name, key, np.max(np.abs(r[key][0] - g[key])), fmax, RTOL, "max|F|")
+
+
 @pytest.fixture(scope="module")
 def capi():
     from tdvmc_b200 import capi as c
 
-    c.load()
-    assert c.load().tdvmc_gpu_device_count() > 0, "no CUDA device: the GPU tests have no fallback"
+    lib = c.load()                       # a missing or unloadable libtdvmc_b200.so is an ERROR, never a skip
+    if lib.tdvmc_gpu_device_count() <= 0:
+        if os.environ.get("TDVMC_REQUIRE_GPU"):
+            raise AssertionError("no CUDA device: the GPU tests have no fallback")
+        pytest.skip("no CUDA device on this machine (the library has no CPU fallback; run with -m gpu on the B200 box)")
     return c
 
 
@@ -88,32 +109,45 @@ def test_min_image_known_answers_and_reference_bits(capi, golden):
     h.close()
 
 
+# the perfect 7^3 lattice wrapped into L = 7: every drift component cancels to ~1e-6 of its terms, so "relative to
+# max |F|" would measure summation-order noise; only there the bound is relative to the summed terms (drift_term_scale)
+LATTICE_CASES = {"bosonsbulk_n343_lattice"}
+
+
 @pytest.mark.parametrize("name", EVAL_CASES)
-def test_fixed_configuration_energy_drift_operators(capi, golden, name):
+def test_fixed_configuration_energy_drift_operators(capi, golden, parity_log, name):
+    """north_star level 1: local energy, drift and O_k within 1e-10 relative of the reference's own CPU evaluation;
+    the drift against max |F| of the fixture, other[4,5,8] (sum |F_R|^2, sum |F_I|^2, 2 sum F_R.F_I) against
+    their own magnitude."""
     g = golden(name)
     spec, h = make_handle(capi, g)
     r = h.evaluate_fixed(g["R"])
-    assert rel(r["ss"][0], g["spline_sums"]) < 1e-13
+    t = "fixed_configuration"
+    parity_log.check(t, name, "spline_sums", np.max(np.abs(r["ss"][0] - g["spline_sums"])), np.max(np.abs(g["spline_sums"])), 1e-13)
     assert r["outer"][0] == float(g["outer_sum"])
-    assert rel(r["O"][0], g["local_operators"]) < RTOL
-    assert abs(r["exponent"][0] - float(g["exponent"])) < RTOL * abs(float(g["exponent"]))
-    assert abs(r["e_r"][0] - float(g["local_energy_r"])) < RTOL * abs(float(g["local_energy_r"]))
-    assert abs(r["e_i"][0] - float(g["local_energy_i"])) < RTOL * abs(float(g["local_energy_i"]))
+    parity_log.check(t, name, "O_k", np.max(np.abs(r["O"][0] - g["local_operators"])), np.max(np.abs(g["local_operators"])), RTOL)
+    for key, gk in (("exponent", "exponent"), ("e_r", "local_energy_r"), ("e_i", "local_energy_i")):
+        parity_log.check(t, name, key, abs(r[key][0] - float(g[gk])), abs(float(g[gk])), RTOL)
+    lattice = name in LATTICE_CASES
     scale = {}
     for key, u in (("drift_r", g["uR"]), ("drift_i", g["uI"])):
-        scale[key] = max(np.max(np.abs(g[key])), drift_term_scale(spec, g["R"], u))
-        assert np.max(np.abs(r[key][0] - g[key])) < RTOL * scale[key], key
+        fmax = np.max(np.abs(g[key]))
+        scale[key] = max(fmax, drift_term_scale(spec, g["R"], u)) if lattice else fmax
+        parity_log.check(t, name, key, np.max(np.abs(r[key][0] - g[key])), scale[key], RTOL,
+                         "sum_i |u'(r_ni)| (perfect lattice, max|F| = %.1e)" % fmax if lattice else "max|F|")
     want = g["other_expectation_values"]
     got = r["other"][0]
     assert got.shape == want.shape
-    # R1 = sum |F_R|^2, I1, R1I1 are quadratic in the drift: d(sum F^2) <= 2 N max|F| dF, with dF bounded as above
+    # on the lattice R1 = sum |F_R|^2, I1, R1I1 are sums of squares of cancelled quantities: d(sum F^2) <= 2 N max|F| dF
     N = spec.n_particles
     fr, fi = np.max(np.abs(g["drift_r"])), np.max(np.abs(g["drift_i"]))
     quad = {4: 2 * N * fr * scale["drift_r"], 5: 2 * N * fi * scale["drift_i"],
-            8: 2 * N * (fr * scale["drift_i"] + fi * scale["drift_r"])}
+            8: 2 * N * (fr * scale["drift_i"] + fi * scale["drift_r"])} if lattice else {}
     for k in range(9):
-        tol = RTOL * max(abs(want[k]), quad.get(k, 0.0), 1e-300)
-        assert abs(got[k] - want[k]) <= tol, (k, got[k], want[k])
+        if want[k] == 0.0 and not lattice:
+            assert got[k] == 0.0, k
+            continue
+        parity_log.check(t, name, "other[%d]" % k, abs(got[k] - want[k]), max(abs(want[k]), quad.get(k, 0.0)), RTOL)
     assert np.all(got[9:] == 0.0) and np.all(want[9:] == 0.0)
     h.close()
 
@@ -454,9 +488,8 @@ def test_evaluate_tile_schedule_edge_sizes(capi, golden, N):
         assert abs(ref["e_r"]) > 0 and abs(ev["e_r"][c] - ref["e_r"]) < RTOL * abs(ref["e_r"])
         assert abs(ev["e_i"][c] - ref["e_i"]) < RTOL * max(abs(ref["e_i"]), abs(ref["e_r"]))
         assert abs(ev["exponent"][c] - ref["exponent"]) < RTOL * abs(ref["exponent"])
-        scale = np.max(np.abs(ref["drift_r"])) + 1e-300
-        assert np.max(np.abs(ev["drift_r"][c] - ref["drift_r"])) < RTOL * scale * 10
-        assert np.max(np.abs(ev["drift_i"][c] - ref["drift_i"])) < RTOL * (np.max(np.abs(ref["drift_i"])) + 1e-300) * 10
+        assert np.max(np.abs(ev["drift_r"][c] - ref["drift_r"])) < RTOL * np.max(np.abs(ref["drift_r"]))
+        assert np.max(np.abs(ev["drift_i"][c] - ref["drift_i"])) < RTOL * np.max(np.abs(ref["drift_i"]))
     # the sweep at the same sizes: chain replay for a few steps
     h.set_positions(R[:, :, :])
     h.sweep(40)
@@ -642,19 +675,14 @@ HE_CASES = ["hebulk_n64_fixture", "hebulk_n64_equil"]
 
 
 @pytest.mark.parametrize("name", HE_CASES)
-def test_hebulk_fixed_configuration(capi, golden, name):
+def test_hebulk_fixed_configuration(capi, golden, parity_log, name):
     g = golden(name)
     spec, h = make_handle(capi, g)
     r = h.evaluate_fixed(g["R"])
     K = spec.n_splines
     assert rel(r["ss"][0][:K], g["spline_sums"]) < 1e-13
     assert abs(r["ss"][0][K] - float(g["mcmillan_sum"])) <= 1e-13 * abs(float(g["mcmillan_sum"]))
-    assert rel(r["O"][0], g["local_operators"]) < RTOL
-    assert abs(r["exponent"][0] - float(g["exponent"])) < RTOL * abs(float(g["exponent"]))
-    assert abs(r["e_r"][0] - float(g["local_energy_r"])) < RTOL * abs(float(g["local_energy_r"]))
-    assert abs(r["e_i"][0] - float(g["local_energy_i"])) < RTOL * abs(float(g["local_energy_i"]))
-    assert rel(r["drift_r"][0], g["drift_r"]) < RTOL
-    assert rel(r["drift_i"][0], g["drift_i"]) < RTOL
+    record_core(parity_log, "hebulk", name, r, g)
     want, got = g["other_expectation_values"], r["other"][0]
     assert got.shape == want.shape == (103,)
     assert abs(got[0] - want[0]) < RTOL * abs(want[0]) and abs(got[1] - want[1]) < RTOL * abs(want[1])
@@ -758,7 +786,7 @@ def test_stored_sample_reevaluation_he_systems(capi, golden, name):
 # HeDrop (BASELINE configs[0], config/drop_6.config): open boundary, two spline grids, const/linear tails, LJ
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["hedrop_n6_fixture", "hedrop_n6_spread", "hedrop_n6_equil", "hedrop_n20_equil"])
-def test_hedrop_fixed_configuration(capi, golden, name):
+def test_hedrop_fixed_configuration(capi, golden, parity_log, name):
     g = golden(name)
     spec, h = make_handle(capi, g)
     r = h.evaluate_fixed(g["R"])
@@ -767,11 +795,7 @@ def test_hedrop_fixed_configuration(capi, golden, name):
     assert abs(r["ss"][0][K] - float(g["mcmillan_sum"])) <= 1e-13 * max(abs(float(g["mcmillan_sum"])), 1e-300)
     assert r["ss"][0][K + 1] == float(g["const_sum"])
     assert abs(r["ss"][0][K + 2] - float(g["linear_sum"])) <= 1e-13 * max(abs(float(g["linear_sum"])), 1e-300)
-    assert rel(r["O"][0], g["local_operators"]) < RTOL
-    assert abs(r["exponent"][0] - float(g["exponent"])) < RTOL * abs(float(g["exponent"]))
-    assert abs(r["e_r"][0] - float(g["local_energy_r"])) < RTOL * abs(float(g["local_energy_r"]))
-    assert abs(r["e_i"][0] - float(g["local_energy_i"])) < RTOL * abs(float(g["local_energy_i"]))
-    assert rel(r["drift_r"][0], g["drift_r"]) < RTOL and rel(r["drift_i"][0], g["drift_i"]) < RTOL
+    record_core(parity_log, "hedrop", name, r, g)
     want, got = g["other_expectation_values"], r["other"][0]
     assert got.shape == want.shape == (403,)
     assert abs(got[0] - want[0]) < RTOL * abs(want[0]) and abs(got[1] - want[1]) < RTOL * abs(want[1])
@@ -828,7 +852,7 @@ MIX4_CASES = ["mixture4_he4he4na_fixture", "mixture4_he4he4na_compact", "mixture
 
 
 @pytest.mark.parametrize("name", MIX_CASES + MIX4_CASES)
-def test_mixture_fixed_configuration(capi, golden, name):
+def test_mixture_fixed_configuration(capi, golden, parity_log, name):
     from oracle_lib import OracleMix
 
     g = golden(name)
@@ -836,11 +860,7 @@ def test_mixture_fixed_configuration(capi, golden, name):
     r = h.evaluate_fixed(g["R"])
     o = OracleMix(spec).evaluate(g["R"], g["uR"], g["uI"], float(g["phiR"]))
     assert rel(r["ss"][0], o["ext"]) < 1e-13
-    assert rel(r["O"][0], g["local_operators"]) < RTOL
-    assert abs(r["exponent"][0] - float(g["exponent"])) < RTOL * abs(float(g["exponent"]))
-    assert abs(r["e_r"][0] - float(g["local_energy_r"])) < RTOL * abs(float(g["local_energy_r"]))
-    assert abs(r["e_i"][0] - float(g["local_energy_i"])) < RTOL * abs(float(g["local_energy_i"]))
-    assert rel(r["drift_r"][0], g["drift_r"]) < RTOL and rel(r["drift_i"][0], g["drift_i"]) < RTOL
+    record_core(parity_log, "mixture", name, r, g)
     want, got = g["other_expectation_values"], r["other"][0]
     assert got.shape == want.shape
     for k in (0, 1, 2, 3, 5):
@@ -1261,7 +1281,7 @@ BR_CASES = ["boxradial_n27_jittered", "boxradial_n27_equil", "boxradial_n64_equi
 
 
 @pytest.mark.parametrize("name", BR_CASES)
-def test_boxradial_fixed_configuration(capi, golden, name):
+def test_boxradial_fixed_configuration(capi, golden, parity_log, name):
     """Local energy, drift, O_k, basis sums, g(r) bins and the scripted-move quotient against the reference's own
     evaluation (config/NUBosonsBulkPBBoxAndRadial3D.config at its own size, and a 64-particle non-uniform-grid case)."""
     from oracle_lib import OracleBR
@@ -1270,16 +1290,11 @@ def test_boxradial_fixed_configuration(capi, golden, name):
     spec, h = make_handle(capi, g)
     K = spec.extra["n_splines"]
     r = h.evaluate_fixed(g["R"][None])
-    assert abs(r["e_r"][0] - float(g["local_energy_r"])) < RTOL * abs(float(g["local_energy_r"]))
-    assert abs(r["e_i"][0] - float(g["local_energy_i"])) < RTOL * abs(float(g["local_energy_i"]))
-    assert rel(r["O"][0], g["local_operators"]) < RTOL
-    assert abs(r["exponent"][0] - float(g["exponent"])) < RTOL * abs(float(g["exponent"]))
+    record_core(parity_log, "boxradial", name, r, g)
     assert rel(r["ss"][0][:K], g["spline_sums_rad"]) < 1e-12 and rel(r["ss"][0][K:], g["spline_sums"]) < 1e-12
     assert rel(r["other"][0][:3], g["other_expectation_values"][:3]) < RTOL
     assert rel(r["other"][0][3:], g["gr_bins"]) < 1e-13 and g["gr_bins"].sum() > 0
-    scale = max(np.abs(g["drift_r"]).max(), np.abs(g["drift_i"]).max())
-    assert np.abs(r["drift_r"][0] - g["drift_r"]).max() < RTOL * scale
-    assert np.abs(r["drift_i"][0] - g["drift_i"]).max() < RTOL * scale
+    scale = np.abs(g["drift_r"]).max()
     # the drift really carries the reference's box-for-radial substitution (NUBosonsBulkPBBoxAndRadial.cpp:493-497):
     # contracting the reference's own tables the "corrected" way moves it by far more than the tolerance
     PR = spec.n_params // 2
@@ -1380,20 +1395,16 @@ INH_CASES = ["inhcontact_n3_fixture", "inhcontact_n3_well", "inhcontact_n3_equil
 
 
 @pytest.mark.parametrize("name", INH_CASES)
-def test_inhcontact_fixed_configuration(capi, golden, name):
+def test_inhcontact_fixed_configuration(capi, golden, parity_log, name):
     from oracle_lib import OracleInh
 
     g = golden(name)
     spec, h = make_handle(capi, g)
     K1 = spec.extra["n_splines_spf"]
     r = h.evaluate_fixed(g["R"][None])
-    assert abs(r["e_r"][0] - float(g["local_energy_r"])) < RTOL * abs(float(g["local_energy_r"]))
-    assert abs(r["e_i"][0] - float(g["local_energy_i"])) < RTOL * abs(float(g["local_energy_i"]))
-    assert rel(r["O"][0], g["local_operators"]) < RTOL
-    assert abs(r["exponent"][0] - float(g["exponent"])) < RTOL * max(abs(float(g["exponent"])), 1.0)
+    record_core(parity_log, "inhcontact", name, r, g, exponent_floor=1.0)
     assert rel(r["ss"][0][:K1], g["spline_sums_spf"]) < 1e-13 and rel(r["ss"][0][K1:], g["spline_sums_pc"]) < 1e-13
     assert rel(r["other"][0], g["other_expectation_values"]) < RTOL
-    assert rel(r["drift_r"][0], g["drift_r"]) < RTOL and rel(r["drift_i"][0], g["drift_i"]) < RTOL
     assert np.all(r["drift_r"][0][:, 1:] == 0.0)
     q, d = h.quotient_fixed(g["R"], g["moves"])
     d_ref = g["move_exponent_new"] - float(g["exponent"])
@@ -1530,7 +1541,7 @@ LOWDIM_CASES = ["bosonsbulk2d_n16_equil", "nubosonsbulkpb2d_n25_equil", "rydberg
 
 
 @pytest.mark.parametrize("name", LOWDIM_CASES)
-def test_low_dimensional_fixed_configuration(capi, golden, name):
+def test_low_dimensional_fixed_configuration(capi, golden, parity_log, name):
     g = golden(name)
     D = int(g["DIM"])
     spec, h = make_handle(capi, g)
@@ -1540,13 +1551,18 @@ def test_low_dimensional_fixed_configuration(capi, golden, name):
     assert abs(r["exponent"][0] - float(g["exponent"])) < RTOL * abs(float(g["exponent"]))
     assert abs(r["e_r"][0] - float(g["local_energy_r"])) < RTOL * abs(float(g["local_energy_r"]))
     assert abs(r["e_i"][0] - float(g["local_energy_i"])) < RTOL * abs(float(g["local_energy_i"]))
-    for key, u in (("drift_r", g["uR"]), ("drift_i", g["uI"])):
-        scale = max(np.max(np.abs(g[key])), drift_term_scale(spec, g["R"], u))
-        assert np.max(np.abs(r[key][0] - g[key])) < RTOL * scale, key
+    for key in ("drift_r", "drift_i"):
+        if np.max(np.abs(g[key])) == 0.0:                          # imaginary parameters all zero
+            assert np.all(r[key][0] == 0.0)
+            continue
+        parity_log.check("low_dimensional", name, key, np.max(np.abs(r[key][0] - g[key])), np.max(np.abs(g[key])), RTOL, "max|F|")
         assert np.all(r[key][0][:, D:] == 0.0)
     want, got = g["other_expectation_values"], r["other"][0]
-    for k in (0, 1, 2, 3, 6, 7):                                   # kinetic, potential, wf, exponent, Laplacian sums
-        assert abs(got[k] - want[k]) <= RTOL * max(abs(want[k]), abs(want[0])), k
+    for k in range(9):
+        if want[k] == 0.0:
+            assert got[k] == 0.0, k
+            continue
+        parity_log.check("low_dimensional", name, "other[%d]" % k, abs(got[k] - want[k]), abs(want[k]), RTOL)
     sD, sD2 = h.tables_fixed(g["R"])
     assert rel(sD[:, :, :D], g["sD"]) < 1e-13 and np.all(sD[:, :, D:] == 0.0) and rel(sD2, g["sD2"]) < 1e-13
     q, d = h.quotient_fixed(g["R"], g["moves"])
