@@ -167,6 +167,12 @@ int tdvmc_gpu_set_params(tdvmc_gpu_handle* h, const double* uR, const double* uI
 /* MoveCoordinatesToFirstCell (src/TDVMC.cpp:787-796). */
 int tdvmc_gpu_wrap_positions(tdvmc_gpu_handle* h);
 
+/* nAcceptances = 0; nTrials = 0 at the start of every time step (src/TDVMC.cpp:3428-3429, 3976-3977): the counters
+ * tdvmc_gpu_allreduce_and_fetch returns count from the last reset (or from creation). */
+int tdvmc_gpu_reset_counters(tdvmc_gpu_handle* h);
+/* MC_STEP is a runtime-changeable config item of the reference (./param file, src/TDVMC.cpp:2718-2744). */
+int tdvmc_gpu_set_mc_step(tdvmc_gpu_handle* h, double mc_step);
+
 /* ---- sampling ---- */
 /* DoMetropolisSteps for every local walker (src/TDVMC.cpp:858-924). */
 int tdvmc_gpu_sweep(tdvmc_gpu_handle* h, int64_t n_steps);

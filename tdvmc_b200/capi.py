@@ -81,6 +81,8 @@ SYMBOLS = [
     ("tdvmc_gpu_get_positions", C.c_int, [_VP, dp, C.c_int32, C.c_int32]),
     ("tdvmc_gpu_set_params", C.c_int, [_VP, dp, dp, C.c_double, C.c_double, C.c_double]),
     ("tdvmc_gpu_wrap_positions", C.c_int, [_VP]),
+    ("tdvmc_gpu_reset_counters", C.c_int, [_VP]),
+    ("tdvmc_gpu_set_mc_step", C.c_int, [_VP, C.c_double]),
     ("tdvmc_gpu_sweep", C.c_int, [_VP, C.c_int64]),
     ("tdvmc_gpu_sample_and_accumulate", C.c_int, [_VP, C.c_int32, C.c_int32, C.c_int32]),
     ("tdvmc_gpu_reevaluate_stored", C.c_int, [_VP]),
@@ -220,6 +222,13 @@ class Handle:
 
     def wrap_positions(self):
         self._ck(self.lib.tdvmc_gpu_wrap_positions(self.h), "wrap_positions")
+
+    def reset_counters(self):
+        """nAcceptances = nTrials = 0 at the start of a time step (src/TDVMC.cpp:3428-3429)."""
+        self._ck(self.lib.tdvmc_gpu_reset_counters(self.h), "reset_counters")
+
+    def set_mc_step(self, mc_step):
+        self._ck(self.lib.tdvmc_gpu_set_mc_step(self.h, float(mc_step)), "set_mc_step")
 
     # ---- sampling ----
     def sweep(self, n_steps):

@@ -1042,6 +1042,23 @@ static int do_sweep(tdvmc_gpu_handle* h, long long n_steps, double* pos = nullpt
     return 0;
 }
 
+int tdvmc_gpu_reset_counters(tdvmc_gpu_handle* h)
+{
+    if (!h) return -1;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemsetAsync(h->d_accepted.p, 0, h->d_accepted.n * sizeof(unsigned long long), h->stream));
+    h->trials_local = 0;
+    return 0;
+}
+
+int tdvmc_gpu_set_mc_step(tdvmc_gpu_handle* h, double mc_step)
+{
+    if (!h) return -1;
+    if (!(mc_step > 0.0) || !std::isfinite(mc_step)) return fail(h, "set_mc_step: MC_STEP must be positive and finite");
+    h->mc_step = mc_step;
+    return 0;
+}
+
 int tdvmc_gpu_sweep(tdvmc_gpu_handle* h, int64_t n_steps)
 {
     if (!h) return -1;

@@ -403,6 +403,10 @@ void GpuEnsembleSystem::GetPositions(std::vector<std::vector<std::vector<double>
 
 void GpuEnsembleSystem::MoveCoordinatesToFirstCell() { Check(tdvmc_gpu_wrap_positions(handle), "wrap_positions"); }
 
+void GpuEnsembleSystem::ResetCounters() { Check(tdvmc_gpu_reset_counters(handle), "reset_counters"); }
+
+void GpuEnsembleSystem::SetMCStep(double MC_STEP) { Check(tdvmc_gpu_set_mc_step(handle, MC_STEP), "set_mc_step"); }
+
 void GpuEnsembleSystem::DoMetropolisSteps(long long n, const std::vector<double>& uR, const std::vector<double>& uI,
                                           double phiR, double phiI)
 {

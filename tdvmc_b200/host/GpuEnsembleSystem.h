@@ -168,6 +168,10 @@ public:
     void SetPositions(const std::vector<std::vector<std::vector<double> > >& R);
     void GetPositions(std::vector<std::vector<std::vector<double> > >& R);
     void MoveCoordinatesToFirstCell();
+    // nAcceptances = 0; nTrials = 0 at the start of a time step (src/TDVMC.cpp:3428-3429)
+    void ResetCounters();
+    // MC_STEP changed at run time (./param file, src/TDVMC.cpp:2718-2744)
+    void SetMCStep(double MC_STEP);
     void DoMetropolisSteps(long long n, const std::vector<double>& uR, const std::vector<double>& uI, double phiR,
                            double phiI);
 

@@ -1,5 +1,7 @@
 /*
- * Single-rank stand-in for <mpi.h>.  TEST INFRASTRUCTURE ONLY (oracle build).
+ * Single-rank stand-in for <mpi.h>, for machines without an MPI installation: used by the driver build
+ * (tdvmc_b200/host/driver/Makefile, one process driving one GPU) and by the CPU-oracle build of the unmodified
+ * reference (oracle/ref_build/Makefile).  With a real MPI, build with MPI_INC= CXX=mpicxx instead.
  *
  * The reference (mathiasgartner/TDVMC) is an MPI program whose only data-path
  * collectives are MPI_Reduce(SUM)->root and MPI_Bcast (src/MPIMethods.h:132-206,
@@ -11,8 +13,8 @@
  * The reference's MPIMethods.h relies on <mpi.h> transitively pulling in a few
  * standard headers (cout, map, strcpy, invalid_argument), hence the includes.
  */
-#ifndef TDVMC_ORACLE_MPI_SHIM_H
-#define TDVMC_ORACLE_MPI_SHIM_H
+#ifndef TDVMC_MPI_SINGLE_RANK_H
+#define TDVMC_MPI_SINGLE_RANK_H
 
 #include <cstddef>
 #include <cstdlib>

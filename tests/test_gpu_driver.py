@@ -1,0 +1,178 @@
+"""The reference's own driver bound to the device (tdvmc_b200/host/build/TDVMC_gpu = src/TDVMC.cpp with the call sites of
+INTEGRATION.md section 2 re-pointed, built by tdvmc_b200/host/driver/Makefile) against the unmodified reference program
+(oracle/_ref/TDVMC_ref): whole time evolutions - config file in, LocalEnergyR.dat / ParametersR.dat out - compared within
+error bars (north_star level 2).  The reference runs ONE Markov chain per process; its error bars come from the spread over
+RNG seeds (RNG state files), the device's from the spread over GPU_SEEDs.
+"""
+import os
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import pytest
+
+from tdvmc_b200 import driver, systems
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TDVMC_REF = os.path.join(ROOT, "oracle", "_ref", "TDVMC_ref")
+
+
+@pytest.fixture(scope="module")
+def binaries():
+    from tdvmc_b200 import capi
+
+    if capi.load().tdvmc_gpu_device_count() <= 0:
+        pytest.skip("no CUDA device on this machine")
+    assert os.path.exists(driver.TDVMC_GPU), "build it: make -C tdvmc_b200/host/driver (done by __graft_entry__.build())"
+    assert os.path.exists(TDVMC_REF), "build it: make -C oracle/ref_build"
+    return driver.TDVMC_GPU, TDVMC_REF
+
+
+def run_seeds(binary, cfg, tag, R0, seeds, tmp_path, gpu_seed=False, workers=None):
+    """One process per seed; for the device arm the seed is GPU_SEED and the runs go one after the other."""
+    def one(sd):
+        c = dict(cfg, GPU_SEED=sd) if gpu_seed else cfg
+        return driver.run_driver(binary, c, str(tmp_path / f"{tag}_{sd}"), R0=R0, seed=sd, timeout=1800)
+
+    with ThreadPoolExecutor(max_workers=1 if gpu_seed else (workers or min(len(seeds), os.cpu_count() or 1))) as ex:
+        return list(ex.map(one, seeds))
+
+
+def compare_trajectories(ref, dev, n_par, parity_log, case, z_max=5.5):
+    """Mean trajectories of the two arms against the standard error of their difference.  The per-run spread of every
+    quantity is taken from the reference runs (the arms are sample-matched, so a device run scatters alike); the
+    normalised deviations must be bounded AND of unit size on average - a test that could not fail proves nothing."""
+    out = {}
+    for name, get, cols in (("E_R", lambda r: r.local_energy_r[:, None], 1), ("uR", lambda r: r.parameters_r[:, :n_par], n_par),
+                            ("uI", lambda r: r.parameters_i[:, :n_par], n_par)):
+        a = np.stack([get(r) for r in ref])            # [seed][step][cols]
+        b = np.stack([get(r) for r in dev])
+        assert a.shape[1:] == b.shape[1:], (name, a.shape, b.shape)
+        assert np.all(np.isfinite(a)) and np.all(np.isfinite(b)), name
+        sd = a.std(axis=0, ddof=1)
+        if name != "E_R":
+            sd = sd[1:]                                  # step 0 holds the start parameters: identical, no spread
+            a, b = a[:, 1:], b[:, 1:]
+        live = sd > 0
+        if not np.any(live):
+            continue
+        z = (b.mean(axis=0) - a.mean(axis=0))[live] / (sd[live] * np.sqrt(1.0 / len(ref) + 1.0 / len(dev)))
+        out[name] = z
+        parity_log.check("driver_evolution", case, f"max|z| {name}", np.max(np.abs(z)), 1.0, z_max,
+                         f"{z.size} values, rms z = {np.sqrt(np.mean(z ** 2)):.2f}")
+        rms = np.sqrt(np.mean(z ** 2))
+        assert rms < 1.8, (name, rms)
+        if z.size >= 100:                                # (a handful of strongly correlated energies can all sit near zero)
+            assert rms > 0.3, (name, rms)
+    return out
+
+
+def test_driver_evolution_n64_matches_reference_program(binaries, golden, parity_log, tmp_path):
+    """BosonsBulk N = 64: ten imaginary-time Euler steps (Cholesky solve with preconditioning) of the reference program,
+    eight seeds, against the same config through TDVMC_gpu (GPU_WALKERS = 512, two samples each = the reference's 1024
+    samples per step), four device seeds."""
+    gpu_bin, ref_bin = binaries
+    g = golden("bosonsbulk_n64_equil")
+    cfg = driver.base_config(N=64, LBOX=4.0, N_PARAM=33, MC_STEP=0.4, MC_NSTEPS=1024, MC_NTHERMSTEPS=64, MC_NINITIALIZATIONSTEPS=64,
+                             MC_VERY_FIRST_NINITIALIZATIONSTEPS=6400, TIMESTEP=2e-4, TOTALTIME=2e-4 * 9.5, IMAGINARY_TIME=1,
+                             USE_PRECONDITIONING=1, PARAMS_REAL=[float(x) for x in g["uR"]], SYSTEM_PARAMS=[1.0, 1.0])
+    ref = run_seeds(ref_bin, cfg, "ref", g["R"], list(range(1, 9)), tmp_path)
+    dev = run_seeds(gpu_bin, dict(cfg, GPU_WALKERS=512, MC_NSTEPS=2), "gpu", g["R"], [1, 2, 3, 4], tmp_path, gpu_seed=True)
+    assert len(dev[0].local_energy_r) == 10 and dev[0].parameters_r.shape == (10, 34)
+    z = compare_trajectories(ref, dev, 33, parity_log, "bosonsbulk_n64_euler_imaginary")
+    assert "uR" in z and "E_R" in z
+    # the evolution is not noise against noise: the parameters moved by many standard errors over the run
+    a = np.stack([r.parameters_r[:, :33] for r in ref])
+    moved = np.abs(a[:, -1] - a[:, 0]).mean(axis=0) / (a[:, -1].std(axis=0, ddof=1) + 1e-300)
+    assert np.max(moved) > 10.0
+    # acceptance rate and the per-step log line of the driver survive the binding
+    assert abs(np.mean(dev[0].acceptance) - np.mean(ref[0].acceptance)) < 1.0
+    assert len(dev[0].step_ms) == 10
+
+
+def test_driver_real_time_qr_branch_n64(binaries, golden, parity_log, tmp_path):
+    """Real time with LINEAR_EQUATION_SOLVER_TYPE = 1: the driver's own Eigen FullPivHouseholderQR branch
+    (src/TDVMC.cpp:1763-1827) solves on the estimators the device fetched - the branch the device solver does not offer."""
+    gpu_bin, ref_bin = binaries
+    g = golden("bosonsbulk_n64_equil")
+    cfg = driver.base_config(N=64, LBOX=4.0, N_PARAM=33, MC_STEP=0.4, MC_NSTEPS=1024, MC_NTHERMSTEPS=64, MC_NINITIALIZATIONSTEPS=64,
+                             MC_VERY_FIRST_NINITIALIZATIONSTEPS=6400, TIMESTEP=1e-4, TOTALTIME=1e-4 * 5.5, IMAGINARY_TIME=0,
+                             LINEAR_EQUATION_SOLVER_TYPE=1, USE_PRECONDITIONING=0, PARAMS_REAL=[float(x) for x in g["uR"]],
+                             SYSTEM_PARAMS=[1.0, 1.0])
+    ref = run_seeds(ref_bin, cfg, "ref", g["R"], list(range(1, 9)), tmp_path)
+    dev = run_seeds(gpu_bin, dict(cfg, GPU_WALKERS=512, MC_NSTEPS=2), "gpu", g["R"], [1, 2, 3, 4], tmp_path, gpu_seed=True)
+    z = compare_trajectories(ref, dev, 33, parity_log, "bosonsbulk_n64_euler_realtime_qr")
+    assert "uI" in z                                     # the imaginary parts grow out of zero in real time
+
+
+def test_driver_sample_reuse_nubosons_n216(binaries, golden, parity_log, tmp_path):
+    """config 4's mode at reduced size: NUBosonsBulkPB (non-uniform knots, reflection rule), UPDATE_SAMPLES_EVERY_NTH_STEP = 1
+    - step 0 samples and stores, every later step advances the stored samples (UpdateSamplesConsecutive) and re-evaluates them
+    (ParallelUpdateExpectationValuesForGivenSamples), here with stored R recomputed on the device instead of 11 MB tables."""
+    gpu_bin, ref_bin = binaries
+    g = golden("nubosonsbulkpb_n216_equil")
+    P = int(g["N_PARAM"])
+    cfg = driver.nubosons_config(g["NURBS_GRID"], g["uR"], np.zeros(P), N=216, LBOX=float(g["LBOX"]), N_PARAM=P,
+                                 SYSTEM_PARAMS=[float(x) for x in g["SYSTEM_PARAMS"]], MC_STEP=0.35, MC_NSTEPS=512, MC_NTHERMSTEPS=108,
+                                 MC_NINITIALIZATIONSTEPS=216, MC_VERY_FIRST_NINITIALIZATIONSTEPS=21600, TIMESTEP=2e-5,
+                                 TOTALTIME=2e-5 * 5.5, IMAGINARY_TIME=1, UPDATE_SAMPLES_PERCENT=100.0)
+    ref = run_seeds(ref_bin, cfg, "ref", g["R"], list(range(1, 9)), tmp_path)
+    dev = run_seeds(gpu_bin, dict(cfg, GPU_WALKERS=256, MC_NSTEPS=2), "gpu", g["R"], [1, 2, 3, 4], tmp_path, gpu_seed=True)
+    assert len(dev[0].local_energy_r) == 6
+    compare_trajectories(ref, dev, P, parity_log, "nubosonsbulkpb_n216_sample_reuse")
+
+
+def test_driver_config3_own_size_against_reference_trajectories(binaries, golden, parity_log, tmp_path):
+    """BASELINE configs[2] at its own size (N = 343, N_PARAM = 201): the device-bound driver against trajectories of the
+    reference program recorded by oracle/gen_driver_fixtures.py (six seeds, ten Euler steps, 4096 samples per step - 160 s
+    per step and host core, which is why they are a fixture and not run here), then the run continued to 50 steps."""
+    gpu_bin, _ = binaries
+    f = golden("driver_cfg3_reference")
+    g = golden("bosonsbulk_n343_equil")
+    uR, uI = systems.smooth_params(201, 3.5)
+    n_steps = f["e_r"].shape[1]
+    cfg = driver.headline_config(uR, uI, MC_NSTEPS=2, MC_NTHERMSTEPS=int(f["MC_NTHERMSTEPS"]), MC_NINITIALIZATIONSTEPS=1000,
+                                 MC_VERY_FIRST_NINITIALIZATIONSTEPS=34300, TIMESTEP=float(f["TIMESTEP"]),
+                                 TOTALTIME=float(f["TIMESTEP"]) * (n_steps - 0.5), LINEAR_EQUATION_SOLVER_TYPE=0, USE_PRECONDITIONING=1,
+                                 GPU_WALKERS=int(f["MC_NSTEPS"]) // 2)
+    dev = run_seeds(gpu_bin, cfg, "gpu", g["R"], [1, 2, 3, 4], tmp_path, gpu_seed=True)
+
+    class Ref:                                            # the fixture's series under the DriverRun attribute names
+        def __init__(self, i):
+            self.local_energy_r, self.parameters_r, self.parameters_i = f["e_r"][i], f["p_r"][i], f["p_i"][i]
+
+    compare_trajectories([Ref(i) for i in range(f["e_r"].shape[0])], dev, 201, parity_log, "bosonsbulk_n343_p201_euler")
+    # 50 Euler steps with the ensemble the headline benchmark uses: stable, energy relaxing in imaginary time
+    long = driver.run_driver(gpu_bin, dict(cfg, GPU_WALKERS=4096, TOTALTIME=float(f["TIMESTEP"]) * 49.5), str(tmp_path / "long"),
+                             R0=g["R"])
+    e = long.local_energy_r
+    assert len(e) == 50 and np.all(np.isfinite(e)) and np.all(np.isfinite(long.parameters_r))
+    assert e[-10:].mean() < e[:10].mean()
+    assert np.median(long.step_ms) < 200.0
+
+
+def test_driver_config4_own_size_runs(binaries, golden, tmp_path):
+    """BASELINE configs[3] at its own size and counts (NUBosonsBulkPB N = 1728, N_PARAM = 200, 50 samples x 200 steps, sample
+    reuse on) through the device-bound driver: three time steps, finite, and the step-0 energy agrees with the fixed-parameter
+    sampler statistics of the same ensemble."""
+    gpu_bin, _ = binaries
+    g = golden("nubosonsbulkpb_n1728_equil")
+    cfg = driver.nubosons_config(g["NURBS_GRID"], g["uR"], g["uI"], MC_VERY_FIRST_NINITIALIZATIONSTEPS=17280, GPU_WALKERS=64,
+                                 TOTALTIME=1e-5 * 2.5, SYSTEM_PARAMS=[float(x) for x in g["SYSTEM_PARAMS"]])
+    r = driver.run_driver(gpu_bin, cfg, str(tmp_path / "cfg4"), R0=g["R"])
+    assert len(r.local_energy_r) == 3 and np.all(np.isfinite(r.local_energy_r)) and np.all(np.isfinite(r.parameters_r))
+    assert abs(r.local_energy_r[1] - r.local_energy_r[0]) < 0.02 * abs(r.local_energy_r[0])
+
+
+def test_device_solve_option_matches_host_solve(binaries, golden, tmp_path):
+    """GPU_DEVICE_SOLVE = 1: CalculateNextParametersEuler served by solve_kernel (bit-identical Cholesky branch) - the
+    trajectory equals the host-solved one of the same ensemble to rounding."""
+    gpu_bin, _ = binaries
+    g = golden("bosonsbulk_n64_equil")
+    cfg = driver.base_config(N=64, LBOX=4.0, N_PARAM=33, MC_STEP=0.4, MC_NSTEPS=2, MC_NTHERMSTEPS=64, MC_NINITIALIZATIONSTEPS=64,
+                             MC_VERY_FIRST_NINITIALIZATIONSTEPS=6400, TIMESTEP=2e-4, TOTALTIME=2e-4 * 5.5, IMAGINARY_TIME=1,
+                             USE_PRECONDITIONING=1, PARAMS_REAL=[float(x) for x in g["uR"]], SYSTEM_PARAMS=[1.0, 1.0], GPU_WALKERS=512)
+    a = driver.run_driver(gpu_bin, cfg, str(tmp_path / "host"), R0=g["R"])
+    b = driver.run_driver(gpu_bin, dict(cfg, GPU_DEVICE_SOLVE=1), str(tmp_path / "dev"), R0=g["R"])
+    assert np.max(np.abs(a.parameters_r[:, :33] - b.parameters_r[:, :33])) < 1e-9
+    assert np.max(np.abs(a.local_energy_r - b.local_energy_r)) < 1e-8 * np.max(np.abs(a.local_energy_r))

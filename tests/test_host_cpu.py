@@ -313,3 +313,62 @@ def test_cpp_table_builders_with_reference_boundary_factors(golden, tmp_path, na
     np.testing.assert_array_equal(np.array(o[1].split(), dtype=np.int64), spec.map_ptr)
     np.testing.assert_array_equal(np.array(o[2].split(), dtype=np.int64), spec.map_col)
     np.testing.assert_array_equal(np.array(o[3].split(), dtype=np.float64), spec.map_val)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference's own driver bound to the library (tdvmc_b200/host/driver): host-side checks
+# ---------------------------------------------------------------------------------------------------
+TDVMC_REF = os.path.join(ROOT, "oracle", "_ref", "TDVMC_ref")
+
+
+def test_driver_patch_applies_to_the_reference_source(tmp_path):
+    """patch_driver.py finds every anchor exactly once in the reference's src/TDVMC.cpp (only where /root/reference exists:
+    the build container) and changes nothing but the documented call sites."""
+    src = "/root/reference/src/TDVMC.cpp"
+    if not os.path.exists(src):
+        pytest.skip("the reference tree is not on this machine (GPU box): the binary was built in the build container")
+    out = tmp_path / "TDVMC_gpu.cpp"
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tdvmc_b200", "host", "driver", "patch_driver.py"), src, str(out)])
+    import difflib
+    a = open(src).read().splitlines()
+    b = open(out).read().splitlines()[2:]
+    added = [l[2:] for l in difflib.ndiff(a, b) if l.startswith("+ ")]
+    removed = [l[2:] for l in difflib.ndiff(a, b) if l.startswith("- ")]
+    assert len(removed) == 2 and len(added) <= 40                  # two lines re-pointed in place, the rest are insertions
+    assert all("gpu" in l.lower() or l.strip() in ("{", "}", "return;") for l in added), added
+
+
+def test_driver_with_gpu_walkers_zero_is_the_reference_byte_for_byte(golden, tmp_path):
+    """GPU_WALKERS = 0 (or absent): every hook falls through and TDVMC_gpu IS the reference - its .dat files equal those of
+    the unmodified TDVMC_ref byte for byte (same host RNG stream, same CPU path).  No GPU needed."""
+    from tdvmc_b200 import driver
+    if not (os.path.exists(TDVMC_REF) and os.path.exists(driver.TDVMC_GPU)):
+        pytest.skip("driver binaries not built (needs /root/reference at build time)")
+    g = golden("bosonsbulk_n64_equil")
+    cfg = driver.base_config(N=64, LBOX=4.0, N_PARAM=33, MC_STEP=0.4, MC_NSTEPS=64, MC_NTHERMSTEPS=32, MC_NINITIALIZATIONSTEPS=64,
+                             MC_VERY_FIRST_NINITIALIZATIONSTEPS=640, TIMESTEP=1e-5, TOTALTIME=1e-5 * 2.5, IMAGINARY_TIME=1,
+                             USE_PRECONDITIONING=1, PARAMS_REAL=[float(x) for x in g["uR"]], SYSTEM_PARAMS=[1.0, 1.0],
+                             MC_NADDITIONALSTEPS=4, MC_NADDITIONALTHERMSTEPS=16, MC_NADDITIONALINITIALIZATIONSTEPS=16)
+    a = driver.run_driver(TDVMC_REF, cfg, str(tmp_path / "ref"), R0=g["R"], seed=5)
+    b = driver.run_driver(driver.TDVMC_GPU, cfg, str(tmp_path / "gpu_off"), R0=g["R"], seed=5)
+    assert len(a.local_energy_r) == 3 and np.all(np.isfinite(a.parameters_r))
+    for name in ("LocalEnergyR", "LocalEnergyI", "LocalOperators", "OtherExpectationValues", "ParametersR", "ParametersI", "timesSystem",
+                 "AdditionalObservables_pairDistribution", "AdditionalObservables_structureFactor"):
+        pa, pb = os.path.join(a.out_dir, name + ".dat"), os.path.join(b.out_dir, name + ".dat")
+        if name.startswith("Additional") and not os.path.exists(pa):
+            continue
+        assert open(pa, "rb").read() == open(pb, "rb").read(), name
+
+
+def test_driver_refuses_gpu_walkers_without_a_device(golden, tmp_path):
+    """GPU_WALKERS > 0 on a machine without a CUDA device: the driver stops with the library's message, it does not fall
+    back to the CPU path silently."""
+    from tdvmc_b200 import capi, driver
+    if not os.path.exists(driver.TDVMC_GPU):
+        pytest.skip("driver binary not built")
+    if capi.load().tdvmc_gpu_device_count() > 0:
+        pytest.skip("this machine has a CUDA device")
+    g = golden("bosonsbulk_n64_equil")
+    cfg = driver.base_config(N=64, LBOX=4.0, N_PARAM=33, PARAMS_REAL=[float(x) for x in g["uR"]], GPU_WALKERS=8)
+    with pytest.raises(RuntimeError, match="no CUDA device|no CPU fallback"):
+        driver.run_driver(driver.TDVMC_GPU, cfg, str(tmp_path / "nogpu"), R0=g["R"])
