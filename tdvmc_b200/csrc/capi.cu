@@ -1142,14 +1142,35 @@ int tdvmc_gpu_sample_and_accumulate(tdvmc_gpu_handle* h, int32_t n_samples, int3
     if (rows_pad > M) // rows beyond M must be zero for the padded SYRK chunks
         CK(cudaMemsetAsync(h->d_A.p + (size_t)M * h->lda, 0, (size_t)(rows_pad - M) * h->lda * sizeof(double), h->stream));
     if (int rc = do_sweep(h, n_init)) return rc; // MC_NINITIALIZATIONSTEPS, src/TDVMC.cpp:1068-1071
+    // One block evaluates one configuration, so a launch over W configurations runs in ceil(W / blocks per wave) waves:
+    // 512 walkers of N = 1728 (one block per SM) are 3.46 waves, 14 % of the last one idle.  Where that loss exceeds a few per
+    // cent - or the sample positions are kept anyway - the positions are snapshot per sample and all n_samples x W
+    // configurations go through ONE launch after the last sweep (same rows, same arithmetic).
+    bool batch = false;
+    if (h->kind == TDVMC_SYSTEM_SPLINE_TABLE && n_samples > 1)
+    {
+        const double waves = (double)h->W / (double)(h->sm_count * evaluate_blocks_per_sm(h->sysdev()));
+        batch = h->keep_positions || std::ceil(waves) / waves > 1.04;
+        if (batch && !h->d_samp_pos.p)
+        {
+            if (h->d_samp_pos.alloc((size_t)h->rows_cap * 3 * h->Np) != cudaSuccess)
+            {
+                cudaGetLastError();
+                batch = false; // no room for the snapshots: evaluate sample by sample
+            }
+        }
+    }
     for (int m = 0; m < n_samples; m++)
     {
         if (int rc = do_sweep(h, n_therm)) return rc; // src/TDVMC.cpp:1075-1078
-        if (int rc = do_evaluate_walkers(h, h->d_pos.p, h->W, (long long)m * h->W)) return rc; // :1080
-        if (h->keep_positions)                                                                 // :1082-1091
+        if (!batch)
+            if (int rc = do_evaluate_walkers(h, h->d_pos.p, h->W, (long long)m * h->W)) return rc; // :1080
+        if (h->keep_positions || batch)                                                        // :1082-1091
             CK(cudaMemcpyAsync(h->d_samp_pos.p + (size_t)m * h->W * 3 * h->Np, h->d_pos.p, (size_t)h->W * 3 * h->Np * sizeof(double),
                                cudaMemcpyDeviceToDevice, h->stream));
     }
+    if (batch)
+        if (int rc = do_evaluate_walkers(h, h->d_samp_pos.p, (int)M, 0)) return rc;
     if (h->keep_positions) h->stored_samples = n_samples; // the update cursor keeps running, as :556 sets it only once
     return do_accumulate(h, h->d_A.p, h->d_other.p, M); // :1103-1109
 }

@@ -11,7 +11,7 @@
 // with u~ = M^T u (boundary-condition map applied to the parameters).  Per-term arithmetic keeps the
 // reference's expressions and association (the monomial table in absolute r is ill-conditioned, so
 // a different evaluation order would differ from the reference at the 1e-10 level); only the order
-// of the sums over particles differs.
+// of the sums differs.
 //
 // Every unordered pair is visited ONCE.  The pair matrix is cut into 32x32 tiles; in "shift" s, warp I
 // takes tile (I, (I+s) mod NT), so the tiles of one shift have distinct row blocks and distinct column
@@ -19,12 +19,24 @@
 // k: the row force stays in the lane's registers, the column force accumulators ROTATE through the warp
 // by shuffle (lane l receives lane l+1's), so no lane ever adds into another lane's data and nothing
 // needs an atomic.  Tiles are flushed into the block's force arrays columns first, rows second, a
-// barrier after each.  The Laplacian terms are symmetric in the pair and are doubled at the end.
-// The basis sums ss[k] (needed for O_k) are a histogram over knot intervals; each warp keeps a
-// private copy and adds to it without atomics: lanes whose pair falls into the same interval are
-// ranked with match.any and take turns, so every round touches distinct addresses.
-// (evaluate_rowwise_kernel below is the first version - thread n walks all partners i, every pair seen
-// twice - kept selectable with TDVMC_EVAL_ROWWISE=1 for A/B timing.)
+// barrier after each.
+//
+// The basis sums ss[k] (needed for O_k) are a histogram over knot intervals; each warp keeps a private copy and adds to
+// it without atomics: lanes whose pair falls into the same interval are ranked with match.any and take turns, so every
+// round touches distinct addresses (f64 shared-memory atomics are CAS loops on sm_100a, 64-bit integer ones too).
+//
+// r02, what bounds the kernel and what was tried (profiles/r02_evaluate_*.txt): everything a step moves between lanes or
+// to and from shared memory - table records, u~, the histogram read-modify-writes, positions, the twelve shuffles of the
+// column rotation - goes through ONE 128 B/clk crossbar per SM; at N = 343 that is ~140 wavefronts per 32-pair step against
+// 80 clocks of FP64 work.  (1) ROT = true: lane l starts with spline piece (l >> 1) & 3 and reads copy l & 1 of a table
+// with 128-byte records, the second copy shifted by 16 bytes; the 16-byte bank group of every LDS.128 is then
+// (2 piece + half + copy) mod 8 whatever the interval, i.e. conflict-free by construction (ncu: 3.75 wavefronts per
+// LDS.128 = one per quarter-warp, against 10 with the 144-byte records).  Used where every lane of a step is inside the
+// cut (the reflection rule of NUBosonsBulkPB); at BosonsBulk's cut r <= L/2 the selects that bring the values back
+// to piece order for the histogram cost what the replays saved.  (2) A piece-parallel variant - pairs inside the cut
+// compacted by ballot, four lanes per pair, one spline piece each, conflict-free table reads, results summed and handed
+// back by shuffle - ran the FP64 work of a step in 137 instead of 160 instructions but needed 48 shuffles per step (each
+// two crossbar wavefronts) and a match.any per round of eight pairs: 4.94 against 3.64 ms per 2960 configurations.  Not kept.
 #include "kernels.cuh"
 
 #include <cstdlib>
@@ -55,22 +67,6 @@ __device__ __forceinline__ void warp_hist_add4(double* hist, int bin, bool activ
     }
 }
 
-struct EvalSmem
-{
-    double* knots;
-    double* rec;
-    double* utR;
-    double* utI;
-    double* px;
-    double* py;
-    double* pz;
-    double* hist;
-    double* frc; // [6][NT*32]: fRx fRy fRz fIx fIy fIz per particle
-    double* sstot;
-    double* red;
-    unsigned short* lut;
-};
-
 struct SmemCarver
 {
     unsigned char* base;
@@ -83,13 +79,43 @@ struct SmemCarver
     }
 };
 
-__host__ __device__ inline size_t eval_smem_layout(const SysDev& s, int nwarps, EvalSmem* out, unsigned char* base)
+// 1/r to full precision without the IEEE division sequence: hardware seed + two Newton steps.
+// Enters only the well-conditioned factors (unit vector, (D-1)/r), never the spline argument.
+__device__ __forceinline__ double rcp_refined(double r)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(r));
+    double e = fma(-r, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-r, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+
+struct EvalSmem2
+{
+    double* knots;
+    double* wtab;  // two copies of [nbins][4 pieces][4 coefficients]; the second starts 16 bytes past a multiple of 128
+    double* utR;
+    double* utI;
+    double* px;
+    double* py;
+    double* pz;
+    double* hist;  // [nwarps][K]
+    double* frc;   // [6][NT*32]
+    double* sstot;
+    double* red;
+    unsigned short* lut;
+};
+
+__host__ __device__ inline size_t eval_smem_layout2(const SysDev& s, int nwarps, bool rot, EvalSmem2* out, unsigned char* base)
 {
     SmemCarver c = { base, 0 };
-    const int Npad = ((s.N + 31) >> 5) << 5; // whole tiles
-    EvalSmem m;
+    const int Npad = ((s.N + 31) >> 5) << 5;
+    EvalSmem2 m;
+    // rot: two copies of 128-byte records on 128-byte phases 0 and 16; else one copy of the 144-byte records
+    m.wtab = c.take(rot ? (size_t)2 * s.nbins * 16 + 2 : (size_t)s.nbins * kRecStride);
     m.knots = c.take(s.K + 4);
-    m.rec = c.take((size_t)s.nbins * kRecStride);
     m.utR = c.take(s.K);
     m.utI = c.take(s.K);
     m.px = c.take(Npad);
@@ -105,25 +131,10 @@ __host__ __device__ inline size_t eval_smem_layout(const SysDev& s, int nwarps, 
     return c.off;
 }
 
-// 1/r to full precision without the IEEE division sequence: hardware seed + two Newton steps.
-// Enters only the well-conditioned factors (unit vector, (D-1)/r), never the spline argument.
-__device__ __forceinline__ double rcp_refined(double r)
-{
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(r));
-    double e = fma(-r, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-r, y, 1.0);
-    y = fma(y, e, y);
-    return y;
-}
-
-// WIDE: 24 warps and one block per SM for configurations whose shared-memory footprint leaves room for one block
-// anyway (N = 1728: positions + forces alone are 125 KB); otherwise 12 warps, two blocks per SM.
-template <bool REFLECT, bool WIDE>
+template <bool REFLECT, bool WIDE, bool ROT>
 __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kernel(EvalArgs a)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const SysDev& s = a.s;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -132,11 +143,25 @@ __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kerne
     const int cfg = blockIdx.x;
     const int N = s.N, K = s.K, P = s.P;
 
-    EvalSmem m;
-    eval_smem_layout(s, nwarps, &m, smem_raw);
+    EvalSmem2 m;
+    eval_smem_layout2(s, nwarps, ROT, &m, smem_raw);
 
+    const int ntab = s.nbins * 16;
+    double* wtab1 = m.wtab + ntab + 2;
+    if (ROT)
+    {
+        for (int i = tid; i < ntab; i += blockDim.x)
+        {
+            const double v = s.rec[(size_t)(i >> 4) * kRecStride + (i & 15)];
+            m.wtab[i] = v;
+            wtab1[i] = v;
+        }
+    }
+    else
+    {
+        for (int i = tid; i < s.nbins * kRecStride; i += blockDim.x) m.wtab[i] = s.rec[i];
+    }
     for (int i = tid; i < K + 4; i += blockDim.x) m.knots[i] = s.knots[i];
-    for (int i = tid; i < s.nbins * kRecStride; i += blockDim.x) m.rec[i] = s.rec[i];
     for (int i = tid; i < K; i += blockDim.x)
     {
         m.utR[i] = s.utR[i];
@@ -157,6 +182,12 @@ __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kerne
     __syncthreads();
 
     double* hist = m.hist + (size_t)warp * K;
+    // lane l starts with spline piece (l >> 1) & 3 and reads table copy l & 1: with 128-byte records the 16-byte bank
+    // group of a coefficient pair is (2 piece + half + copy) mod 8 whatever the interval, so the eight lanes of a
+    // quarter-warp hit eight distinct groups in every one of the eight LDS.128 of a step
+    const int p0 = ROT ? (lane >> 1) & 3 : 0;
+    const int wstride = ROT ? 16 : kRecStride;
+    const double* wmine = ((ROT && (lane & 1)) ? wtab1 : m.wtab) - (size_t)s.first_bin * wstride;
     const double rmax = s.rmax;
     const double pot_a = s.pot_a;
     const int NP32 = NT * 32;
@@ -167,7 +198,7 @@ __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kerne
     double* fIy = fIx + NP32;
     double* fIz = fIy + NP32;
 
-    double lapR = 0.0, lapI = 0.0;
+    double lapR = 0.0, lapI = 0.0;   // sum u~ B'' (piece lanes) + (D-1)/r sum u~ B' (owner lanes)
     int vcount = 0, outer = 0;
 
     const int half = NT >> 1;
@@ -230,14 +261,16 @@ __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kerne
                     if (act)
                     {
                         bin = find_bin_exact(s, m.knots, m.lut, r);
-                        const double* w = m.rec + (size_t)(bin - s.first_bin) * kRecStride;
+                        const double* w = wmine + (size_t)bin * wstride;
                         const double r2 = r * r;
                         const double rinv = rcp_refined(r);
                         const double f2 = s.dm1 * rinv; // (DIM - 1) / r, BosonsBulk.cpp:319-322
                         double gR = 0.0, gI = 0.0;
+                        double vq[4];
 #pragma unroll
-                        for (int p = 0; p < 4; p++)
+                        for (int q = 0; q < 4; q++)
                         {
+                            const int p = ROT ? (p0 + q) & 3 : q;
                             const double2 w01 = *reinterpret_cast<const double2*>(w + p * 4);
                             const double2 w23 = *reinterpret_cast<const double2*>(w + p * 4 + 2);
                             const double d1 = w01.y + 2.0 * w23.x * r + 3.0 * w23.y * r2; // BosonsBulk.cpp:299
@@ -248,7 +281,24 @@ __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kerne
                             gI = fma(uIk, d1, gI);
                             lapR = fma(uRk, t2, lapR);
                             lapI = fma(uIk, t2, lapI);
-                            val[p] = w01.x + w01.y * r + w23.x * r2 + w23.y * (r2 * r); // BosonsBulk.cpp:204
+                            vq[q] = w01.x + w01.y * r + w23.x * r2 + w23.y * (r2 * r); // BosonsBulk.cpp:204
+                        }
+                        // back to piece order for the histogram: val[p] = vq[(p - p0) & 3]
+                        if (ROT)
+                        {
+                            const bool s1 = p0 & 1, s2 = p0 & 2;
+                            const double a0 = s1 ? vq[3] : vq[0], a1 = s1 ? vq[0] : vq[1], a2 = s1 ? vq[1] : vq[2], a3 = s1 ? vq[2] : vq[3];
+                            val[0] = s2 ? a2 : a0;
+                            val[1] = s2 ? a3 : a1;
+                            val[2] = s2 ? a0 : a2;
+                            val[3] = s2 ? a1 : a3;
+                        }
+                        else
+                        {
+                            val[0] = vq[0];
+                            val[1] = vq[1];
+                            val[2] = vq[2];
+                            val[3] = vq[3];
                         }
                         const double ex = vx * rinv, ey = vy * rinv, ez = vz * rinv; // unreflected vec / (reflected) r
                         rRx = fma(gR, ex, rRx);
@@ -388,205 +438,15 @@ __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kerne
     }
 }
 
-template <bool REFLECT>
-__global__ void __launch_bounds__(384, 2) evaluate_rowwise_kernel(EvalArgs a)
+// Rotated piece order (two table copies, conflict-free LDS.128) where nearly every lane of a step is inside the cut - the
+// reflection rule of NUBosonsBulkPB: 22.8 against 25.1 ms per 512 configurations at N = 1728; at BosonsBulk's cut r <= L/2
+// half the lanes idle, the records collide less, and the extra selects cost more than the replays saved (3.80 against
+// 3.64 ms per 2960 configurations at N = 343).
+static bool evaluate_rotated(const SysDev& s) { return s.pair_rule == 1; }
+
+static size_t eval_layout_bytes(const SysDev& s, int nwarps)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const SysDev& s = a.s;
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-    const int nwarps = blockDim.x >> 5;
-    const int cfg = blockIdx.x;
-    const int N = s.N, K = s.K, P = s.P;
-
-    EvalSmem m;
-    eval_smem_layout(s, nwarps, &m, smem_raw);
-
-    for (int i = tid; i < K + 4; i += blockDim.x) m.knots[i] = s.knots[i];
-    for (int i = tid; i < s.nbins * kRecStride; i += blockDim.x) m.rec[i] = s.rec[i];
-    for (int i = tid; i < K; i += blockDim.x)
-    {
-        m.utR[i] = s.utR[i];
-        m.utI[i] = s.utI[i];
-    }
-    for (int i = tid; i < s.ncell; i += blockDim.x) m.lut[i] = s.lut[i];
-    const double* gpos = a.pos + (size_t)cfg * 3 * s.Np;
-    for (int i = tid; i < N; i += blockDim.x)
-    {
-        m.px[i] = gpos[i];
-        m.py[i] = gpos[s.Np + i];
-        m.pz[i] = gpos[2 * s.Np + i];
-    }
-    for (int i = tid; i < nwarps * K; i += blockDim.x) m.hist[i] = 0.0;
-    __syncthreads();
-
-    double* hist = m.hist + (size_t)warp * K;
-    const double rmax = s.rmax;
-    const double pot_a = s.pot_a;
-
-    double R1 = 0.0, I1 = 0.0, RI = 0.0, lapR = 0.0, lapI = 0.0;
-    int vcount = 0, outer = 0;
-
-    for (int n0 = warp * 32; n0 < N; n0 += blockDim.x)
-    {
-        const int n = n0 + lane;
-        const bool valid = n < N;
-        const double xn = valid ? m.px[n] : 0.0, yn = valid ? m.py[n] : 0.0, zn = valid ? m.pz[n] : 0.0;
-        double fRx = 0.0, fRy = 0.0, fRz = 0.0, fIx = 0.0, fIy = 0.0, fIz = 0.0;
-
-        for (int i = 0; i < N; i++)
-        {
-            double vx, vy, vz;
-            double r = disp_exact(s, xn, yn, zn, m.px[i], m.py[i], m.pz[i], vx, vy, vz); // R[n] - R[i]
-            const bool pair = valid && (i != n);
-            bool inside;
-            if (REFLECT)
-            {
-                if (!(r < rmax)) r = 2 * rmax - r; // NUBosonsBulkPB.cpp:250-253, 331-335
-                inside = r < rmax;
-            }
-            else
-            {
-                inside = r <= rmax; // BosonsBulk.cpp:195, 257
-            }
-            const bool act = pair && inside;
-            const bool lower = act && (i < n);
-            if (pair && !inside && (i < n)) outer++; // BosonsBulk.cpp:207-210
-            if (lower && (r < pot_a)) vcount++;      // BosonsBulk.cpp:268-271
-
-            int bin = 0;
-            double val[4] = { 0.0, 0.0, 0.0, 0.0 };
-            if (act)
-            {
-                bin = find_bin_exact(s, m.knots, m.lut, r);
-                const double* w = m.rec + (size_t)(bin - s.first_bin) * kRecStride;
-                const double r2 = r * r;
-                const double rinv = 1.0 / r;
-                const double f2 = s.dm1 * rinv; // (DIM - 1) / r, BosonsBulk.cpp:319-322
-                double gR = 0.0, gI = 0.0;
-#pragma unroll
-                for (int p = 0; p < 4; p++)
-                {
-                    const double2 w01 = *reinterpret_cast<const double2*>(w + p * 4);
-                    const double2 w23 = *reinterpret_cast<const double2*>(w + p * 4 + 2);
-                    const double d1 = w01.y + 2.0 * w23.x * r + 3.0 * w23.y * r2; // BosonsBulk.cpp:299
-                    const double d2 = 2.0 * w23.x + 6.0 * w23.y * r;              // BosonsBulk.cpp:301
-                    const double uRk = m.utR[bin - p], uIk = m.utI[bin - p];
-                    const double t2 = d2 + f2 * d1;
-                    gR = fma(uRk, d1, gR);
-                    gI = fma(uIk, d1, gI);
-                    lapR = fma(uRk, t2, lapR);
-                    lapI = fma(uIk, t2, lapI);
-                    if (lower) val[p] = w01.x + w01.y * r + w23.x * r2 + w23.y * (r2 * r); // BosonsBulk.cpp:204
-                }
-                const double ex = vx * rinv, ey = vy * rinv, ez = vz * rinv; // unreflected vec / (reflected) r
-                fRx = fma(gR, ex, fRx);
-                fRy = fma(gR, ey, fRy);
-                fRz = fma(gR, ez, fRz);
-                fIx = fma(gI, ex, fIx);
-                fIy = fma(gI, ey, fIy);
-                fIz = fma(gI, ez, fIz);
-            }
-            warp_hist_add4(hist, bin, lower, val, lane);
-        }
-
-        if (valid)
-        {
-            R1 += fRx * fRx + fRy * fRy + fRz * fRz;          // VectorNorm2, BosonsBulk.cpp:418-419
-            I1 += fIx * fIx + fIy * fIy + fIz * fIz;
-            RI += fRx * fIx + fRy * fIy + fRz * fIz;          // kineticSumR1I1 / 2, BosonsBulk.cpp:417
-            if (a.drift_r)
-            {
-                double* d = a.drift_r + ((size_t)cfg * N + n) * 3;
-                d[0] = fRx; d[1] = fRy; d[2] = fRz;
-            }
-            if (a.drift_i)
-            {
-                double* d = a.drift_i + ((size_t)cfg * N + n) * 3;
-                d[0] = fIx; d[1] = fIy; d[2] = fIz;
-            }
-        }
-    }
-
-    // block reduction (fixed order -> deterministic)
-    R1 = warp_sum(R1);
-    I1 = warp_sum(I1);
-    RI = warp_sum(RI);
-    lapR = warp_sum(lapR);
-    lapI = warp_sum(lapI);
-    vcount = warp_sum_int(vcount);
-    outer = warp_sum_int(outer);
-    if (lane == 0)
-    {
-        double* r = m.red + warp * 8;
-        r[0] = R1; r[1] = I1; r[2] = RI; r[3] = lapR; r[4] = lapI; r[5] = (double)vcount; r[6] = (double)outer;
-    }
-    __syncthreads();
-
-    for (int k = tid; k < K; k += blockDim.x)
-    {
-        double t = 0.0;
-        for (int w = 0; w < nwarps; w++) t += m.hist[(size_t)w * K + k];
-        m.sstot[k] = t;
-        if (a.ss_out) a.ss_out[(size_t)cfg * K + k] = t;
-    }
-    __syncthreads();
-
-    const long long row = a.row0 + (long long)cfg * a.row_stride;
-    double* Arow = a.A + (size_t)row * a.lda;
-    double epart = 0.0;
-    for (int p = tid; p < P; p += blockDim.x)
-    {
-        double o = 0.0;
-        for (int j = s.map_ptr[p]; j < s.map_ptr[p + 1]; j++) o += s.map_val[j] * m.sstot[s.map_col[j]]; // BosonsBulk.cpp:158-177
-        Arow[p] = o;
-        epart = fma(s.uR[p], o, epart); // BosonsBulk.cpp:526-529
-    }
-    epart = warp_sum(epart);
-    if (lane == 0) m.red[warp * 8 + 7] = epart;
-    __syncthreads();
-
-    if (tid == 0)
-    {
-        double t[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-        for (int w = 0; w < nwarps; w++)
-            for (int q = 0; q < 8; q++) t[q] += m.red[w * 8 + q];
-        const double outer_sum = t[6];
-        const double v_int = s.pot_b * t[5];
-        const double exponent = t[7] + s.uR[s.tail_param] * outer_sum; // BosonsBulk.cpp:532-536
-        const double kR1 = t[0], kI1 = t[1], kRI = 2.0 * t[2], kR2 = t[3], kI2 = t[4];
-        const double kin_r = -(kR1 - kI1 + kR2) * s.hbar; // BosonsBulk.cpp:422
-        const double kin_i = -(kRI + kI2) * s.hbar;       // BosonsBulk.cpp:423
-        const double e_r = kin_r + v_int;                 // :425, external potential is zero (:344-347)
-        const double e_i = kin_i;
-        Arow[P] = e_r;
-        Arow[P + 1] = e_i;
-        Arow[P + 2] = 1.0;
-        double* o = a.other + (size_t)row * s.n_other;   // BosonsBulk.cpp:449-457
-        o[0] = kin_r;
-        o[1] = v_int;
-        o[2] = exp(exponent + s.phiR);
-        o[3] = exponent;
-        o[4] = kR1;
-        o[5] = kI1;
-        o[6] = kR2;
-        o[7] = kI2;
-        o[8] = kRI;
-        if (a.exponent) a.exponent[row] = exponent;
-        if (a.outer_out) a.outer_out[cfg] = outer_sum;
-    }
-}
-
-static bool eval_rowwise()
-{
-    static int v = -1;
-    if (v < 0)
-    {
-        const char* e = getenv("TDVMC_EVAL_ROWWISE"); // A/B timing knob: 1 = first version of the kernel
-        v = (e && atoi(e) == 1) ? 1 : 0;
-    }
-    return v == 1;
+    return eval_smem_layout2(s, nwarps, evaluate_rotated(s), nullptr, nullptr);
 }
 
 // two blocks of <= 12 warps per SM when they fit, else one block of <= 24 warps
@@ -594,19 +454,21 @@ static bool evaluate_wide(const SysDev& s)
 {
     int nt = (s.N + 31) / 32;
     if (nt <= 12) return false;
-    return 2 * (eval_smem_layout(s, 12, nullptr, nullptr) + 1024) > (size_t)227 * 1024;
+    return 2 * (eval_layout_bytes(s, 12) + 1024) > (size_t)227 * 1024;
 }
+
+int evaluate_blocks_per_sm(const SysDev& s) { return evaluate_wide(s) ? 1 : 2; }
 
 int evaluate_threads(const SysDev& s)
 {
     int t = ((s.N + 31) / 32) * 32;
-    const int cap = (evaluate_wide(s) && !eval_rowwise()) ? 768 : 384;
+    const int cap = evaluate_wide(s) ? 768 : 384;
     return t > cap ? cap : t;
 }
 
 size_t evaluate_smem_bytes(const SysDev& s)
 {
-    return eval_smem_layout(s, evaluate_threads(s) / 32, nullptr, nullptr);
+    return eval_layout_bytes(s, evaluate_threads(s) / 32);
 }
 
 template <typename KernelT>
@@ -625,14 +487,11 @@ cudaError_t launch_evaluate(const EvalArgs& a, cudaStream_t st)
     const int threads = evaluate_threads(a.s);
     const size_t smem = evaluate_smem_bytes(a.s);
     const bool refl = a.s.pair_rule == 1;
-    if (eval_rowwise())
-        return refl ? launch_eval_kernel(evaluate_rowwise_kernel<true>, a, threads, smem, st)
-                    : launch_eval_kernel(evaluate_rowwise_kernel<false>, a, threads, smem, st);
     if (evaluate_wide(a.s))
-        return refl ? launch_eval_kernel(evaluate_kernel<true, true>, a, threads, smem, st)
-                    : launch_eval_kernel(evaluate_kernel<false, true>, a, threads, smem, st);
-    return refl ? launch_eval_kernel(evaluate_kernel<true, false>, a, threads, smem, st)
-                : launch_eval_kernel(evaluate_kernel<false, false>, a, threads, smem, st);
+        return refl ? launch_eval_kernel(evaluate_kernel<true, true, true>, a, threads, smem, st)
+                    : launch_eval_kernel(evaluate_kernel<false, true, false>, a, threads, smem, st);
+    return refl ? launch_eval_kernel(evaluate_kernel<true, false, true>, a, threads, smem, st)
+                : launch_eval_kernel(evaluate_kernel<false, false, false>, a, threads, smem, st);
 }
 
 } // namespace tdvmc
