@@ -38,46 +38,47 @@ def run_seeds(binary, cfg, tag, R0, seeds, tmp_path, gpu_seed=False, workers=Non
         return list(ex.map(one, seeds))
 
 
-def compare_trajectories(ref, dev, n_par, parity_log, case, z_max=5.5):
-    """Mean trajectories of the two arms against the standard error of their difference.  The per-run spread of every
-    quantity is taken from the reference runs (the arms are sample-matched, so a device run scatters alike); the
-    normalised deviations must be bounded AND of unit size on average - a test that could not fail proves nothing."""
+def compare_trajectories(ref, dev, n_par, parity_log, case, z_max=6.5):
+    """Mean trajectories of the two arms against the standard error of their difference, each arm with its own seed-to-seed
+    spread (Welch): z = (mean_dev - mean_ref) / sqrt(s_ref^2 / n_ref + s_dev^2 / n_dev).  With 6-8 seeds per arm z follows a
+    t distribution with ~10 degrees of freedom, hence the bound of 6.5 on the maximum over some thousand (strongly
+    correlated) values; the normalised deviations must ALSO be of unit size on average - a test that could not fail proves
+    nothing, and spreads that differed between the arms would show here."""
     out = {}
-    for name, get, cols in (("E_R", lambda r: r.local_energy_r[:, None], 1), ("uR", lambda r: r.parameters_r[:, :n_par], n_par),
-                            ("uI", lambda r: r.parameters_i[:, :n_par], n_par)):
+    for name, get in (("E_R", lambda r: r.local_energy_r[:, None]), ("uR", lambda r: r.parameters_r[:, :n_par]),
+                      ("uI", lambda r: r.parameters_i[:, :n_par])):
         a = np.stack([get(r) for r in ref])            # [seed][step][cols]
         b = np.stack([get(r) for r in dev])
         assert a.shape[1:] == b.shape[1:], (name, a.shape, b.shape)
         assert np.all(np.isfinite(a)) and np.all(np.isfinite(b)), name
-        sd = a.std(axis=0, ddof=1)
         if name != "E_R":
-            sd = sd[1:]                                  # step 0 holds the start parameters: identical, no spread
-            a, b = a[:, 1:], b[:, 1:]
-        live = sd > 0
+            a, b = a[:, 1:], b[:, 1:]                    # step 0 holds the start parameters: identical, no spread
+        sa, sb = a.std(axis=0, ddof=1), b.std(axis=0, ddof=1)
+        live = (sa > 0) & (sb > 0)
         if not np.any(live):
             continue
-        z = (b.mean(axis=0) - a.mean(axis=0))[live] / (sd[live] * np.sqrt(1.0 / len(ref) + 1.0 / len(dev)))
+        z = (b.mean(axis=0) - a.mean(axis=0))[live] / np.sqrt(sa[live] ** 2 / len(ref) + sb[live] ** 2 / len(dev))
         out[name] = z
-        parity_log.check("driver_evolution", case, f"max|z| {name}", np.max(np.abs(z)), 1.0, z_max,
-                         f"{z.size} values, rms z = {np.sqrt(np.mean(z ** 2)):.2f}")
         rms = np.sqrt(np.mean(z ** 2))
+        parity_log.check("driver_evolution", case, f"max|z| {name}", np.max(np.abs(z)), 1.0, z_max,
+                         f"{z.size} values, rms z = {rms:.2f}, spread dev/ref = {np.median(sb[live] / sa[live]):.2f}")
         assert rms < 1.8, (name, rms)
         if z.size >= 100:                                # (a handful of strongly correlated energies can all sit near zero)
-            assert rms > 0.3, (name, rms)
+            assert rms > 0.4, (name, rms)
     return out
 
 
 def test_driver_evolution_n64_matches_reference_program(binaries, golden, parity_log, tmp_path):
     """BosonsBulk N = 64: ten imaginary-time Euler steps (Cholesky solve with preconditioning) of the reference program,
     eight seeds, against the same config through TDVMC_gpu (GPU_WALKERS = 512, two samples each = the reference's 1024
-    samples per step), four device seeds."""
+    samples per step), eight device seeds."""
     gpu_bin, ref_bin = binaries
     g = golden("bosonsbulk_n64_equil")
     cfg = driver.base_config(N=64, LBOX=4.0, N_PARAM=33, MC_STEP=0.4, MC_NSTEPS=1024, MC_NTHERMSTEPS=64, MC_NINITIALIZATIONSTEPS=64,
                              MC_VERY_FIRST_NINITIALIZATIONSTEPS=6400, TIMESTEP=2e-4, TOTALTIME=2e-4 * 9.5, IMAGINARY_TIME=1,
                              USE_PRECONDITIONING=1, PARAMS_REAL=[float(x) for x in g["uR"]], SYSTEM_PARAMS=[1.0, 1.0])
     ref = run_seeds(ref_bin, cfg, "ref", g["R"], list(range(1, 9)), tmp_path)
-    dev = run_seeds(gpu_bin, dict(cfg, GPU_WALKERS=512, MC_NSTEPS=2), "gpu", g["R"], [1, 2, 3, 4], tmp_path, gpu_seed=True)
+    dev = run_seeds(gpu_bin, dict(cfg, GPU_WALKERS=512, MC_NSTEPS=2), "gpu", g["R"], list(range(1, 9)), tmp_path, gpu_seed=True)
     assert len(dev[0].local_energy_r) == 10 and dev[0].parameters_r.shape == (10, 34)
     z = compare_trajectories(ref, dev, 33, parity_log, "bosonsbulk_n64_euler_imaginary")
     assert "uR" in z and "E_R" in z
@@ -100,7 +101,7 @@ def test_driver_real_time_qr_branch_n64(binaries, golden, parity_log, tmp_path):
                              LINEAR_EQUATION_SOLVER_TYPE=1, USE_PRECONDITIONING=0, PARAMS_REAL=[float(x) for x in g["uR"]],
                              SYSTEM_PARAMS=[1.0, 1.0])
     ref = run_seeds(ref_bin, cfg, "ref", g["R"], list(range(1, 9)), tmp_path)
-    dev = run_seeds(gpu_bin, dict(cfg, GPU_WALKERS=512, MC_NSTEPS=2), "gpu", g["R"], [1, 2, 3, 4], tmp_path, gpu_seed=True)
+    dev = run_seeds(gpu_bin, dict(cfg, GPU_WALKERS=512, MC_NSTEPS=2), "gpu", g["R"], list(range(1, 9)), tmp_path, gpu_seed=True)
     z = compare_trajectories(ref, dev, 33, parity_log, "bosonsbulk_n64_euler_realtime_qr")
     assert "uI" in z                                     # the imaginary parts grow out of zero in real time
 
@@ -117,7 +118,7 @@ def test_driver_sample_reuse_nubosons_n216(binaries, golden, parity_log, tmp_pat
                                  MC_NINITIALIZATIONSTEPS=216, MC_VERY_FIRST_NINITIALIZATIONSTEPS=21600, TIMESTEP=2e-5,
                                  TOTALTIME=2e-5 * 5.5, IMAGINARY_TIME=1, UPDATE_SAMPLES_PERCENT=100.0)
     ref = run_seeds(ref_bin, cfg, "ref", g["R"], list(range(1, 9)), tmp_path)
-    dev = run_seeds(gpu_bin, dict(cfg, GPU_WALKERS=256, MC_NSTEPS=2), "gpu", g["R"], [1, 2, 3, 4], tmp_path, gpu_seed=True)
+    dev = run_seeds(gpu_bin, dict(cfg, GPU_WALKERS=256, MC_NSTEPS=2), "gpu", g["R"], list(range(1, 9)), tmp_path, gpu_seed=True)
     assert len(dev[0].local_energy_r) == 6
     compare_trajectories(ref, dev, P, parity_log, "nubosonsbulkpb_n216_sample_reuse")
 
@@ -135,7 +136,7 @@ def test_driver_config3_own_size_against_reference_trajectories(binaries, golden
                                  MC_VERY_FIRST_NINITIALIZATIONSTEPS=34300, TIMESTEP=float(f["TIMESTEP"]),
                                  TOTALTIME=float(f["TIMESTEP"]) * (n_steps - 0.5), LINEAR_EQUATION_SOLVER_TYPE=0, USE_PRECONDITIONING=1,
                                  GPU_WALKERS=int(f["MC_NSTEPS"]) // 2)
-    dev = run_seeds(gpu_bin, cfg, "gpu", g["R"], [1, 2, 3, 4], tmp_path, gpu_seed=True)
+    dev = run_seeds(gpu_bin, cfg, "gpu", g["R"], list(range(1, 9)), tmp_path, gpu_seed=True)
 
     class Ref:                                            # the fixture's series under the DriverRun attribute names
         def __init__(self, i):
