@@ -30,6 +30,9 @@ struct SweepArgs
     double mc_step;
 };
 cudaError_t launch_sweep(SweepArgs a, cudaStream_t st);
+// several warps per walker for small ensembles / large systems (sweep_split_kernel); warps from sweep_split_warps (> 1)
+int sweep_split_warps(const SysDev& s, int W, int sm_count, int resident_per_sm);
+cudaError_t launch_sweep_split(SweepArgs a, int warps, int sm_count, int smem_optin, cudaStream_t st);
 int sweep_blocks_per_sm(const SysDev& s, int wpb, int npp);
 int sweep_walkers_per_warp(const SysDev& s);
 int sweep_max_threads(const SysDev& s);

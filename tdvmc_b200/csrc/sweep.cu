@@ -35,6 +35,7 @@
 #include "kernels.cuh"
 #include "sweep_math.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace tdvmc
@@ -237,6 +238,204 @@ __global__ void __launch_bounds__(GROUP == 32 ? kSweepMaxThreadsWarp : kSweepMax
         gpos[2 * s.Np + i] = pz[i];
     }
     if (gl == 0) a.accepted[w] += n_acc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Small ensembles / large systems: WARPS warps share one walker (r02).
+//
+// With one warp per walker an ensemble of fewer than ~20 x 148 walkers leaves FP64 issue slots empty - the reference's own
+// production runs are O(256) chains (src/MPIMethods.h:334-347) - and a walker of N = 1728 particles fills 41 KB of shared
+// memory, so only four warps fit on an SM.  Here the partners of the moved particle are dealt out to WARPS x 32 lanes; every
+// warp draws the same proposals (counter-based stream: redundant, no exchange), reduces its part of the exponent change
+// by shuffle, the parts meet in shared memory at a named barrier of the walker's warps, and every warp takes the same
+// accept decision from the same fixed-order sum.  A second barrier orders the position write of the leading warp before
+// the next proposal reads it.  Same proposal stream, same accept rule as sweep_kernel: the chains coincide up to the
+// summation order of the exponent change.
+template <bool UNIFORM, bool REFLECT, int WARPS>
+__global__ void __launch_bounds__(kSweepMaxThreadsWarp, 1) sweep_split_kernel(SweepArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SysDev& s = a.s;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int slot = warp / WARPS;            // walker of this block
+    const int wsub = warp % WARPS;            // this warp's share of the walker
+    const int gl = wsub * 32 + lane;          // lane within the walker's WARPS x 32 lanes
+    constexpr int STRIDE = WARPS * 32;
+    const int Npp = a.npp;
+    const int nrec = s.nbins + 1;
+
+    double2* c01s = reinterpret_cast<double2*>(smem_raw);
+    double2* c23s = c01s + (size_t)nrec * kCubCopies;
+    double2* tts = c23s + (size_t)nrec * kCubCopies;
+    unsigned short* lut = reinterpret_cast<unsigned short*>(tts + (UNIFORM ? 0 : nrec));
+    double* pos_base = reinterpret_cast<double*>(smem_raw + a.pos_offset);
+    double* red_base = pos_base + (size_t)a.wpb * 3 * Npp; // [slots][WARPS] partial exponent changes
+    {
+        const double2* g01 = reinterpret_cast<const double2*>(s.cub);
+        const double2* g23 = g01 + nrec;
+        const double2* gtt = g23 + nrec;
+        for (int i = threadIdx.x; i < nrec * kCubCopies; i += blockDim.x)
+        {
+            c01s[i] = g01[i / kCubCopies];
+            c23s[i] = g23[i / kCubCopies];
+        }
+        if (!UNIFORM)
+        {
+            for (int i = threadIdx.x; i < nrec; i += blockDim.x) tts[i] = gtt[i];
+            for (int i = threadIdx.x; i < s.ncell; i += blockDim.x) lut[i] = s.lut[i];
+        }
+    }
+    const double2* c01p = c01s + (lane & (kCubCopies - 1));
+    const double2* c23p = c23s + (lane & (kCubCopies - 1));
+    const double2* ttp = tts;
+
+    const int w = blockIdx.x * a.wpb + slot; // local walker (a.wpb = walkers per block here)
+    double* px = pos_base + (size_t)slot * 3 * Npp;
+    double* py = px + Npp;
+    double* pz = py + Npp;
+    double* red = red_base + slot * WARPS;
+    const bool have = w < a.W;
+    double* gpos = a.pos + (size_t)(have ? w : 0) * 3 * s.Np;
+    const double L = s.L, Linv = s.Linv, Lhalf = s.Lhalf;
+    for (int i = gl; i < s.N; i += STRIDE)
+    {
+        px[i] = wrap_fast(gpos[i], L, Linv);
+        py[i] = wrap_fast(gpos[s.Np + i], L, Linv);
+        pz[i] = wrap_fast(gpos[2 * s.Np + i], L, Linv);
+    }
+    __syncthreads();
+    if (!have) return; // all warps of the slot leave together
+
+    const uint32_t gw = (uint32_t)(a.first_walker + w);
+    const int N = s.N;
+    const int bar_id = 1 + slot; // named barrier of this walker's warps (0 is __syncthreads)
+    unsigned long long n_acc = 0;
+
+    for (long long t0 = 0; t0 < a.n_steps; t0 += 32)
+    {
+        Proposal mine;
+        mine.particle = 0;
+        mine.dx = mine.dy = mine.dz = 0.0;
+        mine.log_u = 0.0;
+        if (t0 + lane < a.n_steps) mine = make_proposal(a.seed, gw, a.first_step + (uint64_t)(t0 + lane), N, a.mc_step);
+        const int nsub = (int)min(32ll, a.n_steps - t0);
+
+        for (int sidx = 0; sidx < nsub; sidx++)
+        {
+            const int p = __shfl_sync(FULL_MASK, mine.particle, sidx);
+            const double ddx = __shfl_sync(FULL_MASK, mine.dx, sidx);
+            const double ddy = __shfl_sync(FULL_MASK, mine.dy, sidx);
+            const double ddz = __shfl_sync(FULL_MASK, mine.dz, sidx);
+            const double log_u = __shfl_sync(FULL_MASK, mine.log_u, sidx);
+
+            const double ox = px[p], oy = py[p], oz = pz[p];
+            const double nx = wrap_fast(ox + ddx, L, Linv);
+            const double ny = wrap_fast(oy + ddy, L, Linv);
+            const double nz = wrap_fast(oz + ddz, L, Linv);
+
+            double delta = 0.0;
+#pragma unroll 2
+            for (int i = gl; i < N; i += STRIDE)
+            {
+                const double xi = px[i], yi = py[i], zi = pz[i];
+                const double r_old = sqrt_fast(dist2<false>(xi - ox, yi - oy, zi - oz, Lhalf));
+                const double r_new = sqrt_fast(dist2<false>(xi - nx, yi - ny, zi - nz, Lhalf));
+                const double u_old = pair_u<UNIFORM, REFLECT, kCubCopies>(s, c01p, c23p, ttp, lut, r_old);
+                const double u_new = pair_u<UNIFORM, REFLECT, kCubCopies>(s, c01p, c23p, ttp, lut, r_new);
+                const double d = u_new - u_old;
+                if (i != p) delta += d;
+            }
+            delta = group_sum<32>(delta);
+            if (lane == 0) red[wsub] = delta;
+            // all warps of the walker: parts published, old positions read
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(STRIDE) : "memory");
+            double tot = 0.0;
+#pragma unroll
+            for (int q = 0; q < WARPS; q++) tot += red[q];
+
+            const double two_delta = 2.0 * tot;
+            const bool accept = (two_delta >= log_u) && (two_delta <= 709.782712893384);
+            if (accept)
+            {
+                if (gl == 0)
+                {
+                    px[p] = nx;
+                    py[p] = ny;
+                    pz[p] = nz;
+                }
+                n_acc++;
+            }
+            // new position visible, sums consumed, before the next proposal
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(STRIDE) : "memory");
+        }
+    }
+
+    for (int i = gl; i < N; i += STRIDE)
+    {
+        gpos[i] = px[i];
+        gpos[s.Np + i] = py[i];
+        gpos[2 * s.Np + i] = pz[i];
+    }
+    if (gl == 0) a.accepted[w] += n_acc;
+}
+
+// warps per walker for an ensemble of W walkers on sm_count SMs: enough to reach ~16 warps per SM, at least two partners
+// per lane, 1 (= sweep_kernel) when the ensemble fills the machine by itself
+int sweep_split_warps(const SysDev& s, int W, int sm_count, int resident_per_sm)
+{
+    if (s.kind != 0 || s.dim != 3 || W <= 0) return 1;
+    if (const char* e = getenv("TDVMC_SWEEP_SPLIT")) // tuning knob: 1 = never split
+    {
+        const int v = atoi(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8) return v;
+    }
+    const int wps = (W + sm_count - 1) / sm_count; // walkers per SM
+    const int target = resident_per_sm > 0 ? (resident_per_sm < 16 ? 16 : resident_per_sm) : 16;
+    int warps = 1;
+    while (warps < 8 && wps * warps * 2 <= target && 64 * warps * 2 <= s.N) warps *= 2;
+    return warps;
+}
+
+static size_t sweep_split_smem_bytes(const SysDev& s, int spb, int warps, int npp, size_t* pos_offset)
+{
+    const size_t nrec = (size_t)s.nbins + 1;
+    size_t off = nrec * kCubCopies * 2 * sizeof(double2);
+    if (!s.uniform) off += nrec * sizeof(double2) + (size_t)s.ncell * sizeof(unsigned short);
+    off = (off + 15) & ~(size_t)15;
+    *pos_offset = off;
+    return off + (size_t)spb * 3 * npp * sizeof(double) + (size_t)spb * warps * sizeof(double);
+}
+
+template <int WARPS>
+static const void* sweep_split_fn(const SysDev& s)
+{
+    const bool refl = s.pair_rule == 1;
+    return s.uniform ? (refl ? (const void*)sweep_split_kernel<true, true, WARPS> : (const void*)sweep_split_kernel<true, false, WARPS>)
+                     : (refl ? (const void*)sweep_split_kernel<false, true, WARPS> : (const void*)sweep_split_kernel<false, false, WARPS>);
+}
+
+// a.wpb is ignored; walkers per block follow from the ensemble size, the thread budget, the named barriers and shared memory
+cudaError_t launch_sweep_split(SweepArgs a, int warps, int sm_count, int smem_optin, cudaStream_t st)
+{
+    const int wps = (a.W + sm_count - 1) / sm_count;
+    int spb = wps < 1 ? 1 : wps;
+    spb = std::min(spb, std::min(kSweepMaxThreadsWarp / (32 * warps), 15));
+    size_t pos_off = 0, smem = 0;
+    for (; spb >= 1; spb--)
+    {
+        smem = sweep_split_smem_bytes(a.s, spb, warps, a.npp, &pos_off);
+        if (smem <= (size_t)smem_optin) break;
+    }
+    if (spb < 1) return cudaErrorInvalidConfiguration;
+    a.wpb = spb;
+    a.pos_offset = (int)pos_off;
+    const void* fn = warps == 2 ? sweep_split_fn<2>(a.s) : (warps == 4 ? sweep_split_fn<4>(a.s) : sweep_split_fn<8>(a.s));
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    void* args[] = { &a };
+    return cudaLaunchKernel(fn, dim3((a.W + spb - 1) / spb), dim3(spb * warps * 32), args, smem, st);
 }
 
 // exponentNew - exponent for scripted moves of one configuration: the ratio evaluator of the sweep,
