@@ -39,9 +39,28 @@ FLOP_PER_WALKER_STEP = 2 * (N - 1) * (22 + 1 + 6)          # 19 836
 FLOP_PER_EVALUATION = 5.0e6
 BYTES_PER_TABLE = 8 * 203 * N * 4 + 24 * N                  # 2 236 360 (K3 table kernel)
 METRIC = "walker-steps/s"
-# dram__bytes_read.sum + dram__bytes_write.sum of one sweep_kernel launch (2960 walkers) from the ncu --set full capture
-# profiles/r01f_sweep_ncu.txt (24.50 MB read, 0 written); algorithmic traffic is 2 x 8.2 KB per walker per launch = 48.7 MB (the write-back stays in L2)
-SWEEP_DRAM_BYTES_PER_LAUNCH_NCU = 24.5e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one sweep_kernel launch (2960 walkers): read from the committed ncu --set full
+# summary of THIS build's kernel (profiles/run_r02a.sh); algorithmic traffic is 2 x 8.2 KB per walker per launch = 48.7 MB (the
+# write-back stays in L2)
+SWEEP_NCU_SUMMARY = os.path.join("profiles", "r02a_sweep_ncu.txt")
+
+
+def sweep_traffic_from_ncu():
+    """(bytes per launch, source) from the committed summary, or (None, reason)."""
+    path = os.path.join(ROOT, SWEEP_NCU_SUMMARY)
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        tot, seen = 0.0, 0
+        for line in open(path):
+            t = line.split()
+            if len(t) >= 3 and t[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(t[1].replace(",", "")) * unit.get(t[2], 1.0)
+                seen += 1
+        if seen == 2:
+            return tot, SWEEP_NCU_SUMMARY + " (ncu --set full, sweep_kernel<1,0,2,0,0,32,0>, 2960 walkers per launch, r02 build)"
+    except OSError:
+        pass
+    return None, "no ncu summary found"
 
 
 def golden_spec():
@@ -54,7 +73,7 @@ def golden_spec():
 
 def workload_config(extra=None):
     c = {"workload": "BosonsBulk3D.config scaled to N=343 (LBOX=7, N_PARAM=201): ParallelUpdateExpectationValues pass",
-         "N": N, "LBOX": LBOX, "N_PARAM": N_PARAM, "MC_STEP": MC_STEP, "MC_NSTEPS": MC_NSTEPS,
+         "N": N, "LBOX": LBOX, "N_PARAM": N_PARAM, "MC_STEP": MC_STEP, "MC_NSTEPS": MC_NSTEPS, "walkers_per_gpu_survey": 4096,
          "MC_NTHERMSTEPS": MC_NTHERMSTEPS, "MC_NINITIALIZATIONSTEPS": MC_NINIT,
          "proposals_per_walker_per_step": STEPS_PER_WALKER,
          "spline_table": "reference SplineFactory::GetWeights3 output (tests/golden/bosonsbulk_n343_equil.npz)"}
@@ -139,6 +158,44 @@ def port_step(cpus):
     return trials, secs
 
 
+
+def reference_time_steps(uR, uI, R, cpus, samples_target):
+    """BASELINE's second metric on the host: `duration for full timestep` (src/TDVMC.cpp:3919-3923) of the unmodified reference
+    PROGRAM (oracle/_ref/TDVMC_ref: config file, Euler step with the config's Eigen QR solve, the seven per-step file appends),
+    one single-rank process per physical core as in BASELINE.md 3.  Two bounded runs of three time steps each - MC_NSTEPS = 2
+    (the config's own count) and MC_NSTEPS = 6 - separate the per-sample cost from the fixed cost of a step, which gives the
+    duration of a step whose TOTAL sample count matches the device's (samples = processes x MC_NSTEPS)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from tdvmc_b200 import driver
+    ref = os.path.join(ROOT, "oracle", "_ref", "TDVMC_ref")
+    if not os.path.exists(ref):
+        return None
+    dur = {}
+    with tempfile.TemporaryDirectory() as td:
+        for ns in (2, 6):
+            cfg = driver.headline_config(uR, uI, MC_NSTEPS=ns, TIMESTEP=1e-7, TOTALTIME=2.5e-7, MC_VERY_FIRST_NINITIALIZATIONSTEPS=1000)
+
+            def one(i):
+                env = dict(os.environ)
+                r = driver.run_driver(ref, cfg, os.path.join(td, f"ts_{ns}_{i}"), R0=R, seed=i + 1, timeout=600,
+                                      prefix=["taskset", "-c", str(cpus[i])], env=env)
+                return float(np.mean(r.step_ms))
+
+            with ThreadPoolExecutor(max_workers=len(cpus)) as ex:
+                dur[ns] = float(np.mean(list(ex.map(one, range(len(cpus))))))
+    per_sample = (dur[6] - dur[2]) / 4.0
+    fixed = dur[2] - 2.0 * per_sample
+    per_core = samples_target / float(len(cpus))
+    matched_ms = fixed + per_core * per_sample
+    return {"cores": len(cpus), "ms_per_time_step_config_counts": dur[2], "samples_per_time_step_config_counts": 2 * len(cpus),
+            "time_steps_per_s_config_counts": 1e3 / dur[2],
+            "ms_per_sample_per_core": per_sample, "ms_fixed_per_time_step": fixed,
+            "samples_per_time_step_matched": samples_target, "ms_per_time_step_sample_matched": matched_ms,
+            "time_steps_per_s_sample_matched": 1e3 / matched_ms,
+            "how": "TDVMC_ref, one pinned single-rank process per physical core, 3 time steps at MC_NSTEPS = 2 and at 6 "
+                   "(MC_NTHERMSTEPS = 5000, MC_NINITIALIZATIONSTEPS = 1000, Euler, LINEAR_EQUATION_SOLVER_TYPE = 1, file appends): "
+                   "step duration = fixed + samples per core x per-sample cost, evaluated at the device arm's samples per time step"}
+
 REFERENCE_KIND = "reference"
 
 
@@ -178,6 +235,11 @@ def reference_main(args, rank):
     with tempfile.TemporaryDirectory() as td:
         trials, secs, cores = run_reference(args.steps, args.warmup, td, spec, uR, uI, R)
     value = trials / secs
+    ts = None
+    try:
+        ts = reference_time_steps(uR, uI, R, physical_cores(), 5920 * max(args.gpus, 1))
+    except Exception as ex:  # a report, never the product
+        ts = {"failed": str(ex)[-300:]}
     what = "the unmodified reference" if REFERENCE_KIND == "reference" else "the plain-C port of the reference (oracle/tdvmc_oracle.c)"
     sample = (f"{cores} single-rank processes of {what} (one per physical core, taskset-pinned, "
               f"serial MPI shim), each one walker's pass per step: {MC_NINIT} initialization proposals run BEFORE the clock starts, "
@@ -187,7 +249,8 @@ def reference_main(args, rank):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config({"walkers": cores}),
-            "time_steps_per_s": args.steps / secs,
+            "time_steps_per_s": (ts or {}).get("time_steps_per_s_sample_matched"),
+            "time_step": ts,
             "cpu_baseline": {"value": value, "unit": "walker-steps/s", "cores": cores, "kind": REFERENCE_KIND, "sample": sample},
             "e2e": {"value": value, "unit": "walker-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -326,6 +389,14 @@ def main():
         dist.broadcast(uid, 0)
         h.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
 
+    def join_comm(hx):
+        if world > 1:
+            uidx = torch.zeros(capi.UNIQUE_ID_BYTES, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                uidx.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
+            dist.broadcast(uidx, 0)
+            hx.comm_init(bytes(uidx.cpu().numpy().tobytes()), rank, world)
+
     # synthetic ensemble: jittered 7^3 lattices (src/TDVMC.cpp:727-739), equilibrated by 100 sweeps
     rng = np.random.default_rng(1000 + rank)
     R_host = torch.empty((W, N, 3), dtype=torch.float64).pin_memory()
@@ -430,6 +501,78 @@ def main():
     n_solve, ms_solve = h.kernel_stats()["solve"]
     h.profile(False, False)
 
+    # ---- the same pass at other ensemble sizes (one JSON line carries them all) ----
+    def side_run(Wx, k):
+        """walker-steps/s of k passes with Wx walkers per GPU (own handle, own communicator, same protocol as the main run)."""
+        hx = capi.Handle(spec, Wx, seed=1, mc_step=MC_STEP, first_walker=rank * Wx, max_samples=MC_NSTEPS, device=local_rank)
+        join_comm(hx)
+        rx = np.random.default_rng(2000 + rank)
+        Rx = systems.jittered_lattice(N, LBOX, rx)[None] + rx.uniform(-0.02, 0.02, (Wx, N, 3))
+        hx.set_params(uR, uI, 0.0, 0.0, 0.0)
+        hx.set_positions(Rx)
+        hx.sweep(100 * N)
+        hx.wrap_positions()
+        ox = None
+
+        def stepx():
+            nonlocal ox
+            hx.set_params(uR, uI, 0.0, 0.0, 0.0)
+            hx.sample_and_accumulate(MC_NSTEPS, MC_NTHERMSTEPS, MC_NINIT)
+            ox = hx.allreduce_and_fetch(ox)
+            hx.flush_l2()
+
+        stepx()
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        hx.synchronize()
+        hx.timer_start()
+        for _ in range(k):
+            stepx()
+        msx = max_over_ranks(hx.timer_stop())
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        hx.close()
+        return {"walkers_per_gpu": Wx, "walkers": Wx * world, "steps": k, "ms_per_step": msx / k,
+                "value": float(Wx) * world * STEPS_PER_WALKER * k / (msx * 1e-3), "unit": "walker-steps/s"}
+
+    side = {}
+    if not args.total_walkers and not args.walkers_per_gpu:
+        k_side = max(3, min(args.steps, 5))
+        # SURVEY.md 8(d): W = 4096 x G walkers (1.38 waves of the sweep kernel per GPU: two launches' time for 1.38x the work)
+        side["survey_w4096"] = side_run(4096, k_side)
+        # strong scaling: the 8-GPU weak-scaling ensemble (8 x 2960 = 23 680 walkers) split over the GPUs of THIS run
+        side["strong"] = dict(side_run(23680 // world, k_side), total_walkers=23680,
+                              note="fixed ensemble of 23 680 walkers (= the weak-scaling ensemble at 8 GPUs) split over n_gpus")
+
+    # ---- TDVMC time-steps/s through the reference's own driver bound to the library (tdvmc_b200/host/build/TDVMC_gpu) ----
+    driver_steps = None
+    if world == 1 and rank == 0:
+        from tdvmc_b200 import driver
+        if os.path.exists(driver.TDVMC_GPU):
+            driver_steps = {}
+            K = max(args.steps, 20)
+            for name, over in (("host_solve_qr", dict(LINEAR_EQUATION_SOLVER_TYPE=1, USE_PRECONDITIONING=0)),
+                               ("device_solve_cholesky", dict(LINEAR_EQUATION_SOLVER_TYPE=0, USE_PRECONDITIONING=1, GPU_DEVICE_SOLVE=1))):
+                try:
+                    with tempfile.TemporaryDirectory() as td:
+                        cfg = driver.headline_config(uR, uI, TIMESTEP=1e-7, TOTALTIME=1e-7 * (K + 0.5), GPU_WALKERS=W,
+                                                     MC_VERY_FIRST_NINITIALIZATIONSTEPS=34300, **over)
+                        t0 = time.perf_counter()
+                        run = driver.run_driver(driver.TDVMC_GPU, cfg, td, R0=R_seed, timeout=600)
+                        wall = time.perf_counter() - t0
+                        e_last = float(run.local_energy_r[-1])   # (the .dat files live in the temporary directory)
+                    ms = run.step_ms[1:]                      # the first step pays the lazy CUDA initialisations
+                    driver_steps[name] = {"time_steps_per_s": 1e3 / float(np.mean(ms)), "ms_per_time_step": float(np.mean(ms)),
+                                          "time_steps": int(len(ms)), "samples_per_time_step": W * MC_NSTEPS,
+                                          "process_wall_s": wall, "local_energy_r_last": e_last}
+                except Exception as ex:
+                    driver_steps[name] = {"failed": str(ex)[-300:]}
+            driver_steps["what"] = ("the reference's own src/TDVMC.cpp (15 call sites re-pointed, tdvmc_b200/host/driver) run as a program: "
+                                    "config file in, per time step BroadcastNewParameters, the estimator pass on the device "
+                                    "(GPU_WALKERS walkers x MC_NSTEPS samples), fetch, SolveForParametersDot + Euler (host Eigen QR as the "
+                                    "config says, or solve_kernel), AcceptNewParams, the seven AppendDataToFile calls; "
+                                    "'duration for full timestep' as the driver prints it (1 ms resolution, mean over the steps)")
+
     proposals = float(W) * world * STEPS_PER_WALKER * args.steps
     value = proposals / (ms_total * 1e-3)
     e2e_value = proposals / (ms_e2e * 1e-3)
@@ -442,8 +585,11 @@ def main():
     n_sweep, ms_sweep = stats["sweep"]
     sweep_flops = FLOP_PER_WALKER_STEP * float(W) * STEPS_PER_WALKER * args.steps
     sweep_tf = sweep_flops / (ms_sweep * 1e-3) / 1e12
+    traffic, traffic_src = sweep_traffic_from_ncu()
+    if W != 2960:
+        traffic, traffic_src = None, "the committed capture is for 2960 walkers per launch"
     roofline = {"kernel": "sweep_kernel (K1)", "bound": "fp64", "achieved": sweep_tf, "peak": dfma_peak, "unit": "TFLOP/s",
-                "frac": sweep_tf / dfma_peak, "traffic": SWEEP_DRAM_BYTES_PER_LAUNCH_NCU,
+                "frac": sweep_tf / dfma_peak, "traffic": traffic, "traffic_source": traffic_src,
                 "note": "FP64 DFMA-pipe bound (SURVEY 8d): 19 836 algorithmic flop per walker-step; peak = DFMA microbenchmark "
                         "measured in this run (MEASURED_PEAKS.json has no FP64 entry); HBM traffic is 16.5 KB per walker per launch",
                 "launches": n_sweep, "avg_launch_ms": ms_sweep / max(n_sweep, 1), "share_of_step": ms_sweep / ms_total}
@@ -466,6 +612,7 @@ def main():
     hbm_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
 
     cpu_baseline = None
+    secondary, ref_ts = [], None
     if not args.no_exhibits and rank == 0:
         # K3 / K4 exhibits: reference table semantics on resident walkers (HBM bound)
         nt = min(W, 1024)
@@ -531,6 +678,22 @@ def main():
             kernels.append({"kernel": f"syrk_kernel (K5, M=2^{logm})", "bound": "tensor", "achieved": fl / tx / 1e12, "peak": dgemm_tf,
                             "unit": "TFLOP/s", "frac": fl / tx / 1e12 / dgemm_tf, "ms": tx * 1e3})
             del Ox
+        # secondary workloads (BASELINE configs 1, 2, 4, 5): device pass with the config's own step : evaluation ratio and the
+        # unmodified reference on EVERY physical core at once; config 4's reference pass is bounded to 2 samples
+        secondary = []
+        if world == 1:
+            sys.path.insert(0, os.path.join(ROOT, "profiles"))
+            try:
+                import bench_configs
+                cpus_all = physical_cores()
+                for idx in (1, 2, 4, 5):
+                    try:
+                        secondary.append(bench_configs.run_config(idx, 3, cpus=cpus_all, dfma_tflops=dfma_peak,
+                                                                  ref_samples=2 if idx == 4 else bench_configs.SAMPLES))
+                    except Exception as ex:
+                        secondary.append({"config": bench_configs.CONFIGS[idx][0], "failed": str(ex)[-300:]})
+            except Exception as ex:
+                secondary.append({"failed": str(ex)[-300:]})
         # CPU baseline: the unmodified reference on this box's host cores, one pass per core
         if world == 1:
             try:
@@ -544,6 +707,10 @@ def main():
                                           f"{secs * cores:.0f} core-seconds"}
             except Exception as ex:  # the baseline is a report, never the product
                 cpu_baseline = {"value": None, "unit": "walker-steps/s", "cores": 0, "kind": REFERENCE_KIND, "sample": f"failed: {ex}"}
+            try:
+                ref_ts = reference_time_steps(uR, uI, R_seed, physical_cores(), W * MC_NSTEPS)
+            except Exception as ex:
+                ref_ts = {"failed": str(ex)[-300:]}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "walker-steps/s", "n_gpus": world, "steps": args.steps,
@@ -552,7 +719,9 @@ def main():
                 "config": workload_config({"walkers_per_gpu": W, "walkers": W * world, "parallelism": f"walkers x{world}",
                                            "l2": "flushed between steps (256 MiB memset); walker state is 29 MB per GPU"}),
                 "time_steps_per_s": args.steps / (ms_ts * 1e-3),
+                "survey_w4096": side.get("survey_w4096"), "strong": side.get("strong"), "secondary": secondary,
                 "time_step": {"ms": ms_ts / args.steps, "samples_per_time_step": W * world * MC_NSTEPS,
+                              "driver_binary": driver_steps, "reference_host": ref_ts,
                               "includes": "set_params, estimator pass, all-reduce, Cholesky solve of S u' = F on the device "
                                           "(P = 201, solve_kernel), Euler update, parameter feedback; every rank solves redundantly",
                               "solve_kernel_ms": ms_solve / max(n_solve, 1),

@@ -154,6 +154,18 @@ typedef struct tdvmc_estimators
 int tdvmc_gpu_abi_version(void);
 int tdvmc_gpu_device_count(void);
 
+/* Supported envelope (tdvmc_gpu_create refuses anything outside it with a message, nothing is truncated):
+ *   all systems          N_PARAM + 3 <= 208 (register-resident S matrix of the accumulation kernel), DIM as stated below
+ *   SPLINE_TABLE         one configuration must fit one SM's shared memory in the evaluation kernel: about N <= 2000 at
+ *                        N_PARAM ~ 200 (N = 1728 of config/NUBosonsBulkPB3D.config fits; N = 8000 of config/BosonsBulk3D.config
+ *                        as shipped does not); DIM 1, 2 or 3
+ *   HE_BULK / HE_DROP    DIM = 3
+ *   MIXTURE              N <= 8 particles, n_ext <= 96, spline order 3 or 4, DIM = 3
+ *   BOX_RADIAL           DIM 2 or 3, one walker's tables must fit shared memory
+ *   INH_CONTACT          DIM = 1, N <= 32
+ *   device solver        N_PARAM <= 1024, Cholesky branch only (LINEAR_EQUATION_SOLVER_TYPE = 0, IMAGINARY_TIME 0 or 1)
+ *   observables          g(r) / S(k) for DIM = 3 */
+
 int tdvmc_gpu_create(const tdvmc_system_desc* system, const tdvmc_ensemble_desc* ensemble, tdvmc_gpu_handle** out);
 void tdvmc_gpu_destroy(tdvmc_gpu_handle* h);
 const char* tdvmc_gpu_last_error(const tdvmc_gpu_handle* h); /* h may be NULL: error of the last failed create */

@@ -2,7 +2,8 @@
 """Throughput of the BASELINE configs that are parity cases rather than the headline (configs 1, 2, 4, 5),
 through the same C ABI as bench.py.  One JSON line per config: walker-steps/s and samples/s of a
 ParallelUpdateExpectationValues pass with the config's own MC_NTHERMSTEPS : 1 evaluation ratio, the share of the sweep and
-evaluation kernels, and the unmodified reference timed on ONE host core with the same counts (oracle/_ref/ref_harness).
+evaluation kernels, and the unmodified reference timed on ONE host core - or, with --full-host, on every physical core at
+once - with the same counts (oracle/_ref/ref_harness).  bench.py imports run_config for its `secondary` list.
 
     python profiles/bench_configs.py [--configs 1,2,4,5] [--reps 3] > profiles/rNN_configs.jsonl
 
@@ -38,8 +39,10 @@ CONFIGS = {
 SAMPLES = 8
 
 
-def reference_one_core(g, system, mc_step, n_therm, n_init, n_samples):
-    """The unmodified reference, one walker on one core, same counts; returns (proposals/s, samples/s) or None."""
+def reference_host(g, system, mc_step, n_therm, n_init, n_samples, cpus=None):
+    """The unmodified reference with the same counts: one walker's pass on one core (cpus None), or one pass on EVERY core of
+    `cpus` at the same time (pinned single-rank processes, rank-seeded) - the full-host figure of BASELINE.md 3.5.
+    Returns (proposals/s, samples/s, cores) or None."""
     if not os.path.exists(HARNESS):
         return None
     dim = int(g["DIM"]) if "DIM" in g.files else 3
@@ -56,21 +59,30 @@ def reference_one_core(g, system, mc_step, n_therm, n_init, n_samples):
         scal["GR_BIN_COUNT"] = 400 if system.startswith("BosonMixtureCluster") else len(g["other_expectation_values"]) - (
             3 if system == "NUBosonsBulkPBBoxAndRadial" else 9)
     with tempfile.TemporaryDirectory() as td:
-        case = os.path.join(td, "case.txt")
-        with open(case, "w") as f:
-            f.write(f"system {system}\nconfigdir {ROOT}/oracle/_ref/config/\n")
-            for k, v in scal.items():
-                f.write(f"{k} {v!r}\n")
-            for k, v in arrays.items():
-                f.write(k + " " + " ".join(repr(float(x)) for x in np.asarray(v).ravel()) + "\n")
-        r = subprocess.run([HARNESS, "bench", case], capture_output=True, text=True, cwd=td)
-        if r.returncode != 0:
-            return None
-        trials, secs, samples = r.stdout.split()[:3]
-        return float(trials) / float(secs), float(samples) / float(secs)
+        procs = []
+        for rank, cpu in enumerate(cpus or [None]):
+            case = os.path.join(td, f"case_{rank}.txt")
+            with open(case, "w") as f:
+                f.write(f"system {system}\nconfigdir {ROOT}/oracle/_ref/config/\n")
+                for k, v in dict(scal, seed=rank + 1).items():
+                    f.write(f"{k} {v!r}\n")
+                for k, v in arrays.items():
+                    f.write(k + " " + " ".join(repr(float(x)) for x in np.asarray(v).ravel()) + "\n")
+            cmd = ([] if cpu is None else ["taskset", "-c", str(cpu)]) + [HARNESS, "bench", case]
+            procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, cwd=td))
+        trials = samples = 0.0
+        secs = 0.0
+        for pr in procs:
+            o = pr.communicate()[0].split()
+            if pr.returncode != 0 or len(o) < 3:
+                return None
+            trials += float(o[0])
+            samples += float(o[2])
+            secs = max(secs, float(o[1]))
+        return trials / secs, samples / secs, len(procs)
 
 
-def run_config(idx, reps):
+def run_config(idx, reps, cpus=None, dfma_tflops=None, ref_samples=SAMPLES):
     path, fixture, system, mc_step, n_therm, n_init, W = CONFIGS[idx]
     g = np.load(os.path.join(GOLDEN, fixture + ".npz"))
     spec = systems.from_golden(g)
@@ -103,11 +115,19 @@ def run_config(idx, reps):
             "accumulate_ms": stats["accumulate"][1] / reps, "resident_walkers_per_sm": per_sm,
             "acceptance": out["n_acceptances"] / out["n_trials"], "local_energy_r": float(out["e_r"][0])}
     h.close()
-    ref = reference_one_core(g, system, mc_step, n_therm, n_init, SAMPLES)
+    # algorithmic work per unit as SURVEY.md 8(d) counts it: 2 (N - 1) x 29 flop per walker-step, 85 flop per pair per sample
+    line["sweep_tflops"] = 2.0 * (N - 1) * 29 * steps / (stats["sweep"][1] * 1e-3) / 1e12
+    line["evaluate_tflops"] = 85.0 * N * (N - 1) / 2 * float(W) * SAMPLES * reps / (stats["evaluate"][1] * 1e-3) / 1e12
+    if dfma_tflops:
+        line["sweep_frac_of_dfma_peak"] = line["sweep_tflops"] / dfma_tflops
+        line["evaluate_frac_of_dfma_peak"] = line["evaluate_tflops"] / dfma_tflops
+    ref = reference_host(g, system, mc_step, n_therm, n_init, ref_samples, cpus)
     if ref:
-        line["reference_one_core"] = {"walker_steps_per_s": ref[0], "samples_per_s": ref[1],
-                                      "note": "unmodified reference (oracle/_ref/ref_harness bench), one walker, one core, same counts"}
-        line["walker_steps_ratio_vs_one_core"] = line["walker_steps_per_s"] / ref[0]
+        key = "reference_full_host" if cpus else "reference_one_core"
+        line[key] = {"walker_steps_per_s": ref[0], "samples_per_s": ref[1], "cores": ref[2],
+                     "note": "unmodified reference (oracle/_ref/ref_harness bench), one walker's pass per core"
+                             f" ({n_init} + {ref_samples} x {n_therm} proposals, {ref_samples} evaluations), pinned single-rank processes"}
+        line["walker_steps_ratio_vs_full_host" if cpus else "walker_steps_ratio_vs_one_core"] = line["walker_steps_per_s"] / ref[0]
     return line
 
 
@@ -115,9 +135,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="1,2,4,5")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--full-host", action="store_true", help="reference on every physical core instead of one")
     a = ap.parse_args()
+    cpus = None
+    if a.full_host:
+        import bench
+        cpus = bench.physical_cores()
     for idx in [int(x) for x in a.configs.split(",")]:
-        print(json.dumps(run_config(idx, a.reps)), flush=True)
+        print(json.dumps(run_config(idx, a.reps, cpus=cpus)), flush=True)
 
 
 if __name__ == "__main__":

@@ -914,6 +914,17 @@ int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed,
     // sweep geometry: as many walkers (warps) per block as keep >= 2 blocks per SM resident
     h->npp = (h->N + 1) & ~1;
     SysDev s = h->sysdev();
+    if (h->kind == TDVMC_SYSTEM_SPLINE_TABLE && evaluate_smem_bytes(s) > (size_t)h->smem_optin)
+    {
+        // one block evaluates one configuration with positions, forces and per-warp histograms in shared memory
+        char msg[256];
+        snprintf(msg, sizeof(msg),
+                 "N = %d particles with %d splines need %zu bytes of shared memory per configuration in the evaluation kernel, "
+                 "the device offers %d (N <= ~2000 at N_PARAM ~ 200): not supported",
+                 h->N, h->K, evaluate_smem_bytes(s), h->smem_optin);
+        h->error = msg;
+        return bail(-3);
+    }
     // Walkers (warps) per block: as many as fit, but a multiple of 4 per SM -- the four SM sub-partitions
     // each run resident/4 warps and the slowest one sets the pace (measured: 20 walkers/SM beat 21 by 13 %).
     int best_wpb = 1, best_res = 0, best_score = -1;

@@ -56,6 +56,7 @@ struct EvalArgs
 };
 cudaError_t launch_evaluate(const EvalArgs& a, cudaStream_t st);
 int evaluate_blocks_per_sm(const SysDev& s);   // 2 (12-warp blocks) or 1 (24-warp blocks, large N)
+size_t evaluate_smem_bytes(const SysDev& s);   // dynamic shared memory of one evaluation block
 cudaError_t launch_evaluate_he(const EvalArgs& a, cudaStream_t st);  // HeBulk, HeDrop (evaluate_he.cu)
 
 // single-particle move ratios for scripted moves of one configuration (quotient_fixed)

@@ -104,14 +104,18 @@ __global__ void __launch_bounds__(kTabWarps * 32) tables_kernel(TableArgs a, int
                 bin = find_bin_exact(s, m.knots, m.lut, r);
                 const double* w = m.rec + (size_t)(bin - s.first_bin) * kRecStride;
                 const double r2 = r * r;
-                const double ex = vx / r, ey = vy / r, ez = vz / r; // BosonsBulk.cpp:304-307
+                // IEEE divisions as in the reference (BosonsBulk.cpp:304-307, 319): on the perfect-lattice fixture the table
+                // entries cancel to ~1e-6 of their terms, and a reciprocal-multiply (one ulp off per term; 3.30 instead of
+                // 3.66 ms per 1024 configurations) fails the 1e-13 table parity there
+                const double ex = vx / r, ey = vy / r, ez = vz / r;
                 const double f2 = s.dm1 / r;                        // secondDerivativeFactor / rni
 #pragma unroll
                 for (int p = 0; p < 4; p++)
                 {
-                    const double w1 = w[p * 4 + 1], w2 = w[p * 4 + 2], w3 = w[p * 4 + 3];
-                    const double d1 = w1 + 2.0 * w2 * r + 3.0 * w3 * r2;
-                    const double d2 = 2.0 * w2 + 6.0 * w3 * r;
+                    const double2 w01 = *reinterpret_cast<const double2*>(w + p * 4);
+                    const double2 w23 = *reinterpret_cast<const double2*>(w + p * 4 + 2);
+                    const double d1 = w01.y + 2.0 * w23.x * r + 3.0 * w23.y * r2;
+                    const double d2 = 2.0 * w23.x + 6.0 * w23.y * r;
                     q[p][0] = d1 * ex;
                     q[p][1] = d1 * ey;
                     q[p][2] = d1 * ez;

@@ -173,11 +173,12 @@ def write_rng_state(cfg_dir, seed, n_particles, rank=0):
             f.write(text + "\n")
 
 
-def run_driver(binary, config, workdir, R0=None, timeout=3600, env=None, seed=None):
+def run_driver(binary, config, workdir, R0=None, timeout=3600, env=None, seed=None, prefix=None):
     """Writes `config` (dict from base_config & co.) and the auxiliary files into `workdir`, runs `binary <config>` there
     and returns a DriverRun.  R0 ([N][DIM]) becomes coords/particleconfiguration_<N>_<D>D_0.csv, the restart format
     InitCoordinateConfiguration reads (src/TDVMC.cpp:677, :640-670).  `seed` (host RNG of the reference's CPU path and of the
-    start jitter) goes in through the RNG state files; the device ensemble's stream is the config item GPU_SEED."""
+    start jitter) goes in through the RNG state files; the device ensemble's stream is the config item GPU_SEED.  `prefix`:
+    command prefix such as ["taskset", "-c", "3"]."""
     os.makedirs(workdir, exist_ok=True)
     cfg_dir = os.path.join(workdir, "cfg")
     out_root = os.path.join(workdir, "output")
@@ -199,7 +200,7 @@ def run_driver(binary, config, workdir, R0=None, timeout=3600, env=None, seed=No
         json.dump(c, f, indent=1)
     import time
     t0 = time.perf_counter()
-    p = subprocess.run([os.path.abspath(binary), path], cwd=workdir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout,
+    p = subprocess.run(list(prefix or []) + [os.path.abspath(binary), path], cwd=workdir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout,
                        env=env)
     wall = time.perf_counter() - t0
     if p.returncode != 0:

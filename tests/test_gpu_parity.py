@@ -1607,3 +1607,12 @@ def test_low_dimensional_chain_and_estimators_match_oracle(capi, golden, name):
     assert abs(got["e_r"][0] - want["e_r"]) < 1e-9 * abs(want["e_r"])
     assert abs(got["e_i"][0] - want["e_i"]) < 1e-9 * max(abs(want["e_i"]), 1e-3 * abs(want["e_r"]))
     h.close()
+
+
+def test_oversized_system_is_refused_at_create(capi, golden):
+    """config/BosonsBulk3D.config as shipped (N = 8000): one configuration does not fit one SM's shared memory in the
+    evaluation kernel - tdvmc_gpu_create says so instead of failing at the first sample."""
+    g = golden("bosonsbulk_n343_equil")
+    spec = systems.bosons_bulk(8000, 20.0, 201, [1.0, 1.0], weights=g["spline_weights"] if False else None)
+    with pytest.raises(capi.TdvmcError, match="shared memory per configuration"):
+        capi.Handle(spec, 4)
