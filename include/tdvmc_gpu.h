@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TDVMC_GPU_ABI_VERSION 1
+#define TDVMC_GPU_ABI_VERSION 2
 
 typedef struct tdvmc_gpu_handle tdvmc_gpu_handle;
 
@@ -207,15 +207,21 @@ int tdvmc_gpu_allreduce_and_fetch(tdvmc_gpu_handle* h, tdvmc_estimators* out);
 int tdvmc_gpu_last_exponent(tdvmc_gpu_handle* h, double* exponent);
 
 /* ---- parameter derivatives and the Euler step on the device ---- */
-/* Options of SolveForParametersDot with LINEAR_EQUATION_SOLVER_TYPE = 0 (src/TDVMC.cpp:1713-1763). */
+/* Options of SolveForParametersDot (src/TDVMC.cpp:1713-1828).  The device offers the Cholesky branch
+ * (LINEAR_EQUATION_SOLVER_TYPE = 0, :1733-1763) for all three values of IMAGINARY_TIME.  The Eigen FullPivHouseholderQR
+ * branch (LINEAR_EQUATION_SOLVER_TYPE = 1, :1763-1827) is NOT offered on the device: a desc with solver_type = 1 is refused
+ * with a message - a driver configured for it fetches the estimators (tdvmc_gpu_allreduce_and_fetch) and keeps its own
+ * host solve, which is what tdvmc_b200/host/driver does (tests/test_gpu_driver.py::test_driver_real_time_qr_branch_n64). */
 typedef struct tdvmc_solver_desc
 {
     uint32_t struct_size;
-    int32_t imaginary_time;      /* IMAGINARY_TIME: 0 real time, 1 imaginary time (the -1 rotation is not offered) */
+    int32_t imaginary_time;      /* IMAGINARY_TIME: 0 real time, 1 imaginary time, -1 the 1.499 pi time rotation (:1475-1504, 1666-1673) */
     int32_t use_preconditioning; /* USE_PRECONDITIONING: scale by sqrt(diag), src/TDVMC.cpp:1684-1701 */
     int32_t force_global_scratch;/* tests: factorise in global memory even when P fits shared memory */
     double regularization;       /* RegularizeEquationSystem; the reference hard-codes 0.001 (src/TDVMC.cpp:1737) */
     double min_scaling;          /* 0 = reference behaviour; > 0 floors the scalings (a parameter whose operator never varied) */
+    int32_t solver_type;         /* LINEAR_EQUATION_SOLVER_TYPE: 0 Cholesky; anything else is refused (see above) */
+    int32_t reserved;            /* 0 */
 } tdvmc_solver_desc;
 /* What the root rank of the reference holds after SolveForParametersDot (+ the energies the driver logs each step). */
 typedef struct tdvmc_parameters_dot

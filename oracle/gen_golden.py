@@ -420,7 +420,7 @@ def gen_mixture_observables():
     np.savez_compressed(os.path.join(GOLDEN, "mixture_he4he4na_obs.npz"), **out)
 
 
-def gen_evolution():
+def gen_evolution(only=None):
     """Time evolution by the reference's own time-step functions (ref_harness evolve): BosonsBulk N = 64, Euler steps
     with the Cholesky solve, 24 RNG seeds -> mean and spread of the parameter trajectories and of the energies
     (north_star level 2: time-evolved parameters agree statistically), plus the first step's estimators and
@@ -430,7 +430,11 @@ def gen_evolution():
     g = np.load(os.path.join(GOLDEN, "bosonsbulk_n64_equil.npz"))
     P = int(g["N_PARAM"])
     seeds = list(range(1, 25))
-    for name, imag, dt, nsteps in (("bosonsbulk_n64_evolution", 1, 2e-4, 30), ("bosonsbulk_n64_evolution_realtime", 0, 1e-4, 12)):
+    for name, imag, dt, nsteps in (("bosonsbulk_n64_evolution", 1, 2e-4, 30), ("bosonsbulk_n64_evolution_realtime", 0, 1e-4, 12),
+                                   # IMAGINARY_TIME = -1: the 1.499 pi time rotation (src/TDVMC.cpp:1475-1504, 1666-1673)
+                                   ("bosonsbulk_n64_evolution_rotation", -1, 1e-4, 6)):
+        if only and name not in only:
+            continue
         base = dict(N=64, LBOX=4.0, N_PARAM=P, time=0.0, phiR=0.0, phiI=0.0, MC_STEP=0.4, MC_NSTEPS=1024, MC_NTHERMSTEPS=32,
                     MC_NINITIALIZATIONSTEPS=64, IMAGINARY_TIME=imag, TIMESTEP=dt, time_steps=nsteps, equilibration_steps=6400)
         arr = dict(R=g["R"], uR=g["uR"], uI=np.zeros(P), SYSTEM_PARAMS=[1.0, 1.0])

@@ -47,7 +47,8 @@ class Estimators(C.Structure):
 class SolverDesc(C.Structure):
     """tdvmc_solver_desc"""
     _fields_ = [("struct_size", C.c_uint32), ("imaginary_time", C.c_int32), ("use_preconditioning", C.c_int32),
-                ("force_global_scratch", C.c_int32), ("regularization", C.c_double), ("min_scaling", C.c_double)]
+                ("force_global_scratch", C.c_int32), ("regularization", C.c_double), ("min_scaling", C.c_double),
+                ("solver_type", C.c_int32), ("reserved", C.c_int32)]
 
 
 class ParametersDot(C.Structure):
@@ -256,9 +257,10 @@ class Handle:
 
     # ---- parameter derivatives / Euler step on the device ----
     @staticmethod
-    def _solver_desc(imaginary_time=1, use_preconditioning=True, regularization=0.001, min_scaling=0.0, force_global=False):
+    def _solver_desc(imaginary_time=1, use_preconditioning=True, regularization=0.001, min_scaling=0.0, force_global=False,
+                     solver_type=0):
         return SolverDesc(C.sizeof(SolverDesc), int(imaginary_time), int(bool(use_preconditioning)), int(bool(force_global)),
-                          float(regularization), float(min_scaling))
+                          float(regularization), float(min_scaling), int(solver_type), 0)
 
     def _dot_out(self):
         o = dict(u_dot_r=np.empty(self.P), u_dot_i=np.empty(self.P))

@@ -1271,8 +1271,10 @@ int tdvmc_gpu_allreduce_and_fetch(tdvmc_gpu_handle* h, tdvmc_estimators* out)
 static int do_solve(tdvmc_gpu_handle* h, const tdvmc_solver_desc* sd, const double* d_est, tdvmc_parameters_dot* out)
 {
     if (sd->struct_size != sizeof(tdvmc_solver_desc)) return fail(h, "solver desc: struct_size mismatch");
-    if (sd->imaginary_time != 0 && sd->imaginary_time != 1)
-        return fail(h, "solver: IMAGINARY_TIME must be 0 or 1 (the time rotation of src/TDVMC.cpp:1448-1504 is not offered)");
+    if (sd->imaginary_time < -1 || sd->imaginary_time > 1) return fail(h, "solver: IMAGINARY_TIME must be -1, 0 or 1");
+    if (sd->solver_type != 0)
+        return fail(h, "solver: LINEAR_EQUATION_SOLVER_TYPE = 1 (Eigen FullPivHouseholderQR, src/TDVMC.cpp:1763-1827) is not offered on "
+                       "the device; fetch the estimators and use the driver's own host solve");
     if (h->P > 1024) return fail(h, "solver: N_PARAM > 1024");
     const int P = h->P;
     CK(h->d_sol.ensure(2 * (size_t)P + 5));

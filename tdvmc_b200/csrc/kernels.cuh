@@ -145,7 +145,7 @@ struct SolveArgs
     const double* est;     // packed estimator SUMS: S[P*P] | F_R[P] | F_I[P] | O[P] | E_R | E_I | other | acc | trials | samples
     int cnt_offset;        // index of `acc` in est
     int P;
-    int imaginary_time;    // IMAGINARY_TIME: 0 real time, 1 imaginary time
+    int imaginary_time;    // IMAGINARY_TIME: 0 real time, 1 imaginary time, -1 time rotation
     int use_preconditioning;
     double regularization; // 0.001 in the reference (src/TDVMC.cpp:1737)
     double min_scaling;    // 0: reference behaviour

@@ -55,7 +55,14 @@ __global__ void __launch_bounds__(1024, 1) solve_kernel(SolveArgs a)
     for (int i = tid; i < P; i += T)
     {
         const double oer = FR[i] * inv, oei = FI[i] * inv;
-        if (a.imaginary_time == 0) // src/TDVMC.cpp:1518-1523
+        if (a.imaginary_time == -1) // BuildSystemOfEquationsForParametersIncludePhiWithTimeRotation, src/TDVMC.cpp:1475-1504
+        {
+            const double rotation = 1.499 * 3.14159265358979323846; // 3/2 Pi -> real time; Pi -> imaginary time (:1477)
+            const double c = cos(rotation), sn = sin(rotation);
+            bR[i] = c * (oer - ER * O[i]) - sn * (oei);
+            bI[i] = sn * (oer - ER * O[i]) + c * (oei);
+        }
+        else if (a.imaginary_time == 0) // src/TDVMC.cpp:1518-1523
         {
             bR[i] = oei - EI * O[i];
             bI[i] = -oer + ER * O[i];
@@ -221,7 +228,13 @@ __global__ void __launch_bounds__(1024, 1) solve_kernel(SolveArgs a)
             pr -= O[i] * xR[i];
             pi -= O[i] * xI[i];
         }
-        if (a.imaginary_time == 0) pi -= ER;
+        if (a.imaginary_time == -1) // CalculatePhiDot, :1666-1673
+        {
+            const double rotation = 1.499 * 3.14159265358979323846;
+            pi -= cos(rotation) * ER;
+            pr -= sin(rotation) * ER;
+        }
+        else if (a.imaginary_time == 0) pi -= ER;
         else pr -= ER;
         double* tail = a.out + 2 * (size_t)P;
         tail[0] = pr;

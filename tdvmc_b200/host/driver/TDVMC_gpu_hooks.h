@@ -340,7 +340,7 @@ bool GpuParallelCalculateAdditionalSystemProperties(vector<double>& uR, vector<d
 // CalculateNextParametersEuler (src/TDVMC.cpp:1834-1853) with the Cholesky branch of SolveForParametersDot on the device
 bool GpuCalculateNextParametersEuler(double dt, vector<double>& uR, vector<double>& uI, double* phiR, double* phiI)
 {
-	if (!gpu || GPU_DEVICE_SOLVE != 1 || LINEAR_EQUATION_SOLVER_TYPE != 0 || IMAGINARY_TIME < 0 || USE_PARAM_START != 0 || (USE_PARAM_END != 0 && USE_PARAM_END != N_PARAM - 1))
+	if (!gpu || GPU_DEVICE_SOLVE != 1 || LINEAR_EQUATION_SOLVER_TYPE != 0 || USE_PARAM_START != 0 || (USE_PARAM_END != 0 && USE_PARAM_END != N_PARAM - 1))
 	{
 		return false;
 	}

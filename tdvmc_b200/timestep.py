@@ -27,8 +27,13 @@ def build_system_of_equations(est, imaginary_time=1):
     elif imaginary_time == 1:
         b_r = -OER + ER * O
         b_i = -OEI                      # :1526 - the imaginary right-hand side is not centred in imaginary time
+    elif imaginary_time == -1:          # BuildSystemOfEquationsForParametersIncludePhiWithTimeRotation, :1475-1504
+        rotation = 1.499 * np.pi
+        c, sn = np.cos(rotation), np.sin(rotation)
+        b_r = c * (OER - ER * O) - sn * OEI
+        b_i = sn * (OER - ER * O) + c * OEI
     else:
-        raise ValueError("time rotation (IMAGINARY_TIME = -1) is not mirrored")
+        raise ValueError("IMAGINARY_TIME must be -1, 0 or 1")
     A = S - np.outer(O, O)
     A = np.tril(A) + np.tril(A, -1).T    # the reference fills the lower triangle and mirrors it (:1528-1533)
     return A, b_r, b_i
@@ -85,7 +90,11 @@ def solve_for_parameters_dot(est, imaginary_time=1, use_preconditioning=True, re
     O = np.asarray(est["localOperators"], np.float64)
     phi_r = -float(np.dot(O, u_r))      # CalculatePhiDot runs BEFORE the scalings are divided out (:1743-1752)
     phi_i = -float(np.dot(O, u_i))
-    if imaginary_time == 0:
+    if imaginary_time == -1:            # CalculatePhiDot, :1666-1673
+        rotation = 1.499 * np.pi
+        phi_i -= np.cos(rotation) * float(est["localEnergyR"])
+        phi_r -= np.sin(rotation) * float(est["localEnergyR"])
+    elif imaginary_time == 0:
         phi_i -= float(est["localEnergyR"])
     else:
         phi_r -= float(est["localEnergyR"])

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == {n for n, _, _ in capi.SYMBOLS}
-    assert capi.load().tdvmc_gpu_abi_version() == 1
+    assert capi.load().tdvmc_gpu_abi_version() == 2
 
 
 def test_struct_layouts_match_header_sizes():
@@ -45,7 +45,7 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(capi.ClusterObservableDesc) == 4 * 4 + 5 * 8 + 8
     assert C.sizeof(capi.EnsembleDesc) == 6 * 4 + 8 + 8
     assert C.sizeof(capi.Estimators) == 7 * 8 + 3 * 8
-    assert C.sizeof(capi.SolverDesc) == 4 * 4 + 2 * 8
+    assert C.sizeof(capi.SolverDesc) == 4 * 4 + 2 * 8 + 2 * 4
     assert C.sizeof(capi.ParametersDot) == 2 * 8 + 4 * 8 + 8
 
 
@@ -223,7 +223,7 @@ def test_cpp_he_table_builders_match_python_specs():
             np.testing.assert_array_equal(got if got.size else np.zeros(P), want if want is not None else np.zeros(P))
 
 
-@pytest.mark.parametrize("name", ["bosonsbulk_n64_evolution", "bosonsbulk_n64_evolution_realtime"])
+@pytest.mark.parametrize("name", ["bosonsbulk_n64_evolution", "bosonsbulk_n64_evolution_realtime", "bosonsbulk_n64_evolution_rotation"])
 def test_timestep_solver_matches_reference(golden, name):
     """tdvmc_b200.timestep (host mirror of SolveForParametersDot, Cholesky branch) reproduces the derivatives the
     reference computed from its own first-step estimators (ref_harness evolve)."""
