@@ -8,7 +8,8 @@ Workload (BASELINE.json configs[2]): config/BosonsBulk3D.config scaled to N=343,
 One "step" is one ParallelUpdateExpectationValues pass (src/TDVMC.cpp:1152-1188) with the config's own
 sample counts: MC_NINITIALIZATIONSTEPS=1000 + MC_NSTEPS=2 x MC_NTHERMSTEPS=5000 Metropolis proposals
 per walker, 2 evaluations per walker, the S/F accumulation, the packed all-reduce and the fetch of
-the seven estimator arrays.  value = proposals of all walkers on all GPUs / time (walker-steps/s).
+the seven estimator arrays, for W = 4096 walkers per GPU.  value = proposals of all walkers on all GPUs /
+time (walker-steps/s).
 
 Prints ONE JSON line (rank 0).  Under torchrun (N > 1) every rank drives one GPU; walkers are
 sharded (fixed count per GPU -> "weak"), the only collective is the packed NCCL all-reduce.
@@ -39,10 +40,11 @@ FLOP_PER_WALKER_STEP = 2 * (N - 1) * (22 + 1 + 6)          # 19 836
 FLOP_PER_EVALUATION = 5.0e6
 BYTES_PER_TABLE = 8 * 203 * N * 4 + 24 * N                  # 2 236 360 (K3 table kernel)
 METRIC = "walker-steps/s"
-# dram__bytes_read.sum + dram__bytes_write.sum of one sweep_kernel launch (2960 walkers): read from the committed ncu --set full
-# summary of THIS build's kernel (profiles/run_r02a.sh); algorithmic traffic is 2 x 8.2 KB per walker per launch = 48.7 MB (the
-# write-back stays in L2)
-SWEEP_NCU_SUMMARY = os.path.join("profiles", "r02a_sweep_ncu.txt")
+SURVEY_WALKERS_PER_GPU = 4096   # W = 4096 x G walkers
+# dram__bytes_read.sum + dram__bytes_write.sum of one sweep launch (4096 walkers, 5000 steps): read from the committed ncu
+# --set full summary of THIS build's kernel (profiles/run_r02.sh); algorithmic traffic is 2 x 8.2 KB per walker per launch =
+# 67 MB; the time-shared kernel moves a walker through L2 once per chunk (10 chunks), which stays in the 126 MB L2
+SWEEP_NCU_SUMMARY = os.path.join("profiles", "r02_sweep_queue_ncu.txt")
 
 
 def sweep_traffic_from_ncu():
@@ -57,7 +59,7 @@ def sweep_traffic_from_ncu():
                 tot += float(t[1].replace(",", "")) * unit.get(t[2], 1.0)
                 seen += 1
         if seen == 2:
-            return tot, SWEEP_NCU_SUMMARY + " (ncu --set full, sweep_kernel<1,0,2,0,0,32,0>, 2960 walkers per launch, r02 build)"
+            return tot, SWEEP_NCU_SUMMARY + " (ncu --set full, sweep_queue_kernel<1,0>, 4096 walkers x 5000 steps per launch, r02 build)"
     except OSError:
         pass
     return None, "no ncu summary found"
@@ -73,7 +75,7 @@ def golden_spec():
 
 def workload_config(extra=None):
     c = {"workload": "BosonsBulk3D.config scaled to N=343 (LBOX=7, N_PARAM=201): ParallelUpdateExpectationValues pass",
-         "N": N, "LBOX": LBOX, "N_PARAM": N_PARAM, "MC_STEP": MC_STEP, "MC_NSTEPS": MC_NSTEPS, "walkers_per_gpu_survey": 4096,
+         "N": N, "LBOX": LBOX, "N_PARAM": N_PARAM, "MC_STEP": MC_STEP, "MC_NSTEPS": MC_NSTEPS, "walkers_per_gpu_survey": SURVEY_WALKERS_PER_GPU,
          "MC_NTHERMSTEPS": MC_NTHERMSTEPS, "MC_NINITIALIZATIONSTEPS": MC_NINIT,
          "proposals_per_walker_per_step": STEPS_PER_WALKER,
          "spline_table": "reference SplineFactory::GetWeights3 output (tests/golden/bosonsbulk_n343_equil.npz)"}
@@ -237,7 +239,7 @@ def reference_main(args, rank):
     value = trials / secs
     ts = None
     try:
-        ts = reference_time_steps(uR, uI, R, physical_cores(), 5920 * max(args.gpus, 1))
+        ts = reference_time_steps(uR, uI, R, physical_cores(), SURVEY_WALKERS_PER_GPU * MC_NSTEPS * max(args.gpus, 1))
     except Exception as ex:  # a report, never the product
         ts = {"failed": str(ex)[-300:]}
     what = "the unmodified reference" if REFERENCE_KIND == "reference" else "the plain-C port of the reference (oracle/tdvmc_oracle.c)"
@@ -343,7 +345,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--walkers-per-gpu", type=int, default=0, help="0: one full wave of the sweep kernel")
+    ap.add_argument("--walkers-per-gpu", type=int, default=0, help="0: 4096 (SURVEY.md 8d)")
     ap.add_argument("--total-walkers", type=int, default=0,
                     help="fixed ensemble split over the GPUs (strong scaling); default: fixed walkers per GPU (weak)")
     ap.add_argument("--no-exhibits", action="store_true", help="skip the K3/K4/K5 roofline exhibits and the CPU baseline")
@@ -371,11 +373,13 @@ def main():
 
     spec, uR, uI, R_seed = golden_spec()
 
-    # ensemble size: one full wave of the sweep kernel per GPU (weak scaling: fixed walkers per GPU)
+    # ensemble size: SURVEY.md 8(d)'s W = 4096 walkers per GPU (weak scaling: fixed walkers per GPU).  That is 1.38 waves of
+    # the one-warp-per-walker sweep kernel (20 resident walkers x 148 SMs = 2960); the library time-shares the resident warps
+    # in that case (sweep_queue_kernel).  The exact-wave ensemble of round 1 is reported beside it as `full_wave`.
     probe = capi.Handle(spec, 1, device=local_rank)
     per_sm, sms = probe.resident_walkers()
     probe.close()
-    W = args.walkers_per_gpu or per_sm * sms
+    W = args.walkers_per_gpu or SURVEY_WALKERS_PER_GPU
     scaling = "weak"
     if args.total_walkers > 0:
         W = max(1, args.total_walkers // world)
@@ -538,8 +542,8 @@ def main():
     side = {}
     if not args.total_walkers and not args.walkers_per_gpu:
         k_side = max(3, min(args.steps, 5))
-        # W = 4096 x G walkers (1.38 waves of the sweep kernel per GPU: two launches' time for 1.38x the work)
-        side["survey_w4096"] = side_run(4096, k_side)
+        # the exact-wave ensemble (resident walkers x SMs = 2960 per GPU): round 1's headline configuration
+        side["full_wave"] = side_run(per_sm * sms, k_side)
         # strong scaling: the 8-GPU weak-scaling ensemble (8 x 2960 = 23 680 walkers) split over the GPUs of THIS run
         side["strong"] = dict(side_run(23680 // world, k_side), total_walkers=23680,
                               note="fixed ensemble of 23 680 walkers (= the weak-scaling ensemble at 8 GPUs) split over n_gpus")
@@ -586,12 +590,12 @@ def main():
     sweep_flops = FLOP_PER_WALKER_STEP * float(W) * STEPS_PER_WALKER * args.steps
     sweep_tf = sweep_flops / (ms_sweep * 1e-3) / 1e12
     traffic, traffic_src = sweep_traffic_from_ncu()
-    if W != 2960:
-        traffic, traffic_src = None, "the committed capture is for 2960 walkers per launch"
-    roofline = {"kernel": "sweep_kernel (K1)", "bound": "fp64", "achieved": sweep_tf, "peak": dfma_peak, "unit": "TFLOP/s",
+    if W != SURVEY_WALKERS_PER_GPU:
+        traffic, traffic_src = None, "the committed capture is for 4096 walkers per launch"
+    roofline = {"kernel": "sweep_queue_kernel (K1, time-shared launch)" if W != per_sm * sms else "sweep_kernel (K1)", "bound": "fp64", "achieved": sweep_tf, "peak": dfma_peak, "unit": "TFLOP/s",
                 "frac": sweep_tf / dfma_peak, "traffic": traffic, "traffic_source": traffic_src,
                 "note": "FP64 DFMA-pipe bound (SURVEY 8d): 19 836 algorithmic flop per walker-step; peak = DFMA microbenchmark "
-                        "measured in this run (MEASURED_PEAKS.json has no FP64 entry); HBM traffic is 16.5 KB per walker per launch",
+                        "measured in this run (MEASURED_PEAKS.json has no FP64 entry); algorithmic HBM traffic is 16.5 KB per walker per launch",
                 "launches": n_sweep, "avg_launch_ms": ms_sweep / max(n_sweep, 1), "share_of_step": ms_sweep / ms_total}
     n_ev, ms_ev = stats["evaluate"]
     ev_tf = FLOP_PER_EVALUATION * float(W) * MC_NSTEPS * args.steps / (ms_ev * 1e-3) / 1e12
@@ -717,9 +721,9 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": scaling,
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config({"walkers_per_gpu": W, "walkers": W * world, "parallelism": f"walkers x{world}",
-                                           "l2": "flushed between steps (256 MiB memset); walker state is 29 MB per GPU"}),
+                                           "l2": "flushed between steps (256 MiB memset); walker state is 34 MB per GPU"}),
                 "time_steps_per_s": args.steps / (ms_ts * 1e-3),
-                "survey_w4096": side.get("survey_w4096"), "strong": side.get("strong"), "secondary": secondary,
+                "full_wave": side.get("full_wave"), "strong": side.get("strong"), "secondary": secondary,
                 "time_step": {"ms": ms_ts / args.steps, "samples_per_time_step": W * world * MC_NSTEPS,
                               "driver_binary": driver_steps, "reference_host": ref_ts,
                               "includes": "set_params, estimator pass, all-reduce, Cholesky solve of S u' = F on the device "

@@ -1048,7 +1048,10 @@ static int do_sweep(tdvmc_gpu_handle* h, long long n_steps, double* pos = nullpt
         CK(h->kind == TDVMC_SYSTEM_MIXTURE ? launch_sweep_mix(a, h->stream)
            : h->kind == TDVMC_SYSTEM_INH_CONTACT ? launch_sweep_inh(a, h->stream)
            : h->kind == TDVMC_SYSTEM_BOX_RADIAL ? launch_sweep_br(a, h->stream)
-           : split > 1 ? launch_sweep_split(a, split, h->sm_count, h->smem_optin, h->stream) : launch_sweep(a, h->stream));
+           : split > 1 ? launch_sweep_split(a, split, h->sm_count, h->smem_optin, h->stream)
+           : (h->kind == TDVMC_SYSTEM_SPLINE_TABLE && sweep_queue_wanted(a.s, h->W, h->sm_count, h->resident_per_sm, n_steps))
+               ? launch_sweep_queue(a, h->sm_count, h->smem_optin, h->stream)
+               : launch_sweep(a, h->stream));
     }
     h->step_counter += (uint64_t)n_steps;
     h->trials_local += (uint64_t)n_steps * (uint64_t)h->W;

@@ -33,6 +33,9 @@ cudaError_t launch_sweep(SweepArgs a, cudaStream_t st);
 // several warps per walker for small ensembles / large systems (sweep_split_kernel); warps from sweep_split_warps (> 1)
 int sweep_split_warps(const SysDev& s, int W, int sm_count, int resident_per_sm);
 cudaError_t launch_sweep_split(SweepArgs a, int warps, int sm_count, int smem_optin, cudaStream_t st);
+// ensembles that are not a whole number of waves: walkers time-share the resident warps (sweep_queue_kernel)
+bool sweep_queue_wanted(const SysDev& s, int W, int sm_count, int resident_per_sm, long long n_steps);
+cudaError_t launch_sweep_queue(SweepArgs a, int sm_count, int smem_optin, cudaStream_t st);
 int sweep_blocks_per_sm(const SysDev& s, int wpb, int npp);
 int sweep_walkers_per_warp(const SysDev& s);
 int sweep_max_threads(const SysDev& s);

@@ -36,6 +36,7 @@
 #include "sweep_math.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 
 namespace tdvmc
@@ -436,6 +437,186 @@ cudaError_t launch_sweep_split(SweepArgs a, int warps, int sm_count, int smem_op
     cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     void* args[] = { &a };
     return cudaLaunchKernel(fn, dim3((a.W + spb - 1) / spb), dim3(spb * warps * 32), args, smem, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Ensembles that are not a whole number of waves: walkers time-share the resident warps (r02).
+//
+// sweep_kernel keeps one walker per warp for the whole launch, so an ensemble of 4096 walkers on 148 SMs x 20 resident
+// warps (1.38 waves - the size SURVEY.md 8(d) specifies) takes the time of two waves.  Here every SM gets an equal share of
+// the walkers (27 or 28 at W = 4096) and its 20 warps draw work units (walker, chunk of ~n_steps / 10 steps) from a
+// shared-memory counter, chunk-major: all warps stay busy until the last round, the launch takes ~(walkers per SM / 20)
+// instead of ceil(.) wave times.  A walker's state travels through HBM between its chunks (16.5 KB per unit - nothing
+// against ~10^7 FP64 instructions per unit); a per-walker flag orders chunk c + 1 after chunk c.  The proposal stream is a
+// function of (seed, walker, step), so the chains are those of sweep_kernel.
+template <bool UNIFORM, bool REFLECT>
+__global__ void __launch_bounds__(kSweepMaxThreadsWarp, 1) sweep_queue_kernel(SweepArgs a, int chunk_steps)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SysDev& s = a.s;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int Npp = a.npp;
+    const int nrec = s.nbins + 1;
+
+    double2* c01s = reinterpret_cast<double2*>(smem_raw);
+    double2* c23s = c01s + (size_t)nrec * kCubCopies;
+    double2* tts = c23s + (size_t)nrec * kCubCopies;
+    unsigned short* lut = reinterpret_cast<unsigned short*>(tts + (UNIFORM ? 0 : nrec));
+    double* pos_base = reinterpret_cast<double*>(smem_raw + a.pos_offset);
+    int* s_next = reinterpret_cast<int*>(pos_base + (size_t)a.wpb * 3 * Npp); // unit counter, then done[walkers of this block]
+    volatile int* s_done = s_next + 1;
+
+    const int w_begin = (int)((long long)blockIdx.x * a.W / gridDim.x);
+    const int w_end = (int)((long long)(blockIdx.x + 1) * a.W / gridDim.x);
+    const int nW = w_end - w_begin;
+    {
+        const double2* g01 = reinterpret_cast<const double2*>(s.cub);
+        const double2* g23 = g01 + nrec;
+        const double2* gtt = g23 + nrec;
+        for (int i = threadIdx.x; i < nrec * kCubCopies; i += blockDim.x)
+        {
+            c01s[i] = g01[i / kCubCopies];
+            c23s[i] = g23[i / kCubCopies];
+        }
+        if (!UNIFORM)
+        {
+            for (int i = threadIdx.x; i < nrec; i += blockDim.x) tts[i] = gtt[i];
+            for (int i = threadIdx.x; i < s.ncell; i += blockDim.x) lut[i] = s.lut[i];
+        }
+        if (threadIdx.x == 0) *s_next = 0;
+        for (int i = threadIdx.x; i < nW; i += blockDim.x) s_done[i] = 0;
+    }
+    __syncthreads();
+    const double2* c01p = c01s + (lane & (kCubCopies - 1));
+    const double2* c23p = c23s + (lane & (kCubCopies - 1));
+    const double2* ttp = tts;
+    double* px = pos_base + (size_t)warp * 3 * Npp;
+    double* py = px + Npp;
+    double* pz = py + Npp;
+    const double L = s.L, Linv = s.Linv, Lhalf = s.Lhalf;
+    const int N = s.N;
+    const int n_chunks = (int)((a.n_steps + chunk_steps - 1) / chunk_steps);
+    const int units = nW * n_chunks;
+
+    for (;;)
+    {
+        int unit = 0;
+        if (lane == 0) unit = atomicAdd(s_next, 1);
+        unit = __shfl_sync(FULL_MASK, unit, 0);
+        if (unit >= units) break;
+        const int c = unit / nW, wl = unit - c * nW;
+        const int w = w_begin + wl;
+        if (lane == 0)
+            while (s_done[wl] < c) __nanosleep(200); // the walker's previous chunk (a smaller unit: no deadlock)
+        __syncwarp();
+        __threadfence_block();
+        double* gpos = a.pos + (size_t)w * 3 * s.Np;
+        for (int i = lane; i < N; i += 32)
+        {
+            px[i] = wrap_fast(__ldcg(gpos + i), L, Linv);
+            py[i] = wrap_fast(__ldcg(gpos + s.Np + i), L, Linv);
+            pz[i] = wrap_fast(__ldcg(gpos + 2 * s.Np + i), L, Linv);
+        }
+        __syncwarp();
+
+        const uint32_t gw = (uint32_t)(a.first_walker + w);
+        const long long t_begin = (long long)c * chunk_steps;
+        const long long t_end = min(a.n_steps, t_begin + chunk_steps);
+        unsigned long long n_acc = 0;
+        for (long long t0 = t_begin; t0 < t_end; t0 += 32)
+        {
+            Proposal mine;
+            mine.particle = 0;
+            mine.dx = mine.dy = mine.dz = 0.0;
+            mine.log_u = 0.0;
+            if (t0 + lane < t_end) mine = make_proposal(a.seed, gw, a.first_step + (uint64_t)(t0 + lane), N, a.mc_step);
+            const int nsub = (int)min(32ll, t_end - t0);
+            for (int sidx = 0; sidx < nsub; sidx++)
+            {
+                const int p = __shfl_sync(FULL_MASK, mine.particle, sidx);
+                const double ddx = __shfl_sync(FULL_MASK, mine.dx, sidx);
+                const double ddy = __shfl_sync(FULL_MASK, mine.dy, sidx);
+                const double ddz = __shfl_sync(FULL_MASK, mine.dz, sidx);
+                const double log_u = __shfl_sync(FULL_MASK, mine.log_u, sidx);
+                const double ox = px[p], oy = py[p], oz = pz[p];
+                const double nx = wrap_fast(ox + ddx, L, Linv);
+                const double ny = wrap_fast(oy + ddy, L, Linv);
+                const double nz = wrap_fast(oz + ddz, L, Linv);
+                double delta = 0.0;
+#pragma unroll 2
+                for (int i = lane; i < N; i += 32)
+                {
+                    const double xi = px[i], yi = py[i], zi = pz[i];
+                    const double r_old = sqrt_fast(dist2<false>(xi - ox, yi - oy, zi - oz, Lhalf));
+                    const double r_new = sqrt_fast(dist2<false>(xi - nx, yi - ny, zi - nz, Lhalf));
+                    const double u_old = pair_u<UNIFORM, REFLECT, kCubCopies>(s, c01p, c23p, ttp, lut, r_old);
+                    const double u_new = pair_u<UNIFORM, REFLECT, kCubCopies>(s, c01p, c23p, ttp, lut, r_new);
+                    const double d = u_new - u_old;
+                    if (i != p) delta += d;
+                }
+                delta = group_sum<32>(delta);
+                const double two_delta = 2.0 * delta;
+                const bool accept = (two_delta >= log_u) && (two_delta <= 709.782712893384);
+                __syncwarp();
+                if (accept)
+                {
+                    if (lane == 0)
+                    {
+                        px[p] = nx;
+                        py[p] = ny;
+                        pz[p] = nz;
+                    }
+                    n_acc++;
+                }
+                __syncwarp();
+            }
+        }
+        for (int i = lane; i < N; i += 32)
+        {
+            __stcg(gpos + i, px[i]);
+            __stcg(gpos + s.Np + i, py[i]);
+            __stcg(gpos + 2 * s.Np + i, pz[i]);
+        }
+        if (lane == 0) atomicAdd(a.accepted + w, n_acc); // (successive chunks of a walker run on different warps)
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) s_done[wl] = c + 1;
+    }
+}
+
+// Use the time-shared launch?  Only for the three-dimensional spline-table systems, when the ensemble is more than one
+// wave and the last wave of a plain launch would leave more than ~8 % of the machine idle.
+bool sweep_queue_wanted(const SysDev& s, int W, int sm_count, int resident_per_sm, long long n_steps)
+{
+    if (s.kind != 0 || s.dim != 3 || resident_per_sm <= 0 || n_steps < 320) return false;
+    if (const char* e = getenv("TDVMC_SWEEP_QUEUE")) // tuning knob: 0 = never
+        if (atoi(e) == 0) return false;
+    const double waves = (double)W / ((double)sm_count * resident_per_sm);
+    if (waves <= 1.0) return false;
+    if ((W + sm_count - 1) / sm_count > 4096) return false; // (the flag array lives in shared memory)
+    return waves / std::ceil(waves) < 0.92;
+}
+
+cudaError_t launch_sweep_queue(SweepArgs a, int sm_count, int smem_optin, cudaStream_t st)
+{
+    const size_t nrec = (size_t)a.s.nbins + 1;
+    size_t off = nrec * kCubCopies * 2 * sizeof(double2);
+    if (!a.s.uniform) off += nrec * sizeof(double2) + (size_t)a.s.ncell * sizeof(unsigned short);
+    off = (off + 15) & ~(size_t)15;
+    a.pos_offset = (int)off;
+    const int per_sm = (a.W + sm_count - 1) / sm_count;
+    const size_t smem = off + (size_t)a.wpb * 3 * a.npp * sizeof(double) + (size_t)(per_sm + 2) * sizeof(int);
+    if (smem > (size_t)smem_optin) return cudaErrorInvalidConfiguration;
+    int chunk = (int)(a.n_steps / 10);
+    chunk = std::max(32, (chunk + 31) / 32 * 32);
+    const void* fn = a.s.uniform ? (a.s.pair_rule == 1 ? (const void*)sweep_queue_kernel<true, true> : (const void*)sweep_queue_kernel<true, false>)
+                                 : (a.s.pair_rule == 1 ? (const void*)sweep_queue_kernel<false, true> : (const void*)sweep_queue_kernel<false, false>);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    void* args[] = { &a, &chunk };
+    return cudaLaunchKernel(fn, dim3(sm_count), dim3(a.wpb * 32), args, smem, st);
 }
 
 // exponentNew - exponent for scripted moves of one configuration: the ratio evaluator of the sweep,

@@ -1626,3 +1626,54 @@ def test_oversized_system_is_refused_at_create(capi, golden):
     spec = systems.bosons_bulk(8000, 20.0, 201, [1.0, 1.0], weights=g["spline_weights"] if False else None)
     with pytest.raises(capi.TdvmcError, match="shared memory per configuration"):
         capi.Handle(spec, 4)
+
+
+def _sweep_with_env(capi, spec, g, W, n_steps, env):
+    """Positions and acceptance counts after n_steps (two launches) of W walkers under the given tuning knobs."""
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        h = capi.Handle(spec, W, seed=21, mc_step=0.5, max_samples=1)
+        h.set_params(g["uR"], g["uI"], float(g["phiR"]), float(g["phiI"]), float(g["time"]))
+        rng = np.random.default_rng(3)
+        h.set_positions(g["R"][None] + rng.uniform(-0.01, 0.01, (W, spec.n_particles, 3)))
+        h.sweep(n_steps // 2)
+        h.sweep(n_steps - n_steps // 2)
+        R = h.get_positions()
+        h.sample_and_accumulate(1, 0, 0)
+        acc = h.allreduce_and_fetch()["n_acceptances"]
+        h.close()
+        return R, acc
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def test_time_shared_sweep_equals_plain_launch(capi, golden):
+    """sweep_queue_kernel (ensembles that are not a whole number of waves: walkers time-share the resident warps, their
+    state travelling through HBM between chunks) against the plain one-warp-per-walker launch: same proposal stream, same
+    arithmetic per walker - bit-identical configurations and acceptance counts."""
+    g = golden("bosonsbulk_n343_equil")
+    spec = systems.from_golden(g)
+    per_sm, sms = capi.Handle(spec, 1).resident_walkers()
+    W = per_sm * sms + sms // 2 + 7                               # 1.03 waves: the plain launch idles most of the second
+    Rq, aq = _sweep_with_env(capi, spec, g, W, 700, {"TDVMC_SWEEP_QUEUE": "1"})
+    Rp, ap = _sweep_with_env(capi, spec, g, W, 700, {"TDVMC_SWEEP_QUEUE": "0"})
+    assert aq == ap and 0.5 < aq / (W * 700.0) < 0.95
+    assert np.array_equal(Rq, Rp)
+
+
+@pytest.mark.parametrize("name,W", [("bosonsbulk_n343_equil", 300), ("nubosonsbulkpb_n1728_equil", 40)])
+def test_split_sweep_equals_one_warp_per_walker(capi, golden, name, W):
+    """sweep_split_kernel (several warps per walker for ensembles that do not fill the machine) against the one-warp launch:
+    same stream, same accept rule; the exponent change is summed in a different order, so configurations agree to rounding
+    and the acceptance counts exactly (a decision flips only if 2 delta sits within 1e-15 of log U)."""
+    g = golden(name)
+    spec = systems.from_golden(g)
+    Rs, a_s = _sweep_with_env(capi, spec, g, W, 400, {"TDVMC_SWEEP_SPLIT": "4"})
+    R1, a_1 = _sweep_with_env(capi, spec, g, W, 400, {"TDVMC_SWEEP_SPLIT": "1"})
+    assert a_s == a_1
+    assert np.max(np.abs(Rs - R1)) < 1e-12
