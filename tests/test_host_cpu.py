@@ -275,6 +275,19 @@ def test_recorded_bench_line_has_the_contract_keys():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["gpu_launches"] > 0
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    # r02 additions: ensemble-size records, secondary configs against the full host, and the
+    # time-steps/s of the reference's own driver program next to a sample-matched reference figure
+    assert d["config"]["walkers_per_gpu"] == d["config"]["walkers_per_gpu_survey"] == 4096
+    assert d["roofline"]["traffic"] and "profiles/" in d["roofline"]["traffic_source"]
+    for rec in ("full_wave", "strong"):
+        assert d[rec]["value"] > 0 and d[rec]["walkers"] > 0
+    assert d["strong"]["total_walkers"] == 23680
+    assert [c["config"] for c in d["secondary"]] == ["config/drop_6.config", "config/bulk_64.config", "config/NUBosonsBulkPB3D.config",
+                                                      "config/He4He4Na.config"]
+    assert all(c["reference_full_host"]["cores"] >= 1 and c["walker_steps_ratio_vs_full_host"] > 1 for c in d["secondary"])
+    ts = d["time_step"]
+    assert ts["driver_binary"]["host_solve_qr"]["time_steps_per_s"] > 0 and ts["driver_binary"]["device_solve_cholesky"]["time_steps_per_s"] > 0
+    assert ts["reference_host"]["samples_per_time_step_matched"] == ts["driver_binary"]["host_solve_qr"]["samples_per_time_step"]
     # value = proposals of all walkers / time
     steps = d["config"]["proposals_per_walker_per_step"] * d["config"]["walkers"] * d["steps"]
     assert abs(steps / (d["ms_per_step"] * d["steps"] * 1e-3) - d["value"]) < 1e-6 * d["value"]
