@@ -54,6 +54,15 @@ TDVMC_GPU_EXPOSE(NU_weights, PhysicalSystems::NUBosonsBulkPB, TdvmcGpuTensor3, s
 TDVMC_GPU_EXPOSE(NU_kValues, PhysicalSystems::NUBosonsBulkPB, TdvmcGpuTensor3, kValues)
 TDVMC_GPU_EXPOSE(NU_gr, PhysicalSystems::NUBosonsBulkPB, Observables::ObservableVsOnGridWithScaling, pairDistribution)
 TDVMC_GPU_EXPOSE(NU_grBinCount, PhysicalSystems::NUBosonsBulkPB, int, grBinCount)
+// BosonMixtureCluster keeps its per-species / per-pair-type data protected (BosonMixtureCluster.h:42-58)
+TDVMC_GPU_EXPOSE(MX_corrTypes, PhysicalSystems::BosonMixtureCluster, vector<vector<int> >, correlationTypes)
+TDVMC_GPU_EXPOSE(MX_particleTypes, PhysicalSystems::BosonMixtureCluster, vector<int>, particleTypes)
+TDVMC_GPU_EXPOSE(MX_cfd, PhysicalSystems::BosonMixtureCluster, vector<CorrelationFunctionData>, corrFuncData)
+TDVMC_GPU_EXPOSE(MX_pp, PhysicalSystems::BosonMixtureCluster, vector<ParticleProperties>, particleProperties)
+TDVMC_GPU_EXPOSE(MX_ppp, PhysicalSystems::BosonMixtureCluster, vector<ParticlePairProperties>, particlePairProperties)
+TDVMC_GPU_EXPOSE(MX_angular, PhysicalSystems::BosonMixtureCluster, Observables::ObservableVsOnGrid, angularDistribution)
+TDVMC_GPU_EXPOSE(MX_density, PhysicalSystems::BosonMixtureCluster, Observables::ObservableVsOnGridWithScaling, densityFromCOM)
+TDVMC_GPU_EXPOSE(MX_distances, PhysicalSystems::BosonMixtureCluster, Observables::ObservableVsOnGrid, particleDistances)
 
 // new config items (registered next to the reference's, src/TDVMC.cpp:297-349; absent keys stay 0)
 int GPU_WALKERS = 0;      // total number of device-resident walkers over all ranks; 0: reference CPU path
@@ -62,7 +71,9 @@ int GPU_DEVICE_SOLVE = 0; // 1: Euler step with LINEAR_EQUATION_SOLVER_TYPE = 0 
 
 tdvmc_host::GpuEnsembleSystem* gpu = nullptr;
 tdvmc_host::ObservableTables gpuObservableTables;
+tdvmc_host::ClusterObservableTables gpuClusterObservableTables;
 bool gpuHasObservables = false;
+bool gpuHasClusterObservables = false;
 bool gpuSamplesStored = false;
 
 void GpuRegisterConfigItems();
@@ -142,6 +153,50 @@ void GpuInit(vector<vector<double> >& R)
 		gpuObservableTables.grScaling = gr.scalingGrid;
 		gpuObservableTables.kValues = TDVMC_GPU_MEMBER(NU_kValues, *s);
 		gpuHasObservables = DIM == 3;
+	}
+	else if (auto s = dynamic_cast<PhysicalSystems::BosonMixtureCluster*>(sys))
+	{
+		// per-species data per particle, per-pair-type spline sets and potentials as InitSystem() left them (BosonMixtureCluster.cpp:104-346)
+		auto& pt = TDVMC_GPU_MEMBER(MX_particleTypes, *s);
+		auto& pp = TDVMC_GPU_MEMBER(MX_pp, *s);
+		auto& cfd = TDVMC_GPU_MEMBER(MX_cfd, *s);
+		auto& ppp = TDVMC_GPU_MEMBER(MX_ppp, *s);
+		vector<double> hbarOver2m(N), mass(N);
+		for (int n = 0; n < N; n++)
+		{
+			hbarOver2m[n] = pp[pt[n]].hbarOver2m;
+			mass[n] = pp[pt[n]].mass;
+		}
+		vector<tdvmc_host::MixturePairType> types(cfd.size());
+		for (size_t c = 0; c < cfd.size(); c++)
+		{
+			types[c].nodes = cfd[c].nodes;
+			types[c].splineWeights = cfd[c].splineWeights;
+			types[c].bcFactors = cfd[c].bcFactors;
+			types[c].mcMillanFactor = cfd[c].mcMillanFactor;
+			types[c].potential = dynamic_cast<Potentials::KTTY_He_Cs*>(ppp[c].potential) ? 2 : (dynamic_cast<Potentials::KTTY_He_Na*>(ppp[c].potential) ? 1 : 0);
+			if (types[c].potential == 0 && !dynamic_cast<Potentials::HFDB_He_He*>(ppp[c].potential))
+			{
+				known = false; // a pair potential the device does not carry (e.g. LJ_He_He)
+			}
+		}
+		if (known)
+		{
+			t = tdvmc_host::MakeBosonMixtureClusterTables(N, TDVMC_GPU_MEMBER(MX_corrTypes, *s), hbarOver2m, mass, types, sys->GetNumOfOtherExpectationValues(), 3);
+			auto& ang = TDVMC_GPU_MEMBER(MX_angular, *s);
+			auto& den = TDVMC_GPU_MEMBER(MX_density, *s);
+			auto& dis = TDVMC_GPU_MEMBER(MX_distances, *s);
+			gpuClusterObservableTables.angleCount = ang.grid.count;
+			gpuClusterObservableTables.angleSpacing = ang.grid.spacing;
+			gpuClusterObservableTables.densityCount = den.grid.count;
+			gpuClusterObservableTables.densitySpacing = den.grid.spacing;
+			gpuClusterObservableTables.densityMax = den.grid.max;
+			gpuClusterObservableTables.densityScaling = den.scalingGrid;
+			gpuClusterObservableTables.distanceCount = dis.grid.count;
+			gpuClusterObservableTables.distanceSpacing = dis.grid.spacing;
+			gpuClusterObservableTables.distanceMax = dis.grid.max;
+			gpuHasClusterObservables = N == 3; // the reference's own pass hard-codes three particles (:696-706)
+		}
 	}
 	else if (dynamic_cast<PhysicalSystems::HeBulk*>(sys))
 	{
@@ -228,9 +283,9 @@ void GpuBeginTimeStep()
 // AlignCoordinates (src/TDVMC.cpp:2569-2582) for the device-resident walkers
 void GpuAlignCoordinates()
 {
-	if (gpu && sys->USE_NIC)
+	if (gpu && (sys->USE_NIC || sys->USE_MOVE_COM_TO_ZERO))
 	{
-		gpu->MoveCoordinatesToFirstCell();
+		gpu->MoveCoordinatesToFirstCell(); // first cell for the periodic systems, (mass-weighted) centre of mass to zero for the open ones
 	}
 }
 
@@ -313,6 +368,34 @@ bool GpuUpdateSamplesConsecutive(int nrOfSamplesToUpdate, vector<double>& uR, ve
 // ParallelCalculateAdditionalSystemProperties (src/TDVMC.cpp:1438-1444) for the bulk spline systems: g(r) and S(k)
 bool GpuParallelCalculateAdditionalSystemProperties(vector<double>& uR, vector<double>& uI, double phiR, double phiI)
 {
+	if (gpu && gpuHasClusterObservables && MC_NADDITIONALSTEPS > 0)
+	{
+		// BosonMixtureCluster::CalculateAdditionalSystemProperties (BosonMixtureCluster.cpp:680-741): r2, the three corner
+		// angles, density from the centre of mass, pair distances - additionalObservables[0..3] in that order (:342-345)
+		auto o = gpu->ParallelCalculateAdditionalSystemPropertiesCluster(uR, uI, phiR, phiI, gpuClusterObservableTables, MC_NADDITIONALSTEPS,
+				MC_NADDITIONALTHERMSTEPS, MC_NADDITIONALINITIALIZATIONSTEPS, sys->GetTime());
+		additionalObservablesMean.ClearValues();
+		if (auto r = dynamic_cast<Observables::Observable*>(additionalObservablesMean.observables[0]))
+		{
+			r->value = o.r2;
+		}
+		const vector<double>* src[3] = { &o.angularDistribution, &o.densityFromCOM, &o.particleDistances };
+		for (int q = 0; q < 3; q++)
+		{
+			if (auto g = dynamic_cast<Observables::ObservableVsOnGrid*>(additionalObservablesMean.observables[q + 1]))
+			{
+				const size_t count = src[q]->size() / 3;
+				for (size_t v = 0; v < g->observablesV.size() && v < 3; v++)
+				{
+					for (size_t i = 0; i < g->observablesV[v].values.size() && i < count; i++)
+					{
+						g->observablesV[v].values[i] = (*src[q])[v * count + i];
+					}
+				}
+			}
+		}
+		return true;
+	}
 	if (!gpu || !gpuHasObservables || MC_NADDITIONALSTEPS <= 0)
 	{
 		return false;

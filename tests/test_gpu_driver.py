@@ -216,3 +216,53 @@ def test_driver_hedrop_config1_first_pass(binaries, golden, parity_log, tmp_path
         live = (sa > 0) & (sb > 0)
         z = (b.mean(axis=0) - a.mean(axis=0))[live] / np.sqrt(sa[live] ** 2 / len(ref) + sb[live] ** 2 / len(dev))
         parity_log.check("driver_first_pass", "hedrop_n6_config1", f"max|z| {name}", np.max(np.abs(z)), 1.0, 6.5, f"{z.size} values")
+
+
+def test_driver_mixture_config5(binaries, golden, parity_log, tmp_path):
+    """BASELINE configs[4], config/He4He4Na.config (BosonMixtureCluster: two He-4 and one Na, two pair types, HFD-B and KTTY
+    potentials).  The config ships TOTALTIME < 0: its whole workload is the end-of-run observable pass (r^2, corner angles,
+    density from the centre of mass, pair distances; BosonMixtureCluster.cpp:680-741), written to AdditionalObservables_*.dat -
+    compared between the two programs, and so is a short imaginary-time evolution with the config's sampling ratio."""
+    gpu_bin, ref_bin = binaries
+    g = golden("mixture_he4he4na_equil")
+    P = int(g["N_PARAM"])
+    base = driver.base_config(SYSTEM_TYPE="BosonMixtureCluster", N=3, LBOX=float(g["LBOX"]), N_PARAM=P, RHO=0.015, RC=8.8, MC_STEP=4.0,
+                              MC_NTHERMSTEPS=20, MC_NINITIALIZATIONSTEPS=1000, MC_VERY_FIRST_NINITIALIZATIONSTEPS=100000,
+                              TIMESTEP=1e-4, IMAGINARY_TIME=1, ODE_SOLVER_TYPE=0, LINEAR_EQUATION_SOLVER_TYPE=0, USE_PRECONDITIONING=1,
+                              USE_NORMALIZE_WF=1, GR_BIN_COUNT=400, USE_NURBS=1, NURBS_GRID=[float(x) for x in g["NURBS_GRID"]],
+                              PARTICLE_TYPES=[int(x) for x in g["PARTICLE_TYPES"]], SYSTEM_PARAMS=[float(x) for x in g["SYSTEM_PARAMS"]],
+                              PARAMS_REAL=[float(x) for x in g["uR"]], PARAMS_IMAGINARY=[0.0] * P, PARAM_PHIR=float(g["phiR"]))
+    # (a) the config as shipped: no time loop, only the observable pass (counts reduced 25-fold on the reference arm)
+    obs = dict(base, TOTALTIME=-1e-4, MC_NSTEPS=100, MC_NADDITIONALSTEPS=20000, MC_NADDITIONALTHERMSTEPS=100,
+               MC_NADDITIONALINITIALIZATIONSTEPS=10000)
+    ref = run_seeds(ref_bin, obs, "ref_obs", g["R"], list(range(1, 9)), tmp_path)
+    dev = run_seeds(gpu_bin, dict(obs, GPU_WALKERS=2000, MC_NADDITIONALSTEPS=10), "gpu_obs", g["R"], list(range(1, 9)), tmp_path, gpu_seed=True)
+
+    def observable(run, name):
+        path = os.path.join(run.out_dir, f"AdditionalObservables_{name}.dat")
+        if name == "r2":
+            return np.array([float(open(path).read().split()[0])])
+        return driver.read_dat(path)[:, 1:].ravel()          # first column: the grid
+
+    for name in ("r2", "angularDistribution", "densityFromCOM", "particleDistances"):
+        a, b = np.stack([observable(r, name) for r in ref]), np.stack([observable(r, name) for r in dev])
+        assert a.shape == b.shape and np.all(np.isfinite(b))
+        sa, sb = a.std(axis=0, ddof=1), b.std(axis=0, ddof=1)
+        live = (sa > 0) & (sb > 0) & (a.mean(axis=0) > 0.02 * a.mean(axis=0).max())   # bins that are actually populated
+        z = (b.mean(axis=0) - a.mean(axis=0))[live] / np.sqrt(sa[live] ** 2 / len(ref) + sb[live] ** 2 / len(dev))
+        parity_log.check("driver_observables", "mixture_he4he4na_config5", f"max|z| {name}", np.max(np.abs(z)), 1.0, 6.5,
+                         f"{z.size} values, rms z = {np.sqrt(np.mean(z ** 2)):.2f}")
+        assert np.sqrt(np.mean(z ** 2)) < 1.8
+    # (b) four imaginary-time Euler steps at the config's ratio of 20 steps per sample.  With the config's USE_PRECONDITIONING = 1
+    # the reference divides by the zero variance of operators whose knot interval is never visited and stops with "Energy not
+    # finite" after the first step - and so does the device-bound program, fed the same estimators; without it both evolve
+    both = [driver.run_driver(b, dict(base, TOTALTIME=1e-4 * 3.5, MC_NSTEPS=ns, GPU_WALKERS=w), str(tmp_path / f"nan_{i}"), R0=g["R"], seed=2)
+            for i, (b, ns, w) in enumerate(((ref_bin, 20000, 0), (gpu_bin, 10, 2000)))]
+    for r in both:
+        assert len(r.local_energy_r) == 2 and np.isfinite(r.local_energy_r[0]) and np.isnan(r.local_energy_r[1])
+        assert "Energy not finite" in r.log
+    evo = dict(base, TOTALTIME=1e-4 * 3.5, MC_NSTEPS=20000, USE_PRECONDITIONING=0)
+    ref = run_seeds(ref_bin, evo, "ref_evo", g["R"], list(range(1, 9)), tmp_path)
+    dev = run_seeds(gpu_bin, dict(evo, GPU_WALKERS=2000, MC_NSTEPS=10), "gpu_evo", g["R"], list(range(1, 9)), tmp_path, gpu_seed=True)
+    assert len(dev[0].local_energy_r) == 4
+    compare_trajectories(ref, dev, P, parity_log, "mixture_he4he4na_config5")
