@@ -696,6 +696,10 @@ def main():
                                                                   ref_samples=2 if idx == 4 else bench_configs.SAMPLES))
                     except Exception as ex:
                         secondary.append({"config": bench_configs.CONFIGS[idx][0], "failed": str(ex)[-300:]})
+                try:   # config 3 exactly as shipped (N = 8000): BASELINE scales it to N = 343 for the headline
+                    secondary.append(bench_configs.run_config3_as_shipped(1, cpus=cpus_all, dfma_tflops=dfma_peak))
+                except Exception as ex:
+                    secondary.append({"config": "config/BosonsBulk3D.config as shipped (N = 8000)", "failed": str(ex)[-300:]})
             except Exception as ex:
                 secondary.append({"failed": str(ex)[-300:]})
         # CPU baseline: the unmodified reference on this box's host cores, one pass per core

@@ -131,13 +131,14 @@ struct tdvmc_gpu_handle
     uint64_t step_counter = 0; // Metropolis steps done per walker (identical for all walkers)
     uint64_t trials_local = 0; // proposals on this rank since creation
     int wpb = 8, npp = 0, resident_per_sm = 0;
+    bool large_sweep = false;   // walker too large for the one-warp sweep: always sweep_split_kernel with 8 warps, 4 table replicas
 
     // device tables
     DevBuf<double> d_knots, d_rec, d_cub, d_map_val, d_uR, d_uI, d_utR, d_utI, d_map_const;
     DevBuf<unsigned short> d_lut;
     DevBuf<int> d_map_ptr, d_map_col;
     // walkers and samples
-    DevBuf<double> d_pos, d_aos, d_A, d_other, d_exponent, d_samp_pos, d_est, d_scratch;
+    DevBuf<double> d_pos, d_aos, d_A, d_other, d_exponent, d_samp_pos, d_est, d_scratch, d_eval_slab;
     DevBuf<unsigned long long> d_accepted;
     DevBuf<double> d_T, d_vint, d_tab_e; // K3/K4 exhibit buffers, allocated on demand
     int lda = 0, ldc = 0;
@@ -916,12 +917,11 @@ int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed,
     SysDev s = h->sysdev();
     if (h->kind == TDVMC_SYSTEM_SPLINE_TABLE && evaluate_smem_bytes(s) > (size_t)h->smem_optin)
     {
-        // one block evaluates one configuration with positions, forces and per-warp histograms in shared memory
+        // (tables + per-warp histograms alone exceed shared memory: thousands of splines; the configuration itself moves to
+        // global memory for large N, see evaluate_scratch_doubles)
         char msg[256];
-        snprintf(msg, sizeof(msg),
-                 "N = %d particles with %d splines need %zu bytes of shared memory per configuration in the evaluation kernel, "
-                 "the device offers %d (N <= ~2000 at N_PARAM ~ 200): not supported",
-                 h->N, h->K, evaluate_smem_bytes(s), h->smem_optin);
+        snprintf(msg, sizeof(msg), "%d splines need %zu bytes of shared memory in the evaluation kernel, the device offers %d: not supported",
+                 h->K, evaluate_smem_bytes(s), h->smem_optin);
         h->error = msg;
         return bail(-3);
     }
@@ -949,9 +949,21 @@ int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed,
         }
     }
     h->resident_per_sm = best_res * sweep_walkers_per_warp(s); // walkers
+    if (best_res == 0 && h->kind == TDVMC_SYSTEM_SPLINE_TABLE && s.dim == 3 && sweep_large_fits(s, h->npp, h->smem_optin))
+    {
+        // one walker's positions alone nearly fill an SM (N = 8000: 192 KB): eight warps share the walker, four instead of
+        // eight replicas of the coefficient planes make room (sweep_split_kernel<..., 8, 4>)
+        h->large_sweep = true;
+        h->resident_per_sm = 1;
+        best_res = 1;
+        best_wpb = 1;
+    }
     if (best_res == 0)
     {
-        h->error = "system does not fit the sweep kernel's shared memory";
+        char msg[256];
+        snprintf(msg, sizeof(msg), "N = %d particles: one walker (%zu bytes of positions + the coefficient planes) does not fit the sweep "
+                 "kernel's shared memory (%d bytes): not supported", h->N, (size_t)3 * h->npp * sizeof(double), h->smem_optin);
+        h->error = msg;
         return bail(-3);
     }
     h->wpb = best_wpb;
@@ -1044,10 +1056,12 @@ static int do_sweep(tdvmc_gpu_handle* h, long long n_steps, double* pos = nullpt
     a.mc_step = h->mc_step;
     {
         Timed t(h, TDVMC_KERNEL_SWEEP);
-        const int split = h->kind == TDVMC_SYSTEM_SPLINE_TABLE ? sweep_split_warps(a.s, h->W, h->sm_count, h->resident_per_sm) : 1;
+        const int split = h->large_sweep ? -8
+                          : h->kind == TDVMC_SYSTEM_SPLINE_TABLE ? sweep_split_warps(a.s, h->W, h->sm_count, h->resident_per_sm) : 1;
         CK(h->kind == TDVMC_SYSTEM_MIXTURE ? launch_sweep_mix(a, h->stream)
            : h->kind == TDVMC_SYSTEM_INH_CONTACT ? launch_sweep_inh(a, h->stream)
            : h->kind == TDVMC_SYSTEM_BOX_RADIAL ? launch_sweep_br(a, h->stream)
+           : split < 0 ? launch_sweep_split(a, -split, h->sm_count, h->smem_optin, h->stream, 4)
            : split > 1 ? launch_sweep_split(a, split, h->sm_count, h->smem_optin, h->stream)
            : (h->kind == TDVMC_SYSTEM_SPLINE_TABLE && sweep_queue_wanted(a.s, h->W, h->sm_count, h->resident_per_sm, n_steps))
                ? launch_sweep_queue(a, h->sm_count, h->smem_optin, h->stream)
@@ -1091,6 +1105,18 @@ static cudaError_t launch_evaluate_any(int kind, const EvalArgs& a, cudaStream_t
     return kind != TDVMC_SYSTEM_SPLINE_TABLE ? launch_evaluate_he(a, st) : launch_evaluate(a, st);
 }
 
+// systems too large for one SM's shared memory: the evaluation kernel keeps the configuration in flight in a per-block slab
+static int eval_slab(tdvmc_gpu_handle* h, EvalArgs& a)
+{
+    a.scratch = nullptr;
+    if (h->kind != TDVMC_SYSTEM_SPLINE_TABLE) return 0;
+    const size_t n = evaluate_scratch_doubles(a.s, h->sm_count);
+    if (n == 0) return 0;
+    CK(h->d_eval_slab.ensure(n));
+    a.scratch = h->d_eval_slab.p;
+    return 0;
+}
+
 static int do_evaluate_walkers(tdvmc_gpu_handle* h, const double* pos, int n_cfg, long long row0)
 {
     EvalArgs a;
@@ -1104,6 +1130,7 @@ static int do_evaluate_walkers(tdvmc_gpu_handle* h, const double* pos, int n_cfg
     a.row_stride = 1;
     a.other = h->d_other.p;
     a.exponent = h->d_exponent.p;
+    if (int rc = eval_slab(h, a)) return rc;
     Timed t(h, TDVMC_KERNEL_EVALUATE);
     CK(launch_evaluate_any(h->kind, a, h->stream));
     return 0;
@@ -1459,6 +1486,7 @@ int tdvmc_gpu_evaluate_fixed(tdvmc_gpu_handle* h, const double* R, int32_t n_cfg
     a.drift_i = di.p;
     a.ss_out = ss.p;
     a.outer_out = out.p;
+    if (int rc = eval_slab(h, a)) return rc;
     {
         Timed t(h, TDVMC_KERNEL_EVALUATE);
         CK(launch_evaluate_any(h->kind, a, h->stream));

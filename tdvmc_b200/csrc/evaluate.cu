@@ -108,7 +108,7 @@ struct EvalSmem2
     unsigned short* lut;
 };
 
-__host__ __device__ inline size_t eval_smem_layout2(const SysDev& s, int nwarps, bool rot, EvalSmem2* out, unsigned char* base)
+__host__ __device__ inline size_t eval_smem_layout2(const SysDev& s, int nwarps, bool rot, bool gmem, EvalSmem2* out, unsigned char* base)
 {
     SmemCarver c = { base, 0 };
     const int Npad = ((s.N + 31) >> 5) << 5;
@@ -118,11 +118,13 @@ __host__ __device__ inline size_t eval_smem_layout2(const SysDev& s, int nwarps,
     m.knots = c.take(s.K + 4);
     m.utR = c.take(s.K);
     m.utI = c.take(s.K);
-    m.px = c.take(Npad);
-    m.py = c.take(Npad);
-    m.pz = c.take(Npad);
+    // gmem: positions and forces of the configuration live in a per-block slab of global memory (L2) instead - systems too
+    // large for one SM's shared memory (N = 8000 of config/BosonsBulk3D.config as shipped: 576 KB)
+    m.px = gmem ? nullptr : c.take(Npad);
+    m.py = gmem ? nullptr : c.take(Npad);
+    m.pz = gmem ? nullptr : c.take(Npad);
     m.hist = c.take((size_t)nwarps * s.K);
-    m.frc = c.take((size_t)6 * Npad);
+    m.frc = gmem ? nullptr : c.take((size_t)6 * Npad);
     m.sstot = c.take(s.K);
     m.red = c.take((size_t)nwarps * 8);
     m.lut = reinterpret_cast<unsigned short*>(base + c.off);
@@ -131,7 +133,7 @@ __host__ __device__ inline size_t eval_smem_layout2(const SysDev& s, int nwarps,
     return c.off;
 }
 
-template <bool REFLECT, bool WIDE, bool ROT>
+template <bool REFLECT, bool WIDE, bool ROT, bool GMEM = false>
 __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kernel(EvalArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -140,11 +142,19 @@ __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kerne
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int nwarps = blockDim.x >> 5;
-    const int cfg = blockIdx.x;
     const int N = s.N, K = s.K, P = s.P;
+    const int NT = (N + 31) >> 5; // tiles of 32 particles
 
     EvalSmem2 m;
-    eval_smem_layout2(s, nwarps, ROT, &m, smem_raw);
+    eval_smem_layout2(s, nwarps, ROT, GMEM, &m, smem_raw);
+    if (GMEM)
+    {
+        double* slab = a.scratch + (size_t)blockIdx.x * 9 * NT * 32; // [px | py | pz | 6 force rows], padded to whole tiles
+        m.px = slab;
+        m.py = slab + NT * 32;
+        m.pz = slab + 2 * NT * 32;
+        m.frc = slab + 3 * NT * 32;
+    }
 
     const int ntab = s.nbins * 16;
     double* wtab1 = m.wtab + ntab + 2;
@@ -168,8 +178,11 @@ __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kerne
         m.utI[i] = s.utI[i];
     }
     for (int i = tid; i < s.ncell; i += blockDim.x) m.lut[i] = s.lut[i];
+    // GMEM: one block per SM walks the configurations (its slab is reused); otherwise one block per configuration
+    int cfg = blockIdx.x;
+    do
+    {
     const double* gpos = a.pos + (size_t)cfg * 3 * s.Np;
-    const int NT = (N + 31) >> 5; // tiles of 32 particles
     for (int i = tid; i < NT * 32; i += blockDim.x)
     {
         const bool v = i < N;
@@ -436,6 +449,10 @@ __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kerne
         if (a.exponent) a.exponent[row] = exponent;
         if (a.outer_out) a.outer_out[cfg] = outer_sum;
     }
+    if (!GMEM) break;  // (compile-time: the one-block-per-configuration kernels have no loop)
+    __syncthreads();   // the slab and the histograms are reused by the next configuration
+    cfg += gridDim.x;
+    } while (cfg < a.n_cfg);
 }
 
 // Rotated piece order (two table copies, conflict-free LDS.128) where nearly every lane of a step is inside the cut - the
@@ -444,17 +461,26 @@ __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kerne
 // 3.64 ms per 2960 configurations at N = 343).
 static bool evaluate_rotated(const SysDev& s) { return s.pair_rule == 1; }
 
+constexpr size_t kEvalSmemLimit = (size_t)227 * 1024; // opt-in shared memory per block on sm_100a
+
+// positions + forces in global memory: when even one 24-warp block per SM does not fit shared memory
+static bool evaluate_gmem(const SysDev& s)
+{
+    return eval_smem_layout2(s, 24, evaluate_rotated(s), false, nullptr, nullptr) + 1024 > kEvalSmemLimit;
+}
+
 static size_t eval_layout_bytes(const SysDev& s, int nwarps)
 {
-    return eval_smem_layout2(s, nwarps, evaluate_rotated(s), nullptr, nullptr);
+    return eval_smem_layout2(s, nwarps, evaluate_rotated(s), evaluate_gmem(s), nullptr, nullptr);
 }
 
 // two blocks of <= 12 warps per SM when they fit, else one block of <= 24 warps
 static bool evaluate_wide(const SysDev& s)
 {
+    if (evaluate_gmem(s)) return true;
     int nt = (s.N + 31) / 32;
     if (nt <= 12) return false;
-    return 2 * (eval_layout_bytes(s, 12) + 1024) > (size_t)227 * 1024;
+    return 2 * (eval_layout_bytes(s, 12) + 1024) > kEvalSmemLimit;
 }
 
 int evaluate_blocks_per_sm(const SysDev& s) { return evaluate_wide(s) ? 1 : 2; }
@@ -471,13 +497,19 @@ size_t evaluate_smem_bytes(const SysDev& s)
     return eval_layout_bytes(s, evaluate_threads(s) / 32);
 }
 
+size_t evaluate_scratch_doubles(const SysDev& s, int sm_count)
+{
+    if (!evaluate_gmem(s)) return 0;
+    return (size_t)sm_count * 9 * (size_t)(((s.N + 31) / 32) * 32);
+}
+
 template <typename KernelT>
-static cudaError_t launch_eval_kernel(KernelT kernel, const EvalArgs& a, int threads, size_t smem, cudaStream_t st)
+static cudaError_t launch_eval_kernel(KernelT kernel, const EvalArgs& a, int threads, size_t smem, int grid, cudaStream_t st)
 {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    kernel<<<a.n_cfg, threads, smem, st>>>(a);
+    kernel<<<grid, threads, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -487,11 +519,21 @@ cudaError_t launch_evaluate(const EvalArgs& a, cudaStream_t st)
     const int threads = evaluate_threads(a.s);
     const size_t smem = evaluate_smem_bytes(a.s);
     const bool refl = a.s.pair_rule == 1;
+    if (evaluate_gmem(a.s))
+    {
+        if (!a.scratch) return cudaErrorInvalidValue;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int grid = a.n_cfg < sms ? a.n_cfg : sms; // one block per SM walks the configurations
+        return refl ? launch_eval_kernel(evaluate_kernel<true, true, true, true>, a, threads, smem, grid, st)
+                    : launch_eval_kernel(evaluate_kernel<false, true, false, true>, a, threads, smem, grid, st);
+    }
     if (evaluate_wide(a.s))
-        return refl ? launch_eval_kernel(evaluate_kernel<true, true, true>, a, threads, smem, st)
-                    : launch_eval_kernel(evaluate_kernel<false, true, false>, a, threads, smem, st);
-    return refl ? launch_eval_kernel(evaluate_kernel<true, false, true>, a, threads, smem, st)
-                : launch_eval_kernel(evaluate_kernel<false, false, false>, a, threads, smem, st);
+        return refl ? launch_eval_kernel(evaluate_kernel<true, true, true>, a, threads, smem, a.n_cfg, st)
+                    : launch_eval_kernel(evaluate_kernel<false, true, false>, a, threads, smem, a.n_cfg, st);
+    return refl ? launch_eval_kernel(evaluate_kernel<true, false, true>, a, threads, smem, a.n_cfg, st)
+                : launch_eval_kernel(evaluate_kernel<false, false, false>, a, threads, smem, a.n_cfg, st);
 }
 
 } // namespace tdvmc

@@ -32,7 +32,8 @@ struct SweepArgs
 cudaError_t launch_sweep(SweepArgs a, cudaStream_t st);
 // several warps per walker for small ensembles / large systems (sweep_split_kernel); warps from sweep_split_warps (> 1)
 int sweep_split_warps(const SysDev& s, int W, int sm_count, int resident_per_sm);
-cudaError_t launch_sweep_split(SweepArgs a, int warps, int sm_count, int smem_optin, cudaStream_t st);
+cudaError_t launch_sweep_split(SweepArgs a, int warps, int sm_count, int smem_optin, cudaStream_t st, int copies = 8);
+bool sweep_large_fits(const SysDev& s, int npp, int smem_optin); // one walker per block, 8 warps, 4 table replicas
 // ensembles that are not a whole number of waves: walkers time-share the resident warps (sweep_queue_kernel)
 bool sweep_queue_wanted(const SysDev& s, int W, int sm_count, int resident_per_sm, long long n_steps);
 cudaError_t launch_sweep_queue(SweepArgs a, int sm_count, int smem_optin, cudaStream_t st);
@@ -56,10 +57,12 @@ struct EvalArgs
     double* drift_i;
     double* ss_out;         // [n_cfg][K] or null
     double* outer_out;      // [n_cfg] or null
+    double* scratch;        // large systems only: [blocks][9][NT*32] positions + forces of the configuration in flight
 };
 cudaError_t launch_evaluate(const EvalArgs& a, cudaStream_t st);
 int evaluate_blocks_per_sm(const SysDev& s);   // 2 (12-warp blocks) or 1 (24-warp blocks, large N)
 size_t evaluate_smem_bytes(const SysDev& s);   // dynamic shared memory of one evaluation block
+size_t evaluate_scratch_doubles(const SysDev& s, int sm_count); // 0 unless the system needs the global-memory variant
 cudaError_t launch_evaluate_he(const EvalArgs& a, cudaStream_t st);  // HeBulk, HeDrop (evaluate_he.cu)
 
 // single-particle move ratios for scripted moves of one configuration (quotient_fixed)

@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(GROUP == 32 ? kSweepMaxThreadsWarp : kSweepMax
 // accept decision from the same fixed-order sum.  A second barrier orders the position write of the leading warp before
 // the next proposal reads it.  Same proposal stream, same accept rule as sweep_kernel: the chains coincide up to the
 // summation order of the exponent change.
-template <bool UNIFORM, bool REFLECT, int WARPS>
+template <bool UNIFORM, bool REFLECT, int WARPS, int COPIES = kCubCopies>
 __global__ void __launch_bounds__(kSweepMaxThreadsWarp, 1) sweep_split_kernel(SweepArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -267,8 +267,8 @@ __global__ void __launch_bounds__(kSweepMaxThreadsWarp, 1) sweep_split_kernel(Sw
     const int nrec = s.nbins + 1;
 
     double2* c01s = reinterpret_cast<double2*>(smem_raw);
-    double2* c23s = c01s + (size_t)nrec * kCubCopies;
-    double2* tts = c23s + (size_t)nrec * kCubCopies;
+    double2* c23s = c01s + (size_t)nrec * COPIES;
+    double2* tts = c23s + (size_t)nrec * COPIES;
     unsigned short* lut = reinterpret_cast<unsigned short*>(tts + (UNIFORM ? 0 : nrec));
     double* pos_base = reinterpret_cast<double*>(smem_raw + a.pos_offset);
     double* red_base = pos_base + (size_t)a.wpb * 3 * Npp; // [slots][WARPS] partial exponent changes
@@ -276,10 +276,10 @@ __global__ void __launch_bounds__(kSweepMaxThreadsWarp, 1) sweep_split_kernel(Sw
         const double2* g01 = reinterpret_cast<const double2*>(s.cub);
         const double2* g23 = g01 + nrec;
         const double2* gtt = g23 + nrec;
-        for (int i = threadIdx.x; i < nrec * kCubCopies; i += blockDim.x)
+        for (int i = threadIdx.x; i < nrec * COPIES; i += blockDim.x)
         {
-            c01s[i] = g01[i / kCubCopies];
-            c23s[i] = g23[i / kCubCopies];
+            c01s[i] = g01[i / COPIES];
+            c23s[i] = g23[i / COPIES];
         }
         if (!UNIFORM)
         {
@@ -287,8 +287,8 @@ __global__ void __launch_bounds__(kSweepMaxThreadsWarp, 1) sweep_split_kernel(Sw
             for (int i = threadIdx.x; i < s.ncell; i += blockDim.x) lut[i] = s.lut[i];
         }
     }
-    const double2* c01p = c01s + (lane & (kCubCopies - 1));
-    const double2* c23p = c23s + (lane & (kCubCopies - 1));
+    const double2* c01p = c01s + (lane & (COPIES - 1));
+    const double2* c23p = c23s + (lane & (COPIES - 1));
     const double2* ttp = tts;
 
     const int w = blockIdx.x * a.wpb + slot; // local walker (a.wpb = walkers per block here)
@@ -342,8 +342,8 @@ __global__ void __launch_bounds__(kSweepMaxThreadsWarp, 1) sweep_split_kernel(Sw
                 const double xi = px[i], yi = py[i], zi = pz[i];
                 const double r_old = sqrt_fast(dist2<false>(xi - ox, yi - oy, zi - oz, Lhalf));
                 const double r_new = sqrt_fast(dist2<false>(xi - nx, yi - ny, zi - nz, Lhalf));
-                const double u_old = pair_u<UNIFORM, REFLECT, kCubCopies>(s, c01p, c23p, ttp, lut, r_old);
-                const double u_new = pair_u<UNIFORM, REFLECT, kCubCopies>(s, c01p, c23p, ttp, lut, r_new);
+                const double u_old = pair_u<UNIFORM, REFLECT, COPIES>(s, c01p, c23p, ttp, lut, r_old);
+                const double u_new = pair_u<UNIFORM, REFLECT, COPIES>(s, c01p, c23p, ttp, lut, r_new);
                 const double d = u_new - u_old;
                 if (i != p) delta += d;
             }
@@ -398,40 +398,49 @@ int sweep_split_warps(const SysDev& s, int W, int sm_count, int resident_per_sm)
     return warps;
 }
 
-static size_t sweep_split_smem_bytes(const SysDev& s, int spb, int warps, int npp, size_t* pos_offset)
+static size_t sweep_split_smem_bytes(const SysDev& s, int spb, int warps, int npp, int copies, size_t* pos_offset)
 {
     const size_t nrec = (size_t)s.nbins + 1;
-    size_t off = nrec * kCubCopies * 2 * sizeof(double2);
+    size_t off = nrec * copies * 2 * sizeof(double2);
     if (!s.uniform) off += nrec * sizeof(double2) + (size_t)s.ncell * sizeof(unsigned short);
     off = (off + 15) & ~(size_t)15;
     *pos_offset = off;
     return off + (size_t)spb * 3 * npp * sizeof(double) + (size_t)spb * warps * sizeof(double);
 }
 
-template <int WARPS>
+bool sweep_large_fits(const SysDev& s, int npp, int smem_optin)
+{
+    size_t off;
+    return sweep_split_smem_bytes(s, 1, 8, npp, 4, &off) <= (size_t)smem_optin;
+}
+
+template <int WARPS, int COPIES>
 static const void* sweep_split_fn(const SysDev& s)
 {
     const bool refl = s.pair_rule == 1;
-    return s.uniform ? (refl ? (const void*)sweep_split_kernel<true, true, WARPS> : (const void*)sweep_split_kernel<true, false, WARPS>)
-                     : (refl ? (const void*)sweep_split_kernel<false, true, WARPS> : (const void*)sweep_split_kernel<false, false, WARPS>);
+    return s.uniform ? (refl ? (const void*)sweep_split_kernel<true, true, WARPS, COPIES> : (const void*)sweep_split_kernel<true, false, WARPS, COPIES>)
+                     : (refl ? (const void*)sweep_split_kernel<false, true, WARPS, COPIES> : (const void*)sweep_split_kernel<false, false, WARPS, COPIES>);
 }
 
-// a.wpb is ignored; walkers per block follow from the ensemble size, the thread budget, the named barriers and shared memory
-cudaError_t launch_sweep_split(SweepArgs a, int warps, int sm_count, int smem_optin, cudaStream_t st)
+// a.wpb is ignored; walkers per block follow from the ensemble size, the thread budget, the named barriers and shared memory.
+// copies = 4: the large-system variant (eight warps per walker only)
+cudaError_t launch_sweep_split(SweepArgs a, int warps, int sm_count, int smem_optin, cudaStream_t st, int copies)
 {
+    if (copies == 4) warps = 8;
     const int wps = (a.W + sm_count - 1) / sm_count;
     int spb = wps < 1 ? 1 : wps;
     spb = std::min(spb, std::min(kSweepMaxThreadsWarp / (32 * warps), 15));
     size_t pos_off = 0, smem = 0;
     for (; spb >= 1; spb--)
     {
-        smem = sweep_split_smem_bytes(a.s, spb, warps, a.npp, &pos_off);
+        smem = sweep_split_smem_bytes(a.s, spb, warps, a.npp, copies, &pos_off);
         if (smem <= (size_t)smem_optin) break;
     }
     if (spb < 1) return cudaErrorInvalidConfiguration;
     a.wpb = spb;
     a.pos_offset = (int)pos_off;
-    const void* fn = warps == 2 ? sweep_split_fn<2>(a.s) : (warps == 4 ? sweep_split_fn<4>(a.s) : sweep_split_fn<8>(a.s));
+    const void* fn = copies == 4 ? sweep_split_fn<8, 4>(a.s)
+                     : warps == 2 ? sweep_split_fn<2, kCubCopies>(a.s) : (warps == 4 ? sweep_split_fn<4, kCubCopies>(a.s) : sweep_split_fn<8, kCubCopies>(a.s));
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);

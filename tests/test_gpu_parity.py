@@ -1619,15 +1619,6 @@ def test_low_dimensional_chain_and_estimators_match_oracle(capi, golden, name):
     h.close()
 
 
-def test_oversized_system_is_refused_at_create(capi, golden):
-    """config/BosonsBulk3D.config as shipped (N = 8000): one configuration does not fit one SM's shared memory in the
-    evaluation kernel - tdvmc_gpu_create says so instead of failing at the first sample."""
-    g = golden("bosonsbulk_n343_equil")
-    spec = systems.bosons_bulk(8000, 20.0, 201, [1.0, 1.0], weights=g["spline_weights"] if False else None)
-    with pytest.raises(capi.TdvmcError, match="shared memory per configuration"):
-        capi.Handle(spec, 4)
-
-
 def _sweep_with_env(capi, spec, g, W, n_steps, env):
     """Positions and acceptance counts after n_steps (two launches) of W walkers under the given tuning knobs."""
     old = {k: os.environ.get(k) for k in env}
@@ -1677,3 +1668,44 @@ def test_split_sweep_equals_one_warp_per_walker(capi, golden, name, W):
     R1, a_1 = _sweep_with_env(capi, spec, g, W, 400, {"TDVMC_SWEEP_SPLIT": "1"})
     assert a_s == a_1
     assert np.max(np.abs(Rs - R1)) < 1e-12
+
+
+@pytest.mark.parametrize("N,L", [(2744, 14.0), (8000, 20.0)])
+def test_large_systems_beyond_one_sm_of_shared_memory(capi, N, L):
+    """N = 2744: the configuration (positions + forces, 198 KB) no longer fits an SM next to the tables, the evaluation kernel
+    keeps it in a per-block slab of global memory.  N = 8000, LBOX = 20, N_PARAM = 201 - config/BosonsBulk3D.config exactly as
+    shipped: also one walker's positions (192 KB) nearly fill an SM, the sweep runs eight warps per walker with four table
+    replicas.  Both against the pinned oracle: E_L, drift, O_k at 1e-10, chain replay move for move."""
+    P = 201
+    spec = systems.bosons_bulk(N, L, P, [1.0, 1.0])
+    uR, uI = systems.smooth_params(P, L / 2)
+    rng = np.random.default_rng(N)
+    R = np.stack([systems.jittered_lattice(N, L, rng) + rng.uniform(-0.05, 0.05, (N, 3)) for _ in range(2)])
+    h = capi.Handle(spec, 2, seed=3, mc_step=0.5)
+    h.set_params(uR, uI, 0.0, 0.0, 0.0)
+    ev = h.evaluate_fixed(R)
+    o = Oracle(spec)
+    for c in range(2):
+        ref = o.evaluate(R[c], uR, uI, 0.0)
+        assert rel(ev["O"][c], ref["O"]) < RTOL
+        assert abs(ev["e_r"][c] - ref["e_r"]) < RTOL * abs(ref["e_r"]) and abs(ev["e_i"][c] - ref["e_i"]) < RTOL * abs(ref["e_i"])
+        assert abs(ev["exponent"][c] - ref["exponent"]) < RTOL * abs(ref["exponent"])
+        assert np.max(np.abs(ev["drift_r"][c] - ref["drift_r"])) < RTOL * np.max(np.abs(ref["drift_r"]))
+        assert np.max(np.abs(ev["drift_i"][c] - ref["drift_i"])) < RTOL * np.max(np.abs(ref["drift_i"]))
+    h.set_positions(R)
+    h.sweep(60)
+    Rg = h.get_positions()
+    for c in range(2):
+        Rr, _ = o.sweep(R[c], uR, 3, c, 0, 60, 0.5)
+        d = Rg[c] - Rr
+        d -= L * np.round(d / L)
+        assert np.max(np.abs(d)) < 1e-9
+    # a whole estimator pass runs (two samples per walker)
+    h2 = capi.Handle(spec, 2, seed=3, mc_step=0.5, max_samples=2)
+    h2.set_params(uR, uI, 0.0, 0.0, 0.0)
+    h2.set_positions(R)
+    h2.sample_and_accumulate(2, 32, 0)
+    got = h2.allreduce_and_fetch()
+    assert got["n_samples"] == 4 and np.isfinite(got["e_r"][0]) and got["n_trials"] == 2 * 64
+    h.close()
+    h2.close()

@@ -282,8 +282,8 @@ def test_recorded_bench_line_has_the_contract_keys():
     for rec in ("full_wave", "strong"):
         assert d[rec]["value"] > 0 and d[rec]["walkers"] > 0
     assert d["strong"]["total_walkers"] == 23680
-    assert [c["config"] for c in d["secondary"]] == ["config/drop_6.config", "config/bulk_64.config", "config/NUBosonsBulkPB3D.config",
-                                                      "config/He4He4Na.config"]
+    assert [c["config"] for c in d["secondary"]][:4] == ["config/drop_6.config", "config/bulk_64.config", "config/NUBosonsBulkPB3D.config",
+                                                          "config/He4He4Na.config"]
     assert all(c["reference_full_host"]["cores"] >= 1 and c["walker_steps_ratio_vs_full_host"] > 1 for c in d["secondary"])
     ts = d["time_step"]
     assert ts["driver_binary"]["host_solve_qr"]["time_steps_per_s"] > 0 and ts["driver_binary"]["device_solve_cholesky"]["time_steps_per_s"] > 0
