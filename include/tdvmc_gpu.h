@@ -156,9 +156,10 @@ int tdvmc_gpu_device_count(void);
 
 /* Supported envelope (tdvmc_gpu_create refuses anything outside it with a message, nothing is truncated):
  *   all systems          N_PARAM + 3 <= 208 (register-resident S matrix of the accumulation kernel), DIM as stated below
- *   SPLINE_TABLE         one configuration must fit one SM's shared memory in the evaluation kernel: about N <= 2000 at
- *                        N_PARAM ~ 200 (N = 1728 of config/NUBosonsBulkPB3D.config fits; N = 8000 of config/BosonsBulk3D.config
- *                        as shipped does not); DIM 1, 2 or 3
+ *   SPLINE_TABLE         any N up to ~8300 (one walker's positions, 24 N bytes, must fit an SM's shared memory next to four
+ *                        replicas of the sweep table: config/BosonsBulk3D.config as shipped, N = 8000, runs); up to N ~ 2000 a
+ *                        configuration is evaluated out of shared memory, beyond that out of a per-block slab in global memory;
+ *                        DIM 1, 2 or 3 (the large-system sweep: DIM = 3)
  *   HE_BULK / HE_DROP    DIM = 3
  *   MIXTURE              N <= 8 particles, n_ext <= 96, spline order 3 or 4, DIM = 3
  *   BOX_RADIAL           DIM 2 or 3, one walker's tables must fit shared memory

@@ -266,3 +266,19 @@ def test_driver_mixture_config5(binaries, golden, parity_log, tmp_path):
     dev = run_seeds(gpu_bin, dict(evo, GPU_WALKERS=2000, MC_NSTEPS=10), "gpu_evo", g["R"], list(range(1, 9)), tmp_path, gpu_seed=True)
     assert len(dev[0].local_energy_r) == 4
     compare_trajectories(ref, dev, P, parity_log, "mixture_he4he4na_config5")
+
+
+def test_driver_config3_as_shipped_n8000(binaries, tmp_path):
+    """config/BosonsBulk3D.config with the values it ships with - N = 8000, LBOX = 20, N_PARAM = 201, all parameters zero,
+    MC_NSTEPS = 2 x MC_NTHERMSTEPS = 5000 + 1000, TIMESTEP = 2e-4, Eigen QR solve - through the device-bound driver (round 1
+    could not hold one such configuration on an SM).  With u = 0 the walk is free (every move accepted) and E_L is the
+    square-well energy b x #(pairs closer than a), about N rho (4 pi / 3) a^3 / 2 = 16 755 for uniformly distributed particles."""
+    gpu_bin, _ = binaries
+    z = [0.0] * 201
+    cfg = driver.headline_config(z, z, N=8000, LBOX=20.0, TIMESTEP=2e-4, TOTALTIME=2e-4 * 1.5, MC_VERY_FIRST_NINITIALIZATIONSTEPS=100000,
+                                 LINEAR_EQUATION_SOLVER_TYPE=1, USE_PRECONDITIONING=0, GPU_WALKERS=148)
+    r = driver.run_driver(gpu_bin, cfg, str(tmp_path / "n8000"), timeout=900)
+    e = r.local_energy_r
+    assert len(e) == 2 and np.all(np.isfinite(e)) and np.all(np.isfinite(r.parameters_r))
+    assert abs(e[0] - 16755.0) < 0.05 * 16755.0
+    assert np.all(r.acceptance[:1] > 99.9)
