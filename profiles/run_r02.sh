@@ -14,7 +14,7 @@ ncu --set full --clock-control none --import-source on -k regex:sweep_queue_kern
     python bench.py --steps 1 --warmup 3 --no-exhibits > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:evaluate_kernel -s 2 -c 1 -f -o gpurun_out/evaluate_r02 \
     python bench.py --steps 1 --warmup 3 --no-exhibits > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:evaluate_kernel -s 15 -c 1 -f -o gpurun_out/evaluate_n1728_r02 \
+ncu --set full --clock-control none --import-source on -k regex:evaluate_kernel -s 17 -c 1 -f -o gpurun_out/evaluate_n1728_r02 \
     python profiles/ab_evaluate.py > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"tables_kernel|contract_kernel" -c 2 -f -o gpurun_out/tables_r02 \
     python profiles/ab_tables.py > /dev/null 2>&1
