@@ -503,6 +503,10 @@ def main():
     h.profile(True, True)
     ms_ts = timed_time_steps(time_step_device)
     n_solve, ms_solve = h.kernel_stats()["solve"]
+    h.profile(True, True)
+    for _ in range(3):
+        h.solve_parameters_dot(imaginary_time=0, use_preconditioning=False, solver_type=1)   # solve_qr_kernel on the same estimators
+    n_qr, ms_qr = h.kernel_stats()["solve"]
     h.profile(False, False)
 
     # ---- the same pass at other ensemble sizes (one JSON line carries them all) ----
@@ -556,6 +560,7 @@ def main():
             driver_steps = {}
             K = max(args.steps, 20)
             for name, over in (("host_solve_qr", dict(LINEAR_EQUATION_SOLVER_TYPE=1, USE_PRECONDITIONING=0)),
+                               ("device_solve_qr", dict(LINEAR_EQUATION_SOLVER_TYPE=1, USE_PRECONDITIONING=0, GPU_DEVICE_SOLVE=1)),
                                ("device_solve_cholesky", dict(LINEAR_EQUATION_SOLVER_TYPE=0, USE_PRECONDITIONING=1, GPU_DEVICE_SOLVE=1))):
                 try:
                     with tempfile.TemporaryDirectory() as td:
@@ -732,7 +737,7 @@ def main():
                               "driver_binary": driver_steps, "reference_host": ref_ts,
                               "includes": "set_params, estimator pass, all-reduce, Cholesky solve of S u' = F on the device "
                                           "(P = 201, solve_kernel), Euler update, parameter feedback; every rank solves redundantly",
-                              "solve_kernel_ms": ms_solve / max(n_solve, 1),
+                              "solve_kernel_ms": ms_solve / max(n_solve, 1), "solve_qr_kernel_ms": ms_qr / max(n_qr, 1),
                               "with_host_lapack_solve": {"ms": ms_ts_host / args.steps,
                                                          "time_steps_per_s": args.steps / (ms_ts_host * 1e-3)}},
                 "e2e": {"value": e2e_value, "unit": "walker-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

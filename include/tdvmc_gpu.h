@@ -164,7 +164,8 @@ int tdvmc_gpu_device_count(void);
  *   MIXTURE              N <= 8 particles, n_ext <= 96, spline order 3 or 4, DIM = 3
  *   BOX_RADIAL           DIM 2 or 3, one walker's tables must fit shared memory
  *   INH_CONTACT          DIM = 1, N <= 32
- *   device solver        N_PARAM <= 1024, Cholesky branch only (LINEAR_EQUATION_SOLVER_TYPE = 0, IMAGINARY_TIME 0 or 1)
+ *   device solver        N_PARAM <= 1024; LINEAR_EQUATION_SOLVER_TYPE 0 and 1; IMAGINARY_TIME -1, 0, 1; all parameters in use
+ *                        (USE_PARAM_START = USE_PARAM_END = 0)
  *   observables          g(r) / S(k) for DIM = 3 */
 
 int tdvmc_gpu_create(const tdvmc_system_desc* system, const tdvmc_ensemble_desc* ensemble, tdvmc_gpu_handle** out);
@@ -208,11 +209,11 @@ int tdvmc_gpu_allreduce_and_fetch(tdvmc_gpu_handle* h, tdvmc_estimators* out);
 int tdvmc_gpu_last_exponent(tdvmc_gpu_handle* h, double* exponent);
 
 /* ---- parameter derivatives and the Euler step on the device ---- */
-/* Options of SolveForParametersDot (src/TDVMC.cpp:1713-1828).  The device offers the Cholesky branch
- * (LINEAR_EQUATION_SOLVER_TYPE = 0, :1733-1763) for all three values of IMAGINARY_TIME.  The Eigen FullPivHouseholderQR
- * branch (LINEAR_EQUATION_SOLVER_TYPE = 1, :1763-1827) is NOT offered on the device: a desc with solver_type = 1 is refused
- * with a message - a driver configured for it fetches the estimators (tdvmc_gpu_allreduce_and_fetch) and keeps its own
- * host solve, which is what tdvmc_b200/host/driver does (tests/test_gpu_driver.py::test_driver_real_time_qr_branch_n64). */
+/* Options of SolveForParametersDot (src/TDVMC.cpp:1713-1828), both branches, all three values of IMAGINARY_TIME:
+ * solver_type 0 = the hand-written Cholesky (:1733-1763; bit-identical to the host code), solver_type 1 = Eigen's
+ * FullPivHouseholderQR followed by the mean subtraction of :1800-1809 (:1763-1827; Eigen's algorithm step by step, results
+ * equal to rounding x condition number).  With use_preconditioning the reference regularises the scaled matrix by 0.001
+ * (type 0) or 0.002 (type 1, :1770) - pass that value in `regularization`; type 1 without preconditioning is not regularised. */
 typedef struct tdvmc_solver_desc
 {
     uint32_t struct_size;
@@ -221,7 +222,7 @@ typedef struct tdvmc_solver_desc
     int32_t force_global_scratch;/* tests: factorise in global memory even when P fits shared memory */
     double regularization;       /* RegularizeEquationSystem; the reference hard-codes 0.001 (src/TDVMC.cpp:1737) */
     double min_scaling;          /* 0 = reference behaviour; > 0 floors the scalings (a parameter whose operator never varied) */
-    int32_t solver_type;         /* LINEAR_EQUATION_SOLVER_TYPE: 0 Cholesky; anything else is refused (see above) */
+    int32_t solver_type;         /* LINEAR_EQUATION_SOLVER_TYPE: 0 Cholesky, 1 full-pivoting Householder QR */
     int32_t reserved;            /* 0 */
 } tdvmc_solver_desc;
 /* What the root rank of the reference holds after SolveForParametersDot (+ the energies the driver logs each step). */

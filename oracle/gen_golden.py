@@ -432,11 +432,19 @@ def gen_evolution(only=None):
     seeds = list(range(1, 25))
     for name, imag, dt, nsteps in (("bosonsbulk_n64_evolution", 1, 2e-4, 30), ("bosonsbulk_n64_evolution_realtime", 0, 1e-4, 12),
                                    # IMAGINARY_TIME = -1: the 1.499 pi time rotation (src/TDVMC.cpp:1475-1504, 1666-1673)
-                                   ("bosonsbulk_n64_evolution_rotation", -1, 1e-4, 6)):
+                                   ("bosonsbulk_n64_evolution_rotation", -1, 1e-4, 6),
+                                   # LINEAR_EQUATION_SOLVER_TYPE = 1: Eigen FullPivHouseholderQR (:1763-1827), with the scaling +
+                                   # 0.002 regularisation of USE_PRECONDITIONING = 1 and without
+                                   ("bosonsbulk_n64_evolution_qr", 1, 2e-4, 6), ("bosonsbulk_n64_evolution_qr_raw", 0, 1e-4, 4)):
         if only and name not in only:
             continue
+        extra = {}
+        if name.endswith("_qr"):
+            extra = dict(LINEAR_EQUATION_SOLVER_TYPE=1, USE_PRECONDITIONING=1)
+        elif name.endswith("_qr_raw"):
+            extra = dict(LINEAR_EQUATION_SOLVER_TYPE=1, USE_PRECONDITIONING=0)
         base = dict(N=64, LBOX=4.0, N_PARAM=P, time=0.0, phiR=0.0, phiI=0.0, MC_STEP=0.4, MC_NSTEPS=1024, MC_NTHERMSTEPS=32,
-                    MC_NINITIALIZATIONSTEPS=64, IMAGINARY_TIME=imag, TIMESTEP=dt, time_steps=nsteps, equilibration_steps=6400)
+                    MC_NINITIALIZATIONSTEPS=64, IMAGINARY_TIME=imag, TIMESTEP=dt, time_steps=nsteps, equilibration_steps=6400, **extra)
         arr = dict(R=g["R"], uR=g["uR"], uI=np.zeros(P), SYSTEM_PARAMS=[1.0, 1.0])
 
         def one(sd):

@@ -636,8 +636,8 @@ int ModeEvolve(const Case& c, const std::string& out)
 {
     SetupReference(c);
     IMAGINARY_TIME = c.i("IMAGINARY_TIME", 1);
-    LINEAR_EQUATION_SOLVER_TYPE = 0;
-    USE_PRECONDITIONING = 1;
+    LINEAR_EQUATION_SOLVER_TYPE = c.i("LINEAR_EQUATION_SOLVER_TYPE", 0); // 1: the Eigen FullPivHouseholderQR branch (:1763-1827)
+    USE_PRECONDITIONING = c.i("USE_PRECONDITIONING", 1);
     USE_PARAM_START = 0;
     USE_PARAM_END = 0;
     USED_PARAM_COUNT = N_PARAM;

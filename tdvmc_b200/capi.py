@@ -257,8 +257,10 @@ class Handle:
 
     # ---- parameter derivatives / Euler step on the device ----
     @staticmethod
-    def _solver_desc(imaginary_time=1, use_preconditioning=True, regularization=0.001, min_scaling=0.0, force_global=False,
+    def _solver_desc(imaginary_time=1, use_preconditioning=True, regularization=None, min_scaling=0.0, force_global=False,
                      solver_type=0):
+        if regularization is None:       # the reference's hard-coded values (src/TDVMC.cpp:1737, :1770)
+            regularization = 0.002 if solver_type == 1 else 0.001
         return SolverDesc(C.sizeof(SolverDesc), int(imaginary_time), int(bool(use_preconditioning)), int(bool(force_global)),
                           float(regularization), float(min_scaling), int(solver_type), 0)
 

@@ -1302,13 +1302,11 @@ static int do_solve(tdvmc_gpu_handle* h, const tdvmc_solver_desc* sd, const doub
 {
     if (sd->struct_size != sizeof(tdvmc_solver_desc)) return fail(h, "solver desc: struct_size mismatch");
     if (sd->imaginary_time < -1 || sd->imaginary_time > 1) return fail(h, "solver: IMAGINARY_TIME must be -1, 0 or 1");
-    if (sd->solver_type != 0)
-        return fail(h, "solver: LINEAR_EQUATION_SOLVER_TYPE = 1 (Eigen FullPivHouseholderQR, src/TDVMC.cpp:1763-1827) is not offered on "
-                       "the device; fetch the estimators and use the driver's own host solve");
+    if (sd->solver_type != 0 && sd->solver_type != 1) return fail(h, "solver: LINEAR_EQUATION_SOLVER_TYPE must be 0 (Cholesky) or 1 (QR)");
     if (h->P > 1024) return fail(h, "solver: N_PARAM > 1024");
     const int P = h->P;
     CK(h->d_sol.ensure(2 * (size_t)P + 5));
-    CK(h->d_solve_L.ensure((size_t)P * (P + 1) / 2));
+    CK(h->d_solve_L.ensure(sd->solver_type == 1 ? (size_t)P * P : (size_t)P * (P + 1) / 2));
     if (!h->h_sol) CK(cudaMallocHost((void**)&h->h_sol, (2 * (size_t)P + 5) * sizeof(double)));
     SolveArgs a;
     memset(&a, 0, sizeof(a));
@@ -1324,7 +1322,8 @@ static int do_solve(tdvmc_gpu_handle* h, const tdvmc_solver_desc* sd, const doub
     a.out = h->d_sol.p;
     {
         Timed t(h, TDVMC_KERNEL_SOLVE);
-        CK(launch_solve(a, h->smem_optin, h->stream));
+        if (sd->solver_type == 1) CK(launch_solve_qr(a, h->stream));
+        else CK(launch_solve(a, h->smem_optin, h->stream));
     }
     CK(cudaMemcpyAsync(h->h_sol, h->d_sol.p, (2 * (size_t)P + 5) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));

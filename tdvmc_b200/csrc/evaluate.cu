@@ -485,11 +485,30 @@ static bool evaluate_wide(const SysDev& s)
 
 int evaluate_blocks_per_sm(const SysDev& s) { return evaluate_wide(s) ? 1 : 2; }
 
+// Warps per block: one tile per warp and round, so ceil(NT / warps) rounds per shift with the last one partly idle (NT = 54
+// tiles at N = 1728 on 24 warps: rounds of 24, 24 and 6 tiles, a quarter of the warp-time waiting at the flush barriers).  Take
+// the warp count in the upper third of the allowed range that wastes least (N = 1728: 18 warps, three full rounds).
 int evaluate_threads(const SysDev& s)
 {
-    int t = ((s.N + 31) / 32) * 32;
-    const int cap = evaluate_wide(s) ? 768 : 384;
-    return t > cap ? cap : t;
+    const int nt = (s.N + 31) / 32;
+    const int cap = evaluate_wide(s) ? 24 : 12;
+    if (nt <= cap) return nt * 32;
+    int best = cap, best_cost = ((nt + cap - 1) / cap) * cap;
+    if (const char* e = getenv("TDVMC_EVAL_WARPS")) // tuning knob
+    {
+        const int w = atoi(e);
+        if (w >= 1 && w <= cap) return w * 32;
+    }
+    for (int w = cap - 1; w >= (2 * cap) / 3; w--)
+    {
+        const int cost = ((nt + w - 1) / w) * w; // warp-rounds per shift
+        if (cost < best_cost)
+        {
+            best_cost = cost;
+            best = w;
+        }
+    }
+    return best * 32;
 }
 
 size_t evaluate_smem_bytes(const SysDev& s)

@@ -161,6 +161,7 @@ struct SolveArgs
     double* out;           // uDotR[P] | uDotI[P] | phiDotR | phiDotI | not-positive-definite flag | <E^R> | <E^I>
 };
 cudaError_t launch_solve(SolveArgs a, int smem_optin, cudaStream_t st);
+cudaError_t launch_solve_qr(SolveArgs a, cudaStream_t st); // LINEAR_EQUATION_SOLVER_TYPE = 1; a.L_global = [P * P] scratch
 
 // ---- small utilities (util.cu) ----
 cudaError_t launch_wrap(const SysDev& s, double* pos, int W, cudaStream_t st);

@@ -250,6 +250,416 @@ __global__ void __launch_bounds__(1024, 1) solve_kernel(SolveArgs a)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// LINEAR_EQUATION_SOLVER_TYPE = 1: Eigen::FullPivHouseholderQR (src/TDVMC.cpp:1763-1827), r02.
+//
+// The reference builds the same system, scales it and adds 0.002 to the diagonal only with USE_PRECONDITIONING = 1
+// (:1767-1771), factorises with Eigen 3.3.7's full-pivoting Householder QR and solves both right-hand sides, subtracts
+// the mean of each solution (:1802-1809), then CalculatePhiDot and the scalings.  This kernel follows Eigen's
+// algorithm step by step (resources/Eigen/src/QR/FullPivHouseholderQR.h computeInPlace / _solve_impl,
+// Householder/Householder.h makeHouseholder / applyHouseholderOnTheLeft): pivot = the first maximum of |a_ij| over the
+// trailing block in column-major order, early exit when it is negligible against the first pivot, row and column
+// transpositions, beta / tau / essential part as there, tmp = essential^T bottom + row 0, row 0 -= tau tmp,
+// bottom -= (tau essential) tmp; rank from |R_ii| > eps P max|R_ii|; Q^T applied to the right-hand sides, back
+// substitution on the leading rank x rank triangle, column permutation undone, zeros beyond the rank.  Dot products and
+// norms are summed in a different order than Eigen's packet reductions, so the results agree to rounding times the
+// condition number, not bit for bit.  One CTA; the matrix lives in global memory (column-major, P^2 doubles: it stays in L2).
+__device__ __forceinline__ double block_sum(double v, double* red, int tid, int T)
+{
+    v = warp_sum(v);
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < (T >> 5); w++) t += red[w];
+    __syncthreads();
+    return t;
+}
+
+__global__ void __launch_bounds__(1024, 1) solve_qr_kernel(SolveArgs a)
+{
+    extern __shared__ __align__(16) double sm[];
+    const int P = a.P, tid = threadIdx.x, T = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
+    double* O = sm;
+    double* cR = sm + P;        // right-hand sides, then Q^T b, then the triangular solution
+    double* cI = sm + 2 * P;
+    double* scal = sm + 3 * P;
+    double* hco = sm + 4 * P;   // Householder coefficients tau_k
+    double* xR = sm + 5 * P;
+    double* xI = sm + 6 * P;
+    double* red = sm + 7 * P;   // 64 doubles of reduction scratch
+    int* rowT = reinterpret_cast<int*>(red + 64);
+    int* colT = rowT + P;
+    int* perm = colT + P;
+    __shared__ double s_best;
+    __shared__ int s_bi, s_bj, s_nonzero;
+    __shared__ double s_maxpivot, s_biggest;
+    double* A = a.L_global;     // [P][P] column-major: A[i + j P]
+
+    const double* S = a.est;
+    const double* FR = S + (size_t)P * P;
+    const double* FI = FR + P;
+    const double* Os = FI + P;
+    const double* E = Os + P;
+    const double n = a.est[a.cnt_offset + 2];
+    const double inv = 1.0 / n;
+    const double ER = E[0] * inv, EI = E[1] * inv;
+
+    for (int i = tid; i < P; i += T) O[i] = Os[i] * inv;
+    __syncthreads();
+    for (int i = tid; i < P; i += T)
+    {
+        const double oer = FR[i] * inv, oei = FI[i] * inv;
+        if (a.imaginary_time == -1)
+        {
+            const double rotation = 1.499 * 3.14159265358979323846;
+            const double c = cos(rotation), sn = sin(rotation);
+            cR[i] = c * (oer - ER * O[i]) - sn * (oei);
+            cI[i] = sn * (oer - ER * O[i]) + c * (oei);
+        }
+        else if (a.imaginary_time == 0)
+        {
+            cR[i] = oei - EI * O[i];
+            cI[i] = -oer + ER * O[i];
+        }
+        else
+        {
+            cR[i] = -oer + ER * O[i];
+            cI[i] = -oei;
+        }
+        scal[i] = 1.0;
+    }
+    // matrix[i][j] = <O_i O_j> - <O_i><O_j> for j <= i, mirrored (:1529-1534)
+    for (int idx = tid; idx < P * P; idx += T)
+    {
+        const int i = idx % P, j = idx / P;
+        const int hi = i > j ? i : j, lo = i > j ? j : i;
+        A[idx] = S[(size_t)hi * P + lo] * inv - O[hi] * O[lo];
+    }
+    __syncthreads();
+    if (a.use_preconditioning) // :1767-1771
+    {
+        for (int i = tid; i < P; i += T)
+        {
+            double sc = sqrt(A[i + (size_t)i * P]);
+            if (a.min_scaling > 0.0 && !(sc >= a.min_scaling)) sc = a.min_scaling;
+            scal[i] = sc;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < P * P; idx += T)
+        {
+            const int i = idx % P, j = idx / P;
+            A[idx] = A[idx] / (scal[i] * scal[j]);
+        }
+        for (int i = tid; i < P; i += T)
+        {
+            cR[i] = cR[i] / scal[i];
+            cI[i] = cI[i] / scal[i];
+        }
+        __syncthreads();
+        for (int i = tid; i < P; i += T) A[i + (size_t)i * P] += a.regularization; // RegularizeEquationSystem(matrix, 0.002)
+        __syncthreads();
+    }
+    if (tid == 0)
+    {
+        s_nonzero = P;
+        s_maxpivot = 0.0;
+        s_biggest = 0.0;
+    }
+    __syncthreads();
+    const double precision = 2.220446049250313e-16 * (double)P; // NumTraits<double>::epsilon() * size
+    double carry_best = -1.0;
+    int carry_idx = 0x7fffffff;
+
+    for (int k = 0; k < P; k++)
+    {
+        // ---- biggest |a_ij| of the trailing block, first in column-major order ----
+        const int m = P - k;
+        double best = carry_best;
+        int bidx = carry_idx; // column-major rank within the block: (j - k) m + (i - k)
+        if (k == 0)           // later steps: found while the previous reflection was applied (one pass over the block less)
+        {
+            for (int idx = tid; idx < m * m; idx += T)
+            {
+                const int i = k + idx % m, j = k + idx / m;
+                const double v = fabs(A[i + (size_t)j * P]);
+                if (v > best || (v == best && idx < bidx))
+                {
+                    best = v;
+                    bidx = idx;
+                }
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            const double ob = __shfl_xor_sync(FULL_MASK, best, o);
+            const int oi = __shfl_xor_sync(FULL_MASK, bidx, o);
+            if (ob > best || (ob == best && oi < bidx))
+            {
+                best = ob;
+                bidx = oi;
+            }
+        }
+        if (lane == 0)
+        {
+            red[warp] = best;
+            reinterpret_cast<int*>(red + 32)[warp] = bidx;
+        }
+        __syncthreads();
+        if (tid == 0)
+        {
+            double b = red[0];
+            int bi = reinterpret_cast<int*>(red + 32)[0];
+            for (int w = 1; w < nwarp; w++)
+            {
+                const double ob = red[w];
+                const int oi = reinterpret_cast<int*>(red + 32)[w];
+                if (ob > b || (ob == b && oi < bi))
+                {
+                    b = ob;
+                    bi = oi;
+                }
+            }
+            s_best = b;
+            s_bi = k + bi % m;
+            s_bj = k + bi / m;
+            if (k == 0) s_biggest = b;
+        }
+        __syncthreads();
+        // isMuchSmallerThan(biggest_in_corner, biggest, precision): |x| <= |y| * prec
+        if (s_best <= s_biggest * precision)
+        {
+            if (tid == 0) s_nonzero = k;
+            for (int i = k + tid; i < P; i += T)
+            {
+                rowT[i] = i;
+                colT[i] = i;
+                hco[i] = 0.0;
+            }
+            __syncthreads();
+            break;
+        }
+        const int pr = s_bi, pc = s_bj;
+        if (tid == 0)
+        {
+            rowT[k] = pr;
+            colT[k] = pc;
+        }
+        if (pr != k) // m_qr.row(k).tail(cols-k).swap(m_qr.row(pr).tail(cols-k))
+            for (int j = k + tid; j < P; j += T)
+            {
+                const double t = A[k + (size_t)j * P];
+                A[k + (size_t)j * P] = A[pr + (size_t)j * P];
+                A[pr + (size_t)j * P] = t;
+            }
+        __syncthreads();
+        if (pc != k) // m_qr.col(k).swap(m_qr.col(pc)): whole columns
+            for (int i = tid; i < P; i += T)
+            {
+                const double t = A[i + (size_t)k * P];
+                A[i + (size_t)k * P] = A[i + (size_t)pc * P];
+                A[i + (size_t)pc * P] = t;
+            }
+        __syncthreads();
+        // ---- makeHouseholderInPlace on A[k:, k] ----
+        double* colk = A + (size_t)k * P;
+        double part = 0.0;
+        for (int i = k + 1 + tid; i < P; i += T) part += colk[i] * colk[i];
+        const double tailSq = block_sum(part, red, tid, T);
+        const double c0 = colk[k];
+        double beta, tau;
+        if (tailSq <= 2.2250738585072014e-308)
+        {
+            tau = 0.0;
+            beta = c0;
+            for (int i = k + 1 + tid; i < P; i += T) colk[i] = 0.0;
+        }
+        else
+        {
+            beta = sqrt(c0 * c0 + tailSq);
+            if (c0 >= 0.0) beta = -beta;
+            const double den = c0 - beta;
+            for (int i = k + 1 + tid; i < P; i += T) colk[i] = colk[i] / den;
+            tau = (beta - c0) / beta;
+        }
+        __syncthreads();
+        if (tid == 0)
+        {
+            colk[k] = beta;
+            hco[k] = tau;
+            if (fabs(beta) > s_maxpivot) s_maxpivot = fabs(beta);
+        }
+        // ---- applyHouseholderOnTheLeft to A[k:, k+1:] (one warp per column); the new trailing block's biggest entry on the way ----
+        carry_best = -1.0;
+        carry_idx = 0x7fffffff;
+        const int m1 = P - k - 1;
+        for (int j = k + 1 + warp; j < P; j += nwarp)
+        {
+            double* cj = A + (size_t)j * P;
+            double tmp = 0.0;
+            if (tau != 0.0)
+            {
+                double d = 0.0;
+                for (int i = k + 1 + lane; i < P; i += 32) d += colk[i] * cj[i];
+                d = warp_sum(d);
+                tmp = d + cj[k];
+                __syncwarp();
+                if (lane == 0) cj[k] = cj[k] - tau * tmp;
+            }
+            for (int i = k + 1 + lane; i < P; i += 32)
+            {
+                double v = cj[i];
+                if (tau != 0.0)
+                {
+                    v = v - (tau * colk[i]) * tmp;
+                    cj[i] = v;
+                }
+                const double av = fabs(v);
+                const int idx = (j - k - 1) * m1 + (i - k - 1);
+                if (av > carry_best || (av == carry_best && idx < carry_idx))
+                {
+                    carry_best = av;
+                    carry_idx = idx;
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- rank, Q^T b, back substitution, permutation (FullPivHouseholderQR::_solve_impl) ----
+    const int nonzero = s_nonzero;
+    const double premult = fabs(s_maxpivot) * (2.220446049250313e-16 * (double)P);
+    int rank = 0;
+    for (int i = 0; i < nonzero; i++) rank += (fabs(A[i + (size_t)i * P]) > premult) ? 1 : 0; // (every thread counts alike)
+    // m_cols_permutation = product of the column transpositions (applyTranspositionOnTheRight)
+    if (tid == 0)
+    {
+        for (int i = 0; i < P; i++) perm[i] = i;
+        for (int k = 0; k < P; k++)
+        {
+            const int t = perm[k];
+            perm[k] = perm[colT[k]];
+            perm[colT[k]] = t;
+        }
+    }
+    __syncthreads();
+    for (int k = 0; k < rank; k++)
+    {
+        if (tid == 0)
+        {
+            const int r = rowT[k];
+            double t = cR[k]; cR[k] = cR[r]; cR[r] = t;
+            t = cI[k]; cI[k] = cI[r]; cI[r] = t;
+        }
+        __syncthreads();
+        const double tau = hco[k];
+        if (tau != 0.0 && P - k > 1)
+        {
+            const double* colk = A + (size_t)k * P;
+            double dR = 0.0, dI = 0.0;
+            for (int i = k + 1 + tid; i < P; i += T)
+            {
+                dR += colk[i] * cR[i];
+                dI += colk[i] * cI[i];
+            }
+            const double tR = block_sum(dR, red, tid, T) + cR[k];
+            const double tI = block_sum(dI, red, tid, T) + cI[k];
+            __syncthreads();
+            if (tid == 0)
+            {
+                cR[k] = cR[k] - tau * tR;
+                cI[k] = cI[k] - tau * tI;
+            }
+            for (int i = k + 1 + tid; i < P; i += T)
+            {
+                cR[i] = cR[i] - (tau * colk[i]) * tR;
+                cI[i] = cI[i] - (tau * colk[i]) * tI;
+            }
+            __syncthreads();
+        }
+        else if (P - k == 1 && tid == 0) // rows() == 1: *this *= 1 - tau
+        {
+            cR[k] = cR[k] * (1.0 - tau);
+            cI[k] = cI[k] * (1.0 - tau);
+        }
+        __syncthreads();
+    }
+    // upper-triangular solve R[0:rank, 0:rank] y = c[0:rank] (column-oriented back substitution)
+    for (int i = rank - 1; i >= 0; i--)
+    {
+        if (tid == 0)
+        {
+            cR[i] = cR[i] / A[i + (size_t)i * P];
+            cI[i] = cI[i] / A[i + (size_t)i * P];
+        }
+        __syncthreads();
+        const double yR = cR[i], yI = cI[i];
+        for (int r = tid; r < i; r += T)
+        {
+            const double rij = A[r + (size_t)i * P];
+            cR[r] = cR[r] - rij * yR;
+            cI[r] = cI[r] - rij * yI;
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < P; i += T)
+    {
+        xR[perm[i]] = i < rank ? cR[i] : 0.0;
+        xI[perm[i]] = i < rank ? cI[i] : 0.0;
+    }
+    __syncthreads();
+    // mean subtraction (:1800-1809), CalculatePhiDot (:1658-1682), scalings (:1818-1825)
+    if (tid == 0)
+    {
+        double mR = 0.0, mI = 0.0;
+        for (int i = 0; i < P; i++)
+        {
+            mR += xR[i];
+            mI += xI[i];
+        }
+        mR = mR / (double)P;
+        mI = mI / (double)P;
+        double pr = 0.0, pi = 0.0;
+        for (int i = 0; i < P; i++)
+        {
+            xR[i] = xR[i] - mR;
+            xI[i] = xI[i] - mI;
+            pr -= O[i] * xR[i];
+            pi -= O[i] * xI[i];
+        }
+        if (a.imaginary_time == -1)
+        {
+            const double rotation = 1.499 * 3.14159265358979323846;
+            pi -= cos(rotation) * ER;
+            pr -= sin(rotation) * ER;
+        }
+        else if (a.imaginary_time == 0) pi -= ER;
+        else pr -= ER;
+        double* tail = a.out + 2 * (size_t)P;
+        tail[0] = pr;
+        tail[1] = pi;
+        tail[2] = 0.0;
+        tail[3] = ER;
+        tail[4] = EI;
+    }
+    __syncthreads();
+    for (int i = tid; i < P; i += T)
+    {
+        a.out[i] = a.use_preconditioning ? xR[i] / scal[i] : xR[i];
+        a.out[P + i] = a.use_preconditioning ? xI[i] / scal[i] : xI[i];
+    }
+}
+
+cudaError_t launch_solve_qr(SolveArgs a, cudaStream_t st)
+{
+    if (a.P < 1 || a.P > 1024 || !a.L_global) return cudaErrorInvalidValue;
+    const size_t smem = (7 * (size_t)a.P + 64) * sizeof(double) + 3 * (size_t)a.P * sizeof(int);
+    cudaError_t e = cudaFuncSetAttribute(solve_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    solve_qr_kernel<<<1, 1024, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
 size_t solve_smem_bytes(int P, bool l_in_smem)
 {
     size_t n = 9 * (size_t)P;

@@ -467,21 +467,22 @@ void GpuEnsembleSystem::SampleExpectationValues(const std::vector<double>& uR, c
     Check(tdvmc_gpu_sample_and_accumulate(handle, MC_NSTEPS, MC_NTHERMSTEPS, MC_NINITIALIZATIONSTEPS), "sample_and_accumulate");
 }
 
-static tdvmc_solver_desc MakeSolverDesc(int IMAGINARY_TIME, int USE_PRECONDITIONING)
+static tdvmc_solver_desc MakeSolverDesc(int IMAGINARY_TIME, int USE_PRECONDITIONING, int LINEAR_EQUATION_SOLVER_TYPE = 0)
 {
     tdvmc_solver_desc sd;
     memset(&sd, 0, sizeof(sd));
     sd.struct_size = sizeof(sd);
     sd.imaginary_time = IMAGINARY_TIME;
     sd.use_preconditioning = USE_PRECONDITIONING;
-    sd.regularization = 0.001; // src/TDVMC.cpp:1737
+    sd.solver_type = LINEAR_EQUATION_SOLVER_TYPE;
+    sd.regularization = LINEAR_EQUATION_SOLVER_TYPE == 1 ? 0.002 : 0.001; // src/TDVMC.cpp:1770, :1737
     return sd;
 }
 
 bool GpuEnsembleSystem::SolveForParametersDot(std::vector<double>& uDotR, std::vector<double>& uDotI, double* phiDotR,
                                               double* phiDotI, int IMAGINARY_TIME, int USE_PRECONDITIONING)
 {
-    const tdvmc_solver_desc sd = MakeSolverDesc(IMAGINARY_TIME, USE_PRECONDITIONING);
+    const tdvmc_solver_desc sd = MakeSolverDesc(IMAGINARY_TIME, USE_PRECONDITIONING, solverType);
     uDotR.assign(P, 0.0);
     uDotI.assign(P, 0.0);
     tdvmc_parameters_dot d;
@@ -498,7 +499,7 @@ bool GpuEnsembleSystem::CalculateNextParametersEuler(double dt, std::vector<doub
                                                      double* phiI, int IMAGINARY_TIME, int USE_PRECONDITIONING, double time,
                                                      double* localEnergyR, double* localEnergyI)
 {
-    const tdvmc_solver_desc sd = MakeSolverDesc(IMAGINARY_TIME, USE_PRECONDITIONING);
+    const tdvmc_solver_desc sd = MakeSolverDesc(IMAGINARY_TIME, USE_PRECONDITIONING, solverType);
     tdvmc_parameters_dot d;
     memset(&d, 0, sizeof(d));
     Check(tdvmc_gpu_euler_step(handle, &sd, dt, time, uR.data(), uI.data(), phiR, phiI, &d), "euler_step");

@@ -192,6 +192,9 @@ public:
     double GetExponent();
 
     // ---- parameter derivatives on the device ----
+    // LINEAR_EQUATION_SOLVER_TYPE of the calls below: 0 the hand-written Cholesky (default), 1 Eigen's FullPivHouseholderQR
+    // with the mean subtraction of src/TDVMC.cpp:1800-1809
+    void SetLinearEquationSolverType(int LINEAR_EQUATION_SOLVER_TYPE) { solverType = LINEAR_EQUATION_SOLVER_TYPE; }
     // ParallelUpdateExpectationValues without the fetch: the estimator sums stay in HBM for the two calls below.
     void SampleExpectationValues(const std::vector<double>& uR, const std::vector<double>& uI, double phiR, double phiI,
                                  int MC_NSTEPS, int MC_NTHERMSTEPS, int MC_NINITIALIZATIONSTEPS, double time);
@@ -247,6 +250,7 @@ private:
     tdvmc_gpu_handle* handle = nullptr;
     int N = 0, P = 0, nOther = 9;
     int nLocal = 0, firstWalker = 0, rank = 0, world = 1;
+    int solverType = 0;
     std::vector<double> flat;
 };
 

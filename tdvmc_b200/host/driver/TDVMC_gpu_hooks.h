@@ -67,7 +67,7 @@ TDVMC_GPU_EXPOSE(MX_distances, PhysicalSystems::BosonMixtureCluster, Observables
 // new config items (registered next to the reference's, src/TDVMC.cpp:297-349; absent keys stay 0)
 int GPU_WALKERS = 0;      // total number of device-resident walkers over all ranks; 0: reference CPU path
 int GPU_SEED = 0;         // Philox seed of the ensemble; 0: 1
-int GPU_DEVICE_SOLVE = 0; // 1: Euler step with LINEAR_EQUATION_SOLVER_TYPE = 0 solved on the device (solve_kernel)
+int GPU_DEVICE_SOLVE = 0; // 1: SolveForParametersDot of the Euler step on the device (solve_kernel / solve_qr_kernel)
 
 tdvmc_host::GpuEnsembleSystem* gpu = nullptr;
 tdvmc_host::ObservableTables gpuObservableTables;
@@ -420,13 +420,15 @@ bool GpuParallelCalculateAdditionalSystemProperties(vector<double>& uR, vector<d
 	return true;
 }
 
-// CalculateNextParametersEuler (src/TDVMC.cpp:1834-1853) with the Cholesky branch of SolveForParametersDot on the device
+// CalculateNextParametersEuler (src/TDVMC.cpp:1834-1853) with SolveForParametersDot (either branch) on the device
 bool GpuCalculateNextParametersEuler(double dt, vector<double>& uR, vector<double>& uI, double* phiR, double* phiI)
 {
-	if (!gpu || GPU_DEVICE_SOLVE != 1 || LINEAR_EQUATION_SOLVER_TYPE != 0 || USE_PARAM_START != 0 || (USE_PARAM_END != 0 && USE_PARAM_END != N_PARAM - 1))
+	if (!gpu || GPU_DEVICE_SOLVE != 1 || (LINEAR_EQUATION_SOLVER_TYPE != 0 && LINEAR_EQUATION_SOLVER_TYPE != 1) || USE_PARAM_START != 0
+			|| (USE_PARAM_END != 0 && USE_PARAM_END != N_PARAM - 1))
 	{
 		return false;
 	}
+	gpu->SetLinearEquationSolverType(LINEAR_EQUATION_SOLVER_TYPE);
 	doNotAcceptStep = gpu->CalculateNextParametersEuler(dt, uR, uI, phiR, phiI, IMAGINARY_TIME, USE_PRECONDITIONING, sys->GetTime() + dt, nullptr, nullptr) || doNotAcceptStep;
 	return true;
 }

@@ -65,12 +65,16 @@ def cholesky_solve(A, rhs_list):
     return out
 
 
-def solve_for_parameters_dot(est, imaginary_time=1, use_preconditioning=True, regularization=0.001, lapack=False,
-                             min_scaling=0.0):
+def solve_for_parameters_dot(est, imaginary_time=1, use_preconditioning=True, regularization=None, lapack=False,
+                             min_scaling=0.0, solver_type=0):
     """SolveForParametersDot with LINEAR_EQUATION_SOLVER_TYPE = 0: returns (uDotR, uDotI, phiDotR, phiDotI).
     lapack=True factorises with numpy's LAPACK (dpotrf/dpotrs through numpy.linalg) instead of the reference's
     hand-written loops - same matrix, same right-hand sides, results equal to rounding."""
+    if regularization is None:
+        regularization = 0.002 if solver_type == 1 else 0.001          # :1770, :1737
     A, b_r, b_i = build_system_of_equations(est, imaginary_time)
+    if solver_type == 1:
+        return _solve_qr_branch(est, A, b_r, b_i, imaginary_time, use_preconditioning, regularization, min_scaling)
     scal = np.ones(len(b_r))
     if use_preconditioning:
         scal = np.sqrt(np.maximum(np.diag(A), 0.0))
@@ -98,6 +102,39 @@ def solve_for_parameters_dot(est, imaginary_time=1, use_preconditioning=True, re
         phi_i -= float(est["localEnergyR"])
     else:
         phi_r -= float(est["localEnergyR"])
+    return u_r / scal, u_i / scal, phi_r, phi_i
+
+
+def _phi_dot(est, u_r, u_i, imaginary_time):
+    O = np.asarray(est["localOperators"], np.float64)
+    phi_r = -float(np.dot(O, u_r))
+    phi_i = -float(np.dot(O, u_i))
+    if imaginary_time == -1:
+        rotation = 1.499 * np.pi
+        phi_i -= np.cos(rotation) * float(est["localEnergyR"])
+        phi_r -= np.sin(rotation) * float(est["localEnergyR"])
+    elif imaginary_time == 0:
+        phi_i -= float(est["localEnergyR"])
+    else:
+        phi_r -= float(est["localEnergyR"])
+    return phi_r, phi_i
+
+
+def _solve_qr_branch(est, A, b_r, b_i, imaginary_time, use_preconditioning, regularization, min_scaling):
+    """LINEAR_EQUATION_SOLVER_TYPE = 1 (src/TDVMC.cpp:1763-1827): scaling and +0.002 only with USE_PRECONDITIONING, a
+    rank-revealing solve (Eigen FullPivHouseholderQR there, LAPACK's least-squares here - the same solution wherever the
+    matrix has full numerical rank), the mean of each solution subtracted, CalculatePhiDot, scalings divided out."""
+    scal = np.ones(len(b_r))
+    if use_preconditioning:
+        scal = np.sqrt(np.maximum(np.diag(A), 0.0))
+        if min_scaling > 0.0:
+            scal = np.maximum(scal, min_scaling)
+        A = A / np.outer(scal, scal) + regularization * np.eye(len(b_r))
+        b_r, b_i = b_r / scal, b_i / scal
+    x = np.linalg.lstsq(A, np.stack([b_r, b_i], axis=1), rcond=len(b_r) * np.finfo(float).eps)[0]
+    u_r = x[:, 0] - x[:, 0].mean()
+    u_i = x[:, 1] - x[:, 1].mean()
+    phi_r, phi_i = _phi_dot(est, u_r, u_i, imaginary_time)
     return u_r / scal, u_i / scal, phi_r, phi_i
 
 

@@ -165,18 +165,22 @@ def test_driver_config4_own_size_runs(binaries, golden, tmp_path):
     assert abs(r.local_energy_r[1] - r.local_energy_r[0]) < 0.02 * abs(r.local_energy_r[0])
 
 
-def test_device_solve_option_matches_host_solve(binaries, golden, tmp_path):
-    """GPU_DEVICE_SOLVE = 1: CalculateNextParametersEuler served by solve_kernel (bit-identical Cholesky branch) - the
-    trajectory equals the host-solved one of the same ensemble to rounding."""
+@pytest.mark.parametrize("solver_type,tol", [(0, 1e-9), (1, 1e-7)])
+def test_device_solve_option_matches_host_solve(binaries, golden, tmp_path, solver_type, tol):
+    """GPU_DEVICE_SOLVE = 1: SolveForParametersDot of the Euler step served by the device - solve_kernel (the hand-written
+    Cholesky, bit-identical) or solve_qr_kernel (Eigen's FullPivHouseholderQR step by step) - against the driver's own host
+    solve on the same ensemble: the trajectories coincide to rounding (times the condition number for QR)."""
     gpu_bin, _ = binaries
     g = golden("bosonsbulk_n64_equil")
     cfg = driver.base_config(N=64, LBOX=4.0, N_PARAM=33, MC_STEP=0.4, MC_NSTEPS=2, MC_NTHERMSTEPS=64, MC_NINITIALIZATIONSTEPS=64,
                              MC_VERY_FIRST_NINITIALIZATIONSTEPS=6400, TIMESTEP=2e-4, TOTALTIME=2e-4 * 5.5, IMAGINARY_TIME=1,
-                             USE_PRECONDITIONING=1, PARAMS_REAL=[float(x) for x in g["uR"]], SYSTEM_PARAMS=[1.0, 1.0], GPU_WALKERS=512)
+                             LINEAR_EQUATION_SOLVER_TYPE=solver_type, USE_PRECONDITIONING=1, PARAMS_REAL=[float(x) for x in g["uR"]],
+                             SYSTEM_PARAMS=[1.0, 1.0], GPU_WALKERS=512)
     a = driver.run_driver(gpu_bin, cfg, str(tmp_path / "host"), R0=g["R"])
     b = driver.run_driver(gpu_bin, dict(cfg, GPU_DEVICE_SOLVE=1), str(tmp_path / "dev"), R0=g["R"])
-    assert np.max(np.abs(a.parameters_r[:, :33] - b.parameters_r[:, :33])) < 1e-9
-    assert np.max(np.abs(a.local_energy_r - b.local_energy_r)) < 1e-8 * np.max(np.abs(a.local_energy_r))
+    assert len(a.local_energy_r) == 6 and np.max(np.abs(a.parameters_r[-1, :33] - a.parameters_r[0, :33])) > 1e-4
+    assert np.max(np.abs(a.parameters_r[:, :33] - b.parameters_r[:, :33])) < tol
+    assert np.max(np.abs(a.local_energy_r - b.local_energy_r)) < 10 * tol * np.max(np.abs(a.local_energy_r))
 
 
 def test_driver_hebulk_config2(binaries, golden, parity_log, tmp_path):

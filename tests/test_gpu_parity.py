@@ -1238,9 +1238,31 @@ def test_device_solver_matches_reference(capi, golden, name):
     assert d["not_positive_definite"]
     with pytest.raises(capi.TdvmcError, match="IMAGINARY_TIME"):
         h.solve_fixed(est, imaginary_time=2)
-    # LINEAR_EQUATION_SOLVER_TYPE = 1 (Eigen FullPivHouseholderQR) is refused up front, never served by the Cholesky branch
-    with pytest.raises(capi.TdvmcError, match="FullPivHouseholderQR"):
-        h.solve_fixed(est, imaginary_time=imag, solver_type=1)
+    with pytest.raises(capi.TdvmcError, match="LINEAR_EQUATION_SOLVER_TYPE"):
+        h.solve_fixed(est, imaginary_time=imag, solver_type=2)
+    h.close()
+
+
+@pytest.mark.parametrize("name", ["bosonsbulk_n64_evolution_qr", "bosonsbulk_n64_evolution_qr_raw"])
+def test_device_qr_solver_matches_eigen(capi, golden, name):
+    """LINEAR_EQUATION_SOLVER_TYPE = 1 on the device (solve_qr_kernel: Eigen's FullPivHouseholderQR step by step, then the mean
+    subtraction of src/TDVMC.cpp:1800-1809) against the derivatives the reference's Eigen branch computed from its own
+    first-step estimators - with the scaling + 0.002 regularisation of USE_PRECONDITIONING = 1 (condition ~500) and without
+    (condition 1.4e5): equal to rounding times the condition number."""
+    g = golden(name)
+    src = golden(str(g["source"]))
+    spec = systems.bosons_bulk(int(g["N"]), float(g["LBOX"]), int(g["N_PARAM"]), g["SYSTEM_PARAMS"], weights=src["spline_weights"])
+    h = capi.Handle(spec, 4)
+    est = dict(O=g["first_O"], S=g["first_S"], OER=g["first_OER"], OEI=g["first_OEI"], e_r=g["first_ER"], e_i=g["first_EI"])
+    pre = bool(int(g["USE_PRECONDITIONING"]))
+    d = h.solve_fixed(est, imaginary_time=int(g["IMAGINARY_TIME"]), use_preconditioning=pre, solver_type=1)
+    tol = 1e-11 if pre else 1e-9
+    scale = max(np.max(np.abs(g["first_uDotR"])), np.max(np.abs(g["first_uDotI"])))
+    assert scale > 0
+    assert np.max(np.abs(d["u_dot_r"] - g["first_uDotR"])) < tol * scale and np.max(np.abs(d["u_dot_i"] - g["first_uDotI"])) < tol * scale
+    pscale = max(abs(float(g["first_phiDotR"])), abs(float(g["first_phiDotI"])))
+    assert abs(d["phi_dot_r"] - float(g["first_phiDotR"])) < tol * pscale and abs(d["phi_dot_i"] - float(g["first_phiDotI"])) < tol * pscale
+    assert abs(np.sum(d["u_dot_r"] * (1.0 if not pre else 0.0))) < 1e-9 * scale * len(d["u_dot_r"])   # mean subtracted (unscaled case)
     h.close()
 
 

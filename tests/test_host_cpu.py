@@ -223,7 +223,8 @@ def test_cpp_he_table_builders_match_python_specs():
             np.testing.assert_array_equal(got if got.size else np.zeros(P), want if want is not None else np.zeros(P))
 
 
-@pytest.mark.parametrize("name", ["bosonsbulk_n64_evolution", "bosonsbulk_n64_evolution_realtime", "bosonsbulk_n64_evolution_rotation"])
+@pytest.mark.parametrize("name", ["bosonsbulk_n64_evolution", "bosonsbulk_n64_evolution_realtime", "bosonsbulk_n64_evolution_rotation",
+                                  "bosonsbulk_n64_evolution_qr", "bosonsbulk_n64_evolution_qr_raw"])
 def test_timestep_solver_matches_reference(golden, name):
     """tdvmc_b200.timestep (host mirror of SolveForParametersDot, Cholesky branch) reproduces the derivatives the
     reference computed from its own first-step estimators (ref_harness evolve)."""
@@ -231,7 +232,10 @@ def test_timestep_solver_matches_reference(golden, name):
     g = golden(name)
     est = dict(localOperators=g["first_O"], localOperatorsMatrix=g["first_S"], localOperatorlocalEnergyR=g["first_OER"],
                localOperatorlocalEnergyI=g["first_OEI"], localEnergyR=float(g["first_ER"]), localEnergyI=float(g["first_EI"]))
-    u_r, u_i, p_r, p_i = timestep.solve_for_parameters_dot(est, imaginary_time=int(g["IMAGINARY_TIME"]))
+    kw = {}
+    if "LINEAR_EQUATION_SOLVER_TYPE" in g.files:       # the Eigen FullPivHouseholderQR branch (src/TDVMC.cpp:1763-1827)
+        kw = dict(solver_type=int(g["LINEAR_EQUATION_SOLVER_TYPE"]), use_preconditioning=bool(int(g["USE_PRECONDITIONING"])))
+    u_r, u_i, p_r, p_i = timestep.solve_for_parameters_dot(est, imaginary_time=int(g["IMAGINARY_TIME"]), **kw)
     # in real time the first step starts from uI = 0, so E^I = 0 and uDotR vanishes identically: one common scale
     scale = max(np.max(np.abs(g["first_uDotR"])), np.max(np.abs(g["first_uDotI"])))
     pscale = max(abs(float(g["first_phiDotR"])), abs(float(g["first_phiDotI"])))
@@ -240,6 +244,8 @@ def test_timestep_solver_matches_reference(golden, name):
     assert np.max(np.abs(u_i - g["first_uDotI"])) <= 1e-9 * scale
     assert abs(p_r - float(g["first_phiDotR"])) <= 1e-9 * pscale
     assert abs(p_i - float(g["first_phiDotI"])) <= 1e-9 * pscale
+    if kw:
+        return                                         # (what follows checks the Cholesky branch against LAPACK)
     v_r, v_i, q_r, q_i = timestep.solve_for_parameters_dot(est, imaginary_time=int(g["IMAGINARY_TIME"]), lapack=True)
     assert np.max(np.abs(v_r - u_r)) <= 1e-9 * scale and np.max(np.abs(v_i - u_i)) <= 1e-9 * scale
     assert abs(q_r - p_r) <= 1e-9 * pscale and abs(q_i - p_i) <= 1e-9 * pscale
