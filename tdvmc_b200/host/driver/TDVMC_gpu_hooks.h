@@ -63,6 +63,21 @@ TDVMC_GPU_EXPOSE(MX_ppp, PhysicalSystems::BosonMixtureCluster, vector<ParticlePa
 TDVMC_GPU_EXPOSE(MX_angular, PhysicalSystems::BosonMixtureCluster, Observables::ObservableVsOnGrid, angularDistribution)
 TDVMC_GPU_EXPOSE(MX_density, PhysicalSystems::BosonMixtureCluster, Observables::ObservableVsOnGridWithScaling, densityFromCOM)
 TDVMC_GPU_EXPOSE(MX_distances, PhysicalSystems::BosonMixtureCluster, Observables::ObservableVsOnGrid, particleDistances)
+// BosonMixtureCluster_4thorder: the same members under the same names (BosonMixtureCluster_4thorder.h:26-62)
+TDVMC_GPU_EXPOSE(M4_corrTypes, PhysicalSystems::BosonMixtureCluster_4thorder, vector<vector<int> >, correlationTypes)
+TDVMC_GPU_EXPOSE(M4_particleTypes, PhysicalSystems::BosonMixtureCluster_4thorder, vector<int>, particleTypes)
+TDVMC_GPU_EXPOSE(M4_cfd, PhysicalSystems::BosonMixtureCluster_4thorder, vector<CorrelationFunctionData>, corrFuncData)
+TDVMC_GPU_EXPOSE(M4_pp, PhysicalSystems::BosonMixtureCluster_4thorder, vector<ParticleProperties>, particleProperties)
+TDVMC_GPU_EXPOSE(M4_ppp, PhysicalSystems::BosonMixtureCluster_4thorder, vector<ParticlePairProperties>, particlePairProperties)
+TDVMC_GPU_EXPOSE(M4_angular, PhysicalSystems::BosonMixtureCluster_4thorder, Observables::ObservableVsOnGrid, angularDistribution)
+TDVMC_GPU_EXPOSE(M4_density, PhysicalSystems::BosonMixtureCluster_4thorder, Observables::ObservableVsOnGridWithScaling, densityFromCOM)
+TDVMC_GPU_EXPOSE(M4_distances, PhysicalSystems::BosonMixtureCluster_4thorder, Observables::ObservableVsOnGrid, particleDistances)
+// NUBosonsBulkPBBoxAndRadial (NUBosonsBulkPBBoxAndRadial.h:22, 41-42) and InhContactBosons (InhContactBosons.h:26-27)
+TDVMC_GPU_EXPOSE(BR_nodes, PhysicalSystems::NUBosonsBulkPBBoxAndRadial, vector<double>, nodes)
+TDVMC_GPU_EXPOSE(BR_weights, PhysicalSystems::NUBosonsBulkPBBoxAndRadial, TdvmcGpuTensor3, splineWeights)
+TDVMC_GPU_EXPOSE(BR_grBinCount, PhysicalSystems::NUBosonsBulkPBBoxAndRadial, int, grBinCount)
+TDVMC_GPU_EXPOSE(IC_spf, PhysicalSystems::InhContactBosons, WFParts::SingleParticleFunction, spf)
+TDVMC_GPU_EXPOSE(IC_pc, PhysicalSystems::InhContactBosons, WFParts::PairCorrelation, pc)
 
 // new config items (registered next to the reference's, src/TDVMC.cpp:297-349; absent keys stay 0)
 int GPU_WALKERS = 0;      // total number of device-resident walkers over all ranks; 0: reference CPU path
@@ -117,6 +132,46 @@ static void GpuCopyEstimators(const tdvmc_host::Estimators& e)
 	nTrials = e.nTrials;
 }
 
+// BosonMixtureCluster and BosonMixtureCluster_4thorder: per-species data per particle, per-pair-type spline sets and
+// potentials as InitSystem() left them (BosonMixtureCluster.cpp:104-346; the 4th-order class differs in the spline
+// order and the 5 x 3 boundary-condition factors only)
+static bool GpuBindMixture(tdvmc_host::SystemTables& t, int splineOrder, vector<int>& pt, vector<ParticleProperties>& pp,
+		vector<CorrelationFunctionData>& cfd, vector<ParticlePairProperties>& ppp, vector<vector<int> >& corrTypes,
+		Observables::ObservableVsOnGrid& ang, Observables::ObservableVsOnGridWithScaling& den, Observables::ObservableVsOnGrid& dis)
+{
+	vector<double> hbarOver2m(N), mass(N);
+	for (int n = 0; n < N; n++)
+	{
+		hbarOver2m[n] = pp[pt[n]].hbarOver2m;
+		mass[n] = pp[pt[n]].mass;
+	}
+	vector<tdvmc_host::MixturePairType> types(cfd.size());
+	for (size_t c = 0; c < cfd.size(); c++)
+	{
+		types[c].nodes = cfd[c].nodes;
+		types[c].splineWeights = cfd[c].splineWeights;
+		types[c].bcFactors = cfd[c].bcFactors;
+		types[c].mcMillanFactor = cfd[c].mcMillanFactor;
+		types[c].potential = dynamic_cast<Potentials::KTTY_He_Cs*>(ppp[c].potential) ? 2 : (dynamic_cast<Potentials::KTTY_He_Na*>(ppp[c].potential) ? 1 : 0);
+		if (types[c].potential == 0 && !dynamic_cast<Potentials::HFDB_He_He*>(ppp[c].potential))
+		{
+			return false; // a pair potential the device does not carry (e.g. LJ_He_He)
+		}
+	}
+	t = tdvmc_host::MakeBosonMixtureClusterTables(N, corrTypes, hbarOver2m, mass, types, sys->GetNumOfOtherExpectationValues(), splineOrder);
+	gpuClusterObservableTables.angleCount = ang.grid.count;
+	gpuClusterObservableTables.angleSpacing = ang.grid.spacing;
+	gpuClusterObservableTables.densityCount = den.grid.count;
+	gpuClusterObservableTables.densitySpacing = den.grid.spacing;
+	gpuClusterObservableTables.densityMax = den.grid.max;
+	gpuClusterObservableTables.densityScaling = den.scalingGrid;
+	gpuClusterObservableTables.distanceCount = dis.grid.count;
+	gpuClusterObservableTables.distanceSpacing = dis.grid.spacing;
+	gpuClusterObservableTables.distanceMax = dis.grid.max;
+	gpuHasClusterObservables = N == 3; // the reference's own pass hard-codes three particles (:696-706)
+	return true;
+}
+
 // Called after sys->InitSystem(); PostSystemInit(); (src/TDVMC.cpp:3132-3133): the system's own InitSystem() results
 // (knots, SplineFactory table, observable grids) become the device-side description.
 void GpuInit(vector<vector<double> >& R)
@@ -156,46 +211,44 @@ void GpuInit(vector<vector<double> >& R)
 	}
 	else if (auto s = dynamic_cast<PhysicalSystems::BosonMixtureCluster*>(sys))
 	{
-		// per-species data per particle, per-pair-type spline sets and potentials as InitSystem() left them (BosonMixtureCluster.cpp:104-346)
-		auto& pt = TDVMC_GPU_MEMBER(MX_particleTypes, *s);
-		auto& pp = TDVMC_GPU_MEMBER(MX_pp, *s);
-		auto& cfd = TDVMC_GPU_MEMBER(MX_cfd, *s);
-		auto& ppp = TDVMC_GPU_MEMBER(MX_ppp, *s);
-		vector<double> hbarOver2m(N), mass(N);
-		for (int n = 0; n < N; n++)
+		known = GpuBindMixture(t, 3, TDVMC_GPU_MEMBER(MX_particleTypes, *s), TDVMC_GPU_MEMBER(MX_pp, *s), TDVMC_GPU_MEMBER(MX_cfd, *s),
+				TDVMC_GPU_MEMBER(MX_ppp, *s), TDVMC_GPU_MEMBER(MX_corrTypes, *s), TDVMC_GPU_MEMBER(MX_angular, *s),
+				TDVMC_GPU_MEMBER(MX_density, *s), TDVMC_GPU_MEMBER(MX_distances, *s));
+	}
+	else if (auto s = dynamic_cast<PhysicalSystems::BosonMixtureCluster_4thorder*>(sys))
+	{
+		known = GpuBindMixture(t, 4, TDVMC_GPU_MEMBER(M4_particleTypes, *s), TDVMC_GPU_MEMBER(M4_pp, *s), TDVMC_GPU_MEMBER(M4_cfd, *s),
+				TDVMC_GPU_MEMBER(M4_ppp, *s), TDVMC_GPU_MEMBER(M4_corrTypes, *s), TDVMC_GPU_MEMBER(M4_angular, *s),
+				TDVMC_GPU_MEMBER(M4_density, *s), TDVMC_GPU_MEMBER(M4_distances, *s));
+	}
+	else if (auto s = dynamic_cast<PhysicalSystems::NUBosonsBulkPBBoxAndRadial*>(sys))
+	{
+		// g(r) rides in otherExpectationValues for this class, so no separate observable pass is bound
+		t = tdvmc_host::MakeNUBosonsBulkPBBoxAndRadialTables(N, LBOX, N_PARAM, TDVMC_GPU_MEMBER(BR_nodes, *s), TDVMC_GPU_MEMBER(BR_weights, *s),
+				SYSTEM_PARAMS, TDVMC_GPU_MEMBER(BR_grBinCount, *s));
+		t.dim = DIM;
+	}
+	else if (auto s = dynamic_cast<PhysicalSystems::InhContactBosons*>(sys))
+	{
+		if (DIM != 1)
 		{
-			hbarOver2m[n] = pp[pt[n]].hbarOver2m;
-			mass[n] = pp[pt[n]].mass;
+			known = false;
 		}
-		vector<tdvmc_host::MixturePairType> types(cfd.size());
-		for (size_t c = 0; c < cfd.size(); c++)
+		else
 		{
-			types[c].nodes = cfd[c].nodes;
-			types[c].splineWeights = cfd[c].splineWeights;
-			types[c].bcFactors = cfd[c].bcFactors;
-			types[c].mcMillanFactor = cfd[c].mcMillanFactor;
-			types[c].potential = dynamic_cast<Potentials::KTTY_He_Cs*>(ppp[c].potential) ? 2 : (dynamic_cast<Potentials::KTTY_He_Na*>(ppp[c].potential) ? 1 : 0);
-			if (types[c].potential == 0 && !dynamic_cast<Potentials::HFDB_He_He*>(ppp[c].potential))
+			tdvmc_host::SplinedFunctionTables f[2];
+			WFParts::SplinedFunction* src[2] = { &TDVMC_GPU_MEMBER(IC_spf, *s), &TDVMC_GPU_MEMBER(IC_pc, *s) };
+			for (int i = 0; i < 2; i++)
 			{
-				known = false; // a pair potential the device does not carry (e.g. LJ_He_He)
+				f[i].nodes = src[i]->nodes;
+				f[i].splineWeights = src[i]->splineWeights;
+				f[i].bcFactorsStart = src[i]->bcFactorsStart;
+				f[i].bcFactorsEnd = src[i]->bcFactorsEnd;
+				f[i].np1 = src[i]->np1;
+				f[i].np2 = src[i]->np2;
+				f[i].np3 = src[i]->np3;
 			}
-		}
-		if (known)
-		{
-			t = tdvmc_host::MakeBosonMixtureClusterTables(N, TDVMC_GPU_MEMBER(MX_corrTypes, *s), hbarOver2m, mass, types, sys->GetNumOfOtherExpectationValues(), 3);
-			auto& ang = TDVMC_GPU_MEMBER(MX_angular, *s);
-			auto& den = TDVMC_GPU_MEMBER(MX_density, *s);
-			auto& dis = TDVMC_GPU_MEMBER(MX_distances, *s);
-			gpuClusterObservableTables.angleCount = ang.grid.count;
-			gpuClusterObservableTables.angleSpacing = ang.grid.spacing;
-			gpuClusterObservableTables.densityCount = den.grid.count;
-			gpuClusterObservableTables.densitySpacing = den.grid.spacing;
-			gpuClusterObservableTables.densityMax = den.grid.max;
-			gpuClusterObservableTables.densityScaling = den.scalingGrid;
-			gpuClusterObservableTables.distanceCount = dis.grid.count;
-			gpuClusterObservableTables.distanceSpacing = dis.grid.spacing;
-			gpuClusterObservableTables.distanceMax = dis.grid.max;
-			gpuHasClusterObservables = N == 3; // the reference's own pass hard-codes three particles (:696-706)
+			t = tdvmc_host::MakeInhContactBosonsTables(N, LBOX, N_PARAM, SYSTEM_PARAMS, f[0], f[1]);
 		}
 	}
 	else if (dynamic_cast<PhysicalSystems::HeBulk*>(sys))

@@ -62,9 +62,10 @@ def compare_trajectories(ref, dev, n_par, parity_log, case, z_max=6.5):
         rms = np.sqrt(np.mean(z ** 2))
         parity_log.check("driver_evolution", case, f"max|z| {name}", np.max(np.abs(z)), 1.0, z_max,
                          f"{z.size} values, rms z = {rms:.2f}, spread dev/ref = {np.median(sb[live] / sa[live]):.2f}")
-        assert rms < 1.8, (name, rms)
-        if z.size >= 100:                                # (a handful of strongly correlated energies can all sit near zero)
-            assert rms > 0.4, (name, rms)
+        if z.size >= 100:
+            assert 0.4 < rms < 1.8, (name, rms)
+        else:                                            # a handful of strongly correlated energies: effectively ONE t-distributed
+            assert rms < 3.5, (name, rms)                # value (24 seeds per arm on this case: |z| <= 1.6, profiles/r02_driver_stability.txt)
     return out
 
 
@@ -222,25 +223,25 @@ def test_driver_hedrop_config1_first_pass(binaries, golden, parity_log, tmp_path
         parity_log.check("driver_first_pass", "hedrop_n6_config1", f"max|z| {name}", np.max(np.abs(z)), 1.0, 6.5, f"{z.size} values")
 
 
-def test_driver_mixture_config5(binaries, golden, parity_log, tmp_path):
-    """BASELINE configs[4], config/He4He4Na.config (BosonMixtureCluster: two He-4 and one Na, two pair types, HFD-B and KTTY
-    potentials).  The config ships TOTALTIME < 0: its whole workload is the end-of-run observable pass (r^2, corner angles,
-    density from the centre of mass, pair distances; BosonMixtureCluster.cpp:680-741), written to AdditionalObservables_*.dat -
-    compared between the two programs, and so is a short imaginary-time evolution with the config's sampling ratio."""
-    gpu_bin, ref_bin = binaries
-    g = golden("mixture_he4he4na_equil")
+def _mixture_base(g, system_type):
     P = int(g["N_PARAM"])
-    base = driver.base_config(SYSTEM_TYPE="BosonMixtureCluster", N=3, LBOX=float(g["LBOX"]), N_PARAM=P, RHO=0.015, RC=8.8, MC_STEP=4.0,
+    return driver.base_config(SYSTEM_TYPE=system_type, N=3, LBOX=float(g["LBOX"]), N_PARAM=P, RHO=0.015, RC=8.8, MC_STEP=4.0,
                               MC_NTHERMSTEPS=20, MC_NINITIALIZATIONSTEPS=1000, MC_VERY_FIRST_NINITIALIZATIONSTEPS=100000,
                               TIMESTEP=1e-4, IMAGINARY_TIME=1, ODE_SOLVER_TYPE=0, LINEAR_EQUATION_SOLVER_TYPE=0, USE_PRECONDITIONING=1,
                               USE_NORMALIZE_WF=1, GR_BIN_COUNT=400, USE_NURBS=1, NURBS_GRID=[float(x) for x in g["NURBS_GRID"]],
                               PARTICLE_TYPES=[int(x) for x in g["PARTICLE_TYPES"]], SYSTEM_PARAMS=[float(x) for x in g["SYSTEM_PARAMS"]],
                               PARAMS_REAL=[float(x) for x in g["uR"]], PARAMS_IMAGINARY=[0.0] * P, PARAM_PHIR=float(g["phiR"]))
-    # (a) the config as shipped: no time loop, only the observable pass (counts reduced 25-fold on the reference arm)
+
+
+def _mixture_observable_pass(binaries, base, g, case, parity_log, tmp_path):
+    """The config as shipped (TOTALTIME < 0): no time loop, only the end-of-run observable pass (counts reduced 25-fold on the
+    reference arm), AdditionalObservables_*.dat of the two programs within error bars."""
+    gpu_bin, ref_bin = binaries
     obs = dict(base, TOTALTIME=-1e-4, MC_NSTEPS=100, MC_NADDITIONALSTEPS=20000, MC_NADDITIONALTHERMSTEPS=100,
                MC_NADDITIONALINITIALIZATIONSTEPS=10000)
     ref = run_seeds(ref_bin, obs, "ref_obs", g["R"], list(range(1, 9)), tmp_path)
     dev = run_seeds(gpu_bin, dict(obs, GPU_WALKERS=2000, MC_NADDITIONALSTEPS=10), "gpu_obs", g["R"], list(range(1, 9)), tmp_path, gpu_seed=True)
+    assert "GPU ensemble: 2000 walkers" in dev[0].log
 
     def observable(run, name):
         path = os.path.join(run.out_dir, f"AdditionalObservables_{name}.dat")
@@ -254,22 +255,98 @@ def test_driver_mixture_config5(binaries, golden, parity_log, tmp_path):
         sa, sb = a.std(axis=0, ddof=1), b.std(axis=0, ddof=1)
         live = (sa > 0) & (sb > 0) & (a.mean(axis=0) > 0.02 * a.mean(axis=0).max())   # bins that are actually populated
         z = (b.mean(axis=0) - a.mean(axis=0))[live] / np.sqrt(sa[live] ** 2 / len(ref) + sb[live] ** 2 / len(dev))
-        parity_log.check("driver_observables", "mixture_he4he4na_config5", f"max|z| {name}", np.max(np.abs(z)), 1.0, 6.5,
+        parity_log.check("driver_observables", case, f"max|z| {name}", np.max(np.abs(z)), 1.0, 6.5,
                          f"{z.size} values, rms z = {np.sqrt(np.mean(z ** 2)):.2f}")
         assert np.sqrt(np.mean(z ** 2)) < 1.8
-    # (b) four imaginary-time Euler steps at the config's ratio of 20 steps per sample.  With the config's USE_PRECONDITIONING = 1
-    # the reference divides by the zero variance of operators whose knot interval is never visited and stops with "Energy not
-    # finite" after the first step - and so does the device-bound program, fed the same estimators; without it both evolve
+
+
+def _mixture_evolution(binaries, base, g, case, parity_log, tmp_path):
+    """Four imaginary-time Euler steps at the config's ratio of 20 steps per sample, without preconditioning."""
+    gpu_bin, ref_bin = binaries
+    evo = dict(base, TOTALTIME=1e-4 * 3.5, MC_NSTEPS=20000, USE_PRECONDITIONING=0)
+    ref = run_seeds(ref_bin, evo, "ref_evo", g["R"], list(range(1, 9)), tmp_path)
+    dev = run_seeds(gpu_bin, dict(evo, GPU_WALKERS=2000, MC_NSTEPS=10), "gpu_evo", g["R"], list(range(1, 9)), tmp_path, gpu_seed=True)
+    assert len(dev[0].local_energy_r) == 4
+    compare_trajectories(ref, dev, int(g["N_PARAM"]), parity_log, case)
+
+
+def test_driver_mixture_config5(binaries, golden, parity_log, tmp_path):
+    """BASELINE configs[4], config/He4He4Na.config (BosonMixtureCluster: two He-4 and one Na, two pair types, HFD-B and KTTY
+    potentials).  The config ships TOTALTIME < 0: its whole workload is the end-of-run observable pass (r^2, corner angles,
+    density from the centre of mass, pair distances; BosonMixtureCluster.cpp:680-741), written to AdditionalObservables_*.dat -
+    compared between the two programs, and so is a short imaginary-time evolution with the config's sampling ratio."""
+    gpu_bin, ref_bin = binaries
+    g = golden("mixture_he4he4na_equil")
+    base = _mixture_base(g, "BosonMixtureCluster")
+    _mixture_observable_pass(binaries, base, g, "mixture_he4he4na_config5", parity_log, tmp_path)
+    # With the config's USE_PRECONDITIONING = 1 the reference divides by the zero variance of operators whose knot interval is
+    # never visited and stops with "Energy not finite" after the first step - and so does the device-bound program, fed the same
+    # estimators; without it both evolve
     both = [driver.run_driver(b, dict(base, TOTALTIME=1e-4 * 3.5, MC_NSTEPS=ns, GPU_WALKERS=w), str(tmp_path / f"nan_{i}"), R0=g["R"], seed=2)
             for i, (b, ns, w) in enumerate(((ref_bin, 20000, 0), (gpu_bin, 10, 2000)))]
     for r in both:
         assert len(r.local_energy_r) == 2 and np.isfinite(r.local_energy_r[0]) and np.isnan(r.local_energy_r[1])
         assert "Energy not finite" in r.log
-    evo = dict(base, TOTALTIME=1e-4 * 3.5, MC_NSTEPS=20000, USE_PRECONDITIONING=0)
-    ref = run_seeds(ref_bin, evo, "ref_evo", g["R"], list(range(1, 9)), tmp_path)
-    dev = run_seeds(gpu_bin, dict(evo, GPU_WALKERS=2000, MC_NSTEPS=10), "gpu_evo", g["R"], list(range(1, 9)), tmp_path, gpu_seed=True)
-    assert len(dev[0].local_energy_r) == 4
-    compare_trajectories(ref, dev, P, parity_log, "mixture_he4he4na_config5")
+    _mixture_evolution(binaries, base, g, "mixture_he4he4na_config5", parity_log, tmp_path)
+
+
+def test_driver_mixture_4thorder(binaries, golden, parity_log, tmp_path):
+    """config/He4He4Na_4thOrder.config (BosonMixtureCluster_4thorder: quartic splines, 28 per pair type, 5 x 3 boundary-condition
+    factors): the same two comparisons as for config 5."""
+    g = golden("mixture4_he4he4na_equil")
+    base = _mixture_base(g, "BosonMixtureCluster_4thorder")
+    _mixture_observable_pass(binaries, base, g, "mixture4_he4he4na", parity_log, tmp_path)
+    _mixture_evolution(binaries, base, g, "mixture4_he4he4na", parity_log, tmp_path)
+
+
+def test_driver_inhcontact_bosons(binaries, golden, parity_log, tmp_path):
+    """config/InhContactBosons.config with its own values (three bosons on a ring of length 3 in one dimension, N_PARAM = 62 =
+    31 single-particle + 31 pair parameters plus the phase pair, MC_NSTEPS = 1000 x MC_NTHERMSTEPS = 100, imaginary-time Euler
+    steps of 2e-4 from all-zero parameters, FullPivHouseholderQR, acceptance check 5, USE_NORMALIZE_WF) - the shipped
+    SYSTEM_PARAMS {0, 10, 0, 0} switch both the contact interaction and the lattice off (gamma = 10 k pi with k = 0,
+    InhContactBosons.cpp:26-29: every estimator is identically zero in both programs), so k = 1, V0 = 2 of the golden fixture are
+    used: ten time steps through both programs."""
+    gpu_bin, ref_bin = binaries
+    g = golden("inhcontact_n3_equil")
+    cfg = driver.base_config(SYSTEM_TYPE="InhContactBosons", N=3, LBOX=3.0, DIM=1, N_PARAM=62, MC_STEP=0.5, MC_NSTEPS=1000,
+                             MC_NTHERMSTEPS=100, MC_NINITIALIZATIONSTEPS=1000, MC_VERY_FIRST_NINITIALIZATIONSTEPS=100000, TIMESTEP=2e-4,
+                             TOTALTIME=2e-4 * 9.5, IMAGINARY_TIME=1, ODE_SOLVER_TYPE=0, LINEAR_EQUATION_SOLVER_TYPE=1, USE_PRECONDITIONING=0,
+                             USE_PARAMETER_ACCEPTANCE_CHECK=1, PARAMETER_ACCEPTANCE_CHECK_TYPE=5, USE_NORMALIZE_WF=1, GR_BIN_COUNT=50,
+                             RHO_BIN_COUNT=50, SYSTEM_PARAMS=[0.0, 10.0, 1.0, 2.0])
+    R0 = np.asarray(g["R"])[:, :1]
+    ref = run_seeds(ref_bin, cfg, "ref", R0, list(range(1, 9)), tmp_path)
+    dev = run_seeds(gpu_bin, dict(cfg, GPU_WALKERS=500, MC_NSTEPS=2), "gpu", R0, list(range(1, 9)), tmp_path, gpu_seed=True)
+    assert "GPU ensemble: 500 walkers" in dev[0].log
+    assert len(dev[0].local_energy_r) == 10
+    compare_trajectories(ref, dev, 62, parity_log, "inhcontact_n3")
+    # the shipped values themselves: both programs report zero energy and leave the parameters at zero
+    flat = dict(cfg, SYSTEM_PARAMS=[0.0, 10.0, 0.0, 0.0], TOTALTIME=2e-4 * 2.5)
+    for r in (driver.run_driver(ref_bin, flat, str(tmp_path / "flat_ref"), R0=R0, seed=1),
+              driver.run_driver(gpu_bin, dict(flat, GPU_WALKERS=500, MC_NSTEPS=2), str(tmp_path / "flat_gpu"), R0=R0, seed=1)):
+        assert np.all(r.local_energy_r == 0.0) and np.all(r.parameters_r[:, :62] == 0.0)
+
+
+def test_driver_boxandradial_n27(binaries, golden, parity_log, tmp_path):
+    """config/NUBosonsBulkPBBoxAndRadial3D.config (N = 27, N_PARAM = 100 = 50 box + 50 radial parameters, MC_NSTEPS = 10 x
+    MC_NTHERMSTEPS = 125, imaginary-time Euler, preconditioned Cholesky, acceptance check 5); the shipped file leaves LBOX, the
+    NURBS grid, SYSTEM_PARAMS and the parameters empty, the golden fixture's are used (LBOX = 3, 51 knots, {0.1, 50}).  With that
+    parameter set the reference's own evolution blows up at the config's step of 1e-4 ("NOT POSITIVE SEMI DEFINITE" after two
+    steps), and with 1000 samples one seed in eight never visits the innermost knot interval (zero variance, the preconditioner
+    divides by it), so six steps of 1e-6 with 4000 samples each go through both programs."""
+    gpu_bin, ref_bin = binaries
+    g = golden("boxradial_n27_equil")
+    cfg = driver.base_config(SYSTEM_TYPE="NUBosonsBulkPBBoxAndRadial", N=27, LBOX=float(g["LBOX"]), DIM=3, N_PARAM=100, MC_STEP=0.5,
+                             MC_NSTEPS=4000, MC_NTHERMSTEPS=125, MC_NINITIALIZATIONSTEPS=250, MC_VERY_FIRST_NINITIALIZATIONSTEPS=10000,
+                             TIMESTEP=1e-6, TOTALTIME=1e-6 * 5.5, IMAGINARY_TIME=1, ODE_SOLVER_TYPE=0, LINEAR_EQUATION_SOLVER_TYPE=0,
+                             USE_PRECONDITIONING=1, USE_PARAMETER_ACCEPTANCE_CHECK=1, PARAMETER_ACCEPTANCE_CHECK_TYPE=5, USE_NORMALIZE_WF=1,
+                             GR_BIN_COUNT=400, USE_NURBS=1, NURBS_GRID=[float(x) for x in g["NURBS_GRID"]],
+                             SYSTEM_PARAMS=[float(x) for x in g["SYSTEM_PARAMS"]], PARAMS_REAL=[float(x) for x in g["uR"]],
+                             PARAMS_IMAGINARY=[float(x) for x in g["uI"]], PARAM_PHIR=float(g["phiR"]))
+    ref = run_seeds(ref_bin, cfg, "ref", g["R"], list(range(1, 9)), tmp_path)
+    dev = run_seeds(gpu_bin, dict(cfg, GPU_WALKERS=2000, MC_NSTEPS=2), "gpu", g["R"], list(range(1, 9)), tmp_path, gpu_seed=True)
+    assert "GPU ensemble: 2000 walkers" in dev[0].log
+    assert len(dev[0].local_energy_r) == 6
+    compare_trajectories(ref, dev, 100, parity_log, "boxradial_n27")
 
 
 def test_driver_config3_as_shipped_n8000(binaries, tmp_path):
