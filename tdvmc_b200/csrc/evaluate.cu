@@ -108,6 +108,7 @@ struct EvalSmem2
     unsigned short* lut;
 };
 
+
 __host__ __device__ inline size_t eval_smem_layout2(const SysDev& s, int nwarps, bool rot, bool gmem, EvalSmem2* out, unsigned char* base)
 {
     SmemCarver c = { base, 0 };
@@ -133,6 +134,114 @@ __host__ __device__ inline size_t eval_smem_layout2(const SysDev& s, int nwarps,
     return c.off;
 }
 
+// Everything after the pair loop: Laplacian factor, |F|^2 sums, drift output, fixed-order block reduction, the histogram
+// folded into O_k through the boundary-condition map, local energy and the otherExpectationValues row.
+__device__ __forceinline__ void eval_finish(const EvalArgs& a, const SysDev& s, const EvalSmem2& m, int cfg, double lapR, double lapI,
+                                            int vcount, int outer)
+{
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const int N = s.N, K = s.K, P = s.P;
+    const int NP32 = ((N + 31) >> 5) * 32;
+    const double* fRx = m.frc;
+    const double* fRy = fRx + NP32;
+    const double* fRz = fRy + NP32;
+    const double* fIx = fRz + NP32;
+    const double* fIy = fIx + NP32;
+    const double* fIz = fIy + NP32;
+    lapR *= 2.0; // each pair enters the Laplacian of both partners with the same value
+    lapI *= 2.0;
+
+    double R1 = 0.0, I1 = 0.0, RI = 0.0;
+    for (int n = tid; n < N; n += blockDim.x)
+    {
+        const double ax = fRx[n], ay = fRy[n], az = fRz[n], bx = fIx[n], by = fIy[n], bz = fIz[n];
+        R1 += ax * ax + ay * ay + az * az;          // VectorNorm2, BosonsBulk.cpp:418-419
+        I1 += bx * bx + by * by + bz * bz;
+        RI += ax * bx + ay * by + az * bz;          // kineticSumR1I1 / 2, BosonsBulk.cpp:417
+        if (a.drift_r)
+        {
+            double* d = a.drift_r + ((size_t)cfg * N + n) * 3;
+            d[0] = ax; d[1] = ay; d[2] = az;
+        }
+        if (a.drift_i)
+        {
+            double* d = a.drift_i + ((size_t)cfg * N + n) * 3;
+            d[0] = bx; d[1] = by; d[2] = bz;
+        }
+    }
+
+    // block reduction (fixed order -> deterministic)
+    R1 = warp_sum(R1);
+    I1 = warp_sum(I1);
+    RI = warp_sum(RI);
+    lapR = warp_sum(lapR);
+    lapI = warp_sum(lapI);
+    vcount = warp_sum_int(vcount);
+    outer = warp_sum_int(outer);
+    if (lane == 0)
+    {
+        double* r = m.red + warp * 8;
+        r[0] = R1; r[1] = I1; r[2] = RI; r[3] = lapR; r[4] = lapI; r[5] = (double)vcount; r[6] = (double)outer;
+    }
+    __syncthreads();
+
+    for (int k = tid; k < K; k += blockDim.x)
+    {
+        double t = 0.0;
+        for (int w = 0; w < nwarps; w++) t += m.hist[(size_t)w * K + k];
+        m.sstot[k] = t;
+        if (a.ss_out) a.ss_out[(size_t)cfg * K + k] = t;
+    }
+    __syncthreads();
+
+    const long long row = a.row0 + (long long)cfg * a.row_stride;
+    double* Arow = a.A + (size_t)row * a.lda;
+    double epart = 0.0;
+    for (int p = tid; p < P; p += blockDim.x)
+    {
+        double o = 0.0;
+        for (int j = s.map_ptr[p]; j < s.map_ptr[p + 1]; j++) o += s.map_val[j] * m.sstot[s.map_col[j]]; // BosonsBulk.cpp:158-177
+        Arow[p] = o;
+        epart = fma(s.uR[p], o, epart); // BosonsBulk.cpp:526-529
+    }
+    epart = warp_sum(epart);
+    if (lane == 0) m.red[warp * 8 + 7] = epart;
+    __syncthreads();
+
+    if (tid == 0)
+    {
+        double t[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+        for (int w = 0; w < nwarps; w++)
+            for (int q = 0; q < 8; q++) t[q] += m.red[w * 8 + q];
+        const double outer_sum = t[6];
+        const double v_int = s.pot_b * t[5];
+        const double exponent = t[7] + s.uR[s.tail_param] * outer_sum; // BosonsBulk.cpp:532-536
+        const double kR1 = t[0], kI1 = t[1], kRI = 2.0 * t[2], kR2 = t[3], kI2 = t[4];
+        const double kin_r = -(kR1 - kI1 + kR2) * s.hbar; // BosonsBulk.cpp:422
+        const double kin_i = -(kRI + kI2) * s.hbar;       // BosonsBulk.cpp:423
+        const double e_r = kin_r + v_int;                 // :425, external potential is zero (:344-347)
+        const double e_i = kin_i;
+        Arow[P] = e_r;
+        Arow[P + 1] = e_i;
+        Arow[P + 2] = 1.0;
+        double* o = a.other + (size_t)row * s.n_other;   // BosonsBulk.cpp:449-457
+        o[0] = kin_r;
+        o[1] = v_int;
+        o[2] = exp(exponent + s.phiR);
+        o[3] = exponent;
+        o[4] = kR1;
+        o[5] = kI1;
+        o[6] = kR2;
+        o[7] = kI2;
+        o[8] = kRI;
+        if (a.exponent) a.exponent[row] = exponent;
+        if (a.outer_out) a.outer_out[cfg] = outer_sum;
+    }
+}
+
 template <bool REFLECT, bool WIDE, bool ROT, bool GMEM = false>
 __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kernel(EvalArgs a)
 {
@@ -142,7 +251,7 @@ __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kerne
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int nwarps = blockDim.x >> 5;
-    const int N = s.N, K = s.K, P = s.P;
+    const int N = s.N, K = s.K;
     const int NT = (N + 31) >> 5; // tiles of 32 particles
 
     EvalSmem2 m;
@@ -360,95 +469,7 @@ __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kerne
             }
         }
     }
-    lapR *= 2.0; // each pair enters the Laplacian of both partners with the same value
-    lapI *= 2.0;
-
-    double R1 = 0.0, I1 = 0.0, RI = 0.0;
-    for (int n = tid; n < N; n += blockDim.x)
-    {
-        const double ax = fRx[n], ay = fRy[n], az = fRz[n], bx = fIx[n], by = fIy[n], bz = fIz[n];
-        R1 += ax * ax + ay * ay + az * az;          // VectorNorm2, BosonsBulk.cpp:418-419
-        I1 += bx * bx + by * by + bz * bz;
-        RI += ax * bx + ay * by + az * bz;          // kineticSumR1I1 / 2, BosonsBulk.cpp:417
-        if (a.drift_r)
-        {
-            double* d = a.drift_r + ((size_t)cfg * N + n) * 3;
-            d[0] = ax; d[1] = ay; d[2] = az;
-        }
-        if (a.drift_i)
-        {
-            double* d = a.drift_i + ((size_t)cfg * N + n) * 3;
-            d[0] = bx; d[1] = by; d[2] = bz;
-        }
-    }
-
-    // block reduction (fixed order -> deterministic)
-    R1 = warp_sum(R1);
-    I1 = warp_sum(I1);
-    RI = warp_sum(RI);
-    lapR = warp_sum(lapR);
-    lapI = warp_sum(lapI);
-    vcount = warp_sum_int(vcount);
-    outer = warp_sum_int(outer);
-    if (lane == 0)
-    {
-        double* r = m.red + warp * 8;
-        r[0] = R1; r[1] = I1; r[2] = RI; r[3] = lapR; r[4] = lapI; r[5] = (double)vcount; r[6] = (double)outer;
-    }
-    __syncthreads();
-
-    for (int k = tid; k < K; k += blockDim.x)
-    {
-        double t = 0.0;
-        for (int w = 0; w < nwarps; w++) t += m.hist[(size_t)w * K + k];
-        m.sstot[k] = t;
-        if (a.ss_out) a.ss_out[(size_t)cfg * K + k] = t;
-    }
-    __syncthreads();
-
-    const long long row = a.row0 + (long long)cfg * a.row_stride;
-    double* Arow = a.A + (size_t)row * a.lda;
-    double epart = 0.0;
-    for (int p = tid; p < P; p += blockDim.x)
-    {
-        double o = 0.0;
-        for (int j = s.map_ptr[p]; j < s.map_ptr[p + 1]; j++) o += s.map_val[j] * m.sstot[s.map_col[j]]; // BosonsBulk.cpp:158-177
-        Arow[p] = o;
-        epart = fma(s.uR[p], o, epart); // BosonsBulk.cpp:526-529
-    }
-    epart = warp_sum(epart);
-    if (lane == 0) m.red[warp * 8 + 7] = epart;
-    __syncthreads();
-
-    if (tid == 0)
-    {
-        double t[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-        for (int w = 0; w < nwarps; w++)
-            for (int q = 0; q < 8; q++) t[q] += m.red[w * 8 + q];
-        const double outer_sum = t[6];
-        const double v_int = s.pot_b * t[5];
-        const double exponent = t[7] + s.uR[s.tail_param] * outer_sum; // BosonsBulk.cpp:532-536
-        const double kR1 = t[0], kI1 = t[1], kRI = 2.0 * t[2], kR2 = t[3], kI2 = t[4];
-        const double kin_r = -(kR1 - kI1 + kR2) * s.hbar; // BosonsBulk.cpp:422
-        const double kin_i = -(kRI + kI2) * s.hbar;       // BosonsBulk.cpp:423
-        const double e_r = kin_r + v_int;                 // :425, external potential is zero (:344-347)
-        const double e_i = kin_i;
-        Arow[P] = e_r;
-        Arow[P + 1] = e_i;
-        Arow[P + 2] = 1.0;
-        double* o = a.other + (size_t)row * s.n_other;   // BosonsBulk.cpp:449-457
-        o[0] = kin_r;
-        o[1] = v_int;
-        o[2] = exp(exponent + s.phiR);
-        o[3] = exponent;
-        o[4] = kR1;
-        o[5] = kI1;
-        o[6] = kR2;
-        o[7] = kI2;
-        o[8] = kRI;
-        if (a.exponent) a.exponent[row] = exponent;
-        if (a.outer_out) a.outer_out[cfg] = outer_sum;
-    }
+    eval_finish(a, s, m, cfg, lapR, lapI, vcount, outer);
     if (!GMEM) break;  // (compile-time: the one-block-per-configuration kernels have no loop)
     __syncthreads();   // the slab and the histograms are reused by the next configuration
     cfg += gridDim.x;
@@ -459,9 +480,9 @@ __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kerne
 // reflection rule of NUBosonsBulkPB: 22.8 against 25.1 ms per 512 configurations at N = 1728; at BosonsBulk's cut r <= L/2
 // half the lanes idle, the records collide less, and the extra selects cost more than the replays saved (3.80 against
 // 3.64 ms per 2960 configurations at N = 343).
-static bool evaluate_rotated(const SysDev& s) { return s.pair_rule == 1; }
-
 constexpr size_t kEvalSmemLimit = (size_t)227 * 1024; // opt-in shared memory per block on sm_100a
+
+static bool evaluate_rotated(const SysDev& s) { return s.pair_rule == 1; }
 
 // positions + forces in global memory: when even one 24-warp block per SM does not fit shared memory
 static bool evaluate_gmem(const SysDev& s)
