@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(kSweepMaxThreadsWarp, 1) sweep_queue_kernel(Sw
     unsigned short* lut = reinterpret_cast<unsigned short*>(tts + (UNIFORM ? 0 : nrec));
     double* pos_base = reinterpret_cast<double*>(smem_raw + a.pos_offset);
     int* s_next = reinterpret_cast<int*>(pos_base + (size_t)a.wpb * 3 * Npp); // unit counter, then done[walkers of this block]
-    volatile int* s_done = s_next + 1;
+    int* s_done = s_next + 1; // per-walker count of finished chunks: written and polled with atomics only (one lane each)
 
     const int w_begin = (int)((long long)blockIdx.x * a.W / gridDim.x);
     const int w_end = (int)((long long)(blockIdx.x + 1) * a.W / gridDim.x);
@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(kSweepMaxThreadsWarp, 1) sweep_queue_kernel(Sw
         const int c = unit / nW, wl = unit - c * nW;
         const int w = w_begin + wl;
         if (lane == 0)
-            while (s_done[wl] < c) __nanosleep(200); // the walker's previous chunk (a smaller unit: no deadlock)
+            while (atomicAdd(s_done + wl, 0) < c) __nanosleep(200); // the walker's previous chunk (a smaller unit: no deadlock)
         __syncwarp();
         __threadfence_block();
         double* gpos = a.pos + (size_t)w * 3 * s.Np;
@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(kSweepMaxThreadsWarp, 1) sweep_queue_kernel(Sw
         if (lane == 0) atomicAdd(a.accepted + w, n_acc); // (successive chunks of a walker run on different warps)
         __threadfence_block();
         __syncwarp();
-        if (lane == 0) s_done[wl] = c + 1;
+        if (lane == 0) atomicExch(s_done + wl, c + 1);
     }
 }
 
@@ -599,11 +599,13 @@ __global__ void __launch_bounds__(kSweepMaxThreadsWarp, 1) sweep_queue_kernel(Sw
 bool sweep_queue_wanted(const SysDev& s, int W, int sm_count, int resident_per_sm, long long n_steps)
 {
     if (s.kind != 0 || s.dim != 3 || resident_per_sm <= 0 || n_steps < 320) return false;
-    if (const char* e = getenv("TDVMC_SWEEP_QUEUE")) // tuning knob: 0 = never
-        if (atoi(e) == 0) return false;
+    int knob = 1;
+    if (const char* e = getenv("TDVMC_SWEEP_QUEUE")) knob = atoi(e); // tuning knob: 0 = never, 2 = whenever possible (tests)
+    if (knob == 0) return false;
+    if ((W + sm_count - 1) / sm_count > 4096) return false; // (the flag array lives in shared memory)
+    if (knob == 2) return true;
     const double waves = (double)W / ((double)sm_count * resident_per_sm);
     if (waves <= 1.0) return false;
-    if ((W + sm_count - 1) / sm_count > 4096) return false; // (the flag array lives in shared memory)
     return waves / std::ceil(waves) < 0.92;
 }
 

@@ -1679,6 +1679,18 @@ def test_time_shared_sweep_equals_plain_launch(capi, golden):
     assert np.array_equal(Rq, Rp)
 
 
+def test_time_shared_sweep_small_ensemble_forced(capi, golden):
+    """The same comparison on an ensemble small enough for compute-sanitizer's racecheck (TDVMC_SWEEP_QUEUE = 2 takes the
+    time-shared launch whatever the wave count): 333 walkers of N = 64, most SMs holding two or three, chunks handed from warp
+    to warp through the per-walker flags."""
+    g = golden("bosonsbulk_n64_equil")
+    spec = systems.from_golden(g)
+    Rq, aq = _sweep_with_env(capi, spec, g, 333, 640, {"TDVMC_SWEEP_QUEUE": "2", "TDVMC_SWEEP_SPLIT": "1"})
+    Rp, ap = _sweep_with_env(capi, spec, g, 333, 640, {"TDVMC_SWEEP_QUEUE": "0", "TDVMC_SWEEP_SPLIT": "1"})
+    assert aq == ap and 0.3 < aq / (333 * 640.0) < 0.98
+    assert np.array_equal(Rq, Rp)
+
+
 @pytest.mark.parametrize("name,W", [("bosonsbulk_n343_equil", 300), ("nubosonsbulkpb_n1728_equil", 40)])
 def test_split_sweep_equals_one_warp_per_walker(capi, golden, name, W):
     """sweep_split_kernel (several warps per walker for ensembles that do not fill the machine) against the one-warp launch:
