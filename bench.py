@@ -601,7 +601,8 @@ def main():
                 "frac": sweep_tf / dfma_peak, "traffic": traffic, "traffic_source": traffic_src,
                 "note": "FP64 DFMA-pipe bound (SURVEY 8d): 19 836 algorithmic flop per walker-step; peak = DFMA microbenchmark "
                         "measured in this run (MEASURED_PEAKS.json has no FP64 entry); algorithmic HBM traffic is 16.5 KB per walker per launch",
-                "launches": n_sweep, "avg_launch_ms": ms_sweep / max(n_sweep, 1), "share_of_step": ms_sweep / ms_total}
+                "launches": n_sweep, "avg_launch_ms": ms_sweep / max(n_sweep, 1), "share_of_step": ms_sweep / ms_total,
+                "sweep_only_walker_steps_per_s": float(W) * STEPS_PER_WALKER * args.steps / (ms_sweep * 1e-3)}   # SURVEY 8(d) metric 1 (i)
     n_ev, ms_ev = stats["evaluate"]
     ev_tf = FLOP_PER_EVALUATION * float(W) * MC_NSTEPS * args.steps / (ms_ev * 1e-3) / 1e12
     kernels = [roofline,
