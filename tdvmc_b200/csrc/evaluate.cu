@@ -44,29 +44,6 @@
 namespace tdvmc
 {
 
-// Conflict-free warp-cooperative  hist[bin - p] += v[p], p = 0..3  for the lanes with active == true.
-// Must be called by all 32 lanes.  Lanes sharing a bin are serialised by their rank within the group;
-// the four pieces are separated by __syncwarp() because bin-p of one lane aliases bin'-p' of another.
-__device__ __forceinline__ void warp_hist_add4(double* hist, int bin, bool active, const double (&v)[4], int lane)
-{
-    const unsigned amask = __ballot_sync(FULL_MASK, active);
-    if (amask == 0u) return;
-    const int key = active ? bin : (-1 - lane);
-    const unsigned peers = __match_any_sync(FULL_MASK, key);
-    const int rank = __popc(peers & ((1u << lane) - 1u));
-    for (int round = 0;; round++)
-    {
-        const bool mine = active && (rank == round);
-        if (__ballot_sync(FULL_MASK, mine) == 0u) break;
-#pragma unroll
-        for (int p = 0; p < 4; p++)
-        {
-            if (mine) hist[bin - p] += v[p];
-            __syncwarp();
-        }
-    }
-}
-
 struct SmemCarver
 {
     unsigned char* base;

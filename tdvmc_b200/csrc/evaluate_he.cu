@@ -16,27 +16,6 @@
 namespace tdvmc
 {
 
-// see evaluate.cu; hist[bin - p] += v[p]
-__device__ __forceinline__ void warp_hist_add4_he(double* hist, int bin, bool active, const double (&v)[4], int lane)
-{
-    const unsigned amask = __ballot_sync(FULL_MASK, active);
-    if (amask == 0u) return;
-    const int key = active ? bin : (-1 - lane);
-    const unsigned peers = __match_any_sync(FULL_MASK, key);
-    const int rank = __popc(peers & ((1u << lane) - 1u));
-    for (int round = 0;; round++)
-    {
-        const bool mine = active && (rank == round);
-        if (__ballot_sync(FULL_MASK, mine) == 0u) break;
-#pragma unroll
-        for (int p = 0; p < 4; p++)
-        {
-            if (mine) hist[bin - p] += v[p];
-            __syncwarp();
-        }
-    }
-}
-
 __device__ __forceinline__ double he_pair_potential(const SysDev& s, double r)
 {
     if (s.potential == 0)
@@ -231,7 +210,7 @@ __global__ void __launch_bounds__(256) evaluate_he_kernel(EvalArgs a)
                     }
                 }
             }
-            warp_hist_add4_he(myhist, bin + 3, spline_val, val, lane);
+            warp_hist_add4(myhist, bin + 3, spline_val, val, lane);
         }
         if (valid)
         {
@@ -556,7 +535,7 @@ __global__ void __launch_bounds__(256) evaluate_he_tile_kernel(EvalArgs a)
                         rRx += gxR; rRy += gyR; rRz += gzR; rIx += gxI; rIy += gyI; rIz += gzI;
                         cRx -= gxR; cRy -= gyR; cRz -= gzR; cIx -= gxI; cIy -= gyI; cIz -= gzI; // the partner sees -v
                     }
-                    warp_hist_add4_he(myhist, bin + 3, spline_val, val, lane);
+                    warp_hist_add4(myhist, bin + 3, spline_val, val, lane);
                 }
             }
             // flush: columns of the first role, columns of the second, rows of the first, rows of the second
