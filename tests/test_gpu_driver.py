@@ -38,13 +38,16 @@ def run_seeds(binary, cfg, tag, R0, seeds, tmp_path, gpu_seed=False, workers=Non
         return list(ex.map(one, seeds))
 
 
-def compare_trajectories(ref, dev, n_par, parity_log, case, z_max=6.5):
+def compare_trajectories(ref, dev, n_par, parity_log, case, z_max=6.5, gauge=None):
     """Mean trajectories of the two arms against the standard error of their difference, each arm with its own seed-to-seed
     spread (Welch): z = (mean_dev - mean_ref) / sqrt(s_ref^2 / n_ref + s_dev^2 / n_dev).  With 6-8 seeds per arm z follows a
     t distribution with ~10 degrees of freedom, hence the bound of 6.5 on the maximum over some thousand (strongly
     correlated) values; the normalised deviations must ALSO be of unit size on average - a test that could not fail proves
-    nothing, and spreads that differed between the arms would show here."""
+    nothing, and spreads that differed between the arms would show here.  `gauge`: a direction in parameter space that leaves
+    the wave function unchanged; the parameters are compared with their component along it removed."""
     out = {}
+    if gauge is not None:
+        gauge = np.asarray(gauge, float) / np.linalg.norm(gauge)
     for name, get in (("E_R", lambda r: r.local_energy_r[:, None]), ("uR", lambda r: r.parameters_r[:, :n_par]),
                       ("uI", lambda r: r.parameters_i[:, :n_par])):
         a = np.stack([get(r) for r in ref])            # [seed][step][cols]
@@ -53,6 +56,9 @@ def compare_trajectories(ref, dev, n_par, parity_log, case, z_max=6.5):
         assert np.all(np.isfinite(a)) and np.all(np.isfinite(b)), name
         if name != "E_R":
             a, b = a[:, 1:], b[:, 1:]                    # step 0 holds the start parameters: identical, no spread
+            if gauge is not None:
+                a = a - (a @ gauge)[..., None] * gauge
+                b = b - (b @ gauge)[..., None] * gauge
         sa, sb = a.std(axis=0, ddof=1), b.std(axis=0, ddof=1)
         live = (sa > 0) & (sb > 0)
         if not np.any(live):
@@ -318,7 +324,11 @@ def test_driver_inhcontact_bosons(binaries, golden, parity_log, tmp_path):
     dev = run_seeds(gpu_bin, dict(cfg, GPU_WALKERS=500, MC_NSTEPS=2), "gpu", R0, list(range(1, 9)), tmp_path, gpu_seed=True)
     assert "GPU ensemble: 500 walkers" in dev[0].log
     assert len(dev[0].local_energy_r) == 10
-    compare_trajectories(ref, dev, 62, parity_log, "inhcontact_n3")
+    # Sum_k B_k = 1 on both knot vectors: a constant added to the 31 single-particle parameters and subtracted from the 31
+    # pair parameters ((N - 1) / 2 = 1 pair per particle) changes nothing but the norm.  S is exactly singular along that
+    # direction, the QR solution's component along it is rounding noise over rounding noise - the reference's own seeds
+    # end +-12 apart there after ten steps - so it is projected out before the comparison
+    compare_trajectories(ref, dev, 62, parity_log, "inhcontact_n3", gauge=[1.0] * 31 + [-1.0] * 31)
     # the shipped values themselves: both programs report zero energy and leave the parameters at zero
     flat = dict(cfg, SYSTEM_PARAMS=[0.0, 10.0, 0.0, 0.0], TOTALTIME=2e-4 * 2.5)
     for r in (driver.run_driver(ref_bin, flat, str(tmp_path / "flat_ref"), R0=R0, seed=1),
