@@ -667,17 +667,6 @@ __global__ void __launch_bounds__(256) evaluate_he_tile_kernel(EvalArgs a)
 }
 
 
-static bool he_rowwise()
-{
-    static int v = -1;
-    if (v < 0)
-    {
-        const char* e = getenv("TDVMC_EVAL_ROWWISE"); // A/B timing knob: 1 = first version of the kernel
-        v = (e && atoi(e) == 1) ? 1 : 0;
-    }
-    return v == 1;
-}
-
 cudaError_t launch_evaluate_he(const EvalArgs& a, cudaStream_t st)
 {
     if (a.n_cfg <= 0) return cudaSuccess;
@@ -687,7 +676,7 @@ cudaError_t launch_evaluate_he(const EvalArgs& a, cudaStream_t st)
     const int nwarps = threads / 32;
     size_t smem = sizeof(double) * ((size_t)2 * s.n_ext + 3 * (size_t)s.N + (size_t)nwarps * s.K + s.n_ext + (size_t)nwarps * 12 + 4) +
                   sizeof(int) * (size_t)(s.gr_bins + s.rho_bins) + 16;
-    if (s.N > 16 && !he_rowwise()) // small clusters (HeDrop's six atoms) keep the walk over partners: a 32x32 tile would idle
+    if (s.N > 16) // small clusters (HeDrop's six atoms) keep the walk over partners: a 32x32 tile would idle
     {
         const int np32 = ((s.N + 31) / 32) * 32;
         smem = sizeof(double) * ((size_t)2 * s.n_ext + 3 * (size_t)np32 + (size_t)nwarps * s.K + s.n_ext + (size_t)nwarps * 12 + 4 +
