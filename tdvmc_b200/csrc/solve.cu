@@ -17,6 +17,8 @@
 // P <= 1024 (one thread per unknown).
 #include "kernels.cuh"
 
+#include <cooperative_groups.h>
+
 namespace tdvmc
 {
 
@@ -263,38 +265,71 @@ __global__ void __launch_bounds__(1024, 1) solve_kernel(SolveArgs a)
 // bottom -= (tau essential) tmp; rank from |R_ii| > eps P max|R_ii|; Q^T applied to the right-hand sides, back
 // substitution on the leading rank x rank triangle, column permutation undone, zeros beyond the rank.  Dot products and
 // norms are summed in a different order than Eigen's packet reductions, so the results agree to rounding times the
-// condition number, not bit for bit.  One CTA; the matrix lives in global memory (column-major, P^2 doubles: it stays in L2).
-__device__ __forceinline__ double block_sum(double v, double* red, int tid, int T)
+// condition number, not bit for bit.
+//
+// Two instances of one kernel.  CLUSTER = true (the default where it fits, P <= 228): a thread-block CLUSTER of two CTAs
+// holds the columns alternately in shared memory (column j in CTA j & 1, P doubles each: 162 KB per CTA at P = 201 - the
+// 323 KB matrix fits no single SM), so that the 201 pivot searches, swaps and reflections never wait for L2.  What crosses
+// between the two SMs goes through distributed shared memory: each CTA publishes the biggest entry of its half of the
+// trailing block, the owner of column k publishes the Householder vector, a column transposition between the halves is an
+// exchange, the back substitution reads the peer's columns in place.  CLUSTER = false: one CTA, the matrix column-major in
+// global memory (it stays in L2).  The 201 steps are a chain of short phases, so the cost is barriers and reduction
+// latency: every reduction is a warp's (the pivot's 32 candidates, the norm of the pivot column), and the right-hand
+// sides travel as two more columns of the reflection - replicated in both CTAs, Q^T applied as the reflections are formed
+// (reflection k only touches rows >= k, so going past the rank changes nothing that is used).  Both instances form every
+// sum with the same lanes in the same order and agree bit for bit.
+namespace cg = cooperative_groups;
+
+// reflection k on one column (or right-hand side), by one warp (Householder.h applyHouseholderOnTheLeft)
+__device__ __forceinline__ void qr_reflect_column(double* cj, const double* v, int k, int P, double tau, int lane, double& tmp)
 {
-    v = warp_sum(v);
-    if ((tid & 31) == 0) red[tid >> 5] = v;
-    __syncthreads();
-    double t = 0.0;
-    for (int w = 0; w < (T >> 5); w++) t += red[w];
-    __syncthreads();
-    return t;
+    double d = 0.0;
+    for (int i = k + 1 + lane; i < P; i += 32) d += v[i] * cj[i];
+    d = warp_sum(d);
+    tmp = d + cj[k];
+    __syncwarp();
+    if (lane == 0) cj[k] = cj[k] - tau * tmp;
 }
 
+template <bool CLUSTER>
 __global__ void __launch_bounds__(1024, 1) solve_qr_kernel(SolveArgs a)
 {
     extern __shared__ __align__(16) double sm[];
+    const int me = CLUSTER ? (int)cg::this_cluster().block_rank() : 0;
     const int P = a.P, tid = threadIdx.x, T = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
-    double* O = sm;
-    double* cR = sm + P;        // right-hand sides, then Q^T b, then the triangular solution
-    double* cI = sm + 2 * P;
-    double* scal = sm + 3 * P;
-    double* hco = sm + 4 * P;   // Householder coefficients tau_k
-    double* xR = sm + 5 * P;
-    double* xI = sm + 6 * P;
-    double* red = sm + 7 * P;   // 64 doubles of reduction scratch
-    int* rowT = reinterpret_cast<int*>(red + 64);
+    constexpr int STEP = CLUSTER ? 2 : 1;   // distance between two columns of this CTA
+    const int ncl = CLUSTER ? (P + 1) >> 1 : 0;
+    double* Aloc = CLUSTER ? sm : a.L_global; // column j at Aloc + (j / STEP) P
+    double* O = sm + (size_t)ncl * P;
+    double* cR = O + P;                     // right-hand sides, then Q^T b, then the triangular solution
+    double* cI = cR + P;
+    double* scal = cI + P;
+    double* hco = scal + P;                 // Householder coefficients tau_k
+    double* xR = hco + P;
+    double* xI = xR + P;
+    double* diag = xI + P;                  // R_kk
+    double* vbuf = diag + P;                // essential part of the step's reflection (rows k + 1 ..)
+    double* xbuf = vbuf + P;                // column on its way to the peer
+    double* red = xbuf + P;                 // 64 doubles of reduction scratch
+    double* pub = red + 64;                 // [0..1] biggest entry found by CTA 0 / 1, [2..3] its rank (as double), [4] tau, [5] beta, [6] den
+    int* rowT = reinterpret_cast<int*>(pub + 8);
     int* colT = rowT + P;
     int* perm = colT + P;
-    __shared__ double s_best;
-    __shared__ int s_bi, s_bj, s_nonzero;
+    double* pub_peer = pub;
+    double* vbuf_peer = vbuf;
+    const double* xbuf_peer = xbuf;
+    const double* Aloc_peer = Aloc;
+    if (CLUSTER)
+    {
+        cg::cluster_group cluster = cg::this_cluster();
+        pub_peer = cluster.map_shared_rank(pub, me ^ 1);
+        vbuf_peer = cluster.map_shared_rank(vbuf, me ^ 1);
+        xbuf_peer = cluster.map_shared_rank(xbuf, me ^ 1);
+        Aloc_peer = cluster.map_shared_rank(Aloc, me ^ 1);
+    }
+    __shared__ int s_nonzero;
     __shared__ double s_maxpivot, s_biggest;
-    double* A = a.L_global;     // [P][P] column-major: A[i + j P]
 
     const double* S = a.est;
     const double* FR = S + (size_t)P * P;
@@ -327,39 +362,36 @@ __global__ void __launch_bounds__(1024, 1) solve_qr_kernel(SolveArgs a)
             cR[i] = -oer + ER * O[i];
             cI[i] = -oei;
         }
-        scal[i] = 1.0;
-    }
-    // matrix[i][j] = <O_i O_j> - <O_i><O_j> for j <= i, mirrored (:1529-1534)
-    for (int idx = tid; idx < P * P; idx += T)
-    {
-        const int i = idx % P, j = idx / P;
-        const int hi = i > j ? i : j, lo = i > j ? j : i;
-        A[idx] = S[(size_t)hi * P + lo] * inv - O[hi] * O[lo];
+        double sc = 1.0;
+        if (a.use_preconditioning) // :1767-1771; the diagonal entry is formed exactly as the matrix entry below
+        {
+            sc = sqrt(S[(size_t)i * P + i] * inv - O[i] * O[i]);
+            if (a.min_scaling > 0.0 && !(sc >= a.min_scaling)) sc = a.min_scaling;
+        }
+        scal[i] = sc;
     }
     __syncthreads();
-    if (a.use_preconditioning) // :1767-1771
+    // matrix[i][j] = <O_i O_j> - <O_i><O_j> for j <= i, mirrored (:1529-1534), scaled and regularised (:1684-1711)
+    const int nloc = CLUSTER ? ncl : P;
+    for (int idx = tid; idx < nloc * P; idx += T)
     {
-        for (int i = tid; i < P; i += T)
+        const int i = idx % P, j = STEP * (idx / P) + me;
+        if (j >= P) continue;
+        const int hi = i > j ? i : j, lo = i > j ? j : i;
+        double v = S[(size_t)hi * P + lo] * inv - O[hi] * O[lo];
+        if (a.use_preconditioning)
         {
-            double sc = sqrt(A[i + (size_t)i * P]);
-            if (a.min_scaling > 0.0 && !(sc >= a.min_scaling)) sc = a.min_scaling;
-            scal[i] = sc;
+            v = v / (scal[i] * scal[j]);
+            if (i == j) v += a.regularization; // RegularizeEquationSystem(matrix, 0.002)
         }
-        __syncthreads();
-        for (int idx = tid; idx < P * P; idx += T)
-        {
-            const int i = idx % P, j = idx / P;
-            A[idx] = A[idx] / (scal[i] * scal[j]);
-        }
+        Aloc[idx] = v;
+    }
+    if (a.use_preconditioning)
         for (int i = tid; i < P; i += T)
         {
             cR[i] = cR[i] / scal[i];
             cI[i] = cI[i] / scal[i];
         }
-        __syncthreads();
-        for (int i = tid; i < P; i += T) A[i + (size_t)i * P] += a.regularization; // RegularizeEquationSystem(matrix, 0.002)
-        __syncthreads();
-    }
     if (tid == 0)
     {
         s_nonzero = P;
@@ -373,20 +405,22 @@ __global__ void __launch_bounds__(1024, 1) solve_qr_kernel(SolveArgs a)
 
     for (int k = 0; k < P; k++)
     {
-        // ---- biggest |a_ij| of the trailing block, first in column-major order ----
+        // ---- biggest |a_ij| of the trailing block, first in column-major order (rank (j - k) m + (i - k)) ----
         const int m = P - k;
         double best = carry_best;
-        int bidx = carry_idx; // column-major rank within the block: (j - k) m + (i - k)
-        if (k == 0)           // later steps: found while the previous reflection was applied (one pass over the block less)
+        int bidx = carry_idx;
+        if (k == 0) // later steps: found while the previous reflection was applied (one pass over the block less)
         {
-            for (int idx = tid; idx < m * m; idx += T)
+            for (int idx = tid; idx < nloc * P; idx += T)
             {
-                const int i = k + idx % m, j = k + idx / m;
-                const double v = fabs(A[i + (size_t)j * P]);
-                if (v > best || (v == best && idx < bidx))
+                const int i = idx % P, j = STEP * (idx / P) + me;
+                if (j >= P) continue;
+                const double v = fabs(Aloc[idx]);
+                const int rk = j * P + i;
+                if (v > best || (v == best && rk < bidx))
                 {
                     best = v;
-                    bidx = idx;
+                    bidx = rk;
                 }
             }
         }
@@ -406,28 +440,48 @@ __global__ void __launch_bounds__(1024, 1) solve_qr_kernel(SolveArgs a)
             reinterpret_cast<int*>(red + 32)[warp] = bidx;
         }
         __syncthreads();
-        if (tid == 0)
+        if (warp == 0)
         {
-            double b = red[0];
-            int bi = reinterpret_cast<int*>(red + 32)[0];
-            for (int w = 1; w < nwarp; w++)
+            double b = lane < nwarp ? red[lane] : -1.0;
+            int bi = lane < nwarp ? reinterpret_cast<int*>(red + 32)[lane] : 0x7fffffff;
+            for (int o = 16; o > 0; o >>= 1)
             {
-                const double ob = red[w];
-                const int oi = reinterpret_cast<int*>(red + 32)[w];
+                const double ob = __shfl_xor_sync(FULL_MASK, b, o);
+                const int oi = __shfl_xor_sync(FULL_MASK, bi, o);
                 if (ob > b || (ob == b && oi < bi))
                 {
                     b = ob;
                     bi = oi;
                 }
             }
-            s_best = b;
-            s_bi = k + bi % m;
-            s_bj = k + bi / m;
-            if (k == 0) s_biggest = b;
+            if (lane == 0)
+            {
+                pub[me] = b;
+                pub[2 + me] = (double)bi;
+                if (CLUSTER)
+                {
+                    pub_peer[me] = b;
+                    pub_peer[2 + me] = (double)bi;
+                }
+            }
         }
-        __syncthreads();
-        // isMuchSmallerThan(biggest_in_corner, biggest, precision): |x| <= |y| * prec
-        if (s_best <= s_biggest * precision)
+        if (CLUSTER) cg::this_cluster().sync();
+        else __syncthreads();
+        double gbest = pub[0];
+        int gidx = (int)pub[2];
+        if (CLUSTER)
+        {
+            const double ob = pub[1];
+            const int oi = (int)pub[3];
+            if (ob > gbest || (ob == gbest && oi < gidx))
+            {
+                gbest = ob;
+                gidx = oi;
+            }
+        }
+        if (k == 0 && tid == 0) s_biggest = gbest;
+        const double biggest = k == 0 ? gbest : s_biggest;
+        if (gbest <= biggest * precision) // isMuchSmallerThan(biggest_in_corner, biggest, precision): |x| <= |y| * prec
         {
             if (tid == 0) s_nonzero = k;
             for (int i = k + tid; i < P; i += T)
@@ -439,79 +493,124 @@ __global__ void __launch_bounds__(1024, 1) solve_qr_kernel(SolveArgs a)
             __syncthreads();
             break;
         }
-        const int pr = s_bi, pc = s_bj;
+        const int pr = k + gidx % m, pc = k + gidx / m;
         if (tid == 0)
         {
             rowT[k] = pr;
             colT[k] = pc;
         }
-        if (pr != k) // m_qr.row(k).tail(cols-k).swap(m_qr.row(pr).tail(cols-k))
-            for (int j = k + tid; j < P; j += T)
+        if (pr != k) // m_qr.row(k).tail(cols-k).swap(m_qr.row(pr).tail(cols-k)), and the same rows of the right-hand sides
+        {
+            for (int j = k + (CLUSTER && (k & 1) != me ? 1 : 0) + STEP * tid; j < P; j += STEP * T)
             {
-                const double t = A[k + (size_t)j * P];
-                A[k + (size_t)j * P] = A[pr + (size_t)j * P];
-                A[pr + (size_t)j * P] = t;
+                double* cj = Aloc + (size_t)(j / STEP) * P;
+                const double t = cj[k];
+                cj[k] = cj[pr];
+                cj[pr] = t;
             }
+            if (tid == T - 1)
+            {
+                double t = cR[k]; cR[k] = cR[pr]; cR[pr] = t;
+                t = cI[k]; cI[k] = cI[pr]; cI[pr] = t;
+            }
+        }
         __syncthreads();
         if (pc != k) // m_qr.col(k).swap(m_qr.col(pc)): whole columns
-            for (int i = tid; i < P; i += T)
+        {
+            const bool own_k = !CLUSTER || (k & 1) == me, own_pc = !CLUSTER || (pc & 1) == me;
+            if (own_k && own_pc)
             {
-                const double t = A[i + (size_t)k * P];
-                A[i + (size_t)k * P] = A[i + (size_t)pc * P];
-                A[i + (size_t)pc * P] = t;
+                double* ck = Aloc + (size_t)(k / STEP) * P;
+                double* cp = Aloc + (size_t)(pc / STEP) * P;
+                for (int i = tid; i < P; i += T)
+                {
+                    const double t = ck[i];
+                    ck[i] = cp[i];
+                    cp[i] = t;
+                }
             }
-        __syncthreads();
-        // ---- makeHouseholderInPlace on A[k:, k] ----
-        double* colk = A + (size_t)k * P;
-        double part = 0.0;
-        for (int i = k + 1 + tid; i < P; i += T) part += colk[i] * colk[i];
-        const double tailSq = block_sum(part, red, tid, T);
-        const double c0 = colk[k];
-        double beta, tau;
-        if (tailSq <= 2.2250738585072014e-308)
-        {
-            tau = 0.0;
-            beta = c0;
-            for (int i = k + 1 + tid; i < P; i += T) colk[i] = 0.0;
+            else if (own_k != own_pc) // one column each: exchange through distributed shared memory
+            {
+                double* mine = Aloc + (size_t)((own_k ? k : pc) / STEP) * P;
+                for (int i = tid; i < P; i += T) xbuf[i] = mine[i];
+                cg::this_cluster().sync();
+                for (int i = tid; i < P; i += T) mine[i] = xbuf_peer[i];
+                cg::this_cluster().sync();
+            }
+            __syncthreads();
         }
-        else
+        // ---- makeHouseholderInPlace on column k (by its owner): norm of the tail by one warp ----
+        if (!CLUSTER || (k & 1) == me)
         {
-            beta = sqrt(c0 * c0 + tailSq);
-            if (c0 >= 0.0) beta = -beta;
-            const double den = c0 - beta;
-            for (int i = k + 1 + tid; i < P; i += T) colk[i] = colk[i] / den;
-            tau = (beta - c0) / beta;
+            double* colk = Aloc + (size_t)(k / STEP) * P;
+            if (warp == 0)
+            {
+                double part = 0.0;
+                for (int i = k + 1 + lane; i < P; i += 32) part += colk[i] * colk[i];
+                const double tailSq = warp_sum(part);
+                if (lane == 0)
+                {
+                    const double c0 = colk[k];
+                    double beta, tau, den;
+                    if (tailSq <= 2.2250738585072014e-308)
+                    {
+                        tau = 0.0;
+                        beta = c0;
+                        den = 0.0; // essential part := 0
+                    }
+                    else
+                    {
+                        beta = sqrt(c0 * c0 + tailSq);
+                        if (c0 >= 0.0) beta = -beta;
+                        den = c0 - beta;
+                        tau = (beta - c0) / beta;
+                    }
+                    pub[4] = tau;
+                    pub[5] = beta;
+                    pub[6] = den;
+                    if (CLUSTER)
+                    {
+                        pub_peer[4] = tau;
+                        pub_peer[5] = beta;
+                    }
+                }
+            }
+            __syncthreads();
+            const double den = pub[6];
+            for (int i = k + 1 + tid; i < P; i += T)
+            {
+                const double v = den == 0.0 ? 0.0 : colk[i] / den;
+                colk[i] = v;
+                vbuf[i] = v;
+                if (CLUSTER) vbuf_peer[i] = v;
+            }
+            if (tid == 0) colk[k] = pub[5];
         }
-        __syncthreads();
+        if (CLUSTER) cg::this_cluster().sync();
+        else __syncthreads();
+        const double tau = pub[4], beta = pub[5];
         if (tid == 0)
         {
-            colk[k] = beta;
             hco[k] = tau;
+            diag[k] = beta;
             if (fabs(beta) > s_maxpivot) s_maxpivot = fabs(beta);
         }
-        // ---- applyHouseholderOnTheLeft to A[k:, k+1:] (one warp per column); the new trailing block's biggest entry on the way ----
+        // ---- applyHouseholderOnTheLeft to the columns j > k of this CTA (one warp per column; the new trailing block's
+        //      biggest entry on the way) and to the two right-hand sides (the last two warps) ----
         carry_best = -1.0;
         carry_idx = 0x7fffffff;
         const int m1 = P - k - 1;
-        for (int j = k + 1 + warp; j < P; j += nwarp)
+        for (int j = k + 1 + (CLUSTER && (k & 1) == me ? 1 : 0) + STEP * warp; j < P; j += STEP * nwarp)
         {
-            double* cj = A + (size_t)j * P;
+            double* cj = Aloc + (size_t)(j / STEP) * P;
             double tmp = 0.0;
-            if (tau != 0.0)
-            {
-                double d = 0.0;
-                for (int i = k + 1 + lane; i < P; i += 32) d += colk[i] * cj[i];
-                d = warp_sum(d);
-                tmp = d + cj[k];
-                __syncwarp();
-                if (lane == 0) cj[k] = cj[k] - tau * tmp;
-            }
+            if (tau != 0.0) qr_reflect_column(cj, vbuf, k, P, tau, lane, tmp);
             for (int i = k + 1 + lane; i < P; i += 32)
             {
                 double v = cj[i];
                 if (tau != 0.0)
                 {
-                    v = v - (tau * colk[i]) * tmp;
+                    v = v - (tau * vbuf[i]) * tmp;
                     cj[i] = v;
                 }
                 const double av = fabs(v);
@@ -523,14 +622,22 @@ __global__ void __launch_bounds__(1024, 1) solve_qr_kernel(SolveArgs a)
                 }
             }
         }
+        if (tau != 0.0 && warp >= nwarp - 2) // Q^T on the right-hand sides, step k (FullPivHouseholderQR::_solve_impl)
+        {
+            double* c = warp == nwarp - 1 ? cR : cI;
+            double tmp;
+            qr_reflect_column(c, vbuf, k, P, tau, lane, tmp);
+            for (int i = k + 1 + lane; i < P; i += 32) c[i] = c[i] - (tau * vbuf[i]) * tmp;
+        }
         __syncthreads();
     }
 
-    // ---- rank, Q^T b, back substitution, permutation (FullPivHouseholderQR::_solve_impl) ----
+    // ---- rank, back substitution, permutation ----
+    __syncthreads();
     const int nonzero = s_nonzero;
     const double premult = fabs(s_maxpivot) * (2.220446049250313e-16 * (double)P);
     int rank = 0;
-    for (int i = 0; i < nonzero; i++) rank += (fabs(A[i + (size_t)i * P]) > premult) ? 1 : 0; // (every thread counts alike)
+    for (int i = 0; i < nonzero; i++) rank += (fabs(diag[i]) > premult) ? 1 : 0; // (every thread counts alike)
     // m_cols_permutation = product of the column transpositions (applyTranspositionOnTheRight)
     if (tid == 0)
     {
@@ -542,65 +649,31 @@ __global__ void __launch_bounds__(1024, 1) solve_qr_kernel(SolveArgs a)
             perm[colT[k]] = t;
         }
     }
-    __syncthreads();
-    for (int k = 0; k < rank; k++)
-    {
-        if (tid == 0)
-        {
-            const int r = rowT[k];
-            double t = cR[k]; cR[k] = cR[r]; cR[r] = t;
-            t = cI[k]; cI[k] = cI[r]; cI[r] = t;
-        }
-        __syncthreads();
-        const double tau = hco[k];
-        if (tau != 0.0 && P - k > 1)
-        {
-            const double* colk = A + (size_t)k * P;
-            double dR = 0.0, dI = 0.0;
-            for (int i = k + 1 + tid; i < P; i += T)
-            {
-                dR += colk[i] * cR[i];
-                dI += colk[i] * cI[i];
-            }
-            const double tR = block_sum(dR, red, tid, T) + cR[k];
-            const double tI = block_sum(dI, red, tid, T) + cI[k];
-            __syncthreads();
-            if (tid == 0)
-            {
-                cR[k] = cR[k] - tau * tR;
-                cI[k] = cI[k] - tau * tI;
-            }
-            for (int i = k + 1 + tid; i < P; i += T)
-            {
-                cR[i] = cR[i] - (tau * colk[i]) * tR;
-                cI[i] = cI[i] - (tau * colk[i]) * tI;
-            }
-            __syncthreads();
-        }
-        else if (P - k == 1 && tid == 0) // rows() == 1: *this *= 1 - tau
-        {
-            cR[k] = cR[k] * (1.0 - tau);
-            cI[k] = cI[k] * (1.0 - tau);
-        }
-        __syncthreads();
-    }
+    if (CLUSTER) cg::this_cluster().sync(); // both halves complete before either CTA reads the other's columns
+    else __syncthreads();
     // upper-triangular solve R[0:rank, 0:rank] y = c[0:rank] (column-oriented back substitution)
     for (int i = rank - 1; i >= 0; i--)
     {
         if (tid == 0)
         {
-            cR[i] = cR[i] / A[i + (size_t)i * P];
-            cI[i] = cI[i] / A[i + (size_t)i * P];
+            cR[i] = cR[i] / diag[i];
+            cI[i] = cI[i] / diag[i];
         }
         __syncthreads();
         const double yR = cR[i], yI = cI[i];
+        const double* ci = ((!CLUSTER || (i & 1) == me) ? Aloc : Aloc_peer) + (size_t)(i / STEP) * P;
         for (int r = tid; r < i; r += T)
         {
-            const double rij = A[r + (size_t)i * P];
+            const double rij = ci[r];
             cR[r] = cR[r] - rij * yR;
             cI[r] = cI[r] - rij * yI;
         }
         __syncthreads();
+    }
+    if (CLUSTER)
+    {
+        cg::this_cluster().sync(); // no CTA leaves while its shared memory may still be read
+        if (me != 0) return;
     }
     for (int i = tid; i < P; i += T)
     {
@@ -650,14 +723,33 @@ __global__ void __launch_bounds__(1024, 1) solve_qr_kernel(SolveArgs a)
     }
 }
 
+static size_t solve_qr_smem(int P, bool cluster)
+{
+    const size_t ncl = cluster ? ((size_t)P + 1) / 2 : 0;
+    return (ncl * P + 11 * (size_t)P + 64 + 8) * sizeof(double) + 3 * (size_t)P * sizeof(int);
+}
+
 cudaError_t launch_solve_qr(SolveArgs a, cudaStream_t st)
 {
     if (a.P < 1 || a.P > 1024 || !a.L_global) return cudaErrorInvalidValue;
-    const size_t smem = (7 * (size_t)a.P + 64) * sizeof(double) + 3 * (size_t)a.P * sizeof(int);
-    cudaError_t e = cudaFuncSetAttribute(solve_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool cluster = !a.force_global && a.P >= 2 && solve_qr_smem(a.P, true) + 1024 <= (size_t)227 * 1024;
+    const size_t smem = solve_qr_smem(a.P, cluster);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cluster ? 2 : 1);
+    cfg.blockDim = dim3(1024);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = cluster ? 1 : 0;
+    void (*fn)(SolveArgs) = cluster ? solve_qr_kernel<true> : solve_qr_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    solve_qr_kernel<<<1, 1024, smem, st>>>(a);
-    return cudaGetLastError();
+    return cudaLaunchKernelEx(&cfg, fn, a);
 }
 
 size_t solve_smem_bytes(int P, bool l_in_smem)

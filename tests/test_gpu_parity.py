@@ -1263,6 +1263,12 @@ def test_device_qr_solver_matches_eigen(capi, golden, name):
     pscale = max(abs(float(g["first_phiDotR"])), abs(float(g["first_phiDotI"])))
     assert abs(d["phi_dot_r"] - float(g["first_phiDotR"])) < tol * pscale and abs(d["phi_dot_i"] - float(g["first_phiDotI"])) < tol * pscale
     assert abs(np.sum(d["u_dot_r"] * (1.0 if not pre else 0.0))) < 1e-9 * scale * len(d["u_dot_r"])   # mean subtracted (unscaled case)
+    # the two-CTA cluster kernel (matrix in distributed shared memory, the default where it fits) and the one-CTA kernel with
+    # the matrix in global memory form every sum in the same order: bit-identical
+    d1 = h.solve_fixed(est, imaginary_time=int(g["IMAGINARY_TIME"]), use_preconditioning=pre, solver_type=1, force_global=True)
+    for key in ("u_dot_r", "u_dot_i"):
+        assert np.array_equal(d[key], d1[key]), (key, np.max(np.abs(d[key] - d1[key])))
+    assert d["phi_dot_r"] == d1["phi_dot_r"] and d["phi_dot_i"] == d1["phi_dot_i"]
     h.close()
 
 
