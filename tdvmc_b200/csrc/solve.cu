@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(1024, 1) solve_qr_kernel(SolveArgs a)
         Aloc_peer = cluster.map_shared_rank(Aloc, me ^ 1);
     }
     __shared__ int s_nonzero;
-    __shared__ double s_maxpivot, s_biggest;
+    __shared__ double s_maxpivot;
 
     const double* S = a.est;
     const double* FR = S + (size_t)P * P;
@@ -396,10 +396,11 @@ __global__ void __launch_bounds__(1024, 1) solve_qr_kernel(SolveArgs a)
     {
         s_nonzero = P;
         s_maxpivot = 0.0;
-        s_biggest = 0.0;
     }
-    __syncthreads();
+    if (CLUSTER) cg::this_cluster().sync(); // (also: the peer has started, its shared memory may be written from here on)
+    else __syncthreads();
     const double precision = 2.220446049250313e-16 * (double)P; // NumTraits<double>::epsilon() * size
+    double biggest = 0.0;                                       // the first pivot (every thread keeps its copy)
     double carry_best = -1.0;
     int carry_idx = 0x7fffffff;
 
@@ -479,8 +480,7 @@ __global__ void __launch_bounds__(1024, 1) solve_qr_kernel(SolveArgs a)
                 gidx = oi;
             }
         }
-        if (k == 0 && tid == 0) s_biggest = gbest;
-        const double biggest = k == 0 ? gbest : s_biggest;
+        if (k == 0) biggest = gbest;
         if (gbest <= biggest * precision) // isMuchSmallerThan(biggest_in_corner, biggest, precision): |x| <= |y| * prec
         {
             if (tid == 0) s_nonzero = k;
