@@ -15,7 +15,9 @@
 namespace tdvmc
 {
 
-constexpr int kTabWarps = 8;
+// Warps per block: one block per SM with as many row slabs (6.5 KB each at K = 203) as fit beside the tables - 24 at N = 343
+// (3.31 against 3.64 ms per 1024 configurations with two blocks of 8), 16 at N = 1728
+constexpr int kTabWarpsMax = 24;
 
 struct TabSmem
 {
@@ -24,11 +26,11 @@ struct TabSmem
     double* px;
     double* py;
     double* pz;
-    double* acc; // [kTabWarps][K][4]
+    double* acc; // [warps][K][4]
     unsigned short* lut;
 };
 
-__host__ __device__ inline size_t tab_smem_layout(const SysDev& s, TabSmem* out, unsigned char* base)
+__host__ __device__ inline size_t tab_smem_layout(const SysDev& s, int nwarps, TabSmem* out, unsigned char* base)
 {
     size_t off = 0;
     const int Npad = (s.N + 1) & ~1;
@@ -38,7 +40,7 @@ __host__ __device__ inline size_t tab_smem_layout(const SysDev& s, TabSmem* out,
     m.px = reinterpret_cast<double*>(base + off);    off += (size_t)Npad * 8;
     m.py = reinterpret_cast<double*>(base + off);    off += (size_t)Npad * 8;
     m.pz = reinterpret_cast<double*>(base + off);    off += (size_t)Npad * 8;
-    m.acc = reinterpret_cast<double*>(base + off);   off += (size_t)kTabWarps * s.K * 4 * 8;
+    m.acc = reinterpret_cast<double*>(base + off);   off += (size_t)nwarps * s.K * 4 * 8;
     m.lut = reinterpret_cast<unsigned short*>(base + off);
     off += ((size_t)s.ncell * sizeof(unsigned short) + 15) & ~(size_t)15;
     if (out) *out = m;
@@ -46,15 +48,16 @@ __host__ __device__ inline size_t tab_smem_layout(const SysDev& s, TabSmem* out,
 }
 
 template <bool REFLECT>
-__global__ void __launch_bounds__(kTabWarps * 32) tables_kernel(TableArgs a, int particles_per_block)
+__global__ void __launch_bounds__(kTabWarpsMax * 32) tables_kernel(TableArgs a, int particles_per_block)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SysDev& s = a.s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cfg = blockIdx.x;
     const int N = s.N, K = s.K;
+    const int nwarps = blockDim.x >> 5;
     TabSmem m;
-    tab_smem_layout(s, &m, smem_raw);
+    tab_smem_layout(s, nwarps, &m, smem_raw);
 
     for (int i = tid; i < K + 4; i += blockDim.x) m.knots[i] = s.knots[i];
     for (int i = tid; i < s.nbins * kRecStride; i += blockDim.x) m.rec[i] = s.rec[i];
@@ -66,7 +69,7 @@ __global__ void __launch_bounds__(kTabWarps * 32) tables_kernel(TableArgs a, int
         m.py[i] = gpos[s.Np + i];
         m.pz[i] = gpos[2 * s.Np + i];
     }
-    for (int i = tid; i < kTabWarps * K * 4; i += blockDim.x) m.acc[i] = 0.0;
+    for (int i = tid; i < nwarps * K * 4; i += blockDim.x) m.acc[i] = 0.0;
     __syncthreads();
 
     double* acc = m.acc + (size_t)warp * K * 4;
@@ -75,7 +78,7 @@ __global__ void __launch_bounds__(kTabWarps * 32) tables_kernel(TableArgs a, int
     const int n_end = min(N, n_begin + particles_per_block);
     int vcount = 0;
 
-    for (int n = n_begin + warp; n < n_end; n += kTabWarps)
+    for (int n = n_begin + warp; n < n_end; n += nwarps)
     {
         const double xn = m.px[n], yn = m.py[n], zn = m.pz[n];
         for (int i0 = 0; i0 < N; i0 += 32)
@@ -165,10 +168,12 @@ __global__ void __launch_bounds__(kTabWarps * 32) tables_kernel(TableArgs a, int
 cudaError_t launch_tables(const TableArgs& a, cudaStream_t st)
 {
     if (a.n_cfg <= 0) return cudaSuccess;
-    const size_t smem = tab_smem_layout(a.s, nullptr, nullptr);
+    int warps = kTabWarpsMax;
+    while (warps > 8 && tab_smem_layout(a.s, warps, nullptr, nullptr) + 1024 > (size_t)227 * 1024) warps -= 8;
+    const size_t smem = tab_smem_layout(a.s, warps, nullptr, nullptr);
     // split the particles of one configuration over several blocks when there are few configurations
     int chunks = 1;
-    if (a.n_cfg < 296) chunks = min((a.s.N + kTabWarps - 1) / kTabWarps, (296 + a.n_cfg - 1) / a.n_cfg);
+    if (a.n_cfg < 148) chunks = min((a.s.N + warps - 1) / warps, (148 + a.n_cfg - 1) / a.n_cfg);
     const int ppb = (a.s.N + chunks - 1) / chunks;
     dim3 grid(a.n_cfg, (a.s.N + ppb - 1) / ppb);
     cudaError_t e = cudaMemsetAsync(a.v_int, 0, sizeof(double) * a.n_cfg, st);
@@ -177,13 +182,13 @@ cudaError_t launch_tables(const TableArgs& a, cudaStream_t st)
     {
         e = cudaFuncSetAttribute(tables_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        tables_kernel<true><<<grid, kTabWarps * 32, smem, st>>>(a, ppb);
+        tables_kernel<true><<<grid, warps * 32, smem, st>>>(a, ppb);
     }
     else
     {
         e = cudaFuncSetAttribute(tables_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        tables_kernel<false><<<grid, kTabWarps * 32, smem, st>>>(a, ppb);
+        tables_kernel<false><<<grid, warps * 32, smem, st>>>(a, ppb);
     }
     return cudaGetLastError();
 }
