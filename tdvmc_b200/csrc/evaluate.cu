@@ -73,8 +73,8 @@ struct EvalSmem2
 {
     double* knots;
     double* wtab;  // two copies of [nbins][4 pieces][4 coefficients]; the second starts 16 bytes past a multiple of 128
-    double* utR;
-    double* utI;
+    double2* ut;   // (u~R_k, u~I_k), `ucopies` interleaved replicas: entry k of replica c at ut[k * ucopies + c]
+    int ucopies;   // 8 where it fits (lane l reads replica l & 7: the eight lanes of a quarter-warp never collide), else 1
     double* px;
     double* py;
     double* pz;
@@ -86,7 +86,8 @@ struct EvalSmem2
 };
 
 
-__host__ __device__ inline size_t eval_smem_layout2(const SysDev& s, int nwarps, bool rot, bool gmem, EvalSmem2* out, unsigned char* base)
+__host__ __device__ inline size_t eval_smem_layout2(const SysDev& s, int nwarps, bool rot, bool gmem, EvalSmem2* out, unsigned char* base,
+                                                    int ucopies = 1)
 {
     SmemCarver c = { base, 0 };
     const int Npad = ((s.N + 31) >> 5) << 5;
@@ -94,8 +95,8 @@ __host__ __device__ inline size_t eval_smem_layout2(const SysDev& s, int nwarps,
     // rot: two copies of 128-byte records on 128-byte phases 0 and 16; else one copy of the 144-byte records
     m.wtab = c.take(rot ? (size_t)2 * s.nbins * 16 + 2 : (size_t)s.nbins * kRecStride);
     m.knots = c.take(s.K + 4);
-    m.utR = c.take(s.K);
-    m.utI = c.take(s.K);
+    m.ucopies = ucopies;
+    m.ut = reinterpret_cast<double2*>(c.take((size_t)2 * s.K * ucopies));
     // gmem: positions and forces of the configuration live in a per-block slab of global memory (L2) instead - systems too
     // large for one SM's shared memory (N = 8000 of config/BosonsBulk3D.config as shipped: 576 KB)
     m.px = gmem ? nullptr : c.take(Npad);
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kerne
     const int NT = (N + 31) >> 5; // tiles of 32 particles
 
     EvalSmem2 m;
-    eval_smem_layout2(s, nwarps, ROT, GMEM, &m, smem_raw);
+    eval_smem_layout2(s, nwarps, ROT, GMEM, &m, smem_raw, a.ucopies);
     if (GMEM)
     {
         double* slab = a.scratch + (size_t)blockIdx.x * 9 * NT * 32; // [px | py | pz | 6 force rows], padded to whole tiles
@@ -260,8 +261,8 @@ __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kerne
     for (int i = tid; i < K + 4; i += blockDim.x) m.knots[i] = s.knots[i];
     for (int i = tid; i < K; i += blockDim.x)
     {
-        m.utR[i] = s.utR[i];
-        m.utI[i] = s.utI[i];
+        const double2 u = make_double2(s.utR[i], s.utI[i]);
+        for (int c = 0; c < m.ucopies; c++) m.ut[(size_t)i * m.ucopies + c] = u;
     }
     for (int i = tid; i < s.ncell; i += blockDim.x) m.lut[i] = s.lut[i];
     // GMEM: one block per SM walks the configurations (its slab is reused); otherwise one block per configuration
@@ -287,6 +288,8 @@ __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kerne
     const int p0 = ROT ? (lane >> 1) & 3 : 0;
     const int wstride = ROT ? 16 : kRecStride;
     const double* wmine = ((ROT && (lane & 1)) ? wtab1 : m.wtab) - (size_t)s.first_bin * wstride;
+    const int ucop = m.ucopies;
+    const double2* umine = m.ut + (lane & (ucop - 1));
     const double rmax = s.rmax;
     const double pot_a = s.pot_a;
     const int NP32 = NT * 32;
@@ -374,7 +377,8 @@ __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kerne
                             const double2 w23 = *reinterpret_cast<const double2*>(w + p * 4 + 2);
                             const double d1 = w01.y + 2.0 * w23.x * r + 3.0 * w23.y * r2; // BosonsBulk.cpp:299
                             const double d2 = 2.0 * w23.x + 6.0 * w23.y * r;              // BosonsBulk.cpp:301
-                            const double uRk = m.utR[bin - p], uIk = m.utI[bin - p];
+                            const double2 uk = umine[(bin - p) * ucop];
+                            const double uRk = uk.x, uIk = uk.y;
                             const double t2 = d2 + f2 * d1;
                             gR = fma(uRk, d1, gR);
                             gI = fma(uIk, d1, gI);
@@ -509,9 +513,20 @@ int evaluate_threads(const SysDev& s)
     return best * 32;
 }
 
+// Replicas of the u~ table: eight (lane l reads replica l & 7, so the lanes of a quarter-warp never collide in an LDS.128)
+// when the block still fits - twice per SM for the 12-warp blocks - else one
+static int evaluate_ucopies(const SysDev& s)
+{
+    int want = 8;
+    if (const char* e = getenv("TDVMC_EVAL_UCOPIES")) want = atoi(e) >= 8 ? 8 : 1; // tuning knob
+    if (want == 1) return 1;
+    const size_t bytes = eval_smem_layout2(s, evaluate_threads(s) / 32, evaluate_rotated(s), evaluate_gmem(s), nullptr, nullptr, 8) + 1024;
+    return evaluate_blocks_per_sm(s) * bytes <= kEvalSmemLimit ? 8 : 1;
+}
+
 size_t evaluate_smem_bytes(const SysDev& s)
 {
-    return eval_layout_bytes(s, evaluate_threads(s) / 32);
+    return eval_smem_layout2(s, evaluate_threads(s) / 32, evaluate_rotated(s), evaluate_gmem(s), nullptr, nullptr, evaluate_ucopies(s));
 }
 
 size_t evaluate_scratch_doubles(const SysDev& s, int sm_count)
@@ -530,9 +545,11 @@ static cudaError_t launch_eval_kernel(KernelT kernel, const EvalArgs& a, int thr
     return cudaGetLastError();
 }
 
-cudaError_t launch_evaluate(const EvalArgs& a, cudaStream_t st)
+cudaError_t launch_evaluate(const EvalArgs& a_in, cudaStream_t st)
 {
-    if (a.n_cfg <= 0) return cudaSuccess;
+    if (a_in.n_cfg <= 0) return cudaSuccess;
+    EvalArgs a = a_in;
+    a.ucopies = evaluate_ucopies(a.s);
     const int threads = evaluate_threads(a.s);
     const size_t smem = evaluate_smem_bytes(a.s);
     const bool refl = a.s.pair_rule == 1;

@@ -58,6 +58,7 @@ struct EvalArgs
     double* ss_out;         // [n_cfg][K] or null
     double* outer_out;      // [n_cfg] or null
     double* scratch;        // large systems only: [blocks][9][NT*32] positions + forces of the configuration in flight
+    int ucopies;            // set by launch_evaluate: shared-memory replicas of the u~ table (8 where they fit)
 };
 cudaError_t launch_evaluate(const EvalArgs& a, cudaStream_t st);
 int evaluate_blocks_per_sm(const SysDev& s);   // 2 (12-warp blocks) or 1 (24-warp blocks, large N)
