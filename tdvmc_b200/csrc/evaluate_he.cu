@@ -43,7 +43,7 @@ __device__ __forceinline__ double he_pair_potential(const SysDev& s, double r)
     return 4.0 * eps * s6 * (s6 - 1.0);
 }
 
-__global__ void __launch_bounds__(256) evaluate_he_kernel(EvalArgs a)
+__global__ void __launch_bounds__(256, 4) evaluate_he_kernel(EvalArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SysDev& s = a.s;
@@ -331,7 +331,7 @@ __device__ __forceinline__ double he_rcp(double r)
     return y;
 }
 
-__global__ void __launch_bounds__(256) evaluate_he_tile_kernel(EvalArgs a)
+__global__ void __launch_bounds__(256, 4) evaluate_he_tile_kernel(EvalArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SysDev& s = a.s;

@@ -6,7 +6,10 @@
 namespace tdvmc
 {
 
-constexpr int kSweepMaxThreads = 704;      // packed small systems (8 / 16 lanes per walker): up to 22 warps, 93 registers
+#ifndef TDVMC_SWEEP_SMALL_THREADS
+#define TDVMC_SWEEP_SMALL_THREADS 704
+#endif
+constexpr int kSweepMaxThreads = TDVMC_SWEEP_SMALL_THREADS;      // packed small systems (8 / 16 lanes per walker): up to 22 warps, 93 registers
 #ifndef TDVMC_SWEEP_THREADS
 #define TDVMC_SWEEP_THREADS 640
 #endif
