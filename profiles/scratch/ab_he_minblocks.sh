@@ -1,5 +1,5 @@
 # one-off: evaluate_he_tile_kernel with __launch_bounds__(256, 1..4) on config 2 (HeBulk N = 64)
-for mb in 704 1024; do
+for mb in 1 12 16; do
   echo "minblocks=$mb"; python - <<PY
 import sys, json; sys.path.insert(0,'.'); sys.path.insert(0,'profiles')
 from tdvmc_b200 import capi

@@ -193,19 +193,51 @@ __global__ void acc_reduce_kernel(const double* partial, int n_cta, int ldc, dou
     G[idx] = t;
 }
 
-__global__ void other_partial_kernel(const double* other, long long M, int n_other, int n_blk, double* part)
+// Column sums of the otherExpectationValues rows (HeDrop / the mixture carry ~400 histogram columns per sample: 9 GB per pass
+// of 2.8 M samples).  grid (n_blk, strips of 32 columns); block b sums rows [b M / n_blk, (b + 1) M / n_blk): a warp reads 32
+// consecutive columns of a row (256 contiguous bytes), the eight warps of the block take the rows in turn with four
+// independent accumulators each, and the eight partial sums meet in shared memory in a fixed order (deterministic).
+// (r02: the first version gave every thread one column and one load in flight - 0.46 TB/s, 19 ms of config 5's 66 ms pass.)
+__global__ void __launch_bounds__(256) other_partial_kernel(const double* __restrict__ other, long long M, int n_other, int n_blk, double* part)
 {
-    // block b sums rows [b*M/n_blk, (b+1)*M/n_blk) for every column; columns across threads (coalesced)
+    __shared__ double red[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.y * 32 + lane;
     const long long r0 = (M * blockIdx.x) / n_blk, r1 = (M * (blockIdx.x + 1)) / n_blk;
-    for (int c = threadIdx.x; c < n_other; c += blockDim.x)
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+    if (c < n_other)
+    {
+        const double* col = other + c;
+        long long r = r0 + warp;
+        for (; r + 24 < r1; r += 32)
+        {
+            t0 += __ldcs(col + (size_t)r * n_other);
+            t1 += __ldcs(col + (size_t)(r + 8) * n_other);
+            t2 += __ldcs(col + (size_t)(r + 16) * n_other);
+            t3 += __ldcs(col + (size_t)(r + 24) * n_other);
+        }
+        for (; r < r1; r += 8) t0 += __ldcs(col + (size_t)r * n_other);
+    }
+    red[warp][lane] = (t0 + t1) + (t2 + t3);
+    __syncthreads();
+    if (warp == 0 && c < n_other)
     {
         double t = 0.0;
-        for (long long r = r0; r < r1; r++) t += other[(size_t)r * n_other + c];
+        for (int w = 0; w < 8; w++) t += red[w][lane];
         part[(size_t)blockIdx.x * n_other + c] = t;
     }
 }
 
-__global__ void pack_est_kernel(AccFinishArgs a, const double* G, const double* other_part, int n_blk)
+// total of the per-walker acceptance counters (integers: the order does not matter)
+__global__ void __launch_bounds__(256) accepted_sum_kernel(const unsigned long long* __restrict__ accepted, int W, unsigned long long* total)
+{
+    unsigned long long t = 0;
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < W; w += gridDim.x * blockDim.x) t += accepted[w];
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL_MASK, t, o);
+    if ((threadIdx.x & 31) == 0 && t) atomicAdd(total, t);
+}
+
+__global__ void pack_est_kernel(AccFinishArgs a, const double* G, const double* other_part, int n_blk, const unsigned long long* accepted_total)
 {
     const int P = a.P, ldc = a.ldc;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -238,15 +270,13 @@ __global__ void pack_est_kernel(AccFinishArgs a, const double* G, const double* 
     {
         E[0] = G[(size_t)P * ldc + P + 2];
         E[1] = G[(size_t)(P + 1) * ldc + P + 2];
-        unsigned long long acc = 0;
-        for (int w = 0; w < a.W; w++) acc += a.accepted[w];
-        cnt[0] = (double)acc;
+        cnt[0] = (double)*accepted_total; // (r02: a one-thread loop over the walkers here cost 6.5 ms at the 175 k walkers of config 1)
         cnt[1] = a.n_trials;
         cnt[2] = G[(size_t)(P + 2) * ldc + P + 2]; // sum of 1*1 over the samples = M
     }
 }
 
-// scratch layout behind a.partial: [n_cta][ldc*ldc] partials | G[ldc*ldc] | other_part[n_blk][n_other]
+// scratch layout behind a.partial: [n_cta][ldc*ldc] partials | G[ldc*ldc] | other_part[148][n_other] | acceptance total
 cudaError_t launch_acc_finish(const AccFinishArgs& a, cudaStream_t st)
 {
     const size_t gsz = (size_t)a.ldc * a.ldc;
@@ -256,8 +286,12 @@ cudaError_t launch_acc_finish(const AccFinishArgs& a, cudaStream_t st)
     if (n_blk > 148) n_blk = 148;
     if (n_blk < 1) n_blk = 1;
     acc_reduce_kernel<<<(int)((gsz + 255) / 256), 256, 0, st>>>(a.partial, a.n_cta, a.ldc, G);
-    other_partial_kernel<<<n_blk, 256, 0, st>>>(a.other, a.M, a.n_other, n_blk, other_part);
-    pack_est_kernel<<<64, 256, 0, st>>>(a, G, other_part, n_blk);
+    other_partial_kernel<<<dim3(n_blk, a.n_other > 32 ? (a.n_other + 31) / 32 : 1), 256, 0, st>>>(a.other, a.M, a.n_other, n_blk, other_part);
+    unsigned long long* accepted_total = reinterpret_cast<unsigned long long*>(other_part + (size_t)148 * a.n_other);
+    cudaError_t e = cudaMemsetAsync(accepted_total, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    accepted_sum_kernel<<<64, 256, 0, st>>>(a.accepted, a.W, accepted_total);
+    pack_est_kernel<<<64, 256, 0, st>>>(a, G, other_part, n_blk, accepted_total);
     return cudaGetLastError();
 }
 

@@ -857,7 +857,7 @@ int tdvmc_gpu_create(const tdvmc_system_desc* sd, const tdvmc_ensemble_desc* ed,
     const long long rows = (long long)h->W * h->max_samples;
     h->rows_cap = ((rows + kAccChunkRows - 1) / kAccChunkRows) * kAccChunkRows;
     h->est_len = (size_t)h->P * h->P + 3 * (size_t)h->P + 2 + h->n_other + 3;
-    const size_t scratch = (size_t)h->sm_count * h->ldc * h->ldc + (size_t)h->ldc * h->ldc + (size_t)148 * h->n_other;
+    const size_t scratch = (size_t)h->sm_count * h->ldc * h->ldc + (size_t)h->ldc * h->ldc + (size_t)148 * h->n_other + 2; // (+ the acceptance total)
     cudaError_t e = cudaSuccess;
     auto A = [&](cudaError_t x) {
         if (e == cudaSuccess) e = x;
@@ -1164,7 +1164,7 @@ static int do_accumulate(tdvmc_gpu_handle* h, const double* A, const double* oth
         CK(launch_accumulate(a, h->stream));
     }
     {
-        Timed t(h, TDVMC_KERNEL_OTHER, 3);
+        Timed t(h, TDVMC_KERNEL_OTHER, 4);
         CK(launch_acc_finish(f, h->stream));
     }
     h->rows_used = M;

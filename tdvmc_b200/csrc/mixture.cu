@@ -291,7 +291,7 @@ __device__ __forceinline__ double mix_pair_u(const SysDev& s, int t, double r)
 }
 
 template <int ORDER>
-__global__ void __launch_bounds__(64) sweep_mix_kernel(SweepArgs a)
+__global__ void __launch_bounds__(64, 16) sweep_mix_kernel(SweepArgs a)
 {
     const SysDev& s = a.s;
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
