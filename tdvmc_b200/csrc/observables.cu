@@ -203,14 +203,20 @@ __global__ void __launch_bounds__(128) cluster_observables_kernel(ClusterObsArgs
     }
 }
 
-__global__ void sum_rows_kernel(const double* rows, int n, double* out)
+// sum of n doubles in a fixed order (deterministic): 256 strided partial sums, then a fixed tree
+__global__ void __launch_bounds__(256) sum_rows_kernel(const double* rows, int n, double* out)
 {
-    if (blockIdx.x == 0 && threadIdx.x == 0)
+    __shared__ double red[256];
+    double t = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) t += rows[i];
+    red[threadIdx.x] = t;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1)
     {
-        double t = 0.0;
-        for (int i = 0; i < n; i++) t += rows[i];
-        *out = t;
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
     }
+    if (threadIdx.x == 0) *out = red[0];
 }
 
 cudaError_t launch_cluster_observables(const ClusterObsArgs& a, cudaStream_t st)
@@ -225,7 +231,7 @@ cudaError_t launch_cluster_observables(const ClusterObsArgs& a, cudaStream_t st)
 
 cudaError_t launch_sum_rows(const double* rows, int n, double* out, cudaStream_t st)
 {
-    sum_rows_kernel<<<1, 32, 0, st>>>(rows, n, out);
+    sum_rows_kernel<<<1, 256, 0, st>>>(rows, n, out);
     return cudaGetLastError();
 }
 
