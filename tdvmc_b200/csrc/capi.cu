@@ -122,6 +122,7 @@ struct tdvmc_gpu_handle
     double phiR = 0, phiI = 0, time = 0;
     bool params_set = false;
     int first_bin = 3, nbins = 0, ncell = 0, uniform = 0;
+    double bin_guard = 0.0; // see SysDev::bin_guard
     double h = 0;
 
     // ensemble
@@ -395,6 +396,15 @@ int build_static_tables(tdvmc_gpu_handle* h)
     }
     h->uniform = uni ? 1 : 0;
     h->h = h0;
+    h->bin_guard = 0.0;
+    if (uni)
+    {
+        // largest deviation of a stored knot from the exact grid, in units of the spacing (the reference's knots are
+        // (i * L / 2) / (P - 1), BosonsBulk.cpp:61-67: a few ulp)
+        double dev = 0.0;
+        for (int j = fb; j <= K; j++) dev = std::max(dev, std::fabs(t[j] - (j - fb) * h0) / h0);
+        if (dev < 1e-7) h->bin_guard = 2.0 * dev + 1e-10;
+    }
     h->ncell = uni ? h->nbins : (int)std::min(8192.0, std::ceil(2.0 * rmax / min_sp));
     if (h->ncell < 1) h->ncell = 1;
     std::vector<unsigned short> lut(h->ncell);
@@ -650,6 +660,7 @@ SysDev tdvmc_gpu_handle::sysdev() const
     s.L = L; s.Linv = L > 0.0 ? 1.0 / L : 0.0; s.Lhalf = L / 2.0; // src/TDVMC.cpp:535-536
     s.kind = kind; s.n_ext = n_ext; s.gr_bins = gr_bins;
     s.dim = dim; s.dm1 = dim - 1.0;
+    s.bin_guard = bin_guard;
     s.periodic = periodic; s.n_short = n_short; s.potential = potential; s.rho_bins = rho_bins; s.use_phi = use_phi;
     s.rmax = kind == TDVMC_SYSTEM_HE_BULK ? L / 2.0 : ((kind != TDVMC_SYSTEM_SPLINE_TABLE && kind != TDVMC_SYSTEM_BOX_RADIAL) ? 1e300 : knots[K]); // HeBulk.cpp:54
     s.n_types = n_types;

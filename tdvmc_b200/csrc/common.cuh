@@ -93,6 +93,10 @@ struct SysDev
     // sweep 1.2 % (13.63 -> 13.80 ms per launch, measured on the same GPU)
     double dm1;                // DIM - 1: secondDerivativeFactor of BosonsBulk.cpp:319, NUBosonsBulkPB.cpp:392
     int dim;
+    // uniform knots (BosonsBulk.cpp:61-67): a distance whose r / h lies further than bin_guard from an integer is in
+    // interval first_bin + floor(r / h) whatever the rounding of the stored knots (bin_guard = twice their largest
+    // deviation from the exact grid, in units of h, + 1e-10); 0: not available, the knots are always consulted
+    double bin_guard;
 };
 
 // ---- minimum image -------------------------------------------------------------------------
@@ -128,6 +132,19 @@ __device__ __forceinline__ int find_bin_exact(const SysDev& s, const double* kno
     while (b < s.K - 1 && r > knots[b + 1]) b++;
     while (b > s.first_bin && !(knots[b] < r)) b--;
     return b;
+}
+
+// Uniform knots: the interval from r / h alone when r is not within bin_guard (in units of h) of a knot - no table
+// look-up, no knot loads; the rare distance next to a knot takes the exact search.  Same result as find_bin_exact.
+__device__ __forceinline__ int find_bin_uniform(const SysDev& s, const double* knots, const unsigned short* lut, double r)
+{
+    const double magic = 6755399441055744.0; // 1.5 * 2^52: x + magic carries round-to-nearest(x) in its low word
+    const double x = r * s.inv_h;
+    const double y = x + magic;
+    const int j = __double2loint(y);
+    const double d = x - (y - magic);        // x - nearest integer, exact
+    if (fabs(d) > s.bin_guard) return s.first_bin + j - (d < 0.0 ? 1 : 0);
+    return find_bin_exact(s, knots, lut, r);
 }
 
 // ---- warp / block reductions ------------------------------------------------------------------

@@ -220,9 +220,22 @@ __device__ __forceinline__ void eval_finish(const EvalArgs& a, const SysDev& s, 
     }
 }
 
-template <bool REFLECT, bool WIDE, bool ROT, bool GMEM = false>
+#ifdef TDVMC_EVAL_KO
+// measurement builds only (profiles/ab_evaluate_variants.py knockout): parts of a step switched off to read their cost
+__device__ int g_eval_ko;
+#define KO(bit) (ko & (bit))
+#else
+#define KO(bit) false
+#endif
+
+// UNI: interval index of a uniform knot vector without the look-up table and the two knot loads (find_bin_uniform):
+// 4.99 -> 4.73 ms per 4096 configurations at N = 343, bit-identical results.
+template <bool REFLECT, bool WIDE, bool ROT, bool GMEM = false, bool UNI = false>
 __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kernel(EvalArgs a)
 {
+#ifdef TDVMC_EVAL_KO
+    const int ko = g_eval_ko;
+#endif
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const SysDev& s = a.s;
     const int tid = threadIdx.x;
@@ -330,7 +343,7 @@ __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kerne
                 const double xn = m.px[n], yn = m.py[n], zn = m.pz[n];
                 for (int k = kfirst; k <= klast; k++)
                 {
-                    if (k > kfirst)
+                    if (k > kfirst && !KO(16))
                     {
                         const int src = (lane + 1) & 31;
                         cRx = __shfl_sync(FULL_MASK, cRx, src);
@@ -362,8 +375,8 @@ __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kerne
                     double val[4] = { 0.0, 0.0, 0.0, 0.0 };
                     if (act)
                     {
-                        bin = find_bin_exact(s, m.knots, m.lut, r);
-                        const double* w = wmine + (size_t)bin * wstride;
+                        bin = UNI ? find_bin_uniform(s, m.knots, m.lut, r) : find_bin_exact(s, m.knots, m.lut, r);
+                        const double* w = wmine + (size_t)(KO(4) ? s.first_bin : bin) * wstride;
                         const double r2 = r * r;
                         const double rinv = rcp_refined(r);
                         const double f2 = s.dm1 * rinv; // (DIM - 1) / r, BosonsBulk.cpp:319-322
@@ -377,7 +390,7 @@ __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kerne
                             const double2 w23 = *reinterpret_cast<const double2*>(w + p * 4 + 2);
                             const double d1 = w01.y + 2.0 * w23.x * r + 3.0 * w23.y * r2; // BosonsBulk.cpp:299
                             const double d2 = 2.0 * w23.x + 6.0 * w23.y * r;              // BosonsBulk.cpp:301
-                            const double2 uk = umine[(bin - p) * ucop];
+                            const double2 uk = KO(2) ? make_double2(0.5 + p, 0.25) : umine[(bin - p) * ucop];
                             const double uRk = uk.x, uIk = uk.y;
                             const double t2 = d2 + f2 * d1;
                             gR = fma(uRk, d1, gR);
@@ -417,7 +430,7 @@ __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kerne
                         cIy = fma(-gI, ey, cIy);
                         cIz = fma(-gI, ez, cIz);
                     }
-                    warp_hist_add4(hist, bin, act, val, lane);
+                    if (!KO(1)) warp_hist_add4(hist, bin, act, val, lane);
                 }
             }
             // flush: columns first, rows second; in the shared shift the two warps of a tile take turns
@@ -462,6 +475,15 @@ __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kerne
 // half the lanes idle, the records collide less, and the extra selects cost more than the replays saved (3.80 against
 // 3.64 ms per 2960 configurations at N = 343).
 constexpr size_t kEvalSmemLimit = (size_t)227 * 1024; // opt-in shared memory per block on sm_100a
+
+static int env_int(const char* name, int dflt)
+{
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+// tuning knob (profiles/ab_evaluate_variants.py, tests): TDVMC_EVAL_UNIBIN = 0 takes the exact search everywhere
+constexpr int kEvalUniBinDefault = 1;
 
 static bool evaluate_rotated(const SysDev& s) { return s.pair_rule == 1; }
 
@@ -517,8 +539,7 @@ int evaluate_threads(const SysDev& s)
 // when the block still fits - twice per SM for the 12-warp blocks - else one
 static int evaluate_ucopies(const SysDev& s)
 {
-    int want = 8;
-    if (const char* e = getenv("TDVMC_EVAL_UCOPIES")) want = atoi(e) >= 8 ? 8 : 1; // tuning knob
+    const int want = env_int("TDVMC_EVAL_UCOPIES", 8) >= 8 ? 8 : 1; // tuning knob
     if (want == 1) return 1;
     const size_t bytes = eval_smem_layout2(s, evaluate_threads(s) / 32, evaluate_rotated(s), evaluate_gmem(s), nullptr, nullptr, 8) + 1024;
     return evaluate_blocks_per_sm(s) * bytes <= kEvalSmemLimit ? 8 : 1;
@@ -553,6 +574,15 @@ cudaError_t launch_evaluate(const EvalArgs& a_in, cudaStream_t st)
     const int threads = evaluate_threads(a.s);
     const size_t smem = evaluate_smem_bytes(a.s);
     const bool refl = a.s.pair_rule == 1;
+    // uniform knots (cut rule: BosonsBulk): the interval index needs no table
+    const bool uni = !refl && a.s.uniform && a.s.bin_guard > 0.0 && env_int("TDVMC_EVAL_UNIBIN", kEvalUniBinDefault) != 0;
+#ifdef TDVMC_EVAL_KO
+    {
+        const int ko = env_int("TDVMC_EVAL_KO", 0);
+        cudaMemcpyToSymbolAsync(g_eval_ko, &ko, sizeof(int), 0, cudaMemcpyHostToDevice, st);
+        cudaStreamSynchronize(st);
+    }
+#endif
     if (evaluate_gmem(a.s))
     {
         if (!a.scratch) return cudaErrorInvalidValue;
@@ -560,14 +590,19 @@ cudaError_t launch_evaluate(const EvalArgs& a_in, cudaStream_t st)
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const int grid = a.n_cfg < sms ? a.n_cfg : sms; // one block per SM walks the configurations
-        return refl ? launch_eval_kernel(evaluate_kernel<true, true, true, true>, a, threads, smem, grid, st)
-                    : launch_eval_kernel(evaluate_kernel<false, true, false, true>, a, threads, smem, grid, st);
+        if (refl) return launch_eval_kernel(evaluate_kernel<true, true, true, true>, a, threads, smem, grid, st);
+        return uni ? launch_eval_kernel(evaluate_kernel<false, true, false, true, true>, a, threads, smem, grid, st)
+                   : launch_eval_kernel(evaluate_kernel<false, true, false, true>, a, threads, smem, grid, st);
     }
     if (evaluate_wide(a.s))
-        return refl ? launch_eval_kernel(evaluate_kernel<true, true, true>, a, threads, smem, a.n_cfg, st)
-                    : launch_eval_kernel(evaluate_kernel<false, true, false>, a, threads, smem, a.n_cfg, st);
-    return refl ? launch_eval_kernel(evaluate_kernel<true, false, true>, a, threads, smem, a.n_cfg, st)
-                : launch_eval_kernel(evaluate_kernel<false, false, false>, a, threads, smem, a.n_cfg, st);
+    {
+        if (refl) return launch_eval_kernel(evaluate_kernel<true, true, true>, a, threads, smem, a.n_cfg, st);
+        return uni ? launch_eval_kernel(evaluate_kernel<false, true, false, false, true>, a, threads, smem, a.n_cfg, st)
+                   : launch_eval_kernel(evaluate_kernel<false, true, false>, a, threads, smem, a.n_cfg, st);
+    }
+    if (refl) return launch_eval_kernel(evaluate_kernel<true, false, true>, a, threads, smem, a.n_cfg, st);
+    return uni ? launch_eval_kernel(evaluate_kernel<false, false, false, false, true>, a, threads, smem, a.n_cfg, st)
+               : launch_eval_kernel(evaluate_kernel<false, false, false>, a, threads, smem, a.n_cfg, st);
 }
 
 } // namespace tdvmc

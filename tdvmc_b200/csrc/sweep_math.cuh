@@ -34,16 +34,26 @@ __device__ __forceinline__ double dist2(double dx, double dy, double dz, double 
     return mi2_wrapped(dx, dy, dz, Lhalf);
 }
 
-// sqrt(x) to ~2 ulp: MUFU.RSQ64H seed (22 bits) + one third-order step; x == 0 gives NaN, which the
-// callers discard (it only happens for the moved particle against itself)
+// sqrt(x) for the sampler: MUFU.RSQ64H seed y (22 bits) and ONE Newton step  t + (x - t^2) y/2,  t = x y.  Three FP64
+// instructions; y/2 is an exponent decrement on the integer pipe (the seed has an empty low word and is never subnormal for
+// a pair distance).  Relative error -1.5 delta^2 <= 9e-14 for a seed error delta <= 2^-22 - a smooth, deterministic
+// function of x, i.e. the chain samples |psi|^2 of distances stretched by < 1e-13, far below the 1e-7 the move ratio is
+// held to against the reference; E_L, O_k and the drift are evaluated with the exact distance.  x == 0 gives NaN, which
+// the callers discard (it only happens for the moved particle against itself).
+// (TDVMC_SQRT_3RD_ORDER: the third-order step of round 1, ~2 ulp, five FP64 instructions.)
 __device__ __forceinline__ double sqrt_fast(double x)
 {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     const double t = x * y;               // ~ sqrt(x)
+#ifdef TDVMC_SQRT_3RD_ORDER
     const double e = fma(-t, y, 1.0);     // 1 - x y^2
     const double p = fma(e, 0.375, 0.5);
     return fma(t * e, p, t);              // t (1 + e/2 + 3 e^2/8)
+#else
+    const double hy = __hiloint2double(__double2hiint(y) - 0x00100000, __double2loint(y));
+    return fma(fma(-t, t, x), hy, t);
+#endif
 }
 
 } // namespace tdvmc

@@ -1749,3 +1749,46 @@ def test_large_systems_beyond_one_sm_of_shared_memory(capi, N, L):
     assert got["n_samples"] == 4 and np.isfinite(got["e_r"][0]) and got["n_trials"] == 2 * 64
     h.close()
     h2.close()
+
+
+def _evaluate_with_env(h, R, env):
+    """evaluate_fixed under tuning knobs (the evaluation kernel reads them at every launch)."""
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return h.evaluate_fixed(R)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("name", ["bosonsbulk_n64_equil", "bosonsbulk_n343_equil"])
+def test_uniform_knot_interval_index_is_the_exact_search(capi, golden, name):
+    """Uniform knots (BosonsBulk.cpp:61-67): the evaluation kernel takes the knot interval from r / h alone and consults the
+    knots only for a distance within ~1e-10 h of one (find_bin_uniform).  Bit-identical outputs to the exact search
+    (std::lower_bound, BosonsBulk.cpp:197-198, the kernel pinned to the reference above) on equilibrated configurations and
+    on configurations with a pair placed ON knots, a few ulp and 1e-12 ... 1e-8 h beside them, and at the cut itself."""
+    g = golden(name)
+    spec, h = make_handle(capi, g, 2)
+    N = spec.n_particles
+    knots = np.asarray(g["knots"])
+    hsp = knots[4] - knots[3]
+    rng = np.random.default_rng(11)
+    cfgs = [g["R"], g["R"] + rng.uniform(-0.02, 0.02, (N, 3))]
+    K = len(knots) - 4
+    for k in sorted({1, 2, min(17, K - 3), max(1, K - 40), K - 4, K - 3}):   # knots[3 + j] = j h; K - 3 is r_max
+        for delta in (0.0, 2.3e-16, -2.3e-16, 1e-12, -1e-12, 3e-11, -3e-11, 1e-8, -1e-8):
+            R = g["R"].copy()
+            d = knots[3 + k] * (1.0 + delta) if delta != 0.0 and abs(delta) < 1e-15 else knots[3 + k] + delta * hsp
+            R[1] = R[0] + np.array([d, 0.0, 0.0])        # (the minimum image folds it back where d > L/2 - never here)
+            cfgs.append(R)
+    R = np.stack(cfgs)
+    exact = _evaluate_with_env(h, R, {"TDVMC_EVAL_UNIBIN": "0"})
+    fast = _evaluate_with_env(h, R, {"TDVMC_EVAL_UNIBIN": "1"})
+    for key in exact:
+        assert np.array_equal(exact[key], fast[key]), key
+    assert rel(fast["O"][0], g["local_operators"]) < RTOL
+    h.close()
