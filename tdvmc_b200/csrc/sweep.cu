@@ -17,7 +17,10 @@
 // so the table is split into 16-byte planes (a random record index then spreads over all eight
 // 16-byte slots of a bank row), uniform knots need no t_lo load, positions are kept wrapped into
 // the first cell so the minimum image is min(|d|, L - |d|) (3 FP64 ops per coordinate instead of 4),
-// and the square root drops the final correctly-rounding step (2 ulp are irrelevant for sampling).
+// and the square root is the hardware seed plus ONE Newton step (sweep_math.cuh: three FP64 instructions, relative error
+// <= 9e-14 - irrelevant for sampling, and a deterministic function of the distance; 22 FP64 instructions per pair in all.
+// Round 1's third-order step, five instructions and ~2 ulp, gave 781 against 841 M walker-steps/s at 4096 walkers, with
+// bit-identical chains over 82 M proposals, profiles/ab_sweep_sqrt.py).
 // Not kept: 64-bit fixed-point coordinates (the two's-complement difference IS the minimum image, which
 // moves 9 of 26 FP64 instructions per pair to the integer pipe and three I2F.F64.S64).  Measured equal
 // (14.01 vs 14.07 ms per launch): the conversions issue at 14 lanes/clk/SM (profiles/microbench/
@@ -88,6 +91,7 @@ __device__ __forceinline__ double pair_u(const SysDev& s, const double2* __restr
     {
         j = max(0, min(c, s.nbins));          // record nbins: constant tail
         t = fma(-(y - kMagic), s.h, r);       // r - floor(r/h) h (multiplies zero coefficients when j was clamped)
+        // (the index converted back on the conversion unit, (double)j, instead of this FP64 add: 838 against 841 M walker-steps/s)
     }
     else
     {

@@ -1792,3 +1792,57 @@ def test_uniform_knot_interval_index_is_the_exact_search(capi, golden, name):
         assert np.array_equal(exact[key], fast[key]), key
     assert rel(fast["O"][0], g["local_operators"]) < RTOL
     h.close()
+
+
+@pytest.mark.parametrize("name", ["bosonsbulk_n64_equil", "bosonsbulk_n343_equil"])
+def test_sampler_exponent_change_against_exact_arithmetic(capi, golden, parity_log, name):
+    """What the Metropolis sweep evaluates per proposal - minimum image of wrapped points, the one-Newton-step square root
+    (sweep_math.cuh), the per-interval cubic in the local coordinate - against the polynomial the caller's spline table
+    DEFINES, u(r) = sum_p u~[bin - p] (w0 + w1 r + w2 r^2 + w3 r^3)_{bin - p, p}, evaluated in 60-digit decimal arithmetic
+    with an exact square root.  The reference's own double evaluation of the same expression carries ~1e-10 per pair term
+    (the 1e-7 of test_scripted_move_quotient); the device stays within 1e-11 of the exact value."""
+    from decimal import Decimal, getcontext
+    getcontext().prec = 60
+    g = golden(name)
+    spec, h = make_handle(capi, g)
+    N, L = spec.n_particles, float(g["LBOX"])
+    knots = np.asarray(g["knots"], np.float64)
+    w = np.asarray(g["spline_weights"], np.float64)
+    K = w.shape[0]
+    ut = spec.spline_space(np.asarray(g["uR"], np.float64))
+    u_tail = float(g["uR"][spec.tail_param]) if spec.tail_param >= 0 else 0.0
+    rmax = knots[K]
+    Ld = Decimal(L)
+
+    def u_exact(a, b):
+        s = Decimal(0)
+        for c in range(3):
+            d = Decimal(float(a[c])) - Decimal(float(b[c]))
+            d -= Ld * (d / Ld).to_integral_value()          # nearest image
+            s += d * d
+        r = s.sqrt()
+        rf = float(r)
+        if rf > rmax:
+            return Decimal(u_tail)
+        b_ = int(np.searchsorted(knots, rf, side="left")) - 1   # knots[b] < r <= knots[b + 1]
+        tot = Decimal(0)
+        for p in range(4):
+            cf = w[b_ - p, p]
+            val = Decimal(float(cf[0])) + r * (Decimal(float(cf[1])) + r * (Decimal(float(cf[2])) + r * Decimal(float(cf[3]))))
+            tot += Decimal(float(ut[b_ - p])) * val
+        return tot
+
+    R = np.asarray(g["R"], np.float64)
+    moves = np.asarray(g["moves"], np.float64)
+    rng = np.random.default_rng(5)
+    extra = np.array([[p, *(R[p] + rng.normal(0.0, 0.5, 3))] for p in rng.integers(0, N, 6)])
+    moves = np.concatenate([moves, extra])
+    _, d = h.quotient_fixed(R, moves)
+    worst = 0.0
+    for m, dm in zip(moves, d):
+        p = int(m[0])
+        exact = sum((u_exact(R[i], m[1:]) - u_exact(R[i], R[p]) for i in range(N) if i != p), Decimal(0))
+        worst = max(worst, abs(float(Decimal(float(dm)) - exact)))
+    parity_log.check("test_sampler_exponent_change_against_exact_arithmetic", name, "delta_exponent", worst, 1.0, 1e-11,
+                     "absolute, against 60-digit arithmetic on the table's polynomial")
+    h.close()
