@@ -83,4 +83,6 @@ for name, kv in VARIANTS:
     out[name] = rec
     print(name, json.dumps(rec), file=sys.stderr, flush=True)
 h.close()
+if len(sys.argv) > 2:  # outputs of the first variant, for comparisons between library builds
+    np.savez(os.path.join(ROOT, "gpurun_out", "ab_eval_outputs_%s.npz" % sys.argv[2]), **base)
 print(json.dumps(out))
