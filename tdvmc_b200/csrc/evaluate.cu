@@ -574,8 +574,8 @@ cudaError_t launch_evaluate(const EvalArgs& a_in, cudaStream_t st)
     const int threads = evaluate_threads(a.s);
     const size_t smem = evaluate_smem_bytes(a.s);
     const bool refl = a.s.pair_rule == 1;
-    // uniform knots (cut rule: BosonsBulk): the interval index needs no table
-    const bool uni = !refl && a.s.uniform && a.s.bin_guard > 0.0 && env_int("TDVMC_EVAL_UNIBIN", kEvalUniBinDefault) != 0;
+    // uniform knots (BosonsBulk's own grid; config/NUBosonsBulkPB3D.config's NURBS_GRID is one too): the interval index needs no table
+    const bool uni = a.s.uniform && a.s.bin_guard > 0.0 && env_int("TDVMC_EVAL_UNIBIN", kEvalUniBinDefault) != 0;
 #ifdef TDVMC_EVAL_KO
     {
         const int ko = env_int("TDVMC_EVAL_KO", 0);
@@ -590,17 +590,23 @@ cudaError_t launch_evaluate(const EvalArgs& a_in, cudaStream_t st)
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const int grid = a.n_cfg < sms ? a.n_cfg : sms; // one block per SM walks the configurations
-        if (refl) return launch_eval_kernel(evaluate_kernel<true, true, true, true>, a, threads, smem, grid, st);
+        if (refl)
+            return uni ? launch_eval_kernel(evaluate_kernel<true, true, true, true, true>, a, threads, smem, grid, st)
+                       : launch_eval_kernel(evaluate_kernel<true, true, true, true>, a, threads, smem, grid, st);
         return uni ? launch_eval_kernel(evaluate_kernel<false, true, false, true, true>, a, threads, smem, grid, st)
                    : launch_eval_kernel(evaluate_kernel<false, true, false, true>, a, threads, smem, grid, st);
     }
     if (evaluate_wide(a.s))
     {
-        if (refl) return launch_eval_kernel(evaluate_kernel<true, true, true>, a, threads, smem, a.n_cfg, st);
+        if (refl)
+            return uni ? launch_eval_kernel(evaluate_kernel<true, true, true, false, true>, a, threads, smem, a.n_cfg, st)
+                       : launch_eval_kernel(evaluate_kernel<true, true, true>, a, threads, smem, a.n_cfg, st);
         return uni ? launch_eval_kernel(evaluate_kernel<false, true, false, false, true>, a, threads, smem, a.n_cfg, st)
                    : launch_eval_kernel(evaluate_kernel<false, true, false>, a, threads, smem, a.n_cfg, st);
     }
-    if (refl) return launch_eval_kernel(evaluate_kernel<true, false, true>, a, threads, smem, a.n_cfg, st);
+    if (refl)
+        return uni ? launch_eval_kernel(evaluate_kernel<true, false, true, false, true>, a, threads, smem, a.n_cfg, st)
+                   : launch_eval_kernel(evaluate_kernel<true, false, true>, a, threads, smem, a.n_cfg, st);
     return uni ? launch_eval_kernel(evaluate_kernel<false, false, false, false, true>, a, threads, smem, a.n_cfg, st)
                : launch_eval_kernel(evaluate_kernel<false, false, false>, a, threads, smem, a.n_cfg, st);
 }

@@ -1765,12 +1765,13 @@ def _evaluate_with_env(h, R, env):
                 os.environ[k] = v
 
 
-@pytest.mark.parametrize("name", ["bosonsbulk_n64_equil", "bosonsbulk_n343_equil"])
+@pytest.mark.parametrize("name", ["bosonsbulk_n64_equil", "bosonsbulk_n343_equil", "nubosonsbulkpb_n1728_equil"])
 def test_uniform_knot_interval_index_is_the_exact_search(capi, golden, name):
     """Uniform knots (BosonsBulk.cpp:61-67): the evaluation kernel takes the knot interval from r / h alone and consults the
     knots only for a distance within ~1e-10 h of one (find_bin_uniform).  Bit-identical outputs to the exact search
     (std::lower_bound, BosonsBulk.cpp:197-198, the kernel pinned to the reference above) on equilibrated configurations and
-    on configurations with a pair placed ON knots, a few ulp and 1e-12 ... 1e-8 h beside them, and at the cut itself."""
+    on configurations with a pair placed ON knots, a few ulp and 1e-12 ... 1e-8 h beside them, and at the cut itself
+    (third case: the reflection rule on the uniform NURBS_GRID of config/NUBosonsBulkPB3D.config, N = 1728)."""
     g = golden(name)
     spec, h = make_handle(capi, g, 2)
     N = spec.n_particles
