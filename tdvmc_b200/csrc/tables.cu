@@ -47,6 +47,31 @@ __host__ __device__ inline size_t tab_smem_layout(const SysDev& s, int nwarps, T
     return off;
 }
 
+// The reference's four IEEE divisions by r_ni (BosonsBulk.cpp:304-307, 319) from ONE reciprocal, correctly rounded all the
+// same (Markstein): y = RN(1 / r) - hardware seed, two Newton steps, one residual correction -, then for every numerator
+// q0 = x y, q = q0 + (x - r q0) y with the residual exact in an FMA.  (A plain reciprocal-multiply is one ulp off now and then,
+// which the perfect-lattice fixture - table entries cancelling to 1e-6 of their terms - shows at the 1e-13 table parity.)
+struct Recip
+{
+    double r, y;
+    __device__ __forceinline__ explicit Recip(double r_) : r(r_)
+    {
+        double y0;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(r_));
+        double e = fma(-r_, y0, 1.0);
+        y0 = fma(y0, e, y0);
+        e = fma(-r_, y0, 1.0);
+        y0 = fma(y0, e, y0);
+        e = fma(-r_, y0, 1.0);
+        y = fma(y0, e, y0);
+    }
+    __device__ __forceinline__ double divide(double x) const
+    {
+        const double q0 = x * y;
+        return fma(fma(-r, q0, x), y, q0);
+    }
+};
+
 template <bool REFLECT>
 __global__ void __launch_bounds__(kTabWarpsMax * 32) tables_kernel(TableArgs a, int particles_per_block)
 {
@@ -104,14 +129,21 @@ __global__ void __launch_bounds__(kTabWarpsMax * 32) tables_kernel(TableArgs a, 
             double q[4][4];
             if (act)
             {
-                bin = find_bin_exact(s, m.knots, m.lut, r);
+                // uniform knots: no look-up (find_bin_uniform, same interval); the branch is uniform over the grid
+                bin = s.bin_guard > 0.0 ? find_bin_uniform(s, m.knots, m.lut, r) : find_bin_exact(s, m.knots, m.lut, r);
                 const double* w = m.rec + (size_t)(bin - s.first_bin) * kRecStride;
                 const double r2 = r * r;
                 // IEEE divisions as in the reference (BosonsBulk.cpp:304-307, 319): on the perfect-lattice fixture the table
                 // entries cancel to ~1e-6 of their terms, and a reciprocal-multiply (one ulp off per term; 3.30 instead of
                 // 3.66 ms per 1024 configurations) fails the 1e-13 table parity there
+#ifdef TDVMC_TABLES_IEEE_DIV
                 const double ex = vx / r, ey = vy / r, ez = vz / r;
                 const double f2 = s.dm1 / r;                        // secondDerivativeFactor / rni
+#else
+                const Recip rc(r);
+                const double ex = rc.divide(vx), ey = rc.divide(vy), ez = rc.divide(vz);
+                const double f2 = rc.divide(s.dm1);                 // secondDerivativeFactor / rni
+#endif
 #pragma unroll
                 for (int p = 0; p < 4; p++)
                 {
