@@ -44,7 +44,7 @@ SURVEY_WALKERS_PER_GPU = 4096   # W = 4096 x G walkers
 # dram__bytes_read.sum + dram__bytes_write.sum of one sweep launch (4096 walkers, 5000 steps): read from the committed ncu
 # --set full summary of THIS build's kernel (profiles/run_r02.sh); algorithmic traffic is 2 x 8.2 KB per walker per launch =
 # 67 MB; the time-shared kernel moves a walker through L2 once per chunk (10 chunks), which stays in the 126 MB L2
-SWEEP_NCU_SUMMARY = os.path.join("profiles", "r02_sweep_queue_ncu.txt")
+SWEEP_NCU_SUMMARY = os.path.join("profiles", "r02f_sweep_queue_ncu.txt")
 
 
 def sweep_traffic_from_ncu():
@@ -59,7 +59,7 @@ def sweep_traffic_from_ncu():
                 tot += float(t[1].replace(",", "")) * unit.get(t[2], 1.0)
                 seen += 1
         if seen == 2:
-            return tot, SWEEP_NCU_SUMMARY + " (ncu --set full, sweep_queue_kernel<1,0>, 4096 walkers x 5000 steps per launch, r02 build)"
+            return tot, SWEEP_NCU_SUMMARY + " (ncu --set full, sweep_queue_kernel<1,0>, 4096 walkers x 5000 steps per launch, final r02 build)"
     except OSError:
         pass
     return None, "no ncu summary found"
