@@ -184,6 +184,26 @@ __device__ __forceinline__ void warp_hist_add4(double* hist, int bin, bool activ
     }
 }
 
+// The same with ballot and match.any issued by the caller as soon as the interval is known, so that the long latency of
+// MATCH.ANY passes behind the spline arithmetic instead of in front of the first read-modify-write.
+__device__ __forceinline__ void warp_hist_add4_ranked(double* hist, int bin, bool active, const double (&v)[4], int lane,
+                                                      unsigned amask, unsigned peers)
+{
+    if (amask == 0u) return;
+    const int rank = __popc(peers & ((1u << lane) - 1u));
+    for (int round = 0;; round++)
+    {
+        const bool mine = active && (rank == round);
+        if (__ballot_sync(FULL_MASK, mine) == 0u) break;
+#pragma unroll
+        for (int p = 0; p < 4; p++)
+        {
+            if (mine) hist[bin - p] += v[p];
+            __syncwarp();
+        }
+    }
+}
+
 // ---- Philox4x32-10 proposal stream (same definition as oracle_proposal in oracle/tdvmc_oracle.c) ----
 struct Philox4
 {

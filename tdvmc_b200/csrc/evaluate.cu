@@ -373,9 +373,15 @@ __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kerne
 
                     int bin = 0;
                     double val[4] = { 0.0, 0.0, 0.0, 0.0 };
+                    // the interval first, and the match.any that ranks the lanes sharing one (warp_hist_add4_ranked) right away:
+                    // its latency - 10 % of the kernel's stall samples when it sat in front of the histogram update -
+                    // passes behind the spline arithmetic (4.73 -> 4.65 ms per 4096 configurations, bit-identical)
+                    if (act) bin = UNI ? find_bin_uniform(s, m.knots, m.lut, r) : find_bin_exact(s, m.knots, m.lut, r);
+                    const unsigned amask = __ballot_sync(FULL_MASK, act);
+                    unsigned peers = 0u;
+                    if (amask != 0u) peers = __match_any_sync(FULL_MASK, act ? bin : (-1 - lane)); // (amask is warp-uniform)
                     if (act)
                     {
-                        bin = UNI ? find_bin_uniform(s, m.knots, m.lut, r) : find_bin_exact(s, m.knots, m.lut, r);
                         const double* w = wmine + (size_t)(KO(4) ? s.first_bin : bin) * wstride;
                         const double r2 = r * r;
                         const double rinv = rcp_refined(r);
@@ -430,7 +436,7 @@ __global__ void __launch_bounds__(WIDE ? 768 : 384, WIDE ? 1 : 2) evaluate_kerne
                         cIy = fma(-gI, ey, cIy);
                         cIz = fma(-gI, ez, cIz);
                     }
-                    if (!KO(1)) warp_hist_add4(hist, bin, act, val, lane);
+                    if (!KO(1)) warp_hist_add4_ranked(hist, bin, act, val, lane, amask, peers);
                 }
             }
             // flush: columns first, rows second; in the shared shift the two warps of a tile take turns
