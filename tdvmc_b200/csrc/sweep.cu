@@ -18,7 +18,7 @@
 // 16-byte slots of a bank row), uniform knots need no t_lo load, positions are kept wrapped into
 // the first cell so the minimum image is min(|d|, L - |d|) (3 FP64 ops per coordinate instead of 4),
 // and the square root is the hardware seed plus ONE Newton step (sweep_math.cuh: three FP64 instructions, relative error
-// <= 9e-14 - irrelevant for sampling, and a deterministic function of the distance; 22 FP64 instructions per pair in all.
+// <= 1.4e-12 - irrelevant for sampling, and a deterministic function of the distance; 22 FP64 instructions per pair in all.
 // Round 1's third-order step, five instructions and ~2 ulp, gave 781 against 841 M walker-steps/s at 4096 walkers, with
 // bit-identical chains over 82 M proposals, profiles/ab_sweep_sqrt.py).
 // Not kept: 64-bit fixed-point coordinates (the two's-complement difference IS the minimum image, which

@@ -34,12 +34,14 @@ __device__ __forceinline__ double dist2(double dx, double dy, double dz, double 
     return mi2_wrapped(dx, dy, dz, Lhalf);
 }
 
-// sqrt(x) for the sampler: MUFU.RSQ64H seed y (22 bits) and ONE Newton step  t + (x - t^2) y/2,  t = x y.  Three FP64
-// instructions; y/2 is an exponent decrement on the integer pipe (the seed has an empty low word and is never subnormal for
-// a pair distance).  Relative error -1.5 delta^2 <= 9e-14 for a seed error delta <= 2^-22 - a smooth, deterministic
-// function of x, i.e. the chain samples |psi|^2 of distances stretched by < 1e-13, far below the 1e-7 the move ratio is
-// held to against the reference; E_L, O_k and the drift are evaluated with the exact distance.  x == 0 gives NaN, which
-// the callers discard (it only happens for the moved particle against itself).
+// sqrt(x) for the sampler: MUFU.RSQ64H seed y and ONE Newton step  t + (x - t^2) y/2,  t = x y.  Three FP64 instructions;
+// y/2 is an exponent decrement on the integer pipe (the seed has an empty low word and is never subnormal for a pair
+// distance).  Relative error -1.5 delta^2 with delta the seed's error: the seed carries the 20 mantissa bits of its high
+// word, delta <= 2^-20, so <= 1.4e-12 (tests/test_device_arithmetic_mirrors.py); on the device the exponent change of a proposal
+// comes out within 3e-13 of exact arithmetic (test_sampler_exponent_change_against_exact_arithmetic).  The error is a
+// smooth, deterministic function of x - the chain samples |psi|^2 of distances stretched by ~1e-12, far below the 1e-7 the
+// move ratio is held to against the reference - and E_L, O_k and the drift are evaluated with the exact distance.
+// x == 0 gives NaN, which the callers discard (it only happens for the moved particle against itself).
 // (TDVMC_SQRT_3RD_ORDER: the third-order step of round 1, ~2 ulp, five FP64 instructions.)
 __device__ __forceinline__ double sqrt_fast(double x)
 {

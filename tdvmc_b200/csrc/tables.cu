@@ -51,6 +51,9 @@ __host__ __device__ inline size_t tab_smem_layout(const SysDev& s, int nwarps, T
 // same (Markstein): y = RN(1 / r) - hardware seed, two Newton steps, one residual correction -, then for every numerator
 // q0 = x y, q = q0 + (x - r q0) y with the residual exact in an FMA.  (A plain reciprocal-multiply is one ulp off now and then,
 // which the perfect-lattice fixture - table entries cancelling to 1e-6 of their terms - shows at the 1e-13 table parity.)
+// Exception: a divisor whose significand is all ones (one double in 2^52) - the Newton step cannot reach RN(1 / r) there and
+// the quotient may be one ulp off.  tests/test_device_arithmetic_mirrors.py emulates this sequence in exact arithmetic and
+// pins both statements; -DTDVMC_TABLES_IEEE_DIV keeps the four divisions.
 struct Recip
 {
     double r, y;
