@@ -59,12 +59,7 @@ def bin_uniform(knots, first_bin, inv_h, guard, r):
     return bin_exact(knots, first_bin, r), False
 
 
-@pytest.mark.parametrize("n_param,half_length", [(201, 3.5), (50, 2.0), (201, 10.0), (100, 0.731)])
-def test_uniform_interval_index_mirror(n_param, half_length):
-    """The guard band of tdvmc_gpu_create (twice the largest deviation of a stored knot from the exact grid, in units of
-    the spacing, + 1e-10) makes the knot-free index exact: random distances, distances ON knots, one ulp and 1e-12 ... 1e-9 h
-    beside them.  The fast path must also be what nearly every distance takes."""
-    knots = np.asarray(splines.uniform_knots(n_param, half_length), np.float64)   # (i * L / 2) / (P - 1), BosonsBulk.cpp:61-67
+def check_uniform_index(knots, seed):
     K = len(knots) - 4
     fb = 3
     assert knots[fb] == 0.0
@@ -74,7 +69,7 @@ def test_uniform_interval_index_mirror(n_param, half_length):
     assert dev < 1e-7
     guard = 2.0 * dev + 1e-10
     inv_h = 1.0 / h0
-    rng = np.random.default_rng(n_param)
+    rng = np.random.default_rng(seed)
     rs = list(rng.uniform(1e-6, knots[K], 20000))
     for j in range(fb + 1, K + 1):
         t = float(knots[j])
@@ -89,6 +84,22 @@ def test_uniform_interval_index_mirror(n_param, half_length):
         fast += was_fast
         assert got == bin_exact(knots, fb, r), (r, got)
     assert fast > 19990
+
+
+@pytest.mark.parametrize("n_param,half_length", [(201, 3.5), (50, 2.0), (201, 10.0), (100, 0.731)])
+def test_uniform_interval_index_mirror(n_param, half_length):
+    """The guard band of tdvmc_gpu_create (twice the largest deviation of a stored knot from the exact grid, in units of
+    the spacing, + 1e-10) makes the knot-free index exact: random distances, distances ON knots, one ulp and 1e-12 ... 1e-9 h
+    beside them.  The fast path must also be what nearly every distance takes."""
+    knots = np.asarray(splines.uniform_knots(n_param, half_length), np.float64)   # (i * L / 2) / (P - 1), BosonsBulk.cpp:61-67
+    check_uniform_index(knots, n_param)
+
+
+@pytest.mark.parametrize("name", ["bosonsbulk_n343_equil", "nubosonsbulkpb_n1728_equil"])
+def test_uniform_interval_index_mirror_on_reference_knots(golden, name):
+    """The same on knot vectors the reference itself produced: BosonsBulk's own grid at the headline size and the NURBS_GRID
+    of config/NUBosonsBulkPB3D.config (decimal literals 0.03 i: uniform to a few ulp, which the guard band absorbs)."""
+    check_uniform_index(np.asarray(golden(name)["knots"], np.float64), 7)
 
 
 # ---- sqrt_fast -------------------------------------------------------------------------------------------------------
